@@ -1,0 +1,750 @@
+// C ABI (include/caz_b200.h) and host-side orchestration of the sm_100a evaluator.
+// Host work done here: BatchNorm folding (fp32), weight re-layout for the kernels, TMA tensor-map
+// construction, buffer ownership, the per-layer launch sequence of the forward pass.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/caz_b200.h"
+#include "conv_tc.cuh"
+#include "kernels_simt.cuh"
+
+namespace {
+
+std::mutex g_err_mutex;
+std::string g_create_error;
+
+std::string fmt(const char* f, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof buf, f, ap);
+  va_end(ap);
+  return buf;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct ConvLayer {
+  int k = 0, cin = 0, cin_pad = 0, cout = 0;
+  void* w = nullptr;      // bf16 [cout][k*k*cin_pad] (tensor path) or fp32 [k*k][cin][cout] (fp32 path)
+  float* bias = nullptr;  // [cout]
+  CUtensorMap tmap_w;
+};
+
+}  // namespace
+
+struct caz_handle {
+  caz_arch arch{};
+  int device = 0;
+  int precision = 0;
+  int max_batch = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::vector<ConvLayer> convs;  // stem, then conv1/conv2 of each block
+  float *head_w = nullptr, *head_b = nullptr;
+  float *pfc_w = nullptr, *pfc_b = nullptr, *vfc1_w = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr,
+        *vfc2_b = nullptr;
+  void* in_act = nullptr;  // [cap][64][in_cpad]
+  int in_cpad = 0;
+  void* act[3] = {nullptr, nullptr, nullptr};  // [cap][64][filters]
+  CUtensorMap tmap_in, tmap_act[3];
+  float *featp = nullptr, *featv = nullptr;
+  // staging for the host-pointer entry points
+  float *d_planes = nullptr, *d_policy = nullptr, *d_value = nullptr;
+  uint8_t *d_mask = nullptr, *d_records = nullptr;
+  int* err_flag_host = nullptr;  // mapped pinned: readable even after a device trap
+  int* err_flag_dev = nullptr;
+  // PUCT scratch
+  void* puct_buf = nullptr;
+  size_t puct_cap = 0;
+  int64_t launches = 0;
+  int64_t weight_bytes = 0;
+  // profiling
+  bool profiling = false, prof_pending = false;
+  cudaEvent_t ev[CAZ_STAGES + 1] = {};
+  float stage_ms[CAZ_STAGES] = {};
+  int64_t stage_launches[CAZ_STAGES] = {};
+  int64_t pending_launches[CAZ_STAGES] = {};
+};
+
+namespace {
+
+int fail(caz_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else {
+    std::lock_guard<std::mutex> g(g_err_mutex);
+    g_create_error = msg;
+  }
+  return code;
+}
+
+#define CU_TRY(h, expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess) {                                                                        \
+      int code__ = CAZ_ERR_CUDA;                                                                     \
+      std::string m__ = fmt("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      if ((h) && (h)->err_flag_host && *(h)->err_flag_host) {                                        \
+        code__ = CAZ_ERR_KERNEL;                                                                     \
+        m__ += fmt(" [kernel watchdog code %d]", *(h)->err_flag_host);                               \
+      }                                                                                              \
+      return fail((h), code__, m__);                                                                 \
+    }                                                                                                \
+  } while (0)
+
+int expected_tensor_count(const caz_arch& a) { return 5 + 10 * a.res_blocks + 7 + 9; }
+
+bool tensor_path(const caz_handle* h) { return h->precision == CAZ_PRECISION_BF16; }
+
+// BatchNorm inference folded into the preceding bias-free convolution (Keras semantics,
+// model_chess.py:65-69): y = conv(x)*inv + (beta - mean*inv), inv = gamma / sqrt(var + eps).
+void bn_fold(const caz_tensor* bn, int c, float eps, std::vector<float>& inv, std::vector<float>& shift) {
+  inv.resize(c);
+  shift.resize(c);
+  for (int i = 0; i < c; ++i) {
+    const double s = static_cast<double>(bn[0].data[i]) / std::sqrt(static_cast<double>(bn[3].data[i]) + eps);
+    inv[i] = static_cast<float>(s);
+    shift[i] = static_cast<float>(static_cast<double>(bn[1].data[i]) - static_cast<double>(bn[2].data[i]) * s);
+  }
+}
+
+int upload(caz_handle* h, void* dst, const void* src, size_t bytes) {
+  CU_TRY(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return CAZ_OK;
+}
+
+int make_tmap(caz_handle* h, CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+              const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(h, CAZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, ones,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, CAZ_ERR_CUDA, fmt("cuTensorMapEncodeTiled failed with CUresult %d", (int)r));
+  return CAZ_OK;
+}
+
+// NHWC bf16 activations [cap][8][8][c] as a 4-D tensor (c, file, rank, position); box = 64 ch x 8 x 8 x 2 boards
+int make_act_tmap(caz_handle* h, CUtensorMap* m, void* base, int c) {
+  cuuint64_t dims[4] = {(cuuint64_t)c, 8, 8, (cuuint64_t)h->max_batch};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 16, (cuuint64_t)c * 128};
+  cuuint32_t box[4] = {64, 8, 8, 2};
+  return make_tmap(h, m, base, 4, dims, strides, box);
+}
+
+// Installs (folds, re-lays-out, uploads) one full weight set. Buffers are allocated on first use.
+int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
+  const caz_arch& a = h->arch;
+  if (n_tensors != expected_tensor_count(a))
+    return fail(h, CAZ_ERR_INVALID, fmt("expected %d tensors for %d residual blocks, got %d",
+                                        expected_tensor_count(a), a.res_blocks, n_tensors));
+  const bool tcp = tensor_path(h);
+  const int F = a.filters;
+  int ti = 0;
+  int64_t wbytes = 0;
+  std::vector<float> inv, shift;
+  const int n_convs = 1 + 2 * a.res_blocks;
+  if (h->convs.empty()) h->convs.resize(n_convs);
+  for (int li = 0; li < n_convs; ++li) {
+    ConvLayer& L = h->convs[li];
+    const int k = li == 0 ? a.stem_kernel : a.block_kernel;
+    const int cin = li == 0 ? a.input_planes : F;
+    const int cin_pad = tcp ? ((cin + 63) / 64) * 64 : cin;
+    const caz_tensor& kt = t[ti];
+    if (kt.numel != (int64_t)k * k * cin * F)
+      return fail(h, CAZ_ERR_INVALID, fmt("conv %d kernel has %lld elements, expected %lld", li,
+                                          (long long)kt.numel, (long long)k * k * cin * F));
+    for (int j = 1; j <= 4; ++j)
+      if (t[ti + j].numel != F) return fail(h, CAZ_ERR_INVALID, fmt("conv %d BatchNorm tensor %d: expected %d values", li, j, F));
+    bn_fold(t + ti + 1, F, a.bn_epsilon, inv, shift);
+    ti += 5;
+    const int taps = k * k;
+    const size_t ktot = (size_t)taps * cin_pad;
+    if (!L.w) {
+      L.k = k; L.cin = cin; L.cin_pad = cin_pad; L.cout = F;
+      CU_TRY(h, cudaMalloc(&L.w, tcp ? ktot * F * 2 : (size_t)taps * cin * F * 4));
+      CU_TRY(h, cudaMalloc(&L.bias, F * sizeof(float)));
+      if (tcp) {
+        cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)F};
+        cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)F};
+        int rc = make_tmap(h, &L.tmap_w, L.w, 2, dims, strides, box);
+        if (rc) return rc;
+      }
+    }
+    if (tcp) {
+      // W[oc][tap*cin_pad + ic] bf16, K-major rows: the B operand of the implicit GEMM
+      std::vector<__nv_bfloat16> wp(ktot * F, __float2bfloat16(0.0f));
+      for (int tap = 0; tap < taps; ++tap)
+        for (int ic = 0; ic < cin; ++ic) {
+          const float* src = kt.data + ((size_t)tap * cin + ic) * F;
+          for (int oc = 0; oc < F; ++oc) wp[(size_t)oc * ktot + (size_t)tap * cin_pad + ic] = __float2bfloat16_rn(src[oc] * inv[oc]);
+        }
+      int rc = upload(h, L.w, wp.data(), wp.size() * 2);
+      if (rc) return rc;
+      wbytes += (int64_t)taps * cin * F * 2;
+    } else {
+      std::vector<float> wp((size_t)taps * cin * F);
+      for (size_t i = 0; i < wp.size(); ++i) wp[i] = kt.data[i] * inv[i % F];
+      int rc = upload(h, L.w, wp.data(), wp.size() * 4);
+      if (rc) return rc;
+      wbytes += (int64_t)wp.size() * 4;
+    }
+    int rc = upload(h, L.bias, shift.data(), F * sizeof(float));
+    if (rc) return rc;
+    wbytes += F * 4;
+  }
+  // ---- heads: 1x1 convs (policy filters first, then value filters), fp32 in both builds ----
+  const int pf = a.policy_filters, vf = a.value_filters, ft = pf + vf;
+  std::vector<float> hw((size_t)ft * F), hb(ft);
+  const caz_tensor* pol = t + ti;       // conv, g, b, m, v, dense k, dense b
+  const caz_tensor* val = t + ti + 7;   // conv, g, b, m, v, d1 k, d1 b, d2 k, d2 b
+  if (pol[0].numel != (int64_t)F * pf || val[0].numel != (int64_t)F * vf)
+    return fail(h, CAZ_ERR_INVALID, "head conv kernel size mismatch");
+  for (int j = 1; j <= 4; ++j)
+    if (pol[j].numel != pf || val[j].numel != vf) return fail(h, CAZ_ERR_INVALID, "head BatchNorm size mismatch");
+  bn_fold(pol + 1, pf, a.bn_epsilon, inv, shift);
+  for (int f = 0; f < pf; ++f) {
+    for (int c = 0; c < F; ++c) hw[(size_t)f * F + c] = pol[0].data[(size_t)c * pf + f] * inv[f];
+    hb[f] = shift[f];
+  }
+  bn_fold(val + 1, vf, a.bn_epsilon, inv, shift);
+  for (int f = 0; f < vf; ++f) {
+    for (int c = 0; c < F; ++c) hw[(size_t)(pf + f) * F + c] = val[0].data[(size_t)c * vf + f] * inv[f];
+    hb[pf + f] = shift[f];
+  }
+  const int kp = pf * 64, kv = vf * 64;
+  if (pol[5].numel != (int64_t)kp * a.n_labels || pol[6].numel != a.n_labels)
+    return fail(h, CAZ_ERR_INVALID, "policy Dense size mismatch");
+  if (val[5].numel != (int64_t)kv * a.value_fc || val[6].numel != a.value_fc || val[7].numel != a.value_fc ||
+      val[8].numel != 1)
+    return fail(h, CAZ_ERR_INVALID, "value Dense size mismatch");
+  if (!h->head_w) {
+    CU_TRY(h, cudaMalloc(&h->head_w, hw.size() * 4));
+    CU_TRY(h, cudaMalloc(&h->head_b, hb.size() * 4));
+    CU_TRY(h, cudaMalloc(&h->pfc_w, (size_t)pol[5].numel * 4));
+    CU_TRY(h, cudaMalloc(&h->pfc_b, (size_t)pol[6].numel * 4));
+    CU_TRY(h, cudaMalloc(&h->vfc1_w, (size_t)val[5].numel * 4));
+    CU_TRY(h, cudaMalloc(&h->vfc1_b, (size_t)val[6].numel * 4));
+    CU_TRY(h, cudaMalloc(&h->vfc2_w, (size_t)val[7].numel * 4));
+    CU_TRY(h, cudaMalloc(&h->vfc2_b, 4));
+  }
+  int rc;
+  if ((rc = upload(h, h->head_w, hw.data(), hw.size() * 4))) return rc;
+  if ((rc = upload(h, h->head_b, hb.data(), hb.size() * 4))) return rc;
+  if ((rc = upload(h, h->pfc_w, pol[5].data, (size_t)pol[5].numel * 4))) return rc;
+  if ((rc = upload(h, h->pfc_b, pol[6].data, (size_t)pol[6].numel * 4))) return rc;
+  if ((rc = upload(h, h->vfc1_w, val[5].data, (size_t)val[5].numel * 4))) return rc;
+  if ((rc = upload(h, h->vfc1_b, val[6].data, (size_t)val[6].numel * 4))) return rc;
+  if ((rc = upload(h, h->vfc2_w, val[7].data, (size_t)val[7].numel * 4))) return rc;
+  if ((rc = upload(h, h->vfc2_b, val[8].data, 4))) return rc;
+  wbytes += (int64_t)(hw.size() + hb.size() + pol[5].numel + pol[6].numel + val[5].numel + val[6].numel + val[7].numel + 1) * 4;
+  h->weight_bytes = wbytes;
+  return CAZ_OK;
+}
+
+int check_launch(caz_handle* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, CAZ_ERR_CUDA, fmt("launch of %s failed: %s", what, cudaGetErrorString(e)));
+  h->launches++;
+  return CAZ_OK;
+}
+
+int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_in, int in_stride, const void* residual,
+                void* out, int batch) {
+  const ConvLayer& L = h->convs[li];
+  if (tensor_path(h)) {
+    caz::tc::ConvArgs args;
+    args.batch = batch;
+    args.num_tiles = (batch + 1) / 2;
+    args.taps_w = L.k;
+    args.taps = L.k * L.k;
+    args.pad = (L.k - 1) / 2;
+    args.kchunks = L.cin_pad / 64;
+    args.n = L.cout;
+    args.relu = 1;
+    args.bias = L.bias;
+    args.residual = static_cast<const __nv_bfloat16*>(residual);
+    args.out = static_cast<__nv_bfloat16*>(out);
+    args.err_flag = h->err_flag_dev;
+    const int grid = args.num_tiles < h->num_sms ? args.num_tiles : h->num_sms;
+    caz::tc::conv_tc_kernel<<<grid, caz::tc::THREADS, caz::tc::SMEM_BYTES, h->stream>>>(*tmap_in, L.tmap_w, args);
+    return check_launch(h, "conv_tc_kernel");
+  }
+  const size_t smem = (size_t)(8 + L.k - 1) * (8 + L.k - 1) * L.cin * sizeof(float);
+  const float* fin = static_cast<const float*>(in);
+  const float* fres = static_cast<const float*>(residual);
+  float* fout = static_cast<float*>(out);
+  const float* fw = static_cast<const float*>(L.w);
+  switch (L.k) {
+    case 1: caz::conv_fp32_kernel<1><<<batch, 256, smem, h->stream>>>(fin, fw, L.bias, fres, fout, L.cin, in_stride, L.cout, 1); break;
+    case 3: caz::conv_fp32_kernel<3><<<batch, 256, smem, h->stream>>>(fin, fw, L.bias, fres, fout, L.cin, in_stride, L.cout, 1); break;
+    case 5: caz::conv_fp32_kernel<5><<<batch, 256, smem, h->stream>>>(fin, fw, L.bias, fres, fout, L.cin, in_stride, L.cout, 1); break;
+    case 7: caz::conv_fp32_kernel<7><<<batch, 256, smem, h->stream>>>(fin, fw, L.bias, fres, fout, L.cin, in_stride, L.cout, 1); break;
+    default: return fail(h, CAZ_ERR_INVALID, "unsupported kernel size");
+  }
+  return check_launch(h, "conv_fp32_kernel");
+}
+
+int prof_begin(caz_handle* h) {
+  if (!h->profiling) return CAZ_OK;
+  if (h->prof_pending) {
+    CU_TRY(h, cudaEventSynchronize(h->ev[CAZ_STAGES]));
+    for (int s = 0; s < CAZ_STAGES; ++s) {
+      float ms = 0;
+      CU_TRY(h, cudaEventElapsedTime(&ms, h->ev[s], h->ev[s + 1]));
+      h->stage_ms[s] += ms;
+      h->stage_launches[s] += h->pending_launches[s];
+    }
+    h->prof_pending = false;
+  }
+  return CAZ_OK;
+}
+
+// Forward pass over device-resident input. Exactly one of d_planes / d_records is non-null.
+int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int batch, float* d_policy, float* d_value,
+            const uint8_t* d_mask) {
+  const caz_arch& a = h->arch;
+  const bool tcp = tensor_path(h);
+  int rc;
+  if ((rc = prof_begin(h))) return rc;
+  const bool prof = h->profiling;
+  int64_t l0 = h->launches;
+  if (prof) CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+  // ---- stage 0: input pack (NCHW fp32 planes -> NHWC activations, channels zero-padded) ----
+  if (d_planes) {
+    const size_t smem = (size_t)a.input_planes * 65 * sizeof(float);
+    if (tcp) caz::pack_planes_kernel<__nv_bfloat16><<<batch, 256, smem, h->stream>>>(d_planes, static_cast<__nv_bfloat16*>(h->in_act), batch, a.input_planes, h->in_cpad);
+    else caz::pack_planes_kernel<float><<<batch, 256, smem, h->stream>>>(d_planes, static_cast<float*>(h->in_act), batch, a.input_planes, h->in_cpad);
+    if ((rc = check_launch(h, "pack_planes_kernel"))) return rc;
+  } else {
+    const size_t total = (size_t)batch * 64 * h->in_cpad;
+    const int blocks = (int)((total + 255) / 256);
+    if (tcp) caz::encode_pack_kernel<__nv_bfloat16><<<blocks, 256, 0, h->stream>>>(d_records, static_cast<__nv_bfloat16*>(h->in_act), batch, h->in_cpad);
+    else caz::encode_pack_kernel<float><<<blocks, 256, 0, h->stream>>>(d_records, static_cast<float*>(h->in_act), batch, h->in_cpad);
+    if ((rc = check_launch(h, "encode_pack_kernel"))) return rc;
+  }
+  if (prof) { CU_TRY(h, cudaEventRecord(h->ev[1], h->stream)); h->pending_launches[0] = h->launches - l0; l0 = h->launches; }
+  // ---- stage 1: stem ----
+  if ((rc = launch_conv(h, 0, h->in_act, &h->tmap_in, h->in_cpad, nullptr, h->act[0], batch))) return rc;
+  if (prof) { CU_TRY(h, cudaEventRecord(h->ev[2], h->stream)); h->pending_launches[1] = h->launches - l0; l0 = h->launches; }
+  // ---- stage 2: residual tower ----
+  int cur = 0;
+  for (int blk = 0; blk < a.res_blocks; ++blk) {
+    const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
+    if ((rc = launch_conv(h, 1 + 2 * blk, h->act[cur], &h->tmap_act[cur], a.filters, nullptr, h->act[t1], batch))) return rc;
+    if ((rc = launch_conv(h, 2 + 2 * blk, h->act[t1], &h->tmap_act[t1], a.filters, h->act[cur], h->act[t2], batch))) return rc;
+    cur = t2;
+  }
+  if (prof) { CU_TRY(h, cudaEventRecord(h->ev[3], h->stream)); h->pending_launches[2] = h->launches - l0; l0 = h->launches; }
+  // ---- stage 3: heads ----
+  const int pf = a.policy_filters, vf = a.value_filters;
+  const size_t hsmem = (size_t)(pf + vf) * a.filters * sizeof(float);
+  if (tcp) caz::head_conv_kernel<__nv_bfloat16><<<batch, 256, hsmem, h->stream>>>(static_cast<const __nv_bfloat16*>(h->act[cur]), h->head_w, h->head_b, h->featp, h->featv, batch, a.filters, pf, vf);
+  else caz::head_conv_kernel<float><<<batch, 256, hsmem, h->stream>>>(static_cast<const float*>(h->act[cur]), h->head_w, h->head_b, h->featp, h->featv, batch, a.filters, pf, vf);
+  if ((rc = check_launch(h, "head_conv_kernel"))) return rc;
+  caz::policy_fc_softmax_kernel<<<(batch + caz::PTM - 1) / caz::PTM, 256, (size_t)caz::PTM * pf * 64 * sizeof(float), h->stream>>>(
+      h->featp, h->pfc_w, h->pfc_b, d_mask, d_policy, batch, pf * 64, a.n_labels);
+  if ((rc = check_launch(h, "policy_fc_softmax_kernel"))) return rc;
+  caz::value_fc_kernel<<<(batch + caz::VTM - 1) / caz::VTM, 256, (size_t)caz::VTM * vf * 64 * sizeof(float), h->stream>>>(
+      h->featv, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, d_value, batch, vf * 64, a.value_fc);
+  if ((rc = check_launch(h, "value_fc_kernel"))) return rc;
+  if (prof) { CU_TRY(h, cudaEventRecord(h->ev[4], h->stream)); h->pending_launches[3] = h->launches - l0; h->prof_pending = true; }
+  return CAZ_OK;
+}
+
+int ensure_puct(caz_handle* h, size_t bytes) {
+  if (bytes <= h->puct_cap) return CAZ_OK;
+  if (h->puct_buf) CU_TRY(h, cudaFree(h->puct_buf));
+  h->puct_buf = nullptr;
+  h->puct_cap = 0;
+  const size_t cap = bytes + bytes / 2 + 4096;
+  CU_TRY(h, cudaMalloc(&h->puct_buf, cap));
+  h->puct_cap = cap;
+  return CAZ_OK;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+int set_device(caz_handle* h) {
+  CU_TRY(h, cudaSetDevice(h->device));
+  return CAZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t caz_abi_version(void) { return CAZ_ABI_VERSION; }
+
+const char* caz_last_error(const caz_handle* h) {
+  if (h) return h->err.c_str();
+  std::lock_guard<std::mutex> g(g_err_mutex);
+  static thread_local std::string copy;
+  copy = g_create_error;
+  return copy.c_str();
+}
+
+void caz_destroy(caz_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& L : h->convs) { cudaFree(L.w); cudaFree(L.bias); }
+  void* ptrs[] = {h->head_w, h->head_b, h->pfc_w, h->pfc_b, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, h->in_act,
+                  h->act[0], h->act[1], h->act[2], h->featp, h->featv, h->d_planes, h->d_policy, h->d_value,
+                  h->d_mask, h->d_records, h->puct_buf};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensors, int32_t device, int32_t precision,
+               int32_t max_batch, caz_handle** out) {
+  if (!arch || !tensors || !out) return fail(nullptr, CAZ_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const caz_arch& a = *arch;
+  if (precision != CAZ_PRECISION_BF16 && precision != CAZ_PRECISION_FP32)
+    return fail(nullptr, CAZ_ERR_INVALID, "precision must be CAZ_PRECISION_BF16 or CAZ_PRECISION_FP32");
+  if (max_batch < 1) return fail(nullptr, CAZ_ERR_INVALID, "max_batch must be >= 1");
+  if (a.input_planes < 1 || a.input_planes > 64 || a.res_blocks < 0 || a.filters < 1 || a.policy_filters < 1 ||
+      a.value_filters < 1 || a.policy_filters + a.value_filters > caz::HEAD_MAX_F || a.value_fc < 1 ||
+      a.n_labels < 1 || a.n_labels > caz::PNJ * 256 || (a.stem_kernel & 1) == 0 || (a.block_kernel & 1) == 0 ||
+      a.stem_kernel > 7 || a.block_kernel > 7)
+    return fail(nullptr, CAZ_ERR_INVALID, "architecture outside the supported envelope");
+  if (precision == CAZ_PRECISION_BF16 && (a.filters % 64 != 0 || a.filters > 256))
+    return fail(nullptr, CAZ_ERR_INVALID,
+                "the tensor-core build needs filters to be a multiple of 64 and <= 256; use CAZ_PRECISION_FP32");
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count <= 0 || device < 0 || device >= count)
+    return fail(nullptr, CAZ_ERR_NO_DEVICE, fmt("no CUDA device %d (%s); this library has no CPU path", device,
+                                                ce == cudaSuccess ? "count is 0 or index out of range" : cudaGetErrorString(ce)));
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+    return fail(nullptr, CAZ_ERR_NO_DEVICE, fmt("device %d is not an sm_100 GPU (compute %d.%d)", device, prop.major, prop.minor));
+  caz_handle* h = new caz_handle();
+  h->arch = a;
+  h->device = device;
+  h->precision = precision;
+  h->max_batch = max_batch;
+  h->num_sms = prop.multiProcessorCount;
+  auto bail = [&](int rc) {
+    fail(nullptr, rc, h->err);
+    caz_destroy(h);
+    return rc;
+  };
+#define CREATE_TRY(expr)                                                                                          \
+  do {                                                                                                            \
+    cudaError_t e__ = (expr);                                                                                     \
+    if (e__ != cudaSuccess) {                                                                                     \
+      h->err = fmt("%s failed: %s", #expr, cudaGetErrorString(e__));                                              \
+      return bail(CAZ_ERR_CUDA);                                                                                  \
+    }                                                                                                             \
+  } while (0)
+  CREATE_TRY(cudaSetDevice(device));
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CREATE_TRY(cudaEventCreate(&e));
+  CREATE_TRY(cudaHostAlloc(&h->err_flag_host, sizeof(int), cudaHostAllocMapped));
+  *h->err_flag_host = 0;
+  CREATE_TRY(cudaHostGetDevicePointer(&h->err_flag_dev, h->err_flag_host, 0));
+  const bool tcp = precision == CAZ_PRECISION_BF16;
+  const size_t esz = tcp ? 2 : 4;
+  const size_t cap = (size_t)max_batch;
+  h->in_cpad = tcp ? 64 : a.input_planes;
+  CREATE_TRY(cudaMalloc(&h->in_act, cap * 64 * h->in_cpad * esz));
+  for (int i = 0; i < 3; ++i) CREATE_TRY(cudaMalloc(&h->act[i], cap * 64 * a.filters * esz));
+  CREATE_TRY(cudaMalloc(&h->featp, cap * a.policy_filters * 64 * 4));
+  CREATE_TRY(cudaMalloc(&h->featv, cap * a.value_filters * 64 * 4));
+  CREATE_TRY(cudaMalloc(&h->d_planes, cap * a.input_planes * 64 * 4));
+  CREATE_TRY(cudaMalloc(&h->d_policy, cap * a.n_labels * 4));
+  CREATE_TRY(cudaMalloc(&h->d_value, cap * 4));
+  CREATE_TRY(cudaMalloc(&h->d_mask, cap * a.n_labels));
+  CREATE_TRY(cudaMalloc(&h->d_records, cap * CAZ_RECORD_BYTES));
+  int rc;
+  if (tcp) {
+    if ((rc = make_act_tmap(h, &h->tmap_in, h->in_act, h->in_cpad))) return bail(rc);
+    for (int i = 0; i < 3; ++i)
+      if ((rc = make_act_tmap(h, &h->tmap_act[i], h->act[i], a.filters))) return bail(rc);
+    CREATE_TRY(cudaFuncSetAttribute(caz::tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc::SMEM_BYTES));
+  } else {
+    const size_t s3 = (size_t)(8 + a.block_kernel - 1) * (8 + a.block_kernel - 1) * a.filters * 4;
+    const size_t s1 = (size_t)(8 + a.stem_kernel - 1) * (8 + a.stem_kernel - 1) * a.input_planes * 4;
+    const size_t need = s3 > s1 ? s3 : s1;
+    if (need > (size_t)prop.sharedMemPerBlockOptin) { h->err = "fp32 build: board tile does not fit shared memory"; return bail(CAZ_ERR_INVALID); }
+    CREATE_TRY(cudaFuncSetAttribute(caz::conv_fp32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    CREATE_TRY(cudaFuncSetAttribute(caz::conv_fp32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    CREATE_TRY(cudaFuncSetAttribute(caz::conv_fp32_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    CREATE_TRY(cudaFuncSetAttribute(caz::conv_fp32_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  }
+#undef CREATE_TRY
+  if ((rc = install_weights(h, tensors, n_tensors))) return bail(rc);
+  *out = h;
+  return CAZ_OK;
+}
+
+int caz_reload(caz_handle* h, const caz_tensor* tensors, int32_t n_tensors) {
+  if (!h || !tensors) return fail(h, CAZ_ERR_INVALID, "null argument");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return install_weights(h, tensors, n_tensors);
+}
+
+int caz_sync(caz_handle* h) {
+  if (!h) return CAZ_ERR_INVALID;
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return CAZ_OK;
+}
+
+int caz_eval_device(caz_handle* h, const float* d_planes, int32_t batch, float* d_policy, float* d_value,
+                    const uint8_t* d_legal_mask, uint32_t flags) {
+  if (!h) return CAZ_ERR_INVALID;
+  if (batch == 0) return CAZ_OK;
+  if (!d_planes || !d_policy || !d_value || batch < 0 || batch > h->max_batch)
+    return fail(h, CAZ_ERR_INVALID, fmt("caz_eval_device: bad argument (batch %d, max_batch %d)", batch, h->max_batch));
+  if ((flags & CAZ_EVAL_MASKED_SOFTMAX) && !d_legal_mask) return fail(h, CAZ_ERR_INVALID, "masked softmax needs a legal mask");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  return forward(h, d_planes, nullptr, batch, d_policy, d_value, (flags & CAZ_EVAL_MASKED_SOFTMAX) ? d_legal_mask : nullptr);
+}
+
+static int eval_host(caz_handle* h, const float* planes, const uint8_t* records, int32_t batch, float* policy,
+                     float* value, const uint8_t* legal_mask, uint32_t flags) {
+  if (!h) return CAZ_ERR_INVALID;
+  if (batch == 0) return CAZ_OK;
+  if ((!planes && !records) || !policy || !value || batch < 0) return fail(h, CAZ_ERR_INVALID, "caz_eval: bad argument");
+  const bool masked = (flags & CAZ_EVAL_MASKED_SOFTMAX) != 0;
+  if (masked && !legal_mask) return fail(h, CAZ_ERR_INVALID, "masked softmax needs a legal mask");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  const caz_arch& a = h->arch;
+  const size_t pin = (size_t)a.input_planes * 64;
+  for (int32_t off = 0; off < batch; off += h->max_batch) {
+    const int32_t nb = batch - off < h->max_batch ? batch - off : h->max_batch;
+    if (planes) CU_TRY(h, cudaMemcpyAsync(h->d_planes, planes + (size_t)off * pin, (size_t)nb * pin * 4, cudaMemcpyHostToDevice, h->stream));
+    else CU_TRY(h, cudaMemcpyAsync(h->d_records, records + (size_t)off * CAZ_RECORD_BYTES, (size_t)nb * CAZ_RECORD_BYTES, cudaMemcpyHostToDevice, h->stream));
+    if (masked) CU_TRY(h, cudaMemcpyAsync(h->d_mask, legal_mask + (size_t)off * a.n_labels, (size_t)nb * a.n_labels, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = forward(h, planes ? h->d_planes : nullptr, planes ? nullptr : h->d_records, nb, h->d_policy, h->d_value, masked ? h->d_mask : nullptr))) return rc;
+    CU_TRY(h, cudaMemcpyAsync(policy + (size_t)off * a.n_labels, h->d_policy, (size_t)nb * a.n_labels * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(value + off, h->d_value, (size_t)nb * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return CAZ_OK;
+}
+
+int caz_eval(caz_handle* h, const float* planes, int32_t batch, float* policy, float* value, const uint8_t* legal_mask,
+             uint32_t flags) {
+  return eval_host(h, planes, nullptr, batch, policy, value, legal_mask, flags);
+}
+
+int caz_eval_records(caz_handle* h, const uint8_t* records, int32_t batch, float* policy, float* value,
+                     const uint8_t* legal_mask, uint32_t flags) {
+  return eval_host(h, nullptr, records, batch, policy, value, legal_mask, flags);
+}
+
+int caz_encode(caz_handle* h, const uint8_t* records, int32_t batch, float* planes) {
+  if (!h) return CAZ_ERR_INVALID;
+  if (batch == 0) return CAZ_OK;
+  if (!records || !planes || batch < 0) return fail(h, CAZ_ERR_INVALID, "caz_encode: bad argument");
+  if (h->arch.input_planes != CAZ_PLANES) return fail(h, CAZ_ERR_INVALID, "caz_encode needs an 18-plane network");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  for (int32_t off = 0; off < batch; off += h->max_batch) {
+    const int32_t nb = batch - off < h->max_batch ? batch - off : h->max_batch;
+    CU_TRY(h, cudaMemcpyAsync(h->d_records, records + (size_t)off * CAZ_RECORD_BYTES, (size_t)nb * CAZ_RECORD_BYTES, cudaMemcpyHostToDevice, h->stream));
+    const size_t total = (size_t)nb * CAZ_PLANE_FLOATS;
+    caz::encode_records_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->d_records, h->d_planes, nb);
+    if ((rc = check_launch(h, "encode_records_kernel"))) return rc;
+    CU_TRY(h, cudaMemcpyAsync(planes + (size_t)off * CAZ_PLANE_FLOATS, h->d_planes, total * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return CAZ_OK;
+}
+
+int caz_push_priors(caz_handle* h, const float* policy, int32_t n_labels, const int32_t* offsets, int32_t n_nodes,
+                    const int32_t* label_index, double* priors) {
+  if (!h) return CAZ_ERR_INVALID;
+  if (n_nodes == 0) return CAZ_OK;
+  if (!policy || !offsets || !label_index || !priors || n_nodes < 0 || n_labels < 1)
+    return fail(h, CAZ_ERR_INVALID, "caz_push_priors: bad argument");
+  const int32_t n_edges = offsets[n_nodes];
+  if (offsets[0] != 0 || n_edges < 0) return fail(h, CAZ_ERR_INVALID, "caz_push_priors: offsets must start at 0");
+  if (n_edges == 0) return CAZ_OK;
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  const size_t b_pol = align256((size_t)n_nodes * n_labels * 4), b_off = align256((size_t)(n_nodes + 1) * 4),
+               b_idx = align256((size_t)n_edges * 4), b_out = align256((size_t)n_edges * 8);
+  if ((rc = ensure_puct(h, b_pol + b_off + b_idx + b_out))) return rc;
+  char* base = static_cast<char*>(h->puct_buf);
+  float* d_pol = reinterpret_cast<float*>(base);
+  int* d_off = reinterpret_cast<int*>(base + b_pol);
+  int* d_idx = reinterpret_cast<int*>(base + b_pol + b_off);
+  double* d_out = reinterpret_cast<double*>(base + b_pol + b_off + b_idx);
+  CU_TRY(h, cudaMemcpyAsync(d_pol, policy, (size_t)n_nodes * n_labels * 4, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaMemcpyAsync(d_off, offsets, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  CU_TRY(h, cudaMemcpyAsync(d_idx, label_index, (size_t)n_edges * 4, cudaMemcpyHostToDevice, h->stream));
+  const int wpb = 8;
+  caz::push_priors_kernel<<<(n_nodes + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>(d_pol, n_labels, d_off, n_nodes, d_idx, d_out);
+  if ((rc = check_launch(h, "push_priors_kernel"))) return rc;
+  CU_TRY(h, cudaMemcpyAsync(priors, d_out, (size_t)n_edges * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return CAZ_OK;
+}
+
+int caz_puct_select(caz_handle* h, const int32_t* offsets, int32_t n_nodes, const int32_t* n, const double* q,
+                    const double* p, const int32_t* sum_n, const double* noise, const uint8_t* is_root, double c_puct,
+                    double noise_eps, int32_t* best_edge) {
+  if (!h) return CAZ_ERR_INVALID;
+  if (n_nodes == 0) return CAZ_OK;
+  if (!offsets || !n || !q || !p || !sum_n || !best_edge || n_nodes < 0) return fail(h, CAZ_ERR_INVALID, "caz_puct_select: bad argument");
+  const int32_t n_edges = offsets[n_nodes];
+  if (offsets[0] != 0 || n_edges < 0) return fail(h, CAZ_ERR_INVALID, "caz_puct_select: offsets must start at 0");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  const bool with_noise = noise && is_root;
+  const size_t ne = (size_t)(n_edges > 0 ? n_edges : 1);
+  const size_t b_off = align256((size_t)(n_nodes + 1) * 4), b_n = align256(ne * 4), b_d = align256(ne * 8),
+               b_sn = align256((size_t)n_nodes * 4), b_root = align256((size_t)n_nodes), b_best = align256((size_t)n_nodes * 4);
+  if ((rc = ensure_puct(h, b_off + b_n + 3 * b_d + b_sn + b_root + b_best))) return rc;
+  char* c = static_cast<char*>(h->puct_buf);
+  int* d_off = reinterpret_cast<int*>(c); c += b_off;
+  int* d_n = reinterpret_cast<int*>(c); c += b_n;
+  double* d_q = reinterpret_cast<double*>(c); c += b_d;
+  double* d_p = reinterpret_cast<double*>(c); c += b_d;
+  double* d_noise = reinterpret_cast<double*>(c); c += b_d;
+  int* d_sn = reinterpret_cast<int*>(c); c += b_sn;
+  uint8_t* d_root = reinterpret_cast<uint8_t*>(c); c += b_root;
+  int* d_best = reinterpret_cast<int*>(c);
+  CU_TRY(h, cudaMemcpyAsync(d_off, offsets, (size_t)(n_nodes + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  if (n_edges > 0) {
+    CU_TRY(h, cudaMemcpyAsync(d_n, n, (size_t)n_edges * 4, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(d_q, q, (size_t)n_edges * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(d_p, p, (size_t)n_edges * 8, cudaMemcpyHostToDevice, h->stream));
+    if (with_noise) CU_TRY(h, cudaMemcpyAsync(d_noise, noise, (size_t)n_edges * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  CU_TRY(h, cudaMemcpyAsync(d_sn, sum_n, (size_t)n_nodes * 4, cudaMemcpyHostToDevice, h->stream));
+  if (with_noise) CU_TRY(h, cudaMemcpyAsync(d_root, is_root, (size_t)n_nodes, cudaMemcpyHostToDevice, h->stream));
+  const int wpb = 8;
+  caz::puct_select_kernel<<<(n_nodes + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>(
+      d_off, n_nodes, d_n, d_q, d_p, d_sn, with_noise ? d_noise : nullptr, with_noise ? d_root : nullptr, c_puct, noise_eps, d_best);
+  if ((rc = check_launch(h, "puct_select_kernel"))) return rc;
+  CU_TRY(h, cudaMemcpyAsync(best_edge, d_best, (size_t)n_nodes * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return CAZ_OK;
+}
+
+int caz_debug_conv_layer(caz_handle* h, int32_t layer, const float* in, const float* residual, int32_t batch,
+                         float* out) {
+  if (!h) return CAZ_ERR_INVALID;
+  if (!in || !out || batch < 1 || batch > h->max_batch || layer < 0 || layer >= (int)h->convs.size())
+    return fail(h, CAZ_ERR_INVALID, "caz_debug_conv_layer: bad argument");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  const ConvLayer& L = h->convs[layer];
+  const bool tcp = tensor_path(h);
+  const size_t rows = (size_t)batch * 64;
+  const int F = h->arch.filters;
+  float *d_in = nullptr, *d_res = nullptr, *d_out = nullptr;
+  CU_TRY(h, cudaMalloc(&d_in, rows * L.cin * 4));
+  CU_TRY(h, cudaMalloc(&d_out, rows * F * 4));
+  CU_TRY(h, cudaMemcpyAsync(d_in, in, rows * L.cin * 4, cudaMemcpyHostToDevice, h->stream));
+  if (residual) {
+    CU_TRY(h, cudaMalloc(&d_res, rows * F * 4));
+    CU_TRY(h, cudaMemcpyAsync(d_res, residual, rows * F * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  // stage into the handle's own activation buffers so the real tensor maps are exercised
+  void* a_in = layer == 0 ? h->in_act : h->act[0];
+  const CUtensorMap* tm = layer == 0 ? &h->tmap_in : &h->tmap_act[0];
+  const int cpad = layer == 0 ? h->in_cpad : F;
+  const unsigned gi = (unsigned)((rows * cpad + 255) / 256), go = (unsigned)((rows * F + 255) / 256);
+  if (tcp) {
+    caz::cast_pad_kernel<__nv_bfloat16><<<gi, 256, 0, h->stream>>>(d_in, (__nv_bfloat16*)a_in, rows, L.cin, cpad);
+    if (residual) caz::cast_pad_kernel<__nv_bfloat16><<<go, 256, 0, h->stream>>>(d_res, (__nv_bfloat16*)h->act[1], rows, F, F);
+  } else {
+    caz::cast_pad_kernel<float><<<gi, 256, 0, h->stream>>>(d_in, (float*)a_in, rows, L.cin, cpad);
+    if (residual) caz::cast_pad_kernel<float><<<go, 256, 0, h->stream>>>(d_res, (float*)h->act[1], rows, F, F);
+  }
+  if ((rc = check_launch(h, "cast_pad_kernel"))) return rc;
+  if ((rc = launch_conv(h, layer, a_in, tm, cpad, residual ? h->act[1] : nullptr, h->act[2], batch))) return rc;
+  if (tcp) caz::widen_kernel<__nv_bfloat16><<<go, 256, 0, h->stream>>>((const __nv_bfloat16*)h->act[2], d_out, rows * F);
+  else caz::widen_kernel<float><<<go, 256, 0, h->stream>>>((const float*)h->act[2], d_out, rows * F);
+  if ((rc = check_launch(h, "widen_kernel"))) return rc;
+  CU_TRY(h, cudaMemcpyAsync(out, d_out, rows * F * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_in); cudaFree(d_out); if (d_res) cudaFree(d_res);
+  return CAZ_OK;
+}
+
+int32_t caz_max_batch(const caz_handle* h) { return h ? h->max_batch : 0; }
+int32_t caz_precision(const caz_handle* h) { return h ? h->precision : -1; }
+void* caz_stream(const caz_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
+int64_t caz_kernel_launches(const caz_handle* h) { return h ? h->launches : 0; }
+int64_t caz_weight_bytes(const caz_handle* h) { return h ? h->weight_bytes : 0; }
+
+int caz_profile(caz_handle* h, int32_t enable) {
+  if (!h) return CAZ_ERR_INVALID;
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  if ((rc = prof_begin(h))) return rc;
+  h->profiling = enable != 0;
+  return CAZ_OK;
+}
+
+int caz_profile_read(caz_handle* h, float* ms_per_stage, int64_t* launches_per_stage, int32_t reset) {
+  if (!h) return CAZ_ERR_INVALID;
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  const bool was = h->profiling;
+  h->profiling = true;
+  rc = prof_begin(h);
+  h->profiling = was;
+  if (rc) return rc;
+  for (int s = 0; s < CAZ_STAGES; ++s) {
+    if (ms_per_stage) ms_per_stage[s] = h->stage_ms[s];
+    if (launches_per_stage) launches_per_stage[s] = h->stage_launches[s];
+    if (reset) { h->stage_ms[s] = 0; h->stage_launches[s] = 0; }
+  }
+  return CAZ_OK;
+}
+
+void* caz_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void caz_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,420 @@
+// CUDA-core kernels of the evaluator: input packing / encoding, the fp32 parity build's convolution,
+// the two heads (1x1 convs, policy Dense + softmax, value Dense-Dense-tanh) and PUCT.
+// Reference semantics cited per kernel; paths relative to /root/reference/src/chess_zero.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace caz {
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ------------------------------------------------------------------------------------------------
+// planes f32 [B][Cin][64] (NCHW, what predict_on_batch receives, agent/api_chess.py:66)
+//   -> activations T [B][64][Cpad] (NHWC, channels zero-padded to Cpad)
+// One block per position; coalesced reads, smem transpose, coalesced writes.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_planes_kernel(const float* __restrict__ planes, T* __restrict__ act, int batch, int cin,
+                                   int cpad) {
+  extern __shared__ float s_pl[];  // [cin][65]
+  const int b = blockIdx.x;
+  if (b >= batch) return;
+  const float* src = planes + static_cast<size_t>(b) * cin * 64;
+  for (int i = threadIdx.x; i < cin * 64; i += blockDim.x) s_pl[(i >> 6) * 65 + (i & 63)] = src[i];
+  __syncthreads();
+  T* dst = act + static_cast<size_t>(b) * 64 * cpad;
+  for (int i = threadIdx.x; i < 64 * cpad; i += blockDim.x) {
+    const int sq = i / cpad, c = i - sq * cpad;
+    dst[i] = from_f32<T>(c < cin ? s_pl[c * 65 + sq] : 0.0f);
+  }
+}
+
+// rows x cin fp32 -> rows x cpad T (zero padded), and back (test hook caz_debug_conv_layer)
+template <typename T>
+__global__ void cast_pad_kernel(const float* __restrict__ in, T* __restrict__ out, size_t rows, int cin, int cpad) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * cpad) return;
+  const size_t r = i / cpad;
+  const int c = static_cast<int>(i - r * cpad);
+  out[i] = from_f32<T>(c < cin ? in[r * cin + c] : 0.0f);
+}
+template <typename T>
+__global__ void widen_kernel(const T* __restrict__ in, float* __restrict__ out, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = to_f32<T>(in[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Board records (68 bytes, include/caz_b200.h) -> canonical (18,8,8) float32 planes.
+// Reproduces env/chess_env.py:231-348 bit for bit: black to move mirrors ranks and swaps piece colour
+// (maybe_flip_fen :251-265), castling planes follow the case-swapped field (:279-283), plane 16 is the raw
+// halfmove clock (:276-277), plane 17 is the en-passant square UN-mirrored (:271-274).
+// One thread per output float; every thread of a block reads the same 68-byte record (L1 broadcast).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float record_plane_value(const uint8_t* __restrict__ rec, int plane, int sq) {
+  const uint8_t flags = rec[64];
+  const bool black = flags & 1;
+  if (plane < 12) {
+    const int r = sq >> 3, f = sq & 7;
+    const int code = rec[black ? ((7 - r) << 3 | f) : sq];  // mirrored source square for black
+    if (code == 0) return 0.0f;
+    int p = code - 1;
+    if (black) p = p >= 6 ? p - 6 : p + 6;  // swap case
+    return p == plane ? 1.0f : 0.0f;
+  }
+  if (plane < 16) {
+    int bit = plane - 12;          // K Q k q as seen by the side to move
+    if (black) bit ^= 2;           // swapcase exchanges KQ <-> kq
+    return (flags >> (1 + bit)) & 1 ? 1.0f : 0.0f;
+  }
+  if (plane == 16) return static_cast<float>(static_cast<int>(rec[66]) | (static_cast<int>(rec[67]) << 8));
+  return rec[65] == sq ? 1.0f : 0.0f;  // 255 never matches
+}
+
+__global__ void encode_records_kernel(const uint8_t* __restrict__ records, float* __restrict__ planes, int batch) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(batch) * 1152;
+  if (i >= total) return;
+  const int b = static_cast<int>(i / 1152);
+  const int rem = static_cast<int>(i - static_cast<size_t>(b) * 1152);
+  planes[i] = record_plane_value(records + static_cast<size_t>(b) * 68, rem >> 6, rem & 63);
+}
+
+// records -> NHWC activations directly (no fp32 planes round trip through HBM)
+template <typename T>
+__global__ void encode_pack_kernel(const uint8_t* __restrict__ records, T* __restrict__ act, int batch, int cpad) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(batch) * 64 * cpad;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % cpad);
+  const size_t t = i / cpad;
+  const int sq = static_cast<int>(t & 63);
+  const size_t b = t >> 6;
+  act[i] = from_f32<T>(c < 18 ? record_plane_value(records + b * 68, c, sq) : 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 parity build: direct "same" convolution on NHWC fp32, BN folded, optional residual + ReLU
+// (agent/model_chess.py:65-69,96-111).  One block per position; the zero-padded input board lives in
+// shared memory; each thread owns one output channel and all 64 squares in registers.
+// w layout: [tap][ic][oc] (= Keras HWIO flattened, scaled by the folded BN factor).
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+conv_fp32_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                 const float* __restrict__ residual, float* __restrict__ out, int cin, int cin_stride, int cout,
+                 int relu) {
+  constexpr int P = (K - 1) / 2;
+  constexpr int HW = 8 + K - 1;
+  extern __shared__ float s_in[];  // [HW*HW][cin]
+  const int b = blockIdx.x;
+  const float* src = in + static_cast<size_t>(b) * 64 * cin_stride;
+  for (int i = threadIdx.x; i < HW * HW * cin; i += blockDim.x) {
+    const int cell = i / cin, c = i - cell * cin;
+    const int r = cell / HW - P, f = cell % HW - P;
+    s_in[i] = (r >= 0 && r < 8 && f >= 0 && f < 8) ? src[(r * 8 + f) * cin_stride + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int oc = threadIdx.x; oc < cout; oc += blockDim.x) {
+    float acc[64];
+#pragma unroll
+    for (int s = 0; s < 64; ++s) acc[s] = 0.0f;
+    for (int tap = 0; tap < K * K; ++tap) {
+      const int dy = tap / K, dx = tap % K;
+      const float* wp = w + static_cast<size_t>(tap) * cin * cout + oc;
+      const float* sp = s_in + (dy * HW + dx) * cin;
+      for (int ic = 0; ic < cin; ++ic) {
+        const float wv = __ldg(wp + static_cast<size_t>(ic) * cout);
+#pragma unroll
+        for (int s = 0; s < 64; ++s) acc[s] = fmaf(wv, sp[((s >> 3) * HW + (s & 7)) * cin + ic], acc[s]);
+      }
+    }
+    const float bv = bias[oc];
+#pragma unroll
+    for (int s = 0; s < 64; ++s) {
+      const size_t o = (static_cast<size_t>(b) * 64 + s) * cout + oc;
+      float v = acc[s] + bv;
+      if (residual) v += residual[o];
+      if (relu) v = fmaxf(v, 0.0f);
+      out[o] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head 1x1 convolutions + folded BN + ReLU + Flatten (agent/model_chess.py:77-81,86-90).
+// in: T [B][64][C]; w: [F][C] fp32 (policy filters first, then value filters), bias [F].
+// Output in Keras channels_first Flatten order: featp[b][c*64 + s], featv[b][c*64 + s].
+// One block (8 warps) per position; a warp takes 8 squares, lanes split the channels.
+// ------------------------------------------------------------------------------------------------
+constexpr int HEAD_MAX_F = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_conv_kernel(const T* __restrict__ act, const float* __restrict__ w, const float* __restrict__ bias,
+                 float* __restrict__ featp, float* __restrict__ featv, int batch, int c, int pf, int vf) {
+  extern __shared__ float s_w[];  // [F][c]
+  const int f_total = pf + vf;
+  for (int i = threadIdx.x; i < f_total * c; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int sq = warp; sq < 64; sq += 8) {
+    const T* row = act + (static_cast<size_t>(b) * 64 + sq) * c;
+    float acc[HEAD_MAX_F];
+#pragma unroll
+    for (int f = 0; f < HEAD_MAX_F; ++f) acc[f] = 0.0f;
+    for (int ch = lane; ch < c; ch += 32) {
+      const float x = to_f32<T>(row[ch]);
+#pragma unroll
+      for (int f = 0; f < HEAD_MAX_F; ++f)
+        if (f < f_total) acc[f] = fmaf(x, s_w[f * c + ch], acc[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < HEAD_MAX_F; ++f) {
+      if (f < f_total) {
+        float v = acc[f];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+          v = fmaxf(v + bias[f], 0.0f);
+          if (f < pf) featp[static_cast<size_t>(b) * pf * 64 + f * 64 + sq] = v;
+          else featv[static_cast<size_t>(b) * vf * 64 + (f - pf) * 64 + sq] = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Policy head: Dense(n_labels) + softmax (agent/model_chess.py:82-83), optionally restricted to a legal
+// mask (how player_chess.py:267-275 consumes the row).  One block = PTM positions x all labels:
+// thread t owns labels t, t+256, ... (coalesced weight and output accesses), logits stay in registers,
+// max / sum are block reductions.  wk: [kin][n_labels] (Keras Dense kernel layout), fp32 throughout.
+// ------------------------------------------------------------------------------------------------
+constexpr int PTM = 8;    // positions per block
+constexpr int PNJ = 8;    // labels per thread (8 * 256 >= 1968)
+
+__global__ void __launch_bounds__(256)
+policy_fc_softmax_kernel(const float* __restrict__ featp, const float* __restrict__ wk, const float* __restrict__ bk,
+                         const uint8_t* __restrict__ mask, float* __restrict__ policy, int batch, int kin,
+                         int n_labels) {
+  extern __shared__ float s_feat[];        // [PTM][kin]
+  __shared__ float s_red[8][PTM];
+  __shared__ float s_bcast[PTM];
+  const int b0 = blockIdx.x * PTM;
+  for (int i = threadIdx.x; i < PTM * kin; i += blockDim.x) {
+    const int m = i / kin, k = i - m * kin;
+    s_feat[i] = (b0 + m < batch) ? featp[static_cast<size_t>(b0 + m) * kin + k] : 0.0f;
+  }
+  __syncthreads();
+  float acc[PNJ][PTM];
+#pragma unroll
+  for (int j = 0; j < PNJ; ++j)
+#pragma unroll
+    for (int m = 0; m < PTM; ++m) acc[j][m] = 0.0f;
+  for (int k = 0; k < kin; ++k) {
+    float wv[PNJ];
+#pragma unroll
+    for (int j = 0; j < PNJ; ++j) {
+      const int n = threadIdx.x + j * 256;
+      wv[j] = n < n_labels ? __ldg(wk + static_cast<size_t>(k) * n_labels + n) : 0.0f;
+    }
+#pragma unroll
+    for (int m = 0; m < PTM; ++m) {
+      const float x = s_feat[m * kin + k];
+#pragma unroll
+      for (int j = 0; j < PNJ; ++j) acc[j][m] = fmaf(x, wv[j], acc[j][m]);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // bias, mask, running max
+  float mx[PTM];
+#pragma unroll
+  for (int m = 0; m < PTM; ++m) mx[m] = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < PNJ; ++j) {
+    const int n = threadIdx.x + j * 256;
+    const float bv = n < n_labels ? bk[n] : 0.0f;
+#pragma unroll
+    for (int m = 0; m < PTM; ++m) {
+      bool on = n < n_labels && b0 + m < batch;
+      if (on && mask) on = mask[static_cast<size_t>(b0 + m) * n_labels + n] != 0;
+      acc[j][m] = on ? acc[j][m] + bv : -INFINITY;
+      mx[m] = fmaxf(mx[m], acc[j][m]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < PTM; ++m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx[m] = fmaxf(mx[m], __shfl_xor_sync(0xffffffffu, mx[m], o));
+    if (lane == 0) s_red[warp][m] = mx[m];
+  }
+  __syncthreads();
+  if (threadIdx.x < PTM) {
+    float v = s_red[0][threadIdx.x];
+    for (int wi = 1; wi < 8; ++wi) v = fmaxf(v, s_red[wi][threadIdx.x]);
+    s_bcast[threadIdx.x] = v;
+  }
+  __syncthreads();
+  float sum[PTM];
+#pragma unroll
+  for (int m = 0; m < PTM; ++m) {
+    const float mm = s_bcast[m];
+    sum[m] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < PNJ; ++j) {
+      const float e = acc[j][m] == -INFINITY ? 0.0f : expf(acc[j][m] - mm);
+      acc[j][m] = e;
+      sum[m] += e;
+    }
+  }
+  __syncthreads();  // s_red reuse
+#pragma unroll
+  for (int m = 0; m < PTM; ++m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum[m] += __shfl_xor_sync(0xffffffffu, sum[m], o);
+    if (lane == 0) s_red[warp][m] = sum[m];
+  }
+  __syncthreads();
+  if (threadIdx.x < PTM) {
+    float v = 0.0f;
+    for (int wi = 0; wi < 8; ++wi) v += s_red[wi][threadIdx.x];
+    s_bcast[threadIdx.x] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < PTM; ++m) {
+    if (b0 + m >= batch) continue;
+    const float tot = s_bcast[m];
+    const float inv = tot > 0.0f ? 1.0f / tot : 0.0f;
+#pragma unroll
+    for (int j = 0; j < PNJ; ++j) {
+      const int n = threadIdx.x + j * 256;
+      if (n < n_labels) policy[static_cast<size_t>(b0 + m) * n_labels + n] = acc[j][m] * inv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Value head: Dense(value_fc, relu) -> Dense(1, tanh) (agent/model_chess.py:91-92).
+// One block = VTM positions; thread t owns hidden unit t (loops if value_fc > blockDim).
+// w1: [kin][hid], w2: [hid].
+// ------------------------------------------------------------------------------------------------
+constexpr int VTM = 8;
+
+__global__ void __launch_bounds__(256)
+value_fc_kernel(const float* __restrict__ featv, const float* __restrict__ w1, const float* __restrict__ b1,
+                const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ value, int batch,
+                int kin, int hid) {
+  extern __shared__ float s_fv[];  // [VTM][kin]
+  __shared__ float s_part[8][VTM];
+  const int b0 = blockIdx.x * VTM;
+  for (int i = threadIdx.x; i < VTM * kin; i += blockDim.x) {
+    const int m = i / kin, k = i - m * kin;
+    s_fv[i] = (b0 + m < batch) ? featv[static_cast<size_t>(b0 + m) * kin + k] : 0.0f;
+  }
+  __syncthreads();
+  float part[VTM];
+#pragma unroll
+  for (int m = 0; m < VTM; ++m) part[m] = 0.0f;
+  for (int h = threadIdx.x; h < hid; h += blockDim.x) {
+    float acc[VTM];
+#pragma unroll
+    for (int m = 0; m < VTM; ++m) acc[m] = 0.0f;
+    for (int k = 0; k < kin; ++k) {
+      const float wv = __ldg(w1 + static_cast<size_t>(k) * hid + h);
+#pragma unroll
+      for (int m = 0; m < VTM; ++m) acc[m] = fmaf(s_fv[m * kin + k], wv, acc[m]);
+    }
+    const float bv = b1[h], w2v = w2[h];
+#pragma unroll
+    for (int m = 0; m < VTM; ++m) part[m] = fmaf(fmaxf(acc[m] + bv, 0.0f), w2v, part[m]);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int m = 0; m < VTM; ++m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part[m] += __shfl_xor_sync(0xffffffffu, part[m], o);
+    if (lane == 0) s_part[warp][m] = part[m];
+  }
+  __syncthreads();
+  if (threadIdx.x < VTM && b0 + threadIdx.x < batch) {
+    float v = b2[0];
+    for (int wi = 0; wi < 8; ++wi) v += s_part[wi][threadIdx.x];
+    value[b0 + threadIdx.x] = tanhf(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PUCT, one warp per tree node (agent/player_chess.py:251-299).  IEEE binary64, one rounding per
+// operation in the reference's evaluation order (Python floats): explicit _rn intrinsics so that the
+// compiler cannot contract a*b+c into an FMA.
+// ------------------------------------------------------------------------------------------------
+// prior push (:267-275): tot = 1e-8 + sum (left to right) of P[idx(a)]; p_a = P[idx(a)] / tot
+__global__ void push_priors_kernel(const float* __restrict__ policy, int n_labels, const int* __restrict__ offsets,
+                                   int n_nodes, const int* __restrict__ label_index, double* __restrict__ priors) {
+  const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (node >= n_nodes) return;
+  const int beg = offsets[node], end = offsets[node + 1];
+  const float* row = policy + static_cast<size_t>(node) * n_labels;
+  // the sum must be sequential to match the reference bit for bit; every lane computes it
+  // redundantly from L1-resident values (<= 218 edges) instead of shuffling a serial chain.
+  double tot = 1e-8;
+  for (int e = beg; e < end; ++e) tot = __dadd_rn(tot, static_cast<double>(row[label_index[e]]));
+  for (int e = beg + lane; e < end; e += 32) priors[e] = __ddiv_rn(static_cast<double>(row[label_index[e]]), tot);
+}
+
+// select (:277-299): b = q + c_puct * p_ * sqrt(sum_n + 1) / (1 + n); first strict maximum from -999
+__global__ void puct_select_kernel(const int* __restrict__ offsets, int n_nodes, const int* __restrict__ n,
+                                   const double* __restrict__ q, const double* __restrict__ p,
+                                   const int* __restrict__ sum_n, const double* __restrict__ noise,
+                                   const uint8_t* __restrict__ is_root, double c_puct, double eps,
+                                   int* __restrict__ best_edge) {
+  const int node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (node >= n_nodes) return;
+  const int beg = offsets[node], end = offsets[node + 1];
+  const double xx = __dsqrt_rn(static_cast<double>(sum_n[node] + 1));
+  const bool root = noise != nullptr && is_root != nullptr && is_root[node] != 0;
+  const double one_minus_eps = __dsub_rn(1.0, eps);
+  double best_s = -999.0;
+  int best_i = 0x7fffffff;
+  for (int e = beg + lane; e < end; e += 32) {
+    double p_ = p[e];
+    if (root) p_ = __dadd_rn(__dmul_rn(one_minus_eps, p_), __dmul_rn(eps, noise[e]));
+    const double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, p_), xx), static_cast<double>(1 + n[e]));
+    const double s = __dadd_rn(q[e], u);
+    if (s > best_s) {  // ascending e within a lane: strict '>' keeps the first maximum
+      best_s = s;
+      best_i = e - beg;
+    }
+  }
+  // warp argmax, ties broken towards the smaller edge index (= the reference's first maximum)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double os = __shfl_xor_sync(0xffffffffu, best_s, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (os > best_s || (os == best_s && oi < best_i)) {
+      best_s = os;
+      best_i = oi;
+    }
+  }
+  if (lane == 0) best_edge[node] = best_i == 0x7fffffff ? -1 : best_i;
+}
+
+}  // namespace caz

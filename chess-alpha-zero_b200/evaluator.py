@@ -1,0 +1,197 @@
+"""The object that stands where ``ChessModel.model`` (a Keras Model) stands in the reference.
+
+``Evaluator.predict_on_batch(data)`` has the contract of the one Keras call on the hot path,
+    policy_ary, value_ary = self.agent_model.model.predict_on_batch(data)
+(/root/reference/src/chess_zero/agent/api_chess.py:66-67): float32 (B,18,8,8) in, [float32 (B,1968),
+float32 (B,1)] out, rows in request order.  Everything between is the sm_100a library.
+"""
+import ctypes
+import threading
+
+import numpy as np
+
+from . import _lib
+from .keras_graph import parse_config
+
+_PRECISIONS = {"bf16": _lib.PRECISION_BF16, "fp32": _lib.PRECISION_FP32}
+
+
+class Evaluator:
+    def __init__(self, keras_config, weights, device=0, precision="bf16", max_batch=4096):
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        self._lib = _lib.load()
+        self.keras_config = keras_config
+        self.arch, self.weight_order = parse_config(keras_config)
+        self.precision = precision
+        self.device = int(device)
+        self._lock = threading.Lock()          # one in-flight call per handle (ABI contract)
+        self._handle = ctypes.c_void_p()
+        tensors, keep = self._pack(weights)
+        rc = self._lib.caz_create(ctypes.byref(self.arch), tensors, len(keep), self.device,
+                                  _PRECISIONS[precision], int(max_batch), ctypes.byref(self._handle))
+        _lib.check(None, rc)
+        self.max_batch = int(max_batch)
+        self.n_labels = int(self.arch.n_labels)
+        self.input_planes = int(self.arch.input_planes)
+
+    # -- weights ---------------------------------------------------------------------------------
+    def _pack(self, weights):
+        keep = []
+        for name in self.weight_order:
+            if name not in weights:
+                raise KeyError(f"weight {name} missing")
+            keep.append(np.ascontiguousarray(weights[name], dtype=np.float32))
+        arr = (_lib.Tensor * len(keep))()
+        for i, a in enumerate(keep):
+            arr[i].data = a.ctypes.data
+            arr[i].numel = a.size
+        return arr, keep
+
+    def reload(self, weights):
+        """Swap the weight set in place; pipes and handles stay open (lib/model_helper.py:26-41)."""
+        tensors, keep = self._pack(weights)
+        with self._lock:
+            _lib.check(self._handle, self._lib.caz_reload(self._handle, tensors, len(keep)))
+
+    # -- the operator ----------------------------------------------------------------------------
+    def predict_on_batch(self, data, legal_mask=None):
+        x = np.ascontiguousarray(data, dtype=np.float32)
+        if x.ndim != 4 or x.shape[1:] != (self.input_planes, 8, 8):
+            raise ValueError(f"expected (B,{self.input_planes},8,8) float32 planes, got {x.shape}")
+        b = x.shape[0]
+        policy = np.empty((b, self.n_labels), np.float32)
+        value = np.empty((b, 1), np.float32)
+        flags, mask = 0, None
+        if legal_mask is not None:
+            mask = _lib.as_array(legal_mask, np.uint8, (b, self.n_labels))
+            flags = _lib.EVAL_MASKED_SOFTMAX
+        with self._lock:
+            rc = self._lib.caz_eval(self._handle, _lib.ptr(x), b, _lib.ptr(policy), _lib.ptr(value),
+                                    _lib.ptr(mask), flags)
+            _lib.check(self._handle, rc)
+        return [policy, value]
+
+    def predict_into(self, planes, policy, value, legal_mask=None):
+        """Same call on caller-owned (ideally pinned) buffers: no allocation, no copies on the host."""
+        b = planes.shape[0]
+        flags = _lib.EVAL_MASKED_SOFTMAX if legal_mask is not None else 0
+        with self._lock:
+            rc = self._lib.caz_eval(self._handle, _lib.ptr(planes), b, _lib.ptr(policy), _lib.ptr(value),
+                                    _lib.ptr(legal_mask), flags)
+            _lib.check(self._handle, rc)
+
+    def predict_records(self, records, legal_mask=None):
+        """Board records (68 B each, see encoder.fen_to_record) in; the encoder runs on the device."""
+        r = _lib.as_array(records, np.uint8)
+        if r.ndim != 2 or r.shape[1] != _lib.RECORD_BYTES:
+            raise ValueError("records must be uint8 (B, 68)")
+        b = r.shape[0]
+        policy = np.empty((b, self.n_labels), np.float32)
+        value = np.empty((b, 1), np.float32)
+        flags, mask = 0, None
+        if legal_mask is not None:
+            mask = _lib.as_array(legal_mask, np.uint8, (b, self.n_labels))
+            flags = _lib.EVAL_MASKED_SOFTMAX
+        with self._lock:
+            rc = self._lib.caz_eval_records(self._handle, _lib.ptr(r), b, _lib.ptr(policy), _lib.ptr(value),
+                                            _lib.ptr(mask), flags)
+            _lib.check(self._handle, rc)
+        return [policy, value]
+
+    def eval_device(self, d_planes_ptr, batch, d_policy_ptr, d_value_ptr, d_mask_ptr=None):
+        """Raw device pointers (ints); enqueues on the handle's stream, no synchronisation."""
+        flags = _lib.EVAL_MASKED_SOFTMAX if d_mask_ptr else 0
+        with self._lock:
+            rc = self._lib.caz_eval_device(self._handle, ctypes.c_void_p(d_planes_ptr), int(batch),
+                                           ctypes.c_void_p(d_policy_ptr), ctypes.c_void_p(d_value_ptr),
+                                           ctypes.c_void_p(d_mask_ptr) if d_mask_ptr else None, flags)
+            _lib.check(self._handle, rc)
+
+    def sync(self):
+        _lib.check(self._handle, self._lib.caz_sync(self._handle))
+
+    # -- encoder / PUCT (same device, same stream) -----------------------------------------------
+    def encode(self, records):
+        r = _lib.as_array(records, np.uint8)
+        if r.ndim != 2 or r.shape[1] != _lib.RECORD_BYTES:
+            raise ValueError("records must be uint8 (B, 68)")
+        planes = np.empty((r.shape[0], 18, 8, 8), np.float32)
+        with self._lock:
+            _lib.check(self._handle, self._lib.caz_encode(self._handle, _lib.ptr(r), r.shape[0], _lib.ptr(planes)))
+        return planes
+
+    def push_priors(self, policy, offsets, label_index):
+        pol = _lib.as_array(policy, np.float32)
+        off = _lib.as_array(offsets, np.int32)
+        idx = _lib.as_array(label_index, np.int32)
+        n_nodes = off.size - 1
+        if pol.shape != (n_nodes, pol.shape[-1]):
+            raise ValueError("policy must be (n_nodes, n_labels)")
+        out = np.empty(idx.size, np.float64)
+        with self._lock:
+            rc = self._lib.caz_push_priors(self._handle, _lib.ptr(pol), pol.shape[1], _lib.ptr(off), n_nodes,
+                                           _lib.ptr(idx), _lib.ptr(out))
+            _lib.check(self._handle, rc)
+        return out
+
+    def puct_select(self, offsets, n, q, p, sum_n, c_puct, noise=None, is_root=None, noise_eps=0.0):
+        off = _lib.as_array(offsets, np.int32)
+        n_nodes = off.size - 1
+        n_ = _lib.as_array(n, np.int32)
+        q_ = _lib.as_array(q, np.float64)
+        p_ = _lib.as_array(p, np.float64)
+        sn = _lib.as_array(sum_n, np.int32, (n_nodes,))
+        nz = None if noise is None else _lib.as_array(noise, np.float64)
+        rt = None if is_root is None else _lib.as_array(is_root, np.uint8, (n_nodes,))
+        best = np.empty(n_nodes, np.int32)
+        with self._lock:
+            rc = self._lib.caz_puct_select(self._handle, _lib.ptr(off), n_nodes, _lib.ptr(n_), _lib.ptr(q_),
+                                           _lib.ptr(p_), _lib.ptr(sn), _lib.ptr(nz), _lib.ptr(rt), float(c_puct),
+                                           float(noise_eps), _lib.ptr(best))
+            _lib.check(self._handle, rc)
+        return best
+
+    def debug_conv_layer(self, layer, x_nhwc, residual=None):
+        """Test hook: one conv layer (0 = stem, then conv1/conv2 per block) through the build's real kernel."""
+        x = _lib.as_array(x_nhwc, np.float32)
+        b = x.shape[0]
+        res = None if residual is None else _lib.as_array(residual, np.float32, (b, 64, self.arch.filters))
+        out = np.empty((b, 64, self.arch.filters), np.float32)
+        with self._lock:
+            rc = self._lib.caz_debug_conv_layer(self._handle, int(layer), _lib.ptr(x), _lib.ptr(res), b, _lib.ptr(out))
+            _lib.check(self._handle, rc)
+        return out
+
+    # -- measurement -----------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return self._lib.caz_stream(self._handle)
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.caz_kernel_launches(self._handle))
+
+    @property
+    def weight_bytes(self):
+        return int(self._lib.caz_weight_bytes(self._handle))
+
+    def profile(self, enable=True):
+        _lib.check(self._handle, self._lib.caz_profile(self._handle, 1 if enable else 0))
+
+    def profile_read(self, reset=True):
+        ms = (ctypes.c_float * _lib.STAGES)()
+        n = (ctypes.c_int64 * _lib.STAGES)()
+        _lib.check(self._handle, self._lib.caz_profile_read(self._handle, ms, n, 1 if reset else 0))
+        return {name: {"ms": float(ms[i]), "launches": int(n[i])} for i, name in enumerate(_lib.STAGE_NAMES)}
+
+    def close(self):
+        if getattr(self, "_handle", None) and self._handle.value:
+            self._lib.caz_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass

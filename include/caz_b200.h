@@ -1,0 +1,181 @@
+/*
+ * caz_b200.h -- C ABI of the B200 (sm_100a) policy/value evaluator for chess-alpha-zero.
+ *
+ * This is the drop-in boundary for ONE path of the reference: the batched network
+ * evaluation that ChessModelAPI._predict_batch_worker performs with
+ *     policy_ary, value_ary = self.agent_model.model.predict_on_batch(data)
+ * (reference src/chess_zero/agent/api_chess.py:66-67), plus the two small kernels
+ * either side of it that north_star names: the input-plane encoder
+ * (src/chess_zero/env/chess_env.py:231-348) and PUCT select
+ * (src/chess_zero/agent/player_chess.py:251-299).
+ *
+ * Plain C types only: no torch, no Python objects, no exceptions across the boundary.
+ * Every entry point returns an int status (0 = CAZ_OK); text for the last failure is
+ * available from caz_last_error().  Buffers are caller-owned; one in-flight call per handle
+ * (the reference has exactly one prediction_worker thread per model, api_chess.py:37-39);
+ * several handles per process are fine (evaluate.py runs two models).
+ *
+ * There is no CPU fallback anywhere behind this header.
+ */
+#ifndef CAZ_B200_H
+#define CAZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAZ_ABI_VERSION 1
+
+/* status codes */
+#define CAZ_OK 0
+#define CAZ_ERR_INVALID 1     /* bad argument / unsupported architecture        */
+#define CAZ_ERR_CUDA 2        /* CUDA runtime or driver error (text in last_error) */
+#define CAZ_ERR_NO_DEVICE 3   /* no sm_100 device visible                       */
+#define CAZ_ERR_KERNEL 4      /* a kernel watchdog fired (pipeline never completed) */
+
+/* numeric builds (BASELINE.json north_star: "fp32-accumulate build" and "bf16 build") */
+#define CAZ_PRECISION_BF16 0  /* bf16 operands on tcgen05 tensor cores, fp32 TMEM accumulators, fp32 heads */
+#define CAZ_PRECISION_FP32 1  /* fp32 operands and accumulation on the CUDA cores (1e-4 parity build)      */
+
+/* eval flags */
+#define CAZ_EVAL_DEFAULT 0
+#define CAZ_EVAL_MASKED_SOFTMAX 1 /* legal_mask given: softmax over mask!=0 entries only, 0 elsewhere */
+
+#define CAZ_PLANES 18
+#define CAZ_SQUARES 64
+#define CAZ_PLANE_FLOATS (CAZ_PLANES * CAZ_SQUARES) /* 1152 floats = one (18,8,8) observation */
+#define CAZ_RECORD_BYTES 68                         /* compact board record, see caz_encode   */
+
+typedef struct caz_handle caz_handle;
+
+/*
+ * Network architecture, as read from the Keras Model.get_config() JSON that
+ * ChessModel.load feeds to Model.from_config (model_chess.py:144-145); graph
+ * shape per ChessModel.build/_build_residual_block (model_chess.py:57-111).
+ */
+typedef struct caz_arch {
+  int32_t input_planes;   /* 18  (InputLayer batch_input_shape[1])              */
+  int32_t stem_kernel;    /* 5   (cnn_first_filter_size; 3 in the shipped JSON) */
+  int32_t filters;        /* 256 (cnn_filter_num)                               */
+  int32_t res_blocks;     /* 7   (res_layer_num)                                */
+  int32_t block_kernel;   /* 3   (cnn_filter_size)                              */
+  int32_t policy_filters; /* 2                                                  */
+  int32_t value_filters;  /* 4   (1 in the shipped JSON)                        */
+  int32_t value_fc;       /* 256 (value_fc_size)                                */
+  int32_t n_labels;       /* 1968 (Config.n_labels, config.py:143-146)          */
+  float bn_epsilon;       /* 1e-3 (BatchNormalization epsilon in the JSON)      */
+} caz_arch;
+
+/*
+ * One fp32 tensor in Keras layout, exactly as Keras stores it in the weight file:
+ * Conv2D kernel (kh, kw, Cin, Cout); Dense kernel (in, out) and bias (out);
+ * BatchNormalization gamma, beta, moving_mean, moving_variance (C each).
+ */
+typedef struct caz_tensor {
+  const float* data;
+  int64_t numel;
+} caz_tensor;
+
+/*
+ * Tensor order expected by caz_create / caz_reload (graph order of model_chess.py:62-92):
+ *   stem:      kernel, gamma, beta, mean, var
+ *   block i:   conv1 kernel, bn1 gamma, beta, mean, var, conv2 kernel, bn2 gamma, beta, mean, var
+ *   policy:    conv kernel, gamma, beta, mean, var, dense kernel, dense bias
+ *   value:     conv kernel, gamma, beta, mean, var, dense1 kernel, dense1 bias, dense2 kernel, dense2 bias
+ * => 5 + 10*res_blocks + 7 + 9 tensors.  BatchNorm is folded into the convolutions here,
+ * in fp32, on the host side of this library (w' = w*gamma*rsqrt(var+eps), b' = beta - mean*that).
+ */
+
+/* Replaces ChessModel.build/.load (model_chess.py:57-94,121-153): materialise the network on `device`.
+ * max_batch bounds the positions one device pass holds (larger eval calls are chunked). */
+int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensors, int32_t device,
+               int32_t precision, int32_t max_batch, caz_handle** out);
+
+/* Replaces the weight swap of reload_best_model_weight_if_changed (lib/model_helper.py:26-41):
+ * same architecture, new tensors; pipes/handles stay open. */
+int caz_reload(caz_handle* h, const caz_tensor* tensors, int32_t n_tensors);
+
+void caz_destroy(caz_handle* h);
+
+/* Replaces model.predict_on_batch(data) (api_chess.py:67).
+ *   planes : host float32 [batch][18][8][8], C-contiguous (api_chess.py:66)
+ *   policy : host float32 [batch][n_labels]   (softmax; rows sum to 1)
+ *   value  : host float32 [batch]             (tanh)
+ *   legal_mask : NULL, or host uint8 [batch][n_labels] used with CAZ_EVAL_MASKED_SOFTMAX
+ * Host<->device copies and the stream synchronisation are inside the call. batch == 0 is a no-op. */
+int caz_eval(caz_handle* h, const float* planes, int32_t batch, float* policy, float* value,
+             const uint8_t* legal_mask, uint32_t flags);
+
+/* Same computation with every buffer already resident on the handle's device; enqueues on the
+ * handle's stream and returns without synchronising (caz_sync waits). batch <= max_batch. */
+int caz_eval_device(caz_handle* h, const float* d_planes, int32_t batch, float* d_policy, float* d_value,
+                    const uint8_t* d_legal_mask, uint32_t flags);
+
+/* Same, but from compact board records (see caz_encode): the encoder kernel writes the input planes
+ * on the device, so only 68 bytes per position cross PCIe. records: host uint8 [batch][68]. */
+int caz_eval_records(caz_handle* h, const uint8_t* records, int32_t batch, float* policy, float* value,
+                     const uint8_t* legal_mask, uint32_t flags);
+
+int caz_sync(caz_handle* h);
+
+/* Replaces canon_input_planes (env/chess_env.py:231-348) for a batch of positions.
+ * record layout (68 bytes): [0..63] square codes in FEN text order (rank 8 first, file a..h) of the
+ * position as written: 0 empty, 1..12 = index into "KQRBNPkqrbnp" + 1; [64] bit0 black to move,
+ * bits1..4 castling K,Q,k,q as written; [65] en-passant square (8-rank)*8+file or 255; [66..67]
+ * halfmove clock, little endian.  planes: host float32 [batch][18][8][8], bit-exact with the reference. */
+int caz_encode(caz_handle* h, const uint8_t* records, int32_t batch, float* planes);
+
+/* Replaces the prior push of select_action_q_and_u (player_chess.py:267-275) for many nodes at once.
+ *   policy      : host float32 [n_nodes][n_labels]  (one network policy row per node)
+ *   offsets     : host int32 [n_nodes+1], CSR offsets into the edge arrays
+ *   label_index : host int32 [n_edges], move label of each legal edge (self.move_lookup[mov])
+ *   priors      : host float64 [n_edges] out: P[idx] / (1e-8 + sum of the node's P[idx], left to right) */
+int caz_push_priors(caz_handle* h, const float* policy, int32_t n_labels, const int32_t* offsets,
+                    int32_t n_nodes, const int32_t* label_index, double* priors);
+
+/* Replaces the scoring loop of select_action_q_and_u (player_chess.py:277-299), one warp per node.
+ *   n, q, p   : host int32 / float64 / float64 [n_edges] (ActionStats.n, .q, .p; player_chess.py:33-55)
+ *   sum_n     : host int32 [n_nodes] (VisitStats.sum_n)
+ *   noise     : NULL or host float64 [n_edges], Dirichlet draw for nodes with is_root[i] != 0
+ *   is_root   : NULL or host uint8 [n_nodes]
+ *   best_edge : host int32 [n_nodes] out: index WITHIN the node of the first maximum of
+ *               q + c_puct*p*sqrt(sum_n+1)/(1+n)  (strict '>' from -999, so -1 for an empty node) */
+int caz_puct_select(caz_handle* h, const int32_t* offsets, int32_t n_nodes, const int32_t* n, const double* q,
+                    const double* p, const int32_t* sum_n, const double* noise, const uint8_t* is_root,
+                    double c_puct, double noise_eps, int32_t* best_edge);
+
+/* --- introspection / measurement ------------------------------------------------------------ */
+const char* caz_last_error(const caz_handle* h); /* h == NULL: last error of a failed caz_create */
+int32_t caz_abi_version(void);
+int32_t caz_max_batch(const caz_handle* h);
+int32_t caz_precision(const caz_handle* h);
+void* caz_stream(const caz_handle* h);            /* cudaStream_t the handle launches on */
+int64_t caz_kernel_launches(const caz_handle* h); /* kernels this handle has launched so far */
+int64_t caz_weight_bytes(const caz_handle* h);    /* folded device weight set, bytes */
+
+/* Per-stage device timing of the forward pass (CUDA events on the handle's stream).
+ * stage ids: 0 input pack, 1 stem conv, 2 residual tower convs, 3 heads. After caz_profile(h,1),
+ * every eval accumulates; caz_profile_read returns accumulated milliseconds and launch counts. */
+#define CAZ_STAGES 4
+int caz_profile(caz_handle* h, int32_t enable);
+int caz_profile_read(caz_handle* h, float* ms_per_stage, int64_t* launches_per_stage, int32_t reset);
+
+/* Test hook: run ONE convolution layer of the installed network (0 = stem, 1.. = conv1/conv2 of each
+ * residual block, in order) on caller-supplied NHWC activations, through the build's real kernel.
+ *   in       : host float32 [batch][64][cin]   (cin = input_planes for layer 0, else filters)
+ *   residual : NULL or host float32 [batch][64][filters]
+ *   out      : host float32 [batch][64][filters] = relu(conv(in) * bn_scale + bn_shift (+ residual))
+ * In the bf16 build inputs are rounded to bf16 on the way in and the bf16 result is widened on the way out. */
+int caz_debug_conv_layer(caz_handle* h, int32_t layer, const float* in, const float* residual, int32_t batch,
+                         float* out);
+
+/* Pinned host memory for callers that want true async DMA (numpy arrays can wrap it). */
+void* caz_host_alloc(int64_t bytes);
+void caz_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAZ_B200_H */

@@ -1,0 +1,256 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+Needs a B200: run with ``-m gpu``.  Tolerances are north_star's: fp32 build <= 1e-4 max-abs on policy and
+value; bf16 build <= 2e-2 on both with the legal-masked argmax identical on >= 99 % of positions; input
+planes, prior push and PUCT select bit-exact."""
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import chess_alpha_zero_b200 as caz
+from chess_alpha_zero_b200 import keras_graph
+from oracle import encoder as oenc
+from oracle import network as onet
+from oracle import puct as opuct
+from oracle import weights as oweights
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4      # north_star: fp32-accumulate build
+BF16_TOL = 2e-2      # north_star: bf16 build, policy probabilities and value
+ARGMAX_AGREE = 0.99  # north_star: bit-exact argmax move agreement
+
+
+def _planes(n, seed=5):
+    fens = oenc.KNOWN_ANSWER_FENS + oenc.synthetic_fens(max(n - 5, 0), seed)
+    return np.stack([oenc.canon_input_planes(f) for f in fens[:n]]), fens[:n]
+
+
+@pytest.fixture(scope="module")
+def net():
+    cfg = oweights.keras_config()                                  # 7 x 256, 5x5 stem, 4-filter value conv
+    w = oweights.synth_weights(cfg, seed=0, recipe="randomized")
+    x, fens = _planes(256)
+    want = onet.forward_graph(cfg, w, x)
+    return cfg, w, x, fens, want
+
+
+@pytest.fixture(scope="module")
+def ev_bf16(net):
+    ev = caz.Evaluator(net[0], net[1], precision="bf16", max_batch=512)
+    yield ev
+    ev.close()
+
+
+@pytest.fixture(scope="module")
+def ev_fp32(net):
+    ev = caz.Evaluator(net[0], net[1], precision="fp32", max_batch=256)
+    yield ev
+    ev.close()
+
+
+# ---- a1: encoder --------------------------------------------------------------------------------
+def test_encoder_bit_exact(ev_fp32, golden_dir):
+    meta = json.load(open(os.path.join(golden_dir, "encoder_fens.json")))
+    want = np.load(os.path.join(golden_dir, "encoder.npz"))["planes_u8"].astype(np.float32)
+    got = ev_fp32.encode(caz.encoder.fens_to_records(meta["fens"]))
+    assert got.dtype == np.float32 and got.tobytes() == want.tobytes()
+    fens = oenc.synthetic_fens(3000, seed=77)                      # > max_batch: exercises chunking
+    got = ev_fp32.encode(caz.encoder.fens_to_records(fens))
+    want = np.stack([oenc.canon_input_planes(f) for f in fens])
+    assert got.tobytes() == want.tobytes()
+    assert ev_fp32.encode(np.zeros((0, 68), np.uint8)).shape == (0, 18, 8, 8)
+
+
+# ---- a9: PUCT ------------------------------------------------------------------------------------
+def test_push_priors_and_select_bit_exact(ev_fp32, golden_dir):
+    g = np.load(os.path.join(golden_dir, "puct.npz"))
+    off = g["offsets"]
+    n_nodes = len(off) - 1
+    policy = np.zeros((n_nodes, 1968), np.float32)
+    for i in range(n_nodes):
+        s = slice(off[i], off[i + 1])
+        policy[i, g["label_idx"][s]] = g["policy_legal"][s]
+    pushed = ev_fp32.push_priors(policy, off, g["label_idx"])
+    assert pushed.dtype == np.float64 and np.array_equal(pushed, g["pushed"])
+    best = ev_fp32.puct_select(off, g["n"], g["q"], g["p"], g["sum_n"], float(g["c_puct"]), noise=g["noise"],
+                               is_root=g["is_root"], noise_eps=float(g["noise_eps"]))
+    assert np.array_equal(best, g["best"])
+    # full-size: 4096 nodes x up to 218 edges against the oracle loop, including empty nodes
+    rng = np.random.RandomState(3)
+    sizes = rng.randint(0, 219, size=4096)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    ne = int(off[-1])
+    n = rng.randint(0, 50, size=ne).astype(np.int32)
+    q = rng.uniform(-1, 1, size=ne)
+    p = rng.dirichlet([0.3] * 8, size=ne)[:, 0]
+    sum_n = np.asarray([n[off[i]:off[i + 1]].sum() for i in range(4096)], np.int32)
+    best = ev_fp32.puct_select(off, n, q, p, sum_n, 1.5)
+    for i in range(0, 4096, 7):
+        s = slice(off[i], off[i + 1])
+        assert best[i] == opuct.select(n[s], q[s], p[s], sum_n[i], 1.5), i
+
+
+# ---- a2/a3: one layer at a time -----------------------------------------------------------------
+def _ref_layer(cfg, w, layer, x_nhwc, res, bf16):
+    tower, _ = onet.fold_plan(cfg, w)
+    _, k, b = tower[layer]
+    kt = torch.from_numpy(k.astype(np.float32)).permute(3, 2, 0, 1).contiguous()
+    xt = torch.from_numpy(x_nhwc.reshape(-1, 8, 8, x_nhwc.shape[-1])).permute(0, 3, 1, 2).contiguous()
+    if bf16:
+        kt, xt = kt.bfloat16().float(), xt.bfloat16().float()
+    y = F.conv2d(xt.double(), kt.double(), padding=(k.shape[0] - 1) // 2) + torch.from_numpy(b).view(1, -1, 1, 1)
+    y = y.permute(0, 2, 3, 1).reshape(x_nhwc.shape[0], 64, -1)
+    if res is not None:
+        r = torch.from_numpy(res)
+        y = y + (r.bfloat16().float() if bf16 else r).double()
+    return torch.relu(y).numpy()
+
+
+@pytest.mark.parametrize("layer,batch,with_res", [(1, 2, False), (2, 5, True), (0, 3, False), (14, 64, True)])
+def test_single_conv_layer_bf16(net, ev_bf16, layer, batch, with_res):
+    cfg, w = net[0], net[1]
+    rng = np.random.RandomState(layer)
+    cin = 18 if layer == 0 else 256
+    x = rng.uniform(-1, 1, size=(batch, 64, cin)).astype(np.float32)
+    res = rng.uniform(-1, 1, size=(batch, 64, 256)).astype(np.float32) if with_res else None
+    got = ev_bf16.debug_conv_layer(layer, x, res)
+    want = _ref_layer(cfg, w, layer, x, res, bf16=True)
+    # exact-operand reference; what remains is fp32 accumulation order + one bf16 rounding of the output
+    assert np.abs(got - want).max() <= 2e-2 * max(1.0, np.abs(want).max()), np.abs(got - want).max()
+    assert np.abs(got - want).mean() <= 2e-3
+
+
+@pytest.mark.parametrize("layer,batch,with_res", [(0, 3, False), (1, 2, False), (2, 3, True)])
+def test_single_conv_layer_fp32(net, ev_fp32, layer, batch, with_res):
+    cfg, w = net[0], net[1]
+    rng = np.random.RandomState(layer)
+    cin = 18 if layer == 0 else 256
+    x = rng.uniform(-1, 1, size=(batch, 64, cin)).astype(np.float32)
+    res = rng.uniform(-1, 1, size=(batch, 64, 256)).astype(np.float32) if with_res else None
+    got = ev_fp32.debug_conv_layer(layer, x, res)
+    want = _ref_layer(cfg, w, layer, x, res, bf16=False)
+    assert np.abs(got - want).max() <= 1e-4
+
+
+# ---- config 1: whole network, 256 synthetic positions -------------------------------------------
+def test_fp32_build_matches_oracle(net, ev_fp32):
+    cfg, w, x, fens, (wp, wv) = net
+    p, v = ev_fp32.predict_on_batch(x)
+    assert p.shape == (256, 1968) and v.shape == (256, 1) and p.dtype == v.dtype == np.float32
+    assert np.abs(p - wp).max() <= FP32_TOL and np.abs(v - wv).max() <= FP32_TOL
+    assert np.allclose(p.sum(axis=1), 1, atol=1e-5)
+    # records in: the encoder runs on the device
+    p2, v2 = ev_fp32.predict_records(caz.encoder.fens_to_records(fens))
+    assert np.array_equal(p2, p) and np.array_equal(v2, v)
+
+
+def test_bf16_build_matches_oracle(net, ev_bf16):
+    cfg, w, x, fens, (wp, wv) = net
+    p, v = ev_bf16.predict_on_batch(x)
+    dp, dv = np.abs(p - wp).max(), np.abs(v - wv).max()
+    masks = onet.synthetic_legal_masks(len(x), seed=1)
+    agree = (onet.legal_masked_argmax(p, masks) == onet.legal_masked_argmax(wp, masks)).mean()
+    raw = (p.argmax(axis=1) == wp.argmax(axis=1)).mean()
+    print(f"bf16 vs fp32 oracle: max|dp|={dp:.3e} max|dv|={dv:.3e} masked argmax {agree:.4f} unmasked {raw:.4f}")
+    assert dp <= BF16_TOL and dv <= BF16_TOL
+    assert agree >= ARGMAX_AGREE
+    assert np.allclose(p.sum(axis=1), 1, atol=1e-5)
+    # tight check against the bf16-rounding emulation of the same arithmetic
+    ep, evv = onet.forward_bf16(cfg, w, x)
+    print(f"bf16 vs bf16 emulation: max|dp|={np.abs(p - ep).max():.3e} max|dv|={np.abs(v - evv).max():.3e}")
+    assert np.abs(p - ep).max() <= 5e-3 and np.abs(v - evv).max() <= 5e-3
+    p2, v2 = ev_bf16.predict_records(caz.encoder.fens_to_records(fens))
+    assert np.array_equal(p2, p) and np.array_equal(v2, v)
+
+
+def test_masked_softmax(net, ev_bf16):
+    cfg, w, x, fens, _ = net
+    masks = onet.synthetic_legal_masks(64, seed=2)
+    p, _ = ev_bf16.predict_on_batch(x[:64])
+    pm, _ = ev_bf16.predict_on_batch(x[:64], legal_mask=masks)
+    assert np.all(pm[masks == 0] == 0) and np.allclose(pm.sum(axis=1), 1, atol=1e-5)
+    want = np.where(masks != 0, p, 0)
+    want = want / want.sum(axis=1, keepdims=True)
+    assert np.abs(pm - want).max() <= 1e-5
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3, 16, 17, 48, 255])
+def test_ragged_batches_are_consistent(net, ev_bf16, batch):
+    x = net[2]
+    full_p, full_v = ev_bf16.predict_on_batch(x)
+    p, v = ev_bf16.predict_on_batch(x[:batch])
+    assert np.array_equal(p, full_p[:batch]) and np.array_equal(v, full_v[:batch])
+
+
+def test_empty_batch_and_chunking(net, ev_bf16):
+    p, v = ev_bf16.predict_on_batch(np.zeros((0, 18, 8, 8), np.float32))
+    assert p.shape == (0, 1968) and v.shape == (0, 1)
+    x = np.concatenate([net[2]] * 5)[:1100]                        # > max_batch (512): 3 chunks
+    p, v = ev_bf16.predict_on_batch(x)
+    base_p, base_v = ev_bf16.predict_on_batch(net[2])
+    assert np.array_equal(p[256:512], base_p) and np.array_equal(p[1024:1100], base_p[:76])
+
+
+def test_shipped_json_variant_and_reload(net):
+    cfg = oweights.keras_config(stem_k=3, value_filters=1)         # what data/model/model_best_config.json holds
+    w = oweights.synth_weights(cfg, seed=4, recipe="randomized")
+    x = net[2][:32]
+    wp, wv = onet.forward_graph(cfg, w, x)
+    ev = caz.Evaluator(cfg, w, precision="bf16", max_batch=64)
+    p, v = ev.predict_on_batch(x)
+    assert np.abs(p - wp).max() <= BF16_TOL and np.abs(v - wv).max() <= BF16_TOL
+    w2 = oweights.synth_weights(cfg, seed=5, recipe="randomized")  # hot reload, handle stays open
+    ev.reload(w2)
+    wp2, wv2 = onet.forward_graph(cfg, w2, x)
+    p2, v2 = ev.predict_on_batch(x)
+    assert np.abs(p2 - wp2).max() <= BF16_TOL and np.abs(v2 - wv2).max() <= BF16_TOL
+    assert np.abs(p2 - p).max() > 1e-4
+    ev.close()
+
+
+def test_keras_default_init_19_blocks(net):
+    cfg = oweights.keras_config(blocks=19)                          # config 5 architecture
+    w = oweights.synth_weights(cfg, seed=6, recipe="keras_default")
+    x = net[2][:16]
+    wp, wv = onet.forward_graph(cfg, w, x)
+    ev = caz.Evaluator(cfg, w, precision="bf16", max_batch=16)
+    p, v = ev.predict_on_batch(x)
+    assert np.abs(p - wp).max() <= BF16_TOL and np.abs(v - wv).max() <= BF16_TOL
+    ev.close()
+
+
+# ---- a7/a8: the pipe protocol, ours and the reference's own server class ------------------------
+def test_chessmodel_pipes_end_to_end(net, tmp_path):
+    cfg, w, x, fens, (wp, wv) = net
+    cpath, wpath = str(tmp_path / "model_best_config.json"), str(tmp_path / "model_best_weight.npz")
+    json.dump(cfg, open(cpath, "wt"))
+    keras_graph.save_weight_file(wpath, w)
+    model = caz.ChessModel(caz.Config("mini"), precision="bf16", max_batch=64)
+    assert model.load(cpath, wpath) and model.digest == caz.ChessModel.fetch_digest(wpath)
+    pipes = model.get_pipes(16)
+    results = {}
+
+    def client(i, pipe):
+        out = []
+        for j in range(i, 64, 16):
+            pipe.send(x[j])
+            p, v = pipe.recv()
+            out.append((j, p, v))
+        results[i] = out
+
+    ts = [threading.Thread(target=client, args=(i, p)) for i, p in enumerate(pipes)]
+    [t.start() for t in ts]
+    [t.join(timeout=60) for t in ts]
+    assert len(results) == 16
+    for out in results.values():
+        for j, p, v in out:
+            assert isinstance(v, float) and p.shape == (1968,) and p.dtype == np.float32
+            assert np.abs(p - wp[j]).max() <= BF16_TOL and abs(v - float(wv[j, 0])) <= BF16_TOL
+    assert model.api.positions == 64
+    model.api.stop()
+    model.model.close()
