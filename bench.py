@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Headline benchmark: positions/sec of the batched policy/value evaluation (7x256 net, batch 4096 per GPU).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A step = one forward pass over one batch of synthetic positions (random-init weights of the named
+architecture; there are no trained weights or datasets offline).  One process per GPU (torchrun sets
+RANK/LOCAL_RANK/WORLD_SIZE); games/positions are independent, so ranks share nothing on the data path
+(weak scaling, no collective); torch.distributed is used only for the barrier and the max-over-ranks time.
+
+JSON keys beyond the base contract:
+  value     device-resident throughput: inputs already in HBM, CUDA events on the evaluator's stream
+  e2e       the same metric through the public API (Evaluator.predict_into == predict_on_batch semantics) with
+            pinned HOST buffers: H2D of the planes and D2H of policy+value inside the timed region
+  roofline  the dominant kernel (3x3 implicit-GEMM conv): algorithmic FLOPs per launch / its mean launch time,
+            measured live with CUDA events around the tower stage of every timed step
+  cpu_baseline  the oracle (torch-CPU restatement of the Keras graph) on this box's host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "positions/sec (7x256, batch 4096)"
+UNIT = "positions/s"
+
+
+def flops_per_position(blocks=7, filters=256, stem_k=5, planes=18, pf=2, vf=4, vfc=256, labels=1968):
+    """2*Cin*k^2*Cout*64 per conv (zero-padded taps counted), Dense 2*in*out."""
+    macs = planes * stem_k * stem_k * filters * 64 + 2 * blocks * filters * 9 * filters * 64
+    macs += filters * pf * 64 + filters * vf * 64 + pf * 64 * labels + vf * 64 * vfc + vfc
+    return 2 * macs
+
+
+def conv3x3_flops_per_launch(batch, filters=256):
+    return 2 * 64 * batch * filters * 9 * filters
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d["hbm_gbs"], "source": "MEASURED_PEAKS.json"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        for t, line in self.lines:
+            if not (t0 <= t <= t1 + 0.2):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def synthetic_batch(batch, seed):
+    """Seeded legal-looking positions through the oracle's generator and this repo's own encoder path
+    (records -> planes is what the product does; planes are what predict_on_batch receives)."""
+    from oracle import encoder as oenc
+    base = np.stack([oenc.canon_input_planes(f) for f in oenc.synthetic_fens(256, seed=seed)])
+    reps = (batch + 255) // 256
+    return np.ascontiguousarray(np.tile(base, (reps, 1, 1, 1))[:batch])
+
+
+def network(blocks):
+    """Random-init weights of the named architecture (Keras default initialisers), seeded."""
+    from chess_alpha_zero_b200 import keras_graph
+    cfg = keras_graph.build_config(blocks=blocks)
+    return cfg, keras_graph.init_weights(cfg, seed=0)
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        import torch
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return world, rank, local
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def cpu_baseline(cfg, weights, planes, seconds=12.0):
+    """Oracle (port of the Keras graph, torch CPU fp32, all host cores) on a bounded sample of the workload."""
+    import torch
+    from oracle import network as onet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = planes[:256]
+    onet.forward_graph(cfg, weights, sample[:32])
+    best, t_end, reps = None, time.perf_counter() + seconds, 0
+    while time.perf_counter() < t_end or reps < 2:
+        t0 = time.perf_counter()
+        onet.forward_graph(cfg, weights, sample)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        reps += 1
+    return {"value": len(sample) / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(sample)} positions of the batch-4096 workload per pass, best of {reps} passes, "
+                      f"oracle.network.forward_graph (torch CPU fp32, {cores} threads)"}
+
+
+def run_reference(args, world, rank):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (Keras/TF are not
+    installable offline), all host threads, bounded sample per step.  Rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import network as onet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, weights = network(args.blocks)
+    sample_n = 256
+    planes = synthetic_batch(sample_n, seed=11)
+    for _ in range(args.warmup):
+        onet.forward_graph(cfg, weights, planes)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        onet.forward_graph(cfg, weights, planes)
+    dt = time.perf_counter() - t0
+    value = sample_n * args.steps / dt
+    sample = (f"{sample_n} positions per step (bounded sample of the batch-{args.batch} workload), "
+              f"oracle.network.forward_graph, torch CPU fp32, {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"7x256 policy/value net, 5x5 stem, batch {args.batch} (sampled {sample_n}/step)",
+                   "res_blocks": args.blocks, "sample_positions_per_step": sample_n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def latency_probe(ev, planes16, calls=1000):
+    """p50 of the host-visible call at batch 16 (pinned buffers), and of the device part (CUDA events)."""
+    import torch
+    from chess_alpha_zero_b200 import _lib
+    pin_x, pin_p, pin_v = _lib.PinnedArray((16, 18, 8, 8), np.float32), _lib.PinnedArray((16, 1968), np.float32), \
+        _lib.PinnedArray((16, 1), np.float32)
+    pin_x.array[:] = planes16
+    for _ in range(50):
+        ev.predict_into(pin_x.array, pin_p.array, pin_v.array)
+    host = []
+    for _ in range(calls):
+        t0 = time.perf_counter()
+        ev.predict_into(pin_x.array, pin_p.array, pin_v.array)
+        host.append(time.perf_counter() - t0)
+    stream = torch.cuda.ExternalStream(ev.stream)
+    d_x = torch.from_numpy(planes16).cuda()
+    d_p = torch.empty((16, 1968), dtype=torch.float32, device="cuda")
+    d_v = torch.empty((16,), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    dev = []
+    for _ in range(min(calls, 300)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ev.eval_device(d_x.data_ptr(), 16, d_p.data_ptr(), d_v.data_ptr())
+        e1.record(stream)
+        e1.synchronize()
+        dev.append(e0.elapsed_time(e1) * 1e-3)
+    q = lambda a, f: float(np.quantile(np.asarray(a), f) * 1e6)
+    return {"batch": 16, "calls": calls, "host_call_p50_us": q(host, 0.5), "host_call_p99_us": q(host, 0.99),
+            "device_p50_us": q(dev, 0.5), "device_p99_us": q(dev, 0.99),
+            "note": "host call = predict_on_batch-equivalent with pinned buffers incl. H2D+D2H+sync; pipe round trips excluded"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="positions per GPU per step")
+    ap.add_argument("--blocks", type=int, default=7, help="residual blocks (19 = config 5)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    world, rank, local = dist_setup(args.gpus)
+    if args.impl == "reference":
+        run_reference(args, world, rank)
+        return
+
+    import torch
+    import chess_alpha_zero_b200 as caz
+    from chess_alpha_zero_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    B = args.batch
+    cfg, weights = network(args.blocks)
+    ev = caz.Evaluator(cfg, weights, device=local, precision=args.precision, max_batch=B)
+    stream = torch.cuda.ExternalStream(ev.stream)
+
+    # inputs: NBUF distinct device batches (> L2 together with the 0.7 GB of activations a step streams)
+    NBUF = 8
+    host_batches = [synthetic_batch(B, seed=100 + rank * NBUF + i) for i in range(2)]
+    d_in = [torch.from_numpy(host_batches[i % 2]).cuda() for i in range(NBUF)]
+    d_pol = torch.empty((B, ev.n_labels), dtype=torch.float32, device="cuda")
+    d_val = torch.empty((B,), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+
+    def step(i):
+        ev.eval_device(d_in[i % NBUF].data_ptr(), B, d_pol.data_ptr(), d_val.data_ptr())
+
+    for i in range(args.warmup):
+        step(i)
+    ev.sync()
+    ev.profile(True)
+    ev.profile_read(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier(world)
+    torch.cuda.synchronize()
+    launches0 = ev.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    e1.synchronize()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    barrier(world)
+    launches = ev.kernel_launches - launches0
+    stages = ev.profile_read(reset=True)
+    ev.profile(False)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    dev_s = max_over_ranks(e0.elapsed_time(e1) * 1e-3, world)
+    value = world * B * args.steps / dev_s
+
+    # ---- e2e: host buffers in, host buffers out, through the public API -----------------------------
+    pin_x, pin_p, pin_v = _lib.PinnedArray((B, 18, 8, 8), np.float32), _lib.PinnedArray((B, ev.n_labels), np.float32), \
+        _lib.PinnedArray((B, 1), np.float32)
+    pin_x.array[:] = host_batches[0]
+    for _ in range(3):
+        ev.predict_into(pin_x.array, pin_p.array, pin_v.array)
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ev.predict_into(pin_x.array, pin_p.array, pin_v.array)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    barrier(world)
+    loss_like = float(pin_v.array.mean())          # the step's result is really read on the host
+    e2e = {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 18 * 64 * 4,
+           "d2h_bytes_per_step": B * (ev.n_labels + 1) * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
+           "api": "Evaluator.predict_into (predict_on_batch semantics, pinned host buffers)", "mean_value": loss_like}
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    tower = stages["tower"]
+    n_conv = max(tower["launches"], 1)
+    conv_ms = tower["ms"] / n_conv
+    achieved = conv3x3_flops_per_launch(B) / (conv_ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (3x3x256->256 implicit GEMM)", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step); "
+                               f"burst peak {peaks['bf16_tflops']}",
+                "flops_per_launch": conv3x3_flops_per_launch(B), "mean_launch_ms": conv_ms, "launches_timed": n_conv,
+                "whole_net_tflops": flops_per_position(args.blocks) * value / world / 1e12,
+                "whole_net_frac_of_peak": flops_per_position(args.blocks) * value / world / 1e12 / peak,
+                "stage_ms_per_step": {k: v["ms"] / args.steps for k, v in stages.items()}}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": f"{args.blocks}x256 policy/value net, 5x5 stem, batch {B} per GPU "
+                               f"(BASELINE.json configs[{1 if args.blocks == 7 else 4}])",
+                   "res_blocks": args.blocks, "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"replicas x{world}, positions sharded, no collective",
+                   "weights": "random-init (Keras default initialisers), seeded",
+                   "l2": f"inputs rotate over {NBUF} device batches; a step streams ~{1.9e-3 * B:.1f} GB of "
+                         "activations through HBM (>> 126 MB L2); the 17.4 MB weight set is meant to stay L2-resident"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "flops_per_position": flops_per_position(args.blocks), "host_cores": os.cpu_count(),
+    }
+    if not args.no_latency and world == 1:
+        out["latency_b16"] = latency_probe(ev, host_batches[0][:16].copy())
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline(cfg, weights, host_batches[0])
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()

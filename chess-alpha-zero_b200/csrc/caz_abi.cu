@@ -71,8 +71,11 @@ struct caz_handle {
         *vfc2_b = nullptr;
   void* in_act = nullptr;  // [cap][64][in_cpad]
   int in_cpad = 0;
-  void* act[3] = {nullptr, nullptr, nullptr};  // [cap][64][filters]
-  CUtensorMap tmap_in, tmap_act[3];
+  // [cap][64][filters] each.  fp32 build: three fp32 buffers in rotation.  Tensor-core build:
+  // act[0] = bf16 copy of the residual stream (A operand of conv1), act[1] = bf16 conv1 output
+  // (A operand of conv2), act[2] = the residual stream itself, kept in fp32.
+  void* act[3] = {nullptr, nullptr, nullptr};
+  CUtensorMap tmap_in, tmap_act[2];
   float *featp = nullptr, *featv = nullptr;
   // staging for the host-pointer entry points
   float *d_planes = nullptr, *d_policy = nullptr, *d_value = nullptr;
@@ -85,11 +88,15 @@ struct caz_handle {
   int64_t launches = 0;
   int64_t weight_bytes = 0;
   // profiling
-  bool profiling = false, prof_pending = false;
-  cudaEvent_t ev[CAZ_STAGES + 1] = {};
+  // one event set per forward pass while profiling; drained (without blocking the forward passes) on read
+  struct EvSet { cudaEvent_t ev[CAZ_STAGES + 1]; int64_t launches[CAZ_STAGES]; };
+  bool profiling = false;
+  std::vector<EvSet> ev_pool;
+  size_t ev_used = 0;
+  cudaEvent_t* ev = nullptr;  // set being recorded by the current forward
   float stage_ms[CAZ_STAGES] = {};
   int64_t stage_launches[CAZ_STAGES] = {};
-  int64_t pending_launches[CAZ_STAGES] = {};
+  int64_t* pending_launches = nullptr;
 };
 
 namespace {
@@ -277,8 +284,10 @@ int check_launch(caz_handle* h, const char* what) {
   return CAZ_OK;
 }
 
-int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_in, int in_stride, const void* residual,
-                void* out, int batch) {
+// residual is fp32 in both builds.  fp32 build: `out` is the fp32 output.  Tensor-core build: `out` is the
+// bf16 output (or null) and `out_f32` the fp32 residual-stream output (or null).
+int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_in, int in_stride, const float* residual,
+                void* out, float* out_f32, int batch) {
   const ConvLayer& L = h->convs[li];
   if (tensor_path(h)) {
     caz::tc::ConvArgs args;
@@ -291,8 +300,9 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
     args.n = L.cout;
     args.relu = 1;
     args.bias = L.bias;
-    args.residual = static_cast<const __nv_bfloat16*>(residual);
-    args.out = static_cast<__nv_bfloat16*>(out);
+    args.residual = residual;
+    args.out_f32 = out_f32;
+    args.out_bf16 = static_cast<__nv_bfloat16*>(out);
     args.err_flag = h->err_flag_dev;
     const int grid = args.num_tiles < h->num_sms ? args.num_tiles : h->num_sms;
     caz::tc::conv_tc_kernel<<<grid, caz::tc::THREADS, caz::tc::SMEM_BYTES, h->stream>>>(*tmap_in, L.tmap_w, args);
@@ -300,7 +310,7 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
   }
   const size_t smem = (size_t)(8 + L.k - 1) * (8 + L.k - 1) * L.cin * sizeof(float);
   const float* fin = static_cast<const float*>(in);
-  const float* fres = static_cast<const float*>(residual);
+  const float* fres = residual;
   float* fout = static_cast<float*>(out);
   const float* fw = static_cast<const float*>(L.w);
   switch (L.k) {
@@ -313,18 +323,33 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
   return check_launch(h, "conv_fp32_kernel");
 }
 
+// Picks the event set for this forward pass (no synchronisation).
 int prof_begin(caz_handle* h) {
+  h->ev = nullptr;
   if (!h->profiling) return CAZ_OK;
-  if (h->prof_pending) {
-    CU_TRY(h, cudaEventSynchronize(h->ev[CAZ_STAGES]));
+  if (h->ev_used == h->ev_pool.size()) {
+    caz_handle::EvSet set{};
+    for (auto& e : set.ev) CU_TRY(h, cudaEventCreate(&e));
+    h->ev_pool.push_back(set);
+  }
+  h->ev = h->ev_pool[h->ev_used].ev;
+  h->pending_launches = h->ev_pool[h->ev_used].launches;
+  h->ev_used++;
+  return CAZ_OK;
+}
+
+// Waits for the recorded forward passes and folds their stage times into the accumulators.
+int prof_drain(caz_handle* h) {
+  if (h->ev_used == 0) return CAZ_OK;
+  CU_TRY(h, cudaEventSynchronize(h->ev_pool[h->ev_used - 1].ev[CAZ_STAGES]));
+  for (size_t i = 0; i < h->ev_used; ++i)
     for (int s = 0; s < CAZ_STAGES; ++s) {
       float ms = 0;
-      CU_TRY(h, cudaEventElapsedTime(&ms, h->ev[s], h->ev[s + 1]));
+      CU_TRY(h, cudaEventElapsedTime(&ms, h->ev_pool[i].ev[s], h->ev_pool[i].ev[s + 1]));
       h->stage_ms[s] += ms;
-      h->stage_launches[s] += h->pending_launches[s];
+      h->stage_launches[s] += h->ev_pool[i].launches[s];
     }
-    h->prof_pending = false;
-  }
+  h->ev_used = 0;
   return CAZ_OK;
 }
 
@@ -335,7 +360,7 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
   const bool tcp = tensor_path(h);
   int rc;
   if ((rc = prof_begin(h))) return rc;
-  const bool prof = h->profiling;
+  const bool prof = h->ev != nullptr;
   int64_t l0 = h->launches;
   if (prof) CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
   // ---- stage 0: input pack (NCHW fp32 planes -> NHWC activations, channels zero-padded) ----
@@ -353,22 +378,29 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
   }
   if (prof) { CU_TRY(h, cudaEventRecord(h->ev[1], h->stream)); h->pending_launches[0] = h->launches - l0; l0 = h->launches; }
   // ---- stage 1: stem ----
-  if ((rc = launch_conv(h, 0, h->in_act, &h->tmap_in, h->in_cpad, nullptr, h->act[0], batch))) return rc;
+  float* xf = static_cast<float*>(h->act[2]);  // tensor-core build: fp32 residual stream
+  if ((rc = launch_conv(h, 0, h->in_act, &h->tmap_in, h->in_cpad, nullptr, h->act[0], tcp ? xf : nullptr, batch))) return rc;
   if (prof) { CU_TRY(h, cudaEventRecord(h->ev[2], h->stream)); h->pending_launches[1] = h->launches - l0; l0 = h->launches; }
   // ---- stage 2: residual tower ----
   int cur = 0;
   for (int blk = 0; blk < a.res_blocks; ++blk) {
+    if (tcp) {
+      // x (bf16 copy) -> conv1 -> y (bf16);  y -> conv2 (+ fp32 x) -> x in place (fp32) and its bf16 copy
+      if ((rc = launch_conv(h, 1 + 2 * blk, h->act[0], &h->tmap_act[0], a.filters, nullptr, h->act[1], nullptr, batch))) return rc;
+      if ((rc = launch_conv(h, 2 + 2 * blk, h->act[1], &h->tmap_act[1], a.filters, xf, h->act[0], xf, batch))) return rc;
+      continue;
+    }
     const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
-    if ((rc = launch_conv(h, 1 + 2 * blk, h->act[cur], &h->tmap_act[cur], a.filters, nullptr, h->act[t1], batch))) return rc;
-    if ((rc = launch_conv(h, 2 + 2 * blk, h->act[t1], &h->tmap_act[t1], a.filters, h->act[cur], h->act[t2], batch))) return rc;
+    if ((rc = launch_conv(h, 1 + 2 * blk, h->act[cur], nullptr, a.filters, nullptr, h->act[t1], nullptr, batch))) return rc;
+    if ((rc = launch_conv(h, 2 + 2 * blk, h->act[t1], nullptr, a.filters, static_cast<const float*>(h->act[cur]), h->act[t2], nullptr, batch))) return rc;
     cur = t2;
   }
   if (prof) { CU_TRY(h, cudaEventRecord(h->ev[3], h->stream)); h->pending_launches[2] = h->launches - l0; l0 = h->launches; }
   // ---- stage 3: heads ----
   const int pf = a.policy_filters, vf = a.value_filters;
   const size_t hsmem = (size_t)(pf + vf) * a.filters * sizeof(float);
-  if (tcp) caz::head_conv_kernel<__nv_bfloat16><<<batch, 256, hsmem, h->stream>>>(static_cast<const __nv_bfloat16*>(h->act[cur]), h->head_w, h->head_b, h->featp, h->featv, batch, a.filters, pf, vf);
-  else caz::head_conv_kernel<float><<<batch, 256, hsmem, h->stream>>>(static_cast<const float*>(h->act[cur]), h->head_w, h->head_b, h->featp, h->featv, batch, a.filters, pf, vf);
+  // both builds feed the heads from fp32 activations (tensor-core build: the fp32 residual stream)
+  caz::head_conv_kernel<float><<<batch, 256, hsmem, h->stream>>>(tcp ? xf : static_cast<const float*>(h->act[cur]), h->head_w, h->head_b, h->featp, h->featv, batch, a.filters, pf, vf);
   if ((rc = check_launch(h, "head_conv_kernel"))) return rc;
   caz::policy_fc_softmax_kernel<<<(batch + caz::PTM - 1) / caz::PTM, 256, (size_t)caz::PTM * pf * 64 * sizeof(float), h->stream>>>(
       h->featp, h->pfc_w, h->pfc_b, d_mask, d_policy, batch, pf * 64, a.n_labels);
@@ -376,7 +408,7 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
   caz::value_fc_kernel<<<(batch + caz::VTM - 1) / caz::VTM, 256, (size_t)caz::VTM * vf * 64 * sizeof(float), h->stream>>>(
       h->featv, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, d_value, batch, vf * 64, a.value_fc);
   if ((rc = check_launch(h, "value_fc_kernel"))) return rc;
-  if (prof) { CU_TRY(h, cudaEventRecord(h->ev[4], h->stream)); h->pending_launches[3] = h->launches - l0; h->prof_pending = true; }
+  if (prof) { CU_TRY(h, cudaEventRecord(h->ev[4], h->stream)); h->pending_launches[3] = h->launches - l0; }
   return CAZ_OK;
 }
 
@@ -422,7 +454,7 @@ void caz_destroy(caz_handle* h) {
                   h->d_mask, h->d_records, h->puct_buf};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
-  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& set : h->ev_pool) for (auto& e : set.ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -472,7 +504,6 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   } while (0)
   CREATE_TRY(cudaSetDevice(device));
   CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  for (auto& e : h->ev) CREATE_TRY(cudaEventCreate(&e));
   CREATE_TRY(cudaHostAlloc(&h->err_flag_host, sizeof(int), cudaHostAllocMapped));
   *h->err_flag_host = 0;
   CREATE_TRY(cudaHostGetDevicePointer(&h->err_flag_dev, h->err_flag_host, 0));
@@ -481,7 +512,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   const size_t cap = (size_t)max_batch;
   h->in_cpad = tcp ? 64 : a.input_planes;
   CREATE_TRY(cudaMalloc(&h->in_act, cap * 64 * h->in_cpad * esz));
-  for (int i = 0; i < 3; ++i) CREATE_TRY(cudaMalloc(&h->act[i], cap * 64 * a.filters * esz));
+  for (int i = 0; i < 3; ++i) CREATE_TRY(cudaMalloc(&h->act[i], cap * 64 * a.filters * (i == 2 ? 4 : esz)));
   CREATE_TRY(cudaMalloc(&h->featp, cap * a.policy_filters * 64 * 4));
   CREATE_TRY(cudaMalloc(&h->featv, cap * a.value_filters * 64 * 4));
   CREATE_TRY(cudaMalloc(&h->d_planes, cap * a.input_planes * 64 * 4));
@@ -492,7 +523,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   int rc;
   if (tcp) {
     if ((rc = make_act_tmap(h, &h->tmap_in, h->in_act, h->in_cpad))) return bail(rc);
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 2; ++i)
       if ((rc = make_act_tmap(h, &h->tmap_act[i], h->act[i], a.filters))) return bail(rc);
     CREATE_TRY(cudaFuncSetAttribute(caz::tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc::SMEM_BYTES));
   } else {
@@ -683,22 +714,20 @@ int caz_debug_conv_layer(caz_handle* h, int32_t layer, const float* in, const fl
     CU_TRY(h, cudaMalloc(&d_res, rows * F * 4));
     CU_TRY(h, cudaMemcpyAsync(d_res, residual, rows * F * 4, cudaMemcpyHostToDevice, h->stream));
   }
-  // stage into the handle's own activation buffers so the real tensor maps are exercised
-  void* a_in = layer == 0 ? h->in_act : h->act[0];
-  const CUtensorMap* tm = layer == 0 ? &h->tmap_in : &h->tmap_act[0];
+  // stage into the handle's own activation buffers so the real tensor maps and kernels are exercised:
+  // input -> in_act (stem) or act[1]; residual -> act[2] (fp32 in both builds); output -> act[0] (+ act[2])
+  void* a_in = layer == 0 ? h->in_act : h->act[1];
+  const CUtensorMap* tm = layer == 0 ? &h->tmap_in : &h->tmap_act[1];
   const int cpad = layer == 0 ? h->in_cpad : F;
   const unsigned gi = (unsigned)((rows * cpad + 255) / 256), go = (unsigned)((rows * F + 255) / 256);
-  if (tcp) {
-    caz::cast_pad_kernel<__nv_bfloat16><<<gi, 256, 0, h->stream>>>(d_in, (__nv_bfloat16*)a_in, rows, L.cin, cpad);
-    if (residual) caz::cast_pad_kernel<__nv_bfloat16><<<go, 256, 0, h->stream>>>(d_res, (__nv_bfloat16*)h->act[1], rows, F, F);
-  } else {
-    caz::cast_pad_kernel<float><<<gi, 256, 0, h->stream>>>(d_in, (float*)a_in, rows, L.cin, cpad);
-    if (residual) caz::cast_pad_kernel<float><<<go, 256, 0, h->stream>>>(d_res, (float*)h->act[1], rows, F, F);
-  }
+  if (tcp) caz::cast_pad_kernel<__nv_bfloat16><<<gi, 256, 0, h->stream>>>(d_in, (__nv_bfloat16*)a_in, rows, L.cin, cpad);
+  else caz::cast_pad_kernel<float><<<gi, 256, 0, h->stream>>>(d_in, (float*)a_in, rows, L.cin, cpad);
   if ((rc = check_launch(h, "cast_pad_kernel"))) return rc;
-  if ((rc = launch_conv(h, layer, a_in, tm, cpad, residual ? h->act[1] : nullptr, h->act[2], batch))) return rc;
-  if (tcp) caz::widen_kernel<__nv_bfloat16><<<go, 256, 0, h->stream>>>((const __nv_bfloat16*)h->act[2], d_out, rows * F);
-  else caz::widen_kernel<float><<<go, 256, 0, h->stream>>>((const float*)h->act[2], d_out, rows * F);
+  float* xf = static_cast<float*>(h->act[2]);
+  if (residual) CU_TRY(h, cudaMemcpyAsync(xf, d_res, rows * F * 4, cudaMemcpyDeviceToDevice, h->stream));
+  if ((rc = launch_conv(h, layer, a_in, tm, cpad, residual ? xf : nullptr, h->act[0], (tcp && (residual || layer == 0)) ? xf : nullptr, batch))) return rc;
+  if (tcp) caz::widen_kernel<__nv_bfloat16><<<go, 256, 0, h->stream>>>((const __nv_bfloat16*)h->act[0], d_out, rows * F);
+  else caz::widen_kernel<float><<<go, 256, 0, h->stream>>>((const float*)h->act[0], d_out, rows * F);
   if ((rc = check_launch(h, "widen_kernel"))) return rc;
   CU_TRY(h, cudaMemcpyAsync(out, d_out, rows * F * 4, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -714,9 +743,6 @@ int64_t caz_weight_bytes(const caz_handle* h) { return h ? h->weight_bytes : 0; 
 
 int caz_profile(caz_handle* h, int32_t enable) {
   if (!h) return CAZ_ERR_INVALID;
-  int rc;
-  if ((rc = set_device(h))) return rc;
-  if ((rc = prof_begin(h))) return rc;
   h->profiling = enable != 0;
   return CAZ_OK;
 }
@@ -725,11 +751,7 @@ int caz_profile_read(caz_handle* h, float* ms_per_stage, int64_t* launches_per_s
   if (!h) return CAZ_ERR_INVALID;
   int rc;
   if ((rc = set_device(h))) return rc;
-  const bool was = h->profiling;
-  h->profiling = true;
-  rc = prof_begin(h);
-  h->profiling = was;
-  if (rc) return rc;
+  if ((rc = prof_drain(h))) return rc;
   for (int s = 0; s < CAZ_STAGES; ++s) {
     if (ms_per_stage) ms_per_stage[s] = h->stage_ms[s];
     if (launches_per_stage) launches_per_stage[s] = h->stage_launches[s];

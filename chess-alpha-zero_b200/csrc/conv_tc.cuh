@@ -16,7 +16,8 @@
 //   warp 0   : TMA producer (one elected lane)      -> full[stage]
 //   warp 1   : tcgen05.mma issuer (one elected lane) -> empty[stage] (tcgen05.commit), tmem_full[acc]
 //   warp 2   : TMEM allocator / deallocator
-//   warps 4-7: epilogue: tcgen05.ld accumulators, + folded-BN bias, + residual, ReLU, bf16 store
+//   warps 4-7: epilogue: tcgen05.ld accumulators, + folded-BN bias, + fp32 residual, ReLU,
+//              fp32 store of the residual stream and/or bf16 store of the next layer's operand
 // Two TMEM accumulator stages (2 x 256 fp32 columns) let the epilogue of tile i overlap the MMAs of i+1.
 #pragma once
 #include <cuda_bf16.h>
@@ -48,9 +49,10 @@ struct ConvArgs {
   int kchunks;      // Cin_padded / 64
   int n;            // Cout, multiple of 16, <= 256
   int relu;
-  const float* bias;              // [n] folded BatchNorm shift
-  const __nv_bfloat16* residual;  // nullptr or [batch*64][n]
-  __nv_bfloat16* out;             // [batch*64][n]
+  const float* bias;        // [n] folded BatchNorm shift
+  const float* residual;    // nullptr or fp32 [batch*64][n]: the residual stream stays in fp32
+  float* out_f32;           // nullptr or fp32 [batch*64][n] (may alias residual: same element, same thread)
+  __nv_bfloat16* out_bf16;  // nullptr or bf16 [batch*64][n]: the next convolution's A operand
   int* err_flag;
 };
 
@@ -173,32 +175,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(args.bias + c0 + j);
           if (args.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(args.residual + row * args.n + c0);
+            const float4* rp = reinterpret_cast<const float4*>(args.residual + row * args.n + c0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 rv = __ldg(rp + q);
-              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                f[q * 8 + e * 2] += __uint_as_float(w[e] << 16);
-                f[q * 8 + e * 2 + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
-              }
+            for (int q = 0; q < 8; ++q) {
+              const float4 rv = rp[q];
+              f[q * 4 + 0] += rv.x;
+              f[q * 4 + 1] += rv.y;
+              f[q * 4 + 2] += rv.z;
+              f[q * 4 + 3] += rv.w;
             }
           }
           if (args.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           }
-          uint4* op = reinterpret_cast<uint4*>(args.out + row * args.n + c0);
+          if (args.out_f32) {
+            float4* op = reinterpret_cast<float4*>(args.out_f32 + row * args.n + c0);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t w[4];
+            for (int q = 0; q < 8; ++q) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+          }
+          if (args.out_bf16) {
+            uint4* op = reinterpret_cast<uint4*>(args.out_bf16 + row * args.n + c0);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
-              w[e] = *reinterpret_cast<const uint32_t*>(&b2);
+            for (int q = 0; q < 4; ++q) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
+                w[e] = *reinterpret_cast<const uint32_t*>(&b2);
+              }
+              op[q] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            op[q] = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
       }

@@ -161,7 +161,7 @@ def _bf16_round(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
-def forward_bf16(cfg, weights, planes, fp32_residual=False, return_logits=False):
+def forward_bf16(cfg, weights, planes, fp32_residual=False, return_logits=False, fp32_head_input=False):
     """bf16-operand / fp32-accumulate emulation of the tensor-core build (see module docstring)."""
     tower, heads = fold_plan(cfg, weights)
     with torch.no_grad():
@@ -177,9 +177,10 @@ def forward_bf16(cfg, weights, planes, fp32_residual=False, return_logits=False)
             if kind == "conv2":
                 y = y + skip
             x = torch.relu(y)
-            if not fp32_residual or kind != "conv2":
-                x = _bf16_round(x)
-        x = _bf16_round(x)
+            if not fp32_residual or kind == "conv1":
+                x = _bf16_round(x)   # with an fp32 residual stream only conv1's output is ever stored as bf16
+        if not fp32_head_input:
+            x = _bf16_round(x)
         B = x.shape[0]
         feats = x.permute(0, 2, 3, 1).reshape(B * 64, -1)
         out = {}

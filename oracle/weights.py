@@ -137,10 +137,10 @@ def synth_weights(cfg, seed=0, recipe="keras_default"):
                 W[f"{name}/bias:0"] = np.zeros((u,), np.float32)
         elif cls == "BatchNormalization":
             if recipe == "randomized":
-                W[f"{name}/gamma:0"] = rng.uniform(0.5, 1.5, size=(cin,)).astype(np.float32)
+                W[f"{name}/gamma:0"] = rng.uniform(0.75, 1.25, size=(cin,)).astype(np.float32)
                 W[f"{name}/beta:0"] = rng.normal(0, 0.1, size=(cin,)).astype(np.float32)
                 W[f"{name}/moving_mean:0"] = rng.normal(0, 0.1, size=(cin,)).astype(np.float32)
-                W[f"{name}/moving_variance:0"] = rng.uniform(0.5, 1.5, size=(cin,)).astype(np.float32)
+                W[f"{name}/moving_variance:0"] = rng.uniform(0.75, 1.25, size=(cin,)).astype(np.float32)
             else:
                 W[f"{name}/gamma:0"] = np.ones((cin,), np.float32)
                 W[f"{name}/beta:0"] = np.zeros((cin,), np.float32)
@@ -149,5 +149,12 @@ def synth_weights(cfg, seed=0, recipe="keras_default"):
     if recipe == "randomized":
         # keep tanh away from saturation and the policy away from uniform: rescale the two output layers
         W["value_out/kernel:0"] *= np.float32(0.25)
-        W["policy_out/kernel:0"] *= np.float32(4.0)
+        W["policy_out/kernel:0"] *= np.float32(2.0)
+        # Tower activations are post-ReLU (all >= 0), so a random 1x1 head filter has an output whose sign is
+        # nearly the same on every square and position; when it is negative the head's ReLU kills the feature
+        # and the policy degenerates to softmax(bias).  Zero-mean head filters keep about half the features alive.
+        for name in list(W):
+            if name.startswith(("policy_conv", "value_conv")) and name.endswith("/kernel:0"):
+                k = W[name]
+                W[name] = (k - k.mean(axis=2, keepdims=True)).astype(np.float32)
     return W
