@@ -38,7 +38,9 @@ constexpr int ACC_COLS = 256;  // TMEM columns per accumulator stage (N <= 256)
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;      // 32 KiB (N = 256 rows)
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int EPI_WARP_BYTES = 4096;                  // per-warp 32x32 fp32 transpose buffer
+constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES + 1024;  // + folded-BN bias (<= 256 floats)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 struct ConvArgs {
   int batch;        // positions
@@ -66,7 +68,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;
+  float* s_bias = reinterpret_cast<float*>(smem_epi + 4 * EPI_WARP_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
   uint64_t* full = bars;                            // [STAGES]
   uint64_t* empty = bars + STAGES;                  // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;          // [ACC_STAGES]
@@ -98,6 +102,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
     ptx::tmem_alloc(tmem_base_slot, ACC_STAGES * ACC_COLS);
     ptx::tmem_relinquish();
   }
+  if (threadIdx.x < args.n) s_bias[threadIdx.x] = args.bias[threadIdx.x];
   ptx::tcgen05_fence_before();
   __syncthreads();
   ptx::tcgen05_fence_after();
@@ -156,62 +161,114 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue =====================
+    // TMEM hands thread t row t of the tile (tcgen05.ld 32x32b), but a row is 1 KiB (fp32) / 512 B (bf16) of
+    // global memory, so row-per-thread global accesses touch 32 lines per instruction.  Every 32x32 block is
+    // therefore transposed through a 4 KiB per-warp staging buffer (XOR-swizzled, conflict-free both ways) so
+    // that each global load/store instruction covers whole 128-byte lines: 4 rows x 128 B (fp32) or
+    // 8 rows x 64 B (bf16) per instruction.  The fp32 residual chunk is prefetched one chunk ahead.
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    float4* stage = reinterpret_cast<float4*>(smem_epi + quad * EPI_WARP_BYTES);
+    uint4* stage_b = reinterpret_cast<uint4*>(stage);
+    const int fr = lane >> 3, fq = lane & 7;   // fp32 transposed mapping: row i*4+fr, float4 column fq
+    const int br = lane >> 2, bc = lane & 3;   // bf16 transposed mapping: row i*8+br, 16-byte column bc
     int acc = 0;
     uint32_t acc_phase = 0;
     const long total_rows = static_cast<long>(args.batch) * 64;
     for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+      const long row0 = static_cast<long>(tile) * BLOCK_M + quad * 32;
+      const long left = total_rows - row0;
+      const int rows_live = left >= 32 ? 32 : (left > 0 ? static_cast<int>(left) : 0);
+      float4 res_pf[8];
+      if (args.residual) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + fr;
+          res_pf[i] = r < rows_live ? *reinterpret_cast<const float4*>(args.residual + (row0 + r) * args.n + fq * 4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       ptx::mbar_wait(&tmem_full[acc], acc_phase, args.err_flag, ERR_EPILOGUE);
       ptx::tcgen05_fence_after();
-      const long row = static_cast<long>(tile) * BLOCK_M + quad * 32 + lane;
-      const bool live = row < total_rows;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS;
       for (int c0 = 0; c0 < args.n; c0 += 32) {
         uint32_t v[32];
         ptx::tmem_ld_32x32(taddr + c0, v);
-        ptx::tmem_ld_wait();
-        if (live) {
-          float f[32];
+        if (args.residual) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(args.bias + c0 + j);
-          if (args.residual) {
-            const float4* rp = reinterpret_cast<const float4*>(args.residual + row * args.n + c0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 rv = rp[q];
-              f[q * 4 + 0] += rv.x;
-              f[q * 4 + 1] += rv.y;
-              f[q * 4 + 2] += rv.z;
-              f[q * 4 + 3] += rv.w;
-            }
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + fr;
+            stage[r * 8 + (fq ^ (r & 7))] = res_pf[i];
           }
-          if (args.relu) {
+          __syncwarp();
+          if (c0 + 32 < args.n) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-          }
-          if (args.out_f32) {
-            float4* op = reinterpret_cast<float4*>(args.out_f32 + row * args.n + c0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
-          }
-          if (args.out_bf16) {
-            uint4* op = reinterpret_cast<uint4*>(args.out_bf16 + row * args.n + c0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
-                w[e] = *reinterpret_cast<const uint32_t*>(&b2);
-              }
-              op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + fr;
+              if (r < rows_live)
+                res_pf[i] = *reinterpret_cast<const float4*>(args.residual + (row0 + r) * args.n + c0 + 32 + fq * 4);
             }
           }
         }
+        ptx::tmem_ld_wait();
+        if (c0 + 32 >= args.n) {
+          // all accumulator columns of this tile are in registers: hand the TMEM stage back to the MMA warp
+          ptx::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+        if (args.residual) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 rv = stage[lane * 8 + (q ^ (lane & 7))];
+            f[q * 4 + 0] += rv.x;
+            f[q * 4 + 1] += rv.y;
+            f[q * 4 + 2] += rv.z;
+            f[q * 4 + 3] += rv.w;
+          }
+        }
+        if (args.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+        }
+        if (args.out_f32) {
+          // own row only: no cross-lane hazard with the residual reads above
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            stage[lane * 8 + (q ^ (lane & 7))] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + fr;
+            const float4 o = stage[r * 8 + (fq ^ (r & 7))];
+            if (r < rows_live) *reinterpret_cast<float4*>(args.out_f32 + (row0 + r) * args.n + c0 + fq * 4) = o;
+          }
+          __syncwarp();
+        }
+        if (args.out_bf16) {
+          if (args.residual && !args.out_f32) __syncwarp();  // residual rows fully read before reuse
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[c * 8 + e * 2], f[c * 8 + e * 2 + 1]);
+              w[e] = *reinterpret_cast<const uint32_t*>(&b2);
+            }
+            stage_b[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + br;
+            const uint4 o = stage_b[r * 4 + (bc ^ ((r >> 1) & 3))];
+            if (r < rows_live) *reinterpret_cast<uint4*>(args.out_bf16 + (row0 + r) * args.n + c0 + bc * 8) = o;
+          }
+          __syncwarp();
+        }
       }
-      ptx::tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
