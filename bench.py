@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -241,8 +241,8 @@ def latency_probe(ev, planes16, calls=1000):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="positions per GPU per step")
     ap.add_argument("--blocks", type=int, default=7, help="residual blocks (19 = config 5)")

@@ -80,6 +80,11 @@ struct caz_handle {
   // staging for the host-pointer entry points
   float *d_planes = nullptr, *d_policy = nullptr, *d_value = nullptr;
   uint8_t *d_mask = nullptr, *d_records = nullptr;
+  // second staging slot + copy streams: caz_eval pipelines H2D / forward / D2H over chunks of a large batch
+  float *d_planes2 = nullptr, *d_policy2 = nullptr, *d_value2 = nullptr;
+  uint8_t *d_mask2 = nullptr, *d_records2 = nullptr;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_in[2] = {}, ev_fwd[2] = {}, ev_out[2] = {};
   int* err_flag_host = nullptr;  // mapped pinned: readable even after a device trap
   int* err_flag_dev = nullptr;
   // PUCT scratch
@@ -287,7 +292,7 @@ int check_launch(caz_handle* h, const char* what) {
 // residual is fp32 in both builds.  fp32 build: `out` is the fp32 output.  Tensor-core build: `out` is the
 // bf16 output (or null) and `out_f32` the fp32 residual-stream output (or null).
 int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_in, int in_stride, const float* residual,
-                void* out, float* out_f32, int batch) {
+                void* out, float* out_f32, int batch, bool fuse_heads = false) {
   const ConvLayer& L = h->convs[li];
   if (tensor_path(h)) {
     caz::tc::ConvArgs args;
@@ -303,6 +308,12 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
     args.residual = residual;
     args.out_f32 = out_f32;
     args.out_bf16 = static_cast<__nv_bfloat16*>(out);
+    args.head_w = fuse_heads ? h->head_w : nullptr;
+    args.head_b = h->head_b;
+    args.featp = h->featp;
+    args.featv = h->featv;
+    args.pf = h->arch.policy_filters;
+    args.vf = h->arch.value_filters;
     args.err_flag = h->err_flag_dev;
     const int grid = args.num_tiles < h->num_sms ? args.num_tiles : h->num_sms;
     caz::tc::conv_tc_kernel<<<grid, caz::tc::THREADS, caz::tc::SMEM_BYTES, h->stream>>>(*tmap_in, L.tmap_w, args);
@@ -379,7 +390,10 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
   if (prof) { CU_TRY(h, cudaEventRecord(h->ev[1], h->stream)); h->pending_launches[0] = h->launches - l0; l0 = h->launches; }
   // ---- stage 1: stem ----
   float* xf = static_cast<float*>(h->act[2]);  // tensor-core build: fp32 residual stream
-  if ((rc = launch_conv(h, 0, h->in_act, &h->tmap_in, h->in_cpad, nullptr, h->act[0], tcp ? xf : nullptr, batch))) return rc;
+  // tensor-core build: the LAST convolution's epilogue also computes the heads' 1x1 convs (no activation store)
+  const bool stem_is_last = tcp && a.res_blocks == 0;
+  if ((rc = launch_conv(h, 0, h->in_act, &h->tmap_in, h->in_cpad, nullptr, stem_is_last ? nullptr : h->act[0],
+                        (tcp && !stem_is_last) ? xf : nullptr, batch, stem_is_last))) return rc;
   if (prof) { CU_TRY(h, cudaEventRecord(h->ev[2], h->stream)); h->pending_launches[1] = h->launches - l0; l0 = h->launches; }
   // ---- stage 2: residual tower ----
   int cur = 0;
@@ -387,7 +401,9 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
     if (tcp) {
       // x (bf16 copy) -> conv1 -> y (bf16);  y -> conv2 (+ fp32 x) -> x in place (fp32) and its bf16 copy
       if ((rc = launch_conv(h, 1 + 2 * blk, h->act[0], &h->tmap_act[0], a.filters, nullptr, h->act[1], nullptr, batch))) return rc;
-      if ((rc = launch_conv(h, 2 + 2 * blk, h->act[1], &h->tmap_act[1], a.filters, xf, h->act[0], xf, batch))) return rc;
+      const bool last = blk == a.res_blocks - 1;
+      if ((rc = launch_conv(h, 2 + 2 * blk, h->act[1], &h->tmap_act[1], a.filters, xf, last ? nullptr : h->act[0],
+                            last ? nullptr : xf, batch, last))) return rc;
       continue;
     }
     const int t1 = (cur + 1) % 3, t2 = (cur + 2) % 3;
@@ -399,12 +415,17 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
   // ---- stage 3: heads ----
   const int pf = a.policy_filters, vf = a.value_filters;
   const size_t hsmem = (size_t)(pf + vf) * a.filters * sizeof(float);
-  // both builds feed the heads from fp32 activations (tensor-core build: the fp32 residual stream)
-  caz::head_conv_kernel<float><<<batch, 256, hsmem, h->stream>>>(tcp ? xf : static_cast<const float*>(h->act[cur]), h->head_w, h->head_b, h->featp, h->featv, batch, a.filters, pf, vf);
-  if ((rc = check_launch(h, "head_conv_kernel"))) return rc;
-  caz::policy_fc_softmax_kernel<<<(batch + caz::PTM - 1) / caz::PTM, 256, (size_t)caz::PTM * pf * 64 * sizeof(float), h->stream>>>(
-      h->featp, h->pfc_w, h->pfc_b, d_mask, d_policy, batch, pf * 64, a.n_labels);
-  if ((rc = check_launch(h, "policy_fc_softmax_kernel"))) return rc;
+  if (!tcp) {
+    caz::head_conv_kernel<float><<<batch, 256, hsmem, h->stream>>>(static_cast<const float*>(h->act[cur]), h->head_w, h->head_b, h->featp, h->featv, batch, a.filters, pf, vf);
+    if ((rc = check_launch(h, "head_conv_kernel"))) return rc;
+  }
+  {
+    const dim3 grid((batch + caz::PG_TM - 1) / caz::PG_TM, (a.n_labels + caz::PG_TN - 1) / caz::PG_TN);
+    caz::policy_logits_kernel<<<grid, 256, 0, h->stream>>>(h->featp, h->pfc_w, h->pfc_b, d_policy, batch, pf * 64, a.n_labels);
+    if ((rc = check_launch(h, "policy_logits_kernel"))) return rc;
+    caz::policy_softmax_kernel<<<batch, 256, 0, h->stream>>>(d_policy, d_mask, a.n_labels);
+    if ((rc = check_launch(h, "policy_softmax_kernel"))) return rc;
+  }
   caz::value_fc_kernel<<<(batch + caz::VTM - 1) / caz::VTM, 256, (size_t)caz::VTM * vf * 64 * sizeof(float), h->stream>>>(
       h->featv, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, d_value, batch, vf * 64, a.value_fc);
   if ((rc = check_launch(h, "value_fc_kernel"))) return rc;
@@ -451,9 +472,17 @@ void caz_destroy(caz_handle* h) {
   for (auto& L : h->convs) { cudaFree(L.w); cudaFree(L.bias); }
   void* ptrs[] = {h->head_w, h->head_b, h->pfc_w, h->pfc_b, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, h->in_act,
                   h->act[0], h->act[1], h->act[2], h->featp, h->featv, h->d_planes, h->d_policy, h->d_value,
-                  h->d_mask, h->d_records, h->puct_buf};
+                  h->d_mask, h->d_records, h->puct_buf, h->d_planes2, h->d_policy2, h->d_value2, h->d_mask2,
+                  h->d_records2};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+    if (h->ev_fwd[i]) cudaEventDestroy(h->ev_fwd[i]);
+    if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+  }
+  if (h->copy_in) cudaStreamDestroy(h->copy_in);
+  if (h->copy_out) cudaStreamDestroy(h->copy_out);
   for (auto& set : h->ev_pool) for (auto& e : set.ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -520,6 +549,18 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   CREATE_TRY(cudaMalloc(&h->d_value, cap * 4));
   CREATE_TRY(cudaMalloc(&h->d_mask, cap * a.n_labels));
   CREATE_TRY(cudaMalloc(&h->d_records, cap * CAZ_RECORD_BYTES));
+  CREATE_TRY(cudaMalloc(&h->d_planes2, cap * a.input_planes * 64 * 4));
+  CREATE_TRY(cudaMalloc(&h->d_policy2, cap * a.n_labels * 4));
+  CREATE_TRY(cudaMalloc(&h->d_value2, cap * 4));
+  CREATE_TRY(cudaMalloc(&h->d_mask2, cap * a.n_labels));
+  CREATE_TRY(cudaMalloc(&h->d_records2, cap * CAZ_RECORD_BYTES));
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_fwd[i], cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+  }
   int rc;
   if (tcp) {
     if ((rc = make_act_tmap(h, &h->tmap_in, h->in_act, h->in_cpad))) return bail(rc);
@@ -581,16 +622,47 @@ static int eval_host(caz_handle* h, const float* planes, const uint8_t* records,
   if ((rc = set_device(h))) return rc;
   const caz_arch& a = h->arch;
   const size_t pin = (size_t)a.input_planes * 64;
-  for (int32_t off = 0; off < batch; off += h->max_batch) {
-    const int32_t nb = batch - off < h->max_batch ? batch - off : h->max_batch;
-    if (planes) CU_TRY(h, cudaMemcpyAsync(h->d_planes, planes + (size_t)off * pin, (size_t)nb * pin * 4, cudaMemcpyHostToDevice, h->stream));
-    else CU_TRY(h, cudaMemcpyAsync(h->d_records, records + (size_t)off * CAZ_RECORD_BYTES, (size_t)nb * CAZ_RECORD_BYTES, cudaMemcpyHostToDevice, h->stream));
-    if (masked) CU_TRY(h, cudaMemcpyAsync(h->d_mask, legal_mask + (size_t)off * a.n_labels, (size_t)nb * a.n_labels, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = forward(h, planes ? h->d_planes : nullptr, planes ? nullptr : h->d_records, nb, h->d_policy, h->d_value, masked ? h->d_mask : nullptr))) return rc;
-    CU_TRY(h, cudaMemcpyAsync(policy + (size_t)off * a.n_labels, h->d_policy, (size_t)nb * a.n_labels * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(value + off, h->d_value, (size_t)nb * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  // Chunking: a small batch is one chunk (latency).  A large one is cut into chunks of five full waves of the
+  // conv kernel (2 boards per tile x SM count per wave) so that chunk k+1's H2D and chunk k-1's D2H run on the
+  // copy engines under chunk k's forward pass; chunks alternate between two staging slots.
+  const int32_t wave = 2 * h->num_sms;
+  int32_t chunk = h->max_batch;
+  if (batch > 4 * wave && 5 * wave < chunk) chunk = 5 * wave;
+  float* dpl[2] = {h->d_planes, h->d_planes2};
+  float* dpo[2] = {h->d_policy, h->d_policy2};
+  float* dva[2] = {h->d_value, h->d_value2};
+  uint8_t* dma[2] = {h->d_mask, h->d_mask2};
+  uint8_t* dre[2] = {h->d_records, h->d_records2};
+  const bool single = batch <= chunk;  // one stream, no cross-stream events: the latency path
+  cudaStream_t sin = single ? h->stream : h->copy_in, sout = single ? h->stream : h->copy_out;
+  int c = 0;
+  for (int32_t off = 0; off < batch; ++c) {
+    int32_t nb = batch - off < chunk ? batch - off : chunk;
+    if (batch - off - nb > 0 && batch - off - nb < wave && batch - off <= h->max_batch) nb = batch - off;  // no sliver
+    const int s = c & 1;
+    // slot s inputs are free once the forward pass of chunk c-2 has consumed them
+    if (!single && c >= 2) CU_TRY(h, cudaStreamWaitEvent(sin, h->ev_fwd[s], 0));
+    if (planes) CU_TRY(h, cudaMemcpyAsync(dpl[s], planes + (size_t)off * pin, (size_t)nb * pin * 4, cudaMemcpyHostToDevice, sin));
+    else CU_TRY(h, cudaMemcpyAsync(dre[s], records + (size_t)off * CAZ_RECORD_BYTES, (size_t)nb * CAZ_RECORD_BYTES, cudaMemcpyHostToDevice, sin));
+    if (masked) CU_TRY(h, cudaMemcpyAsync(dma[s], legal_mask + (size_t)off * a.n_labels, (size_t)nb * a.n_labels, cudaMemcpyHostToDevice, sin));
+    if (!single) {
+      CU_TRY(h, cudaEventRecord(h->ev_in[s], sin));
+      CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_in[s], 0));
+      // slot s outputs are free once chunk c-2's D2H has drained them
+      if (c >= 2) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_out[s], 0));
+    }
+    if ((rc = forward(h, planes ? dpl[s] : nullptr, planes ? nullptr : dre[s], nb, dpo[s], dva[s], masked ? dma[s] : nullptr))) return rc;
+    if (!single) {
+      CU_TRY(h, cudaEventRecord(h->ev_fwd[s], h->stream));
+      CU_TRY(h, cudaStreamWaitEvent(sout, h->ev_fwd[s], 0));
+    }
+    CU_TRY(h, cudaMemcpyAsync(policy + (size_t)off * a.n_labels, dpo[s], (size_t)nb * a.n_labels * 4, cudaMemcpyDeviceToHost, sout));
+    CU_TRY(h, cudaMemcpyAsync(value + off, dva[s], (size_t)nb * 4, cudaMemcpyDeviceToHost, sout));
+    if (!single) CU_TRY(h, cudaEventRecord(h->ev_out[s], sout));
+    off += nb;
   }
+  if (!single) CU_TRY(h, cudaStreamSynchronize(h->copy_out));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
   return CAZ_OK;
 }
 

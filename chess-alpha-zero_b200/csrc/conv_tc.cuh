@@ -39,7 +39,8 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;      // 32 KiB (N = 256 rows)
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_WARP_BYTES = 4096;                  // per-warp 32x32 fp32 transpose buffer
-constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES + 1024;  // + folded-BN bias (<= 256 floats)
+constexpr int HEAD_MAX_F = 8;                          // policy + value 1x1 filters fused into the last epilogue
+constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES + 1024 + HEAD_MAX_F * 256 * 4;  // + bias (<= 256 floats) + head filters
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 struct ConvArgs {
@@ -55,6 +56,14 @@ struct ConvArgs {
   const float* residual;    // nullptr or fp32 [batch*64][n]: the residual stream stays in fp32
   float* out_f32;           // nullptr or fp32 [batch*64][n] (may alias residual: same element, same thread)
   __nv_bfloat16* out_bf16;  // nullptr or bf16 [batch*64][n]: the next convolution's A operand
+  // Last layer of the tower only: the two heads' 1x1 convolutions + folded BN + ReLU + Flatten
+  // (model_chess.py:77-81,86-90) are computed from the fp32 epilogue registers, so the final activation never
+  // goes to HBM.  head_w: fp32 [pf+vf][n]; outputs in Keras channels-first Flatten order [b][c*64 + square].
+  const float* head_w;      // nullptr = not fused
+  const float* head_b;      // [pf+vf]
+  float* featp;             // [batch][pf*64]
+  float* featv;             // [batch][vf*64]
+  int pf, vf;
   int* err_flag;
 };
 
@@ -70,6 +79,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;
   float* s_bias = reinterpret_cast<float*>(smem_epi + 4 * EPI_WARP_BYTES);
+  float* s_head = s_bias + 256;  // [pf+vf][n]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
   uint64_t* full = bars;                            // [STAGES]
   uint64_t* empty = bars + STAGES;                  // [STAGES]
@@ -103,6 +113,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
     ptx::tmem_relinquish();
   }
   if (threadIdx.x < args.n) s_bias[threadIdx.x] = args.bias[threadIdx.x];
+  if (args.head_w)
+    for (int i = threadIdx.x; i < (args.pf + args.vf) * args.n; i += THREADS) s_head[i] = args.head_w[i];
   ptx::tcgen05_fence_before();
   __syncthreads();
   ptx::tcgen05_fence_after();
@@ -190,6 +202,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
       ptx::mbar_wait(&tmem_full[acc], acc_phase, args.err_flag, ERR_EPILOGUE);
       ptx::tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS;
+      float hacc[HEAD_MAX_F];
+#pragma unroll
+      for (int hf = 0; hf < HEAD_MAX_F; ++hf) hacc[hf] = 0.0f;
       for (int c0 = 0; c0 < args.n; c0 += 32) {
         uint32_t v[32];
         ptx::tmem_ld_32x32(taddr + c0, v);
@@ -233,6 +248,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
         }
+        if (args.head_w) {
+          const int hf_total = args.pf + args.vf;
+#pragma unroll
+          for (int hf = 0; hf < HEAD_MAX_F; ++hf) {
+            if (hf < hf_total) {
+              const float4* wp = reinterpret_cast<const float4*>(s_head + hf * args.n + c0);  // warp-uniform: broadcast
+              float a = hacc[hf];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 wv = wp[q];
+                a = fmaf(f[q * 4 + 0], wv.x, a);
+                a = fmaf(f[q * 4 + 1], wv.y, a);
+                a = fmaf(f[q * 4 + 2], wv.z, a);
+                a = fmaf(f[q * 4 + 3], wv.w, a);
+              }
+              hacc[hf] = a;
+            }
+          }
+        }
         if (args.out_f32) {
           // own row only: no cross-lane hazard with the residual reads above
 #pragma unroll
@@ -267,6 +301,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
             if (r < rows_live) *reinterpret_cast<uint4*>(args.out_bf16 + (row0 + r) * args.n + c0 + bc * 8) = o;
           }
           __syncwarp();
+        }
+      }
+      if (args.head_w && lane < rows_live) {
+        // this thread's row is one square of one board: 32 consecutive lanes = 32 consecutive squares
+        const long row = row0 + lane;
+        const long b = row >> 6;
+        const int sq = static_cast<int>(row & 63);
+#pragma unroll
+        for (int hf = 0; hf < HEAD_MAX_F; ++hf) {
+          if (hf < args.pf + args.vf) {
+            const float y = fmaxf(hacc[hf] + args.head_b[hf], 0.0f);
+            if (hf < args.pf) args.featp[b * (args.pf * 64) + hf * 64 + sq] = y;
+            else args.featv[b * (args.vf * 64) + (hf - args.pf) * 64 + sq] = y;
+          }
         }
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }

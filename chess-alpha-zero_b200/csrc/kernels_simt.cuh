@@ -201,111 +201,118 @@ head_conv_kernel(const T* __restrict__ act, const float* __restrict__ w, const f
 
 // ------------------------------------------------------------------------------------------------
 // Policy head: Dense(n_labels) + softmax (agent/model_chess.py:82-83), optionally restricted to a legal
-// mask (how player_chess.py:267-275 consumes the row).  One block = PTM positions x all labels:
-// thread t owns labels t, t+256, ... (coalesced weight and output accesses), logits stay in registers,
-// max / sum are block reductions.  wk: [kin][n_labels] (Keras Dense kernel layout), fp32 throughout.
+// mask (how player_chess.py:267-275 consumes the row).  fp32 throughout, two kernels:
+//   policy_logits_kernel : logits = featp . wk + bk as a shared-memory tiled GEMM, 64 positions x 128 labels
+//                          per block (the 1 MB weight matrix is read once per 64 positions, not once per 8)
+//   policy_softmax_kernel: in-place row softmax, one block per position, the row lives in registers
+// wk: [kin][n_labels] (Keras Dense kernel layout).
 // ------------------------------------------------------------------------------------------------
-constexpr int PTM = 8;    // positions per block
-constexpr int PNJ = 8;    // labels per thread (8 * 256 >= 1968)
+constexpr int PG_TM = 64;    // positions per block
+constexpr int PG_TN = 128;   // labels per block
+constexpr int PG_TK = 32;    // K slab
+constexpr int PNJ = 8;       // labels per thread in the softmax kernel (8 * 256 >= 1968)
 
 __global__ void __launch_bounds__(256)
-policy_fc_softmax_kernel(const float* __restrict__ featp, const float* __restrict__ wk, const float* __restrict__ bk,
-                         const uint8_t* __restrict__ mask, float* __restrict__ policy, int batch, int kin,
-                         int n_labels) {
-  extern __shared__ float s_feat[];        // [PTM][kin]
-  __shared__ float s_red[8][PTM];
-  __shared__ float s_bcast[PTM];
-  const int b0 = blockIdx.x * PTM;
-  for (int i = threadIdx.x; i < PTM * kin; i += blockDim.x) {
-    const int m = i / kin, k = i - m * kin;
-    s_feat[i] = (b0 + m < batch) ? featp[static_cast<size_t>(b0 + m) * kin + k] : 0.0f;
-  }
-  __syncthreads();
-  float acc[PNJ][PTM];
+policy_logits_kernel(const float* __restrict__ featp, const float* __restrict__ wk, const float* __restrict__ bk,
+                     float* __restrict__ logits, int batch, int kin, int n_labels) {
+  __shared__ __align__(16) float sA[PG_TK][PG_TM + 4];  // [k][position]
+  __shared__ __align__(16) float sW[PG_TK][PG_TN];      // [k][label]
+  const int b0 = blockIdx.x * PG_TM, n0 = blockIdx.y * PG_TN;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;  // 4 positions x (4 + 4) labels per thread
+  float acc[4][8];
 #pragma unroll
-  for (int j = 0; j < PNJ; ++j)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int m = 0; m < PTM; ++m) acc[j][m] = 0.0f;
-  for (int k = 0; k < kin; ++k) {
-    float wv[PNJ];
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  for (int k0 = 0; k0 < kin; k0 += PG_TK) {
 #pragma unroll
-    for (int j = 0; j < PNJ; ++j) {
-      const int n = threadIdx.x + j * 256;
-      wv[j] = n < n_labels ? __ldg(wk + static_cast<size_t>(k) * n_labels + n) : 0.0f;
+    for (int i = 0; i < (PG_TM * PG_TK) / 256; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      const int pos = idx / PG_TK, k = idx % PG_TK;
+      sA[k][pos] = (b0 + pos < batch && k0 + k < kin) ? featp[static_cast<size_t>(b0 + pos) * kin + k0 + k] : 0.0f;
     }
 #pragma unroll
-    for (int m = 0; m < PTM; ++m) {
-      const float x = s_feat[m * kin + k];
+    for (int i = 0; i < (PG_TK * PG_TN) / 256; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      const int k = idx / PG_TN, n = idx % PG_TN;
+      sW[k][n] = (n0 + n < n_labels && k0 + k < kin) ? __ldg(wk + static_cast<size_t>(k0 + k) * n_labels + n0 + n) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < PG_TK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+      const float4 w0 = *reinterpret_cast<const float4*>(&sW[k][tx * 4]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&sW[k][64 + tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-      for (int j = 0; j < PNJ; ++j) acc[j][m] = fmaf(x, wv[j], acc[j][m]);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int b = b0 + ty * 4 + i;
+    if (b >= batch) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n < n_labels) logits[static_cast<size_t>(b) * n_labels + n] = acc[i][j] + bk[n];
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+policy_softmax_kernel(float* __restrict__ policy, const uint8_t* __restrict__ mask, int n_labels) {
+  __shared__ float s_red[8];
+  __shared__ float s_bc;
+  float* row = policy + static_cast<size_t>(blockIdx.x) * n_labels;
+  const uint8_t* mrow = mask ? mask + static_cast<size_t>(blockIdx.x) * n_labels : nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // bias, mask, running max
-  float mx[PTM];
-#pragma unroll
-  for (int m = 0; m < PTM; ++m) mx[m] = -INFINITY;
+  float x[PNJ];
+  float mx = -INFINITY;
 #pragma unroll
   for (int j = 0; j < PNJ; ++j) {
     const int n = threadIdx.x + j * 256;
-    const float bv = n < n_labels ? bk[n] : 0.0f;
-#pragma unroll
-    for (int m = 0; m < PTM; ++m) {
-      bool on = n < n_labels && b0 + m < batch;
-      if (on && mask) on = mask[static_cast<size_t>(b0 + m) * n_labels + n] != 0;
-      acc[j][m] = on ? acc[j][m] + bv : -INFINITY;
-      mx[m] = fmaxf(mx[m], acc[j][m]);
-    }
+    const bool on = n < n_labels && (!mrow || mrow[n] != 0);
+    x[j] = on ? row[n] : -INFINITY;
+    mx = fmaxf(mx, x[j]);
   }
 #pragma unroll
-  for (int m = 0; m < PTM; ++m) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx[m] = fmaxf(mx[m], __shfl_xor_sync(0xffffffffu, mx[m], o));
-    if (lane == 0) s_red[warp][m] = mx[m];
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = s_red[0];
+    for (int wi = 1; wi < 8; ++wi) v = fmaxf(v, s_red[wi]);
+    s_bc = v;
   }
   __syncthreads();
-  if (threadIdx.x < PTM) {
-    float v = s_red[0][threadIdx.x];
-    for (int wi = 1; wi < 8; ++wi) v = fmaxf(v, s_red[wi][threadIdx.x]);
-    s_bcast[threadIdx.x] = v;
-  }
-  __syncthreads();
-  float sum[PTM];
+  mx = s_bc;
+  float sum = 0.0f;
 #pragma unroll
-  for (int m = 0; m < PTM; ++m) {
-    const float mm = s_bcast[m];
-    sum[m] = 0.0f;
-#pragma unroll
-    for (int j = 0; j < PNJ; ++j) {
-      const float e = acc[j][m] == -INFINITY ? 0.0f : expf(acc[j][m] - mm);
-      acc[j][m] = e;
-      sum[m] += e;
-    }
+  for (int j = 0; j < PNJ; ++j) {
+    x[j] = x[j] == -INFINITY ? 0.0f : expf(x[j] - mx);
+    sum += x[j];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   __syncthreads();  // s_red reuse
-#pragma unroll
-  for (int m = 0; m < PTM; ++m) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum[m] += __shfl_xor_sync(0xffffffffu, sum[m], o);
-    if (lane == 0) s_red[warp][m] = sum[m];
-  }
+  if (lane == 0) s_red[warp] = sum;
   __syncthreads();
-  if (threadIdx.x < PTM) {
+  if (threadIdx.x == 0) {
     float v = 0.0f;
-    for (int wi = 0; wi < 8; ++wi) v += s_red[wi][threadIdx.x];
-    s_bcast[threadIdx.x] = v;
+    for (int wi = 0; wi < 8; ++wi) v += s_red[wi];
+    s_bc = v;
   }
   __syncthreads();
+  const float inv = s_bc > 0.0f ? 1.0f / s_bc : 0.0f;
 #pragma unroll
-  for (int m = 0; m < PTM; ++m) {
-    if (b0 + m >= batch) continue;
-    const float tot = s_bcast[m];
-    const float inv = tot > 0.0f ? 1.0f / tot : 0.0f;
-#pragma unroll
-    for (int j = 0; j < PNJ; ++j) {
-      const int n = threadIdx.x + j * 256;
-      if (n < n_labels) policy[static_cast<size_t>(b0 + m) * n_labels + n] = acc[j][m] * inv;
-    }
+  for (int j = 0; j < PNJ; ++j) {
+    const int n = threadIdx.x + j * 256;
+    if (n < n_labels) row[n] = x[j] * inv;
   }
 }
 
@@ -314,7 +321,7 @@ policy_fc_softmax_kernel(const float* __restrict__ featp, const float* __restric
 // One block = VTM positions; thread t owns hidden unit t (loops if value_fc > blockDim).
 // w1: [kin][hid], w2: [hid].
 // ------------------------------------------------------------------------------------------------
-constexpr int VTM = 8;
+constexpr int VTM = 16;
 
 __global__ void __launch_bounds__(256)
 value_fc_kernel(const float* __restrict__ featv, const float* __restrict__ w1, const float* __restrict__ b1,
