@@ -8,12 +8,14 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/caz_b200.h"
+#include "conv_sb.cuh"
 #include "conv_tc.cuh"
 #include "kernels_simt.cuh"
 
@@ -66,6 +68,20 @@ struct caz_handle {
   cudaStream_t stream = nullptr;
   std::string err;
   std::vector<ConvLayer> convs;  // stem, then conv1/conv2 of each block
+  // weight slabs the layers point into: the tower's layers are contiguous so that one tensor map covers them
+  void* w_stem = nullptr;
+  void* w_tower = nullptr;   // [2*res_blocks][filters][9*filters] (tensor-core build)
+  float* bias_all = nullptr; // [1 + 2*res_blocks][filters]
+  // small-batch persistent tower kernel (conv_sb.cuh)
+  bool sb_ok = false;        // architecture fits it
+  int sb_limit = -1;         // batches <= this use it; -1 = automatic
+  CUtensorMap sb_tm_in[2], sb_tm_xb[2], sb_tm_y[2];  // halo views for 1 and 2 boards per CTA tile
+  CUtensorMap sb_tm_w_stem[3], sb_tm_w_tower[3];      // weight maps for N_s = 16, 32, 64
+  int sb_force_nb = 0;
+  unsigned* sb_counter = nullptr;
+  long long* sb_trace = nullptr;   // [64][8] clock stamps of CTA 0 (debug)
+  bool sb_trace_on = false;
+  unsigned sb_epoch = 0;
   float *head_w = nullptr, *head_b = nullptr;
   float *pfc_w = nullptr, *pfc_b = nullptr, *vfc1_w = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr,
         *vfc2_b = nullptr;
@@ -76,7 +92,7 @@ struct caz_handle {
   // (A operand of conv2), act[2] = the residual stream itself, kept in fp32.
   void* act[3] = {nullptr, nullptr, nullptr};
   CUtensorMap tmap_in, tmap_act[2];
-  float *featp = nullptr, *featv = nullptr;
+  float *featp = nullptr, *featv = nullptr, *vhid = nullptr;
   // staging for the host-pointer entry points
   float *d_planes = nullptr, *d_policy = nullptr, *d_value = nullptr;
   uint8_t *d_mask = nullptr, *d_records = nullptr;
@@ -183,7 +199,21 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
   int64_t wbytes = 0;
   std::vector<float> inv, shift;
   const int n_convs = 1 + 2 * a.res_blocks;
-  if (h->convs.empty()) h->convs.resize(n_convs);
+  const bool first_install = h->convs.empty();
+  if (first_install) {
+    h->convs.resize(n_convs);
+    const int scin = a.input_planes, scin_pad = tcp ? ((scin + 63) / 64) * 64 : scin;
+    const size_t stem_elems = (size_t)a.stem_kernel * a.stem_kernel * scin_pad * F;
+    const size_t blk_elems = (size_t)a.block_kernel * a.block_kernel * F * F;
+    const size_t esz = tcp ? 2 : 4;
+    CU_TRY(h, cudaMalloc(&h->w_stem, stem_elems * esz));
+    if (a.res_blocks > 0) CU_TRY(h, cudaMalloc(&h->w_tower, blk_elems * esz * 2 * a.res_blocks));
+    CU_TRY(h, cudaMalloc(&h->bias_all, (size_t)n_convs * F * sizeof(float)));
+    for (int li = 0; li < n_convs; ++li) {
+      h->convs[li].w = li == 0 ? h->w_stem : static_cast<char*>(h->w_tower) + (size_t)(li - 1) * blk_elems * esz;
+      h->convs[li].bias = h->bias_all + (size_t)li * F;
+    }
+  }
   for (int li = 0; li < n_convs; ++li) {
     ConvLayer& L = h->convs[li];
     const int k = li == 0 ? a.stem_kernel : a.block_kernel;
@@ -199,10 +229,8 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
     ti += 5;
     const int taps = k * k;
     const size_t ktot = (size_t)taps * cin_pad;
-    if (!L.w) {
+    if (first_install) {
       L.k = k; L.cin = cin; L.cin_pad = cin_pad; L.cout = F;
-      CU_TRY(h, cudaMalloc(&L.w, tcp ? ktot * F * 2 : (size_t)taps * cin * F * 4));
-      CU_TRY(h, cudaMalloc(&L.bias, F * sizeof(float)));
       if (tcp) {
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)F};
         cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
@@ -334,6 +362,149 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
   return check_launch(h, "conv_fp32_kernel");
 }
 
+// ---- small-batch persistent tower (conv_sb.cuh) -------------------------------------------------------
+// Halo view of NHWC bf16 activations [cap][8][8][c]: dims (c, file, position, rank), box 64 x hw x 2 x hw, fetched at
+// (c0, -pad, n0, -pad): the out-of-bounds fill supplies the zero border on all four sides.
+int make_halo_tmap(caz_handle* h, CUtensorMap* m, void* base, int c, int k, int nb) {
+  const cuuint32_t hw = 8 + k - 1;
+  cuuint64_t dims[4] = {(cuuint64_t)c, 8, (cuuint64_t)h->max_batch, 8};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 128, (cuuint64_t)c * 16};
+  cuuint32_t box[4] = {64, hw, (cuuint32_t)nb, hw};
+  return make_tmap(h, m, base, 4, dims, strides, box);
+}
+
+int setup_small_batch(caz_handle* h) {
+  const caz_arch& a = h->arch;
+  h->sb_ok = false;
+  if (!tensor_path(h) || a.block_kernel != 3 || a.filters != 256 && a.filters != 128 && a.filters != 64) return CAZ_OK;
+  if ((8 + a.stem_kernel - 1) * 2 * (8 + a.stem_kernel - 1) * 128 * (h->in_cpad / 64) > caz::sb::A_BYTES) return CAZ_OK;
+  int rc;
+  for (int nb = 1; nb <= 2; ++nb) {
+    if ((rc = make_halo_tmap(h, &h->sb_tm_in[nb - 1], h->in_act, h->in_cpad, a.stem_kernel, nb))) return rc;
+    if ((rc = make_halo_tmap(h, &h->sb_tm_xb[nb - 1], h->act[0], a.filters, a.block_kernel, nb))) return rc;
+    if ((rc = make_halo_tmap(h, &h->sb_tm_y[nb - 1], h->act[1], a.filters, a.block_kernel, nb))) return rc;
+  }
+  if (const char* e = getenv("CAZ_SB_BOARDS")) h->sb_force_nb = atoi(e);
+  const int F = a.filters;
+  for (int i = 0; i < 3; ++i) {
+    const cuuint32_t ns = 16u << i;
+    if (ns > (cuuint32_t)F) { h->sb_tm_w_stem[i] = h->sb_tm_w_stem[0]; h->sb_tm_w_tower[i] = h->sb_tm_w_tower[0]; continue; }
+    const cuuint64_t kst = (cuuint64_t)a.stem_kernel * a.stem_kernel * h->in_cpad;
+    cuuint64_t dims_s[2] = {kst, (cuuint64_t)F};
+    cuuint64_t str_s[1] = {kst * 2};
+    cuuint32_t box[2] = {64, ns};
+    if ((rc = make_tmap(h, &h->sb_tm_w_stem[i], h->w_stem, 2, dims_s, str_s, box))) return rc;
+    if (a.res_blocks > 0) {
+      const cuuint64_t kt = (cuuint64_t)9 * F;
+      cuuint64_t dims_t[2] = {kt, (cuuint64_t)F * 2 * a.res_blocks};
+      cuuint64_t str_t[1] = {kt * 2};
+      if ((rc = make_tmap(h, &h->sb_tm_w_tower[i], h->w_tower, 2, dims_t, str_t, box))) return rc;
+    } else {
+      h->sb_tm_w_tower[i] = h->sb_tm_w_stem[i];
+    }
+  }
+  CU_TRY(h, cudaMalloc(&h->sb_counter, sizeof(unsigned)));
+  CU_TRY(h, cudaMemset(h->sb_counter, 0, sizeof(unsigned)));
+  CU_TRY(h, cudaMalloc(&h->sb_trace, (1024 + 16 * 256 * 2) * sizeof(long long)));
+  CU_TRY(h, cudaMemset(h->sb_trace, 0, (1024 + 16 * 256 * 2) * sizeof(long long)));
+  CU_TRY(h, cudaFuncSetAttribute(caz::sb::forward_sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::sb::SMEM_BYTES));
+  h->sb_ok = true;
+  return CAZ_OK;
+}
+
+// Grid geometry for a batch: boards per CTA tile (1 -> M = 64 MMAs, 2 -> M = 128) and output-channel slices, such that
+// every CTA is co-resident.
+bool sb_geometry(const caz_handle* h, int batch, int* nb_out, int* slices_out) {
+  if (!h->sb_ok) return false;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int nb = 1; nb <= 2; ++nb) {
+      if (h->sb_force_nb && nb != h->sb_force_nb) continue;
+      const int tiles = (batch + nb - 1) / nb;
+      for (int s = 16; s >= 4; s >>= 1) {
+        const int ns = h->arch.filters / s;
+        if (ns < 16 || ns > 64 || h->arch.filters % s != 0 || tiles * s > h->num_sms) continue;
+        // first pass: one board per tile (M = 64) only while it still allows the finest channel slicing -- measured:
+        // a tcgen05.mma costs ~55 cycles whatever its shape, so more slices (fewer rows of work per CTA) never hurt,
+        // and one-board tiles win only for the tiniest batches
+        if (pass == 0 && nb == 1 && s < 16) break;
+        *nb_out = nb;
+        *slices_out = s;
+        return true;
+      }
+    }
+  return false;
+}
+
+bool use_small_batch(const caz_handle* h, int batch) {
+  const int limit = h->sb_limit < 0 ? caz::sb::MAX_BATCH : h->sb_limit;
+  int nb, sl;
+  return batch <= limit && batch <= caz::sb::MAX_BATCH && sb_geometry(h, batch, &nb, &sl);
+}
+
+// The whole forward pass of a small batch: one cooperative launch (conv_sb.cuh).
+int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_records, int batch, float* d_policy,
+                         float* d_value, const uint8_t* d_mask) {
+  const caz_arch& a = h->arch;
+  int nb = 2, slices = 4;
+  sb_geometry(h, batch, &nb, &slices);
+  const int ns = a.filters / slices;
+  const int wi = ns == 16 ? 0 : (ns == 32 ? 1 : 2);
+  caz::sb::Args args;
+  args.batch = batch;
+  args.nb = nb;
+  args.n_layers = 1 + 2 * a.res_blocks;
+  args.ns = ns;
+  args.n_slices = slices;
+  args.filters = a.filters;
+  args.stem_k = a.stem_kernel;
+  args.stem_kchunks = h->in_cpad / 64;
+  args.blk_k = a.block_kernel;
+  args.in_planes = a.input_planes;
+  args.in_cpad = h->in_cpad;
+  const int sb_stem = caz::sb::taps_per_slot(a.stem_kernel, ns) * ns * 128;
+  const int sb_blk = a.res_blocks > 0 ? caz::sb::taps_per_slot(a.block_kernel, ns) * ns * 128 : 0;
+  args.slot_bytes = sb_stem > sb_blk ? sb_stem : sb_blk;
+  args.n_slots = caz::sb::W_RING_BYTES / args.slot_bytes;
+  if (args.n_slots > caz::sb::MAX_W_SLOTS) args.n_slots = caz::sb::MAX_W_SLOTS;
+  args.planes = d_planes;
+  args.records = d_records;
+  args.in_act = static_cast<__nv_bfloat16*>(h->in_act);
+  args.bias_all = h->bias_all;
+  args.xf = static_cast<float*>(h->act[2]);
+  args.xb = static_cast<__nv_bfloat16*>(h->act[0]);
+  args.y = static_cast<__nv_bfloat16*>(h->act[1]);
+  args.pf = a.policy_filters;
+  args.vf = a.value_filters;
+  args.value_fc = a.value_fc;
+  args.n_labels = a.n_labels;
+  args.head_w = h->head_w;
+  args.head_b = h->head_b;
+  args.featp = h->featp;
+  args.featv = h->featv;
+  args.pfc_w = h->pfc_w;
+  args.pfc_b = h->pfc_b;
+  args.vfc1_w = h->vfc1_w;
+  args.vfc1_b = h->vfc1_b;
+  args.vfc2_w = h->vfc2_w;
+  args.vfc2_b = h->vfc2_b;
+  args.vhid = h->vhid;
+  args.mask = d_mask;
+  args.policy = d_policy;
+  args.value = d_value;
+  args.counter = h->sb_counter;
+  args.base = h->sb_epoch;
+  args.trace = (h->sb_trace_on && args.n_layers <= 64) ? h->sb_trace : nullptr;
+  args.err_flag = h->err_flag_dev;
+  const int grid = ((batch + nb - 1) / nb) * slices;
+  h->sb_epoch += (unsigned)(args.n_layers + caz::sb::EXTRA_PHASES) * (unsigned)grid;
+  void* params[] = {&h->sb_tm_in[nb - 1], &h->sb_tm_xb[nb - 1], &h->sb_tm_y[nb - 1], &h->sb_tm_w_stem[wi], &h->sb_tm_w_tower[wi], &args};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(caz::sb::forward_sb_kernel), dim3(grid),
+                                              dim3(caz::sb::THREADS), params, caz::sb::SMEM_BYTES, h->stream);
+  if (e != cudaSuccess) return fail(h, CAZ_ERR_CUDA, fmt("cooperative launch of forward_sb_kernel failed: %s", cudaGetErrorString(e)));
+  h->launches++;
+  return CAZ_OK;
+}
+
 // Picks the event set for this forward pass (no synchronisation).
 int prof_begin(caz_handle* h) {
   h->ev = nullptr;
@@ -374,6 +545,13 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
   const bool prof = h->ev != nullptr;
   int64_t l0 = h->launches;
   if (prof) CU_TRY(h, cudaEventRecord(h->ev[0], h->stream));
+  if (tcp && use_small_batch(h, batch)) {
+    // one persistent kernel does pack + stem + tower + heads; its time is booked under the tower stage
+    if (prof) { CU_TRY(h, cudaEventRecord(h->ev[1], h->stream)); CU_TRY(h, cudaEventRecord(h->ev[2], h->stream)); h->pending_launches[0] = h->pending_launches[1] = 0; }
+    if ((rc = launch_forward_small(h, d_planes, d_records, batch, d_policy, d_value, d_mask))) return rc;
+    if (prof) { CU_TRY(h, cudaEventRecord(h->ev[3], h->stream)); CU_TRY(h, cudaEventRecord(h->ev[4], h->stream)); h->pending_launches[2] = 1; h->pending_launches[3] = 0; }
+    return CAZ_OK;
+  }
   // ---- stage 0: input pack (NCHW fp32 planes -> NHWC activations, channels zero-padded) ----
   if (d_planes) {
     const size_t smem = (size_t)a.input_planes * 65 * sizeof(float);
@@ -388,8 +566,10 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
     if ((rc = check_launch(h, "encode_pack_kernel"))) return rc;
   }
   if (prof) { CU_TRY(h, cudaEventRecord(h->ev[1], h->stream)); h->pending_launches[0] = h->launches - l0; l0 = h->launches; }
-  // ---- stage 1: stem ----
   float* xf = static_cast<float*>(h->act[2]);  // tensor-core build: fp32 residual stream
+  int cur_fp32 = 0;
+  {
+  // ---- stage 1: stem ----
   // tensor-core build: the LAST convolution's epilogue also computes the heads' 1x1 convs (no activation store)
   const bool stem_is_last = tcp && a.res_blocks == 0;
   if ((rc = launch_conv(h, 0, h->in_act, &h->tmap_in, h->in_cpad, nullptr, stem_is_last ? nullptr : h->act[0],
@@ -410,13 +590,15 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
     if ((rc = launch_conv(h, 1 + 2 * blk, h->act[cur], nullptr, a.filters, nullptr, h->act[t1], nullptr, batch))) return rc;
     if ((rc = launch_conv(h, 2 + 2 * blk, h->act[t1], nullptr, a.filters, static_cast<const float*>(h->act[cur]), h->act[t2], nullptr, batch))) return rc;
     cur = t2;
+    cur_fp32 = cur;
   }
   if (prof) { CU_TRY(h, cudaEventRecord(h->ev[3], h->stream)); h->pending_launches[2] = h->launches - l0; l0 = h->launches; }
+  }
   // ---- stage 3: heads ----
   const int pf = a.policy_filters, vf = a.value_filters;
   const size_t hsmem = (size_t)(pf + vf) * a.filters * sizeof(float);
   if (!tcp) {
-    caz::head_conv_kernel<float><<<batch, 256, hsmem, h->stream>>>(static_cast<const float*>(h->act[cur]), h->head_w, h->head_b, h->featp, h->featv, batch, a.filters, pf, vf);
+    caz::head_conv_kernel<float><<<batch, 256, hsmem, h->stream>>>(static_cast<const float*>(h->act[cur_fp32]), h->head_w, h->head_b, h->featp, h->featv, batch, a.filters, pf, vf);
     if ((rc = check_launch(h, "head_conv_kernel"))) return rc;
   }
   {
@@ -469,9 +651,13 @@ void caz_destroy(caz_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (auto& L : h->convs) { cudaFree(L.w); cudaFree(L.bias); }
+  if (h->w_stem) cudaFree(h->w_stem);
+  if (h->w_tower) cudaFree(h->w_tower);
+  if (h->bias_all) cudaFree(h->bias_all);
+  if (h->sb_counter) cudaFree(h->sb_counter);
+  if (h->sb_trace) cudaFree(h->sb_trace);
   void* ptrs[] = {h->head_w, h->head_b, h->pfc_w, h->pfc_b, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, h->in_act,
-                  h->act[0], h->act[1], h->act[2], h->featp, h->featv, h->d_planes, h->d_policy, h->d_value,
+                  h->act[0], h->act[1], h->act[2], h->featp, h->featv, h->vhid, h->d_planes, h->d_policy, h->d_value,
                   h->d_mask, h->d_records, h->puct_buf, h->d_planes2, h->d_policy2, h->d_value2, h->d_mask2,
                   h->d_records2};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -544,6 +730,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   for (int i = 0; i < 3; ++i) CREATE_TRY(cudaMalloc(&h->act[i], cap * 64 * a.filters * (i == 2 ? 4 : esz)));
   CREATE_TRY(cudaMalloc(&h->featp, cap * a.policy_filters * 64 * 4));
   CREATE_TRY(cudaMalloc(&h->featv, cap * a.value_filters * 64 * 4));
+  CREATE_TRY(cudaMalloc(&h->vhid, cap * a.value_fc * 4));
   CREATE_TRY(cudaMalloc(&h->d_planes, cap * a.input_planes * 64 * 4));
   CREATE_TRY(cudaMalloc(&h->d_policy, cap * a.n_labels * 4));
   CREATE_TRY(cudaMalloc(&h->d_value, cap * 4));
@@ -579,6 +766,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   }
 #undef CREATE_TRY
   if ((rc = install_weights(h, tensors, n_tensors))) return bail(rc);
+  if ((rc = setup_small_batch(h))) return bail(rc);
   *out = h;
   return CAZ_OK;
 }
@@ -804,6 +992,24 @@ int caz_debug_conv_layer(caz_handle* h, int32_t layer, const float* in, const fl
   CU_TRY(h, cudaMemcpyAsync(out, d_out, rows * F * 4, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   cudaFree(d_in); cudaFree(d_out); if (d_res) cudaFree(d_res);
+  return CAZ_OK;
+}
+
+int caz_debug_sb_trace(caz_handle* h, int32_t enable, int64_t* stamps, int32_t n) {
+  if (!h || !h->sb_ok) return fail(h, CAZ_ERR_INVALID, "small-batch kernel not available");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  h->sb_trace_on = enable != 0;
+  if (stamps && n > 0) {
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaMemcpy(stamps, h->sb_trace, (size_t)(n > 1024 + 16 * 256 * 2 ? 1024 + 16 * 256 * 2 : n) * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  return CAZ_OK;
+}
+
+int caz_set_small_batch_limit(caz_handle* h, int32_t limit) {
+  if (!h) return CAZ_ERR_INVALID;
+  h->sb_limit = limit;
   return CAZ_OK;
 }
 

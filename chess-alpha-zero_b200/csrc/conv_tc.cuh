@@ -120,56 +120,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
+  // The single-thread roles run as WARP-UNIFORM loops: all 32 lanes wait on the mbarriers and walk the loop
+  // counters, and only the instruction issue sits under elect.sync.  (Issuing from inside an `if (lane == 0)` region
+  // makes the compiler wrap every UTCHMMA / UTMALDG in an election loop with R2UR moves: ~700 issue cycles per K
+  // block, more than the 512 cycles the four MMAs take.)
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
-        const int n0 = tile * 2;
-        for (int tap = 0; tap < args.taps; ++tap) {
-          const int dy = tap / args.taps_w - args.pad;
-          const int dx = tap % args.taps_w - args.pad;
-          for (int kc = 0; kc < args.kchunks; ++kc) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+      const int n0 = tile * 2;
+      int kcol = 0;  // K coordinate of the weight block: (tap * kchunks + kc) * 64
+      for (int dy = -args.pad; dy <= args.pad; ++dy)
+        for (int dx = -args.pad; dx <= args.pad; ++dx)
+          for (int kc = 0; kc < args.kchunks; ++kc, kcol += BLOCK_K) {
             ptx::mbar_wait(&empty[stage], phase ^ 1, args.err_flag, ERR_PRODUCER);
-            ptx::mbar_expect_tx(&full[stage], A_STAGE_BYTES + b_bytes);
-            ptx::tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmap_act, &full[stage], kc * BLOCK_K, dx, dy, n0);
-            ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_w, &full[stage],
-                             (tap * args.kchunks + kc) * BLOCK_K, 0);
+            if (ptx::elect_one()) {
+              ptx::mbar_expect_tx(&full[stage], A_STAGE_BYTES + b_bytes);
+              ptx::tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmap_act, &full[stage], kc * BLOCK_K, dx, dy, n0);
+              ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_w, &full[stage], kcol, 0);
+            }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-        }
-      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = ptx::idesc_bf16_f32(BLOCK_M, args.n);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, args.err_flag, ERR_MMA_ACC);
+    const uint32_t idesc = ptx::idesc_bf16_f32(BLOCK_M, args.n);
+    // descriptors differ only in the 14-bit start-address field: add (byte offset >> 4) to a template
+    const uint64_t a_desc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_a));
+    const uint64_t b_desc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_b));
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, args.err_flag, ERR_MMA_ACC);
+      ptx::tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        ptx::mbar_wait(&full[stage], phase, args.err_flag, ERR_MMA_FULL);
         ptx::tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
-          ptx::mbar_wait(&full[stage], phase, args.err_flag, ERR_MMA_FULL);
-          ptx::tcgen05_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+        if (ptx::elect_one()) {
+          const uint64_t adesc = a_desc0 + static_cast<uint64_t>((stage * A_STAGE_BYTES) >> 4);
+          const uint64_t bdesc = b_desc0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adesc = ptx::smem_desc_sw128(a_addr + k * UMMA_K * 2);
-            const uint64_t bdesc = ptx::smem_desc_sw128(b_addr + k * UMMA_K * 2);
-            ptx::mma_bf16_ss(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          ptx::mma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            ptx::mma_bf16_ss(tmem_d, adesc + k * ((UMMA_K * 2) >> 4), bdesc + k * ((UMMA_K * 2) >> 4), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+          ptx::mma_commit(&empty[stage]);                             // smem slot reusable once these MMAs have read it
+          if (kb == num_k_blocks - 1) ptx::mma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         }
-        ptx::mma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue =====================

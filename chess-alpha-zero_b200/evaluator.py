@@ -108,6 +108,10 @@ class Evaluator:
                                            ctypes.c_void_p(d_mask_ptr) if d_mask_ptr else None, flags)
             _lib.check(self._handle, rc)
 
+    def set_small_batch_limit(self, limit):
+        """Batches <= limit use the persistent small-batch tower kernel; -1 = automatic, 0 = never."""
+        _lib.check(self._handle, self._lib.caz_set_small_batch_limit(self._handle, int(limit)))
+
     def sync(self):
         _lib.check(self._handle, self._lib.caz_sync(self._handle))
 

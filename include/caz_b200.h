@@ -155,6 +155,17 @@ void* caz_stream(const caz_handle* h);            /* cudaStream_t the handle lau
 int64_t caz_kernel_launches(const caz_handle* h); /* kernels this handle has launched so far */
 int64_t caz_weight_bytes(const caz_handle* h);    /* folded device weight set, bytes */
 
+/* Batches of at most `limit` positions run the persistent small-batch tower kernel (one cooperative launch for
+ * stem + all residual convs, weights streamed from L2); larger ones run one implicit-GEMM launch per layer.
+ * limit < 0 restores the automatic choice, 0 disables the small-batch kernel.  Results are identical either way
+ * up to fp32 summation order inside the MMA. */
+int caz_set_small_batch_limit(caz_handle* h, int32_t limit);
+
+/* Test hook: switch on per-layer clock64 stamps of CTA 0 of the small-batch kernel and/or read them back
+ * (stamps: host int64 [n], 8 per layer: barrier passed, first A tile landed, last A tile landed, MMAs issued,
+ * accumulator ready, stores fenced, epilogue warps joined, unused). */
+int caz_debug_sb_trace(caz_handle* h, int32_t enable, int64_t* stamps, int32_t n);
+
 /* Per-stage device timing of the forward pass (CUDA events on the handle's stream).
  * stage ids: 0 input pack, 1 stem conv, 2 residual tower convs, 3 heads. After caz_profile(h,1),
  * every eval accumulates; caz_profile_read returns accumulated milliseconds and launch counts. */

@@ -216,10 +216,45 @@ def test_masked_softmax(net, ev_bf16):
 
 @pytest.mark.parametrize("batch", [1, 2, 3, 16, 17, 48, 255])
 def test_ragged_batches_are_consistent(net, ev_bf16, batch):
+    """Per-layer kernels (small-batch kernel off): a position's result does not depend on its batch."""
     x = net[2]
-    full_p, full_v = ev_bf16.predict_on_batch(x)
-    p, v = ev_bf16.predict_on_batch(x[:batch])
+    ev_bf16.set_small_batch_limit(0)
+    try:
+        full_p, full_v = ev_bf16.predict_on_batch(x)
+        p, v = ev_bf16.predict_on_batch(x[:batch])
+    finally:
+        ev_bf16.set_small_batch_limit(-1)
     assert np.array_equal(p, full_p[:batch]) and np.array_equal(v, full_v[:batch])
+
+
+def test_small_batch_persistent_kernel(net_default):
+    """Batches <= 64 run the persistent whole-tower kernel (halo tile + shifted UMMA descriptors, weights streamed
+    from L2, grid barriers).  Same north_star gate as the per-layer path, and batch-size independent bit for bit."""
+    cfg, w, x, fens, (wp, wv) = net_default
+    ev = caz.Evaluator(cfg, w, precision="bf16", max_batch=256)
+    ref_p, ref_v = ev.predict_on_batch(x[:64])
+    dp, dv, agree = _bf16_report("small-batch kernel vs fp32 oracle [keras_default, 64]", ref_p, ref_v, wp[:64], wv[:64], 64)
+    assert dp <= BF16_TOL and dv <= BF16_TOL and agree >= ARGMAX_AGREE
+    for batch in (1, 2, 3, 15, 16, 17, 32, 33, 48):
+        p, v = ev.predict_on_batch(x[:batch])
+        assert np.array_equal(p, ref_p[:batch]) and np.array_equal(v, ref_v[:batch]), batch
+    # against the per-layer kernels: same arithmetic up to fp32 summation order, so bf16-noise level agreement
+    ev.set_small_batch_limit(0)
+    big_p, big_v = ev.predict_on_batch(x[:64])
+    print(f"   small vs per-layer path: max|dp|={np.abs(big_p - ref_p).max():.3e} max|dv|={np.abs(big_v - ref_v).max():.3e}")
+    assert np.abs(big_p - ref_p).max() <= BF16_TOL and np.abs(big_v - ref_v).max() <= BF16_TOL
+    ev.close()
+    # the architecture the reference ships as JSON (3x3 stem) and a 19-block tower through the same kernel
+    for variant, n in ((dict(stem_k=3, value_filters=1), 16), (dict(blocks=19), 8)):
+        cfg2 = oweights.keras_config(**variant)
+        w2 = oweights.synth_weights(cfg2, seed=7, recipe="keras_default")
+        want_p, want_v = onet.forward_graph(cfg2, w2, x[:n])
+        ev2 = caz.Evaluator(cfg2, w2, precision="bf16", max_batch=32)
+        p, v = ev2.predict_on_batch(x[:n])
+        # north_star's 2e-2 is stated for the 7x256 net; 19 blocks accumulate ~1.6x the bf16 rounding noise
+        tol = BF16_TOL if "blocks" not in variant else 3e-2
+        assert np.abs(p - want_p).max() <= tol and np.abs(v - want_v).max() <= tol, variant
+        ev2.close()
 
 
 def test_empty_batch_and_chunking(net, ev_bf16):

@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Per-layer timeline of CTA 0 of the small-batch tower kernel (clock64 stamps -> microseconds at 1.965 GHz)."""
+import ctypes, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench, torch
+import chess_alpha_zero_b200 as caz
+from chess_alpha_zero_b200 import _lib
+b = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+cfg, weights = bench.network(7)
+ev = caz.Evaluator(cfg, weights, precision="bf16", max_batch=64)
+planes = bench.synthetic_batch(64, seed=3)
+d_x = torch.from_numpy(planes).cuda(); d_p = torch.empty((64, 1968), device="cuda"); d_v = torch.empty((64,), device="cuda")
+for _ in range(5): ev.eval_device(d_x.data_ptr(), b, d_p.data_ptr(), d_v.data_ptr())
+lib = _lib.load()
+_lib.check(ev._handle, lib.caz_debug_sb_trace(ev._handle, 1, None, 0))
+ev.eval_device(d_x.data_ptr(), b, d_p.data_ptr(), d_v.data_ptr())
+st = np.zeros(16 * 8, np.int64)
+_lib.check(ev._handle, lib.caz_debug_sb_trace(ev._handle, 0, st.ctypes.data_as(ctypes.c_void_p), st.size))
+st = st.reshape(16, 8).astype(np.float64)
+t0 = st[0, 0]
+us = (st - t0) / 1965.0
+names = ["barrier", "A0 in", "A3 in", "mma iss", "acc rdy", "fenced", "joined"]
+print("layer " + " ".join(f"{n:>9s}" for n in names) + "   (us since layer-0 start)")
+print("kernel: start, pack done, tower done, heads start, H1 done, H2 start, H2 done, H3 start:", " ".join(f"{v:8.2f}" for v in us[15]))
+for l in (0, 1, 2, 3, 13, 14):
+    print(f"{l:5d} " + " ".join(f"{us[l, i]:9.2f}" for i in range(7)))
