@@ -179,11 +179,13 @@ int make_tmap(caz_handle* h, CUtensorMap* m, void* base, int rank, const cuuint6
   return CAZ_OK;
 }
 
-// NHWC bf16 activations [cap][8][8][c] as a 4-D tensor (c, file, rank, position); box = 64 ch x 8 x 8 x 2 boards
-int make_act_tmap(caz_handle* h, CUtensorMap* m, void* base, int c) {
-  cuuint64_t dims[4] = {(cuuint64_t)c, 8, 8, (cuuint64_t)h->max_batch};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 16, (cuuint64_t)c * 128};
-  cuuint32_t box[4] = {64, 8, 8, 2};
+// Halo view of NHWC bf16 activations [cap][8][8][c]: dims (c, file, position, rank), box 64 x hw x nb x hw, fetched at
+// (c0, -pad, n0, -pad): the out-of-bounds fill supplies the zero border on all four sides (hw = 8 + k - 1).
+int make_halo_tmap(caz_handle* h, CUtensorMap* m, void* base, int c, int k, int nb) {
+  const cuuint32_t hw = 8 + k - 1;
+  cuuint64_t dims[4] = {(cuuint64_t)c, 8, (cuuint64_t)h->max_batch, 8};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 128, (cuuint64_t)c * 16};
+  cuuint32_t box[4] = {64, hw, (cuuint32_t)nb, hw};
   return make_tmap(h, m, base, 4, dims, strides, box);
 }
 
@@ -326,9 +328,7 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
     caz::tc::ConvArgs args;
     args.batch = batch;
     args.num_tiles = (batch + 1) / 2;
-    args.taps_w = L.k;
-    args.taps = L.k * L.k;
-    args.pad = (L.k - 1) / 2;
+    args.ksize = L.k;
     args.kchunks = L.cin_pad / 64;
     args.n = L.cout;
     args.relu = 1;
@@ -363,16 +363,6 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
 }
 
 // ---- small-batch persistent tower (conv_sb.cuh) -------------------------------------------------------
-// Halo view of NHWC bf16 activations [cap][8][8][c]: dims (c, file, position, rank), box 64 x hw x 2 x hw, fetched at
-// (c0, -pad, n0, -pad): the out-of-bounds fill supplies the zero border on all four sides.
-int make_halo_tmap(caz_handle* h, CUtensorMap* m, void* base, int c, int k, int nb) {
-  const cuuint32_t hw = 8 + k - 1;
-  cuuint64_t dims[4] = {(cuuint64_t)c, 8, (cuuint64_t)h->max_batch, 8};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 128, (cuuint64_t)c * 16};
-  cuuint32_t box[4] = {64, hw, (cuuint32_t)nb, hw};
-  return make_tmap(h, m, base, 4, dims, strides, box);
-}
-
 int setup_small_batch(caz_handle* h) {
   const caz_arch& a = h->arch;
   h->sb_ok = false;
@@ -750,9 +740,9 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   }
   int rc;
   if (tcp) {
-    if ((rc = make_act_tmap(h, &h->tmap_in, h->in_act, h->in_cpad))) return bail(rc);
+    if ((rc = make_halo_tmap(h, &h->tmap_in, h->in_act, h->in_cpad, a.stem_kernel, 2))) return bail(rc);
     for (int i = 0; i < 2; ++i)
-      if ((rc = make_act_tmap(h, &h->tmap_act[i], h->act[i], a.filters))) return bail(rc);
+      if ((rc = make_halo_tmap(h, &h->tmap_act[i], h->act[i], a.filters, a.block_kernel, 2))) return bail(rc);
     CREATE_TRY(cudaFuncSetAttribute(caz::tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc::SMEM_BYTES));
   } else {
     const size_t s3 = (size_t)(8 + a.block_kernel - 1) * (8 + a.block_kernel - 1) * a.filters * 4;

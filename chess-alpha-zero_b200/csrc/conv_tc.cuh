@@ -4,20 +4,34 @@
 //   Conv2D(k x k, padding="same", use_bias=False) + BatchNormalization (+ Add) + ReLU
 // in ChessModel.build / _build_residual_block (reference src/chess_zero/agent/model_chess.py:65-69,96-111).
 //
-// GEMM view:  D[m, oc] = sum_{tap, ic} A_tap[m, ic] * W[oc, tap*Cin + ic]
-//   m   = position*64 + rank*8 + file            (M = 64 * batch, 128 rows = 2 boards per tile)
-//   A_tap[m, ic] = x[position, rank+dy-pad, file+dx-pad, ic], zero outside the board
-//   activations are NHWC bf16, so A_tap for one (tap, 64-channel chunk) is a 4-D TMA box
-//   {64 ch, 8 files, 8 ranks, 2 boards} fetched at signed coordinates (c0, dx-pad, dy-pad, n0): the TMA
-//   unit's out-of-bounds zero fill IS the "same" padding, no halo is ever materialised.
-//   The box lands as 128 rows x 128 bytes with the 128-byte swizzle = the canonical K-major UMMA layout.
+// GEMM view:  D[m, oc] = sum_{tap, ic} A_tap[m, ic] * W[oc, tap*Cin + ic],  one tile = 128 rows = two boards.
 //
-// Warp roles (256 threads, persistent over M tiles):
-//   warp 0   : TMA producer (one elected lane)      -> full[stage]
-//   warp 1   : tcgen05.mma issuer (one elected lane) -> empty[stage] (tcgen05.commit), tmem_full[acc]
+// What bounds this kernel is NOT the tensor pipe but the bytes each SM pulls from L2 per tile: a B200 SM sustains
+// ~100-110 GB/s of TMA fill with all 148 SMs pulling (measured: V1 fetched 1.77 MB per tile -- nine shifted copies
+// of the activations plus the layer's weights -- and took 17.8 us per tile against 9.6 us of MMA time).  So:
+//   * activations: ONE zero-padded halo tile per 64-channel chunk, [10 ranks][2 boards][10 files][64 ch] = 25.6 KB,
+//     fetched by a single 4-D TMA box at signed coordinates (c0, -pad, n0, -pad) -- the out-of-bounds zero fill
+//     is the convolution's "same" padding -- and shared by all k*k taps: tap (dy, dx) is the same tile read through
+//     a UMMA descriptor whose start address is shifted by (2*hw*dy + dx) rows of 128 bytes and whose 8-row-group
+//     stride is hw rows.  The 128-byte swizzle is a function of the shared-memory address, so the shifted view is
+//     consistent with what TMA wrote.  102 KB of activations per tile instead of 590 KB.
+//   * the K loop runs chunk-major (kc outer, taps inner); a chunk tile lives for k*k K-blocks (~2.7 us), far longer
+//     than a TMA round trip, so the activation ring is just two chunk tiles.
+//   * weights: [oc][tap*Cin + ic] bf16, one 32 KB TMA box per (tap, chunk).  With the activations nearly free, what
+//     bounds a tile is the weight ring's DEPTH: each K block needs 32 KB that take ~1.2 us to arrive under load, so
+//     K blocks complete at (stages / latency); every byte of shared memory the halo trick freed goes to that ring.
+// TMEM lane m of the accumulator is row (rank h = m>>4, board p = (m>>3)&1, file w = m&7).
+//
+// Warp roles (256 threads, persistent over tiles; single-thread roles are warp-uniform loops with only the
+// instruction issue under elect.sync -- issuing from an `if (lane == 0)` region makes the compiler wrap every
+// UTCHMMA / UTMALDG in an election loop):
+//   warp 0   : weight (B) TMA producer
+//   warp 3   : activation (A) halo-tile TMA producer
+//   warp 1   : tcgen05.mma issuer; tcgen05.commit frees the weight stage / the chunk tile / hands over the accumulator
 //   warp 2   : TMEM allocator / deallocator
-//   warps 4-7: epilogue: tcgen05.ld accumulators, + folded-BN bias, + fp32 residual, ReLU,
-//              fp32 store of the residual stream and/or bf16 store of the next layer's operand
+//   warps 4-7: epilogue: tcgen05.ld accumulators, + folded-BN bias, + fp32 residual, ReLU, fp32 store of the
+//              residual stream and/or bf16 store of the next layer's operand (or, on the last layer, the heads'
+//              1x1 convolutions straight from the registers)
 // Two TMEM accumulator stages (2 x 256 fp32 columns) let the epilogue of tile i overlap the MMAs of i+1.
 #pragma once
 #include <cuda_bf16.h>
@@ -30,27 +44,25 @@ namespace tc {
 constexpr int BLOCK_M = 128;  // rows per tile: two boards
 constexpr int BLOCK_K = 64;   // bf16 elements per 128-byte swizzled row
 constexpr int UMMA_K = 16;    // K per tcgen05.mma, 16-bit operands
-constexpr int STAGES = 4;
+constexpr int B_STAGES = 4;
 constexpr int THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int ACC_STAGES = 2;
-constexpr int ACC_COLS = 256;  // TMEM columns per accumulator stage (N <= 256)
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;      // 32 KiB (N = 256 rows)
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int EPI_WARP_BYTES = 4096;                  // per-warp 32x32 fp32 transpose buffer
+constexpr int ACC_COLS = 256;                          // TMEM columns per accumulator stage (N <= 256)
+constexpr int A_RING_BYTES = 2 * (10 * 2 * 10 * 128);  // 51 200: two 3x3 chunk tiles (or one 5x5 / 7x7 one)
+constexpr int MAX_A_SLOTS = 2;
+constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;       // 32 KiB (N = 256 rows)
+constexpr int EPI_WARP_BYTES = 4096;                   // per-warp 32x32 fp32 transpose buffer
 constexpr int HEAD_MAX_F = 8;                          // policy + value 1x1 filters fused into the last epilogue
 constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES + 1024 + HEAD_MAX_F * 256 * 4;  // + bias (<= 256 floats) + head filters
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = A_RING_BYTES + B_STAGES * B_STAGE_BYTES + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 struct ConvArgs {
   int batch;        // positions
   int num_tiles;    // ceil(batch / 2)
-  int taps_w;       // kernel width  (3 or 5)
-  int taps;         // kernel height * width
-  int pad;          // (k-1)/2
+  int ksize;        // kernel height = width (3 or 5)
   int kchunks;      // Cin_padded / 64
-  int n;            // Cout, multiple of 16, <= 256
+  int n;            // Cout, multiple of 32, <= 256
   int relu;
   const float* bias;        // [n] folded BatchNorm shift
   const float* residual;    // nullptr or fp32 [batch*64][n]: the residual stream stays in fp32
@@ -67,39 +79,59 @@ struct ConvArgs {
   int* err_flag;
 };
 
-enum : int { ERR_PRODUCER = 101, ERR_MMA_FULL = 102, ERR_MMA_ACC = 103, ERR_EPILOGUE = 104 };
+enum : int { ERR_PRODUCER_B = 101, ERR_PRODUCER_A = 105, ERR_MMA_FULL = 102, ERR_MMA_ACC = 103, ERR_EPILOGUE = 104, ERR_MMA_A = 106 };
 
+// K-major SWIZZLE_128B descriptor with an explicit 8-row-group stride (the halo view needs hw*128, weights 1024)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// tmap_halo: NHWC bf16 activations as (channel, file, position, rank) with box 64 x hw x 2 x hw (see caz_abi.cu)
 __global__ void __launch_bounds__(THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_constant__ CUtensorMap tmap_w,
                const ConvArgs args) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* smem_epi = smem + STAGES * STAGE_BYTES;
+  uint8_t* smem_b = smem + A_RING_BYTES;
+  uint8_t* smem_epi = smem_b + B_STAGES * B_STAGE_BYTES;
   float* s_bias = reinterpret_cast<float*>(smem_epi + 4 * EPI_WARP_BYTES);
   float* s_head = s_bias + 256;  // [pf+vf][n]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
-  uint64_t* full = bars;                            // [STAGES]
-  uint64_t* empty = bars + STAGES;                  // [STAGES]
-  uint64_t* tmem_full = bars + 2 * STAGES;          // [ACC_STAGES]
-  uint64_t* tmem_empty = bars + 2 * STAGES + ACC_STAGES;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+  uint64_t* a_full = bars;                          // [MAX_A_SLOTS]
+  uint64_t* a_empty = a_full + MAX_A_SLOTS;         // [MAX_A_SLOTS]
+  uint64_t* b_full = a_empty + MAX_A_SLOTS;         // [B_STAGES]
+  uint64_t* b_empty = b_full + B_STAGES;            // [B_STAGES]
+  uint64_t* tmem_full = b_empty + B_STAGES;         // [ACC_STAGES]
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;    // [ACC_STAGES]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_k_blocks = args.taps * args.kchunks;
+  const int k = args.ksize, pad = (k - 1) / 2, hw = 8 + k - 1;
+  const int plane_bytes = hw * 2 * hw * 128;           // one chunk tile; a multiple of 1024
+  const int a_slots = A_RING_BYTES / plane_bytes < MAX_A_SLOTS ? A_RING_BYTES / plane_bytes : MAX_A_SLOTS;
   const uint32_t b_bytes = static_cast<uint32_t>(args.n) * BLOCK_K * 2;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmap_act);
+    ptx::prefetch_tmap(&tmap_halo);
     ptx::prefetch_tmap(&tmap_w);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
-      ptx::mbar_init(&full[i], 1);
-      ptx::mbar_init(&empty[i], 1);
+    for (int i = 0; i < a_slots; ++i) {
+      ptx::mbar_init(&a_full[i], 1);
+      ptx::mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < B_STAGES; ++i) {
+      ptx::mbar_init(&b_full[i], 1);
+      ptx::mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       ptx::mbar_init(&tmem_full[i], 1);
@@ -120,88 +152,106 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  // The single-thread roles run as WARP-UNIFORM loops: all 32 lanes wait on the mbarriers and walk the loop
-  // counters, and only the instruction issue sits under elect.sync.  (Issuing from inside an `if (lane == 0)` region
-  // makes the compiler wrap every UTCHMMA / UTMALDG in an election loop with R2UR moves: ~700 issue cycles per K
-  // block, more than the 512 cycles the four MMAs take.)
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== weight producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
-      const int n0 = tile * 2;
-      int kcol = 0;  // K coordinate of the weight block: (tap * kchunks + kc) * 64
-      for (int dy = -args.pad; dy <= args.pad; ++dy)
-        for (int dx = -args.pad; dx <= args.pad; ++dx)
-          for (int kc = 0; kc < args.kchunks; ++kc, kcol += BLOCK_K) {
-            ptx::mbar_wait(&empty[stage], phase ^ 1, args.err_flag, ERR_PRODUCER);
-            if (ptx::elect_one()) {
-              ptx::mbar_expect_tx(&full[stage], A_STAGE_BYTES + b_bytes);
-              ptx::tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmap_act, &full[stage], kc * BLOCK_K, dx, dy, n0);
-              ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_w, &full[stage], kcol, 0);
-            }
-            __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x)
+      for (int kc = 0; kc < args.kchunks; ++kc)
+        for (int tap = 0; tap < k * k; ++tap) {
+          ptx::mbar_wait(&b_empty[stage], phase ^ 1, args.err_flag, ERR_PRODUCER_B);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&b_full[stage], b_bytes);
+            ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_w, &b_full[stage], (tap * args.kchunks + kc) * BLOCK_K, 0);
           }
-    }
+          __syncwarp();
+          if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+        }
+  } else if (warp == 3) {
+    // ===================== activation producer: one halo tile per (board pair, channel chunk) =====================
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x)
+      for (int kc = 0; kc < args.kchunks; ++kc) {
+        ptx::mbar_wait(&a_empty[slot], phase ^ 1, args.err_flag, ERR_PRODUCER_A);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&a_full[slot], plane_bytes);
+          ptx::tma_load_4d(smem_a + slot * plane_bytes, &tmap_halo, &a_full[slot], kc * BLOCK_K, -pad, tile * 2, -pad);
+        }
+        __syncwarp();
+        if (++slot == a_slots) { slot = 0; phase ^= 1; }
+      }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = ptx::idesc_bf16_f32(BLOCK_M, args.n);
     // descriptors differ only in the 14-bit start-address field: add (byte offset >> 4) to a template
-    const uint64_t a_desc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_a));
-    const uint64_t b_desc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_b));
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const uint64_t a_desc0 = desc_sw128(ptx::smem_u32(smem_a), hw * 128);  // next 8-row group = next (rank, board)
+    const uint64_t b_desc0 = desc_sw128(ptx::smem_u32(smem_b), 1024);
+    int stage = 0, slot = 0, acc = 0;
+    uint32_t phase = 0, a_phase = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, args.err_flag, ERR_MMA_ACC);
       ptx::tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        ptx::mbar_wait(&full[stage], phase, args.err_flag, ERR_MMA_FULL);
-        ptx::tcgen05_fence_after();
-        if (ptx::elect_one()) {
-          const uint64_t adesc = a_desc0 + static_cast<uint64_t>((stage * A_STAGE_BYTES) >> 4);
-          const uint64_t bdesc = b_desc0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
+      for (int kc = 0; kc < args.kchunks; ++kc) {
+        ptx::mbar_wait(&a_full[slot], a_phase, args.err_flag, ERR_MMA_A);
+        const uint64_t a_plane = a_desc0 + static_cast<uint64_t>((slot * plane_bytes) >> 4);
+        for (int dy = 0; dy < k; ++dy)
+          for (int dx = 0; dx < k; ++dx) {
+            ptx::mbar_wait(&b_full[stage], phase, args.err_flag, ERR_MMA_FULL);
+            ptx::tcgen05_fence_after();
+            if (ptx::elect_one()) {
+              // tap (dy, dx) = the same halo tile, viewed (2*hw*dy + dx) rows of 128 bytes further on
+              const uint64_t adesc = a_plane + static_cast<uint64_t>((dy * 2 * hw + dx) * 8);
+              const uint64_t bdesc = b_desc0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
+              const uint32_t first = (kc | dy | dx) == 0 ? 0u : 1u;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            ptx::mma_bf16_ss(tmem_d, adesc + k * ((UMMA_K * 2) >> 4), bdesc + k * ((UMMA_K * 2) >> 4), idesc,
-                             (kb | k) != 0 ? 1u : 0u);
-          ptx::mma_commit(&empty[stage]);                             // smem slot reusable once these MMAs have read it
-          if (kb == num_k_blocks - 1) ptx::mma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                ptx::mma_bf16_ss(tmem_d, adesc + kk * 2, bdesc + kk * 2, idesc, kk == 0 ? first : 1u);
+              ptx::mma_commit(&b_empty[stage]);  // weight stage reusable once these MMAs have read it
+              if (dy == k - 1 && dx == k - 1) {
+                ptx::mma_commit(&a_empty[slot]);                                  // chunk tile fully consumed
+                if (kc == args.kchunks - 1) ptx::mma_commit(&tmem_full[acc]);     // accumulator complete -> epilogue
+              }
+            }
+            __syncwarp();
+            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+          }
+        if (++slot == a_slots) { slot = 0; a_phase ^= 1; }
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue =====================
-    // TMEM hands thread t row t of the tile (tcgen05.ld 32x32b), but a row is 1 KiB (fp32) / 512 B (bf16) of
+    // TMEM hands thread t the tile row in lane t (tcgen05.ld 32x32b), but a row is 1 KiB (fp32) / 512 B (bf16) of
     // global memory, so row-per-thread global accesses touch 32 lines per instruction.  Every 32x32 block is
     // therefore transposed through a 4 KiB per-warp staging buffer (XOR-swizzled, conflict-free both ways) so
     // that each global load/store instruction covers whole 128-byte lines: 4 rows x 128 B (fp32) or
     // 8 rows x 64 B (bf16) per instruction.  The fp32 residual chunk is prefetched one chunk ahead.
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    // Warp `quad` owns TMEM lanes 32*quad .. +31 = ranks 2*quad, 2*quad+1 of both boards: local row r is
+    // (rank 2*quad + (r>>4), board (r>>3)&1, file r&7), eight consecutive r = eight consecutive global rows.
+    const int quad = warp & 3;
     float4* stage = reinterpret_cast<float4*>(smem_epi + quad * EPI_WARP_BYTES);
     uint4* stage_b = reinterpret_cast<uint4*>(stage);
     const int fr = lane >> 3, fq = lane & 7;   // fp32 transposed mapping: row i*4+fr, float4 column fq
     const int br = lane >> 2, bc = lane & 3;   // bf16 transposed mapping: row i*8+br, 16-byte column bc
     int acc = 0;
     uint32_t acc_phase = 0;
-    const long total_rows = static_cast<long>(args.batch) * 64;
     for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
-      const long row0 = static_cast<long>(tile) * BLOCK_M + quad * 32;
-      const long left = total_rows - row0;
-      const int rows_live = left >= 32 ? 32 : (left > 0 ? static_cast<int>(left) : 0);
+      const int n0 = tile * 2;
+      const int boards_live = args.batch - n0 >= 2 ? 2 : 1;
+      // global row of local row r, and whether its board exists
+      auto grow = [&](int r) -> long {
+        return (static_cast<long>(n0 + ((r >> 3) & 1)) << 6) + ((2 * quad + (r >> 4)) << 3) + (r & 7);
+      };
+      auto live = [&](int r) -> bool { return ((r >> 3) & 1) < boards_live; };
       float4 res_pf[8];
       if (args.residual) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + fr;
-          res_pf[i] = r < rows_live ? *reinterpret_cast<const float4*>(args.residual + (row0 + r) * args.n + fq * 4)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          res_pf[i] = live(r) ? *reinterpret_cast<const float4*>(args.residual + grow(r) * args.n + fq * 4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       ptx::mbar_wait(&tmem_full[acc], acc_phase, args.err_flag, ERR_EPILOGUE);
@@ -224,8 +274,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = i * 4 + fr;
-              if (r < rows_live)
-                res_pf[i] = *reinterpret_cast<const float4*>(args.residual + (row0 + r) * args.n + c0 + 32 + fq * 4);
+              if (live(r))
+                res_pf[i] = *reinterpret_cast<const float4*>(args.residual + grow(r) * args.n + c0 + 32 + fq * 4);
             }
           }
         }
@@ -282,7 +332,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
           for (int i = 0; i < 8; ++i) {
             const int r = i * 4 + fr;
             const float4 o = stage[r * 8 + (fq ^ (r & 7))];
-            if (r < rows_live) *reinterpret_cast<float4*>(args.out_f32 + (row0 + r) * args.n + c0 + fq * 4) = o;
+            if (live(r)) *reinterpret_cast<float4*>(args.out_f32 + grow(r) * args.n + c0 + fq * 4) = o;
           }
           __syncwarp();
         }
@@ -303,16 +353,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_consta
           for (int i = 0; i < 4; ++i) {
             const int r = i * 8 + br;
             const uint4 o = stage_b[r * 4 + (bc ^ ((r >> 1) & 3))];
-            if (r < rows_live) *reinterpret_cast<uint4*>(args.out_bf16 + (row0 + r) * args.n + c0 + bc * 8) = o;
+            if (live(r)) *reinterpret_cast<uint4*>(args.out_bf16 + grow(r) * args.n + c0 + bc * 8) = o;
           }
           __syncwarp();
         }
       }
-      if (args.head_w && lane < rows_live) {
-        // this thread's row is one square of one board: 32 consecutive lanes = 32 consecutive squares
-        const long row = row0 + lane;
-        const long b = row >> 6;
-        const int sq = static_cast<int>(row & 63);
+      if (args.head_w && live(lane)) {
+        // this thread's row is one square of one board
+        const long b = n0 + ((lane >> 3) & 1);
+        const int sq = ((2 * quad + (lane >> 4)) << 3) + (lane & 7);
 #pragma unroll
         for (int hf = 0; hf < HEAD_MAX_F; ++hf) {
           if (hf < args.pf + args.vf) {
