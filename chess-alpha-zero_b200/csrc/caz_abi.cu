@@ -17,6 +17,7 @@
 #include "../../include/caz_b200.h"
 #include "conv_sb.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc2.cuh"
 #include "kernels_simt.cuh"
 
 namespace {
@@ -54,7 +55,8 @@ struct ConvLayer {
   int k = 0, cin = 0, cin_pad = 0, cout = 0;
   void* w = nullptr;      // bf16 [cout][k*k*cin_pad] (tensor path) or fp32 [k*k][cin][cout] (fp32 path)
   float* bias = nullptr;  // [cout]
-  CUtensorMap tmap_w;
+  CUtensorMap tmap_w;    // box 64 x cout       (one-CTA kernel)
+  CUtensorMap tmap_w2;   // box 64 x cout / 2   (CTA-pair kernel: each CTA stages half of the output channels)
 };
 
 }  // namespace
@@ -68,6 +70,7 @@ struct caz_handle {
   cudaStream_t stream = nullptr;
   std::string err;
   std::vector<ConvLayer> convs;  // stem, then conv1/conv2 of each block
+  bool use_2cta = true;          // per-layer convolutions as CTA pairs (cta_group::2); CAZ_CONV_2CTA=0 turns it off
   // weight slabs the layers point into: the tower's layers are contiguous so that one tensor map covers them
   void* w_stem = nullptr;
   void* w_tower = nullptr;   // [2*res_blocks][filters][9*filters] (tensor-core build)
@@ -239,6 +242,8 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
         cuuint32_t box[2] = {64, (cuuint32_t)F};
         int rc = make_tmap(h, &L.tmap_w, L.w, 2, dims, strides, box);
         if (rc) return rc;
+        cuuint32_t box2[2] = {64, (cuuint32_t)F / 2};
+        if ((rc = make_tmap(h, &L.tmap_w2, L.w, 2, dims, strides, box2))) return rc;
       }
     }
     if (tcp) {
@@ -343,6 +348,14 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
     args.pf = h->arch.policy_filters;
     args.vf = h->arch.value_filters;
     args.err_flag = h->err_flag_dev;
+    if (h->use_2cta && args.num_tiles >= 2 && L.cout % 64 == 0) {
+      // CTA pairs: one cta_group::2 MMA covers two tiles (four boards)
+      const int pairs = (args.num_tiles + 1) / 2;
+      const int max_pairs = h->num_sms / 2;
+      const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+      caz::tc2::conv_tc2_kernel<<<grid, caz::tc2::THREADS, caz::tc2::SMEM_BYTES, h->stream>>>(*tmap_in, L.tmap_w2, args);
+      return check_launch(h, "conv_tc2_kernel");
+    }
     const int grid = args.num_tiles < h->num_sms ? args.num_tiles : h->num_sms;
     caz::tc::conv_tc_kernel<<<grid, caz::tc::THREADS, caz::tc::SMEM_BYTES, h->stream>>>(*tmap_in, L.tmap_w, args);
     return check_launch(h, "conv_tc_kernel");
@@ -744,6 +757,8 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
     for (int i = 0; i < 2; ++i)
       if ((rc = make_halo_tmap(h, &h->tmap_act[i], h->act[i], a.filters, a.block_kernel, 2))) return bail(rc);
     CREATE_TRY(cudaFuncSetAttribute(caz::tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc::SMEM_BYTES));
+    CREATE_TRY(cudaFuncSetAttribute(caz::tc2::conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc2::SMEM_BYTES));
+    if (const char* e = getenv("CAZ_CONV_2CTA")) h->use_2cta = atoi(e) != 0;
   } else {
     const size_t s3 = (size_t)(8 + a.block_kernel - 1) * (8 + a.block_kernel - 1) * a.filters * 4;
     const size_t s1 = (size_t)(8 + a.stem_kernel - 1) * (8 + a.stem_kernel - 1) * a.input_planes * 4;

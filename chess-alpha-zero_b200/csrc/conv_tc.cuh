@@ -92,6 +92,159 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr, uint32_t sbo_
   return d;
 }
 
+constexpr uint32_t kLocalCta = 0xffffffffu;
+
+// Epilogue of ONE tile by one of the four epilogue warps (shared by the 1-CTA and the 2-CTA kernel).
+//   n0          first board of the tile (boards n0, n0+1; a board >= batch does not exist)
+//   taddr       TMEM address of this warp's lane quadrant in the accumulator stage
+//   full_bar    mbarrier the MMA commit arrives on when the accumulator is complete
+//   empty_bar   mbarrier to arrive on once the accumulator has been read out; in CTA `release_rank` of the cluster,
+//               or in this CTA when release_rank == kLocalCta
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* smem_epi, const float* s_bias,
+                                              const float* s_head, int quad, int lane, int n0, uint32_t taddr,
+                                              uint64_t* full_bar, uint32_t full_phase, uint64_t* empty_bar,
+                                              uint32_t release_rank) {
+  float4* stage = reinterpret_cast<float4*>(smem_epi + quad * EPI_WARP_BYTES);
+  uint4* stage_b = reinterpret_cast<uint4*>(stage);
+  const int fr = lane >> 3, fq = lane & 7;   // fp32 transposed mapping: row i*4+fr, float4 column fq
+  const int br = lane >> 2, bc = lane & 3;   // bf16 transposed mapping: row i*8+br, 16-byte column bc
+  const int left = args.batch - n0;
+  const int boards_live = left >= 2 ? 2 : (left > 0 ? left : 0);
+  // global row of local row r, and whether its board exists
+  auto grow = [&](int r) -> long {
+    return (static_cast<long>(n0 + ((r >> 3) & 1)) << 6) + ((2 * quad + (r >> 4)) << 3) + (r & 7);
+  };
+  auto live = [&](int r) -> bool { return ((r >> 3) & 1) < boards_live; };
+  float4 res_pf[8];
+  if (args.residual) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + fr;
+      res_pf[i] = live(r) ? *reinterpret_cast<const float4*>(args.residual + grow(r) * args.n + fq * 4)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  ptx::mbar_wait(full_bar, full_phase, args.err_flag, ERR_EPILOGUE);
+  ptx::tcgen05_fence_after();
+    float hacc[HEAD_MAX_F];
+#pragma unroll
+  for (int hf = 0; hf < HEAD_MAX_F; ++hf) hacc[hf] = 0.0f;
+  for (int c0 = 0; c0 < args.n; c0 += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(taddr + c0, v);
+    if (args.residual) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + fr;
+        stage[r * 8 + (fq ^ (r & 7))] = res_pf[i];
+      }
+      __syncwarp();
+      if (c0 + 32 < args.n) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + fr;
+          if (live(r))
+            res_pf[i] = *reinterpret_cast<const float4*>(args.residual + grow(r) * args.n + c0 + 32 + fq * 4);
+        }
+      }
+    }
+    ptx::tmem_ld_wait();
+    if (c0 + 32 >= args.n) {
+      // all accumulator columns of this tile are in registers: hand the TMEM stage back to the MMA warp
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (release_rank == kLocalCta) ptx::mbar_arrive(empty_bar);
+        else ptx::mbar_arrive_cluster(empty_bar, release_rank);
+      }
+    }
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+    if (args.residual) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 rv = stage[lane * 8 + (q ^ (lane & 7))];
+        f[q * 4 + 0] += rv.x;
+        f[q * 4 + 1] += rv.y;
+        f[q * 4 + 2] += rv.z;
+        f[q * 4 + 3] += rv.w;
+      }
+    }
+    if (args.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+    }
+    if (args.head_w) {
+      const int hf_total = args.pf + args.vf;
+#pragma unroll
+      for (int hf = 0; hf < HEAD_MAX_F; ++hf) {
+        if (hf < hf_total) {
+          const float4* wp = reinterpret_cast<const float4*>(s_head + hf * args.n + c0);  // warp-uniform: broadcast
+          float a = hacc[hf];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 wv = wp[q];
+            a = fmaf(f[q * 4 + 0], wv.x, a);
+            a = fmaf(f[q * 4 + 1], wv.y, a);
+            a = fmaf(f[q * 4 + 2], wv.z, a);
+            a = fmaf(f[q * 4 + 3], wv.w, a);
+          }
+          hacc[hf] = a;
+        }
+      }
+    }
+    if (args.out_f32) {
+      // own row only: no cross-lane hazard with the residual reads above
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        stage[lane * 8 + (q ^ (lane & 7))] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + fr;
+        const float4 o = stage[r * 8 + (fq ^ (r & 7))];
+        if (live(r)) *reinterpret_cast<float4*>(args.out_f32 + grow(r) * args.n + c0 + fq * 4) = o;
+      }
+      __syncwarp();
+    }
+    if (args.out_bf16) {
+      if (args.residual && !args.out_f32) __syncwarp();  // residual rows fully read before reuse
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[c * 8 + e * 2], f[c * 8 + e * 2 + 1]);
+          w[e] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        stage_b[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + br;
+        const uint4 o = stage_b[r * 4 + (bc ^ ((r >> 1) & 3))];
+        if (live(r)) *reinterpret_cast<uint4*>(args.out_bf16 + grow(r) * args.n + c0 + bc * 8) = o;
+      }
+      __syncwarp();
+    }
+  }
+  if (args.head_w && live(lane)) {
+    // this thread's row is one square of one board
+    const long b = n0 + ((lane >> 3) & 1);
+    const int sq = ((2 * quad + (lane >> 4)) << 3) + (lane & 7);
+#pragma unroll
+    for (int hf = 0; hf < HEAD_MAX_F; ++hf) {
+      if (hf < args.pf + args.vf) {
+        const float y = fmaxf(hacc[hf] + args.head_b[hf], 0.0f);
+        if (hf < args.pf) args.featp[b * (args.pf * 64) + hf * 64 + sq] = y;
+        else args.featv[b * (args.vf * 64) + (hf - args.pf) * 64 + sq] = y;
+      }
+    }
+  }
+}
+
 // tmap_halo: NHWC bf16 activations as (channel, file, position, rank) with box 64 x hw x 2 x hw (see caz_abi.cu)
 __global__ void __launch_bounds__(THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_constant__ CUtensorMap tmap_w,
@@ -231,146 +384,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_const
     // Warp `quad` owns TMEM lanes 32*quad .. +31 = ranks 2*quad, 2*quad+1 of both boards: local row r is
     // (rank 2*quad + (r>>4), board (r>>3)&1, file r&7), eight consecutive r = eight consecutive global rows.
     const int quad = warp & 3;
-    float4* stage = reinterpret_cast<float4*>(smem_epi + quad * EPI_WARP_BYTES);
-    uint4* stage_b = reinterpret_cast<uint4*>(stage);
-    const int fr = lane >> 3, fq = lane & 7;   // fp32 transposed mapping: row i*4+fr, float4 column fq
-    const int br = lane >> 2, bc = lane & 3;   // bf16 transposed mapping: row i*8+br, 16-byte column bc
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
       const int n0 = tile * 2;
-      const int boards_live = args.batch - n0 >= 2 ? 2 : 1;
-      // global row of local row r, and whether its board exists
-      auto grow = [&](int r) -> long {
-        return (static_cast<long>(n0 + ((r >> 3) & 1)) << 6) + ((2 * quad + (r >> 4)) << 3) + (r & 7);
-      };
-      auto live = [&](int r) -> bool { return ((r >> 3) & 1) < boards_live; };
-      float4 res_pf[8];
-      if (args.residual) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + fr;
-          res_pf[i] = live(r) ? *reinterpret_cast<const float4*>(args.residual + grow(r) * args.n + fq * 4)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      ptx::mbar_wait(&tmem_full[acc], acc_phase, args.err_flag, ERR_EPILOGUE);
-      ptx::tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS;
-      float hacc[HEAD_MAX_F];
-#pragma unroll
-      for (int hf = 0; hf < HEAD_MAX_F; ++hf) hacc[hf] = 0.0f;
-      for (int c0 = 0; c0 < args.n; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr + c0, v);
-        if (args.residual) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + fr;
-            stage[r * 8 + (fq ^ (r & 7))] = res_pf[i];
-          }
-          __syncwarp();
-          if (c0 + 32 < args.n) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = i * 4 + fr;
-              if (live(r))
-                res_pf[i] = *reinterpret_cast<const float4*>(args.residual + grow(r) * args.n + c0 + 32 + fq * 4);
-            }
-          }
-        }
-        ptx::tmem_ld_wait();
-        if (c0 + 32 >= args.n) {
-          // all accumulator columns of this tile are in registers: hand the TMEM stage back to the MMA warp
-          ptx::tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-        }
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
-        if (args.residual) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 rv = stage[lane * 8 + (q ^ (lane & 7))];
-            f[q * 4 + 0] += rv.x;
-            f[q * 4 + 1] += rv.y;
-            f[q * 4 + 2] += rv.z;
-            f[q * 4 + 3] += rv.w;
-          }
-        }
-        if (args.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-        }
-        if (args.head_w) {
-          const int hf_total = args.pf + args.vf;
-#pragma unroll
-          for (int hf = 0; hf < HEAD_MAX_F; ++hf) {
-            if (hf < hf_total) {
-              const float4* wp = reinterpret_cast<const float4*>(s_head + hf * args.n + c0);  // warp-uniform: broadcast
-              float a = hacc[hf];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 wv = wp[q];
-                a = fmaf(f[q * 4 + 0], wv.x, a);
-                a = fmaf(f[q * 4 + 1], wv.y, a);
-                a = fmaf(f[q * 4 + 2], wv.z, a);
-                a = fmaf(f[q * 4 + 3], wv.w, a);
-              }
-              hacc[hf] = a;
-            }
-          }
-        }
-        if (args.out_f32) {
-          // own row only: no cross-lane hazard with the residual reads above
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            stage[lane * 8 + (q ^ (lane & 7))] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + fr;
-            const float4 o = stage[r * 8 + (fq ^ (r & 7))];
-            if (live(r)) *reinterpret_cast<float4*>(args.out_f32 + grow(r) * args.n + c0 + fq * 4) = o;
-          }
-          __syncwarp();
-        }
-        if (args.out_bf16) {
-          if (args.residual && !args.out_f32) __syncwarp();  // residual rows fully read before reuse
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[c * 8 + e * 2], f[c * 8 + e * 2 + 1]);
-              w[e] = *reinterpret_cast<const uint32_t*>(&b2);
-            }
-            stage_b[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = i * 8 + br;
-            const uint4 o = stage_b[r * 4 + (bc ^ ((r >> 1) & 3))];
-            if (live(r)) *reinterpret_cast<uint4*>(args.out_bf16 + grow(r) * args.n + c0 + bc * 8) = o;
-          }
-          __syncwarp();
-        }
-      }
-      if (args.head_w && live(lane)) {
-        // this thread's row is one square of one board
-        const long b = n0 + ((lane >> 3) & 1);
-        const int sq = ((2 * quad + (lane >> 4)) << 3) + (lane & 7);
-#pragma unroll
-        for (int hf = 0; hf < HEAD_MAX_F; ++hf) {
-          if (hf < args.pf + args.vf) {
-            const float y = fmaxf(hacc[hf] + args.head_b[hf], 0.0f);
-            if (hf < args.pf) args.featp[b * (args.pf * 64) + hf * 64 + sq] = y;
-            else args.featv[b * (args.vf * 64) + (hf - args.pf) * 64 + sq] = y;
-          }
-        }
-      }
+      epilogue_tile(args, smem_epi, s_bias, s_head, quad, lane, n0,
+                    tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS, &tmem_full[acc], acc_phase,
+                    &tmem_empty[acc], kLocalCta);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }

@@ -1,0 +1,202 @@
+// Two-SM variant of the implicit-GEMM convolution (conv_tc.cuh): the two CTAs of a cluster pair run ONE
+// tcgen05.mma.cta_group::2 per K step, M = 256 = four boards, each CTA contributing its 128 rows.
+//
+// Why: with the halo tile the activations cost almost nothing, and a tile is bound by the weight stream -- 32 KB per K
+// block that take ~1.2 us to arrive under load, so K blocks complete at (ring depth / latency).  In a CTA pair each
+// CTA stages only HALF of every weight block (its 128 of the 256 output channels; the tensor cores exchange the halves
+// over the pair's private path), so the same shared memory holds twice as many K blocks in flight, and each SM pulls
+// half the weight bytes from L2.
+//
+// Pair protocol (rank 0 = leader):
+//   * both CTAs load their own halo tiles and their own half of each weight block; every load counts its bytes on
+//     the LEADER's mbarrier (cp.async.bulk.tensor ... .cta_group::2 with a shared::cluster barrier address)
+//   * only the leader's warp 1 issues MMAs; tcgen05.commit.cta_group::2 ... multicast arrives on the stage-empty /
+//     accumulator-full barriers of BOTH CTAs
+//   * both CTAs' epilogue warps drain their own 128 accumulator rows and arrive on the leader's accumulator-empty
+//     barrier (8 arrivals: 4 local, 4 remote)
+#pragma once
+#include <cuda_bf16.h>
+
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace caz {
+namespace tc2 {
+
+using tc::ConvArgs;
+
+constexpr int THREADS = 256;
+constexpr int BLOCK_K = 64;
+constexpr int B_STAGES = 8;
+constexpr int B_STAGE_BYTES = 128 * BLOCK_K * 2;   // 16 KiB: this CTA's 128 weight rows of one K block
+constexpr int A_RING_BYTES = tc::A_RING_BYTES;
+constexpr int MAX_A_SLOTS = tc::MAX_A_SLOTS;
+constexpr int ACC_STAGES = 2;
+constexpr int ACC_COLS = 256;
+constexpr int SMEM_BYTES = A_RING_BYTES + B_STAGES * B_STAGE_BYTES + tc::EPI_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
+
+enum : int { ERR2_PRODUCER_B = 301, ERR2_PRODUCER_A = 302, ERR2_MMA_B = 303, ERR2_MMA_A = 304, ERR2_MMA_ACC = 305 };
+
+// tmap_w: weight rows [oc][K] with box 64 x (n/2)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_constant__ CUtensorMap tmap_w,
+                const ConvArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + A_RING_BYTES;
+  uint8_t* smem_epi = smem_b + B_STAGES * B_STAGE_BYTES;
+  float* s_bias = reinterpret_cast<float*>(smem_epi + 4 * tc::EPI_WARP_BYTES);
+  float* s_head = s_bias + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + tc::EPI_BYTES);
+  uint64_t* a_full = bars;                          // [MAX_A_SLOTS]   (the leader's copy is the live one)
+  uint64_t* a_empty = a_full + MAX_A_SLOTS;         // [MAX_A_SLOTS]   per CTA, multicast arrive
+  uint64_t* b_full = a_empty + MAX_A_SLOTS;         // [B_STAGES]      leader's copy live
+  uint64_t* b_empty = b_full + B_STAGES;            // [B_STAGES]      per CTA, multicast arrive
+  uint64_t* tmem_full = b_empty + B_STAGES;         // [ACC_STAGES]    per CTA, multicast arrive
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;    // [ACC_STAGES]    leader's copy live, 8 arrivals
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair0 = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1;
+  const int num_pairs = (args.num_tiles + 1) >> 1;
+  const int k = args.ksize, pad = (k - 1) / 2, hw = 8 + k - 1;
+  const int plane_bytes = hw * 2 * hw * 128;
+  const int a_slots = A_RING_BYTES / plane_bytes < MAX_A_SLOTS ? A_RING_BYTES / plane_bytes : MAX_A_SLOTS;
+  const int n_half = args.n >> 1;
+  const uint32_t b_bytes = static_cast<uint32_t>(n_half) * BLOCK_K * 2;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_halo);
+    ptx::prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < a_slots; ++i) {
+      ptx::mbar_init(&a_full[i], 1);
+      ptx::mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < B_STAGES; ++i) {
+      ptx::mbar_init(&b_full[i], 1);
+      ptx::mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      ptx::mbar_init(&tmem_full[i], 1);
+      ptx::mbar_init(&tmem_empty[i], 8);  // four epilogue warps in each CTA of the pair
+    }
+    ptx::mbar_fence_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2cta(tmem_base_slot, ACC_STAGES * ACC_COLS);
+    ptx::tmem_relinquish_2cta();
+  }
+  if (threadIdx.x < args.n) s_bias[threadIdx.x] = args.bias[threadIdx.x];
+  if (args.head_w)
+    for (int i = threadIdx.x; i < (args.pf + args.vf) * args.n; i += THREADS) s_head[i] = args.head_w[i];
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== weight producer: this CTA's half of the output channels =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pair = pair0; pair < num_pairs; pair += n_pairs_grid)
+      for (int kc = 0; kc < args.kchunks; ++kc)
+        for (int tap = 0; tap < k * k; ++tap) {
+          ptx::mbar_wait(&b_empty[stage], phase ^ 1, args.err_flag, ERR2_PRODUCER_B);
+          if (ptx::elect_one()) {
+            if (leader) ptx::mbar_expect_tx(&b_full[stage], 2 * b_bytes);   // both CTAs' halves
+            ptx::tma_load_2d_2cta(smem_b + stage * B_STAGE_BYTES, &tmap_w, ptx::mapa_u32(&b_full[stage], 0),
+                                  (tap * args.kchunks + kc) * BLOCK_K, static_cast<int>(rank) * n_half);
+          }
+          __syncwarp();
+          if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+        }
+  } else if (warp == 3) {
+    // ===================== activation producer: this CTA's two boards =====================
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int pair = pair0; pair < num_pairs; pair += n_pairs_grid) {
+      const int tile = 2 * pair + static_cast<int>(rank);
+      for (int kc = 0; kc < args.kchunks; ++kc) {
+        ptx::mbar_wait(&a_empty[slot], phase ^ 1, args.err_flag, ERR2_PRODUCER_A);
+        if (ptx::elect_one()) {
+          if (leader) ptx::mbar_expect_tx(&a_full[slot], 2 * plane_bytes);
+          ptx::tma_load_4d_2cta(smem_a + slot * plane_bytes, &tmap_halo, ptx::mapa_u32(&a_full[slot], 0), kc * BLOCK_K,
+                                -pad, tile * 2, -pad);
+        }
+        __syncwarp();
+        if (++slot == a_slots) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (leader) {
+      const uint32_t idesc = ptx::idesc_bf16_f32(256, args.n);
+      const uint64_t a_desc0 = tc::desc_sw128(ptx::smem_u32(smem_a), hw * 128);
+      const uint64_t b_desc0 = tc::desc_sw128(ptx::smem_u32(smem_b), 1024);
+      int stage = 0, slot = 0, acc = 0;
+      uint32_t phase = 0, a_phase = 0, acc_phase = 0;
+      for (int pair = pair0; pair < num_pairs; pair += n_pairs_grid) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, args.err_flag, ERR2_MMA_ACC);
+        ptx::tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+        for (int kc = 0; kc < args.kchunks; ++kc) {
+          ptx::mbar_wait(&a_full[slot], a_phase, args.err_flag, ERR2_MMA_A);
+          const uint64_t a_plane = a_desc0 + static_cast<uint64_t>((slot * plane_bytes) >> 4);
+          for (int dy = 0; dy < k; ++dy)
+            for (int dx = 0; dx < k; ++dx) {
+              ptx::mbar_wait(&b_full[stage], phase, args.err_flag, ERR2_MMA_B);
+              ptx::tcgen05_fence_after();
+              if (ptx::elect_one()) {
+                const uint64_t adesc = a_plane + static_cast<uint64_t>((dy * 2 * hw + dx) * 8);
+                const uint64_t bdesc = b_desc0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
+                const uint32_t first = (kc | dy | dx) == 0 ? 0u : 1u;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  ptx::mma_bf16_ss_2cta(tmem_d, adesc + kk * 2, bdesc + kk * 2, idesc, kk == 0 ? first : 1u);
+                ptx::mma_commit_2cta(&b_empty[stage]);
+                if (dy == k - 1 && dx == k - 1) {
+                  ptx::mma_commit_2cta(&a_empty[slot]);
+                  if (kc == args.kchunks - 1) ptx::mma_commit_2cta(&tmem_full[acc]);
+                }
+              }
+              __syncwarp();
+              if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+            }
+          if (++slot == a_slots) { slot = 0; a_phase ^= 1; }
+        }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: this CTA's 128 rows =====================
+    const int quad = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int pair = pair0; pair < num_pairs; pair += n_pairs_grid) {
+      const int tile = 2 * pair + static_cast<int>(rank);
+      tc::epilogue_tile(args, smem_epi, s_bias, s_head, quad, lane, tile * 2,
+                        tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS, &tmem_full[acc], acc_phase,
+                        &tmem_empty[acc], 0u /* the leader owns the accumulator-empty barrier */);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();  // nobody frees TMEM or exits while the peer may still signal it
+  if (warp == 2) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc_2cta(tmem_base, ACC_STAGES * ACC_COLS);
+  }
+}
+
+}  // namespace tc2
+}  // namespace caz
