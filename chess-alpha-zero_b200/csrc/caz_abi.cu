@@ -104,6 +104,7 @@ struct caz_handle {
   uint8_t *d_mask2 = nullptr, *d_records2 = nullptr;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_in[2] = {}, ev_fwd[2] = {}, ev_out[2] = {};
+  int next_slot = 0;
   int* err_flag_host = nullptr;  // mapped pinned: readable even after a device trap
   int* err_flag_dev = nullptr;
   // PUCT scratch
@@ -804,6 +805,37 @@ int caz_eval_device(caz_handle* h, const float* d_planes, int32_t batch, float* 
   return forward(h, d_planes, nullptr, batch, d_policy, d_value, (flags & CAZ_EVAL_MASKED_SOFTMAX) ? d_legal_mask : nullptr);
 }
 
+// One chunk (<= max_batch positions) through the three-stream pipeline: H2D on copy_in, forward on the compute
+// stream, D2H on copy_out, chained by events; `slot` picks one of the two staging buffer sets.  Nothing here blocks
+// the host.  Waiting on an event that was never recorded is a no-op, so first uses need no special case.
+static int enqueue_pipelined(caz_handle* h, int slot, const float* planes, const uint8_t* records, int32_t nb,
+                             float* policy, float* value, const uint8_t* legal_mask, bool masked) {
+  const caz_arch& a = h->arch;
+  const size_t pin = (size_t)a.input_planes * 64;
+  float* dpl = slot ? h->d_planes2 : h->d_planes;
+  float* dpo = slot ? h->d_policy2 : h->d_policy;
+  float* dva = slot ? h->d_value2 : h->d_value;
+  uint8_t* dma = slot ? h->d_mask2 : h->d_mask;
+  uint8_t* dre = slot ? h->d_records2 : h->d_records;
+  int rc;
+  // this slot's inputs are free once the last forward pass that read them has finished
+  CU_TRY(h, cudaStreamWaitEvent(h->copy_in, h->ev_fwd[slot], 0));
+  if (planes) CU_TRY(h, cudaMemcpyAsync(dpl, planes, (size_t)nb * pin * 4, cudaMemcpyHostToDevice, h->copy_in));
+  else CU_TRY(h, cudaMemcpyAsync(dre, records, (size_t)nb * CAZ_RECORD_BYTES, cudaMemcpyHostToDevice, h->copy_in));
+  if (masked) CU_TRY(h, cudaMemcpyAsync(dma, legal_mask, (size_t)nb * a.n_labels, cudaMemcpyHostToDevice, h->copy_in));
+  CU_TRY(h, cudaEventRecord(h->ev_in[slot], h->copy_in));
+  CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
+  // ... and its outputs once the last D2H that drained them has finished
+  CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_out[slot], 0));
+  if ((rc = forward(h, planes ? dpl : nullptr, planes ? nullptr : dre, nb, dpo, dva, masked ? dma : nullptr))) return rc;
+  CU_TRY(h, cudaEventRecord(h->ev_fwd[slot], h->stream));
+  CU_TRY(h, cudaStreamWaitEvent(h->copy_out, h->ev_fwd[slot], 0));
+  CU_TRY(h, cudaMemcpyAsync(policy, dpo, (size_t)nb * a.n_labels * 4, cudaMemcpyDeviceToHost, h->copy_out));
+  CU_TRY(h, cudaMemcpyAsync(value, dva, (size_t)nb * 4, cudaMemcpyDeviceToHost, h->copy_out));
+  CU_TRY(h, cudaEventRecord(h->ev_out[slot], h->copy_out));
+  return CAZ_OK;
+}
+
 static int eval_host(caz_handle* h, const float* planes, const uint8_t* records, int32_t batch, float* policy,
                      float* value, const uint8_t* legal_mask, uint32_t flags) {
   if (!h) return CAZ_ERR_INVALID;
@@ -815,47 +847,55 @@ static int eval_host(caz_handle* h, const float* planes, const uint8_t* records,
   if ((rc = set_device(h))) return rc;
   const caz_arch& a = h->arch;
   const size_t pin = (size_t)a.input_planes * 64;
-  // Chunking: a small batch is one chunk (latency).  A large one is cut into chunks of five full waves of the
-  // conv kernel (2 boards per tile x SM count per wave) so that chunk k+1's H2D and chunk k-1's D2H run on the
-  // copy engines under chunk k's forward pass; chunks alternate between two staging slots.
-  const int32_t wave = 2 * h->num_sms;
-  int32_t chunk = h->max_batch;
-  if (batch > 4 * wave && 5 * wave < chunk) chunk = 5 * wave;
-  float* dpl[2] = {h->d_planes, h->d_planes2};
-  float* dpo[2] = {h->d_policy, h->d_policy2};
-  float* dva[2] = {h->d_value, h->d_value2};
-  uint8_t* dma[2] = {h->d_mask, h->d_mask2};
-  uint8_t* dre[2] = {h->d_records, h->d_records2};
-  const bool single = batch <= chunk;  // one stream, no cross-stream events: the latency path
-  cudaStream_t sin = single ? h->stream : h->copy_in, sout = single ? h->stream : h->copy_out;
+  if (batch <= h->max_batch) {
+    // One pass on one stream, no cross-stream events: the latency path.  (Cutting a batch into pipelined chunks was
+    // measured: the smaller launches lose what the copy overlap gains; overlap ACROSS calls is caz_submit/caz_collect.)
+    CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_out[0], 0));   // a still-draining caz_submit on slot 0
+    if (planes) CU_TRY(h, cudaMemcpyAsync(h->d_planes, planes, (size_t)batch * pin * 4, cudaMemcpyHostToDevice, h->stream));
+    else CU_TRY(h, cudaMemcpyAsync(h->d_records, records, (size_t)batch * CAZ_RECORD_BYTES, cudaMemcpyHostToDevice, h->stream));
+    if (masked) CU_TRY(h, cudaMemcpyAsync(h->d_mask, legal_mask, (size_t)batch * a.n_labels, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = forward(h, planes ? h->d_planes : nullptr, planes ? nullptr : h->d_records, batch, h->d_policy, h->d_value, masked ? h->d_mask : nullptr))) return rc;
+    CU_TRY(h, cudaMemcpyAsync(policy, h->d_policy, (size_t)batch * a.n_labels * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(value, h->d_value, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return CAZ_OK;
+  }
+  // larger than the device buffers: max_batch-sized chunks, alternating staging slots, copies under compute
   int c = 0;
   for (int32_t off = 0; off < batch; ++c) {
-    int32_t nb = batch - off < chunk ? batch - off : chunk;
-    if (batch - off - nb > 0 && batch - off - nb < wave && batch - off <= h->max_batch) nb = batch - off;  // no sliver
-    const int s = c & 1;
-    // slot s inputs are free once the forward pass of chunk c-2 has consumed them
-    if (!single && c >= 2) CU_TRY(h, cudaStreamWaitEvent(sin, h->ev_fwd[s], 0));
-    if (planes) CU_TRY(h, cudaMemcpyAsync(dpl[s], planes + (size_t)off * pin, (size_t)nb * pin * 4, cudaMemcpyHostToDevice, sin));
-    else CU_TRY(h, cudaMemcpyAsync(dre[s], records + (size_t)off * CAZ_RECORD_BYTES, (size_t)nb * CAZ_RECORD_BYTES, cudaMemcpyHostToDevice, sin));
-    if (masked) CU_TRY(h, cudaMemcpyAsync(dma[s], legal_mask + (size_t)off * a.n_labels, (size_t)nb * a.n_labels, cudaMemcpyHostToDevice, sin));
-    if (!single) {
-      CU_TRY(h, cudaEventRecord(h->ev_in[s], sin));
-      CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_in[s], 0));
-      // slot s outputs are free once chunk c-2's D2H has drained them
-      if (c >= 2) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_out[s], 0));
-    }
-    if ((rc = forward(h, planes ? dpl[s] : nullptr, planes ? nullptr : dre[s], nb, dpo[s], dva[s], masked ? dma[s] : nullptr))) return rc;
-    if (!single) {
-      CU_TRY(h, cudaEventRecord(h->ev_fwd[s], h->stream));
-      CU_TRY(h, cudaStreamWaitEvent(sout, h->ev_fwd[s], 0));
-    }
-    CU_TRY(h, cudaMemcpyAsync(policy + (size_t)off * a.n_labels, dpo[s], (size_t)nb * a.n_labels * 4, cudaMemcpyDeviceToHost, sout));
-    CU_TRY(h, cudaMemcpyAsync(value + off, dva[s], (size_t)nb * 4, cudaMemcpyDeviceToHost, sout));
-    if (!single) CU_TRY(h, cudaEventRecord(h->ev_out[s], sout));
+    const int32_t nb = batch - off < h->max_batch ? batch - off : h->max_batch;
+    if ((rc = enqueue_pipelined(h, c & 1, planes ? planes + (size_t)off * pin : nullptr,
+                                records ? records + (size_t)off * CAZ_RECORD_BYTES : nullptr, nb,
+                                policy + (size_t)off * a.n_labels, value + off,
+                                masked ? legal_mask + (size_t)off * a.n_labels : nullptr, masked))) return rc;
     off += nb;
   }
-  if (!single) CU_TRY(h, cudaStreamSynchronize(h->copy_out));
+  CU_TRY(h, cudaStreamSynchronize(h->copy_out));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return CAZ_OK;
+}
+
+int caz_submit(caz_handle* h, const float* planes, int32_t batch, float* policy, float* value, const uint8_t* legal_mask,
+               uint32_t flags, int32_t* ticket) {
+  if (!h) return CAZ_ERR_INVALID;
+  if (!planes || !policy || !value || !ticket || batch < 1 || batch > h->max_batch)
+    return fail(h, CAZ_ERR_INVALID, fmt("caz_submit: bad argument (batch %d, max_batch %d)", batch, h->max_batch));
+  const bool masked = (flags & CAZ_EVAL_MASKED_SOFTMAX) != 0;
+  if (masked && !legal_mask) return fail(h, CAZ_ERR_INVALID, "masked softmax needs a legal mask");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  const int slot = h->next_slot;
+  if ((rc = enqueue_pipelined(h, slot, planes, nullptr, batch, policy, value, legal_mask, masked))) return rc;
+  h->next_slot ^= 1;
+  *ticket = slot;
+  return CAZ_OK;
+}
+
+int caz_collect(caz_handle* h, int32_t ticket) {
+  if (!h || ticket < 0 || ticket > 1) return fail(h, CAZ_ERR_INVALID, "caz_collect: bad ticket");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  CU_TRY(h, cudaEventSynchronize(h->ev_out[ticket]));
   return CAZ_OK;
 }
 

@@ -81,6 +81,21 @@ class Evaluator:
                                     _lib.ptr(legal_mask), flags)
             _lib.check(self._handle, rc)
 
+    def submit(self, planes, policy, value, legal_mask=None):
+        """Non-blocking predict_into: returns a ticket for collect().  Keep at most two in flight; the host
+        buffers (ideally pinned) must stay untouched until collected.  Copies of one batch then overlap the forward
+        pass of the other."""
+        ticket = ctypes.c_int32(-1)
+        flags = _lib.EVAL_MASKED_SOFTMAX if legal_mask is not None else 0
+        with self._lock:
+            rc = self._lib.caz_submit(self._handle, _lib.ptr(planes), planes.shape[0], _lib.ptr(policy),
+                                      _lib.ptr(value), _lib.ptr(legal_mask), flags, ctypes.byref(ticket))
+            _lib.check(self._handle, rc)
+        return ticket.value
+
+    def collect(self, ticket):
+        _lib.check(self._handle, self._lib.caz_collect(self._handle, int(ticket)))
+
     def predict_records(self, records, legal_mask=None):
         """Board records (68 B each, see encoder.fen_to_record) in; the encoder runs on the device."""
         r = _lib.as_array(records, np.uint8)

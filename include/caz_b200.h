@@ -118,6 +118,15 @@ int caz_eval_device(caz_handle* h, const float* d_planes, int32_t batch, float* 
 int caz_eval_records(caz_handle* h, const uint8_t* records, int32_t batch, float* policy, float* value,
                      const uint8_t* legal_mask, uint32_t flags);
 
+/* Pipelined form of caz_eval for callers that keep two batches in flight (batch <= max_batch): caz_submit enqueues
+ * H2D, forward pass and D2H on three streams and returns at once with a ticket (0 or 1, alternating staging slots);
+ * caz_collect(ticket) blocks until that batch's outputs are in the caller's host buffers.  Batch i+1's H2D and
+ * batch i-1's D2H then run under batch i's forward pass.  At most two tickets may be outstanding; host buffers must
+ * stay valid (and should be pinned, caz_host_alloc) until collected. */
+int caz_submit(caz_handle* h, const float* planes, int32_t batch, float* policy, float* value,
+               const uint8_t* legal_mask, uint32_t flags, int32_t* ticket);
+int caz_collect(caz_handle* h, int32_t ticket);
+
 int caz_sync(caz_handle* h);
 
 /* Replaces canon_input_planes (env/chess_env.py:231-348) for a batch of positions.

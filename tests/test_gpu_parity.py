@@ -271,6 +271,27 @@ def test_empty_batch_and_chunking(net, ev_bf16):
     assert np.array_equal(p[256:512], base_p) and np.array_equal(p[1024:1100], base_p[:76])
 
 
+def test_submit_collect_pipelined_api(net, ev_bf16):
+    """Two batches in flight through caz_submit / caz_collect give exactly what the synchronous call gives."""
+    from chess_alpha_zero_b200 import _lib
+    x = net[2]
+    want = [ev_bf16.predict_on_batch(x[:200]), ev_bf16.predict_on_batch(x[56:256])]
+    pins = [(_lib.PinnedArray((200, 18, 8, 8), np.float32), _lib.PinnedArray((200, 1968), np.float32),
+             _lib.PinnedArray((200, 1), np.float32)) for _ in range(2)]
+    pins[0][0].array[:] = x[:200]
+    pins[1][0].array[:] = x[56:256]
+    for rounds in range(3):
+        t = [ev_bf16.submit(pins[i][0].array, pins[i][1].array, pins[i][2].array) for i in range(2)]
+        assert sorted(t) == [0, 1]
+        for i in range(2):
+            ev_bf16.collect(t[i])
+            assert np.array_equal(pins[i][1].array, want[i][0]) and np.array_equal(pins[i][2].array, want[i][1])
+        for i in range(2):
+            pins[i][1].array[:] = 0
+    with pytest.raises(caz.CazError):
+        ev_bf16.submit(np.zeros((513, 18, 8, 8), np.float32), np.zeros((513, 1968), np.float32), np.zeros((513, 1), np.float32))
+
+
 def test_shipped_json_variant_and_reload(net):
     cfg = oweights.keras_config(stem_k=3, value_filters=1)         # what data/model/model_best_config.json holds
     w = oweights.synth_weights(cfg, seed=4, recipe="randomized")
