@@ -247,7 +247,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="positions per GPU per step")
     ap.add_argument("--blocks", type=int, default=7, help="residual blocks (19 = config 5)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
@@ -371,7 +371,7 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": {"workload": f"{args.blocks}x256 policy/value net, 5x5 stem, batch {B} per GPU "
                                f"(BASELINE.json configs[{1 if args.blocks == 7 else 4}])",
                    "res_blocks": args.blocks, "batch_per_gpu": B, "global_batch": B * world,

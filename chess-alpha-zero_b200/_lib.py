@@ -13,6 +13,7 @@ from . import build as _build
 CAZ_OK = 0
 PRECISION_BF16 = 0
 PRECISION_FP32 = 1
+PRECISION_FP16 = 2
 EVAL_MASKED_SOFTMAX = 1
 RECORD_BYTES = 68
 STAGES = 4

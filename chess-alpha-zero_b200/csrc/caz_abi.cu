@@ -3,6 +3,7 @@
 // construction, buffer ownership, the per-layer launch sequence of the forward pass.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -151,7 +152,8 @@ int fail(caz_handle* h, int code, const std::string& msg) {
 
 int expected_tensor_count(const caz_arch& a) { return 5 + 10 * a.res_blocks + 7 + 9; }
 
-bool tensor_path(const caz_handle* h) { return h->precision == CAZ_PRECISION_BF16; }
+bool tensor_path(const caz_handle* h) { return h->precision == CAZ_PRECISION_BF16 || h->precision == CAZ_PRECISION_FP16; }
+bool is_fp16(const caz_handle* h) { return h->precision == CAZ_PRECISION_FP16; }
 
 // BatchNorm inference folded into the preceding bias-free convolution (Keras semantics,
 // model_chess.py:65-69): y = conv(x)*inv + (beta - mean*inv), inv = gamma / sqrt(var + eps).
@@ -176,7 +178,7 @@ int make_tmap(caz_handle* h, CUtensorMap* m, void* base, int rank, const cuuint6
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(h, CAZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, ones,
+  CUresult r = enc(m, is_fp16(h) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, ones,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, CAZ_ERR_CUDA, fmt("cuTensorMapEncodeTiled failed with CUresult %d", (int)r));
@@ -249,11 +251,19 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
     }
     if (tcp) {
       // W[oc][tap*cin_pad + ic] bf16, K-major rows: the B operand of the implicit GEMM
-      std::vector<__nv_bfloat16> wp(ktot * F, __float2bfloat16(0.0f));
+      // 16-bit words: bf16, or fp16 in the FP16 build (both have a +0.0 bit pattern of 0)
+      std::vector<uint16_t> wp(ktot * F, 0);
+      const bool f16 = is_fp16(h);
       for (int tap = 0; tap < taps; ++tap)
         for (int ic = 0; ic < cin; ++ic) {
           const float* src = kt.data + ((size_t)tap * cin + ic) * F;
-          for (int oc = 0; oc < F; ++oc) wp[(size_t)oc * ktot + (size_t)tap * cin_pad + ic] = __float2bfloat16_rn(src[oc] * inv[oc]);
+          for (int oc = 0; oc < F; ++oc) {
+            const float v = src[oc] * inv[oc];
+            uint16_t bits;
+            if (f16) { const __half hv = __float2half_rn(v); memcpy(&bits, &hv, 2); }
+            else { const __nv_bfloat16 bv = __float2bfloat16_rn(v); memcpy(&bits, &bv, 2); }
+            wp[(size_t)oc * ktot + (size_t)tap * cin_pad + ic] = bits;
+          }
         }
       int rc = upload(h, L.w, wp.data(), wp.size() * 2);
       if (rc) return rc;
@@ -348,6 +358,7 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
     args.featv = h->featv;
     args.pf = h->arch.policy_filters;
     args.vf = h->arch.value_filters;
+    args.fp16 = is_fp16(h) ? 1 : 0;
     args.err_flag = h->err_flag_dev;
     if (h->use_2cta && args.num_tiles >= 2 && L.cout % 64 == 0) {
       // CTA pairs: one cta_group::2 MMA covers two tiles (four boards)
@@ -465,6 +476,7 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   args.blk_k = a.block_kernel;
   args.in_planes = a.input_planes;
   args.in_cpad = h->in_cpad;
+  args.fp16 = is_fp16(h) ? 1 : 0;
   const int sb_stem = caz::sb::taps_per_slot(a.stem_kernel, ns) * ns * 128;
   const int sb_blk = a.res_blocks > 0 ? caz::sb::taps_per_slot(a.block_kernel, ns) * ns * 128 : 0;
   args.slot_bytes = sb_stem > sb_blk ? sb_stem : sb_blk;
@@ -559,13 +571,15 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
   // ---- stage 0: input pack (NCHW fp32 planes -> NHWC activations, channels zero-padded) ----
   if (d_planes) {
     const size_t smem = (size_t)a.input_planes * 65 * sizeof(float);
-    if (tcp) caz::pack_planes_kernel<__nv_bfloat16><<<batch, 256, smem, h->stream>>>(d_planes, static_cast<__nv_bfloat16*>(h->in_act), batch, a.input_planes, h->in_cpad);
+    if (tcp && is_fp16(h)) caz::pack_planes_kernel<__half><<<batch, 256, smem, h->stream>>>(d_planes, static_cast<__half*>(h->in_act), batch, a.input_planes, h->in_cpad);
+    else if (tcp) caz::pack_planes_kernel<__nv_bfloat16><<<batch, 256, smem, h->stream>>>(d_planes, static_cast<__nv_bfloat16*>(h->in_act), batch, a.input_planes, h->in_cpad);
     else caz::pack_planes_kernel<float><<<batch, 256, smem, h->stream>>>(d_planes, static_cast<float*>(h->in_act), batch, a.input_planes, h->in_cpad);
     if ((rc = check_launch(h, "pack_planes_kernel"))) return rc;
   } else {
     const size_t total = (size_t)batch * 64 * h->in_cpad;
     const int blocks = (int)((total + 255) / 256);
-    if (tcp) caz::encode_pack_kernel<__nv_bfloat16><<<blocks, 256, 0, h->stream>>>(d_records, static_cast<__nv_bfloat16*>(h->in_act), batch, h->in_cpad);
+    if (tcp && is_fp16(h)) caz::encode_pack_kernel<__half><<<blocks, 256, 0, h->stream>>>(d_records, static_cast<__half*>(h->in_act), batch, h->in_cpad);
+    else if (tcp) caz::encode_pack_kernel<__nv_bfloat16><<<blocks, 256, 0, h->stream>>>(d_records, static_cast<__nv_bfloat16*>(h->in_act), batch, h->in_cpad);
     else caz::encode_pack_kernel<float><<<blocks, 256, 0, h->stream>>>(d_records, static_cast<float*>(h->in_act), batch, h->in_cpad);
     if ((rc = check_launch(h, "encode_pack_kernel"))) return rc;
   }
@@ -683,15 +697,15 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   if (!arch || !tensors || !out) return fail(nullptr, CAZ_ERR_INVALID, "null argument");
   *out = nullptr;
   const caz_arch& a = *arch;
-  if (precision != CAZ_PRECISION_BF16 && precision != CAZ_PRECISION_FP32)
-    return fail(nullptr, CAZ_ERR_INVALID, "precision must be CAZ_PRECISION_BF16 or CAZ_PRECISION_FP32");
+  if (precision != CAZ_PRECISION_BF16 && precision != CAZ_PRECISION_FP32 && precision != CAZ_PRECISION_FP16)
+    return fail(nullptr, CAZ_ERR_INVALID, "precision must be CAZ_PRECISION_BF16, CAZ_PRECISION_FP16 or CAZ_PRECISION_FP32");
   if (max_batch < 1) return fail(nullptr, CAZ_ERR_INVALID, "max_batch must be >= 1");
   if (a.input_planes < 1 || a.input_planes > 64 || a.res_blocks < 0 || a.filters < 1 || a.policy_filters < 1 ||
       a.value_filters < 1 || a.policy_filters + a.value_filters > caz::HEAD_MAX_F || a.value_fc < 1 ||
       a.n_labels < 1 || a.n_labels > caz::PNJ * 256 || (a.stem_kernel & 1) == 0 || (a.block_kernel & 1) == 0 ||
       a.stem_kernel > 7 || a.block_kernel > 7)
     return fail(nullptr, CAZ_ERR_INVALID, "architecture outside the supported envelope");
-  if (precision == CAZ_PRECISION_BF16 && (a.filters % 64 != 0 || a.filters > 256))
+  if (precision != CAZ_PRECISION_FP32 && (a.filters % 64 != 0 || a.filters > 256))
     return fail(nullptr, CAZ_ERR_INVALID,
                 "the tensor-core build needs filters to be a multiple of 64 and <= 256; use CAZ_PRECISION_FP32");
   int count = 0;
@@ -726,7 +740,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   CREATE_TRY(cudaHostAlloc(&h->err_flag_host, sizeof(int), cudaHostAllocMapped));
   *h->err_flag_host = 0;
   CREATE_TRY(cudaHostGetDevicePointer(&h->err_flag_dev, h->err_flag_host, 0));
-  const bool tcp = precision == CAZ_PRECISION_BF16;
+  const bool tcp = precision != CAZ_PRECISION_FP32;
   const size_t esz = tcp ? 2 : 4;
   const size_t cap = (size_t)max_batch;
   h->in_cpad = tcp ? 64 : a.input_planes;
@@ -1025,13 +1039,15 @@ int caz_debug_conv_layer(caz_handle* h, int32_t layer, const float* in, const fl
   const CUtensorMap* tm = layer == 0 ? &h->tmap_in : &h->tmap_act[1];
   const int cpad = layer == 0 ? h->in_cpad : F;
   const unsigned gi = (unsigned)((rows * cpad + 255) / 256), go = (unsigned)((rows * F + 255) / 256);
-  if (tcp) caz::cast_pad_kernel<__nv_bfloat16><<<gi, 256, 0, h->stream>>>(d_in, (__nv_bfloat16*)a_in, rows, L.cin, cpad);
+  if (tcp && is_fp16(h)) caz::cast_pad_kernel<__half><<<gi, 256, 0, h->stream>>>(d_in, (__half*)a_in, rows, L.cin, cpad);
+  else if (tcp) caz::cast_pad_kernel<__nv_bfloat16><<<gi, 256, 0, h->stream>>>(d_in, (__nv_bfloat16*)a_in, rows, L.cin, cpad);
   else caz::cast_pad_kernel<float><<<gi, 256, 0, h->stream>>>(d_in, (float*)a_in, rows, L.cin, cpad);
   if ((rc = check_launch(h, "cast_pad_kernel"))) return rc;
   float* xf = static_cast<float*>(h->act[2]);
   if (residual) CU_TRY(h, cudaMemcpyAsync(xf, d_res, rows * F * 4, cudaMemcpyDeviceToDevice, h->stream));
   if ((rc = launch_conv(h, layer, a_in, tm, cpad, residual ? xf : nullptr, h->act[0], (tcp && (residual || layer == 0)) ? xf : nullptr, batch))) return rc;
-  if (tcp) caz::widen_kernel<__nv_bfloat16><<<go, 256, 0, h->stream>>>((const __nv_bfloat16*)h->act[0], d_out, rows * F);
+  if (tcp && is_fp16(h)) caz::widen_kernel<__half><<<go, 256, 0, h->stream>>>((const __half*)h->act[0], d_out, rows * F);
+  else if (tcp) caz::widen_kernel<__nv_bfloat16><<<go, 256, 0, h->stream>>>((const __nv_bfloat16*)h->act[0], d_out, rows * F);
   else caz::widen_kernel<float><<<go, 256, 0, h->stream>>>((const float*)h->act[0], d_out, rows * F);
   if ((rc = check_launch(h, "widen_kernel"))) return rc;
   CU_TRY(h, cudaMemcpyAsync(out, d_out, rows * F * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -59,6 +59,7 @@ struct Args {
   int stem_k, stem_kchunks;  // stem kernel size, input channel chunks (in_cpad / 64)
   int blk_k;                  // tower kernel size
   int in_planes, in_cpad;
+  int fp16;                   // 16-bit operands are fp16 instead of bf16
   int slot_bytes, n_slots;    // weight ring geometry
   const float* planes;        // fp32 [batch][in_planes][64] or nullptr
   const uint8_t* records;     // u8 [batch][68] or nullptr (exactly one of the two)
@@ -226,7 +227,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         if (c < args.in_planes)
           v = args.planes ? args.planes[(static_cast<size_t>(b) * args.in_planes + c) * 64 + sq]
                           : record_plane_value(args.records + static_cast<size_t>(b) * 68, c, sq);
-        dst[i] = __float2bfloat16_rn(v);
+        reinterpret_cast<uint16_t*>(dst)[i] = ptx::pack_h16(v, args.fp16 != 0);
       }
     }
     __threadfence();
@@ -289,7 +290,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     // ============ MMA issuers (two warps: a tcgen05.mma costs its issuing thread ~60 cycles whatever its shape,
     // so with N = 16..64 the issue rate, not the tensor pipe, bounds a layer) ============
     const int which = warp - 1;
-    const uint32_t idesc = ptx::idesc_bf16_f32(64 * args.nb, args.ns);
+    const uint32_t idesc = ptx::idesc_h16_f32(64 * args.nb, args.ns, args.fp16 != 0);
     const uint64_t b_desc0 = desc_sw128(ptx::smem_u32(smem_w), 1024);
     const int tap_desc = tap_bytes >> 4;
     int slot = 0;
@@ -401,8 +402,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1]);
-              pk[e] = *reinterpret_cast<const uint32_t*>(&b2);
+              pk[e] = ptx::pack_h16x2(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1], args.fp16 != 0);
             }
             *reinterpret_cast<uint4*>(orow + q * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }

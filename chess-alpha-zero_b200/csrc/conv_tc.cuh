@@ -76,6 +76,7 @@ struct ConvArgs {
   float* featp;             // [batch][pf*64]
   float* featv;             // [batch][vf*64]
   int pf, vf;
+  int fp16;                 // 16-bit operands are fp16 instead of bf16 (CAZ_PRECISION_FP16)
   int* err_flag;
 };
 
@@ -215,8 +216,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[c * 8 + e * 2], f[c * 8 + e * 2 + 1]);
-          w[e] = *reinterpret_cast<const uint32_t*>(&b2);
+          w[e] = ptx::pack_h16x2(f[c * 8 + e * 2], f[c * 8 + e * 2 + 1], args.fp16 != 0);
         }
         stage_b[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_uint4(w[0], w[1], w[2], w[3]);
       }
@@ -336,7 +336,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_const
       }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = ptx::idesc_bf16_f32(BLOCK_M, args.n);
+    const uint32_t idesc = ptx::idesc_h16_f32(BLOCK_M, args.n, args.fp16 != 0);
     // descriptors differ only in the 14-bit start-address field: add (byte offset >> 4) to a template
     const uint64_t a_desc0 = desc_sw128(ptx::smem_u32(smem_a), hw * 128);  // next 8-row group = next (rank, board)
     const uint64_t b_desc0 = desc_sw128(ptx::smem_u32(smem_b), 1024);

@@ -138,7 +138,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (leader only) =====================
     if (leader) {
-      const uint32_t idesc = ptx::idesc_bf16_f32(256, args.n);
+      const uint32_t idesc = ptx::idesc_h16_f32(256, args.n, args.fp16 != 0);
       const uint64_t a_desc0 = tc::desc_sw128(ptx::smem_u32(smem_a), hw * 128);
       const uint64_t b_desc0 = tc::desc_sw128(ptx::smem_u32(smem_b), 1024);
       int stage = 0, slot = 0, acc = 0;

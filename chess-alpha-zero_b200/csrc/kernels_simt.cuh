@@ -3,6 +3,7 @@
 // Reference semantics cited per kernel; paths relative to /root/reference/src/chess_zero.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -14,8 +15,12 @@ template <>
 __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 template <typename T>
 __device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f)); }
 template <>
 __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>

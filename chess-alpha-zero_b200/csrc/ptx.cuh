@@ -3,6 +3,8 @@
 // generic and async proxies.  One instruction per wrapper; no library dependencies.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -297,6 +299,29 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
+}
+// same with fp16 operands (format code 0) when `fp16` is set: identical tensor throughput, 11-bit significand
+__host__ __device__ constexpr uint32_t idesc_h16_f32(int m, int n, bool fp16) {
+  return fp16 ? ((1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24))
+              : idesc_bf16_f32(m, n);
+}
+
+// two fp32 values -> one 32-bit word of 16-bit operands (bf16, or fp16 saturated to its finite range)
+__device__ __forceinline__ uint32_t pack_h16x2(float a, float b, bool fp16) {
+  if (fp16) {
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint16_t pack_h16(float a, bool fp16) {
+  if (fp16) {
+    const __half h = __float2half_rn(fminf(fmaxf(a, -65504.0f), 65504.0f));
+    return *reinterpret_cast<const uint16_t*>(&h);
+  }
+  const __nv_bfloat16 h = __float2bfloat16_rn(a);
+  return *reinterpret_cast<const uint16_t*>(&h);
 }
 
 }  // namespace ptx

@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib
 from .keras_graph import parse_config
 
-_PRECISIONS = {"bf16": _lib.PRECISION_BF16, "fp32": _lib.PRECISION_FP32}
+_PRECISIONS = {"bf16": _lib.PRECISION_BF16, "fp16": _lib.PRECISION_FP16, "fp32": _lib.PRECISION_FP32}
 
 
 class Evaluator:

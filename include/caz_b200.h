@@ -38,6 +38,8 @@ extern "C" {
 /* numeric builds (BASELINE.json north_star: "fp32-accumulate build" and "bf16 build") */
 #define CAZ_PRECISION_BF16 0  /* bf16 operands on tcgen05 tensor cores, fp32 TMEM accumulators, fp32 heads */
 #define CAZ_PRECISION_FP32 1  /* fp32 operands and accumulation on the CUDA cores (1e-4 parity build)      */
+#define CAZ_PRECISION_FP16 2  /* the tensor-core build with fp16 operands: same kernels and throughput as BF16, 8x finer
+                                 operand rounding; activations are saturated to +-65504 when stored as operands   */
 
 /* eval flags */
 #define CAZ_EVAL_DEFAULT 0

@@ -195,6 +195,18 @@ def test_bf16_build_matches_oracle_reference_init(net_default):
     ev.close()
 
 
+def test_fp16_build_matches_oracle_reference_init(net_default, net):
+    """Same tensor-core kernels with fp16 operands (CAZ_PRECISION_FP16): north_star's bf16 gate with a wide margin."""
+    for tag, (cfg, w, x, fens, (wp, wv)) in (("keras_default", net_default), ("randomized", net)):
+        ev = caz.Evaluator(cfg, w, precision="fp16", max_batch=256)
+        p, v = ev.predict_on_batch(x)
+        dp, dv, agree = _bf16_report(f"fp16 vs fp32 oracle [{tag}]", p, v, wp, wv, len(x))
+        assert dp <= BF16_TOL / 4 and dv <= BF16_TOL / 4 and agree >= ARGMAX_AGREE
+        ps, vs = ev.predict_on_batch(x[:16])                          # small-batch kernel, same operands
+        assert np.abs(ps - wp[:16]).max() <= BF16_TOL / 4 and np.abs(vs - wv[:16]).max() <= BF16_TOL / 4
+        ev.close()
+
+
 def test_bf16_build_matches_oracle(net, ev_bf16):
     """Stress recipe (random BN statistics, biases, head scales; many near-uniform policy rows, so the argmax bar
     is lower than north_star's): probabilities and value inside north_star's 2e-2."""
