@@ -620,15 +620,15 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
     if ((rc = check_launch(h, "head_conv_kernel"))) return rc;
   }
   {
-    const dim3 grid((batch + caz::PG_TM - 1) / caz::PG_TM, (a.n_labels + caz::PG_TN - 1) / caz::PG_TN);
-    caz::policy_logits_kernel<<<grid, 256, 0, h->stream>>>(h->featp, h->pfc_w, h->pfc_b, d_policy, batch, pf * 64, a.n_labels);
-    if ((rc = check_launch(h, "policy_logits_kernel"))) return rc;
-    caz::policy_softmax_kernel<<<batch, 256, 0, h->stream>>>(d_policy, d_mask, a.n_labels);
+    const dim3 gp((batch + caz::PG_TM - 1) / caz::PG_TM, (a.n_labels + caz::PG_TN - 1) / caz::PG_TN);
+    caz::dense_tiled_kernel<<<gp, 256, 0, h->stream>>>(h->featp, h->pfc_w, h->pfc_b, d_policy, batch, pf * 64, a.n_labels, 0);
+    if ((rc = check_launch(h, "dense_tiled_kernel (policy)"))) return rc;
+    const dim3 gv((batch + caz::PG_TM - 1) / caz::PG_TM, (a.value_fc + caz::PG_TN - 1) / caz::PG_TN);
+    caz::dense_tiled_kernel<<<gv, 256, 0, h->stream>>>(h->featv, h->vfc1_w, h->vfc1_b, h->vhid, batch, vf * 64, a.value_fc, 1);
+    if ((rc = check_launch(h, "dense_tiled_kernel (value)"))) return rc;
+    caz::policy_softmax_kernel<<<batch, 256, 0, h->stream>>>(d_policy, d_mask, a.n_labels, h->vhid, h->vfc2_w, h->vfc2_b, d_value, a.value_fc);
     if ((rc = check_launch(h, "policy_softmax_kernel"))) return rc;
   }
-  caz::value_fc_kernel<<<(batch + caz::VTM - 1) / caz::VTM, 256, (size_t)caz::VTM * vf * 64 * sizeof(float), h->stream>>>(
-      h->featv, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, d_value, batch, vf * 64, a.value_fc);
-  if ((rc = check_launch(h, "value_fc_kernel"))) return rc;
   if (prof) { CU_TRY(h, cudaEventRecord(h->ev[4], h->stream)); h->pending_launches[3] = h->launches - l0; }
   return CAZ_OK;
 }

@@ -41,6 +41,18 @@ __global__ void pack_planes_kernel(const float* __restrict__ planes, T* __restri
   for (int i = threadIdx.x; i < cin * 64; i += blockDim.x) s_pl[(i >> 6) * 65 + (i & 63)] = src[i];
   __syncthreads();
   T* dst = act + static_cast<size_t>(b) * 64 * cpad;
+  if (sizeof(T) == 2 && (cpad & 7) == 0) {
+    // 16-bit activations: one 16-byte store = 8 channels of one square
+    const int chunks = cpad >> 3;
+    for (int i = threadIdx.x; i < 64 * chunks; i += blockDim.x) {
+      const int sq = i / chunks, c0 = (i - sq * chunks) * 8;
+      T v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = from_f32<T>(c0 + j < cin ? s_pl[(c0 + j) * 65 + sq] : 0.0f);
+      *reinterpret_cast<uint4*>(dst + static_cast<size_t>(sq) * cpad + c0) = *reinterpret_cast<const uint4*>(v);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < 64 * cpad; i += blockDim.x) {
     const int sq = i / cpad, c = i - sq * cpad;
     dst[i] = from_f32<T>(c < cin ? s_pl[c * 65 + sq] : 0.0f);
@@ -212,65 +224,94 @@ head_conv_kernel(const T* __restrict__ act, const float* __restrict__ w, const f
 //   policy_softmax_kernel: in-place row softmax, one block per position, the row lives in registers
 // wk: [kin][n_labels] (Keras Dense kernel layout).
 // ------------------------------------------------------------------------------------------------
-constexpr int PG_TM = 64;    // positions per block
-constexpr int PG_TN = 128;   // labels per block
-constexpr int PG_TK = 32;    // K slab
+constexpr int PG_TM = 128;   // rows (positions) per block
+constexpr int PG_TN = 128;   // columns (labels / hidden units) per block
+constexpr int PG_TK = 16;    // K slab
 constexpr int PNJ = 8;       // labels per thread in the softmax kernel (8 * 256 >= 1968)
 
+// C[M][N] = act(A[M][K] . W[K][N] + bias[N]), fp32 on the CUDA cores.  128 x 128 block tile, 8 x 8 register tile per
+// thread, K slabs of 16 double-buffered through registers (the next slab's global loads are in flight while the
+// current one is multiplied).  Used for the policy logits (N = 1968, K = 128) and the value head's hidden layer
+// (N = 256, K = 256, ReLU): agent/model_chess.py:82-83,91.
 __global__ void __launch_bounds__(256)
-policy_logits_kernel(const float* __restrict__ featp, const float* __restrict__ wk, const float* __restrict__ bk,
-                     float* __restrict__ logits, int batch, int kin, int n_labels) {
-  __shared__ __align__(16) float sA[PG_TK][PG_TM + 4];  // [k][position]
-  __shared__ __align__(16) float sW[PG_TK][PG_TN];      // [k][label]
-  const int b0 = blockIdx.x * PG_TM, n0 = blockIdx.y * PG_TN;
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;  // 4 positions x (4 + 4) labels per thread
-  float acc[4][8];
+dense_tiled_kernel(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ c, int m, int kdim, int n, int relu) {
+  __shared__ __align__(16) float sA[PG_TK][PG_TM + 4];  // [k][row]
+  __shared__ __align__(16) float sW[PG_TK][PG_TN];      // [k][col]
+  const int m0 = blockIdx.x * PG_TM, n0 = blockIdx.y * PG_TN;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;  // rows ty*8..+7, cols tx*4..+3 and 64+tx*4..+3
+  // global -> register staging: A slab is 128 rows x 16 k = 2048 floats (8 per thread), W slab 16 k x 128 cols (8 per thread)
+  const int a_row = threadIdx.x >> 1, a_k0 = (threadIdx.x & 1) * 8;   // 8 consecutive k of one row
+  const int w_k = threadIdx.x >> 4, w_c0 = (threadIdx.x & 15) * 8;    // 8 consecutive cols of one k
+  float ra[8], rw[8];
+  auto load_slab = [&](int k0) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 8; ++j) {
+      const int kk = k0 + a_k0 + j;
+      ra[j] = (m0 + a_row < m && kk < kdim) ? a[static_cast<size_t>(m0 + a_row) * kdim + kk] : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = n0 + w_c0 + j;
+      rw[j] = (k0 + w_k < kdim && col < n) ? __ldg(w + static_cast<size_t>(k0 + w_k) * n + col) : 0.0f;
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-  for (int k0 = 0; k0 < kin; k0 += PG_TK) {
+  load_slab(0);
+  for (int k0 = 0; k0 < kdim; k0 += PG_TK) {
+    __syncthreads();  // previous slab fully consumed
 #pragma unroll
-    for (int i = 0; i < (PG_TM * PG_TK) / 256; ++i) {
-      const int idx = threadIdx.x + i * 256;
-      const int pos = idx / PG_TK, k = idx % PG_TK;
-      sA[k][pos] = (b0 + pos < batch && k0 + k < kin) ? featp[static_cast<size_t>(b0 + pos) * kin + k0 + k] : 0.0f;
-    }
+    for (int j = 0; j < 8; ++j) sA[a_k0 + j][a_row] = ra[j];
 #pragma unroll
-    for (int i = 0; i < (PG_TK * PG_TN) / 256; ++i) {
-      const int idx = threadIdx.x + i * 256;
-      const int k = idx / PG_TN, n = idx % PG_TN;
-      sW[k][n] = (n0 + n < n_labels && k0 + k < kin) ? __ldg(wk + static_cast<size_t>(k0 + k) * n_labels + n0 + n) : 0.0f;
-    }
+    for (int j = 0; j < 8; ++j) sW[w_k][w_c0 + j] = rw[j];
     __syncthreads();
-#pragma unroll 8
+    if (k0 + PG_TK < kdim) load_slab(k0 + PG_TK);
+#pragma unroll
     for (int k = 0; k < PG_TK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+      const float4 a0 = *reinterpret_cast<const float4*>(&sA[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sA[k][ty * 8 + 4]);
       const float4 w0 = *reinterpret_cast<const float4*>(&sW[k][tx * 4]);
       const float4 w1 = *reinterpret_cast<const float4*>(&sW[k][64 + tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
     }
-    __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int b = b0 + ty * 4 + i;
-    if (b >= batch) continue;
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + ty * 8 + i;
+    if (row >= m) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
-      if (n < n_labels) logits[static_cast<size_t>(b) * n_labels + n] = acc[i][j] + bk[n];
+    for (int half = 0; half < 2; ++half) {
+      const int col = n0 + half * 64 + tx * 4;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = col + j < n ? acc[i][half * 4 + j] + bias[col + j] : 0.0f;
+        if (relu) v[j] = fmaxf(v[j], 0.0f);
+      }
+      float* dst = c + static_cast<size_t>(row) * n + col;
+      if (col + 3 < n && (n & 3) == 0) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      else
+        for (int j = 0; j < 4; ++j)
+          if (col + j < n) dst[j] = v[j];
     }
   }
 }
 
+// In-place row softmax of the policy logits (optionally restricted to a legal mask), one block per position, the row
+// in registers; the same block finishes the value head: value = tanh(vhid . w2 + b2) (agent/model_chess.py:92).
 __global__ void __launch_bounds__(256)
-policy_softmax_kernel(float* __restrict__ policy, const uint8_t* __restrict__ mask, int n_labels) {
+policy_softmax_kernel(float* __restrict__ policy, const uint8_t* __restrict__ mask, int n_labels,
+                      const float* __restrict__ vhid, const float* __restrict__ w2, const float* __restrict__ b2,
+                      float* __restrict__ value, int hid) {
   __shared__ float s_red[8];
   __shared__ float s_bc;
   float* row = policy + static_cast<size_t>(blockIdx.x) * n_labels;
@@ -318,6 +359,20 @@ policy_softmax_kernel(float* __restrict__ policy, const uint8_t* __restrict__ ma
   for (int j = 0; j < PNJ; ++j) {
     const int n = threadIdx.x + j * 256;
     if (n < n_labels) row[n] = x[j] * inv;
+  }
+  if (value) {
+    float part = 0.0f;
+    for (int hh = threadIdx.x; hh < hid; hh += 256) part = fmaf(vhid[static_cast<size_t>(blockIdx.x) * hid + hh], w2[hh], part);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float v = b2[0];
+      for (int wi = 0; wi < 8; ++wi) v += s_red[wi];
+      value[blockIdx.x] = tanhf(v);
+    }
   }
 }
 
