@@ -745,7 +745,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   const size_t cap = (size_t)max_batch;
   h->in_cpad = tcp ? 64 : a.input_planes;
   CREATE_TRY(cudaMalloc(&h->in_act, cap * 64 * h->in_cpad * esz));
-  for (int i = 0; i < 3; ++i) CREATE_TRY(cudaMalloc(&h->act[i], cap * 64 * a.filters * (i == 2 ? 4 : esz)));
+  for (int i = 0; i < 3; ++i) CREATE_TRY(cudaMalloc(&h->act[i], ((cap + 1) & ~size_t(1)) * 64 * a.filters * (i == 2 ? 4 : esz)));
   CREATE_TRY(cudaMalloc(&h->featp, cap * a.policy_filters * 64 * 4));
   CREATE_TRY(cudaMalloc(&h->featv, cap * a.value_filters * 64 * 4));
   CREATE_TRY(cudaMalloc(&h->vhid, cap * a.value_fc * 4));
@@ -1044,7 +1044,13 @@ int caz_debug_conv_layer(caz_handle* h, int32_t layer, const float* in, const fl
   else caz::cast_pad_kernel<float><<<gi, 256, 0, h->stream>>>(d_in, (float*)a_in, rows, L.cin, cpad);
   if ((rc = check_launch(h, "cast_pad_kernel"))) return rc;
   float* xf = static_cast<float*>(h->act[2]);
-  if (residual) CU_TRY(h, cudaMemcpyAsync(xf, d_res, rows * F * 4, cudaMemcpyDeviceToDevice, h->stream));
+  if (residual && tcp) {
+    const size_t total4 = ((rows + 127) / 128) * (F / 32) * 8 * 128;
+    caz::xf_to_native_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, h->stream>>>(d_res, reinterpret_cast<float4*>(xf), rows, F);
+    if ((rc = check_launch(h, "xf_to_native_kernel"))) return rc;
+  } else if (residual) {
+    CU_TRY(h, cudaMemcpyAsync(xf, d_res, rows * F * 4, cudaMemcpyDeviceToDevice, h->stream));
+  }
   if ((rc = launch_conv(h, layer, a_in, tm, cpad, residual ? xf : nullptr, h->act[0], (tcp && (residual || layer == 0)) ? xf : nullptr, batch))) return rc;
   if (tcp && is_fp16(h)) caz::widen_kernel<__half><<<go, 256, 0, h->stream>>>((const __half*)h->act[0], d_out, rows * F);
   else if (tcp) caz::widen_kernel<__nv_bfloat16><<<go, 256, 0, h->stream>>>((const __nv_bfloat16*)h->act[0], d_out, rows * F);

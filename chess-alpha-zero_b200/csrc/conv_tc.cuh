@@ -65,8 +65,8 @@ struct ConvArgs {
   int n;            // Cout, multiple of 32, <= 256
   int relu;
   const float* bias;        // [n] folded BatchNorm shift
-  const float* residual;    // nullptr or fp32 [batch*64][n]: the residual stream stays in fp32
-  float* out_f32;           // nullptr or fp32 [batch*64][n] (may alias residual: same element, same thread)
+  const float* residual;    // nullptr or the fp32 residual stream, epilogue-native layout (see xf_index)
+  float* out_f32;           // nullptr or the same stream to write (may alias residual: same element, same thread)
   __nv_bfloat16* out_bf16;  // nullptr or bf16 [batch*64][n]: the next convolution's A operand
   // Last layer of the tower only: the two heads' 1x1 convolutions + folded BN + ReLU + Flatten
   // (model_chess.py:77-81,86-90) are computed from the fp32 epilogue registers, so the final activation never
@@ -95,60 +95,53 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr, uint32_t sbo_
 
 constexpr uint32_t kLocalCta = 0xffffffffu;
 
+// The fp32 residual stream is private to these epilogues (written by one, read by the next, by the SAME thread of the
+// SAME tile), so it is not stored row-major but in the order the epilogue touches it:
+//   xf[tile][32-column chunk][float4 q of the chunk (8)][TMEM lane m (128)]   (float4 units)
+// A warp's load/store of one float4 per thread is then 512 contiguous bytes -- no shared-memory transposition, which
+// matters because the tensor cores' operand reads already use most of the shared-memory bandwidth.
+__device__ __forceinline__ size_t xf_index(int tile, int chunks, int chunk, int q, int m) {
+  return ((static_cast<size_t>(tile) * chunks + chunk) * 8 + q) * 128 + m;
+}
+
 // Epilogue of ONE tile by one of the four epilogue warps (shared by the 1-CTA and the 2-CTA kernel).
 //   n0          first board of the tile (boards n0, n0+1; a board >= batch does not exist)
 //   taddr       TMEM address of this warp's lane quadrant in the accumulator stage
 //   full_bar    mbarrier the MMA commit arrives on when the accumulator is complete
 //   empty_bar   mbarrier to arrive on once the accumulator has been read out; in CTA `release_rank` of the cluster,
 //               or in this CTA when release_rank == kLocalCta
+// Warp `quad` owns TMEM lanes 32*quad .. +31 = ranks 2*quad, 2*quad+1 of both boards: local row r is
+// (rank 2*quad + (r>>4), board (r>>3)&1, file r&7), eight consecutive r = eight consecutive global rows.
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* smem_epi, const float* s_bias,
                                               const float* s_head, int quad, int lane, int n0, uint32_t taddr,
                                               uint64_t* full_bar, uint32_t full_phase, uint64_t* empty_bar,
                                               uint32_t release_rank) {
-  float4* stage = reinterpret_cast<float4*>(smem_epi + quad * EPI_WARP_BYTES);
-  uint4* stage_b = reinterpret_cast<uint4*>(stage);
-  const int fr = lane >> 3, fq = lane & 7;   // fp32 transposed mapping: row i*4+fr, float4 column fq
-  const int br = lane >> 2, bc = lane & 3;   // bf16 transposed mapping: row i*8+br, 16-byte column bc
+  uint4* stage_b = reinterpret_cast<uint4*>(smem_epi + quad * EPI_WARP_BYTES);
+  const int br = lane >> 2, bc = lane & 3;   // 16-bit transposed mapping: row i*8+br, 16-byte column bc
   const int left = args.batch - n0;
   const int boards_live = left >= 2 ? 2 : (left > 0 ? left : 0);
-  // global row of local row r, and whether its board exists
+  // global (NHWC) row of local row r, and whether its board exists
   auto grow = [&](int r) -> long {
     return (static_cast<long>(n0 + ((r >> 3) & 1)) << 6) + ((2 * quad + (r >> 4)) << 3) + (r & 7);
   };
   auto live = [&](int r) -> bool { return ((r >> 3) & 1) < boards_live; };
+  const int tile = n0 >> 1, chunks = args.n >> 5, m = quad * 32 + lane;
+  const float4* res4 = reinterpret_cast<const float4*>(args.residual);
+  float4* out4 = reinterpret_cast<float4*>(args.out_f32);
   float4 res_pf[8];
   if (args.residual) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = i * 4 + fr;
-      res_pf[i] = live(r) ? *reinterpret_cast<const float4*>(args.residual + grow(r) * args.n + fq * 4)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int q = 0; q < 8; ++q) res_pf[q] = res4[xf_index(tile, chunks, 0, q, m)];
   }
   ptx::mbar_wait(full_bar, full_phase, args.err_flag, ERR_EPILOGUE);
   ptx::tcgen05_fence_after();
-    float hacc[HEAD_MAX_F];
+  float hacc[HEAD_MAX_F];
 #pragma unroll
   for (int hf = 0; hf < HEAD_MAX_F; ++hf) hacc[hf] = 0.0f;
   for (int c0 = 0; c0 < args.n; c0 += 32) {
+    const int chunk = c0 >> 5;
     uint32_t v[32];
     ptx::tmem_ld_32x32(taddr + c0, v);
-    if (args.residual) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + fr;
-        stage[r * 8 + (fq ^ (r & 7))] = res_pf[i];
-      }
-      __syncwarp();
-      if (c0 + 32 < args.n) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + fr;
-          if (live(r))
-            res_pf[i] = *reinterpret_cast<const float4*>(args.residual + grow(r) * args.n + c0 + 32 + fq * 4);
-        }
-      }
-    }
     ptx::tmem_ld_wait();
     if (c0 + 32 >= args.n) {
       // all accumulator columns of this tile are in registers: hand the TMEM stage back to the MMA warp
@@ -165,11 +158,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
     if (args.residual) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 rv = stage[lane * 8 + (q ^ (lane & 7))];
-        f[q * 4 + 0] += rv.x;
-        f[q * 4 + 1] += rv.y;
-        f[q * 4 + 2] += rv.z;
-        f[q * 4 + 3] += rv.w;
+        f[q * 4 + 0] += res_pf[q].x;
+        f[q * 4 + 1] += res_pf[q].y;
+        f[q * 4 + 2] += res_pf[q].z;
+        f[q * 4 + 3] += res_pf[q].w;
+      }
+      if (c0 + 32 < args.n) {  // next chunk's residual, in flight during this chunk's math and stores
+#pragma unroll
+        for (int q = 0; q < 8; ++q) res_pf[q] = res4[xf_index(tile, chunks, chunk + 1, q, m)];
       }
     }
     if (args.relu) {
@@ -196,28 +192,18 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
       }
     }
     if (args.out_f32) {
-      // own row only: no cross-lane hazard with the residual reads above
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        stage[lane * 8 + (q ^ (lane & 7))] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + fr;
-        const float4 o = stage[r * 8 + (fq ^ (r & 7))];
-        if (live(r)) *reinterpret_cast<float4*>(args.out_f32 + grow(r) * args.n + c0 + fq * 4) = o;
-      }
-      __syncwarp();
+        out4[xf_index(tile, chunks, chunk, q, m)] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
     }
     if (args.out_bf16) {
-      if (args.residual && !args.out_f32) __syncwarp();  // residual rows fully read before reuse
+      // the 16-bit operand copy must be NHWC for the next layer's TMA: transpose the 32x32 block through a 2 KiB
+      // XOR-swizzled per-warp staging buffer so that each store instruction covers 8 rows x 64 contiguous bytes
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t w[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          w[e] = ptx::pack_h16x2(f[c * 8 + e * 2], f[c * 8 + e * 2 + 1], args.fp16 != 0);
-        }
+        for (int e = 0; e < 4; ++e) w[e] = ptx::pack_h16x2(f[c * 8 + e * 2], f[c * 8 + e * 2 + 1], args.fp16 != 0);
         stage_b[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_uint4(w[0], w[1], w[2], w[3]);
       }
       __syncwarp();

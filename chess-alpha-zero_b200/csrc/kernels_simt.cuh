@@ -68,6 +68,24 @@ __global__ void cast_pad_kernel(const float* __restrict__ in, T* __restrict__ ou
   const int c = static_cast<int>(i - r * cpad);
   out[i] = from_f32<T>(c < cin ? in[r * cin + c] : 0.0f);
 }
+// row-major fp32 [rows][n] -> the tensor-core epilogues' native residual layout (conv_tc.cuh: xf_index):
+// [tile][n/32 chunks][8 float4][128 lanes], lane m of a tile = (rank m>>4, board (m>>3)&1, file m&7)
+__global__ void xf_to_native_kernel(const float* __restrict__ in, float4* __restrict__ out, size_t rows, int n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // one float4 of the output
+  const int chunks = n >> 5;
+  const size_t total = ((rows + 127) / 128) * chunks * 8 * 128;
+  if (i >= total) return;
+  const int m = static_cast<int>(i & 127);
+  const int q = static_cast<int>((i >> 7) & 7);
+  const size_t t = i >> 10;
+  const int chunk = static_cast<int>(t % chunks);
+  const size_t tile = t / chunks;
+  const size_t row = (tile * 2 + ((m >> 3) & 1)) * 64 + (m >> 4) * 8 + (m & 7);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < rows) v = *reinterpret_cast<const float4*>(in + row * n + chunk * 32 + q * 4);
+  out[i] = v;
+}
+
 template <typename T>
 __global__ void widen_kernel(const T* __restrict__ in, float* __restrict__ out, size_t n) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -233,7 +251,7 @@ constexpr int PNJ = 8;       // labels per thread in the softmax kernel (8 * 256
 // thread, K slabs of 16 double-buffered through registers (the next slab's global loads are in flight while the
 // current one is multiplied).  Used for the policy logits (N = 1968, K = 128) and the value head's hidden layer
 // (N = 256, K = 256, ReLU): agent/model_chess.py:82-83,91.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dense_tiled_kernel(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
                    float* __restrict__ c, int m, int kdim, int n, int relu) {
   __shared__ __align__(16) float sA[PG_TK][PG_TM + 4];  // [k][row]
