@@ -74,6 +74,8 @@ struct caz_handle {
   bool use_2cta = true;          // per-layer convolutions as CTA pairs (cta_group::2); CAZ_CONV_2CTA=0 turns it off
   // weight slabs the layers point into: the tower's layers are contiguous so that one tensor map covers them
   void* w_stem = nullptr;
+  void* sb_w_stem = nullptr;   // stem weights padded to 64 input channels (small-batch kernel)
+  void* sb_in_act = nullptr;   // its input activations, [64 + 2][64][64]
   void* w_tower = nullptr;   // [2*res_blocks][filters][9*filters] (tensor-core build)
   float* bias_all = nullptr; // [1 + 2*res_blocks][filters]
   // small-batch persistent tower kernel (conv_sb.cuh)
@@ -174,12 +176,13 @@ int upload(caz_handle* h, void* dst, const void* src, size_t bytes) {
 }
 
 int make_tmap(caz_handle* h, CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-              const cuuint32_t* box) {
+              const cuuint32_t* box, int row_bytes = 128) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(h, CAZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, is_fp16(h) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, ones,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, CAZ_ERR_CUDA, fmt("cuTensorMapEncodeTiled failed with CUresult %d", (int)r));
   return CAZ_OK;
@@ -187,12 +190,12 @@ int make_tmap(caz_handle* h, CUtensorMap* m, void* base, int rank, const cuuint6
 
 // Halo view of NHWC bf16 activations [cap][8][8][c]: dims (c, file, position, rank), box 64 x hw x nb x hw, fetched at
 // (c0, -pad, n0, -pad): the out-of-bounds fill supplies the zero border on all four sides (hw = 8 + k - 1).
-int make_halo_tmap(caz_handle* h, CUtensorMap* m, void* base, int c, int k, int nb) {
+int make_halo_tmap(caz_handle* h, CUtensorMap* m, void* base, int c, int k, int nb, int cap = 0, int row_bytes = 128) {
   const cuuint32_t hw = 8 + k - 1;
-  cuuint64_t dims[4] = {(cuuint64_t)c, 8, (cuuint64_t)h->max_batch, 8};
+  cuuint64_t dims[4] = {(cuuint64_t)c, 8, (cuuint64_t)(cap ? cap : h->max_batch), 8};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 128, (cuuint64_t)c * 16};
-  cuuint32_t box[4] = {64, hw, (cuuint32_t)nb, hw};
-  return make_tmap(h, m, base, 4, dims, strides, box);
+  cuuint32_t box[4] = {(cuuint32_t)row_bytes / 2, hw, (cuuint32_t)nb, hw};
+  return make_tmap(h, m, base, 4, dims, strides, box, row_bytes);
 }
 
 // Installs (folds, re-lays-out, uploads) one full weight set. Buffers are allocated on first use.
@@ -210,7 +213,7 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
   const bool first_install = h->convs.empty();
   if (first_install) {
     h->convs.resize(n_convs);
-    const int scin = a.input_planes, scin_pad = tcp ? ((scin + 63) / 64) * 64 : scin;
+    const int scin_pad = h->in_cpad;
     const size_t stem_elems = (size_t)a.stem_kernel * a.stem_kernel * scin_pad * F;
     const size_t blk_elems = (size_t)a.block_kernel * a.block_kernel * F * F;
     const size_t esz = tcp ? 2 : 4;
@@ -226,7 +229,7 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
     ConvLayer& L = h->convs[li];
     const int k = li == 0 ? a.stem_kernel : a.block_kernel;
     const int cin = li == 0 ? a.input_planes : F;
-    const int cin_pad = tcp ? ((cin + 63) / 64) * 64 : cin;
+    const int cin_pad = li == 0 ? h->in_cpad : (tcp ? ((cin + 63) / 64) * 64 : cin);
     const caz_tensor& kt = t[ti];
     if (kt.numel != (int64_t)k * k * cin * F)
       return fail(h, CAZ_ERR_INVALID, fmt("conv %d kernel has %lld elements, expected %lld", li,
@@ -242,11 +245,12 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
       if (tcp) {
         cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)F};
         cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)F};
-        int rc = make_tmap(h, &L.tmap_w, L.w, 2, dims, strides, box);
+        const int rbytes = li == 0 ? h->in_cpad * 2 : 128;   // operand row = swizzle span
+        cuuint32_t box[2] = {(cuuint32_t)rbytes / 2, (cuuint32_t)F};
+        int rc = make_tmap(h, &L.tmap_w, L.w, 2, dims, strides, box, rbytes);
         if (rc) return rc;
-        cuuint32_t box2[2] = {64, (cuuint32_t)F / 2};
-        if ((rc = make_tmap(h, &L.tmap_w2, L.w, 2, dims, strides, box2))) return rc;
+        cuuint32_t box2[2] = {(cuuint32_t)rbytes / 2, (cuuint32_t)F / 2};
+        if ((rc = make_tmap(h, &L.tmap_w2, L.w, 2, dims, strides, box2, rbytes))) return rc;
       }
     }
     if (tcp) {
@@ -268,6 +272,16 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
       int rc = upload(h, L.w, wp.data(), wp.size() * 2);
       if (rc) return rc;
       wbytes += (int64_t)taps * cin * F * 2;
+      if (li == 0) {
+        // the small-batch kernel keeps 128-byte operand rows everywhere: its own copy of the stem, padded to 64 channels
+        const size_t k64 = (size_t)taps * 64;
+        std::vector<uint16_t> w64(k64 * F, 0);
+        for (int oc = 0; oc < F; ++oc)
+          for (int tap = 0; tap < taps; ++tap)
+            for (int ic = 0; ic < cin && ic < 64; ++ic) w64[(size_t)oc * k64 + (size_t)tap * 64 + ic] = wp[(size_t)oc * ktot + (size_t)tap * cin_pad + ic];
+        if (!h->sb_w_stem) CU_TRY(h, cudaMalloc(&h->sb_w_stem, w64.size() * 2));
+        if ((rc = upload(h, h->sb_w_stem, w64.data(), w64.size() * 2))) return rc;
+      }
     } else {
       std::vector<float> wp((size_t)taps * cin * F);
       for (size_t i = 0; i < wp.size(); ++i) wp[i] = kt.data[i] * inv[i % F];
@@ -345,7 +359,8 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
     args.batch = batch;
     args.num_tiles = (batch + 1) / 2;
     args.ksize = L.k;
-    args.kchunks = L.cin_pad / 64;
+    args.row_bytes = li == 0 ? h->in_cpad * 2 : 128;
+    args.kchunks = L.cin_pad / (args.row_bytes / 2);
     args.n = L.cout;
     args.relu = 1;
     args.bias = L.bias;
@@ -392,10 +407,12 @@ int setup_small_batch(caz_handle* h) {
   const caz_arch& a = h->arch;
   h->sb_ok = false;
   if (!tensor_path(h) || a.block_kernel != 3 || a.filters != 256 && a.filters != 128 && a.filters != 64) return CAZ_OK;
-  if ((8 + a.stem_kernel - 1) * 2 * (8 + a.stem_kernel - 1) * 128 * (h->in_cpad / 64) > caz::sb::A_BYTES) return CAZ_OK;
+  if (a.input_planes > 64 || (8 + a.stem_kernel - 1) * 2 * (8 + a.stem_kernel - 1) * 128 > caz::sb::A_BYTES) return CAZ_OK;
+  const int sb_cap = caz::sb::MAX_BATCH + 2;
+  CU_TRY(h, cudaMalloc(&h->sb_in_act, (size_t)sb_cap * 64 * 64 * 2));
   int rc;
   for (int nb = 1; nb <= 2; ++nb) {
-    if ((rc = make_halo_tmap(h, &h->sb_tm_in[nb - 1], h->in_act, h->in_cpad, a.stem_kernel, nb))) return rc;
+    if ((rc = make_halo_tmap(h, &h->sb_tm_in[nb - 1], h->sb_in_act, 64, a.stem_kernel, nb, sb_cap))) return rc;
     if ((rc = make_halo_tmap(h, &h->sb_tm_xb[nb - 1], h->act[0], a.filters, a.block_kernel, nb))) return rc;
     if ((rc = make_halo_tmap(h, &h->sb_tm_y[nb - 1], h->act[1], a.filters, a.block_kernel, nb))) return rc;
   }
@@ -404,11 +421,11 @@ int setup_small_batch(caz_handle* h) {
   for (int i = 0; i < 3; ++i) {
     const cuuint32_t ns = 16u << i;
     if (ns > (cuuint32_t)F) { h->sb_tm_w_stem[i] = h->sb_tm_w_stem[0]; h->sb_tm_w_tower[i] = h->sb_tm_w_tower[0]; continue; }
-    const cuuint64_t kst = (cuuint64_t)a.stem_kernel * a.stem_kernel * h->in_cpad;
+    const cuuint64_t kst = (cuuint64_t)a.stem_kernel * a.stem_kernel * 64;
     cuuint64_t dims_s[2] = {kst, (cuuint64_t)F};
     cuuint64_t str_s[1] = {kst * 2};
     cuuint32_t box[2] = {64, ns};
-    if ((rc = make_tmap(h, &h->sb_tm_w_stem[i], h->w_stem, 2, dims_s, str_s, box))) return rc;
+    if ((rc = make_tmap(h, &h->sb_tm_w_stem[i], h->sb_w_stem, 2, dims_s, str_s, box))) return rc;
     if (a.res_blocks > 0) {
       const cuuint64_t kt = (cuuint64_t)9 * F;
       cuuint64_t dims_t[2] = {kt, (cuuint64_t)F * 2 * a.res_blocks};
@@ -472,10 +489,10 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   args.n_slices = slices;
   args.filters = a.filters;
   args.stem_k = a.stem_kernel;
-  args.stem_kchunks = h->in_cpad / 64;
+  args.stem_kchunks = 1;
   args.blk_k = a.block_kernel;
   args.in_planes = a.input_planes;
-  args.in_cpad = h->in_cpad;
+  args.in_cpad = 64;
   args.fp16 = is_fp16(h) ? 1 : 0;
   const int sb_stem = caz::sb::taps_per_slot(a.stem_kernel, ns) * ns * 128;
   const int sb_blk = a.res_blocks > 0 ? caz::sb::taps_per_slot(a.block_kernel, ns) * ns * 128 : 0;
@@ -484,7 +501,7 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   if (args.n_slots > caz::sb::MAX_W_SLOTS) args.n_slots = caz::sb::MAX_W_SLOTS;
   args.planes = d_planes;
   args.records = d_records;
-  args.in_act = static_cast<__nv_bfloat16*>(h->in_act);
+  args.in_act = static_cast<__nv_bfloat16*>(h->sb_in_act);
   args.bias_all = h->bias_all;
   args.xf = static_cast<float*>(h->act[2]);
   args.xb = static_cast<__nv_bfloat16*>(h->act[0]);
@@ -670,6 +687,8 @@ void caz_destroy(caz_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->w_stem) cudaFree(h->w_stem);
+  if (h->sb_w_stem) cudaFree(h->sb_w_stem);
+  if (h->sb_in_act) cudaFree(h->sb_in_act);
   if (h->w_tower) cudaFree(h->w_tower);
   if (h->bias_all) cudaFree(h->bias_all);
   if (h->sb_counter) cudaFree(h->sb_counter);
@@ -743,7 +762,8 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   const bool tcp = precision != CAZ_PRECISION_FP32;
   const size_t esz = tcp ? 2 : 4;
   const size_t cap = (size_t)max_batch;
-  h->in_cpad = tcp ? 64 : a.input_planes;
+  // 16-bit builds: the stem's input rows are one swizzle span: 32 channels (64-byte rows) when the planes fit, else 64
+  h->in_cpad = tcp ? (a.input_planes <= 32 ? 32 : 64) : a.input_planes;
   CREATE_TRY(cudaMalloc(&h->in_act, cap * 64 * h->in_cpad * esz));
   for (int i = 0; i < 3; ++i) CREATE_TRY(cudaMalloc(&h->act[i], ((cap + 1) & ~size_t(1)) * 64 * a.filters * (i == 2 ? 4 : esz)));
   CREATE_TRY(cudaMalloc(&h->featp, cap * a.policy_filters * 64 * 4));
@@ -768,7 +788,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   }
   int rc;
   if (tcp) {
-    if ((rc = make_halo_tmap(h, &h->tmap_in, h->in_act, h->in_cpad, a.stem_kernel, 2))) return bail(rc);
+    if ((rc = make_halo_tmap(h, &h->tmap_in, h->in_act, h->in_cpad, a.stem_kernel, 2, 0, h->in_cpad * 2))) return bail(rc);
     for (int i = 0; i < 2; ++i)
       if ((rc = make_halo_tmap(h, &h->tmap_act[i], h->act[i], a.filters, a.block_kernel, 2))) return bail(rc);
     CREATE_TRY(cudaFuncSetAttribute(caz::tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc::SMEM_BYTES));

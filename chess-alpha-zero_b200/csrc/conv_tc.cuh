@@ -61,7 +61,9 @@ struct ConvArgs {
   int batch;        // positions
   int num_tiles;    // ceil(batch / 2)
   int ksize;        // kernel height = width (3 or 5)
-  int kchunks;      // Cin_padded / 64
+  int kchunks;      // Cin_padded / (row_bytes / 2)
+  int row_bytes;    // bytes of one operand row in shared memory = swizzle span: 128 (64 channels per K block) or
+                    // 64 (32 channels: the stem, whose 18 input planes would otherwise be padded to 64)
   int n;            // Cout, multiple of 32, <= 256
   int relu;
   const float* bias;        // [n] folded BatchNorm shift
@@ -82,14 +84,15 @@ struct ConvArgs {
 
 enum : int { ERR_PRODUCER_B = 101, ERR_PRODUCER_A = 105, ERR_MMA_FULL = 102, ERR_MMA_ACC = 103, ERR_EPILOGUE = 104, ERR_MMA_A = 106 };
 
-// K-major SWIZZLE_128B descriptor with an explicit 8-row-group stride (the halo view needs hw*128, weights 1024)
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+// K-major swizzled descriptor with an explicit 8-row-group stride (the halo view needs hw*row_bytes, weights
+// 8*row_bytes).  row_bytes 128 -> SWIZZLE_128B (layout type 2), 64 -> SWIZZLE_64B (layout type 4).
+__device__ __forceinline__ uint64_t desc_sw(uint32_t smem_addr, uint32_t sbo_bytes, int row_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
   d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : 4) << 61;
   return d;
 }
 
@@ -255,9 +258,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int k = args.ksize, pad = (k - 1) / 2, hw = 8 + k - 1;
-  const int plane_bytes = hw * 2 * hw * 128;           // one chunk tile; a multiple of 1024
+  const int rb = args.row_bytes, kblk = rb >> 1;        // operand row bytes, K elements per K block
+  const int plane_bytes = hw * 2 * hw * rb;            // one chunk tile; a multiple of 1024
   const int a_slots = A_RING_BYTES / plane_bytes < MAX_A_SLOTS ? A_RING_BYTES / plane_bytes : MAX_A_SLOTS;
-  const uint32_t b_bytes = static_cast<uint32_t>(args.n) * BLOCK_K * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(args.n) * rb;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_halo);
@@ -301,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_const
           ptx::mbar_wait(&b_empty[stage], phase ^ 1, args.err_flag, ERR_PRODUCER_B);
           if (ptx::elect_one()) {
             ptx::mbar_expect_tx(&b_full[stage], b_bytes);
-            ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_w, &b_full[stage], (tap * args.kchunks + kc) * BLOCK_K, 0);
+            ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmap_w, &b_full[stage], (tap * args.kchunks + kc) * kblk, 0);
           }
           __syncwarp();
           if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
@@ -315,7 +319,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_const
         ptx::mbar_wait(&a_empty[slot], phase ^ 1, args.err_flag, ERR_PRODUCER_A);
         if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&a_full[slot], plane_bytes);
-          ptx::tma_load_4d(smem_a + slot * plane_bytes, &tmap_halo, &a_full[slot], kc * BLOCK_K, -pad, tile * 2, -pad);
+          ptx::tma_load_4d(smem_a + slot * plane_bytes, &tmap_halo, &a_full[slot], kc * kblk, -pad, tile * 2, -pad);
         }
         __syncwarp();
         if (++slot == a_slots) { slot = 0; phase ^= 1; }
@@ -324,8 +328,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_const
     // ===================== MMA issuer =====================
     const uint32_t idesc = ptx::idesc_h16_f32(BLOCK_M, args.n, args.fp16 != 0);
     // descriptors differ only in the 14-bit start-address field: add (byte offset >> 4) to a template
-    const uint64_t a_desc0 = desc_sw128(ptx::smem_u32(smem_a), hw * 128);  // next 8-row group = next (rank, board)
-    const uint64_t b_desc0 = desc_sw128(ptx::smem_u32(smem_b), 1024);
+    const uint64_t a_desc0 = desc_sw(ptx::smem_u32(smem_a), hw * rb, rb);  // next 8-row group = next (rank, board)
+    const uint64_t b_desc0 = desc_sw(ptx::smem_u32(smem_b), 8 * rb, rb);
+    const int tap_rows16 = rb >> 4;   // one halo row in descriptor units (16 bytes)
     int stage = 0, slot = 0, acc = 0;
     uint32_t phase = 0, a_phase = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
@@ -340,13 +345,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_const
             ptx::mbar_wait(&b_full[stage], phase, args.err_flag, ERR_MMA_FULL);
             ptx::tcgen05_fence_after();
             if (ptx::elect_one()) {
-              // tap (dy, dx) = the same halo tile, viewed (2*hw*dy + dx) rows of 128 bytes further on
-              const uint64_t adesc = a_plane + static_cast<uint64_t>((dy * 2 * hw + dx) * 8);
+              // tap (dy, dx) = the same halo tile, viewed (2*hw*dy + dx) rows further on
+              const uint64_t adesc = a_plane + static_cast<uint64_t>((dy * 2 * hw + dx) * tap_rows16);
               const uint64_t bdesc = b_desc0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
               const uint32_t first = (kc | dy | dx) == 0 ? 0u : 1u;
-#pragma unroll
-              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-                ptx::mma_bf16_ss(tmem_d, adesc + kk * 2, bdesc + kk * 2, idesc, kk == 0 ? first : 1u);
+              ptx::mma_bf16_ss(tmem_d, adesc, bdesc, idesc, first);
+              ptx::mma_bf16_ss(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+              if (rb == 128) {
+                ptx::mma_bf16_ss(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+                ptx::mma_bf16_ss(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+              }
               ptx::mma_commit(&b_empty[stage]);  // weight stage reusable once these MMAs have read it
               if (dy == k - 1 && dx == k - 1) {
                 ptx::mma_commit(&a_empty[slot]);                                  // chunk tile fully consumed

@@ -64,10 +64,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   const int pair0 = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1;
   const int num_pairs = (args.num_tiles + 1) >> 1;
   const int k = args.ksize, pad = (k - 1) / 2, hw = 8 + k - 1;
-  const int plane_bytes = hw * 2 * hw * 128;
+  const int rb = args.row_bytes, kblk = rb >> 1;
+  const int plane_bytes = hw * 2 * hw * rb;
   const int a_slots = A_RING_BYTES / plane_bytes < MAX_A_SLOTS ? A_RING_BYTES / plane_bytes : MAX_A_SLOTS;
   const int n_half = args.n >> 1;
-  const uint32_t b_bytes = static_cast<uint32_t>(n_half) * BLOCK_K * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(n_half) * rb;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_halo);
@@ -113,7 +114,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_expect_tx(&b_full[stage], 2 * b_bytes);   // both CTAs' halves
             ptx::tma_load_2d_2cta(smem_b + stage * B_STAGE_BYTES, &tmap_w, ptx::mapa_u32(&b_full[stage], 0),
-                                  (tap * args.kchunks + kc) * BLOCK_K, static_cast<int>(rank) * n_half);
+                                  (tap * args.kchunks + kc) * kblk, static_cast<int>(rank) * n_half);
           }
           __syncwarp();
           if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
@@ -128,7 +129,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
         ptx::mbar_wait(&a_empty[slot], phase ^ 1, args.err_flag, ERR2_PRODUCER_A);
         if (ptx::elect_one()) {
           if (leader) ptx::mbar_expect_tx(&a_full[slot], 2 * plane_bytes);
-          ptx::tma_load_4d_2cta(smem_a + slot * plane_bytes, &tmap_halo, ptx::mapa_u32(&a_full[slot], 0), kc * BLOCK_K,
+          ptx::tma_load_4d_2cta(smem_a + slot * plane_bytes, &tmap_halo, ptx::mapa_u32(&a_full[slot], 0), kc * kblk,
                                 -pad, tile * 2, -pad);
         }
         __syncwarp();
@@ -139,8 +140,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
     // ===================== MMA issuer (leader only) =====================
     if (leader) {
       const uint32_t idesc = ptx::idesc_h16_f32(256, args.n, args.fp16 != 0);
-      const uint64_t a_desc0 = tc::desc_sw128(ptx::smem_u32(smem_a), hw * 128);
-      const uint64_t b_desc0 = tc::desc_sw128(ptx::smem_u32(smem_b), 1024);
+      const uint64_t a_desc0 = tc::desc_sw(ptx::smem_u32(smem_a), hw * rb, rb);
+      const uint64_t b_desc0 = tc::desc_sw(ptx::smem_u32(smem_b), 8 * rb, rb);
+      const int tap_rows16 = rb >> 4;
       int stage = 0, slot = 0, acc = 0;
       uint32_t phase = 0, a_phase = 0, acc_phase = 0;
       for (int pair = pair0; pair < num_pairs; pair += n_pairs_grid) {
@@ -155,12 +157,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
               ptx::mbar_wait(&b_full[stage], phase, args.err_flag, ERR2_MMA_B);
               ptx::tcgen05_fence_after();
               if (ptx::elect_one()) {
-                const uint64_t adesc = a_plane + static_cast<uint64_t>((dy * 2 * hw + dx) * 8);
+                const uint64_t adesc = a_plane + static_cast<uint64_t>((dy * 2 * hw + dx) * tap_rows16);
                 const uint64_t bdesc = b_desc0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
                 const uint32_t first = (kc | dy | dx) == 0 ? 0u : 1u;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  ptx::mma_bf16_ss_2cta(tmem_d, adesc + kk * 2, bdesc + kk * 2, idesc, kk == 0 ? first : 1u);
+                ptx::mma_bf16_ss_2cta(tmem_d, adesc, bdesc, idesc, first);
+                ptx::mma_bf16_ss_2cta(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+                if (rb == 128) {
+                  ptx::mma_bf16_ss_2cta(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+                  ptx::mma_bf16_ss_2cta(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+                }
                 ptx::mma_commit_2cta(&b_empty[stage]);
                 if (dy == k - 1 && dx == k - 1) {
                   ptx::mma_commit_2cta(&a_empty[slot]);
