@@ -99,6 +99,13 @@ struct caz_handle {
   void* act[3] = {nullptr, nullptr, nullptr};
   CUtensorMap tmap_in, tmap_act[2];
   float *featp = nullptr, *featv = nullptr, *vhid = nullptr;
+  // heads' Dense layers on the tensor cores (3-term 16-bit split, see split3_kernel)
+  bool dense_tc = false;
+  int mpad = 0;                       // rows of the split operands: max_batch rounded up to 128
+  uint16_t *a3p = nullptr, *a3v = nullptr, *w3p = nullptr, *w3v = nullptr;
+  float *bias3p = nullptr;            // policy bias padded to a multiple of 256
+  int np_pad = 0;
+  CUtensorMap tm_a3p, tm_a3v, tm_w3p, tm_w3v;
   // staging for the host-pointer entry points
   float *d_planes = nullptr, *d_policy = nullptr, *d_value = nullptr;
   uint8_t *d_mask = nullptr, *d_records = nullptr;
@@ -197,6 +204,8 @@ int make_halo_tmap(caz_handle* h, CUtensorMap* m, void* base, int c, int k, int 
   cuuint32_t box[4] = {(cuuint32_t)row_bytes / 2, hw, (cuuint32_t)nb, hw};
   return make_tmap(h, m, base, 4, dims, strides, box, row_bytes);
 }
+
+int setup_dense_tc(caz_handle* h, const float* pfc_w, const float* pfc_b, const float* vfc1_w);
 
 // Installs (folds, re-lays-out, uploads) one full weight set. Buffers are allocated on first use.
 int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
@@ -339,6 +348,7 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
   if ((rc = upload(h, h->vfc2_b, val[8].data, 4))) return rc;
   wbytes += (int64_t)(hw.size() + hb.size() + pol[5].numel + pol[6].numel + val[5].numel + val[6].numel + val[7].numel + 1) * 4;
   h->weight_bytes = wbytes;
+  if (tcp && (rc = setup_dense_tc(h, pol[5].data, pol[6].data, val[5].data))) return rc;
   return CAZ_OK;
 }
 
@@ -374,6 +384,10 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
     args.pf = h->arch.policy_filters;
     args.vf = h->arch.value_filters;
     args.fp16 = is_fp16(h) ? 1 : 0;
+    args.n_tiles = 1;
+    args.n_total = L.cout;
+    args.m_rows = batch * 64;
+    args.out_rm = nullptr;
     args.err_flag = h->err_flag_dev;
     if (h->use_2cta && args.num_tiles >= 2 && L.cout % 64 == 0) {
       // CTA pairs: one cta_group::2 MMA covers two tiles (four boards)
@@ -568,6 +582,94 @@ int prof_drain(caz_handle* h) {
   return CAZ_OK;
 }
 
+// ---- heads' Dense layers as tensor-core GEMMs (conv_tc2_kernel in GEMM mode) -----------------------------
+uint16_t round16(float v, bool f16) {
+  uint16_t bits;
+  if (f16) { const __half hv = __float2half_rn(v); memcpy(&bits, &hv, 2); }
+  else { const __nv_bfloat16 bv = __float2bfloat16_rn(v); memcpy(&bits, &bv, 2); }
+  return bits;
+}
+float widen16(uint16_t bits, bool f16) {
+  if (f16) { __half hv; memcpy(&hv, &bits, 2); return __half2float(hv); }
+  __nv_bfloat16 bv; memcpy(&bv, &bits, 2); return __bfloat162float(bv);
+}
+
+// W [k][n] fp32 (Keras Dense kernel) -> [npad][3k] 16-bit rows = [wh | wl | wh]
+int upload_w3(caz_handle* h, uint16_t* dst, const float* w, int k, int n, int npad) {
+  const bool f16 = is_fp16(h);
+  std::vector<uint16_t> w3((size_t)npad * 3 * k, 0);
+  for (int col = 0; col < n; ++col)
+    for (int kk = 0; kk < k; ++kk) {
+      const float v = w[(size_t)kk * n + col];
+      const uint16_t hi = round16(v, f16), lo = round16(v - widen16(hi, f16), f16);
+      uint16_t* row = w3.data() + (size_t)col * 3 * k;
+      row[kk] = hi;
+      row[k + kk] = lo;
+      row[2 * k + kk] = hi;
+    }
+  return upload(h, dst, w3.data(), w3.size() * 2);
+}
+
+int setup_dense_tc(caz_handle* h, const float* pfc_w, const float* pfc_b, const float* vfc1_w) {
+  const caz_arch& a = h->arch;
+  const int kp = a.policy_filters * 64, kv = a.value_filters * 64;
+  h->dense_tc = tensor_path(h) && a.value_fc % 64 == 0 && a.value_fc <= 256 && h->use_2cta;
+  if (!h->dense_tc) return CAZ_OK;
+  int rc;
+  const bool first = h->a3p == nullptr;
+  if (first) {
+    h->mpad = ((h->max_batch + 127) / 128) * 128;
+    h->np_pad = ((a.n_labels + 255) / 256) * 256;
+    CU_TRY(h, cudaMalloc(&h->a3p, (size_t)h->mpad * 3 * kp * 2));
+    CU_TRY(h, cudaMalloc(&h->a3v, (size_t)h->mpad * 3 * kv * 2));
+    CU_TRY(h, cudaMalloc(&h->w3p, (size_t)h->np_pad * 3 * kp * 2));
+    CU_TRY(h, cudaMalloc(&h->w3v, (size_t)a.value_fc * 3 * kv * 2));
+    CU_TRY(h, cudaMalloc(&h->bias3p, (size_t)h->np_pad * 4));
+    // A operands: rows in groups of 64 play the role of boards; ksize 1 -> the "halo" tile is the plain 128 x 64 tile
+    if ((rc = make_halo_tmap(h, &h->tm_a3p, h->a3p, 3 * kp, 1, 2, h->mpad / 64))) return rc;
+    if ((rc = make_halo_tmap(h, &h->tm_a3v, h->a3v, 3 * kv, 1, 2, h->mpad / 64))) return rc;
+    cuuint64_t dp[2] = {(cuuint64_t)3 * kp, (cuuint64_t)h->np_pad}, sp[1] = {(cuuint64_t)3 * kp * 2};
+    cuuint32_t bp[2] = {64, 128};
+    if ((rc = make_tmap(h, &h->tm_w3p, h->w3p, 2, dp, sp, bp))) return rc;
+    cuuint64_t dv[2] = {(cuuint64_t)3 * kv, (cuuint64_t)a.value_fc}, sv[1] = {(cuuint64_t)3 * kv * 2};
+    cuuint32_t bv[2] = {64, (cuuint32_t)a.value_fc / 2};
+    if ((rc = make_tmap(h, &h->tm_w3v, h->w3v, 2, dv, sv, bv))) return rc;
+  }
+  if ((rc = upload_w3(h, h->w3p, pfc_w, kp, a.n_labels, h->np_pad))) return rc;
+  if ((rc = upload_w3(h, h->w3v, vfc1_w, kv, a.value_fc, a.value_fc))) return rc;
+  std::vector<float> b3(h->np_pad, 0.0f);
+  memcpy(b3.data(), pfc_b, (size_t)a.n_labels * 4);
+  return upload(h, h->bias3p, b3.data(), b3.size() * 4);
+}
+
+// out[m][n_total] = act(in[m][k] . W + bias) through the CTA-pair tensor-core kernel
+int launch_dense_tc(caz_handle* h, const float* in, uint16_t* a3, const CUtensorMap* tm_a, const CUtensorMap* tm_w, int k,
+                    int n_tile, int n_tiles, int n_total, const float* bias, int relu, float* out, int m) {
+  int rc;
+  const size_t total = (size_t)(((m + 127) / 128) * 128) * k;
+  caz::split3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(in, a3, m, ((m + 127) / 128) * 128, k, is_fp16(h) ? 1 : 0);
+  if ((rc = check_launch(h, "split3_kernel"))) return rc;
+  caz::tc::ConvArgs args{};
+  args.batch = (m + 63) / 64;          // "boards" = groups of 64 rows
+  args.num_tiles = (args.batch + 1) / 2;
+  args.ksize = 1;
+  args.row_bytes = 128;
+  args.kchunks = 3 * k / 64;
+  args.n = n_tile;
+  args.relu = relu;
+  args.bias = bias;
+  args.fp16 = is_fp16(h) ? 1 : 0;
+  args.n_tiles = n_tiles;
+  args.n_total = n_total;
+  args.m_rows = m;
+  args.out_rm = out;
+  args.err_flag = h->err_flag_dev;
+  const int work = ((args.num_tiles + 1) / 2) * n_tiles, max_pairs = h->num_sms / 2;
+  const int grid = 2 * (work < max_pairs ? work : max_pairs);
+  caz::tc2::conv_tc2_kernel<<<grid, caz::tc2::THREADS, caz::tc2::SMEM_BYTES, h->stream>>>(*tm_a, *tm_w, args);
+  return check_launch(h, "conv_tc2_kernel (dense)");
+}
+
 // Forward pass over device-resident input. Exactly one of d_planes / d_records is non-null.
 int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int batch, float* d_policy, float* d_value,
             const uint8_t* d_mask) {
@@ -637,12 +739,19 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
     if ((rc = check_launch(h, "head_conv_kernel"))) return rc;
   }
   {
-    const dim3 gp((batch + caz::PG_TM - 1) / caz::PG_TM, (a.n_labels + caz::PG_TN - 1) / caz::PG_TN);
-    caz::dense_tiled_kernel<<<gp, 256, 0, h->stream>>>(h->featp, h->pfc_w, h->pfc_b, d_policy, batch, pf * 64, a.n_labels, 0);
-    if ((rc = check_launch(h, "dense_tiled_kernel (policy)"))) return rc;
-    const dim3 gv((batch + caz::PG_TM - 1) / caz::PG_TM, (a.value_fc + caz::PG_TN - 1) / caz::PG_TN);
-    caz::dense_tiled_kernel<<<gv, 256, 0, h->stream>>>(h->featv, h->vfc1_w, h->vfc1_b, h->vhid, batch, vf * 64, a.value_fc, 1);
-    if ((rc = check_launch(h, "dense_tiled_kernel (value)"))) return rc;
+    if (h->dense_tc) {
+      if ((rc = launch_dense_tc(h, h->featp, h->a3p, &h->tm_a3p, &h->tm_w3p, pf * 64, 256, h->np_pad / 256, a.n_labels,
+                                h->bias3p, 0, d_policy, batch))) return rc;
+      if ((rc = launch_dense_tc(h, h->featv, h->a3v, &h->tm_a3v, &h->tm_w3v, vf * 64, a.value_fc, 1, a.value_fc,
+                                h->vfc1_b, 1, h->vhid, batch))) return rc;
+    } else {
+      const dim3 gp((batch + caz::PG_TM - 1) / caz::PG_TM, (a.n_labels + caz::PG_TN - 1) / caz::PG_TN);
+      caz::dense_tiled_kernel<<<gp, 256, 0, h->stream>>>(h->featp, h->pfc_w, h->pfc_b, d_policy, batch, pf * 64, a.n_labels, 0);
+      if ((rc = check_launch(h, "dense_tiled_kernel (policy)"))) return rc;
+      const dim3 gv((batch + caz::PG_TM - 1) / caz::PG_TM, (a.value_fc + caz::PG_TN - 1) / caz::PG_TN);
+      caz::dense_tiled_kernel<<<gv, 256, 0, h->stream>>>(h->featv, h->vfc1_w, h->vfc1_b, h->vhid, batch, vf * 64, a.value_fc, 1);
+      if ((rc = check_launch(h, "dense_tiled_kernel (value)"))) return rc;
+    }
     caz::policy_softmax_kernel<<<batch, 256, 0, h->stream>>>(d_policy, d_mask, a.n_labels, h->vhid, h->vfc2_w, h->vfc2_b, d_value, a.value_fc);
     if ((rc = check_launch(h, "policy_softmax_kernel"))) return rc;
   }
@@ -694,7 +803,7 @@ void caz_destroy(caz_handle* h) {
   if (h->sb_counter) cudaFree(h->sb_counter);
   if (h->sb_trace) cudaFree(h->sb_trace);
   void* ptrs[] = {h->head_w, h->head_b, h->pfc_w, h->pfc_b, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, h->in_act,
-                  h->act[0], h->act[1], h->act[2], h->featp, h->featv, h->vhid, h->d_planes, h->d_policy, h->d_value,
+                  h->act[0], h->act[1], h->act[2], h->featp, h->featv, h->vhid, h->a3p, h->a3v, h->w3p, h->w3v, h->bias3p, h->d_planes, h->d_policy, h->d_value,
                   h->d_mask, h->d_records, h->puct_buf, h->d_planes2, h->d_policy2, h->d_value2, h->d_mask2,
                   h->d_records2};
   for (void* p : ptrs) if (p) cudaFree(p);

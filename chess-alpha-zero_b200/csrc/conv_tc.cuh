@@ -79,6 +79,12 @@ struct ConvArgs {
   float* featv;             // [batch][vf*64]
   int pf, vf;
   int fp16;                 // 16-bit operands are fp16 instead of bf16 (CAZ_PRECISION_FP16)
+  // Plain-GEMM use of the same kernel (the heads' Dense layers: ksize 1, rows = positions in groups of 64):
+  // the N dimension is walked in n_tiles tiles of `n` columns, the result goes to a ROW-MAJOR fp32 matrix.
+  int n_tiles;              // 1 for convolutions
+  int n_total;              // valid output columns (<= n_tiles * n)
+  int m_rows;               // valid output rows
+  float* out_rm;            // nullptr or fp32 [m_rows][n_total] row-major; bias is then [n_tiles * n]
   int* err_flag;
 };
 
@@ -118,8 +124,10 @@ __device__ __forceinline__ size_t xf_index(int tile, int chunks, int chunk, int 
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* smem_epi, const float* s_bias,
                                               const float* s_head, int quad, int lane, int n0, uint32_t taddr,
                                               uint64_t* full_bar, uint32_t full_phase, uint64_t* empty_bar,
-                                              uint32_t release_rank) {
+                                              uint32_t release_rank, int nt = 0) {
   uint4* stage_b = reinterpret_cast<uint4*>(smem_epi + quad * EPI_WARP_BYTES);
+  float4* stage_f = reinterpret_cast<float4*>(stage_b);
+  const int fr = lane >> 3, fq = lane & 7;   // fp32 transposed mapping: row i*4+fr, float4 column fq
   const int br = lane >> 2, bc = lane & 3;   // 16-bit transposed mapping: row i*8+br, 16-byte column bc
   const int left = args.batch - n0;
   const int boards_live = left >= 2 ? 2 : (left > 0 ? left : 0);
@@ -157,7 +165,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
     }
     float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+    for (int j = 0; j < 32; ++j)
+      f[j] = __uint_as_float(v[j]) + (args.n_tiles > 1 ? __ldg(args.bias + nt * args.n + c0 + j) : s_bias[c0 + j]);
     if (args.residual) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -198,6 +207,29 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         out4[xf_index(tile, chunks, chunk, q, m)] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+    }
+    if (args.out_rm) {
+      // row-major fp32 result (GEMM use): transpose the 32x32 block through the per-warp staging buffer so that each
+      // store instruction covers 4 rows x 128 contiguous bytes
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        stage_f[lane * 8 + (q ^ (lane & 7))] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+      __syncwarp();
+      const int col = nt * args.n + c0 + fq * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + fr;
+        const float4 o = stage_f[r * 8 + (fq ^ (r & 7))];
+        const long row = grow(r);
+        if (row < args.m_rows && col + 3 < args.n_total)
+          *reinterpret_cast<float4*>(args.out_rm + row * args.n_total + col) = o;
+        else if (row < args.m_rows) {
+          const float ov[4] = {o.x, o.y, o.z, o.w};
+          for (int j = 0; j < 4; ++j)
+            if (col + j < args.n_total) args.out_rm[row * args.n_total + col + j] = ov[j];
+        }
+      }
+      __syncwarp();
     }
     if (args.out_bf16) {
       // the 16-bit operand copy must be NHWC for the next layer's TMA: transpose the 32x32 block through a 2 KiB

@@ -63,6 +63,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   const bool leader = rank == 0;
   const int pair0 = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1;
   const int num_pairs = (args.num_tiles + 1) >> 1;
+  const int num_work = num_pairs * args.n_tiles;   // (board-pair pair, N tile) work items
   const int k = args.ksize, pad = (k - 1) / 2, hw = 8 + k - 1;
   const int rb = args.row_bytes, kblk = rb >> 1;
   const int plane_bytes = hw * 2 * hw * rb;
@@ -94,7 +95,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
     ptx::tmem_alloc_2cta(tmem_base_slot, ACC_STAGES * ACC_COLS);
     ptx::tmem_relinquish_2cta();
   }
-  if (threadIdx.x < args.n) s_bias[threadIdx.x] = args.bias[threadIdx.x];
+  if (threadIdx.x < args.n && args.n_tiles == 1) s_bias[threadIdx.x] = args.bias[threadIdx.x];
   if (args.head_w)
     for (int i = threadIdx.x; i < (args.pf + args.vf) * args.n; i += THREADS) s_head[i] = args.head_w[i];
   ptx::tcgen05_fence_before();
@@ -107,24 +108,26 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
     // ===================== weight producer: this CTA's half of the output channels =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int pair = pair0; pair < num_pairs; pair += n_pairs_grid)
+    for (int t = pair0; t < num_work; t += n_pairs_grid) {
+      const int nt = t % args.n_tiles;
       for (int kc = 0; kc < args.kchunks; ++kc)
         for (int tap = 0; tap < k * k; ++tap) {
           ptx::mbar_wait(&b_empty[stage], phase ^ 1, args.err_flag, ERR2_PRODUCER_B);
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_expect_tx(&b_full[stage], 2 * b_bytes);   // both CTAs' halves
             ptx::tma_load_2d_2cta(smem_b + stage * B_STAGE_BYTES, &tmap_w, ptx::mapa_u32(&b_full[stage], 0),
-                                  (tap * args.kchunks + kc) * kblk, static_cast<int>(rank) * n_half);
+                                  (tap * args.kchunks + kc) * kblk, nt * args.n + static_cast<int>(rank) * n_half);
           }
           __syncwarp();
           if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
         }
+    }
   } else if (warp == 3) {
     // ===================== activation producer: this CTA's two boards =====================
     int slot = 0;
     uint32_t phase = 0;
-    for (int pair = pair0; pair < num_pairs; pair += n_pairs_grid) {
-      const int tile = 2 * pair + static_cast<int>(rank);
+    for (int t = pair0; t < num_work; t += n_pairs_grid) {
+      const int tile = 2 * (t / args.n_tiles) + static_cast<int>(rank);
       for (int kc = 0; kc < args.kchunks; ++kc) {
         ptx::mbar_wait(&a_empty[slot], phase ^ 1, args.err_flag, ERR2_PRODUCER_A);
         if (ptx::elect_one()) {
@@ -145,7 +148,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
       const int tap_rows16 = rb >> 4;
       int stage = 0, slot = 0, acc = 0;
       uint32_t phase = 0, a_phase = 0, acc_phase = 0;
-      for (int pair = pair0; pair < num_pairs; pair += n_pairs_grid) {
+      for (int t = pair0; t < num_work; t += n_pairs_grid) {
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, args.err_flag, ERR2_MMA_ACC);
         ptx::tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
@@ -185,11 +188,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
     const int quad = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int pair = pair0; pair < num_pairs; pair += n_pairs_grid) {
-      const int tile = 2 * pair + static_cast<int>(rank);
+    for (int t = pair0; t < num_work; t += n_pairs_grid) {
+      const int tile = 2 * (t / args.n_tiles) + static_cast<int>(rank);
       tc::epilogue_tile(args, smem_epi, s_bias, s_head, quad, lane, tile * 2,
                         tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS, &tmem_full[acc], acc_phase,
-                        &tmem_empty[acc], 0u /* the leader owns the accumulator-empty barrier */);
+                        &tmem_empty[acc], 0u /* the leader owns the accumulator-empty barrier */, t % args.n_tiles);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }

@@ -68,6 +68,31 @@ __global__ void cast_pad_kernel(const float* __restrict__ in, T* __restrict__ ou
   const int c = static_cast<int>(i - r * cpad);
   out[i] = from_f32<T>(c < cin ? in[r * cin + c] : 0.0f);
 }
+// fp32 [m][k] -> 16-bit [mpad][3k] = [hi | hi | lo] with hi = round16(x), lo = round16(x - hi): the A operand of the
+// "3-term split" tensor-core GEMM  x.w ~= hi.wh + hi.wl + lo.wh  (error ~2^-17 relative with bf16, fp32 accumulate)
+__global__ void split3_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int m, int mpad, int k, int fp16) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(mpad) * k) return;
+  const int row = static_cast<int>(i / k), col = static_cast<int>(i - static_cast<size_t>(row) * k);
+  float x = row < m ? in[i] : 0.0f;
+  uint16_t hi, lo;
+  if (fp16) {
+    const __half h = __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f));
+    const __half l = __float2half_rn(x - __half2float(h));
+    hi = *reinterpret_cast<const uint16_t*>(&h);
+    lo = *reinterpret_cast<const uint16_t*>(&l);
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = *reinterpret_cast<const uint16_t*>(&h);
+    lo = *reinterpret_cast<const uint16_t*>(&l);
+  }
+  uint16_t* o = out + static_cast<size_t>(row) * 3 * k;
+  o[col] = hi;
+  o[k + col] = hi;
+  o[2 * k + col] = lo;
+}
+
 // row-major fp32 [rows][n] -> the tensor-core epilogues' native residual layout (conv_tc.cuh: xf_index):
 // [tile][n/32 chunks][8 float4][128 lanes], lane m of a tile = (rank m>>4, board (m>>3)&1, file m&7)
 __global__ void xf_to_native_kernel(const float* __restrict__ in, float4* __restrict__ out, size_t rows, int n) {
