@@ -1,5 +1,5 @@
 // CUDA-core kernels of the evaluator: input packing / encoding, the fp32 parity build's convolution,
-// the two heads (1x1 convs, policy Dense + softmax, value Dense-Dense-tanh) and PUCT.
+// the heads (1x1 convs, tiled Dense, softmax + value output, operand split for the tensor-core Dense) and PUCT.
 // Reference semantics cited per kernel; paths relative to /root/reference/src/chess_zero.
 #pragma once
 #include <cuda_bf16.h>
@@ -416,56 +416,6 @@ policy_softmax_kernel(float* __restrict__ policy, const uint8_t* __restrict__ ma
       for (int wi = 0; wi < 8; ++wi) v += s_red[wi];
       value[blockIdx.x] = tanhf(v);
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Value head: Dense(value_fc, relu) -> Dense(1, tanh) (agent/model_chess.py:91-92).
-// One block = VTM positions; thread t owns hidden unit t (loops if value_fc > blockDim).
-// w1: [kin][hid], w2: [hid].
-// ------------------------------------------------------------------------------------------------
-constexpr int VTM = 16;
-
-__global__ void __launch_bounds__(256)
-value_fc_kernel(const float* __restrict__ featv, const float* __restrict__ w1, const float* __restrict__ b1,
-                const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ value, int batch,
-                int kin, int hid) {
-  extern __shared__ float s_fv[];  // [VTM][kin]
-  __shared__ float s_part[8][VTM];
-  const int b0 = blockIdx.x * VTM;
-  for (int i = threadIdx.x; i < VTM * kin; i += blockDim.x) {
-    const int m = i / kin, k = i - m * kin;
-    s_fv[i] = (b0 + m < batch) ? featv[static_cast<size_t>(b0 + m) * kin + k] : 0.0f;
-  }
-  __syncthreads();
-  float part[VTM];
-#pragma unroll
-  for (int m = 0; m < VTM; ++m) part[m] = 0.0f;
-  for (int h = threadIdx.x; h < hid; h += blockDim.x) {
-    float acc[VTM];
-#pragma unroll
-    for (int m = 0; m < VTM; ++m) acc[m] = 0.0f;
-    for (int k = 0; k < kin; ++k) {
-      const float wv = __ldg(w1 + static_cast<size_t>(k) * hid + h);
-#pragma unroll
-      for (int m = 0; m < VTM; ++m) acc[m] = fmaf(s_fv[m * kin + k], wv, acc[m]);
-    }
-    const float bv = b1[h], w2v = w2[h];
-#pragma unroll
-    for (int m = 0; m < VTM; ++m) part[m] = fmaf(fmaxf(acc[m] + bv, 0.0f), w2v, part[m]);
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int m = 0; m < VTM; ++m) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part[m] += __shfl_xor_sync(0xffffffffu, part[m], o);
-    if (lane == 0) s_part[warp][m] = part[m];
-  }
-  __syncthreads();
-  if (threadIdx.x < VTM && b0 + threadIdx.x < batch) {
-    float v = b2[0];
-    for (int wi = 0; wi < 8; ++wi) v += s_part[wi][threadIdx.x];
-    value[b0 + threadIdx.x] = tanhf(v);
   }
 }
 
