@@ -47,6 +47,22 @@ def conv3x3_flops_per_launch(batch, filters=256):
     return 2 * 64 * batch * filters * 9 * filters
 
 
+def ncu_traffic_bytes(batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per tower-conv launch from the committed ncu launch list
+    (profiles/r1_v6_launches.csv, batch 4096; mean over the conv1-type and conv2-type launches), else None."""
+    path = os.path.join(ROOT, "profiles", "r1_v6_launches.csv")
+    if batch != 4096 or not os.path.exists(path):
+        return None
+    import csv
+    per = {}
+    for row in csv.DictReader(l for l in open(path) if l.startswith('"')):
+        if "conv_tc" in row["Kernel Name"] and row["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[row["Metric Unit"]]
+            per[row["ID"]] = per.get(row["ID"], 0.0) + float(row["Metric Value"].replace(",", "")) * scale
+    vals = [v for v in per.values() if v > 150e6]     # tower launches (the stem and dense launches move less)
+    return sum(vals) / len(vals) if vals else None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -361,7 +377,7 @@ def main():
     achieved = conv3x3_flops_per_launch(B) / (conv_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (3x3x256->256 implicit GEMM)", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(B),
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step); "
                                f"burst peak {peaks['bf16_tflops']}",
                 "flops_per_launch": conv3x3_flops_per_launch(B), "mean_launch_ms": conv_ms, "launches_timed": n_conv,

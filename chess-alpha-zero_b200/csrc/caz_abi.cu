@@ -71,6 +71,8 @@ struct caz_handle {
   cudaStream_t stream = nullptr;
   std::string err;
   std::vector<ConvLayer> convs;  // stem, then conv1/conv2 of each block
+  bool snake = true;             // odd layers walk the batch backwards (CAZ_SNAKE=0 turns it off)
+  bool l2_prefetch = false;       // CAZ_L2_PREFETCH=0 turns the one-tile-ahead L2 prefetches off
   bool use_2cta = true;          // per-layer convolutions as CTA pairs (cta_group::2); CAZ_CONV_2CTA=0 turns it off
   // weight slabs the layers point into: the tower's layers are contiguous so that one tensor map covers them
   void* w_stem = nullptr;
@@ -388,6 +390,14 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
     args.n_total = L.cout;
     args.m_rows = batch * 64;
     args.out_rm = nullptr;
+    args.l2_prefetch = h->l2_prefetch ? 1 : 0;
+    args.reverse = (h->snake && (li & 1)) ? 1 : 0;
+    if (const char* e = getenv("CAZ_DBG_EPI")) {   // timing experiments only (results are wrong): drop epilogue traffic
+      const int m = atoi(e);
+      if (m & 1) args.residual = nullptr;
+      if (m & 2) args.out_f32 = nullptr;
+      if (m & 4) args.out_bf16 = nullptr;
+    }
     args.err_flag = h->err_flag_dev;
     if (h->use_2cta && args.num_tiles >= 2 && L.cout % 64 == 0) {
       // CTA pairs: one cta_group::2 MMA covers two tiles (four boards)
@@ -903,6 +913,8 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
     CREATE_TRY(cudaFuncSetAttribute(caz::tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc::SMEM_BYTES));
     CREATE_TRY(cudaFuncSetAttribute(caz::tc2::conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc2::SMEM_BYTES));
     if (const char* e = getenv("CAZ_CONV_2CTA")) h->use_2cta = atoi(e) != 0;
+    if (const char* e = getenv("CAZ_L2_PREFETCH")) h->l2_prefetch = atoi(e) != 0;
+    if (const char* e = getenv("CAZ_SNAKE")) h->snake = atoi(e) != 0;
   } else {
     const size_t s3 = (size_t)(8 + a.block_kernel - 1) * (8 + a.block_kernel - 1) * a.filters * 4;
     const size_t s1 = (size_t)(8 + a.stem_kernel - 1) * (8 + a.stem_kernel - 1) * a.input_planes * 4;

@@ -85,6 +85,8 @@ struct ConvArgs {
   int n_total;              // valid output columns (<= n_tiles * n)
   int m_rows;               // valid output rows
   float* out_rm;            // nullptr or fp32 [m_rows][n_total] row-major; bias is then [n_tiles * n]
+  int reverse;              // walk the tiles from the last to the first (CTA-pair kernel; see conv_tc2.cuh)
+  int l2_prefetch;          // pull the next tile's activations / residual into L2 one tile ahead
   int* err_flag;
 };
 
@@ -124,7 +126,7 @@ __device__ __forceinline__ size_t xf_index(int tile, int chunks, int chunk, int 
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* smem_epi, const float* s_bias,
                                               const float* s_head, int quad, int lane, int n0, uint32_t taddr,
                                               uint64_t* full_bar, uint32_t full_phase, uint64_t* empty_bar,
-                                              uint32_t release_rank, int nt = 0) {
+                                              uint32_t release_rank, int nt = 0, int next_n0 = -1) {
   uint4* stage_b = reinterpret_cast<uint4*>(smem_epi + quad * EPI_WARP_BYTES);
   float4* stage_f = reinterpret_cast<float4*>(stage_b);
   const int fr = lane >> 3, fq = lane & 7;   // fp32 transposed mapping: row i*4+fr, float4 column fq
@@ -143,6 +145,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
   if (args.residual) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) res_pf[q] = res4[xf_index(tile, chunks, 0, q, m)];
+    // The residual stream comes from HBM (it is larger than L2 at big batches) and is consumed 4 KiB per warp and chunk
+    // with only one chunk of lookahead in registers: pull the NEXT tile's slice into L2 now, a whole tile ahead.
+    // A warp's slice of one chunk is 8 x 512 contiguous bytes = 32 lines: one prefetch per lane and chunk.
+    if (next_n0 >= 0 && args.l2_prefetch) {
+      const int ntile = next_n0 >> 1;
+      for (int ch = 0; ch < chunks; ++ch)
+        ptx::prefetch_l2(res4 + xf_index(ntile, chunks, ch, lane >> 2, quad * 32 + (lane & 3) * 8));
+    }
   }
   ptx::mbar_wait(full_bar, full_phase, args.err_flag, ERR_EPILOGUE);
   ptx::tcgen05_fence_after();
@@ -414,9 +424,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_const
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
       const int n0 = tile * 2;
+      const int next_tile = tile + static_cast<int>(gridDim.x);
       epilogue_tile(args, smem_epi, s_bias, s_head, quad, lane, n0,
                     tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS, &tmem_full[acc], acc_phase,
-                    &tmem_empty[acc], kLocalCta);
+                    &tmem_empty[acc], kLocalCta, 0, next_tile < args.num_tiles ? next_tile * 2 : -1);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }

@@ -64,6 +64,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   const int pair0 = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1;
   const int num_pairs = (args.num_tiles + 1) >> 1;
   const int num_work = num_pairs * args.n_tiles;   // (board-pair pair, N tile) work items
+  // Consecutive layers walk the batch in opposite directions ("snake"): a layer starts with the tiles its predecessor
+  // wrote LAST, which are still in the 126 MB L2 -- the activations of a big batch are larger than L2.
+  auto pair_of = [&](int t) -> int { const int pr = t / args.n_tiles; return args.reverse ? num_pairs - 1 - pr : pr; };
   const int k = args.ksize, pad = (k - 1) / 2, hw = 8 + k - 1;
   const int rb = args.row_bytes, kblk = rb >> 1;
   const int plane_bytes = hw * 2 * hw * rb;
@@ -127,7 +130,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
     int slot = 0;
     uint32_t phase = 0;
     for (int t = pair0; t < num_work; t += n_pairs_grid) {
-      const int tile = 2 * (t / args.n_tiles) + static_cast<int>(rank);
+      const int tile = 2 * pair_of(t) + static_cast<int>(rank);
+      // the activations of a big batch come from HBM and the ring holds only two chunk tiles: ask L2 for the NEXT
+      // work item's tiles now, a whole tile ahead of need
+      if (args.l2_prefetch && t + n_pairs_grid < num_work && ptx::elect_one()) {
+        const int ntile = 2 * pair_of(t + n_pairs_grid) + static_cast<int>(rank);
+        for (int kc = 0; kc < args.kchunks; ++kc) ptx::tma_prefetch_4d(&tmap_halo, kc * kblk, -pad, ntile * 2, -pad);
+      }
+      __syncwarp();
       for (int kc = 0; kc < args.kchunks; ++kc) {
         ptx::mbar_wait(&a_empty[slot], phase ^ 1, args.err_flag, ERR2_PRODUCER_A);
         if (ptx::elect_one()) {
@@ -189,10 +199,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair0; t < num_work; t += n_pairs_grid) {
-      const int tile = 2 * (t / args.n_tiles) + static_cast<int>(rank);
+      const int tile = 2 * pair_of(t) + static_cast<int>(rank);
+      const int tn = t + n_pairs_grid;
+      const int next_tile = tn < num_work ? 2 * pair_of(tn) + static_cast<int>(rank) : -1;
       tc::epilogue_tile(args, smem_epi, s_bias, s_head, quad, lane, tile * 2,
                         tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS, &tmem_full[acc], acc_phase,
-                        &tmem_empty[acc], 0u /* the leader owns the accumulator-empty barrier */, t % args.n_tiles);
+                        &tmem_empty[acc], 0u /* the leader owns the accumulator-empty barrier */, t % args.n_tiles,
+                        next_tile >= 0 && next_tile < args.num_tiles ? next_tile * 2 : -1);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }

@@ -166,6 +166,16 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// L2 prefetches: a tensor box (no shared-memory destination, no barrier) and a single 128-byte line
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
+}
+
 // 2-CTA (cta_group::2) loads: the data lands in the issuing CTA's shared memory, the completion bytes are counted on
 // an mbarrier that may live in the PEER CTA (`bar_cluster_addr` = shared::cluster address from mapa).
 __device__ __forceinline__ uint32_t mapa_u32(const void* local_smem, uint32_t cta_rank) {
