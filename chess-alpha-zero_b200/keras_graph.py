@@ -330,7 +330,8 @@ def load_config_file(path):
 def load_weight_file(path, cfg):
     """Returns {keras weight name: float32 array}.  Accepts
       * ``.npz`` keyed by Keras weight names (this package's native container), and
-      * Keras ``save_weights`` HDF5 (model_chess.py:164) through :mod:`.hdf5_min` (no h5py needed)."""
+      * Keras ``save_weights`` / ``model.save`` HDF5 (model_chess.py:164) through :mod:`.hdf5_min`, a
+        dependency-free reader of the format subset Keras writes (h5py is not needed)."""
     shapes = expected_shapes(cfg)
     with open(path, "rb") as f:
         magic = f.read(8)
@@ -353,8 +354,20 @@ def load_weight_file(path, cfg):
     return out
 
 
-def save_weight_file(path, weights):
+def save_weight_file(path, weights, cfg=None):
+    """``.h5`` / ``.hdf5`` paths get the Keras ``save_weights`` tree (needs the model config for the layer list);
+    anything else an ``.npz`` keyed by Keras weight names."""
     tmp = path + ".tmp"
-    with open(tmp, "wb") as f:
-        np.savez(f, **{k: np.asarray(v, np.float32) for k, v in weights.items()})
+    if path.endswith((".h5", ".hdf5")):
+        if cfg is None:
+            raise ValueError("writing a Keras HDF5 weight file needs the model config")
+        from . import hdf5_min
+        layers = []
+        for layer in _Graph(cfg).cfg["layers"]:
+            prefix = layer["name"] + "/"
+            layers.append((layer["name"], [(k, np.asarray(v, np.float32)) for k, v in weights.items() if k.startswith(prefix)]))
+        hdf5_min.write_keras_weights(tmp, layers)
+    else:
+        with open(tmp, "wb") as f:
+            np.savez(f, **{k: np.asarray(v, np.float32) for k, v in weights.items()})
     os.replace(tmp, path)

@@ -84,5 +84,5 @@ class ChessModel:
             raise RuntimeError("nothing to save: call build() or load() first")
         with open(config_path, "wt") as f:
             json.dump(self.keras_config, f)
-        keras_graph.save_weight_file(weight_path, self.weights)
+        keras_graph.save_weight_file(weight_path, self.weights, self.keras_config)
         self.digest = self.fetch_digest(weight_path)
