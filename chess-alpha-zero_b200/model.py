@@ -21,11 +21,12 @@ logger = getLogger(__name__)
 
 
 class ChessModel:
-    def __init__(self, config=None, device=0, precision="bf16", max_batch=4096):
+    def __init__(self, config=None, device=0, precision="bf16", max_batch=4096, transport="pipe"):
         self.config = config if config is not None else Config()
         self.device = device
         self.precision = precision
         self.max_batch = max_batch
+        self.transport = transport     # "pipe": multiprocessing.Pipe payloads (the reference's); "shm": shm_pipes.py
         self.model = None      # Evaluator; the attribute name the reference's ChessModelAPI reads
         self.digest = None
         self.api = None
@@ -34,7 +35,7 @@ class ChessModel:
 
     def get_pipes(self, num=1):
         if self.api is None:
-            self.api = ChessModelAPI(self)
+            self.api = ChessModelAPI(self, transport=self.transport)
             self.api.start()
         return [self.api.create_pipe() for _ in range(num)]
 

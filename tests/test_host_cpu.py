@@ -145,9 +145,43 @@ def _client(pipe, k, out):
         out.append((int(p.argmax()) == int(x.sum()) % 1968, abs(v - (k * 20 + j)) < 1e-6, isinstance(v, float)))
 
 
-@pytest.mark.parametrize("which", ["ours", "reference"])
+def _process_client(pipe, k, queue):
+    out = []
+    _client(pipe, k, out)
+    queue.put(out)
+
+
+@pytest.mark.parametrize("transport", ["pipe", "shm"])
+def test_pipe_protocol_across_processes(transport):
+    """The endpoint objects travel to spawned workers the way the reference hands Connections to its pool
+    (worker/self_play.py:47,122-129)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    api = caz.ChessModelAPI(_FakeModel(), transport=transport)
+    pipes = [api.create_pipe() for _ in range(3)]
+    api.start()
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_process_client, args=(p, k, queue)) for k, p in enumerate(pipes)]
+    [p.start() for p in procs]
+    out = [r for _ in procs for r in queue.get(timeout=120)]
+    [p.join(timeout=30) for p in procs]
+    api.stop()
+    assert len(out) == 60 and all(all(r) for r in out)
+
+
+def test_shm_slab_capacity_is_enforced():
+    api = caz.ChessModelAPI(_FakeModel(), transport="shm", shm_capacity=2)
+    api.create_pipe(), api.create_pipe()
+    with pytest.raises(RuntimeError, match="shm_capacity"):
+        api.create_pipe()
+    api.stop()
+
+
+@pytest.mark.parametrize("which", ["ours", "ours-shm", "reference"])
 def test_pipe_protocol(which):
-    if which == "reference":
+    if which == "ours-shm":
+        ChessModelAPI = lambda m: caz.ChessModelAPI(m, transport="shm")  # noqa: E731
+    elif which == "reference":
         if not os.path.exists("/root/reference/src"):
             pytest.skip("reference checkout absent (GPU box)")
         import sys
@@ -168,13 +202,14 @@ def test_pipe_protocol(which):
     assert len(out) == 160 and all(all(r) for r in out)
 
 
-def test_pipe_server_delivers_failures_instead_of_hanging():
+@pytest.mark.parametrize("transport", ["pipe", "shm"])
+def test_pipe_server_delivers_failures_instead_of_hanging(transport):
     class Broken:
         class model:
             @staticmethod
             def predict_on_batch(data):
                 raise RuntimeError("device lost")
-    api = caz.ChessModelAPI(Broken())
+    api = caz.ChessModelAPI(Broken(), transport=transport)
     pipe = api.create_pipe()
     api.start()
     pipe.send(np.zeros((18, 8, 8), np.float32))
