@@ -40,10 +40,10 @@ constexpr int THREADS = 256;
 constexpr int A_PLANES = 4;                          // up to 256 input channels
 constexpr int A_PLANE_BYTES_3 = 10 * 2 * 10 * 128;   // 25 600: 3x3 halo tile of one 64-channel chunk
 constexpr int A_BYTES = A_PLANES * A_PLANE_BYTES_3;  // 102 400 (a 5x5 / 7x7 single-plane stem tile fits inside)
-constexpr int W_RING_BYTES = 96 * 1024;
-constexpr int W_SLOT_MAX_BYTES = 24 * 1024;
+constexpr int W_RING_BYTES = 108 * 1024;
+constexpr int W_SLOT_MAX_BYTES = 36 * 1024;   // a whole 3x3 filter of 32 output channels
 constexpr int MAX_W_SLOTS = 16;
-constexpr int NACC = 8;
+constexpr int NACC = 4;   // accumulator groups in TMEM: one per K sub-step of a 64-channel chunk row
 constexpr int BAR_BYTES = 1024;
 constexpr int SMEM_BYTES = A_BYTES + W_RING_BYTES + BAR_BYTES + 1024 /*alignment*/;
 constexpr int SCRATCH_FLOATS = (A_BYTES + W_RING_BYTES) / 4;  // what the head phases may use
@@ -139,25 +139,33 @@ __device__ __forceinline__ void grid_sync_all(const Args& args, unsigned phases_
   __syncthreads();
 }
 
-// The MMAs of `TPS` consecutive taps of one 64-channel chunk, issued by ONE thread.  `tap0` is the first tap's
-// index within the filter, `first` the number of taps issued before it in this layer (accumulator rotation).
-// Two warps issue: `which` (0/1) takes the taps whose index in the layer is even/odd -- exactly the taps that
-// accumulate into accumulator group 0-3 / 4-7, so the two issuers never touch the same TMEM columns.
+// The MMAs of `TPS` consecutive taps of one 64-channel chunk (one weight-ring slot), issued by ONE thread.
+// A tcgen05.mma at these shapes occupies the tensor pipe for (M + N) * 32 B / 128 B per cycle of operand reads
+// (M = 64: 25 cycles, M = 128: 41 cycles at N = 16; tools/ub/ub_small.cu) -- IF the issuing thread keeps up: every
+// scalar instruction between two MMAs costs the pipe time.  So everything is hoisted: the caller passes descriptors
+// that already point at this chunk and slot, the tap geometry is compile-time where the slot shape allows it, and
+// what is left per MMA is two 64-bit adds.
+// Two warps issue, taking alternate 64-channel chunks of a layer, so that one of them is feeding the pipe while the
+// other waits for weights; each accumulates into its own two TMEM column groups (even / odd K sub-steps).  Which MMA
+// lands in which accumulator, and in what order, depends only on (chunk, tap, sub-step) -- not on the slot shape or
+// the grid geometry -- so results are bit-identical across batch sizes.
+//   a_plane: A descriptor of the chunk's halo tile;  b_slot: B descriptor of the ring slot
+//   (dy0, dx0): filter position of the slot's first tap; rp8 = halo rows between ranks * 8 (descriptor units of 16 B)
 template <int K, int TPS>
-__device__ __forceinline__ void issue_taps(uint64_t a_plane, uint64_t b_slot, int tap0, int first, int row_pitch,
-                                           int tap_desc, uint32_t tmem_base, int ns, uint32_t idesc, int which) {
+__device__ __forceinline__ void issue_taps(uint64_t a_plane, uint64_t b_slot, int dy0, int dx0, uint64_t rp8,
+                                           uint64_t tap_desc, uint32_t tm0, uint32_t tm1, uint32_t idesc, bool fresh) {
+  const uint64_t a_row = a_plane + static_cast<uint64_t>(dy0) * rp8 + static_cast<uint64_t>(dx0 * 8);
 #pragma unroll
   for (int t = 0; t < TPS; ++t) {
-    if (((first + t) & 1) != which) continue;
-    const int tap = tap0 + t;
-    const int dy = tap / K, dx = tap - dy * K;
-    // tap (dy, dx) = the same halo tile, viewed (nb*hw*dy + dx) rows of 128 bytes further on
-    const uint64_t adesc = a_plane + static_cast<uint64_t>((dy * row_pitch + dx) * 8);
-    const uint64_t bdesc = b_slot + static_cast<uint64_t>(t * tap_desc);
-    const uint32_t accum = first + t >= 2 ? 1u : 0u;        // taps 0 and 1 of a layer initialise the 8 accumulators
-    const uint32_t tm = tmem_base + static_cast<uint32_t>(((first + t) & 1) * 4 * ns);
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) ptx::mma_bf16_ss(tm + kk * ns, adesc + kk * 2, bdesc + kk * 2, idesc, accum);
+    // TPS == K*K: the whole filter (dy0 = dx0 = 0); TPS == K: one filter row (dx0 = 0); TPS == 1: one tap
+    const uint64_t adesc = TPS == K * K ? a_row + static_cast<uint64_t>(t / K) * rp8 + static_cast<uint64_t>((t % K) * 8)
+                                        : a_row + static_cast<uint64_t>(t * 8);
+    const uint64_t bdesc = b_slot + static_cast<uint64_t>(t) * tap_desc;
+    const uint32_t accum = (t > 0 || !fresh) ? 1u : 0u;   // this issuer's first tap of a layer initialises its accumulators
+    ptx::mma_bf16_ss(tm0, adesc, bdesc, idesc, accum);
+    ptx::mma_bf16_ss(tm1, adesc + 2, bdesc + 2, idesc, accum);
+    ptx::mma_bf16_ss(tm0, adesc + 4, bdesc + 4, idesc, 1u);
+    ptx::mma_bf16_ss(tm1, adesc + 6, bdesc + 6, idesc, 1u);
   }
 }
 
@@ -196,7 +204,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     for (int i = 0; i < A_PLANES; ++i) ptx::mbar_init(&a_full[i], 1);
     for (int i = 0; i < args.n_slots; ++i) {
       ptx::mbar_init(&w_full[i], 1);
-      ptx::mbar_init(&w_empty[i], 2);   // one tcgen05.commit from each of the two MMA issuer warps
+      ptx::mbar_init(&w_empty[i], 1);   // the tcgen05.commit of the issuer warp that consumed the slot
     }
     ptx::mbar_init(acc_full, 2);
     ptx::mbar_fence_init();
@@ -285,6 +293,10 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         }
       }
       __syncwarp();
+      if (args.trace && blockIdx.x == 0) {   // when did the layer's last activation plane land (debug only)
+        ptx::mbar_wait(&a_full[kch - 1], l == 0 ? 0u : (kch - 1 < args.stem_kchunks ? (l & 1) : ((l - 1) & 1)), args.err_flag, ERR_A);
+        if (lane == 0) args.trace[l * 8 + 7] = clock64();
+      }
     }
   } else if (warp == 1 || warp == 2) {
     // ============ MMA issuers (two warps: a tcgen05.mma costs its issuing thread ~60 cycles whatever its shape,
@@ -292,49 +304,53 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     const int which = warp - 1;
     const uint32_t idesc = ptx::idesc_h16_f32(64 * args.nb, args.ns, args.fp16 != 0);
     const uint64_t b_desc0 = desc_sw128(ptx::smem_u32(smem_w), 1024);
-    const int tap_desc = tap_bytes >> 4;
+    const uint64_t tap_desc = static_cast<uint64_t>(tap_bytes >> 4);
+    const uint64_t slot_desc = static_cast<uint64_t>(args.slot_bytes >> 4);
+    const uint32_t tm0 = tmem_base + static_cast<uint32_t>(2 * which * args.ns), tm1 = tm0 + static_cast<uint32_t>(args.ns);
     int slot = 0;
     uint32_t phase = 0, a_phase = 0;
+    uint64_t b_slot = b_desc0;
     for (int l = 0; l < args.n_layers; ++l) {
       const int k = l == 0 ? args.stem_k : args.blk_k;
       const int kch = l == 0 ? args.stem_kchunks : args.filters / 64;
       const int tps = taps_per_slot(k, args.ns);
       const int hw = 8 + k - 1;
-      const int plane_bytes = hw * args.nb * hw * 128;
-      const int row_pitch = args.nb * hw;  // halo rows between consecutive ranks
+      const uint64_t plane_desc = static_cast<uint64_t>((hw * args.nb * hw * 128) >> 4);
+      const uint64_t rp8 = static_cast<uint64_t>(args.nb * hw * 8);  // halo rows between consecutive ranks, x 128 B / 16
       // next 8-row group = next (rank, board) = hw halo rows further on
-      const uint64_t a_desc0 = desc_sw128(ptx::smem_u32(smem_a), hw * 128);
-      for (int kc = 0; kc < kch; ++kc) {
+      uint64_t a_plane = desc_sw128(ptx::smem_u32(smem_a), hw * 128);
+      bool fresh = true;   // this issuer has not written its accumulators in this layer yet
+      const int shape = (k == 3 && tps == 9) ? 0 : (k == 3 && tps == 3) ? 1 : (k == 5 && tps == 5) ? 2 : 3;
+      for (int kc = 0; kc < kch; ++kc, a_plane += plane_desc) {
         // plane kc completes once per layer that uses it (the stem may use fewer planes than the tower)
         ptx::mbar_wait(&a_full[kc], (a_phase >> kc) & 1u, args.err_flag, ERR_MMA_A);
         a_phase ^= 1u << kc;
         if (args.trace && blockIdx.x == 0 && lane == 0 && kc == 0 && which == 0) args.trace[l * 8 + 1] = clock64();
         if (args.trace && blockIdx.x == 0 && lane == 0 && kc == kch - 1 && which == 0) args.trace[l * 8 + 2] = clock64();
+        int dy0 = 0, dx0 = 0;
         for (int tap0 = 0; tap0 < k * k; tap0 += tps) {
-          ptx::mbar_wait(&w_full[slot], phase, args.err_flag, ERR_MMA_W);
-          ptx::tcgen05_fence_after();
-          if (ptx::elect_one()) {
-            const uint64_t a_plane = a_desc0 + static_cast<uint64_t>((kc * plane_bytes) >> 4);
-            const uint64_t b_slot = b_desc0 + static_cast<uint64_t>((slot * args.slot_bytes) >> 4);
-            const int first = kc * k * k + tap0;
-            if (k == 3 && tps == 9) issue_taps<3, 9>(a_plane, b_slot, tap0, first, row_pitch, tap_desc, tmem_base, args.ns, idesc, which);
-            else if (k == 3 && tps == 3) issue_taps<3, 3>(a_plane, b_slot, tap0, first, row_pitch, tap_desc, tmem_base, args.ns, idesc, which);
-            else if (k == 5 && tps == 5) issue_taps<5, 5>(a_plane, b_slot, tap0, first, row_pitch, tap_desc, tmem_base, args.ns, idesc, which);
-            else {
-              for (int t = 0; t < tps; ++t) {
-                if (((first + t) & 1) != which) continue;
-                const int tap = tap0 + t, dy = tap / k, dx = tap - dy * k;
-                const uint64_t adesc = a_plane + static_cast<uint64_t>((dy * row_pitch + dx) * 8);
-                const uint64_t bdesc = b_slot + static_cast<uint64_t>(t * tap_desc);
-                const uint32_t tm = tmem_base + static_cast<uint32_t>(((first + t) & 1) * 4 * args.ns);
-                for (int kk = 0; kk < 4; ++kk)
-                  ptx::mma_bf16_ss(tm + kk * args.ns, adesc + kk * 2, bdesc + kk * 2, idesc, first + t >= 2 ? 1u : 0u);
-              }
+          if ((kc & 1) == which) {   // issuer `which` takes the chunks with kc % 2 == which
+            ptx::mbar_wait(&w_full[slot], phase, args.err_flag, ERR_MMA_W);
+            ptx::tcgen05_fence_after();
+            if (ptx::elect_one()) {
+              if (shape == 0) issue_taps<3, 9>(a_plane, b_slot, 0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
+              else if (shape == 1) issue_taps<3, 3>(a_plane, b_slot, dy0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
+              else if (shape == 2) issue_taps<5, 5>(a_plane, b_slot, dy0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
+              else
+                for (int t = 0, dy = dy0, dx = dx0; t < tps; ++t) {
+                  issue_taps<1, 1>(a_plane, b_slot + static_cast<uint64_t>(t) * tap_desc, dy, dx, rp8, tap_desc, tm0, tm1, idesc,
+                                   fresh && t == 0);
+                  if (++dx == k) { dx = 0; ++dy; }
+                }
+              ptx::mma_commit(&w_empty[slot]);
             }
-            ptx::mma_commit(&w_empty[slot]);
+            __syncwarp();
+            fresh = false;
           }
-          __syncwarp();
-          if (++slot == args.n_slots) { slot = 0; phase ^= 1; }
+          dx0 += tps;
+          while (dx0 >= k) { dx0 -= k; ++dy0; }
+          b_slot += slot_desc;
+          if (++slot == args.n_slots) { slot = 0; phase ^= 1; b_slot = b_desc0; }
         }
       }
       if (args.trace && blockIdx.x == 0 && lane == 0 && which == 0) args.trace[l * 8 + 3] = clock64();
@@ -355,6 +371,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     for (int l = 0; l < args.n_layers; ++l) {
       const bool conv1 = l > 0 && (l & 1);     // bf16 out to y only
       const bool has_res = l > 0 && !(l & 1);  // conv2: + residual, out to xf and xb
+      const bool two_issuers = (l == 0 ? args.stem_kchunks : args.filters / 64) > 1;
       const float* bias = args.bias_all + static_cast<size_t>(l) * args.filters + col0;
       for (int c0 = 0; c0 < args.ns; c0 += 16) {
         // bias and the residual slice (written by this very thread two layers ago) are fetched BEFORE the wait
@@ -375,17 +392,20 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           if (args.trace && blockIdx.x == 0 && threadIdx.x == 128) args.trace[l * 8 + 4] = clock64();
         }
         {
+          // a single-chunk layer (the stem) is issued by issuer 0 alone: accumulators 2 and 3 were not written
           uint32_t v[NACC][16];
-#pragma unroll
-          for (int a2 = 0; a2 < NACC; ++a2) ptx::tmem_ld_32x16(taddr + a2 * args.ns + c0, v[a2]);
+          ptx::tmem_ld_32x16(taddr + c0, v[0]);
+          ptx::tmem_ld_32x16(taddr + args.ns + c0, v[1]);
+          if (two_issuers) {
+            ptx::tmem_ld_32x16(taddr + 2 * args.ns + c0, v[2]);
+            ptx::tmem_ld_32x16(taddr + 3 * args.ns + c0, v[3]);
+          }
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float s01 = __uint_as_float(v[0][j]) + __uint_as_float(v[1][j]);
-            const float s23 = __uint_as_float(v[2][j]) + __uint_as_float(v[3][j]);
-            const float s45 = __uint_as_float(v[4][j]) + __uint_as_float(v[5][j]);
-            const float s67 = __uint_as_float(v[6][j]) + __uint_as_float(v[7][j]);
-            f[j] += (s01 + s23) + (s45 + s67);
+            const float s23 = two_issuers ? __uint_as_float(v[2][j]) + __uint_as_float(v[3][j]) : 0.0f;
+            f[j] += s01 + s23;
           }
         }
         if (live) {

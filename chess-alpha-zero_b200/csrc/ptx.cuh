@@ -114,6 +114,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
   }
 }
 
+// Same, for warps that wait while ANOTHER warp of their scheduler partition does latency-critical issue work (the MMA
+// issuers): back off between polls so the spin does not take issue slots from it.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, int* err_flag, int code, unsigned ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 22)) {
+      if (err_flag) atomicExch(err_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
 // ---- cross-CTA (grid-scope) flags and proxy fences ----------------------------------------------------
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
