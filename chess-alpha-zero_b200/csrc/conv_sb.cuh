@@ -60,6 +60,7 @@ struct Args {
   int blk_k;                  // tower kernel size
   int in_planes, in_cpad;
   int fp16;                   // 16-bit operands are fp16 instead of bf16
+  int head_reps;              // 1; > 1 repeats the head phases (measurement aid)
   int slot_bytes, n_slots;    // weight ring geometry
   const float* planes;        // fp32 [batch][in_planes][64] or nullptr
   const uint8_t* records;     // u8 [batch][68] or nullptr (exactly one of the two)
@@ -84,8 +85,10 @@ struct Args {
   const uint8_t* mask;        // nullptr or [batch][n_labels]
   float* policy;              // [batch][n_labels]
   float* value;               // [batch]
-  unsigned* counter;          // grid barrier counter
-  unsigned base;              // its value when this launch started
+  unsigned* flags;            // [gridDim.x] progress flag of every CTA: base + number of phases it has completed
+  unsigned base;              // flag value that means "nothing of this launch done yet" (monotonic across launches)
+  unsigned* counter;          // grid-wide barrier counter for the three head phases (one poller per CTA, one address)
+  unsigned cbase;             // its value when this launch started
   long long* trace;           // nullptr or [n_layers+1][8] clock64 stamps of CTA 0 (see caz_debug_sb_trace)
   int* err_flag;
 };
@@ -93,8 +96,9 @@ struct Args {
 enum : int { ERR_W = 201, ERR_A = 202, ERR_GRID = 203, ERR_MMA_A = 204, ERR_MMA_W = 205, ERR_EPI = 206 };
 
 // Grid phases: 0 input pack, 1..L the L conv layers, L+1 head 1x1 convs, L+2 head dense layers.
-// Phase i is complete when the counter has advanced by (i+1) * gridDim.x.
-constexpr int EXTRA_PHASES = 3;  // pack + two head phases that end in a barrier
+// A CTA that has packed its share of the input publishes flag = base + 1, after layer l flag = base + 2 + l.
+constexpr int GRID_PHASES = 3;   // grid-wide arrivals per launch: tower done, head convs done, head dense layers done
+constexpr int MAX_TILES = 64;   // flags: 16 words per board tile
 
 // taps per weight-ring slot: the whole filter, one filter row, or one tap -- the largest that fits a slot
 __host__ __device__ inline int taps_per_slot(int k, int ns) {
@@ -113,28 +117,31 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr, uint32_t sbo_
   return d;
 }
 
-// wait until every CTA has completed `phases_done` phases
-__device__ __forceinline__ void grid_wait(const Args& args, unsigned phases_done) {
-  const unsigned target = args.base + phases_done * gridDim.x;
+__device__ __forceinline__ void sync_trap(const Args& args) {
+  if (args.err_flag) atomicExch(args.err_flag, ERR_GRID);
+  __threadfence_system();
+  __trap();
+}
+
+// Grid-wide barrier of the head phases (3 per launch): one release-add per CTA on one L2 counter, one polling thread
+// per CTA.  (The tower layers do NOT use it: they synchronise per board tile through the progress flags.  Polling the
+// flags of every tile from every CTA was measured to swamp the L2 slices that hold them.)
+__device__ __forceinline__ void grid_wait(const Args& args, unsigned n) {
+  const unsigned target = args.cbase + n * gridDim.x;
   uint32_t spins = 0;
   // relaxed polls (an acquire per poll is a fence per poll), one acquire fence once the count is there
-  while (static_cast<int>(ptx::ld_relaxed_gpu(args.counter) - target) < 0) {
-    if (++spins > (1u << 26)) {
-      if (args.err_flag) atomicExch(args.err_flag, ERR_GRID);
-      __threadfence_system();
-      __trap();
-    }
-  }
+  while (static_cast<int>(ptx::ld_relaxed_gpu(args.counter) - target) < 0)
+    if (++spins > (1u << 26)) sync_trap(args);
   ptx::fence_acq_rel_gpu();
 }
 
-// all threads of the CTA: publish this CTA's stores, count it as arrived, wait for phase `phases_done`
-__device__ __forceinline__ void grid_sync_all(const Args& args, unsigned phases_done) {
+// all threads of the CTA: publish this CTA's stores, count it as arrived, wait for grid-wide arrival number n
+__device__ __forceinline__ void grid_sync_all(const Args& args, unsigned n) {
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     ptx::red_relaxed_gpu_add(args.counter, 1u);
-    grid_wait(args, phases_done);
+    grid_wait(args, n);
   }
   __syncthreads();
 }
@@ -241,7 +248,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     __threadfence();
     ptx::fence_proxy_async_all();
     asm volatile("bar.sync 2, 224;" ::: "memory");
-    if (threadIdx.x == 32) ptx::red_relaxed_gpu_add(args.counter, 1u);
+    if (threadIdx.x == 32) ptx::publish_flag_gpu(args.flags + tile * 16 + slice, args.base + 1u);
     if (ktrace) ktrace[1] = clock64();
   }
 
@@ -270,23 +277,39 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         }
     }
   } else if (warp == 3) {
-    // ============ activation producer: one halo tile per channel chunk, after the previous phase's barrier ====
+    // ============ activation producer: one halo tile per 64-channel chunk, as soon as the CTAs that own those
+    // channels of this board tile have published the previous layer (no grid-wide barrier: a tile's CTAs only ever
+    // read what CTAs of the same tile wrote, and a chunk can start while other slices are still in their epilogue) ====
+    const unsigned* tile_flags = args.flags + tile * 16;
     for (int l = 0; l < args.n_layers; ++l) {
       const int k = l == 0 ? args.stem_k : args.blk_k;
       const int kch = l == 0 ? args.stem_kchunks : args.filters / 64;
       const int hw = 8 + k - 1, pad = (k - 1) / 2;
       const int plane_bytes = hw * args.nb * hw * 128;
       const CUtensorMap* tm = l == 0 ? &tm_in : ((l & 1) ? &tm_xb : &tm_y);
-      if (lane == 0) grid_wait(args, static_cast<unsigned>(l) + 1);  // pack + layers 0..l-1 complete everywhere
-      __syncwarp();
-      if (ptx::elect_one()) {
+      const unsigned target = args.base + 1u + static_cast<unsigned>(l);   // pack + layers 0..l-1
+      if (lane == 0) {
+        // one thread reads all of the tile's flags (independent loads: one L2 round trip per poll), then one acquire fence
+        uint32_t spins = 0;
+        for (;;) {
+          // 16 flag words per tile (n_slices <= 16 of them in use), fetched as four independent 16-byte loads
+          uint4 v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = q * 4 < args.n_slices ? ptx::ld_relaxed_gpu_v4(tile_flags + q * 4) : make_uint4(target, target, target, target);
+          int behind = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            behind |= static_cast<int>(v[q].x - target);
+            if (q * 4 + 1 < args.n_slices) behind |= static_cast<int>(v[q].y - target);
+            if (q * 4 + 2 < args.n_slices) behind |= static_cast<int>(v[q].z - target);
+            if (q * 4 + 3 < args.n_slices) behind |= static_cast<int>(v[q].w - target);
+          }
+          if (behind >= 0) break;
+          if (++spins > (1u << 24)) sync_trap(args);
+        }
+        ptx::fence_acq_rel_gpu();
         ptx::fence_proxy_async_all();  // other CTAs' generic-proxy stores -> our async-proxy (TMA) reads
         if (args.trace && blockIdx.x == 0) args.trace[l * 8 + 0] = clock64();
-        if (args.trace && l < 16) {
-          long long gt;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-          args.trace[1024 + (l * 256 + blockIdx.x) * 2 + 1] = gt;
-        }
         for (int kc = 0; kc < kch; ++kc) {
           ptx::mbar_expect_tx(&a_full[kc], plane_bytes);
           ptx::tma_load_4d(smem_a + kc * plane_bytes, tm, &a_full[kc], kc * 64, -pad, n0, -pad);
@@ -439,7 +462,10 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         args.trace[1024 + (l * 256 + blockIdx.x) * 2] = gt;
       }
-      if (threadIdx.x == 128) ptx::red_relaxed_gpu_add(args.counter, 1u);
+      if (threadIdx.x == 128) {
+        ptx::publish_flag_gpu(args.flags + tile * 16 + slice, args.base + 2u + static_cast<unsigned>(l));
+        if (l == args.n_layers - 1) ptx::red_relaxed_gpu_add(args.counter, 1u);   // the heads read every tile
+      }
     }
   }
   ptx::tcgen05_fence_before();
@@ -456,10 +482,11 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   const int F = args.filters;
   for (int i = threadIdx.x; i < hf_total * F; i += THREADS) scratch[i] = args.head_w[i];
   if (ktrace) ktrace[2] = clock64();
-  if (threadIdx.x == 0) grid_wait(args, L + 1);  // every CTA has stored the last layer's output
+  if (threadIdx.x == 0) grid_wait(args, 1);  // every CTA has stored the last layer's output
   __syncthreads();
-  if (ktrace) ktrace[3] = clock64();
   // ---- H1: 1x1 convs + folded BN + ReLU + Flatten (model_chess.py:77-81,86-90), one warp per board square ----
+  for (int rep = 0; rep < args.head_reps; ++rep) {   // head_reps > 1 is a measurement aid (cold vs warm instruction cache)
+  if (ktrace) ktrace[3] = clock64();
   for (int r = blockIdx.x * 8 + warp; r < args.batch * 64; r += gridDim.x * 8) {
     const int b = r >> 6, sq = r & 63;
     const float* x = args.xf + static_cast<size_t>(r) * F;
@@ -477,11 +504,13 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       }
     }
   }
+  }
   if (ktrace) ktrace[4] = clock64();
-  grid_sync_all(args, L + 2);
-  if (ktrace) ktrace[5] = clock64();
+  grid_sync_all(args, 2);
   // ---- H2: policy logits (labels sliced over CTAs) and the value head's hidden layer (units sliced) ----
-  {
+  for (int rep = 0; rep < args.head_reps; ++rep) {
+    if (ktrace) ktrace[5] = clock64();
+    __syncthreads();
     const int kp = args.pf * 64, kv = args.vf * 64;
     // labels / hidden units per CTA, rounded up to 4 so that every row slice is 16-byte aligned for cp.async
     const int ls = (((args.n_labels + gridDim.x - 1) / gridDim.x) + 3) & ~3;
@@ -524,8 +553,10 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           if (hh < args.value_fc) ptx::cp_async_4(s_wv + i, args.vfc1_w + static_cast<size_t>(k) * args.value_fc + hh);
         }
       }
+      if (ktrace) ktrace[8] = clock64();
       ptx::cp_async_wait_all();
       __syncthreads();
+      if (ktrace) ktrace[9] = clock64();
     }
 #pragma unroll 1
     for (int i = threadIdx.x; i < args.batch * ls; i += THREADS) {
@@ -544,6 +575,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         args.policy[static_cast<size_t>(b) * args.n_labels + n] = a0 + args.pfc_b[n];
       }
     }
+    if (ktrace) ktrace[10] = clock64();
 #pragma unroll 1
     for (int i = threadIdx.x; i < args.batch * hs; i += THREADS) {
       const int b = i / hs, j = i - b * hs, hh = h0 + j;
@@ -563,7 +595,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     }
   }
   if (ktrace) ktrace[6] = clock64();
-  grid_sync_all(args, L + 3);
+  grid_sync_all(args, 3);
   if (ktrace) ktrace[7] = clock64();
   // ---- H3: softmax (optionally legal-masked) and Dense(1, tanh), one CTA per position ----
   for (int b = blockIdx.x; b < args.batch; b += gridDim.x) {

@@ -139,10 +139,21 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const unsigned* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 // relaxed add: the caller has already fenced its (and, through a CTA barrier, its CTA's) stores at gpu scope
 __device__ __forceinline__ void red_relaxed_gpu_add(unsigned* p, unsigned v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Publish a progress flag: an L2 atomic, not a store -- a plain st.relaxed may sit in the SM's write path until the next
+// fence (measured: pollers saw such flags microseconds late), an atomic is performed at L2 as soon as it is issued.
+__device__ __forceinline__ void publish_flag_gpu(unsigned* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.relaxed.gpu.global.exch.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

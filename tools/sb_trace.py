@@ -16,13 +16,14 @@ for _ in range(5): ev.eval_device(d_x.data_ptr(), b, d_p.data_ptr(), d_v.data_pt
 lib = _lib.load()
 _lib.check(ev._handle, lib.caz_debug_sb_trace(ev._handle, 1, None, 0))
 ev.eval_device(d_x.data_ptr(), b, d_p.data_ptr(), d_v.data_ptr())
-st = np.zeros(16 * 8, np.int64)
+st = np.zeros(17 * 8, np.int64)
 _lib.check(ev._handle, lib.caz_debug_sb_trace(ev._handle, 0, st.ctypes.data_as(ctypes.c_void_p), st.size))
-st = st.reshape(16, 8).astype(np.float64)
+st = st.reshape(17, 8).astype(np.float64)
 t0 = st[0, 0]
 us = (st - t0) / 1965.0
 names = ["barrier", "A0 in", "A3 in", "mma iss", "acc rdy", "fenced", "joined"]
 print("layer " + " ".join(f"{n:>9s}" for n in names) + "   (us since layer-0 start)")
 print("kernel: start, pack done, tower done, heads start, H1 done, H2 start, H2 done, H3 start:", " ".join(f"{v:8.2f}" for v in us[15]))
+print("H2: staging issued, staged, policy done:", " ".join(f"{v:8.2f}" for v in us[16, :3]))
 for l in (0, 1, 2, 3, 13, 14):
     print(f"{l:5d} " + " ".join(f"{us[l, i]:9.2f}" for i in range(7)) + f"   last A plane landed {us[l, 7]:6.2f}")
