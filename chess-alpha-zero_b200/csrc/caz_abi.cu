@@ -90,8 +90,8 @@ struct caz_handle {
   long long* sb_trace = nullptr;   // [64][8] clock stamps of CTA 0 (debug)
   bool sb_trace_on = false;
   unsigned sb_epoch = 0;
-  unsigned* sb_gcounter = nullptr;
-  unsigned sb_gepoch = 0;
+  float* sb_hpart = nullptr;    // partial head-conv sums of the small-batch kernel
+  float* sb_hstats = nullptr;   // its softmax / value statistics
   float *head_w = nullptr, *head_b = nullptr;
   float *pfc_w = nullptr, *pfc_b = nullptr, *vfc1_w = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr,
         *vfc2_b = nullptr;
@@ -461,8 +461,8 @@ int setup_small_batch(caz_handle* h) {
       h->sb_tm_w_tower[i] = h->sb_tm_w_stem[i];
     }
   }
-  CU_TRY(h, cudaMalloc(&h->sb_gcounter, sizeof(unsigned)));
-  CU_TRY(h, cudaMemset(h->sb_gcounter, 0, sizeof(unsigned)));
+  CU_TRY(h, cudaMalloc(&h->sb_hpart, (size_t)sb_cap * 16 * caz::sb::HEAD_FILTERS_MAX * 64 * sizeof(float)));
+  CU_TRY(h, cudaMalloc(&h->sb_hstats, (size_t)sb_cap * caz::sb::HSTAT_FLOATS * sizeof(float)));
   CU_TRY(h, cudaMalloc(&h->sb_counter, caz::sb::MAX_TILES * 16 * sizeof(unsigned)));
   CU_TRY(h, cudaMemset(h->sb_counter, 0, caz::sb::MAX_TILES * 16 * sizeof(unsigned)));
   CU_TRY(h, cudaMalloc(&h->sb_trace, (1024 + 16 * 256 * 2) * sizeof(long long)));
@@ -483,6 +483,7 @@ bool sb_geometry(const caz_handle* h, int batch, int* nb_out, int* slices_out) {
       for (int s = 16; s >= 4; s >>= 1) {
         const int ns = h->arch.filters / s;
         if (ns < 16 || ns > 64 || h->arch.filters % s != 0 || tiles * s > h->num_sms) continue;
+        if (!caz::sb::heads_fit(h->arch.policy_filters, h->arch.value_filters, h->arch.n_labels, h->arch.value_fc, s)) continue;
         // first pass: one board per tile (M = 64: the tensor pipe is bound by operand reads from shared memory,
         // (M + N) * 32 B per MMA, tools/ub/ub_small.cu) as long as that leaves slices of at most 32 channels
         if (pass == 0 && nb == 1 && s < 8) break;
@@ -521,7 +522,6 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   args.in_planes = a.input_planes;
   args.in_cpad = 64;
   args.fp16 = is_fp16(h) ? 1 : 0;
-  { const char* e = getenv("CAZ_SB_HEAD_REPS"); args.head_reps = e && atoi(e) > 1 ? atoi(e) : 1; }
   const int sb_stem = caz::sb::taps_per_slot(a.stem_kernel, ns) * ns * 128;
   const int sb_blk = a.res_blocks > 0 ? caz::sb::taps_per_slot(a.block_kernel, ns) * ns * 128 : 0;
   args.slot_bytes = sb_stem > sb_blk ? sb_stem : sb_blk;
@@ -540,27 +540,28 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   args.n_labels = a.n_labels;
   args.head_w = h->head_w;
   args.head_b = h->head_b;
-  args.featp = h->featp;
-  args.featv = h->featv;
+  args.hpart = h->sb_hpart;
+  args.hstats = h->sb_hstats;
   args.pfc_w = h->pfc_w;
   args.pfc_b = h->pfc_b;
   args.vfc1_w = h->vfc1_w;
   args.vfc1_b = h->vfc1_b;
   args.vfc2_w = h->vfc2_w;
   args.vfc2_b = h->vfc2_b;
-  args.vhid = h->vhid;
   args.mask = d_mask;
   args.policy = d_policy;
   args.value = d_value;
   args.flags = h->sb_counter;
-  args.counter = h->sb_gcounter;
-  args.cbase = h->sb_gepoch;
+
+  if (h->sb_epoch > 0x40000000u) {   // long before the flag epochs could wrap past a stale tile's value: start over
+    CU_TRY(h, cudaMemsetAsync(h->sb_counter, 0, caz::sb::MAX_TILES * 16 * sizeof(unsigned), h->stream));
+    h->sb_epoch = 0;
+  }
   args.base = h->sb_epoch;
   args.trace = (h->sb_trace_on && args.n_layers <= 64) ? h->sb_trace : nullptr;
   args.err_flag = h->err_flag_dev;
   const int grid = ((batch + nb - 1) / nb) * slices;
-  h->sb_epoch += (unsigned)(args.n_layers + 1);
-  h->sb_gepoch += (unsigned)caz::sb::GRID_PHASES * (unsigned)grid;
+  h->sb_epoch += (unsigned)(args.n_layers + caz::sb::FLAG_STEPS_EXTRA);
   void* params[] = {&h->sb_tm_in[nb - 1], &h->sb_tm_xb[nb - 1], &h->sb_tm_y[nb - 1], &h->sb_tm_w_stem[wi], &h->sb_tm_w_tower[wi], &args};
   cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(caz::sb::forward_sb_kernel), dim3(grid),
                                               dim3(caz::sb::THREADS), params, caz::sb::SMEM_BYTES, h->stream);
@@ -818,7 +819,8 @@ void caz_destroy(caz_handle* h) {
   if (h->w_tower) cudaFree(h->w_tower);
   if (h->bias_all) cudaFree(h->bias_all);
   if (h->sb_counter) cudaFree(h->sb_counter);
-  if (h->sb_gcounter) cudaFree(h->sb_gcounter);
+  if (h->sb_hpart) cudaFree(h->sb_hpart);
+  if (h->sb_hstats) cudaFree(h->sb_hstats);
   if (h->sb_trace) cudaFree(h->sb_trace);
   void* ptrs[] = {h->head_w, h->head_b, h->pfc_w, h->pfc_b, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, h->in_act,
                   h->act[0], h->act[1], h->act[2], h->featp, h->featv, h->vhid, h->a3p, h->a3v, h->w3p, h->w3v, h->bias3p, h->d_planes, h->d_policy, h->d_value,

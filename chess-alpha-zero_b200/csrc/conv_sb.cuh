@@ -46,7 +46,7 @@ constexpr int MAX_W_SLOTS = 16;
 constexpr int NACC = 4;   // accumulator groups in TMEM: one per K sub-step of a 64-channel chunk row
 constexpr int BAR_BYTES = 1024;
 constexpr int SMEM_BYTES = A_BYTES + W_RING_BYTES + BAR_BYTES + 1024 /*alignment*/;
-constexpr int SCRATCH_FLOATS = (A_BYTES + W_RING_BYTES) / 4;  // what the head phases may use
+constexpr int HEAD_SMEM_BYTES = A_BYTES + W_RING_BYTES;        // what the head phases may use for staged weights
 constexpr int MAX_BATCH = 64;
 
 struct Args {
@@ -60,7 +60,6 @@ struct Args {
   int blk_k;                  // tower kernel size
   int in_planes, in_cpad;
   int fp16;                   // 16-bit operands are fp16 instead of bf16
-  int head_reps;              // 1; > 1 repeats the head phases (measurement aid)
   int slot_bytes, n_slots;    // weight ring geometry
   const float* planes;        // fp32 [batch][in_planes][64] or nullptr
   const uint8_t* records;     // u8 [batch][68] or nullptr (exactly one of the two)
@@ -71,34 +70,43 @@ struct Args {
   __nv_bfloat16* y;           // bf16 conv1 output       (A operand of conv2)
   // heads (fp32)
   int pf, vf, value_fc, n_labels;
-  const float* head_w;        // [pf+vf][filters]
+  const float* head_w;        // [pf+vf][filters]  1x1 head convolutions, BN folded
   const float* head_b;        // [pf+vf]
-  float* featp;               // [batch][pf*64]
-  float* featv;               // [batch][vf*64]
+  float* hpart;               // [batch][16 channel groups][8 head filters][64 squares] partial head-conv sums
   const float* pfc_w;         // [pf*64][n_labels]
   const float* pfc_b;
   const float* vfc1_w;        // [vf*64][value_fc]
   const float* vfc1_b;
   const float* vfc2_w;        // [value_fc]
   const float* vfc2_b;
-  float* vhid;                // [batch][value_fc]
+  float* hstats;              // [batch][HSTAT_FLOATS]: per 128-label unit (max, sum of exp), per 16-unit group value partial
   const uint8_t* mask;        // nullptr or [batch][n_labels]
   float* policy;              // [batch][n_labels]
   float* value;               // [batch]
   unsigned* flags;            // [gridDim.x] progress flag of every CTA: base + number of phases it has completed
   unsigned base;              // flag value that means "nothing of this launch done yet" (monotonic across launches)
-  unsigned* counter;          // grid-wide barrier counter for the three head phases (one poller per CTA, one address)
-  unsigned cbase;             // its value when this launch started
   long long* trace;           // nullptr or [n_layers+1][8] clock64 stamps of CTA 0 (see caz_debug_sb_trace)
   int* err_flag;
 };
 
-enum : int { ERR_W = 201, ERR_A = 202, ERR_GRID = 203, ERR_MMA_A = 204, ERR_MMA_W = 205, ERR_EPI = 206 };
+enum : int { ERR_HEADW = 207, ERR_W = 201, ERR_A = 202, ERR_GRID = 203, ERR_MMA_A = 204, ERR_MMA_W = 205, ERR_EPI = 206 };
 
 // Grid phases: 0 input pack, 1..L the L conv layers, L+1 head 1x1 convs, L+2 head dense layers.
-// A CTA that has packed its share of the input publishes flag = base + 1, after layer l flag = base + 2 + l.
-constexpr int GRID_PHASES = 3;   // grid-wide arrivals per launch: tower done, head convs done, head dense layers done
+// A CTA that has packed its share of the input publishes flag = base + 1, after layer l flag = base + 2 + l, after its
+// head statistics flag = base + 2 + n_layers: FLAG_STEPS values per launch.
+constexpr int FLAG_STEPS_EXTRA = 2;
 constexpr int MAX_TILES = 64;   // flags: 16 words per board tile
+// Heads: every quantity that is summed across CTAs is split into CANONICAL pieces that do not depend on how many
+// slices the grid has -- 16-channel groups for the 1x1 head convolutions, 128-label units for the softmax statistics,
+// 16-unit groups for the value head's hidden layer -- and the pieces are combined in a fixed order, so the outputs
+// are bit-identical for every batch size / grid geometry.
+constexpr int HEAD_FILTERS_MAX = 8;    // pf + vf
+constexpr int LABEL_UNIT = 128;        // labels per softmax unit (4 warps)
+constexpr int LABEL_UNITS_MAX = 16;    // => n_labels <= 2048
+constexpr int HID_GROUP = 16;          // hidden units per value-head group
+constexpr int HID_GROUPS_MAX = 16;     // => value_fc <= 256
+constexpr int HSTAT_FLOATS = 2 * LABEL_UNITS_MAX + HID_GROUPS_MAX;   // per position
+constexpr int LABEL_CHUNK = 256;       // labels per pass over the staged policy weights (one per thread)
 
 // taps per weight-ring slot: the whole filter, one filter row, or one tap -- the largest that fits a slot
 __host__ __device__ inline int taps_per_slot(int k, int ns) {
@@ -123,27 +131,77 @@ __device__ __forceinline__ void sync_trap(const Args& args) {
   __trap();
 }
 
-// Grid-wide barrier of the head phases (3 per launch): one release-add per CTA on one L2 counter, one polling thread
-// per CTA.  (The tower layers do NOT use it: they synchronise per board tile through the progress flags.  Polling the
-// flags of every tile from every CTA was measured to swamp the L2 slices that hold them.)
-__device__ __forceinline__ void grid_wait(const Args& args, unsigned n) {
-  const unsigned target = args.cbase + n * gridDim.x;
+// ONE thread: wait until every CTA of board tile `tile` has published `target`, then acquire.  (Tile-local on purpose:
+// a tile's CTAs only ever read what CTAs of the same tile wrote.  Polling the flags of every tile from every CTA was
+// measured to swamp the L2 slices that hold them.)
+__device__ __forceinline__ void wait_tile(const Args& args, const unsigned* tile_flags, unsigned target) {
   uint32_t spins = 0;
-  // relaxed polls (an acquire per poll is a fence per poll), one acquire fence once the count is there
-  while (static_cast<int>(ptx::ld_relaxed_gpu(args.counter) - target) < 0)
-    if (++spins > (1u << 26)) sync_trap(args);
+  for (;;) {
+    // 16 flag words per tile (n_slices <= 16 of them in use), fetched as four independent 16-byte loads
+    uint4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      v[q] = q * 4 < args.n_slices ? ptx::ld_relaxed_gpu_v4(tile_flags + q * 4) : make_uint4(target, target, target, target);
+    int behind = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      behind |= static_cast<int>(v[q].x - target);
+      if (q * 4 + 1 < args.n_slices) behind |= static_cast<int>(v[q].y - target);
+      if (q * 4 + 2 < args.n_slices) behind |= static_cast<int>(v[q].z - target);
+      if (q * 4 + 3 < args.n_slices) behind |= static_cast<int>(v[q].w - target);
+    }
+    if (behind >= 0) break;
+    if (++spins > (1u << 24)) sync_trap(args);
+  }
   ptx::fence_acq_rel_gpu();
 }
 
-// all threads of the CTA: publish this CTA's stores, count it as arrived, wait for grid-wide arrival number n
-__device__ __forceinline__ void grid_sync_all(const Args& args, unsigned n) {
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    ptx::red_relaxed_gpu_add(args.counter, 1u);
-    grid_wait(args, n);
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   ptx::smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+
+// Geometry of the head phases for a grid with n_slices output-channel slices per board tile.
+struct HeadGeom {
+  int units_total, upl;      // 128-label units in all / per slice
+  int groups_total, gps;     // 16-unit hidden groups in all / per slice
+  int hsp;                   // hidden units per slice = gps * 16 (row pitch of the staged value weights)
+};
+__host__ __device__ inline HeadGeom head_geom(int n_labels, int value_fc, int n_slices) {
+  HeadGeom g;
+  g.units_total = (n_labels + LABEL_UNIT - 1) / LABEL_UNIT;
+  g.upl = (g.units_total + n_slices - 1) / n_slices;
+  g.groups_total = (value_fc + HID_GROUP - 1) / HID_GROUP;
+  g.gps = (g.groups_total + n_slices - 1) / n_slices;
+  g.hsp = g.gps * HID_GROUP;
+  return g;
+}
+// can the head phases run for this architecture with `n_slices` slices (staged weights must fit the tower's smem)
+__host__ __device__ inline bool heads_fit(int pf, int vf, int n_labels, int value_fc, int n_slices) {
+  if (pf + vf > HEAD_FILTERS_MAX || (n_labels & 3) || (value_fc & 3)) return false;
+  const HeadGeom g = head_geom(n_labels, value_fc, n_slices);
+  if (g.units_total > LABEL_UNITS_MAX || g.groups_total > HID_GROUPS_MAX) return false;
+  if ((g.upl * LABEL_UNIT + LABEL_CHUNK - 1) / LABEL_CHUNK > 2) return false;   // logits live in registers: two label chunks
+  return (pf * 64 * LABEL_CHUNK + vf * 64 * g.hsp) * 4 <= HEAD_SMEM_BYTES && (pf + vf) * 64 <= 512;
+}
+
+// Stage head weights for this CTA: policy Dense rows [kp][lab_first, +cnt) -> s_wp[k][LABEL_CHUNK]; with_value: this
+// slice's columns of the value Dense kernel -> s_wv[k][hsp].  One warp; completion on `bar` (one phase per call).
+__device__ __forceinline__ void stage_head_weights(const Args& args, float* s_wp, float* s_wv, uint64_t* bar, int lane,
+                                                   int lab_first, int cnt, bool with_value, int h0, int hcnt, int hsp) {
+  const int kp = args.pf * 64, kv = args.vf * 64;
+  if (lane == 0) {
+    ptx::mbar_expect_tx(bar, static_cast<uint32_t>((cnt > 0 ? kp * cnt : 0) + (with_value && hcnt > 0 ? kv * hcnt : 0)) * 4u);
   }
-  __syncthreads();
+  __syncwarp();
+  if (cnt > 0)
+    for (int k = lane; k < kp; k += 32)
+      bulk_g2s(s_wp + k * LABEL_CHUNK, args.pfc_w + static_cast<size_t>(k) * args.n_labels + lab_first, cnt * 4, bar);
+  if (with_value && hcnt > 0)
+    for (int k = lane; k < kv; k += 32)
+      bulk_g2s(s_wv + k * hsp, args.vfc1_w + static_cast<size_t>(k) * args.value_fc + h0, hcnt * 4, bar);
 }
 
 // The MMAs of `TPS` consecutive taps of one 64-channel chunk (one weight-ring slot), issued by ONE thread.
@@ -190,6 +248,11 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   uint64_t* w_empty = w_full + MAX_W_SLOTS;      // [MAX_W_SLOTS]
   uint64_t* acc_full = w_empty + MAX_W_SLOTS;    // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* hw_full = acc_full + 2;              // [1] staged head weights
+  uint64_t* tower_done = acc_full + 3;           // [1] the last layer's MMAs have completed (both issuers)
+  __shared__ __align__(16) float s_hw[HEAD_FILTERS_MAX * 64];   // this slice's columns of the 1x1 head convolutions
+  __shared__ __align__(16) float s_feat[2 * 512];               // head-conv outputs of this tile's boards (Flatten order)
+  __shared__ float s_red[64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / args.n_slices, slice = blockIdx.x % args.n_slices;
@@ -197,6 +260,13 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   const int tap_bytes = args.ns * 128;
   const uint32_t tmem_cols = static_cast<uint32_t>(NACC * args.ns);  // 128, 256 or 512: powers of two
   const unsigned L = static_cast<unsigned>(args.n_layers);
+  const HeadGeom hg = head_geom(args.n_labels, args.value_fc, args.n_slices);
+  const int lab0 = slice * hg.upl * LABEL_UNIT;                         // this CTA's labels: [lab0, lab0 + lab_cnt)
+  const int lab_cnt = max(0, min(hg.upl * LABEL_UNIT, args.n_labels - lab0));
+  const int hid0 = slice * hg.hsp;                                      // this CTA's hidden units: [hid0, hid0 + hid_cnt)
+  const int hid_cnt = max(0, min(hg.hsp, args.value_fc - hid0));
+  float* s_wp = reinterpret_cast<float*>(smem);                         // heads: [pf*64][LABEL_CHUNK], over the tower's tiles
+  float* s_wv = s_wp + args.pf * 64 * LABEL_CHUNK;                      //        [vf*64][hsp]
   long long* ktrace = (args.trace && blockIdx.x == 0 && threadIdx.x == 32) ? args.trace + args.n_layers * 8 : nullptr;
   if (ktrace) ktrace[0] = clock64();
 
@@ -214,6 +284,8 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       ptx::mbar_init(&w_empty[i], 1);   // the tcgen05.commit of the issuer warp that consumed the slot
     }
     ptx::mbar_init(acc_full, 2);
+    ptx::mbar_init(hw_full, 1);
+    ptx::mbar_init(tower_done, 2);
     ptx::mbar_fence_init();
     ptx::fence_proxy_async();
   }
@@ -276,6 +348,10 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           if (++slot == args.n_slots) { slot = 0; phase ^= 1; }
         }
     }
+    // The last layer's MMAs are done with the tiles and the ring: stage this CTA's head weights over them while the
+    // epilogue warps are still busy (the Dense weights do not depend on the activations).
+    ptx::mbar_wait(tower_done, 0, args.err_flag, ERR_HEADW);
+    stage_head_weights(args, s_wp, s_wv, hw_full, lane, lab0, min(lab_cnt, LABEL_CHUNK), true, hid0, hid_cnt, hg.hsp);
   } else if (warp == 3) {
     // ============ activation producer: one halo tile per 64-channel chunk, as soon as the CTAs that own those
     // channels of this board tile have published the previous layer (no grid-wide barrier: a tile's CTAs only ever
@@ -289,25 +365,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       const CUtensorMap* tm = l == 0 ? &tm_in : ((l & 1) ? &tm_xb : &tm_y);
       const unsigned target = args.base + 1u + static_cast<unsigned>(l);   // pack + layers 0..l-1
       if (lane == 0) {
-        // one thread reads all of the tile's flags (independent loads: one L2 round trip per poll), then one acquire fence
-        uint32_t spins = 0;
-        for (;;) {
-          // 16 flag words per tile (n_slices <= 16 of them in use), fetched as four independent 16-byte loads
-          uint4 v[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) v[q] = q * 4 < args.n_slices ? ptx::ld_relaxed_gpu_v4(tile_flags + q * 4) : make_uint4(target, target, target, target);
-          int behind = 0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            behind |= static_cast<int>(v[q].x - target);
-            if (q * 4 + 1 < args.n_slices) behind |= static_cast<int>(v[q].y - target);
-            if (q * 4 + 2 < args.n_slices) behind |= static_cast<int>(v[q].z - target);
-            if (q * 4 + 3 < args.n_slices) behind |= static_cast<int>(v[q].w - target);
-          }
-          if (behind >= 0) break;
-          if (++spins > (1u << 24)) sync_trap(args);
-        }
-        ptx::fence_acq_rel_gpu();
+        wait_tile(args, tile_flags, target);   // the tile's CTAs have published the previous layer
         ptx::fence_proxy_async_all();  // other CTAs' generic-proxy stores -> our async-proxy (TMA) reads
         if (args.trace && blockIdx.x == 0) args.trace[l * 8 + 0] = clock64();
         for (int kc = 0; kc < kch; ++kc) {
@@ -377,7 +435,10 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         }
       }
       if (args.trace && blockIdx.x == 0 && lane == 0 && which == 0) args.trace[l * 8 + 3] = clock64();
-      if (ptx::elect_one()) ptx::mma_commit(acc_full);
+      if (ptx::elect_one()) {
+        ptx::mma_commit(acc_full);
+        if (l == args.n_layers - 1) ptx::mma_commit(tower_done);
+      }
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -391,7 +452,14 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     const bool live = pos < args.batch && (args.nb == 2 || lane < 16);
     const size_t row = static_cast<size_t>(pos) * 64 + h * 8 + w;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const int hf_all = args.pf + args.vf;
+    for (int i = threadIdx.x - 128; i < HEAD_FILTERS_MAX * 64; i += 128) {
+      const int f6 = i >> 6, j = i & 63;
+      s_hw[i] = (f6 < hf_all && j < args.ns) ? args.head_w[f6 * args.filters + col0 + j] : 0.0f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     for (int l = 0; l < args.n_layers; ++l) {
+      const bool last = l == args.n_layers - 1;   // its output only feeds the heads: no activation stores
       const bool conv1 = l > 0 && (l & 1);     // bf16 out to y only
       const bool has_res = l > 0 && !(l & 1);  // conv2: + residual, out to xf and xb
       const bool two_issuers = (l == 0 ? args.stem_kchunks : args.filters / 64) > 1;
@@ -431,7 +499,27 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
             f[j] += s01 + s23;
           }
         }
-        if (live) {
+        if (live && last) {
+          // 1x1 head convolutions (model_chess.py:77,86): this thread's row, this 16-channel group -> one partial sum
+          // per head filter; the groups are added up, in order, by the head phase below
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+          float* hp = args.hpart + ((static_cast<size_t>(pos) * 16 + ((col0 + c0) >> 4)) * HEAD_FILTERS_MAX) * 64 + h * 8 + w;
+#pragma unroll
+          for (int f6 = 0; f6 < HEAD_FILTERS_MAX; ++f6) {
+            if (f6 < hf_all) {
+              const float4* wq = reinterpret_cast<const float4*>(s_hw + f6 * 64 + c0);
+              float acc = 0.0f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 wv = wq[q];
+                acc = fmaf(f[q * 4 + 0], wv.x, acc); acc = fmaf(f[q * 4 + 1], wv.y, acc);
+                acc = fmaf(f[q * 4 + 2], wv.z, acc); acc = fmaf(f[q * 4 + 3], wv.w, acc);
+              }
+              hp[f6 * 64] = acc;
+            }
+          }
+        } else if (live) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
           if (!conv1) {
@@ -462,10 +550,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         args.trace[1024 + (l * 256 + blockIdx.x) * 2] = gt;
       }
-      if (threadIdx.x == 128) {
-        ptx::publish_flag_gpu(args.flags + tile * 16 + slice, args.base + 2u + static_cast<unsigned>(l));
-        if (l == args.n_layers - 1) ptx::red_relaxed_gpu_add(args.counter, 1u);   // the heads read every tile
-      }
+      if (threadIdx.x == 128) ptx::publish_flag_gpu(args.flags + tile * 16 + slice, args.base + 2u + static_cast<unsigned>(l));
     }
   }
   ptx::tcgen05_fence_before();
@@ -475,192 +560,168 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     ptx::tmem_dealloc(tmem_base, tmem_cols);
   }
 
-  // ===================== heads: three SIMT phases over the whole grid =====================
-  // The tower's shared memory is free now: reuse it as fp32 scratch.
-  float* scratch = reinterpret_cast<float*>(smem);
+  // ===================== heads, per board tile (no grid-wide step) =====================
+  // H1: this tile's head-conv outputs from the 16 channel-group partials (+ folded BN shift, ReLU, Flatten order).
+  // H2: this CTA's labels of the policy Dense layer and its hidden units of the value head, from staged weights;
+  //     per-128-label softmax statistics and per-16-unit value partials are published for the tile.
+  // H3: after the tile's second rendezvous every CTA normalises its own labels; slice 0 writes the value.
+  const unsigned* tile_flags = args.flags + tile * 16;
   const int hf_total = args.pf + args.vf;
-  const int F = args.filters;
-  for (int i = threadIdx.x; i < hf_total * F; i += THREADS) scratch[i] = args.head_w[i];
+  const int kp = args.pf * 64, kv = args.vf * 64;
   if (ktrace) ktrace[2] = clock64();
-  if (threadIdx.x == 0) grid_wait(args, 1);  // every CTA has stored the last layer's output
+  if (threadIdx.x == 0) wait_tile(args, tile_flags, args.base + 1u + L);   // the tile's CTAs have stored their partials
   __syncthreads();
-  // ---- H1: 1x1 convs + folded BN + ReLU + Flatten (model_chess.py:77-81,86-90), one warp per board square ----
-  for (int rep = 0; rep < args.head_reps; ++rep) {   // head_reps > 1 is a measurement aid (cold vs warm instruction cache)
   if (ktrace) ktrace[3] = clock64();
-  for (int r = blockIdx.x * 8 + warp; r < args.batch * 64; r += gridDim.x * 8) {
-    const int b = r >> 6, sq = r & 63;
-    const float* x = args.xf + static_cast<size_t>(r) * F;
-#pragma unroll 1
-    for (int f = 0; f < hf_total; ++f) {
-      float v = 0.0f;
-#pragma unroll 1
-      for (int c = lane; c < F; c += 32) v = fmaf(x[c], scratch[f * F + c], v);
+  for (int i = threadIdx.x; i < args.nb * hf_total * 64; i += THREADS) {
+    const int sq = i & 63, f6 = (i >> 6) % hf_total, bl = i / (64 * hf_total);
+    float v = 0.0f;
+    if (n0 + bl < args.batch) {
+      const float* hp = args.hpart + ((static_cast<size_t>(n0 + bl) * 16) * HEAD_FILTERS_MAX + f6) * 64 + sq;
+      float part[16];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) {
-        v = fmaxf(v + args.head_b[f], 0.0f);
-        if (f < args.pf) args.featp[static_cast<size_t>(b) * args.pf * 64 + f * 64 + sq] = v;
-        else args.featv[static_cast<size_t>(b) * args.vf * 64 + (f - args.pf) * 64 + sq] = v;
-      }
+      for (int g = 0; g < 16; ++g) part[g] = g * 16 < args.filters ? hp[static_cast<size_t>(g) * HEAD_FILTERS_MAX * 64] : 0.0f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) v += part[g];
+      v = fmaxf(v + args.head_b[f6], 0.0f);
     }
+    // Keras channels-first Flatten: index c*64 + square (model_chess.py:80,89); policy filters first, then value
+    s_feat[bl * 512 + (f6 < args.pf ? f6 * 64 + sq : kp + (f6 - args.pf) * 64 + sq)] = v;
   }
-  }
+  __syncthreads();
   if (ktrace) ktrace[4] = clock64();
-  grid_sync_all(args, 2);
-  // ---- H2: policy logits (labels sliced over CTAs) and the value head's hidden layer (units sliced) ----
-  for (int rep = 0; rep < args.head_reps; ++rep) {
-    if (ktrace) ktrace[5] = clock64();
-    __syncthreads();
-    const int kp = args.pf * 64, kv = args.vf * 64;
-    // labels / hidden units per CTA, rounded up to 4 so that every row slice is 16-byte aligned for cp.async
-    const int ls = (((args.n_labels + gridDim.x - 1) / gridDim.x) + 3) & ~3;
-    const int lab0 = blockIdx.x * ls;
-    const int hs = (((args.value_fc + gridDim.x - 1) / gridDim.x) + 3) & ~3;
-    const int h0 = blockIdx.x * hs;
-    float* s_fp = scratch;                        // [batch][kp]
-    float* s_fv = s_fp + args.batch * kp;         // [batch][kv]
-    float* s_wv = s_fv + args.batch * kv;         // [kv][hs]  this CTA's columns of the value Dense kernel
-    float* s_wp = s_wv + kv * hs;                 // [kp][ls]  this CTA's columns of the policy Dense kernel
-    const bool staged = args.batch * (kp + kv) + kv * hs + kp * ls <= SCRATCH_FLOATS;   // else straight from L2
-    const bool vec = (args.n_labels & 3) == 0 && (args.value_fc & 3) == 0;
-    if (staged) {
-      // asynchronous copies, all in flight at once: one L2 latency, no register staging
-#pragma unroll 1
-      for (int i = threadIdx.x; i < args.batch * kp; i += THREADS) ptx::cp_async_4(s_fp + i, args.featp + i);
-#pragma unroll 1
-      for (int i = threadIdx.x; i < args.batch * kv; i += THREADS) ptx::cp_async_4(s_fv + i, args.featv + i);
-      if (vec) {
-        const int lq = ls >> 2, hq = hs >> 2;
-#pragma unroll 1
-        for (int i = threadIdx.x; i < kp * lq; i += THREADS) {
-          const int k = i / lq, n = lab0 + (i - k * lq) * 4;
-          if (n < args.n_labels) ptx::cp_async_16(s_wp + k * ls + (n - lab0), args.pfc_w + static_cast<size_t>(k) * args.n_labels + n);
-        }
-#pragma unroll 1
-        for (int i = threadIdx.x; i < kv * hq; i += THREADS) {
-          const int k = i / hq, hh = h0 + (i - k * hq) * 4;
-          if (hh < args.value_fc) ptx::cp_async_16(s_wv + k * hs + (hh - h0), args.vfc1_w + static_cast<size_t>(k) * args.value_fc + hh);
-        }
-      } else {
-#pragma unroll 1
-        for (int i = threadIdx.x; i < kp * ls; i += THREADS) {
-          const int k = i / ls, n = lab0 + i % ls;
-          if (n < args.n_labels) ptx::cp_async_4(s_wp + i, args.pfc_w + static_cast<size_t>(k) * args.n_labels + n);
-        }
-#pragma unroll 1
-        for (int i = threadIdx.x; i < kv * hs; i += THREADS) {
-          const int k = i / hs, hh = h0 + i % hs;
-          if (hh < args.value_fc) ptx::cp_async_4(s_wv + i, args.vfc1_w + static_cast<size_t>(k) * args.value_fc + hh);
-        }
+
+  // ---- H2 ----
+  const int n_lchunks = (hg.upl * LABEL_UNIT + LABEL_CHUNK - 1) / LABEL_CHUNK;
+  float lg[2][2];   // [label chunk][board of the tile]: this thread's logits (n_lchunks <= 2 is checked on the host)
+  const int unit_in_chunk = threadIdx.x >> 7;   // threads 0-127 / 128-255 = the chunk's first / second 128-label unit
+  for (int c = 0; c < n_lchunks; ++c) {
+    if (c > 0) {
+      __syncthreads();   // everyone is done with the previous chunk's weights
+      if (warp == 0)
+        stage_head_weights(args, s_wp, s_wv, hw_full, lane, lab0 + c * LABEL_CHUNK, min(lab_cnt - c * LABEL_CHUNK, LABEL_CHUNK),
+                           false, 0, 0, hg.hsp);
+    }
+    ptx::mbar_wait(hw_full, c & 1, args.err_flag, ERR_HEADW);
+    if (ktrace && c == 0) ktrace[5] = clock64();
+    const int n = lab0 + c * LABEL_CHUNK + threadIdx.x;
+    const bool valid = c * LABEL_CHUNK + threadIdx.x < lab_cnt;
+    float a0 = 0.0f, a1 = 0.0f;
+    if (valid) {
+      const float* wcol = s_wp + threadIdx.x;
+#pragma unroll 8
+      for (int k = 0; k < kp; ++k) {
+        const float wv = wcol[k * LABEL_CHUNK];
+        a0 = fmaf(s_feat[k], wv, a0);
+        a1 = fmaf(s_feat[512 + k], wv, a1);
       }
-      if (ktrace) ktrace[8] = clock64();
-      ptx::cp_async_wait_all();
+      const float bn = args.pfc_b[n];
+      a0 += bn; a1 += bn;
+    }
+#pragma unroll
+    for (int bl = 0; bl < 2; ++bl) {
+      const int b = n0 + bl;
+      const bool on = valid && bl < args.nb && b < args.batch &&
+                      (!args.mask || args.mask[static_cast<size_t>(b) * args.n_labels + n] != 0);
+      const float x = on ? (bl ? a1 : a0) : -INFINITY;
+      lg[c][bl] = x;
+      // statistics of this 128-label unit: max, then the sum of exp(x - max), reduced in a fixed order
+      float mx = x;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) s_red[warp] = mx;
       __syncthreads();
-      if (ktrace) ktrace[9] = clock64();
-    }
-#pragma unroll 1
-    for (int i = threadIdx.x; i < args.batch * ls; i += THREADS) {
-      const int b = i / ls, j = i - b * ls, n = lab0 + j;   // consecutive threads -> consecutive labels
-      if (n < args.n_labels) {
-        float a0 = 0.f;
-        if (staged) {
-          const float* fp = s_fp + b * kp;
-#pragma unroll 4
-          for (int k = 0; k < kp; ++k) a0 = fmaf(fp[k], s_wp[k * ls + j], a0);
-        } else {
-          const float* fp = args.featp + static_cast<size_t>(b) * kp;
-#pragma unroll 8
-          for (int k = 0; k < kp; ++k) a0 = fmaf(fp[k], __ldg(args.pfc_w + static_cast<size_t>(k) * args.n_labels + n), a0);
-        }
-        args.policy[static_cast<size_t>(b) * args.n_labels + n] = a0 + args.pfc_b[n];
-      }
-    }
-    if (ktrace) ktrace[10] = clock64();
-#pragma unroll 1
-    for (int i = threadIdx.x; i < args.batch * hs; i += THREADS) {
-      const int b = i / hs, j = i - b * hs, hh = h0 + j;
-      if (hh < args.value_fc) {
-        float a0 = 0.f;
-        if (staged) {
-          const float* fv = s_fv + b * kv;
-#pragma unroll 4
-          for (int k = 0; k < kv; ++k) a0 = fmaf(fv[k], s_wv[k * hs + j], a0);
-        } else {
-          const float* fv = args.featv + static_cast<size_t>(b) * kv;
-#pragma unroll 8
-          for (int k = 0; k < kv; ++k) a0 = fmaf(fv[k], __ldg(args.vfc1_w + static_cast<size_t>(k) * args.value_fc + hh), a0);
-        }
-        args.vhid[static_cast<size_t>(b) * args.value_fc + hh] = fmaxf(a0 + args.vfc1_b[hh], 0.0f);
+      mx = fmaxf(fmaxf(s_red[unit_in_chunk * 4], s_red[unit_in_chunk * 4 + 1]),
+                 fmaxf(s_red[unit_in_chunk * 4 + 2], s_red[unit_in_chunk * 4 + 3]));
+      float e = x == -INFINITY ? 0.0f : expf(x - mx);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+      __syncthreads();
+      if (lane == 0) s_red[8 + warp] = e;
+      __syncthreads();
+      const int unit = slice * hg.upl + c * (LABEL_CHUNK / LABEL_UNIT) + unit_in_chunk;
+      if ((threadIdx.x & 127) == 0 && bl < args.nb && b < args.batch && unit < LABEL_UNITS_MAX &&
+          c * (LABEL_CHUNK / LABEL_UNIT) + unit_in_chunk < hg.upl) {
+        const float se = (s_red[8 + unit_in_chunk * 4] + s_red[8 + unit_in_chunk * 4 + 1]) +
+                         (s_red[8 + unit_in_chunk * 4 + 2] + s_red[8 + unit_in_chunk * 4 + 3]);
+        float* st = args.hstats + static_cast<size_t>(b) * HSTAT_FLOATS + unit * 2;
+        st[0] = mx;
+        st[1] = se;
       }
     }
   }
   if (ktrace) ktrace[6] = clock64();
-  grid_sync_all(args, 3);
+  // value head hidden layer (model_chess.py:91): unit u = hid0 + (t & (hsp-1))... every thread takes one (unit, k-eighth):
+  // eight partial dot products per unit over k = kq, kq+8, ..., added in order
+  {
+    float* s_part = s_wp;   // the policy weights are consumed: [2 boards][8][hsp] partials
+    __syncthreads();
+    const int per = hg.hsp * 8;
+    for (int i = threadIdx.x; i < per; i += THREADS) {
+      const int u = i % hg.hsp, kq = i / hg.hsp;
+      float a0 = 0.0f, a1 = 0.0f;
+      if (u < hid_cnt)
+        for (int k = kq; k < kv; k += 8) {
+          const float wv = s_wv[k * hg.hsp + u];
+          a0 = fmaf(s_feat[kp + k], wv, a0);
+          a1 = fmaf(s_feat[512 + kp + k], wv, a1);
+        }
+      s_part[i] = a0;
+      s_part[per + i] = a1;
+    }
+    __syncthreads();
+    // one thread per (board, 16-unit group): hidden = relu(sum of the 8 partials + bias), times the output weights
+    for (int i = threadIdx.x; i < 2 * hg.gps; i += THREADS) {
+      const int bl = i / hg.gps, gl = i % hg.gps, b = n0 + bl, grp = slice * hg.gps + gl;
+      if (bl < args.nb && b < args.batch && grp < hg.groups_total) {
+        float pv = 0.0f;
+        for (int uu = 0; uu < HID_GROUP; ++uu) {
+          const int u = gl * HID_GROUP + uu, hu = hid0 + u;
+          if (hu < args.value_fc) {
+            float hsum = 0.0f;
+#pragma unroll
+            for (int kq = 0; kq < 8; ++kq) hsum += s_part[bl * per + kq * hg.hsp + u];
+            pv = fmaf(fmaxf(hsum + args.vfc1_b[hu], 0.0f), args.vfc2_w[hu], pv);
+          }
+        }
+        args.hstats[static_cast<size_t>(b) * HSTAT_FLOATS + 2 * LABEL_UNITS_MAX + grp] = pv;
+      }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ptx::publish_flag_gpu(args.flags + tile * 16 + slice, args.base + 2u + L);
+    wait_tile(args, tile_flags, args.base + 2u + L);
+  }
+  __syncthreads();
   if (ktrace) ktrace[7] = clock64();
-  // ---- H3: softmax (optionally legal-masked) and Dense(1, tanh), one CTA per position ----
-  for (int b = blockIdx.x; b < args.batch; b += gridDim.x) {
-    __shared__ float s_red[8];
-    __shared__ float s_bc;
-    float* prow = args.policy + static_cast<size_t>(b) * args.n_labels;
-    const uint8_t* mrow = args.mask ? args.mask + static_cast<size_t>(b) * args.n_labels : nullptr;
-    float x[PNJ];
+
+  // ---- H3: softmax over all of the board's labels (model_chess.py:83) from the units' statistics; tanh value ----
+#pragma unroll
+  for (int bl = 0; bl < 2; ++bl) {
+    const int b = n0 + bl;
+    if (bl >= args.nb || b >= args.batch) continue;
+    const float* st = args.hstats + static_cast<size_t>(b) * HSTAT_FLOATS;
     float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < PNJ; ++j) {
-      const int n = threadIdx.x + j * THREADS;
-      const bool on = n < args.n_labels && (!mrow || mrow[n] != 0);
-      x[j] = on ? prow[n] : -INFINITY;
-      mx = fmaxf(mx, x[j]);
+    for (int u = 0; u < hg.units_total; ++u) mx = fmaxf(mx, ptx::ld_cg_f32(st + 2 * u));
+    float z = 0.0f;
+    for (int u = 0; u < hg.units_total; ++u) {
+      const float mu = ptx::ld_cg_f32(st + 2 * u), su = ptx::ld_cg_f32(st + 2 * u + 1);
+      if (mu != -INFINITY) z += su * expf(mu - mx);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) s_red[warp] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float v = s_red[0];
-      for (int wi = 1; wi < 8; ++wi) v = fmaxf(v, s_red[wi]);
-      s_bc = v;
+    const float inv = z > 0.0f ? 1.0f / z : 0.0f;
+    for (int c = 0; c < n_lchunks; ++c) {
+      const int n = lab0 + c * LABEL_CHUNK + threadIdx.x;
+      if (c * LABEL_CHUNK + threadIdx.x < lab_cnt) {
+        const float x = c ? lg[1][bl] : lg[0][bl];
+        args.policy[static_cast<size_t>(b) * args.n_labels + n] = x == -INFINITY ? 0.0f : expf(x - mx) * inv;
+      }
     }
-    __syncthreads();
-    mx = s_bc;
-    float sum = 0.0f;
-#pragma unroll
-    for (int j = 0; j < PNJ; ++j) {
-      x[j] = x[j] == -INFINITY ? 0.0f : expf(x[j] - mx);
-      sum += x[j];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    __syncthreads();
-    if (lane == 0) s_red[warp] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float v = 0.0f;
-      for (int wi = 0; wi < 8; ++wi) v += s_red[wi];
-      s_bc = v;
-    }
-    __syncthreads();
-    const float inv = s_bc > 0.0f ? 1.0f / s_bc : 0.0f;
-#pragma unroll
-    for (int j = 0; j < PNJ; ++j) {
-      const int n = threadIdx.x + j * THREADS;
-      if (n < args.n_labels) prow[n] = x[j] * inv;
-    }
-    // value: tanh(vhid . w2 + b2)
-    float part = 0.0f;
-    for (int hh = threadIdx.x; hh < args.value_fc; hh += THREADS)
-      part = fmaf(args.vhid[static_cast<size_t>(b) * args.value_fc + hh], args.vfc2_w[hh], part);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    __syncthreads();
-    if (lane == 0) s_red[warp] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (slice == 0 && threadIdx.x == 0) {
       float v = args.vfc2_b[0];
-      for (int wi = 0; wi < 8; ++wi) v += s_red[wi];
+      for (int g = 0; g < hg.groups_total; ++g) v += ptx::ld_cg_f32(st + 2 * LABEL_UNITS_MAX + g);
       args.value[b] = tanhf(v);
     }
-    __syncthreads();
   }
 }
 

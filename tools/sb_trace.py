@@ -23,7 +23,6 @@ t0 = st[0, 0]
 us = (st - t0) / 1965.0
 names = ["barrier", "A0 in", "A3 in", "mma iss", "acc rdy", "fenced", "joined"]
 print("layer " + " ".join(f"{n:>9s}" for n in names) + "   (us since layer-0 start)")
-print("kernel: start, pack done, tower done, heads start, H1 done, H2 start, H2 done, H3 start:", " ".join(f"{v:8.2f}" for v in us[15]))
-print("H2: staging issued, staged, policy done:", " ".join(f"{v:8.2f}" for v in us[16, :3]))
+print("kernel: start, pack done, tower done, tile ready, feat done, head weights staged, policy+stats done, 2nd rendezvous:", " ".join(f"{v:8.2f}" for v in us[15]))
 for l in (0, 1, 2, 3, 13, 14):
     print(f"{l:5d} " + " ".join(f"{us[l, i]:9.2f}" for i in range(7)) + f"   last A plane landed {us[l, 7]:6.2f}")
