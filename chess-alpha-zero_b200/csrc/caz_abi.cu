@@ -522,6 +522,7 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   args.in_planes = a.input_planes;
   args.in_cpad = 64;
   args.fp16 = is_fp16(h) ? 1 : 0;
+  { const char* e = getenv("CAZ_SB_DBG"); args.dbg = e ? atoi(e) : 0; }
   const int sb_stem = caz::sb::taps_per_slot(a.stem_kernel, ns) * ns * 128;
   const int sb_blk = a.res_blocks > 0 ? caz::sb::taps_per_slot(a.block_kernel, ns) * ns * 128 : 0;
   args.slot_bytes = sb_stem > sb_blk ? sb_stem : sb_blk;
@@ -563,7 +564,10 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   const int grid = ((batch + nb - 1) / nb) * slices;
   h->sb_epoch += (unsigned)(args.n_layers + caz::sb::FLAG_STEPS_EXTRA);
   void* params[] = {&h->sb_tm_in[nb - 1], &h->sb_tm_xb[nb - 1], &h->sb_tm_y[nb - 1], &h->sb_tm_w_stem[wi], &h->sb_tm_w_tower[wi], &args};
-  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(caz::sb::forward_sb_kernel), dim3(grid),
+  static const bool plain = getenv("CAZ_SB_PLAIN_LAUNCH") && atoi(getenv("CAZ_SB_PLAIN_LAUNCH")) != 0;
+  cudaError_t e = plain ? cudaLaunchKernel(reinterpret_cast<const void*>(caz::sb::forward_sb_kernel), dim3(grid),
+                                           dim3(caz::sb::THREADS), params, caz::sb::SMEM_BYTES, h->stream)
+                        : cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(caz::sb::forward_sb_kernel), dim3(grid),
                                               dim3(caz::sb::THREADS), params, caz::sb::SMEM_BYTES, h->stream);
   if (e != cudaSuccess) return fail(h, CAZ_ERR_CUDA, fmt("cooperative launch of forward_sb_kernel failed: %s", cudaGetErrorString(e)));
   h->launches++;

@@ -60,6 +60,7 @@ struct Args {
   int blk_k;                  // tower kernel size
   int in_planes, in_cpad;
   int fp16;                   // 16-bit operands are fp16 instead of bf16
+  int dbg;                    // experiment switches (CAZ_SB_DBG), 0 in production
   int slot_bytes, n_slots;    // weight ring geometry
   const float* planes;        // fp32 [batch][in_planes][64] or nullptr
   const uint8_t* records;     // u8 [batch][68] or nullptr (exactly one of the two)
@@ -153,7 +154,7 @@ __device__ __forceinline__ void wait_tile(const Args& args, const unsigned* tile
     if (behind >= 0) break;
     if (++spins > (1u << 24)) sync_trap(args);
   }
-  ptx::fence_acq_rel_gpu();
+  if (!(args.dbg & 1)) ptx::fence_acq_rel_gpu();
 }
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -268,7 +269,12 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   float* s_wp = reinterpret_cast<float*>(smem);                         // heads: [pf*64][LABEL_CHUNK], over the tower's tiles
   float* s_wv = s_wp + args.pf * 64 * LABEL_CHUNK;                      //        [vf*64][hsp]
   long long* ktrace = (args.trace && blockIdx.x == 0 && threadIdx.x == 32) ? args.trace + args.n_layers * 8 : nullptr;
-  if (ktrace) ktrace[0] = clock64();
+  if (ktrace) {
+    ktrace[0] = clock64();
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    ktrace[8] = gt;
+  }
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_in);
@@ -722,6 +728,12 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       for (int g = 0; g < hg.groups_total; ++g) v += ptx::ld_cg_f32(st + 2 * LABEL_UNITS_MAX + g);
       args.value[b] = tanhf(v);
     }
+  }
+  if (ktrace) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    ktrace[9] = gt;
+    ktrace[10] = clock64();
   }
 }
 

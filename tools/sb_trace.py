@@ -24,5 +24,7 @@ us = (st - t0) / 1965.0
 names = ["barrier", "A0 in", "A3 in", "mma iss", "acc rdy", "fenced", "joined"]
 print("layer " + " ".join(f"{n:>9s}" for n in names) + "   (us since layer-0 start)")
 print("kernel: start, pack done, tower done, tile ready, feat done, head weights staged, policy+stats done, 2nd rendezvous:", " ".join(f"{v:8.2f}" for v in us[15]))
+cyc = st[16, 2] - st[15, 0]; ns = st[16, 1] - st[16, 0]
+print(f"CTA 0 lifetime: {cyc:.0f} cycles in {ns / 1e3:.2f} us (globaltimer) -> SM clock {cyc / ns * 1e3:.0f} MHz; the table assumes 1965 MHz")
 for l in (0, 1, 2, 3, 13, 14):
     print(f"{l:5d} " + " ".join(f"{us[l, i]:9.2f}" for i in range(7)) + f"   last A plane landed {us[l, 7]:6.2f}")
