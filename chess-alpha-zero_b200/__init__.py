@@ -6,12 +6,13 @@ plus PUCT select.  All compute is in ``csrc/`` (hand-written CUDA, tcgen05 + TMA
 ``include/caz_b200.h``; this package is the Python host mirror of the reference's interface.
 There is no CPU fallback: importing works anywhere, computing needs the built library and a B200.
 """
-from . import _lib, encoder, keras_graph, labels
+from . import _lib, encoder, keras_graph, labels, mcts
 from ._lib import CazError, library_path
 from .api import ChessModelAPI
 from .config import Config
 from .evaluator import Evaluator
+from .mcts import SelfPlaySearch
 from .model import ChessModel
 
 __all__ = ["ChessModel", "ChessModelAPI", "Evaluator", "Config", "CazError", "library_path", "encoder",
-           "keras_graph", "labels"]
+           "keras_graph", "labels", "mcts", "SelfPlaySearch"]

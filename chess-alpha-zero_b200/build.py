@@ -7,6 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_native")
 LIB_PATH = os.path.join(OUT_DIR, "libcaz_b200.so")
+MCTS_LIB_PATH = os.path.join(OUT_DIR, "libcaz_mcts.so")   # host-only search driver (include/caz_mcts.h), g++
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -43,5 +44,35 @@ def build_native(force=False, verbose=False):
     return LIB_PATH
 
 
+def _mcts_sources():
+    chess = os.path.join(CSRC, "chess")
+    return [os.path.join(CSRC, "caz_mcts.cpp"), os.path.join(INCLUDE, "caz_mcts.h")] + \
+        sorted(os.path.join(chess, f) for f in os.listdir(chess))
+
+
+def mcts_is_stale():
+    if not os.path.exists(MCTS_LIB_PATH):
+        return True
+    built = os.path.getmtime(MCTS_LIB_PATH)
+    return any(os.path.getmtime(s) > built for s in _mcts_sources())
+
+
+def build_mcts(force=False):
+    """Compile the host-side batched search (no CUDA in it). Returns the library path."""
+    if not force and not mcts_is_stale():
+        return MCTS_LIB_PATH
+    gxx = shutil.which("g++")
+    if not gxx:
+        raise RuntimeError("g++ not found: cannot build libcaz_mcts.so")
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", INCLUDE, "-I", CSRC, "-o", MCTS_LIB_PATH,
+           os.path.join(CSRC, "caz_mcts.cpp")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return MCTS_LIB_PATH
+
+
 if __name__ == "__main__":
-    print(build_native(force=True, verbose=True))
+    print(build_mcts(force=True))
+    print(build_native(force=True, verbose="-v" in __import__("sys").argv))

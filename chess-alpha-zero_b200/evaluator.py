@@ -114,6 +114,16 @@ class Evaluator:
             _lib.check(self._handle, rc)
         return [policy, value]
 
+    def predict_records_into(self, records, policy, value):
+        """predict_records with caller-owned (ideally pinned, _lib.PinnedArray) outputs: policy (B, n_labels), value (B,)."""
+        r = _lib.as_array(records, np.uint8)
+        b = r.shape[0]
+        if r.ndim != 2 or r.shape[1] != _lib.RECORD_BYTES or policy.shape[0] < b or value.shape[0] < b:
+            raise ValueError("records must be uint8 (B, 68) and the outputs must hold B rows")
+        with self._lock:
+            rc = self._lib.caz_eval_records(self._handle, _lib.ptr(r), b, _lib.ptr(policy), _lib.ptr(value), None, 0)
+            _lib.check(self._handle, rc)
+
     def eval_device(self, d_planes_ptr, batch, d_policy_ptr, d_value_ptr, d_mask_ptr=None):
         """Raw device pointers (ints); enqueues on the handle's stream, no synchronisation."""
         flags = _lib.EVAL_MASKED_SOFTMAX if d_mask_ptr else 0

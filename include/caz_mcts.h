@@ -1,0 +1,87 @@
+/*
+ * caz_mcts.h -- C ABI of the host-side batched self-play search that feeds the B200 evaluator.
+ *
+ * Replaces, for many concurrent games at once, the reference's ChessPlayer.action / search_moves / search_my_move /
+ * select_action_q_and_u (src/chess_zero/agent/player_chess.py:119-333), the game loop of self_play_buffer
+ * (src/chess_zero/worker/self_play.py:113-154), ChessEnv.step/_game_over/_resign/adjudicate
+ * (src/chess_zero/env/chess_env.py:79-129) and the python-chess calls those make (Board(), push, legal_moves, fen(),
+ * result(claim_draw=True); python-chess==0.25.1, requirements.txt:1).
+ *
+ * Host only (libcaz_mcts.so, no CUDA): the leaves come out as the 68-byte board records of caz_encode
+ * (include/caz_b200.h), so one round of the search for ALL games is
+ *     caz_mcts_collect(m, records, cap, &n);  caz_eval_records(h, records, n, policy, value, NULL, 0);
+ *     caz_mcts_apply(m, policy, value, n);
+ * Plain C types, int status codes (0 = ok), caller-owned buffers.
+ */
+#ifndef CAZ_MCTS_H
+#define CAZ_MCTS_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct caz_mcts caz_mcts;
+
+/* PlayConfig of the reference (configs/normal.py:28-43) */
+typedef struct caz_mcts_config {
+  int32_t simulation_num_per_move; /* 800  */
+  int32_t search_threads;          /* 16: descents of one game in flight per round (virtual loss between them) */
+  double c_puct;                   /* 1.5  */
+  double noise_eps;                /* 0.25 */
+  double dirichlet_alpha;          /* 0.3  */
+  double tau_decay_rate;           /* 0.99 */
+  int32_t virtual_loss;            /* 3    */
+  int32_t resign_enabled;          /* 1    */
+  double resign_threshold;         /* -0.8 */
+  int32_t min_resign_turn;         /* 5    */
+  int32_t max_game_length;         /* 1000 */
+  int32_t n_labels;                /* 1968 */
+  int32_t continuous;              /* 1: start a new game when one ends (SelfPlayWorker), 0: games stay finished */
+} caz_mcts_config;
+
+typedef struct caz_mcts_stats {
+  int64_t descents;         /* completed simulations (search_my_move calls from the root) */
+  int64_t leaves_evaluated; /* positions sent to the network */
+  int64_t terminal_hits;    /* descents that ended in a finished game (no evaluation) */
+  int64_t withdrawn;        /* descents withdrawn because they ran into a leaf still being evaluated */
+  int64_t moves_played, games_finished, white_wins, black_wins, draws, resignations, adjudications;
+  int64_t tree_nodes_last;  /* nodes in the most recently completed move's tree */
+} caz_mcts_stats;
+
+/* move_label: int32 [64*64*5], (from*64+to)*5 + promotion (0 none, 1 n, 2 b, 3 r, 4 q) -> index into Config.labels
+ * (config.py:76-123) or -1; unflipped_index: int32 [n_labels] (config.py:185).  Squares: a1 = 0 ... h8 = 63. */
+int caz_mcts_create(const caz_mcts_config* cfg, int32_t n_games, uint64_t seed, const int32_t* move_label,
+                    const int32_t* unflipped_index, int32_t n_threads, caz_mcts** out);
+void caz_mcts_destroy(caz_mcts* m);
+
+/* Walks the descents of every game (at most search_threads per game); records: uint8 [capacity][68] out,
+ * capacity >= n_games * search_threads.  *n_leaves = 0 only when every game is finished (continuous = 0). */
+int caz_mcts_collect(caz_mcts* m, uint8_t* records, int32_t capacity, int32_t* n_leaves);
+/* policy: float32 [n][n_labels] and value: float32 [n] for the leaves of the last collect, in the same order. */
+int caz_mcts_apply(caz_mcts* m, const float* policy, const float* value, int32_t n);
+
+int caz_mcts_get_stats(const caz_mcts* m, caz_mcts_stats* out);
+/* ChessEnv.update(fen): restart game `game` from a position */
+int caz_mcts_set_position(caz_mcts* m, int32_t game, const char* fen);
+/* env.observation of a game (board.fen()); returns the length, or -1 if buf is too small */
+int caz_mcts_game_fen(const caz_mcts* m, int32_t game, char* buf, int32_t cap);
+/* 0 running, 1 white won, 2 black won, 3 draw (only meaningful with continuous = 0) */
+int caz_mcts_game_result(const caz_mcts* m, int32_t game);
+/* Root statistics of a game's current search: for each legal move (python-chess order) label, n, q, p. Returns the
+ * number of edges written (<= cap), -1 if the root has not been expanded yet. */
+int caz_mcts_root_edges(const caz_mcts* m, int32_t game, int32_t* label, int32_t* n, double* q, double* p, int32_t cap);
+
+/* ---- the chess rules underneath (tests pin them with published perft counts) ---- */
+uint64_t caz_chess_perft(const char* fen, int32_t depth);
+/* legal moves in python-chess generation order, space separated UCI; returns the move count, -1 if buf too small */
+int caz_chess_legal_moves(const char* fen, char* buf, int32_t cap);
+/* Board(fen); push_uci each of `moves` (space separated); returns result(claim_draw=True): 0 "*", 1 "1-0", 2 "0-1",
+ * 3 "1/2-1/2", -1 on an illegal move; fen_out (may be NULL) receives board.fen() afterwards */
+int caz_chess_play(const char* fen, const char* moves, char* fen_out, int32_t cap);
+/* the 68-byte record of caz_encode for a FEN, as this library derives it */
+int caz_chess_record(const char* fen, uint8_t* record68);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAZ_MCTS_H */
