@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -86,7 +87,9 @@ struct caz_handle {
   CUtensorMap sb_tm_in[2], sb_tm_xb[2], sb_tm_y[2];  // halo views for 1 and 2 boards per CTA tile
   CUtensorMap sb_tm_w_stem[3], sb_tm_w_tower[3];      // weight maps for N_s = 16, 32, 64
   int sb_force_nb = 0;
-  unsigned* sb_counter = nullptr;
+  unsigned* sb_counter = nullptr;   // progress flags of the small-batch kernel: 32 candidate grains of 4 KB
+  uint16_t sb_flag_line[2][64];   // [copy][tile] -> candidate line of that tile's flags (copy 0 / 1: the two latency classes)
+  bool sb_two_dies = false;
   long long* sb_trace = nullptr;   // [64][8] clock stamps of CTA 0 (debug)
   bool sb_trace_on = false;
   unsigned sb_epoch = 0;
@@ -429,6 +432,60 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
 }
 
 // ---- small-batch persistent tower (conv_sb.cuh) -------------------------------------------------------
+constexpr int FLAG_CANDIDATES = 512;   // candidate 128-byte lines for the progress flags
+
+// ONE thread on one SM: for every candidate line, how long until a flag published the way the kernel does it
+// (L2 atomic) is visible to a gpu-scope poll from the same SM.  Lines homed in the other die's L2 take about twice as
+// long (measured on B200: ~340 vs ~720 cycles), which splits the candidates into the two dies.
+__global__ void flag_line_probe_kernel(unsigned* cand, unsigned* out_cycles) {
+  for (int c = 0; c < FLAG_CANDIDATES; ++c) {
+    unsigned* p = cand + static_cast<size_t>(c) * 32 + 31;
+    unsigned best = 0xffffffffu;
+    for (unsigned trial = 1; trial <= 4; ++trial) {
+      const long long t0 = clock64();
+      caz::ptx::publish_flag_gpu(p, trial);
+      unsigned spins = 0;
+      while (caz::ptx::ld_relaxed_gpu(p) != trial && ++spins < (1u << 20)) {}
+      const unsigned d = static_cast<unsigned>(clock64() - t0);
+      best = d < best ? d : best;
+    }
+    caz::ptx::publish_flag_gpu(p, 0u);
+    out_cycles[c] = best;
+  }
+}
+
+// Lays out the two copies of the per-tile flag lines (conv_sb.cuh, Args::flag_line) on lines of the two latency
+// classes.  Without a clear split (one die, or noise) both copies still get distinct lines: nothing depends on the
+// split being right except speed.
+int calibrate_flag_copies(caz_handle* h) {
+  unsigned* d_cyc = nullptr;
+  CU_TRY(h, cudaMalloc(&d_cyc, FLAG_CANDIDATES * sizeof(unsigned)));
+  for (int rep = 0; rep < 2; ++rep) flag_line_probe_kernel<<<1, 1, 0, h->stream>>>(h->sb_counter, d_cyc);
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  std::vector<unsigned> cyc(FLAG_CANDIDATES);
+  CU_TRY(h, cudaMemcpy(cyc.data(), d_cyc, cyc.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  cudaFree(d_cyc);
+  std::vector<unsigned> sorted(cyc);
+  std::sort(sorted.begin(), sorted.end());
+  unsigned gap = 0, split = 0;
+  for (int i = FLAG_CANDIDATES / 8; i + 1 < FLAG_CANDIDATES - FLAG_CANDIDATES / 8; ++i)
+    if (sorted[i + 1] - sorted[i] > gap) { gap = sorted[i + 1] - sorted[i]; split = (sorted[i + 1] + sorted[i]) / 2; }
+  h->sb_two_dies = gap * 4 > sorted[FLAG_CANDIDATES / 2];   // a jump of more than a quarter of the median
+  int n[2] = {0, 0};
+  for (int c = 0; c < FLAG_CANDIDATES; ++c) {
+    const int cls = h->sb_two_dies ? (cyc[c] > split ? 1 : 0) : (c & 1);
+    if (n[cls] < caz::sb::MAX_TILES) h->sb_flag_line[cls][n[cls]++] = (uint16_t)c;
+  }
+  if (n[0] < caz::sb::MAX_TILES || n[1] < caz::sb::MAX_TILES) {   // lopsided: fall back to alternating lines
+    h->sb_two_dies = false;
+    for (int t = 0; t < caz::sb::MAX_TILES; ++t) { h->sb_flag_line[0][t] = (uint16_t)(2 * t); h->sb_flag_line[1][t] = (uint16_t)(2 * t + 1); }
+  }
+  if (getenv("CAZ_SB_VERBOSE"))
+    fprintf(stderr, "caz: flag lines: two latency classes=%d (gap %u, split %u, min %u, median %u, max %u)\n", (int)h->sb_two_dies, gap,
+            split, sorted.front(), sorted[FLAG_CANDIDATES / 2], sorted.back());
+  return CAZ_OK;
+}
+
 int setup_small_batch(caz_handle* h) {
   const caz_arch& a = h->arch;
   h->sb_ok = false;
@@ -463,8 +520,9 @@ int setup_small_batch(caz_handle* h) {
   }
   CU_TRY(h, cudaMalloc(&h->sb_hpart, (size_t)sb_cap * 16 * caz::sb::HEAD_FILTERS_MAX * 64 * sizeof(float)));
   CU_TRY(h, cudaMalloc(&h->sb_hstats, (size_t)sb_cap * caz::sb::HSTAT_FLOATS * sizeof(float)));
-  CU_TRY(h, cudaMalloc(&h->sb_counter, caz::sb::MAX_TILES * 16 * sizeof(unsigned)));
-  CU_TRY(h, cudaMemset(h->sb_counter, 0, caz::sb::MAX_TILES * 16 * sizeof(unsigned)));
+  CU_TRY(h, cudaMalloc(&h->sb_counter, FLAG_CANDIDATES * 128));
+  CU_TRY(h, cudaMemset(h->sb_counter, 0, FLAG_CANDIDATES * 128));
+  if ((rc = calibrate_flag_copies(h))) return rc;
   CU_TRY(h, cudaMalloc(&h->sb_trace, (1024 + 16 * 256 * 2) * sizeof(long long)));
   CU_TRY(h, cudaMemset(h->sb_trace, 0, (1024 + 16 * 256 * 2) * sizeof(long long)));
   CU_TRY(h, cudaFuncSetAttribute(caz::sb::forward_sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::sb::SMEM_BYTES));
@@ -552,10 +610,12 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   args.mask = d_mask;
   args.policy = d_policy;
   args.value = d_value;
-  args.flags = h->sb_counter;
+  args.flag_base = h->sb_counter;
+  for (int c = 0; c < 2; ++c)
+    for (int t = 0; t < caz::sb::MAX_TILES; ++t) args.flag_line[c][t] = h->sb_flag_line[c][t];
 
   if (h->sb_epoch > 0x40000000u) {   // long before the flag epochs could wrap past a stale tile's value: start over
-    CU_TRY(h, cudaMemsetAsync(h->sb_counter, 0, caz::sb::MAX_TILES * 16 * sizeof(unsigned), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->sb_counter, 0, FLAG_CANDIDATES * 128, h->stream));
     h->sb_epoch = 0;
   }
   args.base = h->sb_epoch;

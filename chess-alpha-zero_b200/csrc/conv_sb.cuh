@@ -48,6 +48,7 @@ constexpr int BAR_BYTES = 1024;
 constexpr int SMEM_BYTES = A_BYTES + W_RING_BYTES + BAR_BYTES + 1024 /*alignment*/;
 constexpr int HEAD_SMEM_BYTES = A_BYTES + W_RING_BYTES;        // what the head phases may use for staged weights
 constexpr int MAX_BATCH = 64;
+constexpr int MAX_TILES = 64;   // board tiles per launch (one flag line each)
 
 struct Args {
   int batch;        // positions (<= MAX_BATCH)
@@ -84,7 +85,14 @@ struct Args {
   const uint8_t* mask;        // nullptr or [batch][n_labels]
   float* policy;              // [batch][n_labels]
   float* value;               // [batch]
-  unsigned* flags;            // [gridDim.x] progress flag of every CTA: base + number of phases it has completed
+  // Progress flags: base + number of phases a CTA has completed; one 128-byte line per board tile (words 0-15: the
+  // slices' flags, words 16-31: scratch for the start-up probe).  B200 is two dies, and an L2 atomic on a line homed in
+  // the OTHER die's L2 takes twice as long to become visible to a gpu-scope poll (~720 vs ~340 cycles, measured); with
+  // all flags on one die half of the tiles ran 6.2 us per layer instead of 5.4.  So every tile has two flag lines, one
+  // from each latency class (caz_abi.cu classifies candidate lines at creation): a CTA publishes to both and polls the
+  // one that answers faster from its own SM (probed once per launch, off the critical path).
+  unsigned* flag_base;
+  uint16_t flag_line[2][MAX_TILES];   // [copy][tile] -> line index (x 32 words)
   unsigned base;              // flag value that means "nothing of this launch done yet" (monotonic across launches)
   long long* trace;           // nullptr or [n_layers+1][8] clock64 stamps of CTA 0 (see caz_debug_sb_trace)
   int* err_flag;
@@ -93,10 +101,8 @@ struct Args {
 enum : int { ERR_HEADW = 207, ERR_W = 201, ERR_A = 202, ERR_GRID = 203, ERR_MMA_A = 204, ERR_MMA_W = 205, ERR_EPI = 206 };
 
 // Grid phases: 0 input pack, 1..L the L conv layers, L+1 head 1x1 convs, L+2 head dense layers.
-// A CTA that has packed its share of the input publishes flag = base + 1, after layer l flag = base + 2 + l, after its
-// head statistics flag = base + 2 + n_layers: FLAG_STEPS values per launch.
-constexpr int FLAG_STEPS_EXTRA = 2;
-constexpr int MAX_TILES = 64;   // flags: 16 words per board tile
+// A CTA publishes flag = base + 1 + l after layer l and base + 1 + n_layers after its head statistics.
+constexpr int FLAG_STEPS_EXTRA = 1;
 // Heads: every quantity that is summed across CTAs is split into CANONICAL pieces that do not depend on how many
 // slices the grid has -- 16-channel groups for the 1x1 head convolutions, 128-label units for the softmax statistics,
 // 16-unit groups for the value head's hidden layer -- and the pieces are combined in a fixed order, so the outputs
@@ -155,6 +161,15 @@ __device__ __forceinline__ void wait_tile(const Args& args, const unsigned* tile
     if (++spins > (1u << 24)) sync_trap(args);
   }
   if (!(args.dbg & 1)) ptx::fence_acq_rel_gpu();
+}
+
+__device__ __forceinline__ unsigned* tile_flag_line(const Args& args, int copy, int tile) {
+  return args.flag_base + static_cast<size_t>(args.flag_line[copy][tile]) * 32;
+}
+// one thread: publish this CTA's progress in both copies (fire and forget)
+__device__ __forceinline__ void publish(const Args& args, int tile, int slice, unsigned value) {
+  ptx::publish_flag_gpu(tile_flag_line(args, 0, tile) + slice, value);
+  ptx::publish_flag_gpu(tile_flag_line(args, 1, tile) + slice, value);
 }
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -256,8 +271,14 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   __shared__ float s_red[64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x / args.n_slices, slice = blockIdx.x % args.n_slices;
+  // which CTA takes which (tile, slice): consecutive block ids go to different GPCs (classic placement), so
+  // tile = id / n_slices spreads a tile over the GPCs, tile = id % n_tiles (dbg bit 1) keeps strides together
+  const unsigned trace_cta = static_cast<unsigned>(args.dbg >> 8);   // which CTA writes the per-layer trace (debug)
+  const int n_tiles = gridDim.x / args.n_slices;
+  const int tile = (args.dbg & 2) ? blockIdx.x % n_tiles : blockIdx.x / args.n_slices;
+  const int slice = (args.dbg & 2) ? blockIdx.x / n_tiles : blockIdx.x % args.n_slices;
   const int n0 = tile * args.nb, col0 = slice * args.ns;
+  __shared__ int s_near_copy;   // which of the tile's two flag lines this SM polls (set by warp 3 during layer 0)
   const int tap_bytes = args.ns * 128;
   const uint32_t tmem_cols = static_cast<uint32_t>(NACC * args.ns);  // 128, 256 or 512: powers of two
   const unsigned L = static_cast<unsigned>(args.n_layers);
@@ -268,7 +289,12 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   const int hid_cnt = max(0, min(hg.hsp, args.value_fc - hid0));
   float* s_wp = reinterpret_cast<float*>(smem);                         // heads: [pf*64][LABEL_CHUNK], over the tower's tiles
   float* s_wv = s_wp + args.pf * 64 * LABEL_CHUNK;                      //        [vf*64][hsp]
-  long long* ktrace = (args.trace && blockIdx.x == 0 && threadIdx.x == 32) ? args.trace + args.n_layers * 8 : nullptr;
+  long long* ktrace = (args.trace && blockIdx.x == trace_cta && threadIdx.x == 32) ? args.trace + args.n_layers * 8 : nullptr;
+  if (args.trace && threadIdx.x == 0) {   // where does this CTA run
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    args.trace[1024 + (15 * 256 + blockIdx.x) * 2] = smid;
+  }
   if (ktrace) {
     ktrace[0] = clock64();
     long long gt;
@@ -304,29 +330,33 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // ===================== phase 0: input pack =====================
-  // fp32 NCHW planes (what predict_on_batch receives) or 68-byte board records -> bf16 NHWC, channels zero-padded.
+  // ===================== phase 0: the stem's halo tile, built in place =====================
+  // fp32 NCHW planes (what predict_on_batch receives) or 68-byte board records -> the zero-padded tile
+  // [hw ranks][nb boards][hw files][64 channels] of 16-bit operands, written straight into shared memory in the layout a
+  // TMA box with the 128-byte swizzle would have produced (16-byte chunk index XOR row & 7; the tile is 1024-byte
+  // aligned).  Every CTA of a tile builds its own copy: 1 152 values per board, no global round trip, no rendezvous.
   // The weight producer does not take part: it starts streaming layer 0's weights immediately.
   if (warp != 0) {
-    const int per_pos = 64 * args.in_cpad;
     const int nthr = THREADS - 32, t = threadIdx.x - 32;
-    // board b is packed by the n_slices CTAs of its own pair, CTA `slice` taking every n_slices-th element
-    for (int b = n0; b < n0 + args.nb && b < args.batch; ++b) {
-      __nv_bfloat16* dst = args.in_act + static_cast<size_t>(b) * per_pos;
-#pragma unroll 1
-      for (int i = slice * nthr + t; i < per_pos; i += nthr * args.n_slices) {
-        const int sq = i / args.in_cpad, c = i - sq * args.in_cpad;
-        float v = 0.0f;
-        if (c < args.in_planes)
-          v = args.planes ? args.planes[(static_cast<size_t>(b) * args.in_planes + c) * 64 + sq]
-                          : record_plane_value(args.records + static_cast<size_t>(b) * 68, c, sq);
-        reinterpret_cast<uint16_t*>(dst)[i] = ptx::pack_h16(v, args.fp16 != 0);
-      }
-    }
-    __threadfence();
-    ptx::fence_proxy_async_all();
+    const int hw = 8 + args.stem_k - 1, pad = (args.stem_k - 1) / 2;
+    const int rows = hw * args.nb * hw;
+    uint4* tile16 = reinterpret_cast<uint4*>(smem_a);
+    for (int i = t; i < rows * 8; i += nthr) tile16[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("bar.sync 2, 224;" ::: "memory");
-    if (threadIdx.x == 32) ptx::publish_flag_gpu(args.flags + tile * 16 + slice, args.base + 1u);
+    const int per_board = args.in_planes * 64;
+    for (int i = t; i < args.nb * per_board; i += nthr) {
+      const int p = i / per_board, rem = i - p * per_board;
+      const int c = rem >> 6, sq = rem & 63;   // consecutive threads -> consecutive squares of one plane (coalesced)
+      const int b = n0 + p;
+      if (b >= args.batch) continue;
+      const float v = args.planes ? args.planes[(static_cast<size_t>(b) * args.in_planes + c) * 64 + sq]
+                                  : record_plane_value(args.records + static_cast<size_t>(b) * 68, c, sq);
+      const int row = ((sq >> 3) + pad) * args.nb * hw + p * hw + (sq & 7) + pad;
+      const int off = row * 128 + (((c >> 3) ^ (row & 7)) << 4) + ((c & 7) << 1);
+      *reinterpret_cast<uint16_t*>(smem_a + off) = ptx::pack_h16(v, args.fp16 != 0);
+    }
+    ptx::fence_proxy_async();   // generic-proxy writes -> the tensor core's async-proxy reads
+    asm volatile("bar.sync 2, 224;" ::: "memory");
     if (ktrace) ktrace[1] = clock64();
   }
 
@@ -362,25 +392,50 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     // ============ activation producer: one halo tile per 64-channel chunk, as soon as the CTAs that own those
     // channels of this board tile have published the previous layer (no grid-wide barrier: a tile's CTAs only ever
     // read what CTAs of the same tile wrote, and a chunk can start while other slices are still in their epilogue) ====
-    const unsigned* tile_flags = args.flags + tile * 16;
+    const unsigned* tile_flags = tile_flag_line(args, 0, tile);   // lane 0 replaces it with the nearer copy during layer 0
     for (int l = 0; l < args.n_layers; ++l) {
       const int k = l == 0 ? args.stem_k : args.blk_k;
       const int kch = l == 0 ? args.stem_kchunks : args.filters / 64;
       const int hw = 8 + k - 1, pad = (k - 1) / 2;
       const int plane_bytes = hw * args.nb * hw * 128;
       const CUtensorMap* tm = l == 0 ? &tm_in : ((l & 1) ? &tm_xb : &tm_y);
-      const unsigned target = args.base + 1u + static_cast<unsigned>(l);   // pack + layers 0..l-1
+      const unsigned target = args.base + static_cast<unsigned>(l);   // layers 0..l-1
+      if (l == 0) {
+        // the stem's tile was built in shared memory above (this warp took part and has passed its barrier)
+        if (lane == 0) {
+          if (args.trace && blockIdx.x == trace_cta) args.trace[0] = clock64();
+          ptx::mbar_arrive(&a_full[0]);
+          // while layer 0 computes: which of the tile's two flag lines answers faster from this SM?  Publish a value
+          // to this slice's scratch word of each line and time until a poll sees it (two rounds, best of each).
+          unsigned best[2] = {0xffffffffu, 0xffffffffu};
+          for (unsigned round = 1; round <= 2; ++round)
+            for (int c = 0; c < 2; ++c) {
+              unsigned* pw = tile_flag_line(args, c, tile) + 16 + slice;
+              const unsigned val = args.base + round;
+              const long long t0 = clock64();
+              ptx::publish_flag_gpu(pw, val);
+              unsigned spins = 0;
+              while (ptx::ld_relaxed_gpu(pw) != val && ++spins < (1u << 16)) {}
+              const unsigned d = static_cast<unsigned>(clock64() - t0);
+              best[c] = d < best[c] ? d : best[c];
+            }
+          s_near_copy = best[1] < best[0] ? 1 : 0;
+          tile_flags = tile_flag_line(args, s_near_copy, tile);
+        }
+        __syncwarp();
+        continue;
+      }
       if (lane == 0) {
         wait_tile(args, tile_flags, target);   // the tile's CTAs have published the previous layer
         ptx::fence_proxy_async_all();  // other CTAs' generic-proxy stores -> our async-proxy (TMA) reads
-        if (args.trace && blockIdx.x == 0) args.trace[l * 8 + 0] = clock64();
+        if (args.trace && blockIdx.x == trace_cta) args.trace[l * 8 + 0] = clock64();
         for (int kc = 0; kc < kch; ++kc) {
           ptx::mbar_expect_tx(&a_full[kc], plane_bytes);
           ptx::tma_load_4d(smem_a + kc * plane_bytes, tm, &a_full[kc], kc * 64, -pad, n0, -pad);
         }
       }
       __syncwarp();
-      if (args.trace && blockIdx.x == 0) {   // when did the layer's last activation plane land (debug only)
+      if (args.trace && blockIdx.x == trace_cta) {   // when did the layer's last activation plane land (debug only)
         ptx::mbar_wait(&a_full[kch - 1], l == 0 ? 0u : (kch - 1 < args.stem_kchunks ? (l & 1) : ((l - 1) & 1)), args.err_flag, ERR_A);
         if (lane == 0) args.trace[l * 8 + 7] = clock64();
       }
@@ -412,8 +467,8 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         // plane kc completes once per layer that uses it (the stem may use fewer planes than the tower)
         ptx::mbar_wait(&a_full[kc], (a_phase >> kc) & 1u, args.err_flag, ERR_MMA_A);
         a_phase ^= 1u << kc;
-        if (args.trace && blockIdx.x == 0 && lane == 0 && kc == 0 && which == 0) args.trace[l * 8 + 1] = clock64();
-        if (args.trace && blockIdx.x == 0 && lane == 0 && kc == kch - 1 && which == 0) args.trace[l * 8 + 2] = clock64();
+        if (args.trace && blockIdx.x == trace_cta && lane == 0 && kc == 0 && which == 0) args.trace[l * 8 + 1] = clock64();
+        if (args.trace && blockIdx.x == trace_cta && lane == 0 && kc == kch - 1 && which == 0) args.trace[l * 8 + 2] = clock64();
         int dy0 = 0, dx0 = 0;
         for (int tap0 = 0; tap0 < k * k; tap0 += tps) {
           if ((kc & 1) == which) {   // issuer `which` takes the chunks with kc % 2 == which
@@ -440,7 +495,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           if (++slot == args.n_slots) { slot = 0; phase ^= 1; b_slot = b_desc0; }
         }
       }
-      if (args.trace && blockIdx.x == 0 && lane == 0 && which == 0) args.trace[l * 8 + 3] = clock64();
+      if (args.trace && blockIdx.x == trace_cta && lane == 0 && which == 0) args.trace[l * 8 + 3] = clock64();
       if (ptx::elect_one()) {
         ptx::mma_commit(acc_full);
         if (l == args.n_layers - 1) ptx::mma_commit(tower_done);
@@ -464,29 +519,34 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       s_hw[i] = (f6 < hf_all && j < args.ns) ? args.head_w[f6 * args.filters + col0 + j] : 0.0f;
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    float res[4][16];   // fp32 residual stream: this thread's row, this CTA's channels (up to 64)
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) res[ci][j] = 0.0f;
     for (int l = 0; l < args.n_layers; ++l) {
       const bool last = l == args.n_layers - 1;   // its output only feeds the heads: no activation stores
       const bool conv1 = l > 0 && (l & 1);     // bf16 out to y only
       const bool has_res = l > 0 && !(l & 1);  // conv2: + residual, out to xf and xb
       const bool two_issuers = (l == 0 ? args.stem_kchunks : args.filters / 64) > 1;
       const float* bias = args.bias_all + static_cast<size_t>(l) * args.filters + col0;
-      for (int c0 = 0; c0 < args.ns; c0 += 16) {
-        // bias and the residual slice (written by this very thread two layers ago) are fetched BEFORE the wait
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c0 = ci * 16;
+        if (c0 >= args.ns) break;
+        // bias is fetched BEFORE the wait; the fp32 residual stream of this row and these channels never leaves the
+        // thread: it lives in registers from one block to the next (res)
         float f[16];
-        float* xrow = args.xf + row * args.filters + col0 + c0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) f[j] = __ldg(bias + c0 + j);
-        if (has_res && live) {
+        if (has_res) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 r = *reinterpret_cast<const float4*>(xrow + q * 4);
-            f[q * 4 + 0] += r.x; f[q * 4 + 1] += r.y; f[q * 4 + 2] += r.z; f[q * 4 + 3] += r.w;
-          }
+          for (int j = 0; j < 16; ++j) f[j] += res[ci][j];
         }
         if (c0 == 0) {
           ptx::mbar_wait(acc_full, l & 1, args.err_flag, ERR_EPI);
           ptx::tcgen05_fence_after();
-          if (args.trace && blockIdx.x == 0 && threadIdx.x == 128) args.trace[l * 8 + 4] = clock64();
+          if (args.trace && blockIdx.x == trace_cta && threadIdx.x == 128) args.trace[l * 8 + 4] = clock64();
         }
         {
           // a single-chunk layer (the stem) is issued by issuer 0 alone: accumulators 2 and 3 were not written
@@ -530,8 +590,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
           for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
           if (!conv1) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<float4*>(xrow + q * 4) = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+            for (int j = 0; j < 16; ++j) res[ci][j] = f[j];
           }
           __nv_bfloat16* orow = (conv1 ? args.y : args.xb) + row * args.filters + col0 + c0;
 #pragma unroll
@@ -548,15 +607,15 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       __threadfence();               // this thread's stores visible at gpu scope ...
       ptx::fence_proxy_async_all();  // ... and ordered before later async-proxy reads
       ptx::tcgen05_fence_before();   // TMEM reads done before the next layer's MMAs overwrite the accumulators
-      if (args.trace && blockIdx.x == 0 && threadIdx.x == 128) args.trace[l * 8 + 5] = clock64();
+      if (args.trace && blockIdx.x == trace_cta && threadIdx.x == 128) args.trace[l * 8 + 5] = clock64();
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (args.trace && blockIdx.x == 0 && threadIdx.x == 128) args.trace[l * 8 + 6] = clock64();
+      if (args.trace && blockIdx.x == trace_cta && threadIdx.x == 128) args.trace[l * 8 + 6] = clock64();
       if (args.trace && threadIdx.x == 128 && l < 16) {
         long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         args.trace[1024 + (l * 256 + blockIdx.x) * 2] = gt;
       }
-      if (threadIdx.x == 128) ptx::publish_flag_gpu(args.flags + tile * 16 + slice, args.base + 2u + static_cast<unsigned>(l));
+      if (threadIdx.x == 128) publish(args, tile, slice, args.base + 1u + static_cast<unsigned>(l));
     }
   }
   ptx::tcgen05_fence_before();
@@ -571,11 +630,11 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   // H2: this CTA's labels of the policy Dense layer and its hidden units of the value head, from staged weights;
   //     per-128-label softmax statistics and per-16-unit value partials are published for the tile.
   // H3: after the tile's second rendezvous every CTA normalises its own labels; slice 0 writes the value.
-  const unsigned* tile_flags = args.flags + tile * 16;
   const int hf_total = args.pf + args.vf;
   const int kp = args.pf * 64, kv = args.vf * 64;
   if (ktrace) ktrace[2] = clock64();
-  if (threadIdx.x == 0) wait_tile(args, tile_flags, args.base + 1u + L);   // the tile's CTAs have stored their partials
+  const unsigned* tile_flags = tile_flag_line(args, s_near_copy, tile);   // written by warp 3 long before the __syncthreads above
+  if (threadIdx.x == 0) wait_tile(args, tile_flags, args.base + L);   // the tile's CTAs have stored their partials
   __syncthreads();
   if (ktrace) ktrace[3] = clock64();
   for (int i = threadIdx.x; i < args.nb * hf_total * 64; i += THREADS) {
@@ -696,8 +755,8 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    ptx::publish_flag_gpu(args.flags + tile * 16 + slice, args.base + 2u + L);
-    wait_tile(args, tile_flags, args.base + 2u + L);
+    publish(args, tile, slice, args.base + 1u + L);
+    wait_tile(args, tile_flags, args.base + 1u + L);
   }
   __syncthreads();
   if (ktrace) ktrace[7] = clock64();

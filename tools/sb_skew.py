@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Arrival skew at the grid barrier of the small-batch kernel: per layer, when each CTA joined (globaltimer) and
-when it saw the barrier open."""
+"""When does each CTA of the small-batch kernel finish each layer (globaltimer, ns)?  Board tiles synchronise only
+within themselves, so the kernel is as long as its slowest tile: prints per-layer finish times per tile."""
 import ctypes, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -22,8 +22,19 @@ st = np.zeros(n, np.int64)
 _lib.check(ev._handle, lib.caz_debug_sb_trace(ev._handle, 0, st.ctypes.data_as(ctypes.c_void_p), n))
 g = st[1024:].reshape(16, 256, 2).astype(np.float64)
 ncta = int((g[0, :, 0] > 0).sum())
-print("CTAs:", ncta)
-for l in range(0, 14):
-    j = g[l, :ncta, 0]; o = g[l + 1, :ncta, 1]
-    print(f"layer {l:2d}: joined min..max spread {1e-3 * (j.max() - j.min()):6.2f} us | last join -> first open {1e-3 * (o.min() - j.max()):6.2f} us"
-          f" | open spread {1e-3 * (o.max() - o.min()):6.2f} us | layer period {1e-3 * (g[l + 1, :ncta, 0].max() - j.max()):6.2f} us")
+t0 = st[16 * 8 + 0]   # globaltimer at CTA 0's start
+print("CTAs:", ncta, " kernel start (CTA 0) = 0")
+for l in (0, 1, 7, 14):
+    j = (g[l, :ncta, 0] - t0) * 1e-3
+    print(f"layer {l:2d} finished: min {j.min():7.2f} us  median {np.median(j):7.2f}  max {j.max():7.2f}   (CTA 0: {j[0]:7.2f})")
+slices = ncta // ((b + 1) // 2) if b > 16 else ncta // b if ncta % b == 0 else 8
+j = (g[14, :ncta, 0] - t0) * 1e-3
+print("last layer finish per CTA, in block-id order:")
+for i in range(0, ncta, 16):
+    print("   ", " ".join(f"{x:6.1f}" for x in j[i:i + 16]))
+
+smid = g[15, :ncta, 0].astype(int)
+order = np.argsort(smid)
+print("by SM id: (smid, tile, finish us)")
+for i in range(0, ncta, 8):
+    print("   ", "  ".join(f"{smid[k]:3d}/t{k // slices:02d}/{j[k]:5.1f}" for k in order[i:i + 8]))
