@@ -266,6 +266,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--selfplay-seconds", type=float, default=8.0,
+                    help="BASELINE configs[2]: seconds of 256-game / 800-sim self-play through this evaluator (0 = skip; N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -400,6 +402,12 @@ def main():
     }
     if not args.no_latency and world == 1:
         out["latency_b16"] = latency_probe(ev, host_batches[0][:16].copy())
+    if args.selfplay_seconds > 0 and world == 1 and args.batch >= 2048:
+        # configs[2]: the host-side batched search (include/caz_mcts.h) feeding caz_eval_records, two half-groups alternating
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import selfplay_bench
+        out["selfplay"] = selfplay_bench.run(ev, games=256, sims=800, search_threads=16, seconds=args.selfplay_seconds, groups=2,
+                                             label=f"{args.blocks}x256 net ({args.precision}), random-init weights")
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(cfg, weights, host_batches[0])
     print(json.dumps(out))

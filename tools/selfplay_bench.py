@@ -24,51 +24,34 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--games", type=int, default=256)
-    ap.add_argument("--sims", type=int, default=800)
-    ap.add_argument("--search-threads", type=int, default=16)
-    ap.add_argument("--seconds", type=float, default=20.0)
-    ap.add_argument("--groups", type=int, default=2)
-    ap.add_argument("--host-threads", type=int, default=0, help="worker threads per group (0 = cores / groups)")
-    ap.add_argument("--blocks", type=int, default=7)
-    ap.add_argument("--precision", default="bf16")
-    ap.add_argument("--seed", type=int, default=1)
-    args = ap.parse_args()
-
-    rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    import torch
-    torch.cuda.set_device(rank)
+def run(ev, games=256, sims=800, search_threads=16, seconds=20.0, groups=2, host_threads=0, seed=1, rank=0, world=1,
+        label=""):
+    """Self-play rounds for `seconds` on the evaluator `ev` (max_batch >= games / groups * search_threads)."""
     import chess_alpha_zero_b200 as caz
     from chess_alpha_zero_b200 import _lib, mcts
-
-    cfg_net, weights = bench.network(args.blocks)
-    per_group = args.games // args.groups
-    cap = per_group * args.search_threads
-    ev = caz.Evaluator(cfg_net, weights, device=rank, precision=args.precision, max_batch=cap)
+    per_group = games // groups
+    cap = per_group * search_threads
     cores = os.cpu_count() or 1
-    host_threads = args.host_threads or max(1, cores // max(1, world) // args.groups)
-    mcfg = mcts.MctsConfig.normal(simulation_num_per_move=args.sims, search_threads=args.search_threads)
-    groups = [caz.SelfPlaySearch(per_group, mcfg, seed=args.seed * 1000 + rank * 10 + g, n_threads=host_threads)
-              for g in range(args.groups)]
-    pins = [(_lib.PinnedArray((cap, 1968), np.float32), _lib.PinnedArray((cap,), np.float32)) for _ in groups]
+    host_threads = host_threads or max(1, cores // max(1, world) // groups)
+    mcfg = mcts.MctsConfig.normal(simulation_num_per_move=sims, search_threads=search_threads)
+    searches = [caz.SelfPlaySearch(per_group, mcfg, seed=seed * 1000 + rank * 10 + g, n_threads=host_threads)
+                for g in range(groups)]
+    pins = [(_lib.PinnedArray((cap, 1968), np.float32), _lib.PinnedArray((cap,), np.float32)) for _ in searches]
 
-    # warm-up round (first-touch, clocks)
-    for g, (pp, pv) in zip(groups, pins):
+    # warm-up round (first touch, clocks)
+    for g, (pp, pv) in zip(searches, pins):
         rec = g.collect()
         ev.predict_records_into(rec, pp.array, pv.array)
         g.apply(pp.array[:len(rec)], pv.array[:len(rec)])
-    base = [g.stats() for g in groups]
+    base = [g.stats() for g in searches]
 
-    acc = [dict(collect=0.0, eval=0.0, apply=0.0, leaves=0, rounds=0) for _ in groups]
-    stop_at = time.perf_counter() + args.seconds
+    acc = [dict(collect=0.0, eval=0.0, apply=0.0, leaves=0, rounds=0) for _ in searches]
+    stop_at = time.perf_counter() + seconds
     ev_lock = threading.Lock()
     busy = [0.0]
 
     def loop(i):
-        g, (pp, pv), a = groups[i], pins[i], acc[i]
+        g, (pp, pv), a = searches[i], pins[i], acc[i]
         while time.perf_counter() < stop_at:
             t0 = time.perf_counter()
             rec = g.collect()
@@ -87,7 +70,7 @@ def main():
             a["rounds"] += 1
 
     t_start = time.perf_counter()
-    threads = [threading.Thread(target=loop, args=(i,)) for i in range(len(groups))]
+    threads = [threading.Thread(target=loop, args=(i,)) for i in range(len(searches))]
     for t in threads:
         t.start()
     for t in threads:
@@ -95,7 +78,7 @@ def main():
     wall = time.perf_counter() - t_start
 
     tot = {}
-    for g, b in zip(groups, base):
+    for g, b in zip(searches, base):
         s = g.stats()
         for k in s:
             tot[k] = tot.get(k, 0) + (s[k] - b[k] if k != "tree_nodes_last" else 0)
@@ -103,23 +86,49 @@ def main():
     rounds = sum(a["rounds"] for a in acc)
     moves_per_game = 80.0   # a typical self-play game length, only used for the games/hour extrapolation
     out = {
-        "workload": f"self-play MCTS, {args.sims} sims/move, {args.games} concurrent games, search_threads {args.search_threads}, "
-                    f"{args.blocks}x256 net ({args.precision}), random-init weights",
+        "workload": f"self-play MCTS, {sims} sims/move, {games} concurrent games, search_threads {search_threads}, {label}",
         "rank": rank, "world": world, "seconds": wall,
         "sims_per_s": tot["descents"] / wall,
         "positions_per_s_through_evaluator": leaves / wall,
         "mean_batch": leaves / max(1, rounds),
         "evaluator_occupancy": busy[0] / wall,
-        "host_threads_per_group": host_threads, "groups": args.groups, "host_cores": cores,
+        "host_threads_per_group": host_threads, "groups": groups, "host_cores": cores,
         "per_round_ms": {k: 1e3 * sum(a[k] for a in acc) / max(1, rounds) for k in ("collect", "eval", "apply")},
         "moves_played": tot["moves_played"], "games_finished": tot["games_finished"],
         "terminal_hits": tot["terminal_hits"], "withdrawn": tot["withdrawn"],
         "moves_per_hour": tot["moves_played"] / wall * 3600,
         "games_per_hour_at_80_moves": tot["moves_played"] / wall * 3600 / moves_per_game,
     }
-    print(json.dumps(out), flush=True)
-    for g in groups:
+    for g in searches:
         g.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--games", type=int, default=256)
+    ap.add_argument("--sims", type=int, default=800)
+    ap.add_argument("--search-threads", type=int, default=16)
+    ap.add_argument("--seconds", type=float, default=20.0)
+    ap.add_argument("--groups", type=int, default=2)
+    ap.add_argument("--host-threads", type=int, default=0, help="worker threads per group (0 = cores / ranks / groups)")
+    ap.add_argument("--blocks", type=int, default=7)
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--seed", type=int, default=1)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch
+    torch.cuda.set_device(rank)
+    import chess_alpha_zero_b200 as caz
+
+    cfg_net, weights = bench.network(args.blocks)
+    cap = args.games // args.groups * args.search_threads
+    ev = caz.Evaluator(cfg_net, weights, device=rank, precision=args.precision, max_batch=cap)
+    out = run(ev, args.games, args.sims, args.search_threads, args.seconds, args.groups, args.host_threads, args.seed, rank,
+              world, label=f"{args.blocks}x256 net ({args.precision}), random-init weights")
+    print(json.dumps(out), flush=True)
     ev.close()
 
 
