@@ -34,6 +34,7 @@ int caz_mcts_create(const caz_mcts_config* c, int32_t n_games, uint64_t seed, co
   m.min_resign_turn = c->min_resign_turn;
   m.max_game_length = c->max_game_length;
   m.n_labels = c->n_labels;
+  m.record_play_data = c->record_play_data;
   caz_mcts* h = new (std::nothrow) caz_mcts;
   if (!h) return 2;
   h->impl = new Mcts(m, n_games, seed, move_label, unflipped_index, n_threads);
@@ -115,6 +116,16 @@ int caz_mcts_root_edges(const caz_mcts* m, int32_t game, int32_t* label, int32_t
     if (p) p[k] = e.p;
   }
   return k;
+}
+
+int64_t caz_mcts_drain_play_data(caz_mcts* m, uint8_t* buf, int64_t cap) {
+  if (!m) return -1;
+  std::lock_guard<std::mutex> lk(m->impl->play_data_mu);
+  const int64_t need = static_cast<int64_t>(m->impl->play_data.size());
+  if (need > cap || (need > 0 && !buf)) return need;
+  if (need > 0) std::memcpy(buf, m->impl->play_data.data(), static_cast<size_t>(need));
+  m->impl->play_data.clear();
+  return need;
 }
 
 uint64_t caz_chess_perft(const char* fen, int32_t depth) {

@@ -25,6 +25,7 @@
 #include <mutex>
 #include <random>
 #include <thread>
+#include <string>
 #include <vector>
 
 #include "board.hpp"
@@ -45,6 +46,7 @@ struct MctsConfig {
   int min_resign_turn = 5;             // :42
   int max_game_length = 1000;          // :43
   int n_labels = 1968;
+  int record_play_data = 0;            // keep [fen, policy, z] rows of finished games (self_play.py:90-100, 135-152)
 };
 
 struct MctsStats {
@@ -189,6 +191,9 @@ class GameSearch {
   bool finished = false;
   int winner = 0;                       // 1 white, 2 black, 3 draw
   int64_t games_played = 0;
+  // ChessPlayer.moves of both players, in game order: observation, visit-count policy (sparse), who moved
+  struct MoveRecord { std::string fen; std::vector<std::pair<uint16_t, float>> policy; int mover; };
+  std::vector<MoveRecord> move_log;
 
   void new_game() {
     Position p;
@@ -196,6 +201,7 @@ class GameSearch {
     game.reset(p);
     finished = false;
     winner = 0;
+    move_log.clear();
     begin_move();
   }
   int expected_nodes = 1024;
@@ -514,6 +520,17 @@ class Mcts {
         end_game(gs, st);
         return;
       }
+      if (cfg.record_play_data) {   // self.moves.append([env.observation, list(policy)]) (player_chess.py:145) -- not on a resignation
+        GameSearch::MoveRecord rec;
+        rec.fen = gs.game.pos.fen();
+        rec.mover = gs.game.pos.turn;
+        for (int i = 0; i < root.n_edges; ++i) {
+          const Edge& e = gs.edges[root.first_edge + i];
+          const int l = move_label[(move_from(e.move) * 64 + move_to(e.move)) * 5 + move_promo(e.move)];
+          if (l >= 0 && e.n > 0) rec.policy.emplace_back(static_cast<uint16_t>(l), static_cast<float>(e.n / total));
+        }
+        gs.move_log.push_back(std::move(rec));
+      }
       gs.game.push(move_of[action]);
       ++st.moves_played;
       const int res = gs.game.result();
@@ -546,7 +563,33 @@ class Mcts {
     return v > 0 ? 1 : 2;
   }
 
+  // Finished games' rows, serialised: per row  fen '\0' | z int8 | n uint16 | n x (label uint16, probability float32);
+  // z as finish_game assigns it (self_play.py:135-143): +1 the mover won, -1 lost, 0 draw.
+  std::vector<uint8_t> play_data;
+  std::mutex play_data_mu;
+  void flush_play_data(GameSearch& gs) {
+    std::vector<uint8_t> buf;
+    for (const auto& r : gs.move_log) {
+      buf.insert(buf.end(), r.fen.begin(), r.fen.end());
+      buf.push_back(0);
+      const int z = gs.winner == 3 ? 0 : ((gs.winner == 1) == (r.mover == WHITE) ? 1 : -1);
+      buf.push_back(static_cast<uint8_t>(static_cast<int8_t>(z)));
+      const uint16_t n = static_cast<uint16_t>(r.policy.size());
+      const uint8_t* pn = reinterpret_cast<const uint8_t*>(&n);
+      buf.insert(buf.end(), pn, pn + 2);
+      for (const auto& lp : r.policy) {
+        const uint8_t* a = reinterpret_cast<const uint8_t*>(&lp.first);
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(&lp.second);
+        buf.insert(buf.end(), a, a + 2);
+        buf.insert(buf.end(), b, b + 4);
+      }
+    }
+    std::lock_guard<std::mutex> lk(play_data_mu);
+    play_data.insert(play_data.end(), buf.begin(), buf.end());
+  }
+
   void end_game(GameSearch& gs, MctsStats& st) {
+    if (cfg.record_play_data) flush_play_data(gs);
     ++st.games_finished;
     if (gs.winner == 1) ++st.white_wins;
     else if (gs.winner == 2) ++st.black_wins;

@@ -17,7 +17,8 @@ RECORD_BYTES = 68
 
 SYMBOLS = (
     "caz_mcts_create", "caz_mcts_destroy", "caz_mcts_collect", "caz_mcts_apply", "caz_mcts_get_stats",
-    "caz_mcts_set_position", "caz_mcts_game_fen", "caz_mcts_game_result", "caz_mcts_root_edges", "caz_chess_perft",
+    "caz_mcts_set_position", "caz_mcts_game_fen", "caz_mcts_game_result", "caz_mcts_root_edges",
+    "caz_mcts_drain_play_data", "caz_chess_perft",
     "caz_chess_legal_moves", "caz_chess_play", "caz_chess_record",
 )
 
@@ -28,13 +29,14 @@ class MctsConfig(ctypes.Structure):
                 ("c_puct", ctypes.c_double), ("noise_eps", ctypes.c_double), ("dirichlet_alpha", ctypes.c_double),
                 ("tau_decay_rate", ctypes.c_double), ("virtual_loss", ctypes.c_int32), ("resign_enabled", ctypes.c_int32),
                 ("resign_threshold", ctypes.c_double), ("min_resign_turn", ctypes.c_int32),
-                ("max_game_length", ctypes.c_int32), ("n_labels", ctypes.c_int32), ("continuous", ctypes.c_int32)]
+                ("max_game_length", ctypes.c_int32), ("n_labels", ctypes.c_int32), ("continuous", ctypes.c_int32),
+                ("record_play_data", ctypes.c_int32)]
 
     @classmethod
     def normal(cls, **over):
         c = cls(simulation_num_per_move=800, search_threads=16, c_puct=1.5, noise_eps=0.25, dirichlet_alpha=0.3,
                 tau_decay_rate=0.99, virtual_loss=3, resign_enabled=1, resign_threshold=-0.8, min_resign_turn=5,
-                max_game_length=1000, n_labels=_labels.N_LABELS, continuous=1)
+                max_game_length=1000, n_labels=_labels.N_LABELS, continuous=1, record_play_data=0)
         for k, v in over.items():
             setattr(c, k, v)
         return c
@@ -75,6 +77,8 @@ def load():
     lib.caz_mcts_game_fen.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32]
     lib.caz_mcts_game_result.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     lib.caz_mcts_root_edges.argtypes = [ctypes.c_void_p, ctypes.c_int32] + [ctypes.c_void_p] * 4 + [ctypes.c_int32]
+    lib.caz_mcts_drain_play_data.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    lib.caz_mcts_drain_play_data.restype = ctypes.c_int64
     lib.caz_chess_perft.argtypes = [ctypes.c_char_p, ctypes.c_int32]
     lib.caz_chess_perft.restype = ctypes.c_uint64
     lib.caz_chess_legal_moves.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32]
@@ -201,6 +205,33 @@ class SelfPlaySearch:
 
     def result(self, game):
         return RESULTS[load().caz_mcts_game_result(self._h, game)]
+
+    def drain_play_data(self, dense=True):
+        """Rows of the games finished since the last call, as SelfPlayWorker.flush_buffer would json.dump them
+        (self_play.py:90-100): [[fen, policy, z], ...]; policy is the dense n_labels list (dense=True) or {label: p}."""
+        lib = load()
+        need = lib.caz_mcts_drain_play_data(self._h, None, 0)
+        if need <= 0:
+            return []
+        buf = np.zeros(need, np.uint8)
+        got = lib.caz_mcts_drain_play_data(self._h, buf.ctypes.data_as(ctypes.c_void_p), need)
+        raw = buf[:got].tobytes()
+        rows, i = [], 0
+        while i < len(raw):
+            j = raw.index(b"\0", i)
+            fen = raw[i:j].decode()
+            z = int(np.frombuffer(raw, np.int8, 1, j + 1)[0])
+            n = int(np.frombuffer(raw[j + 2:j + 4], np.uint16)[0])
+            pairs = np.frombuffer(raw[j + 4:j + 4 + 6 * n], np.dtype([("l", "<u2"), ("p", "<f4")]))
+            if dense:
+                pol = np.zeros(self.config.n_labels, np.float64)
+                pol[pairs["l"]] = pairs["p"]
+                policy = pol.tolist()
+            else:
+                policy = {int(a): float(b) for a, b in zip(pairs["l"], pairs["p"])}
+            rows.append([fen, policy, z])
+            i = j + 4 + 6 * n
+        return rows
 
     def root_edges(self, game):
         """(label, n, q, p) arrays of the root's edges in legal-move order, or None before the root is expanded."""

@@ -37,6 +37,7 @@ typedef struct caz_mcts_config {
   int32_t max_game_length;         /* 1000 */
   int32_t n_labels;                /* 1968 */
   int32_t continuous;              /* 1: start a new game when one ends (SelfPlayWorker), 0: games stay finished */
+  int32_t record_play_data;        /* 1: keep the [observation, policy, z] rows of finished games for caz_mcts_drain_play_data */
 } caz_mcts_config;
 
 typedef struct caz_mcts_stats {
@@ -70,6 +71,13 @@ int caz_mcts_game_result(const caz_mcts* m, int32_t game);
 /* Root statistics of a game's current search: for each legal move (python-chess order) label, n, q, p. Returns the
  * number of edges written (<= cap), -1 if the root has not been expanded yet. */
 int caz_mcts_root_edges(const caz_mcts* m, int32_t game, int32_t* label, int32_t* n, double* q, double* p, int32_t cap);
+
+/* The training rows of the games finished since the last call (self_play_buffer's `data`, self_play.py:135-152;
+ * what SelfPlayWorker.flush_buffer writes as JSON [[fen, policy[n_labels], z], ...], :90-100), serialised as
+ *   fen bytes, 0 | z int8 (+1 the side that moved won, -1 lost, 0 draw) | n uint16 | n x (label uint16, probability float32)
+ * per move, little endian, policy = visit counts / total over the labels visited.  Returns the number of bytes the
+ * pending data needs; if that exceeds cap nothing is copied and nothing is dropped. */
+int64_t caz_mcts_drain_play_data(caz_mcts* m, uint8_t* buf, int64_t cap);
 
 /* ---- the chess rules underneath (tests pin them with published perft counts) ---- */
 uint64_t caz_chess_perft(const char* fen, int32_t depth);

@@ -204,3 +204,36 @@ def test_games_run_to_completion():
     with pytest.raises(ValueError):
         s.apply(np.zeros((3, labels.N_LABELS), np.float32), np.zeros(3, np.float32))
     s.close()
+
+
+def test_play_data_rows_match_the_reference_format():
+    """self_play_buffer's data (self_play.py:135-152): one [fen, policy, z] row per move, z from the mover's side."""
+    cfg = mcts.MctsConfig.normal(simulation_num_per_move=16, search_threads=4, max_game_length=12, continuous=0,
+                                 record_play_data=1, resign_enabled=0)
+    s = caz.SelfPlaySearch(3, cfg, seed=21, n_threads=1)
+    for _ in range(1000):
+        rec = s.collect()
+        if len(rec) == 0:
+            break
+        s.apply(*_fake_net(rec))
+    rows = s.drain_play_data()
+    st = s.stats()
+    assert len(rows) == st["moves_played"] == 3 * 12 and s.drain_play_data() == []
+    results = {"1-0": 1, "0-1": -1, "1/2-1/2": 0}
+    game_of_row = 0
+    for k, (fen, policy, z) in enumerate(rows):
+        if k and fen.startswith("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w"):
+            game_of_row += 1
+        assert len(policy) == labels.N_LABELS and abs(sum(policy) - 1.0) < 1e-5
+        legal = {labels.LABEL_INDEX[m] for m in mcts.legal_moves(fen)}
+        assert {i for i, p in enumerate(policy) if p > 0} <= legal
+        white_to_move = fen.split()[1] == "w"
+        assert z in (-1, 0, 1)
+    # z is consistent inside a game: white's rows carry the white result, black's the negation
+    assert game_of_row == 2
+    per_game = [rows[i * 12:(i + 1) * 12] for i in range(3)]
+    for g, chunk in enumerate(per_game):
+        want_white = results[s.result(g)] if s.result(g) in results else None
+        for fen, _, z in chunk:
+            assert z == (want_white if fen.split()[1] == "w" else -want_white)
+    s.close()
