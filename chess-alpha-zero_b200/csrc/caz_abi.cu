@@ -78,13 +78,12 @@ struct caz_handle {
   // weight slabs the layers point into: the tower's layers are contiguous so that one tensor map covers them
   void* w_stem = nullptr;
   void* sb_w_stem = nullptr;   // stem weights padded to 64 input channels (small-batch kernel)
-  void* sb_in_act = nullptr;   // its input activations, [64 + 2][64][64]
   void* w_tower = nullptr;   // [2*res_blocks][filters][9*filters] (tensor-core build)
   float* bias_all = nullptr; // [1 + 2*res_blocks][filters]
   // small-batch persistent tower kernel (conv_sb.cuh)
   bool sb_ok = false;        // architecture fits it
   int sb_limit = -1;         // batches <= this use it; -1 = automatic
-  CUtensorMap sb_tm_in[2], sb_tm_xb[2], sb_tm_y[2];  // halo views for 1 and 2 boards per CTA tile
+  CUtensorMap sb_tm_xb[2], sb_tm_y[2];  // halo views for 1 and 2 boards per CTA tile
   CUtensorMap sb_tm_w_stem[3], sb_tm_w_tower[3];      // weight maps for N_s = 16, 32, 64
   int sb_force_nb = 0;
   unsigned* sb_counter = nullptr;   // progress flags of the small-batch kernel: 32 candidate grains of 4 KB
@@ -492,10 +491,8 @@ int setup_small_batch(caz_handle* h) {
   if (!tensor_path(h) || a.block_kernel != 3 || a.filters != 256 && a.filters != 128 && a.filters != 64) return CAZ_OK;
   if (a.input_planes > 64 || (8 + a.stem_kernel - 1) * 2 * (8 + a.stem_kernel - 1) * 128 > caz::sb::A_BYTES) return CAZ_OK;
   const int sb_cap = caz::sb::MAX_BATCH + 2;
-  CU_TRY(h, cudaMalloc(&h->sb_in_act, (size_t)sb_cap * 64 * 64 * 2));
   int rc;
   for (int nb = 1; nb <= 2; ++nb) {
-    if ((rc = make_halo_tmap(h, &h->sb_tm_in[nb - 1], h->sb_in_act, 64, a.stem_kernel, nb, sb_cap))) return rc;
     if ((rc = make_halo_tmap(h, &h->sb_tm_xb[nb - 1], h->act[0], a.filters, a.block_kernel, nb))) return rc;
     if ((rc = make_halo_tmap(h, &h->sb_tm_y[nb - 1], h->act[1], a.filters, a.block_kernel, nb))) return rc;
   }
@@ -588,9 +585,7 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   if (args.n_slots > caz::sb::MAX_W_SLOTS) args.n_slots = caz::sb::MAX_W_SLOTS;
   args.planes = d_planes;
   args.records = d_records;
-  args.in_act = static_cast<__nv_bfloat16*>(h->sb_in_act);
   args.bias_all = h->bias_all;
-  args.xf = static_cast<float*>(h->act[2]);
   args.xb = static_cast<__nv_bfloat16*>(h->act[0]);
   args.y = static_cast<__nv_bfloat16*>(h->act[1]);
   args.pf = a.policy_filters;
@@ -623,7 +618,7 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   args.err_flag = h->err_flag_dev;
   const int grid = ((batch + nb - 1) / nb) * slices;
   h->sb_epoch += (unsigned)(args.n_layers + caz::sb::FLAG_STEPS_EXTRA);
-  void* params[] = {&h->sb_tm_in[nb - 1], &h->sb_tm_xb[nb - 1], &h->sb_tm_y[nb - 1], &h->sb_tm_w_stem[wi], &h->sb_tm_w_tower[wi], &args};
+  void* params[] = {&h->sb_tm_xb[nb - 1], &h->sb_tm_y[nb - 1], &h->sb_tm_w_stem[wi], &h->sb_tm_w_tower[wi], &args};
   static const bool plain = getenv("CAZ_SB_PLAIN_LAUNCH") && atoi(getenv("CAZ_SB_PLAIN_LAUNCH")) != 0;
   cudaError_t e = plain ? cudaLaunchKernel(reinterpret_cast<const void*>(caz::sb::forward_sb_kernel), dim3(grid),
                                            dim3(caz::sb::THREADS), params, caz::sb::SMEM_BYTES, h->stream)
@@ -879,7 +874,6 @@ void caz_destroy(caz_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->w_stem) cudaFree(h->w_stem);
   if (h->sb_w_stem) cudaFree(h->sb_w_stem);
-  if (h->sb_in_act) cudaFree(h->sb_in_act);
   if (h->w_tower) cudaFree(h->w_tower);
   if (h->bias_all) cudaFree(h->bias_all);
   if (h->sb_counter) cudaFree(h->sb_counter);

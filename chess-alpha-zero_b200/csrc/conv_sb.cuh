@@ -1,32 +1,28 @@
-// Small-batch path: the WHOLE forward pass (input pack, stem, every residual conv, both heads) in ONE persistent,
+// Small-batch path: the WHOLE forward pass (input conversion, stem, every residual conv, both heads) in ONE persistent,
 // cooperatively launched kernel, for MCTS-sized batches (reference batches are <= 48 positions:
 // search_threads x max_processes, configs/normal.py:30-31).
 //
-// At batch 16 a forward pass is ~17 GFLOP -- nothing for the tensor cores -- but every layer needs the 1.18 MB
-// of its weights and has to wait for the previous layer: the pass is bound by latency and by L2->SM bandwidth.
-// So:
-//   * grid = (board pairs) x (output-channel slices): CTA (t, s) owns rows of boards 2t, 2t+1 and N_s = 256/S
-//     output channels in EVERY layer (batch 16: 8 x 16 = 128 CTAs, N_s = 16).  Its residual slice and its bias
-//     never leave the CTA; only the bf16 activations cross CTAs, through L2.
-//   * weights: the bf16 weight set (17.4 MB) is L2-resident; each CTA streams its [N_s x K] slice through a
-//     shared-memory ring with TMA, running AHEAD across layer boundaries (weights do not depend on the previous
-//     layer), so after the first layer the weight fetch is off the critical path.  A ring slot holds several
-//     filter taps, so the MMA warp waits once per slot and then issues its MMAs back to back.
-//   * activations: ONE zero-padded halo tile per 64-channel chunk, [10 ranks][2 boards][10 files][64 ch] (TMA box
+// At batch 16 a forward pass is ~17 GFLOP -- nothing for the tensor cores -- but every layer needs the 1.18 MB of its
+// weights and has to wait for the previous layer: the pass is bound by latency chains and by operand bandwidth.  So:
+//   * grid = (board tiles) x (output-channel slices): CTA (t, s) owns the rows of tile t (one board, M = 64, up to
+//     batch 16; two boards, M = 128, above) and N_s = 256/S output channels in EVERY layer.  Its slice of the fp32
+//     residual stream stays in the epilogue threads' registers; only 16-bit activations cross CTAs, through L2.
+//   * a tcgen05.mma at these shapes costs its operand reads from shared memory, (M + N) x 32 B at 128 B/cycle
+//     (tools/ub/ub_small.cu), IF the issuing thread keeps up: descriptors are hoisted, tap geometry is compile-time, two
+//     warps issue alternate 64-channel chunks into their own accumulators (4 TMEM column groups, added by the epilogue).
+//   * weights: the 16-bit weight set (17.4 MB) is L2-resident; each CTA streams its [N_s x K] slice through a
+//     shared-memory ring with TMA, running AHEAD across layer boundaries.
+//   * activations: ONE zero-padded halo tile per 64-channel chunk, [10 ranks][nb boards][10 files][64 ch] (TMA box
 //     with out-of-bounds fill), serves all nine taps: tap (dy, dx) is the same tile read through a UMMA descriptor
-//     whose start address is shifted by (20*dy + dx) rows and whose 8-row-group stride is 10 rows.  The 128-byte
-//     swizzle is a function of the shared-memory address, so the shifted view stays consistent with what TMA
-//     wrote.  Activation traffic per CTA and layer: 102 KB instead of 9 x 64 KB.
-//   * consecutive tcgen05.mma into one accumulator serialise; with N = 16..64 an MMA is far shorter than that
-//     latency, so the K loop rotates over NACC accumulators (TMEM column groups) that the epilogue adds up.
-//   * phases are separated by a grid barrier (one release-add + acquire-spin on an L2 counter; cooperative launch
-//     guarantees co-residency; the spin is bounded and traps instead of hanging).  (A cluster-per-board-pair
-//     variant with DSMEM mbarriers was measured slower: 16-CTA clusters do not all fit at once and the 16 CTAs of
-//     a cluster then pull the same activation tile through one GPC's port.)
-//   * the input pack runs as phase 0 and the heads as three SIMT phases after the tower (1x1 convs per row;
-//     policy logits / value hidden layer sliced over CTAs; softmax / tanh per position): no extra launches.
-//     Those phases run once per launch, i.e. from a cold instruction cache: their loops are kept rolled.
-// TMEM lane m of the accumulator is row (rank h = m>>4, board p = (m>>3)&1, file w = m&7).
+//     whose start address is shifted by (10*nb*dy + dx) rows and whose 8-row-group stride is 10 rows.  The stem's tile
+//     is built in place by the CTA itself from the fp32 planes / 68-byte records (no pack phase, no global round trip).
+//   * layers rendezvous per board tile through progress flags (L2 atomics, one polling thread, one acquire fence);
+//     every tile has a flag line on each die's L2 and polls the near one (see Args::flag_line).  Cooperative launch
+//     guarantees co-residency; every spin is bounded and traps instead of hanging.
+//   * heads per tile: head-conv partial sums from the last epilogue, Dense weights staged over the tower's tiles while
+//     it runs, softmax / value statistics exchanged through the tile's flags; canonical summation order, so outputs
+//     are bit-identical for every batch size.
+// TMEM lane m of an M = 128 accumulator is row (rank h = m>>4, board p = (m>>3)&1, file w = m&7).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -65,9 +61,7 @@ struct Args {
   int slot_bytes, n_slots;    // weight ring geometry
   const float* planes;        // fp32 [batch][in_planes][64] or nullptr
   const uint8_t* records;     // u8 [batch][68] or nullptr (exactly one of the two)
-  __nv_bfloat16* in_act;      // bf16 [batch][64][in_cpad]
   const float* bias_all;      // [n_layers][filters]
-  float* xf;                  // fp32 residual stream   [batch*64][filters]
   __nv_bfloat16* xb;          // bf16 copy of it         (A operand of conv1)
   __nv_bfloat16* y;           // bf16 conv1 output       (A operand of conv2)
   // heads (fp32)
@@ -251,7 +245,7 @@ __device__ __forceinline__ void issue_taps(uint64_t a_plane, uint64_t b_slot, in
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_xb,
+forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
                   const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_w_stem,
                   const __grid_constant__ CUtensorMap tm_w_tower, const Args args) {
   extern __shared__ uint8_t smem_raw[];
@@ -303,7 +297,6 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   }
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tm_in);
     ptx::prefetch_tmap(&tm_xb);
     ptx::prefetch_tmap(&tm_y);
     ptx::prefetch_tmap(&tm_w_stem);
@@ -398,7 +391,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
       const int kch = l == 0 ? args.stem_kchunks : args.filters / 64;
       const int hw = 8 + k - 1, pad = (k - 1) / 2;
       const int plane_bytes = hw * args.nb * hw * 128;
-      const CUtensorMap* tm = l == 0 ? &tm_in : ((l & 1) ? &tm_xb : &tm_y);
+      const CUtensorMap* tm = (l & 1) ? &tm_xb : &tm_y;   // layer 0 builds its tile in place, see above
       const unsigned target = args.base + static_cast<unsigned>(l);   // layers 0..l-1
       if (l == 0) {
         // the stem's tile was built in shared memory above (this warp took part and has passed its barrier)
