@@ -274,6 +274,26 @@ def test_small_batch_persistent_kernel(net_default):
         ev2.close()
 
 
+@pytest.mark.parametrize("precision,tol_p,tol_v", [("bf16", BF16_TOL, BF16_VALUE_TOL_REFERENCE_INIT), ("fp16", 4e-3, 4e-3)])
+def test_small_batch_kernel_records_masks_and_precisions(net_default, precision, tol_p, tol_v):
+    """The persistent kernel's other entrances: board records (its in-kernel encoder builds the stem tile), the
+    legal-move mask in its per-tile softmax, fp16 operands."""
+    from chess_alpha_zero_b200 import encoder
+    cfg, w, x, fens, (wp, wv) = net_default
+    ev = caz.Evaluator(cfg, w, precision=precision, max_batch=64)
+    for n in (5, 16, 24, 40):
+        p, v = ev.predict_on_batch(x[:n])
+        assert np.abs(p - wp[:n]).max() <= tol_p and np.abs(v - wv[:n]).max() <= tol_v
+        pr, vr = ev.predict_records(encoder.fens_to_records(fens[:n]))
+        assert np.array_equal(pr, p) and np.array_equal(vr, v)       # records in == planes in, bit for bit
+        masks = onet.synthetic_legal_masks(n, seed=n)
+        pm, vm = ev.predict_on_batch(x[:n], legal_mask=masks)
+        assert np.all(pm[masks == 0] == 0) and np.allclose(pm.sum(axis=1), 1, atol=1e-5) and np.array_equal(vm, v)
+        want = np.where(masks != 0, p, 0)
+        assert np.abs(pm - want / want.sum(axis=1, keepdims=True)).max() <= 1e-5
+    ev.close()
+
+
 def test_empty_batch_and_chunking(net, ev_bf16):
     p, v = ev_bf16.predict_on_batch(np.zeros((0, 18, 8, 8), np.float32))
     assert p.shape == (0, 1968) and v.shape == (0, 1)
