@@ -1059,6 +1059,15 @@ static int enqueue_pipelined(caz_handle* h, int slot, const float* planes, const
   return CAZ_OK;
 }
 
+// Device-side alias of a caller buffer if it is pinned, mapped host memory (what caz_host_alloc returns), else nullptr.
+// Asked on every call (~1 us): an address can change hands between a pinned and a pageable allocation.
+static void* mapped_alias(const void* host) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost) return at.devicePointer;
+  cudaGetLastError();
+  return nullptr;
+}
+
 static int eval_host(caz_handle* h, const float* planes, const uint8_t* records, int32_t batch, float* policy,
                      float* value, const uint8_t* legal_mask, uint32_t flags) {
   if (!h) return CAZ_ERR_INVALID;
@@ -1077,9 +1086,21 @@ static int eval_host(caz_handle* h, const float* planes, const uint8_t* records,
     if (planes) CU_TRY(h, cudaMemcpyAsync(h->d_planes, planes, (size_t)batch * pin * 4, cudaMemcpyHostToDevice, h->stream));
     else CU_TRY(h, cudaMemcpyAsync(h->d_records, records, (size_t)batch * CAZ_RECORD_BYTES, cudaMemcpyHostToDevice, h->stream));
     if (masked) CU_TRY(h, cudaMemcpyAsync(h->d_mask, legal_mask, (size_t)batch * a.n_labels, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = forward(h, planes ? h->d_planes : nullptr, planes ? nullptr : h->d_records, batch, h->d_policy, h->d_value, masked ? h->d_mask : nullptr))) return rc;
-    CU_TRY(h, cudaMemcpyAsync(policy, h->d_policy, (size_t)batch * a.n_labels * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(value, h->d_value, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
+    // MCTS-sized batches whose outputs are pinned + mapped: the persistent kernel stores policy and value straight into
+    // the caller's memory (posted PCIe writes under the kernel's tail) instead of two device-to-host copies after it.
+    float* dpol = h->d_policy;
+    float* dval = h->d_value;
+    bool direct = false;
+    if (tensor_path(h) && use_small_batch(h, batch) && !getenv("CAZ_NO_DIRECT_OUTPUT")) {
+      void* ap = mapped_alias(policy);
+      void* av = mapped_alias(value);
+      if (ap && av) { dpol = static_cast<float*>(ap); dval = static_cast<float*>(av); direct = true; }
+    }
+    if ((rc = forward(h, planes ? h->d_planes : nullptr, planes ? nullptr : h->d_records, batch, dpol, dval, masked ? h->d_mask : nullptr))) return rc;
+    if (!direct) {
+      CU_TRY(h, cudaMemcpyAsync(policy, h->d_policy, (size_t)batch * a.n_labels * 4, cudaMemcpyDeviceToHost, h->stream));
+      CU_TRY(h, cudaMemcpyAsync(value, h->d_value, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return CAZ_OK;
   }
