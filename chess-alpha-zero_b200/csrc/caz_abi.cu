@@ -1083,7 +1083,11 @@ static int eval_host(caz_handle* h, const float* planes, const uint8_t* records,
     // One pass on one stream, no cross-stream events: the latency path.  (Cutting a batch into pipelined chunks was
     // measured: the smaller launches lose what the copy overlap gains; overlap ACROSS calls is caz_submit/caz_collect.)
     CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_out[0], 0));   // a still-draining caz_submit on slot 0
+    // (same for board records in pinned + mapped memory: 68 bytes per board, read by the kernel itself)
+    const bool sb_direct = tensor_path(h) && use_small_batch(h, batch) && !getenv("CAZ_NO_DIRECT_OUTPUT");
+    const uint8_t* drec = h->d_records;
     if (planes) CU_TRY(h, cudaMemcpyAsync(h->d_planes, planes, (size_t)batch * pin * 4, cudaMemcpyHostToDevice, h->stream));
+    else if (sb_direct && (reinterpret_cast<uintptr_t>(records) & 3) == 0 && mapped_alias(records)) drec = static_cast<const uint8_t*>(mapped_alias(records));
     else CU_TRY(h, cudaMemcpyAsync(h->d_records, records, (size_t)batch * CAZ_RECORD_BYTES, cudaMemcpyHostToDevice, h->stream));
     if (masked) CU_TRY(h, cudaMemcpyAsync(h->d_mask, legal_mask, (size_t)batch * a.n_labels, cudaMemcpyHostToDevice, h->stream));
     // MCTS-sized batches whose outputs are pinned + mapped: the persistent kernel stores policy and value straight into
@@ -1091,12 +1095,12 @@ static int eval_host(caz_handle* h, const float* planes, const uint8_t* records,
     float* dpol = h->d_policy;
     float* dval = h->d_value;
     bool direct = false;
-    if (tensor_path(h) && use_small_batch(h, batch) && !getenv("CAZ_NO_DIRECT_OUTPUT")) {
+    if (sb_direct) {
       void* ap = mapped_alias(policy);
       void* av = mapped_alias(value);
       if (ap && av) { dpol = static_cast<float*>(ap); dval = static_cast<float*>(av); direct = true; }
     }
-    if ((rc = forward(h, planes ? h->d_planes : nullptr, planes ? nullptr : h->d_records, batch, dpol, dval, masked ? h->d_mask : nullptr))) return rc;
+    if ((rc = forward(h, planes ? h->d_planes : nullptr, planes ? nullptr : drec, batch, dpol, dval, masked ? h->d_mask : nullptr))) return rc;
     if (!direct) {
       CU_TRY(h, cudaMemcpyAsync(policy, h->d_policy, (size_t)batch * a.n_labels * 4, cudaMemcpyDeviceToHost, h->stream));
       CU_TRY(h, cudaMemcpyAsync(value, h->d_value, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));

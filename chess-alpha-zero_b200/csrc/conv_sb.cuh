@@ -263,6 +263,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   __shared__ __align__(16) float s_hw[HEAD_FILTERS_MAX * 64];   // this slice's columns of the 1x1 head convolutions
   __shared__ __align__(16) float s_feat[2 * 512];               // head-conv outputs of this tile's boards (Flatten order)
   __shared__ float s_red[64];
+  __shared__ uint32_t s_rec[2 * 17];                            // this tile's board records (68 bytes each)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // which CTA takes which (tile, slice): consecutive block ids go to different GPCs (classic placement), so
@@ -335,6 +336,12 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     const int rows = hw * args.nb * hw;
     uint4* tile16 = reinterpret_cast<uint4*>(smem_a);
     for (int i = t; i < rows * 8; i += nthr) tile16[i] = make_uint4(0u, 0u, 0u, 0u);
+    // board records are fetched once (17 words per board; they may live in the caller's pinned host memory) and decoded
+    // from shared memory
+    if (args.records && t < args.nb * 17) {
+      const int p = t / 17, wd = t - p * 17;
+      s_rec[p * 17 + wd] = n0 + p < args.batch ? reinterpret_cast<const uint32_t*>(args.records + static_cast<size_t>(n0 + p) * 68)[wd] : 0u;
+    }
     asm volatile("bar.sync 2, 224;" ::: "memory");
     const int per_board = args.in_planes * 64;
     for (int i = t; i < args.nb * per_board; i += nthr) {
@@ -343,7 +350,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       const int b = n0 + p;
       if (b >= args.batch) continue;
       const float v = args.planes ? args.planes[(static_cast<size_t>(b) * args.in_planes + c) * 64 + sq]
-                                  : record_plane_value(args.records + static_cast<size_t>(b) * 68, c, sq);
+                                  : record_plane_value(reinterpret_cast<const uint8_t*>(s_rec + p * 17), c, sq);
       const int row = ((sq >> 3) + pad) * args.nb * hw + p * hw + (sq & 7) + pad;
       const int off = row * 128 + (((c >> 3) ^ (row & 7)) << 4) + ((c & 7) << 1);
       *reinterpret_cast<uint16_t*>(smem_a + off) = ptx::pack_h16(v, args.fp16 != 0);

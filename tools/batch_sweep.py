@@ -62,8 +62,20 @@ def main():
             t0 = time.perf_counter()
             ev.predict_into(px.array, pp.array, pv.array)
             host.append((time.perf_counter() - t0) * 1e6)
+        # the same call from board records (68 B per position; the encoder runs inside the forward pass)
+        from chess_alpha_zero_b200 import encoder
+        from oracle import encoder as oenc
+        prec = _lib.PinnedArray((b, 68), np.uint8)
+        fens = oenc.synthetic_fens(256, seed=3)
+        prec.array[:] = encoder.fens_to_records([fens[i % 256] for i in range(b)])
+        pv1 = _lib.PinnedArray((b,), np.float32)
+        host_rec = []
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            ev.predict_records_into(prec.array, pp.array, pv1.array)
+            host_rec.append((time.perf_counter() - t0) * 1e6)
         print(json.dumps({"batch": b, "device_p50_us": float(np.median(dev)), "device_min_us": float(np.min(dev)),
-                          "host_call_p50_us": float(np.median(host)), "positions_per_s_back_to_back": thr,
+                          "host_call_p50_us": float(np.median(host)), "host_call_records_p50_us": float(np.median(host_rec)), "positions_per_s_back_to_back": thr,
                           "tflops": thr * bench.flops_per_position(args.blocks) / 1e12}), flush=True)
     ev.close()
 
