@@ -49,8 +49,10 @@ def conv3x3_flops_per_launch(batch, filters=256):
 
 def ncu_traffic_bytes(batch):
     """dram__bytes_read.sum + dram__bytes_write.sum per tower-conv launch from the committed ncu launch list
-    (profiles/r1_v6_launches.csv, batch 4096; mean over the conv1-type and conv2-type launches), else None."""
-    path = os.path.join(ROOT, "profiles", "r1_v6_launches.csv")
+    (profiles/r1_v11_launches.csv, batch 4096; mean over the conv1-type and conv2-type launches), else None."""
+    path = os.path.join(ROOT, "profiles", "r1_v11_launches.csv")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1_v6_launches.csv")
     if batch != 4096 or not os.path.exists(path):
         return None
     import csv
