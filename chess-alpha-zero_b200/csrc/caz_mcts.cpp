@@ -128,6 +128,18 @@ int64_t caz_mcts_drain_play_data(caz_mcts* m, uint8_t* buf, int64_t cap) {
   return need;
 }
 
+int caz_mcts_debug_dirichlet(uint64_t seed, double alpha, int32_t n, int32_t draws, double* out) {
+  if (!out || n < 1 || n > 256 || draws < 1 || alpha <= 0) return 1;
+  FastRng rng;
+  rng.seed(seed * 0x9E3779B97F4A7C15ull + 1);
+  for (int32_t d = 0; d < draws; ++d) {
+    double tot = 0.0;
+    for (int32_t i = 0; i < n; ++i) { out[(size_t)d * n + i] = rng.gamma(static_cast<float>(alpha)); tot += out[(size_t)d * n + i]; }
+    for (int32_t i = 0; i < n; ++i) out[(size_t)d * n + i] /= tot > 0 ? tot : 1.0;
+  }
+  return 0;
+}
+
 uint64_t caz_chess_perft(const char* fen, int32_t depth) {
   Position p;
   if (!fen || !p.from_fen(fen)) return 0;

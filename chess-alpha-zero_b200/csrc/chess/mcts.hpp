@@ -71,6 +71,59 @@ struct Request {
   int32_t path_begin, path_len;   // into Search::path_pool: (node, edge) pairs from the root down
 };
 
+// Per-game random numbers: xoshiro256++ with single-precision Gamma draws for the root's Dirichlet noise.  The reference
+// draws np.random.dirichlet([alpha] * n) afresh in EVERY root selection (player_chess.py:285-286), 800 times per move:
+// with std::gamma_distribution that was a third of the search's time.
+struct FastRng {
+  uint64_t s[4];
+  float spare = 0.0f;
+  bool has_spare = false;
+  void seed(uint64_t x) {
+    for (auto& w : s) {   // splitmix64
+      uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      w = z ^ (z >> 31);
+    }
+    has_spare = false;
+  }
+  static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+  uint64_t next() {
+    const uint64_t r = rotl(s[0] + s[3], 23) + s[0], t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+    s[2] ^= t;
+    s[3] = rotl(s[3], 45);
+    return r;
+  }
+  double uniform() { return static_cast<double>(next() >> 11) * (1.0 / 9007199254740992.0); }   // [0, 1)
+  float uniform_open() { return (static_cast<float>(next() >> 40) + 0.5f) * (1.0f / 16777216.0f); }  // (0, 1)
+  float normal() {   // Marsaglia's polar method, values in pairs
+    if (has_spare) { has_spare = false; return spare; }
+    for (;;) {
+      const float u = 2.0f * uniform_open() - 1.0f, v = 2.0f * uniform_open() - 1.0f, q = u * u + v * v;
+      if (q >= 1.0f || q == 0.0f) continue;
+      const float f = std::sqrt(-2.0f * std::log(q) / q);
+      spare = v * f;
+      has_spare = true;
+      return u * f;
+    }
+  }
+  // Gamma(alpha, 1): Marsaglia & Tsang (2000); for alpha < 1 the usual Gamma(alpha + 1) * U^(1/alpha)
+  float gamma(float alpha) {
+    const float a = alpha < 1.0f ? alpha + 1.0f : alpha;
+    const float d = a - 1.0f / 3.0f, c = 1.0f / std::sqrt(9.0f * d);
+    float g;
+    for (;;) {
+      const float x = normal(), t = 1.0f + c * x;
+      if (t <= 0.0f) continue;
+      const float v = t * t * t, u = uniform_open();
+      if (std::log(u) < 0.5f * x * x + d - d * v + d * std::log(v)) { g = d * v; break; }
+    }
+    if (alpha < 1.0f) g *= std::exp(std::log(uniform_open()) / alpha);
+    return g;
+  }
+};
+
 // state key -> node index, open addressing (a tree holds at most simulation_num_per_move + 1 nodes)
 class NodeIndex {
  public:
@@ -178,7 +231,7 @@ class WorkerPool {
 class GameSearch {
  public:
   Game game;
-  std::mt19937_64 rng;
+  FastRng rng;
   // the tree of the move being searched (ChessPlayer.reset() clears it for every move, player_chess.py:131)
   NodeIndex index;
   std::vector<Node> nodes;
@@ -277,17 +330,19 @@ class Mcts {
     double best_s = -999.0;
     int best = -1;
     double noise[256];
-    if (is_root && nd.n_edges > 0) {
+    const bool noisy = is_root && cfg.noise_eps != 0.0;   // with eps = 0 the draw cannot change the choice: skipped
+    if (noisy && nd.n_edges > 0) {
       // np.random.dirichlet([alpha] * n): independent Gamma(alpha, 1) draws, normalised -- a fresh draw per call (:285-286)
-      std::gamma_distribution<double> gamma(cfg.dirichlet_alpha, 1.0);
+      const float alpha = static_cast<float>(cfg.dirichlet_alpha);
       double tot = 0.0;
-      for (int i = 0; i < nd.n_edges; ++i) { noise[i] = gamma(gs.rng); tot += noise[i]; }
+      for (int i = 0; i < nd.n_edges; ++i) { noise[i] = gs.rng.gamma(alpha); tot += noise[i]; }
+      if (tot <= 0.0) tot = 1.0;
       for (int i = 0; i < nd.n_edges; ++i) noise[i] /= tot;
     }
     for (int i = 0; i < nd.n_edges; ++i) {
       const Edge& e = gs.edges[nd.first_edge + i];
       double p = e.p;
-      if (is_root) p = (1 - cfg.noise_eps) * p + cfg.noise_eps * noise[i];
+      if (noisy) p = (1 - cfg.noise_eps) * p + cfg.noise_eps * noise[i];
       const double b = e.q + cfg.c_puct * p * xx / (1 + e.n);
       if (b > best_s) { best_s = b; best = i; }
     }
@@ -499,8 +554,7 @@ class Mcts {
       } else {
         double sum = 0.0;
         for (auto& x : pol) { x = std::pow(x, 1 / tau); sum += x; }
-        std::uniform_real_distribution<double> uni(0.0, 1.0);
-        const double u = uni(gs.rng) * sum;
+        const double u = gs.rng.uniform() * sum;
         double acc = 0.0;
         action = -1;
         int last_nonzero = 0;

@@ -18,7 +18,7 @@ RECORD_BYTES = 68
 SYMBOLS = (
     "caz_mcts_create", "caz_mcts_destroy", "caz_mcts_collect", "caz_mcts_apply", "caz_mcts_get_stats",
     "caz_mcts_set_position", "caz_mcts_game_fen", "caz_mcts_game_result", "caz_mcts_root_edges",
-    "caz_mcts_drain_play_data", "caz_chess_perft",
+    "caz_mcts_drain_play_data", "caz_mcts_debug_dirichlet", "caz_chess_perft",
     "caz_chess_legal_moves", "caz_chess_play", "caz_chess_record",
 )
 
@@ -79,6 +79,7 @@ def load():
     lib.caz_mcts_root_edges.argtypes = [ctypes.c_void_p, ctypes.c_int32] + [ctypes.c_void_p] * 4 + [ctypes.c_int32]
     lib.caz_mcts_drain_play_data.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
     lib.caz_mcts_drain_play_data.restype = ctypes.c_int64
+    lib.caz_mcts_debug_dirichlet.argtypes = [ctypes.c_uint64, ctypes.c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
     lib.caz_chess_perft.argtypes = [ctypes.c_char_p, ctypes.c_int32]
     lib.caz_chess_perft.restype = ctypes.c_uint64
     lib.caz_chess_legal_moves.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32]
@@ -97,6 +98,14 @@ def move_label_table():
         promo = "?nbrq".index(lab[4]) if len(lab) > 4 else 0
         t[(f * 64 + to) * 5 + promo] = i
     return t
+
+
+def dirichlet_draws(seed, alpha, n, draws):
+    """`draws` samples of the root noise Dirichlet([alpha] * n) from the search's generator (test hook)."""
+    out = np.zeros((draws, n), np.float64)
+    if load().caz_mcts_debug_dirichlet(seed, alpha, n, draws, out.ctypes.data_as(ctypes.c_void_p)):
+        raise ValueError("bad arguments")
+    return out
 
 
 # ---- chess rules (tests, tools) ------------------------------------------------------------------------------

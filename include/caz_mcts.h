@@ -79,6 +79,10 @@ int caz_mcts_root_edges(const caz_mcts* m, int32_t game, int32_t* label, int32_t
  * pending data needs; if that exceeds cap nothing is copied and nothing is dropped. */
 int64_t caz_mcts_drain_play_data(caz_mcts* m, uint8_t* buf, int64_t cap);
 
+/* Test hook: `draws` samples of the root's Dirichlet([alpha] * n) noise from the search's own generator (row major
+ * [draws][n], float64), seeded like game 0 of a search created with `seed`. */
+int caz_mcts_debug_dirichlet(uint64_t seed, double alpha, int32_t n, int32_t draws, double* out);
+
 /* ---- the chess rules underneath (tests pin them with published perft counts) ---- */
 uint64_t caz_chess_perft(const char* fen, int32_t depth);
 /* legal moves in python-chess generation order, space separated UCI; returns the move count, -1 if buf too small */

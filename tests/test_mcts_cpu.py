@@ -237,3 +237,18 @@ def test_play_data_rows_match_the_reference_format():
         for fen, _, z in chunk:
             assert z == (want_white if fen.split()[1] == "w" else -want_white)
     s.close()
+
+
+def test_root_noise_is_dirichlet():
+    """np.random.dirichlet([0.3] * n) (player_chess.py:285-286) from the search's own fast generator: moments of
+    Dirichlet(alpha, ..., alpha): mean 1/n, variance (n - 1) / (n^2 (n alpha + 1)); marginals are Beta(alpha, (n-1) alpha)."""
+    n, alpha = 30, 0.3
+    x = mcts.dirichlet_draws(7, alpha, n, 200000)
+    assert np.allclose(x.sum(1), 1.0, atol=1e-12) and (x >= 0).all()
+    assert np.abs(x.mean(0) - 1.0 / n).max() < 6e-4
+    want_var = (n - 1) / (n * n * (n * alpha + 1))
+    assert np.abs(x.var(0) / want_var - 1).max() < 0.03
+    # the spiky shape that matters for exploration: P(x_i > 0.2) for Beta(0.3, 8.7)
+    from scipy import stats
+    assert abs((x[:, 0] > 0.2).mean() - stats.beta.sf(0.2, alpha, (n - 1) * alpha)) < 2e-3
+    assert not np.array_equal(mcts.dirichlet_draws(8, alpha, n, 4), x[:4])
