@@ -154,7 +154,7 @@ __device__ __forceinline__ void wait_tile(const Args& args, const unsigned* tile
     if (behind >= 0) break;
     if (++spins > (1u << 24)) sync_trap(args);
   }
-  if (!(args.dbg & 1)) ptx::fence_acq_rel_gpu();
+  if (!(args.dbg & 1)) ptx::fence_acq_rel_gpu();   // (dbg bit 0: measured cost of this fence, 2.4 us per pass)
 }
 
 __device__ __forceinline__ unsigned* tile_flag_line(const Args& args, int copy, int tile) {

@@ -150,6 +150,11 @@ __device__ __forceinline__ float ld_cg_f32(const float* p) {
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint4 ld_acquire_gpu_v4(const unsigned* p) {
+  uint4 v;
+  asm volatile("ld.acquire.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 // relaxed add: the caller has already fenced its (and, through a CTA barrier, its CTA's) stores at gpu scope
 __device__ __forceinline__ void red_relaxed_gpu_add(unsigned* p, unsigned v) {
