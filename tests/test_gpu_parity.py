@@ -294,6 +294,26 @@ def test_small_batch_kernel_records_masks_and_precisions(net_default, precision,
     ev.close()
 
 
+def test_full_size_batch_properties(net):
+    """BASELINE's full size (batch 4096 on one GPU), through size-independent properties: every 256-position block of a
+    4096 batch is bit-identical to the 256-position evaluation that is checked against the oracle above; rows are
+    probability vectors; values are tanh outputs; a permuted batch gives the permuted result."""
+    cfg, w, x, fens, (wp, wv) = net
+    ev = caz.Evaluator(cfg, w, precision="bf16", max_batch=4096)
+    base_p, base_v = ev.predict_on_batch(x)
+    assert np.abs(base_p - wp).max() <= BF16_TOL
+    big = np.ascontiguousarray(np.tile(x, (16, 1, 1, 1)))
+    p, v = ev.predict_on_batch(big)
+    assert p.shape == (4096, 1968) and v.shape == (4096, 1)
+    for blk in range(16):
+        assert np.array_equal(p[blk * 256:(blk + 1) * 256], base_p) and np.array_equal(v[blk * 256:(blk + 1) * 256], base_v)
+    assert np.allclose(p.sum(axis=1), 1.0, atol=1e-5) and (p >= 0).all() and (np.abs(v) < 1).all()
+    perm = np.random.default_rng(0).permutation(4096)
+    pp, pv = ev.predict_on_batch(np.ascontiguousarray(big[perm]))
+    assert np.array_equal(pp, p[perm]) and np.array_equal(pv, v[perm])
+    ev.close()
+
+
 def test_empty_batch_and_chunking(net, ev_bf16):
     p, v = ev_bf16.predict_on_batch(np.zeros((0, 18, 8, 8), np.float32))
     assert p.shape == (0, 1968) and v.shape == (0, 1)
