@@ -152,7 +152,20 @@ def dist_setup(n_gpus):
         if backend == "nccl":
             torch.cuda.set_device(local)
         kw = {"device_id": torch.device("cuda", local)} if backend == "nccl" else {}
-        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+        # NCCL writes its banner ("NCCL version ...") to stdout when the communicator comes up; stdout carries exactly
+        # one JSON line, so the rendezvous and a first barrier run with fd 1 pointed at stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+            dist.barrier()
+            if backend == "nccl":
+                torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     return world, rank, local
 
 
