@@ -96,6 +96,8 @@ def run(ev, games=256, sims=800, search_threads=16, seconds=20.0, groups=2, host
         "per_round_ms": {k: 1e3 * sum(a[k] for a in acc) / max(1, rounds) for k in ("collect", "eval", "apply")},
         "moves_played": tot["moves_played"], "games_finished": tot["games_finished"],
         "terminal_hits": tot["terminal_hits"], "withdrawn": tot["withdrawn"],
+        "results": {k: tot[k] for k in ("white_wins", "black_wins", "draws", "resignations", "adjudications")},
+        "games_per_hour_measured": tot["games_finished"] / wall * 3600,
         "moves_per_hour": tot["moves_played"] / wall * 3600,
         "games_per_hour_at_80_moves": tot["moves_played"] / wall * 3600 / moves_per_game,
     }
