@@ -123,9 +123,17 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def synthetic_batch(batch, seed):
-    """Seeded legal-looking positions through the oracle's generator and this repo's own encoder path
-    (records -> planes is what the product does; planes are what predict_on_batch receives)."""
+def synthetic_batch(batch, seed, ev):
+    """Seeded legal-looking positions, encoded by the product itself: FEN -> 68-byte records on the host, records ->
+    input planes by the encoder kernel of evaluator `ev` (planes are what predict_on_batch receives)."""
+    from chess_alpha_zero_b200 import encoder
+    base = ev.encode(encoder.fens_to_records(encoder.synthetic_fens(256, seed=seed)))
+    reps = (batch + 255) // 256
+    return np.ascontiguousarray(np.tile(base, (reps, 1, 1, 1))[:batch])
+
+
+def synthetic_batch_oracle(batch, seed):
+    """The same kind of input for the CPU-only reference arm (no GPU in that process): oracle generator and encoder."""
     from oracle import encoder as oenc
     base = np.stack([oenc.canon_input_planes(f) for f in oenc.synthetic_fens(256, seed=seed)])
     reps = (batch + 255) // 256
@@ -216,7 +224,7 @@ def run_reference(args, world, rank):
     torch.set_num_threads(cores)
     cfg, weights = network(args.blocks)
     sample_n = 256
-    planes = synthetic_batch(sample_n, seed=11)
+    planes = synthetic_batch_oracle(sample_n, seed=11)
     for _ in range(args.warmup):
         onet.forward_graph(cfg, weights, planes)
     t0 = time.perf_counter()
@@ -304,7 +312,7 @@ def main():
 
     # inputs: NBUF distinct device batches (> L2 together with the 0.7 GB of activations a step streams)
     NBUF = 8
-    host_batches = [synthetic_batch(B, seed=100 + rank * NBUF + i) for i in range(2)]
+    host_batches = [synthetic_batch(B, seed=100 + rank * NBUF + i, ev=ev) for i in range(2)]
     d_in = [torch.from_numpy(host_batches[i % 2]).cuda() for i in range(NBUF)]
     d_pol = torch.empty((B, ev.n_labels), dtype=torch.float32, device="cuda")
     d_val = torch.empty((B,), dtype=torch.float32, device="cuda")

@@ -52,3 +52,28 @@ def fens_to_records(fens):
     for i, fen in enumerate(fens):
         fen_to_record(fen, recs[i])
     return recs
+
+
+def synthetic_fens(n, seed=0):
+    """Seeded legal-looking FENs for benchmarks: 4-32 pieces on distinct squares, random castling subset,
+    halfmove clock U{0..99}, ~10 % with an en-passant square, 50 % black to move."""
+    rng = np.random.RandomState(seed)
+    pool = list("QRRBBNNPPPPPPPP") + list("qrrbbnnpppppppp")
+    fens = []
+    for _ in range(n):
+        count = int(rng.randint(4, 33))
+        chars = ["K", "k"] + [pool[i] for i in rng.permutation(len(pool))[: count - 2]]
+        board = ["."] * 64
+        for sq, c in zip(rng.permutation(64)[: len(chars)], chars):
+            board[sq] = c
+        rows = []
+        for r in range(8):
+            row = "".join(board[r * 8:r * 8 + 8])
+            for run in range(8, 0, -1):
+                row = row.replace("." * run, str(run))
+            rows.append(row)
+        side = "b" if rng.rand() < 0.5 else "w"
+        castling = "".join(c for c in "KQkq" if rng.rand() < 0.5) or "-"
+        ep = "abcdefgh"[rng.randint(8)] + ("6" if side == "w" else "3") if rng.rand() < 0.1 else "-"
+        fens.append(f"{'/'.join(rows)} {side} {castling} {ep} {int(rng.randint(0, 100))} {int(rng.randint(1, 120))}")
+    return fens

@@ -29,7 +29,7 @@ def main():
     ev = caz.Evaluator(cfg, weights, precision="bf16", max_batch=max(batches))
     ev.set_small_batch_limit(args.small_limit)
     stream = torch.cuda.ExternalStream(ev.stream)
-    planes = bench.synthetic_batch(max(batches), seed=3)
+    planes = bench.synthetic_batch(max(batches), seed=3, ev=ev)
     d_x = torch.from_numpy(planes).cuda()
     d_p = torch.empty((max(batches), 1968), dtype=torch.float32, device="cuda")
     d_v = torch.empty((max(batches),), dtype=torch.float32, device="cuda")
@@ -64,9 +64,8 @@ def main():
             host.append((time.perf_counter() - t0) * 1e6)
         # the same call from board records (68 B per position; the encoder runs inside the forward pass)
         from chess_alpha_zero_b200 import encoder
-        from oracle import encoder as oenc
         prec = _lib.PinnedArray((b, 68), np.uint8)
-        fens = oenc.synthetic_fens(256, seed=3)
+        fens = encoder.synthetic_fens(256, seed=3)
         prec.array[:] = encoder.fens_to_records([fens[i % 256] for i in range(b)])
         pv1 = _lib.PinnedArray((b,), np.float32)
         host_rec = []

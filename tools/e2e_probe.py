@@ -10,7 +10,7 @@ from chess_alpha_zero_b200 import _lib
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 cfg, weights = bench.network(7)
 ev = caz.Evaluator(cfg, weights, precision="bf16", max_batch=B)
-x = bench.synthetic_batch(B, seed=1)
+x = bench.synthetic_batch(B, seed=1, ev=ev)
 px, pp, pv = _lib.PinnedArray((B, 18, 8, 8), np.float32), _lib.PinnedArray((B, 1968), np.float32), _lib.PinnedArray((B, 1), np.float32)
 px.array[:] = x
 for _ in range(10): ev.predict_into(px.array, pp.array, pv.array)

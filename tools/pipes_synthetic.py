@@ -72,7 +72,7 @@ def main():
         while total() == 0:
             time.sleep(0.1)
     else:
-        planes = bench.synthetic_batch(256, seed=5)
+        planes = bench.synthetic_batch(256, seed=5, ev=model.model)
         stop = threading.Event()
         counts = [0] * n
         ts = [threading.Thread(target=client_loop, args=(i, p, planes, counts, stop), daemon=True)

@@ -10,7 +10,7 @@ from chess_alpha_zero_b200 import _lib
 b = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 cfg, weights = bench.network(7)
 ev = caz.Evaluator(cfg, weights, precision="bf16", max_batch=64)
-planes = bench.synthetic_batch(64, seed=3)
+planes = bench.synthetic_batch(64, seed=3, ev=ev)
 d_x = torch.from_numpy(planes).cuda(); d_p = torch.empty((64, 1968), device="cuda"); d_v = torch.empty((64,), device="cuda")
 for _ in range(5): ev.eval_device(d_x.data_ptr(), b, d_p.data_ptr(), d_v.data_ptr())
 lib = _lib.load()

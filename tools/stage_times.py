@@ -12,7 +12,7 @@ limit = int(sys.argv[2]) if len(sys.argv) > 2 else -1
 cfg, weights = bench.network(7)
 ev = caz.Evaluator(cfg, weights, precision="bf16", max_batch=max(batches))
 ev.set_small_batch_limit(limit)
-planes = bench.synthetic_batch(max(batches), seed=3)
+planes = bench.synthetic_batch(max(batches), seed=3, ev=ev)
 d_x = torch.from_numpy(planes).cuda()
 d_p = torch.empty((max(batches), 1968), dtype=torch.float32, device="cuda")
 d_v = torch.empty((max(batches),), dtype=torch.float32, device="cuda")
