@@ -35,12 +35,22 @@ int caz_mcts_create(const caz_mcts_config* c, int32_t n_games, uint64_t seed, co
   m.max_game_length = c->max_game_length;
   m.n_labels = c->n_labels;
   m.record_play_data = c->record_play_data;
-  caz_mcts* h = new (std::nothrow) caz_mcts;
-  if (!h) return 2;
-  h->impl = new Mcts(m, n_games, seed, move_label, unflipped_index, n_threads);
-  h->impl->continuous = c->continuous != 0;
-  *out = h;
-  return 0;
+  // no exception may cross the C boundary: allocation or thread-creation failures become status 2
+  try {
+    caz_mcts* h = new caz_mcts;
+    h->impl = nullptr;
+    try {
+      h->impl = new Mcts(m, n_games, seed, move_label, unflipped_index, n_threads);
+    } catch (...) {
+      delete h;
+      throw;
+    }
+    h->impl->continuous = c->continuous != 0;
+    *out = h;
+    return 0;
+  } catch (...) {
+    return 2;
+  }
 }
 
 void caz_mcts_destroy(caz_mcts* m) {
@@ -52,14 +62,23 @@ void caz_mcts_destroy(caz_mcts* m) {
 int caz_mcts_collect(caz_mcts* m, uint8_t* records, int32_t capacity, int32_t* n_leaves) {
   if (!m || !records || !n_leaves) return 1;
   int n = 0;
-  const int rc = m->impl->collect(records, capacity, &n);
+  int rc;
+  try {
+    rc = m->impl->collect(records, capacity, &n);
+  } catch (...) {
+    rc = 2;
+  }
   *n_leaves = n;
   return rc;
 }
 
 int caz_mcts_apply(caz_mcts* m, const float* policy, const float* value, int32_t n) {
   if (!m || (n > 0 && (!policy || !value))) return 1;
-  return m->impl->apply(policy, value, n);
+  try {
+    return m->impl->apply(policy, value, n);
+  } catch (...) {
+    return 2;
+  }
 }
 
 int caz_mcts_get_stats(const caz_mcts* m, caz_mcts_stats* out) {

@@ -11,7 +11,8 @@
  * (include/caz_b200.h), so one round of the search for ALL games is
  *     caz_mcts_collect(m, records, cap, &n);  caz_eval_records(h, records, n, policy, value, NULL, 0);
  *     caz_mcts_apply(m, policy, value, n);
- * Plain C types, int status codes (0 = ok), caller-owned buffers.
+ * Plain C types, int status codes (0 = ok, 1 = bad argument or call order, 2 = out of memory / threads), caller-owned
+ * buffers, no exception crosses the boundary.  One caller thread per caz_mcts object; the object runs its own workers.
  */
 #ifndef CAZ_MCTS_H
 #define CAZ_MCTS_H
