@@ -522,15 +522,28 @@ int setup_small_batch(caz_handle* h) {
   if ((rc = calibrate_flag_copies(h))) return rc;
   CU_TRY(h, cudaMalloc(&h->sb_trace, (1024 + 16 * 256 * 2) * sizeof(long long)));
   CU_TRY(h, cudaMemset(h->sb_trace, 0, (1024 + 16 * 256 * 2) * sizeof(long long)));
-  CU_TRY(h, cudaFuncSetAttribute(caz::sb::forward_sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::sb::SMEM_BYTES));
+  CU_TRY(h, cudaFuncSetAttribute(caz::sb::forward_sb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::sb::SMEM_BYTES));
+  CU_TRY(h, cudaFuncSetAttribute(caz::sb::forward_sb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::sb::SMEM_BYTES));
   h->sb_ok = true;
   return CAZ_OK;
 }
 
 // Grid geometry for a batch: boards per CTA tile (1 -> M = 64 MMAs, 2 -> M = 128) and output-channel slices, such that
 // every CTA is co-resident.
-bool sb_geometry(const caz_handle* h, int batch, int* nb_out, int* slices_out) {
+bool sb_geometry(const caz_handle* h, int batch, int* nb_out, int* slices_out, int* pair_out = nullptr) {
   if (!h->sb_ok) return false;
+  if (pair_out) *pair_out = 0;
+  // 9-18 boards: CTA pairs (cta_group::2, one board per CTA, a 32-channel slice per pair).  Per MMA a CTA reads 2.5 KB of
+  // operands instead of 3 KB and stages half of the slice's weights; below 9 boards the 16-channel
+  // slices of the unpaired form move the same bytes with twice the CTAs.
+  if (batch >= 9 && batch <= 18 && !h->sb_force_nb && !getenv("CAZ_SB_NO_PAIRS") && h->arch.filters % 32 == 0 &&
+      h->arch.filters / 32 <= 16 && ((batch + 1) / 2) * (h->arch.filters / 32) * 2 <= h->num_sms &&
+      caz::sb::heads_fit(h->arch.policy_filters, h->arch.value_filters, h->arch.n_labels, h->arch.value_fc, h->arch.filters / 32)) {
+    *nb_out = 1;
+    *slices_out = h->arch.filters / 32;
+    if (pair_out) *pair_out = 1;
+    return true;
+  }
   for (int pass = 0; pass < 2; ++pass)
     for (int nb = 1; nb <= 2; ++nb) {
       if (h->sb_force_nb && nb != h->sb_force_nb) continue;
@@ -560,13 +573,15 @@ bool use_small_batch(const caz_handle* h, int batch) {
 int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_records, int batch, float* d_policy,
                          float* d_value, const uint8_t* d_mask) {
   const caz_arch& a = h->arch;
-  int nb = 2, slices = 4;
-  sb_geometry(h, batch, &nb, &slices);
+  int nb = 2, slices = 4, pair = 0;
+  sb_geometry(h, batch, &nb, &slices, &pair);
   const int ns = a.filters / slices;
-  const int wi = ns == 16 ? 0 : (ns == 32 ? 1 : 2);
+  const int ns_cta = pair ? ns / 2 : ns;   // weight rows one CTA stages
+  const int wi = ns_cta == 16 ? 0 : (ns_cta == 32 ? 1 : 2);
   caz::sb::Args args;
   args.batch = batch;
   args.nb = nb;
+  args.pair = pair;
   args.n_layers = 1 + 2 * a.res_blocks;
   args.ns = ns;
   args.n_slices = slices;
@@ -578,8 +593,8 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   args.in_cpad = 64;
   args.fp16 = is_fp16(h) ? 1 : 0;
   { const char* e = getenv("CAZ_SB_DBG"); args.dbg = e ? atoi(e) : 0; }
-  const int sb_stem = caz::sb::taps_per_slot(a.stem_kernel, ns) * ns * 128;
-  const int sb_blk = a.res_blocks > 0 ? caz::sb::taps_per_slot(a.block_kernel, ns) * ns * 128 : 0;
+  const int sb_stem = caz::sb::taps_per_slot(a.stem_kernel, ns_cta) * ns_cta * 128;
+  const int sb_blk = a.res_blocks > 0 ? caz::sb::taps_per_slot(a.block_kernel, ns_cta) * ns_cta * 128 : 0;
   args.slot_bytes = sb_stem > sb_blk ? sb_stem : sb_blk;
   args.n_slots = caz::sb::W_RING_BYTES / args.slot_bytes;
   if (args.n_slots > caz::sb::MAX_W_SLOTS) args.n_slots = caz::sb::MAX_W_SLOTS;
@@ -616,14 +631,25 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   args.base = h->sb_epoch;
   args.trace = (h->sb_trace_on && args.n_layers <= 64) ? h->sb_trace : nullptr;
   args.err_flag = h->err_flag_dev;
-  const int grid = ((batch + nb - 1) / nb) * slices;
+  const int grid = pair ? ((batch + 1) / 2) * slices * 2 : ((batch + nb - 1) / nb) * slices;
   h->sb_epoch += (unsigned)(args.n_layers + caz::sb::FLAG_STEPS_EXTRA);
   void* params[] = {&h->sb_tm_xb[nb - 1], &h->sb_tm_y[nb - 1], &h->sb_tm_w_stem[wi], &h->sb_tm_w_tower[wi], &args};
-  static const bool plain = getenv("CAZ_SB_PLAIN_LAUNCH") && atoi(getenv("CAZ_SB_PLAIN_LAUNCH")) != 0;
-  cudaError_t e = plain ? cudaLaunchKernel(reinterpret_cast<const void*>(caz::sb::forward_sb_kernel), dim3(grid),
-                                           dim3(caz::sb::THREADS), params, caz::sb::SMEM_BYTES, h->stream)
-                        : cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(caz::sb::forward_sb_kernel), dim3(grid),
-                                              dim3(caz::sb::THREADS), params, caz::sb::SMEM_BYTES, h->stream);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(caz::sb::THREADS);
+  cfg.dynamicSmemBytes = caz::sb::SMEM_BYTES;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeCooperative;   // every CTA co-resident: the kernel's rendezvous spin on each other
+  attrs[0].val.cooperative = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = pair ? 2 : 1;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = pair ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelExC(&cfg, pair ? reinterpret_cast<const void*>(caz::sb::forward_sb_kernel<true>)
+                                                 : reinterpret_cast<const void*>(caz::sb::forward_sb_kernel<false>), params);
   if (e != cudaSuccess) return fail(h, CAZ_ERR_CUDA, fmt("cooperative launch of forward_sb_kernel failed: %s", cudaGetErrorString(e)));
   h->launches++;
   return CAZ_OK;

@@ -50,7 +50,9 @@ struct Args {
   int batch;        // positions (<= MAX_BATCH)
   int n_layers;     // 1 + 2 * res_blocks
   int nb;           // boards per CTA tile: 2 (M = 128) or 1 (M = 64: half the A-operand bytes per MMA)
-  int ns;           // output channels per CTA (16, 32 or 64)
+  int ns;           // output channels per slice (16, 32 or 64)
+  int pair;         // 1: the two CTAs of a cluster share a slice (cta_group::2, M = 128: one board each, half of the
+                    //    slice's weights each); needs nb = 1 and ns >= 32
   int n_slices;     // filters / ns
   int filters;
   int stem_k, stem_kchunks;  // stem kernel size, input channel chunks (in_cpad / 64)
@@ -226,7 +228,18 @@ __device__ __forceinline__ void stage_head_weights(const Args& args, float* s_wp
 // the grid geometry -- so results are bit-identical across batch sizes.
 //   a_plane: A descriptor of the chunk's halo tile;  b_slot: B descriptor of the ring slot
 //   (dy0, dx0): filter position of the slot's first tap; rp8 = halo rows between ranks * 8 (descriptor units of 16 B)
-template <int K, int TPS>
+template <bool PAIR>
+__device__ __forceinline__ void mma_h16(uint32_t tm, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if constexpr (PAIR) ptx::mma_bf16_ss_2cta(tm, adesc, bdesc, idesc, accum);
+  else ptx::mma_bf16_ss(tm, adesc, bdesc, idesc, accum);
+}
+template <bool PAIR>
+__device__ __forceinline__ void commit_to(uint64_t* bar) {
+  if constexpr (PAIR) ptx::mma_commit_2cta(bar);   // arrives on the barrier at this offset in BOTH CTAs of the pair
+  else ptx::mma_commit(bar);
+}
+
+template <int K, int TPS, bool PAIR>
 __device__ __forceinline__ void issue_taps(uint64_t a_plane, uint64_t b_slot, int dy0, int dx0, uint64_t rp8,
                                            uint64_t tap_desc, uint32_t tm0, uint32_t tm1, uint32_t idesc, bool fresh) {
   const uint64_t a_row = a_plane + static_cast<uint64_t>(dy0) * rp8 + static_cast<uint64_t>(dx0 * 8);
@@ -237,13 +250,14 @@ __device__ __forceinline__ void issue_taps(uint64_t a_plane, uint64_t b_slot, in
                                         : a_row + static_cast<uint64_t>(t * 8);
     const uint64_t bdesc = b_slot + static_cast<uint64_t>(t) * tap_desc;
     const uint32_t accum = (t > 0 || !fresh) ? 1u : 0u;   // this issuer's first tap of a layer initialises its accumulators
-    ptx::mma_bf16_ss(tm0, adesc, bdesc, idesc, accum);
-    ptx::mma_bf16_ss(tm1, adesc + 2, bdesc + 2, idesc, accum);
-    ptx::mma_bf16_ss(tm0, adesc + 4, bdesc + 4, idesc, 1u);
-    ptx::mma_bf16_ss(tm1, adesc + 6, bdesc + 6, idesc, 1u);
+    mma_h16<PAIR>(tm0, adesc, bdesc, idesc, accum);
+    mma_h16<PAIR>(tm1, adesc + 2, bdesc + 2, idesc, accum);
+    mma_h16<PAIR>(tm0, adesc + 4, bdesc + 4, idesc, 1u);
+    mma_h16<PAIR>(tm1, adesc + 6, bdesc + 6, idesc, 1u);
   }
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
                   const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_w_stem,
@@ -260,6 +274,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   uint64_t* hw_full = acc_full + 2;              // [1] staged head weights
   uint64_t* tower_done = acc_full + 3;           // [1] the last layer's MMAs have completed (both issuers)
+  uint64_t* stem_ready = acc_full + 4;           // [1] the stem tile(s) built in place are complete (both CTAs of a pair)
   __shared__ __align__(16) float s_hw[HEAD_FILTERS_MAX * 64];   // this slice's columns of the 1x1 head convolutions
   __shared__ __align__(16) float s_feat[2 * 512];               // head-conv outputs of this tile's boards (Flatten order)
   __shared__ float s_red[64];
@@ -269,13 +284,18 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   // which CTA takes which (tile, slice): consecutive block ids go to different GPCs (classic placement), so
   // tile = id / n_slices spreads a tile over the GPCs, tile = id % n_tiles (dbg bit 1) keeps strides together
   const unsigned trace_cta = static_cast<unsigned>(args.dbg >> 8);   // which CTA writes the per-layer trace (debug)
-  const int n_tiles = gridDim.x / args.n_slices;
-  const int tile = (args.dbg & 2) ? blockIdx.x % n_tiles : blockIdx.x / args.n_slices;
-  const int slice = (args.dbg & 2) ? blockIdx.x / n_tiles : blockIdx.x % args.n_slices;
+  // pair mode: cluster c = blockIdx.x / 2 is (board pair c / n_slices, slice c % n_slices); its CTA `rank` takes board
+  // 2 * pair + rank and stages rows [rank * ns/2, +ns/2) of the slice's weights; rank 0 (the leader) issues the MMAs.
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile = PAIR ? (unit / args.n_slices) * 2 + static_cast<int>(rank) : unit / args.n_slices;
+  const int slice = unit % args.n_slices;
   const int n0 = tile * args.nb, col0 = slice * args.ns;
+  const int ns_cta = PAIR ? args.ns / 2 : args.ns;   // weight rows this CTA stages = TMEM columns per accumulator
   __shared__ int s_near_copy;   // which of the tile's two flag lines this SM polls (set by warp 3 during layer 0)
-  const int tap_bytes = args.ns * 128;
-  const uint32_t tmem_cols = static_cast<uint32_t>(NACC * args.ns);  // 128, 256 or 512: powers of two
+  const int tap_bytes = ns_cta * 128;
+  const uint32_t tmem_cols = static_cast<uint32_t>(NACC * ns_cta);  // 64 .. 512: powers of two
   const unsigned L = static_cast<unsigned>(args.n_layers);
   const HeadGeom hg = head_geom(args.n_labels, args.value_fc, args.n_slices);
   const int lab0 = slice * hg.upl * LABEL_UNIT;                         // this CTA's labels: [lab0, lab0 + lab_cnt)
@@ -312,15 +332,17 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     ptx::mbar_init(acc_full, 2);
     ptx::mbar_init(hw_full, 1);
     ptx::mbar_init(tower_done, 2);
+    ptx::mbar_init(stem_ready, PAIR ? 2 : 1);
     ptx::mbar_fence_init();
     ptx::fence_proxy_async();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, tmem_cols);
-    ptx::tmem_relinquish();
+    if constexpr (PAIR) { ptx::tmem_alloc_2cta(tmem_slot, tmem_cols); ptx::tmem_relinquish_2cta(); }
+    else { ptx::tmem_alloc(tmem_slot, tmem_cols); ptx::tmem_relinquish(); }
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -368,17 +390,27 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     for (int l = 0; l < args.n_layers; ++l) {
       const int k = l == 0 ? args.stem_k : args.blk_k;
       const int kch = l == 0 ? args.stem_kchunks : args.filters / 64;
-      const int tps = taps_per_slot(k, args.ns);
+      const int tps = taps_per_slot(k, ns_cta);
       const CUtensorMap* tm = l == 0 ? &tm_w_stem : &tm_w_tower;
-      const int row = (l == 0 ? 0 : (l - 1) * args.filters) + col0;
+      const int row = (l == 0 ? 0 : (l - 1) * args.filters) + col0 + static_cast<int>(rank) * ns_cta;
       for (int kc = 0; kc < kch; ++kc)
         for (int tap0 = 0; tap0 < k * k; tap0 += tps) {
           ptx::mbar_wait(&w_empty[slot], phase ^ 1, args.err_flag, ERR_W);
           if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(&w_full[slot], tps * tap_bytes);
-            for (int t = 0; t < tps; ++t)
-              ptx::tma_load_2d(smem_w + slot * args.slot_bytes + t * tap_bytes, tm, &w_full[slot],
-                               ((tap0 + t) * kch + kc) * 64, row);
+            if constexpr (!PAIR) {
+              ptx::mbar_expect_tx(&w_full[slot], tps * tap_bytes);
+              for (int t = 0; t < tps; ++t)
+                ptx::tma_load_2d(smem_w + slot * args.slot_bytes + t * tap_bytes, tm, &w_full[slot],
+                                 ((tap0 + t) * kch + kc) * 64, row);
+            } else {
+              // both CTAs' halves of the slot count on the LEADER's barrier; each CTA waits for its own slot to be free
+              // (the leader's tcgen05.commit arrives on w_empty in both CTAs)
+              if (leader) ptx::mbar_expect_tx(&w_full[slot], 2 * tps * tap_bytes);
+              const uint32_t bar0 = ptx::mapa_u32(&w_full[slot], 0);
+              for (int t = 0; t < tps; ++t)
+                ptx::tma_load_2d_2cta(smem_w + slot * args.slot_bytes + t * tap_bytes, tm, bar0,
+                                      ((tap0 + t) * kch + kc) * 64, row);
+            }
           }
           __syncwarp();
           if (++slot == args.n_slots) { slot = 0; phase ^= 1; }
@@ -404,7 +436,8 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
         // the stem's tile was built in shared memory above (this warp took part and has passed its barrier)
         if (lane == 0) {
           if (args.trace && blockIdx.x == trace_cta) args.trace[0] = clock64();
-          ptx::mbar_arrive(&a_full[0]);
+          if (leader) ptx::mbar_arrive(stem_ready);
+          else ptx::mbar_arrive_cluster(stem_ready, 0);   // release.cluster: this CTA's tile is complete
           // while layer 0 computes: which of the tile's two flag lines answers faster from this SM?  Publish a value
           // to this slice's scratch word of each line and time until a poll sees it (two rounds, best of each).
           unsigned best[2] = {0xffffffffu, 0xffffffffu};
@@ -430,32 +463,39 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
         ptx::fence_proxy_async_all();  // other CTAs' generic-proxy stores -> our async-proxy (TMA) reads
         if (args.trace && blockIdx.x == trace_cta) args.trace[l * 8 + 0] = clock64();
         for (int kc = 0; kc < kch; ++kc) {
-          ptx::mbar_expect_tx(&a_full[kc], plane_bytes);
-          ptx::tma_load_4d(smem_a + kc * plane_bytes, tm, &a_full[kc], kc * 64, -pad, n0, -pad);
+          if constexpr (!PAIR) {
+            ptx::mbar_expect_tx(&a_full[kc], plane_bytes);
+            ptx::tma_load_4d(smem_a + kc * plane_bytes, tm, &a_full[kc], kc * 64, -pad, n0, -pad);
+          } else {
+            // each CTA of the pair fetches its own board's tile when ITS tile group is ready; the bytes of both count
+            // on the leader's barrier
+            if (leader) ptx::mbar_expect_tx(&a_full[kc], 2 * plane_bytes);
+            ptx::tma_load_4d_2cta(smem_a + kc * plane_bytes, tm, ptx::mapa_u32(&a_full[kc], 0), kc * 64, -pad, n0, -pad);
+          }
         }
       }
       __syncwarp();
-      if (args.trace && blockIdx.x == trace_cta) {   // when did the layer's last activation plane land (debug only)
-        ptx::mbar_wait(&a_full[kch - 1], l == 0 ? 0u : (kch - 1 < args.stem_kchunks ? (l & 1) : ((l - 1) & 1)), args.err_flag, ERR_A);
+      if (args.trace && blockIdx.x == trace_cta && leader) {   // when did the layer's last activation plane land (debug only)
+        ptx::mbar_wait(&a_full[kch - 1], (l - 1) & 1, args.err_flag, ERR_A);   // plane's first TMA fill is layer 1's
         if (lane == 0) args.trace[l * 8 + 7] = clock64();
       }
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if ((warp == 1 || warp == 2) && leader) {   // (pair mode: the leader issues for both CTAs)
     // ============ MMA issuers (two warps: a tcgen05.mma costs its issuing thread ~60 cycles whatever its shape,
     // so with N = 16..64 the issue rate, not the tensor pipe, bounds a layer) ============
     const int which = warp - 1;
-    const uint32_t idesc = ptx::idesc_h16_f32(64 * args.nb, args.ns, args.fp16 != 0);
+    const uint32_t idesc = ptx::idesc_h16_f32(PAIR ? 128 : 64 * args.nb, args.ns, args.fp16 != 0);
     const uint64_t b_desc0 = desc_sw128(ptx::smem_u32(smem_w), 1024);
     const uint64_t tap_desc = static_cast<uint64_t>(tap_bytes >> 4);
     const uint64_t slot_desc = static_cast<uint64_t>(args.slot_bytes >> 4);
-    const uint32_t tm0 = tmem_base + static_cast<uint32_t>(2 * which * args.ns), tm1 = tm0 + static_cast<uint32_t>(args.ns);
+    const uint32_t tm0 = tmem_base + static_cast<uint32_t>(2 * which * ns_cta), tm1 = tm0 + static_cast<uint32_t>(ns_cta);
     int slot = 0;
     uint32_t phase = 0, a_phase = 0;
     uint64_t b_slot = b_desc0;
     for (int l = 0; l < args.n_layers; ++l) {
       const int k = l == 0 ? args.stem_k : args.blk_k;
       const int kch = l == 0 ? args.stem_kchunks : args.filters / 64;
-      const int tps = taps_per_slot(k, args.ns);
+      const int tps = taps_per_slot(k, ns_cta);
       const int hw = 8 + k - 1;
       const uint64_t plane_desc = static_cast<uint64_t>((hw * args.nb * hw * 128) >> 4);
       const uint64_t rp8 = static_cast<uint64_t>(args.nb * hw * 8);  // halo rows between consecutive ranks, x 128 B / 16
@@ -465,8 +505,13 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       const int shape = (k == 3 && tps == 9) ? 0 : (k == 3 && tps == 3) ? 1 : (k == 5 && tps == 5) ? 2 : 3;
       for (int kc = 0; kc < kch; ++kc, a_plane += plane_desc) {
         // plane kc completes once per layer that uses it (the stem may use fewer planes than the tower)
-        ptx::mbar_wait(&a_full[kc], (a_phase >> kc) & 1u, args.err_flag, ERR_MMA_A);
-        a_phase ^= 1u << kc;
+        if (l == 0) {
+          // the stem's tile was written by this CTA's (and, in pair mode, the peer's) threads, not by TMA
+          ptx::mbar_wait_cluster(stem_ready, 0, args.err_flag, ERR_MMA_A);
+        } else {
+          ptx::mbar_wait(&a_full[kc], (a_phase >> kc) & 1u, args.err_flag, ERR_MMA_A);
+          a_phase ^= 1u << kc;
+        }
         if (args.trace && blockIdx.x == trace_cta && lane == 0 && kc == 0 && which == 0) args.trace[l * 8 + 1] = clock64();
         if (args.trace && blockIdx.x == trace_cta && lane == 0 && kc == kch - 1 && which == 0) args.trace[l * 8 + 2] = clock64();
         int dy0 = 0, dx0 = 0;
@@ -475,16 +520,29 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
             ptx::mbar_wait(&w_full[slot], phase, args.err_flag, ERR_MMA_W);
             ptx::tcgen05_fence_after();
             if (ptx::elect_one()) {
-              if (shape == 0) issue_taps<3, 9>(a_plane, b_slot, 0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
-              else if (shape == 1) issue_taps<3, 3>(a_plane, b_slot, dy0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
-              else if (shape == 2) issue_taps<5, 5>(a_plane, b_slot, dy0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
-              else
-                for (int t = 0, dy = dy0, dx = dx0; t < tps; ++t) {
-                  issue_taps<1, 1>(a_plane, b_slot + static_cast<uint64_t>(t) * tap_desc, dy, dx, rp8, tap_desc, tm0, tm1, idesc,
-                                   fresh && t == 0);
-                  if (++dx == k) { dx = 0; ++dy; }
-                }
-              ptx::mma_commit(&w_empty[slot]);
+              if constexpr (!PAIR) {
+                if (shape == 0) issue_taps<3, 9, false>(a_plane, b_slot, 0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
+                else if (shape == 1) issue_taps<3, 3, false>(a_plane, b_slot, dy0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
+                else if (shape == 2) issue_taps<5, 5, false>(a_plane, b_slot, dy0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
+                else
+                  for (int t = 0, dy = dy0, dx = dx0; t < tps; ++t) {
+                    issue_taps<1, 1, false>(a_plane, b_slot + static_cast<uint64_t>(t) * tap_desc, dy, dx, rp8, tap_desc, tm0, tm1,
+                                            idesc, fresh && t == 0);
+                    if (++dx == k) { dx = 0; ++dy; }
+                  }
+                ptx::mma_commit(&w_empty[slot]);
+              } else {
+                if (shape == 0) issue_taps<3, 9, true>(a_plane, b_slot, 0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
+                else if (shape == 1) issue_taps<3, 3, true>(a_plane, b_slot, dy0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
+                else if (shape == 2) issue_taps<5, 5, true>(a_plane, b_slot, dy0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
+                else
+                  for (int t = 0, dy = dy0, dx = dx0; t < tps; ++t) {
+                    issue_taps<1, 1, true>(a_plane, b_slot + static_cast<uint64_t>(t) * tap_desc, dy, dx, rp8, tap_desc, tm0, tm1,
+                                           idesc, fresh && t == 0);
+                    if (++dx == k) { dx = 0; ++dy; }
+                  }
+                ptx::mma_commit_2cta(&w_empty[slot]);   // frees the slot in both CTAs
+              }
             }
             __syncwarp();
             fresh = false;
@@ -497,8 +555,13 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       }
       if (args.trace && blockIdx.x == trace_cta && lane == 0 && which == 0) args.trace[l * 8 + 3] = clock64();
       if (ptx::elect_one()) {
-        ptx::mma_commit(acc_full);
-        if (l == args.n_layers - 1) ptx::mma_commit(tower_done);
+        if constexpr (!PAIR) {
+          ptx::mma_commit(acc_full);
+          if (l == args.n_layers - 1) ptx::mma_commit(tower_done);
+        } else {   // both CTAs' epilogues (and head-weight stagers) wait on their own copies
+          ptx::mma_commit_2cta(acc_full);
+          if (l == args.n_layers - 1) ptx::mma_commit_2cta(tower_done);
+        }
       }
       __syncwarp();
     }
@@ -506,11 +569,14 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     // ============ epilogue: bias (+ fp32 residual) + ReLU, stores, grid barrier arrive ============
     // M = 128 (two boards): TMEM lane m = quad*32 + lane is row (rank m>>4, board (m>>3)&1, file m&7).
     // M = 64 (one board): the 64 rows sit in lanes 0-15 of each 32-lane quadrant, row i = quad*16 + lane.
+    // Pair (cta_group::2, M = 128): this CTA's 64 rows sit in lanes 0-63 for the slice's first ns/2 columns and again in
+    // lanes 64-127 for the other ns/2 (measured, tools/ub/ub_pair_layout.cu): row = (quad & 1) * 32 + lane, half = quad >> 1.
     const int quad = warp & 3;
-    const int m = args.nb == 2 ? quad * 32 + lane : quad * 16 + (lane & 15);
+    const int m = PAIR ? (quad & 1) * 32 + lane : (args.nb == 2 ? quad * 32 + lane : quad * 16 + (lane & 15));
     const int h = args.nb == 2 ? m >> 4 : m >> 3, p = args.nb == 2 ? (m >> 3) & 1 : 0, w = m & 7;
     const int pos = n0 + p;
-    const bool live = pos < args.batch && (args.nb == 2 || lane < 16);
+    const bool live = pos < args.batch && (PAIR || args.nb == 2 || lane < 16);
+    const int cb = PAIR ? (quad >> 1) * ns_cta : 0;   // this thread's first channel within the slice
     const size_t row = static_cast<size_t>(pos) * 64 + h * 8 + w;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int hf_all = args.pf + args.vf;
@@ -529,11 +595,11 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       const bool conv1 = l > 0 && (l & 1);     // bf16 out to y only
       const bool has_res = l > 0 && !(l & 1);  // conv2: + residual, out to xf and xb
       const bool two_issuers = (l == 0 ? args.stem_kchunks : args.filters / 64) > 1;
-      const float* bias = args.bias_all + static_cast<size_t>(l) * args.filters + col0;
+      const float* bias = args.bias_all + static_cast<size_t>(l) * args.filters + col0 + cb;
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
         const int c0 = ci * 16;
-        if (c0 >= args.ns) break;
+        if (c0 >= ns_cta) break;
         // bias is fetched BEFORE the wait; the fp32 residual stream of this row and these channels never leaves the
         // thread: it lives in registers from one block to the next (res)
         float f[16];
@@ -552,10 +618,10 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
           // a single-chunk layer (the stem) is issued by issuer 0 alone: accumulators 2 and 3 were not written
           uint32_t v[NACC][16];
           ptx::tmem_ld_32x16(taddr + c0, v[0]);
-          ptx::tmem_ld_32x16(taddr + args.ns + c0, v[1]);
+          ptx::tmem_ld_32x16(taddr + ns_cta + c0, v[1]);
           if (two_issuers) {
-            ptx::tmem_ld_32x16(taddr + 2 * args.ns + c0, v[2]);
-            ptx::tmem_ld_32x16(taddr + 3 * args.ns + c0, v[3]);
+            ptx::tmem_ld_32x16(taddr + 2 * ns_cta + c0, v[2]);
+            ptx::tmem_ld_32x16(taddr + 3 * ns_cta + c0, v[3]);
           }
           ptx::tmem_ld_wait();
 #pragma unroll
@@ -570,11 +636,11 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
           // per head filter; the groups are added up, in order, by the head phase below
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
-          float* hp = args.hpart + ((static_cast<size_t>(pos) * 16 + ((col0 + c0) >> 4)) * HEAD_FILTERS_MAX) * 64 + h * 8 + w;
+          float* hp = args.hpart + ((static_cast<size_t>(pos) * 16 + ((col0 + cb + c0) >> 4)) * HEAD_FILTERS_MAX) * 64 + h * 8 + w;
 #pragma unroll
           for (int f6 = 0; f6 < HEAD_FILTERS_MAX; ++f6) {
             if (f6 < hf_all) {
-              const float4* wq = reinterpret_cast<const float4*>(s_hw + f6 * 64 + c0);
+              const float4* wq = reinterpret_cast<const float4*>(s_hw + f6 * 64 + cb + c0);
               float acc = 0.0f;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -592,7 +658,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
 #pragma unroll
             for (int j = 0; j < 16; ++j) res[ci][j] = f[j];
           }
-          __nv_bfloat16* orow = (conv1 ? args.y : args.xb) + row * args.filters + col0 + c0;
+          __nv_bfloat16* orow = (conv1 ? args.y : args.xb) + row * args.filters + col0 + cb + c0;
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             uint32_t pk[4];
@@ -620,9 +686,11 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync_all();  // nobody frees TMEM while the peer may still signal or read it
   if (warp == 2) {
     ptx::tcgen05_fence_after();
-    ptx::tmem_dealloc(tmem_base, tmem_cols);
+    if constexpr (PAIR) ptx::tmem_dealloc_2cta(tmem_base, tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, tmem_cols);
   }
 
   // ===================== heads, per board tile (no grid-wide step) =====================
