@@ -533,16 +533,22 @@ int setup_small_batch(caz_handle* h) {
 bool sb_geometry(const caz_handle* h, int batch, int* nb_out, int* slices_out, int* pair_out = nullptr) {
   if (!h->sb_ok) return false;
   if (pair_out) *pair_out = 0;
-  // 9-18 boards: CTA pairs (cta_group::2, one board per CTA, a 32-channel slice per pair).  Per MMA a CTA reads 2.5 KB of
-  // operands instead of 3 KB and stages half of the slice's weights; below 9 boards the 16-channel
-  // slices of the unpaired form move the same bytes with twice the CTAs.
-  if (batch >= 9 && batch <= 18 && !h->sb_force_nb && !getenv("CAZ_SB_NO_PAIRS") && h->arch.filters % 32 == 0 &&
-      h->arch.filters / 32 <= 16 && ((batch + 1) / 2) * (h->arch.filters / 32) * 2 <= h->num_sms &&
-      caz::sb::heads_fit(h->arch.policy_filters, h->arch.value_filters, h->arch.n_labels, h->arch.value_fc, h->arch.filters / 32)) {
-    *nb_out = 1;
-    *slices_out = h->arch.filters / 32;
-    if (pair_out) *pair_out = 1;
-    return true;
+  // 9-36 boards: CTA pairs (cta_group::2, one board per CTA; a 32-channel slice per pair up to 18 boards, a 64-channel
+  // slice above).  Per MMA a CTA reads its 64 activation rows plus HALF of the slice's weight rows and stages half of the
+  // slice's weights: 484 KB of shared-memory traffic per layer instead of 630 KB at 16 boards, 630 KB
+  // instead of 969 KB at 32.  Below 9 boards the 16-channel slices of the unpaired form move the same bytes with twice
+  // the CTAs.
+  if (batch >= 9 && !h->sb_force_nb && !getenv("CAZ_SB_NO_PAIRS")) {
+    const caz_arch& a = h->arch;
+    for (int ns = 32; ns <= 64; ns *= 2) {
+      const int s = a.filters / ns;
+      if (a.filters % ns != 0 || s < 1 || s > 16 || ((batch + 1) / 2) * s * 2 > h->num_sms) continue;
+      if (!caz::sb::heads_fit(a.policy_filters, a.value_filters, a.n_labels, a.value_fc, s)) continue;
+      *nb_out = 1;
+      *slices_out = s;
+      if (pair_out) *pair_out = 1;
+      return true;
+    }
   }
   for (int pass = 0; pass < 2; ++pass)
     for (int nb = 1; nb <= 2; ++nb) {
