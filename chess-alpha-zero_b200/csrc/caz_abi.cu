@@ -533,12 +533,12 @@ int setup_small_batch(caz_handle* h) {
 bool sb_geometry(const caz_handle* h, int batch, int* nb_out, int* slices_out, int* pair_out = nullptr) {
   if (!h->sb_ok) return false;
   if (pair_out) *pair_out = 0;
-  // 9-36 boards: CTA pairs (cta_group::2, one board per CTA; a 32-channel slice per pair up to 18 boards, a 64-channel
+  // Up to 36 boards: CTA pairs (cta_group::2, one board per CTA; a 32-channel slice per pair up to 18 boards, a 64-channel
   // slice above).  Per MMA a CTA reads its 64 activation rows plus HALF of the slice's weight rows and stages half of the
   // slice's weights: 484 KB of shared-memory traffic per layer instead of 630 KB at 16 boards, 630 KB
-  // instead of 969 KB at 32.  Below 9 boards the 16-channel slices of the unpaired form move the same bytes with twice
-  // the CTAs.
-  if (batch >= 9 && !h->sb_force_nb && !getenv("CAZ_SB_NO_PAIRS")) {
+  // instead of 969 KB at 32; and all 128 epilogue threads have rows (an M = 64 single-CTA accumulator leaves half idle),
+  // which is why the pair form also wins below 9 boards (measured: 111 us vs 115 us).
+  if (batch >= 1 && !h->sb_force_nb && !getenv("CAZ_SB_NO_PAIRS")) {
     const caz_arch& a = h->arch;
     for (int ns = 32; ns <= 64; ns *= 2) {
       const int s = a.filters / ns;
