@@ -654,6 +654,14 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   attrs[1].val.clusterDim.z = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = pair ? 2 : 1;
+  // Nsight Compute cannot launch a kernel that is cooperative AND clustered (LaunchFailed before the first pass, grid
+  // reported as 0x0x0).  Under its injection the pair form is launched with the cluster attribute only: the profiler
+  // serialises kernels, so the grid (<= one CTA per SM) is co-resident anyway.
+  static const bool under_ncu = getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
+  if (pair && under_ncu) {
+    attrs[0] = attrs[1];
+    cfg.numAttrs = 1;
+  }
   cudaError_t e = cudaLaunchKernelExC(&cfg, pair ? reinterpret_cast<const void*>(caz::sb::forward_sb_kernel<true>)
                                                  : reinterpret_cast<const void*>(caz::sb::forward_sb_kernel<false>), params);
   if (e != cudaSuccess) return fail(h, CAZ_ERR_CUDA, fmt("cooperative launch of forward_sb_kernel failed: %s", cudaGetErrorString(e)));

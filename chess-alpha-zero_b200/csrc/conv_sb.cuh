@@ -4,9 +4,11 @@
 //
 // At batch 16 a forward pass is ~17 GFLOP -- nothing for the tensor cores -- but every layer needs the 1.18 MB of its
 // weights and has to wait for the previous layer: the pass is bound by latency chains and by operand bandwidth.  So:
-//   * grid = (board tiles) x (output-channel slices): CTA (t, s) owns the rows of tile t (one board, M = 64, up to
-//     batch 16; two boards, M = 128, above) and N_s = 256/S output channels in EVERY layer.  Its slice of the fp32
-//     residual stream stays in the epilogue threads' registers; only 16-bit activations cross CTAs, through L2.
+//   * grid = (board tiles) x (output-channel slices): a tile's rows and N_s = 256/S output channels belong to the same
+//     CTA(s) in EVERY layer.  Up to 36 boards a slice of a PAIR of boards is run by a CTA pair (cta_group::2, M = 128:
+//     one board per CTA, each CTA staging half of the slice's weight rows, the leader issuing for both); above that one
+//     CTA takes two boards (M = 128) and a 64-channel slice.  The fp32 residual stream of a thread's row and channels
+//     stays in its registers; only 16-bit activations cross CTAs, through L2.
 //   * a tcgen05.mma at these shapes costs its operand reads from shared memory, (M + N) x 32 B at 128 B/cycle
 //     (tools/ub/ub_small.cu), IF the issuing thread keeps up: descriptors are hoisted, tap geometry is compile-time, two
 //     warps issue alternate 64-channel chunks into their own accumulators (4 TMEM column groups, added by the epilogue).
