@@ -61,7 +61,7 @@ struct Args {
   int blk_k;                  // tower kernel size
   int in_planes, in_cpad;
   int fp16;                   // 16-bit operands are fp16 instead of bf16
-  int dbg;                    // measurement switches (CAZ_SB_DBG), 0 in production: bit 1 = strided tile-to-CTA mapping, bits 8.. = traced CTA
+  int dbg;                    // measurement switch (CAZ_SB_DBG), 0 in production: bits 8.. = the CTA that writes the trace
   int slot_bytes, n_slots;    // weight ring geometry
   const float* planes;        // fp32 [batch][in_planes][64] or nullptr
   const uint8_t* records;     // u8 [batch][68] or nullptr (exactly one of the two)
