@@ -314,6 +314,31 @@ def test_full_size_batch_properties(net):
     ev.close()
 
 
+def test_small_batch_kernel_soak(net_default):
+    """Random batch sizes 1..64 back to back for a few seconds (paired and unpaired geometries alternate, flag epochs
+    advance): every repeat is bit-identical, and row i does not depend on the batch it came in."""
+    import time
+    cfg, w, x, fens, _ = net_default
+    ev = caz.Evaluator(cfg, w, precision="bf16", max_batch=64)
+    rng = np.random.default_rng(0)
+    seen, calls, t0 = {}, 0, time.time()
+    while time.time() - t0 < 3.0:
+        b, off = int(rng.integers(1, 65)), int(rng.integers(0, 4)) * 64
+        p, v = ev.predict_on_batch(x[off:off + b])
+        if (b, off) in seen:
+            assert np.array_equal(seen[(b, off)][0], p) and np.array_equal(seen[(b, off)][1], v), (b, off, calls)
+        else:
+            seen[(b, off)] = (p.copy(), v.copy())
+        calls += 1
+    for off in range(0, 256, 64):
+        full = ev.predict_on_batch(x[off:off + 64])
+        for (b, o), (p, v) in seen.items():
+            if o == off:
+                assert np.array_equal(p, full[0][:b]) and np.array_equal(v, full[1][:b]), (b, off)
+    assert calls > 1000
+    ev.close()
+
+
 def test_empty_batch_and_chunking(net, ev_bf16):
     p, v = ev_bf16.predict_on_batch(np.zeros((0, 18, 8, 8), np.float32))
     assert p.shape == (0, 1968) and v.shape == (0, 1)
