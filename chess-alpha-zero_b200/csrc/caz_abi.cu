@@ -87,7 +87,7 @@ struct caz_handle {
   CUtensorMap sb_tm_w_stem[3], sb_tm_w_tower[3];      // weight maps for N_s = 16, 32, 64
   int sb_force_nb = 0;
   unsigned* sb_counter = nullptr;   // progress flags of the small-batch kernel: 32 candidate grains of 4 KB
-  uint16_t sb_flag_line[2][64];   // [copy][tile] -> candidate line of that tile's flags (copy 0 / 1: the two latency classes)
+  uint16_t sb_flag_line[2][caz::sb::MAX_TILES];   // [copy][tile] -> candidate line of that tile's flags (copy 0 / 1: the two latency classes)
   bool sb_two_dies = false;
   long long* sb_trace = nullptr;   // [64][8] clock stamps of CTA 0 (debug)
   bool sb_trace_on = false;
@@ -533,14 +533,14 @@ int setup_small_batch(caz_handle* h) {
 bool sb_geometry(const caz_handle* h, int batch, int* nb_out, int* slices_out, int* pair_out = nullptr) {
   if (!h->sb_ok) return false;
   if (pair_out) *pair_out = 0;
-  // Up to 36 boards: CTA pairs (cta_group::2, one board per CTA; a 32-channel slice per pair up to 18 boards, a 64-channel
-  // slice above).  Per MMA a CTA reads its 64 activation rows plus HALF of the slice's weight rows and stages half of the
+  // Up to 72 boards: CTA pairs (cta_group::2, one board per CTA; a 32-channel slice per pair up to 18 boards, 64 channels up
+  // to 36, 128 above).  Per MMA a CTA reads its 64 activation rows plus HALF of the slice's weight rows and stages half of the
   // slice's weights: 484 KB of shared-memory traffic per layer instead of 630 KB at 16 boards, 630 KB
   // instead of 969 KB at 32; and all 128 epilogue threads have rows (an M = 64 single-CTA accumulator leaves half idle),
   // which is why the pair form also wins below 9 boards (measured: 111 us vs 115 us).
   if (batch >= 1 && !h->sb_force_nb && !getenv("CAZ_SB_NO_PAIRS")) {
     const caz_arch& a = h->arch;
-    for (int ns = 32; ns <= 64; ns *= 2) {
+    for (int ns = 32; ns <= 128; ns *= 2) {   // 128-channel slices: 37-72 boards
       const int s = a.filters / ns;
       if (a.filters % ns != 0 || s < 1 || s > 16 || ((batch + 1) / 2) * s * 2 > h->num_sms) continue;
       if (!caz::sb::heads_fit(a.policy_filters, a.value_filters, a.n_labels, a.value_fc, s)) continue;

@@ -45,8 +45,8 @@ constexpr int NACC = 4;   // accumulator groups in TMEM: one per K sub-step of a
 constexpr int BAR_BYTES = 1024;
 constexpr int SMEM_BYTES = A_BYTES + W_RING_BYTES + BAR_BYTES + 1024 /*alignment*/;
 constexpr int HEAD_SMEM_BYTES = A_BYTES + W_RING_BYTES;        // what the head phases may use for staged weights
-constexpr int MAX_BATCH = 64;
-constexpr int MAX_TILES = 64;   // board tiles per launch (one flag line each)
+constexpr int MAX_BATCH = 72;   // 36 CTA pairs x 2 slices of 128 channels = 144 CTAs
+constexpr int MAX_TILES = 72;   // board tiles per launch (one flag line each)
 
 struct Args {
   int batch;        // positions (<= MAX_BATCH)
@@ -112,6 +112,7 @@ constexpr int HID_GROUP = 16;          // hidden units per value-head group
 constexpr int HID_GROUPS_MAX = 16;     // => value_fc <= 256
 constexpr int HSTAT_FLOATS = 2 * LABEL_UNITS_MAX + HID_GROUPS_MAX;   // per position
 constexpr int LABEL_CHUNK = 256;       // labels per pass over the staged policy weights (one per thread)
+constexpr int LCHUNKS_MAX = 4;         // passes per CTA: 1 024 labels, i.e. two slices per board at the least
 
 // taps per weight-ring slot: the whole filter, one filter row, or one tap -- the largest that fits a slot
 __host__ __device__ inline int taps_per_slot(int k, int ns) {
@@ -197,8 +198,13 @@ __host__ __device__ inline bool heads_fit(int pf, int vf, int n_labels, int valu
   if (pf + vf > HEAD_FILTERS_MAX || (n_labels & 3) || (value_fc & 3)) return false;
   const HeadGeom g = head_geom(n_labels, value_fc, n_slices);
   if (g.units_total > LABEL_UNITS_MAX || g.groups_total > HID_GROUPS_MAX) return false;
-  if ((g.upl * LABEL_UNIT + LABEL_CHUNK - 1) / LABEL_CHUNK > 2) return false;   // logits live in registers: two label chunks
-  return (pf * 64 * LABEL_CHUNK + vf * 64 * g.hsp) * 4 <= HEAD_SMEM_BYTES && (pf + vf) * 64 <= 512;
+  if ((g.upl * LABEL_UNIT + LABEL_CHUNK - 1) / LABEL_CHUNK > LCHUNKS_MAX) return false;   // logits live in registers
+  // (the value Dense columns are staged next to the policy chunk if they fit, else read from L2: value_staged())
+  return pf * 64 * LABEL_CHUNK * 4 <= HEAD_SMEM_BYTES && (pf + vf) * 64 <= 512;
+}
+
+__host__ __device__ inline bool value_staged(int pf, int vf, int hsp) {
+  return (pf * 64 * LABEL_CHUNK + vf * 64 * hsp) * 4 <= HEAD_SMEM_BYTES;
 }
 
 // Stage head weights for this CTA: policy Dense rows [kp][lab_first, +cnt) -> s_wp[k][LABEL_CHUNK]; with_value: this
@@ -277,7 +283,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   uint64_t* hw_full = acc_full + 2;              // [1] staged head weights
   uint64_t* tower_done = acc_full + 3;           // [1] the last layer's MMAs have completed (both issuers)
   uint64_t* stem_ready = acc_full + 4;           // [1] the stem tile(s) built in place are complete (both CTAs of a pair)
-  __shared__ __align__(16) float s_hw[HEAD_FILTERS_MAX * 64];   // this slice's columns of the 1x1 head convolutions
+  __shared__ __align__(16) float s_hw[HEAD_FILTERS_MAX * 128];  // this slice's columns of the 1x1 head convolutions
   __shared__ __align__(16) float s_feat[2 * 512];               // head-conv outputs of this tile's boards (Flatten order)
   __shared__ float s_red[64];
   __shared__ uint32_t s_rec[2 * 17];                            // this tile's board records (68 bytes each)
@@ -421,7 +427,8 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     // The last layer's MMAs are done with the tiles and the ring: stage this CTA's head weights over them while the
     // epilogue warps are still busy (the Dense weights do not depend on the activations).
     ptx::mbar_wait(tower_done, 0, args.err_flag, ERR_HEADW);
-    stage_head_weights(args, s_wp, s_wv, hw_full, lane, lab0, min(lab_cnt, LABEL_CHUNK), true, hid0, hid_cnt, hg.hsp);
+    stage_head_weights(args, s_wp, s_wv, hw_full, lane, lab0, min(lab_cnt, LABEL_CHUNK), value_staged(args.pf, args.vf, hg.hsp),
+                       hid0, hid_cnt, hg.hsp);
   } else if (warp == 3) {
     // ============ activation producer: one halo tile per 64-channel chunk, as soon as the CTAs that own those
     // channels of this board tile have published the previous layer (no grid-wide barrier: a tile's CTAs only ever
@@ -582,8 +589,8 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     const size_t row = static_cast<size_t>(pos) * 64 + h * 8 + w;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int hf_all = args.pf + args.vf;
-    for (int i = threadIdx.x - 128; i < HEAD_FILTERS_MAX * 64; i += 128) {
-      const int f6 = i >> 6, j = i & 63;
+    for (int i = threadIdx.x - 128; i < HEAD_FILTERS_MAX * 128; i += 128) {
+      const int f6 = i >> 7, j = i & 127;
       s_hw[i] = (f6 < hf_all && j < args.ns) ? args.head_w[f6 * args.filters + col0 + j] : 0.0f;
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -642,7 +649,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
 #pragma unroll
           for (int f6 = 0; f6 < HEAD_FILTERS_MAX; ++f6) {
             if (f6 < hf_all) {
-              const float4* wq = reinterpret_cast<const float4*>(s_hw + f6 * 64 + cb + c0);
+              const float4* wq = reinterpret_cast<const float4*>(s_hw + f6 * 128 + cb + c0);
               float acc = 0.0f;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -727,9 +734,11 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
 
   // ---- H2 ----
   const int n_lchunks = (hg.upl * LABEL_UNIT + LABEL_CHUNK - 1) / LABEL_CHUNK;
-  float lg[2][2];   // [label chunk][board of the tile]: this thread's logits (n_lchunks <= 2 is checked on the host)
+  float lg[LCHUNKS_MAX][2];   // [label chunk][board of the tile]: this thread's logits (n_lchunks is checked on the host)
   const int unit_in_chunk = threadIdx.x >> 7;   // threads 0-127 / 128-255 = the chunk's first / second 128-label unit
-  for (int c = 0; c < n_lchunks; ++c) {
+#pragma unroll
+  for (int c = 0; c < LCHUNKS_MAX; ++c) {
+    if (c >= n_lchunks) break;
     if (c > 0) {
       __syncthreads();   // everyone is done with the previous chunk's weights
       if (warp == 0)
@@ -794,9 +803,10 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     for (int i = threadIdx.x; i < per; i += THREADS) {
       const int u = i % hg.hsp, kq = i / hg.hsp;
       float a0 = 0.0f, a1 = 0.0f;
+      const bool staged = value_staged(args.pf, args.vf, hg.hsp);
       if (u < hid_cnt)
         for (int k = kq; k < kv; k += 8) {
-          const float wv = s_wv[k * hg.hsp + u];
+          const float wv = staged ? s_wv[k * hg.hsp + u] : __ldg(args.vfc1_w + static_cast<size_t>(k) * args.value_fc + hid0 + u);
           a0 = fmaf(s_feat[kp + k], wv, a0);
           a1 = fmaf(s_feat[512 + kp + k], wv, a1);
         }
@@ -845,10 +855,12 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       if (mu != -INFINITY) z += su * expf(mu - mx);
     }
     const float inv = z > 0.0f ? 1.0f / z : 0.0f;
-    for (int c = 0; c < n_lchunks; ++c) {
+#pragma unroll
+    for (int c = 0; c < LCHUNKS_MAX; ++c) {
+      if (c >= n_lchunks) break;
       const int n = lab0 + c * LABEL_CHUNK + threadIdx.x;
       if (c * LABEL_CHUNK + threadIdx.x < lab_cnt) {
-        const float x = c ? lg[1][bl] : lg[0][bl];
+        const float x = lg[c][bl];
         args.policy[static_cast<size_t>(b) * args.n_labels + n] = x == -INFINITY ? 0.0f : expf(x - mx) * inv;
       }
     }

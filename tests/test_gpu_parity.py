@@ -252,9 +252,13 @@ def test_small_batch_persistent_kernel(net_default):
     ref_p, ref_v = ev.predict_on_batch(x[:64])
     dp, dv, agree = _bf16_report("small-batch kernel vs fp32 oracle [keras_default, 64]", ref_p, ref_v, wp[:64], wv[:64], 64)
     assert dp <= BF16_TOL and dv <= BF16_VALUE_TOL_REFERENCE_INIT and agree >= ARGMAX_AGREE
-    for batch in (1, 2, 3, 15, 16, 17, 32, 33, 48):
+    for batch in (1, 2, 3, 15, 16, 17, 32, 33, 36, 37, 48):
         p, v = ev.predict_on_batch(x[:batch])
         assert np.array_equal(p, ref_p[:batch]) and np.array_equal(v, ref_v[:batch]), batch
+    for batch in (65, 72):   # the largest grids of the persistent kernel: 36 CTA pairs x 2 slices
+        p, v = ev.predict_on_batch(x[:batch])
+        assert np.array_equal(p[:64], ref_p) and np.array_equal(v[:64], ref_v), batch
+        assert np.abs(p - wp[:batch]).max() <= BF16_TOL and np.abs(v - wv[:batch]).max() <= BF16_VALUE_TOL_REFERENCE_INIT
     # against the per-layer kernels: same arithmetic up to fp32 summation order, so bf16-noise level agreement
     ev.set_small_batch_limit(0)
     big_p, big_v = ev.predict_on_batch(x[:64])
