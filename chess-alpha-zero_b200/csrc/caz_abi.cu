@@ -992,7 +992,12 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   // 16-bit builds: the stem's input rows are one swizzle span: 32 channels (64-byte rows) when the planes fit, else 64
   h->in_cpad = tcp ? (a.input_planes <= 32 ? 32 : 64) : a.input_planes;
   CREATE_TRY(cudaMalloc(&h->in_act, cap * 64 * h->in_cpad * esz));
-  for (int i = 0; i < 3; ++i) CREATE_TRY(cudaMalloc(&h->act[i], ((cap + 1) & ~size_t(1)) * 64 * a.filters * (i == 2 ? 4 : esz)));
+  for (int i = 0; i < 3; ++i) {
+    const size_t bytes = ((cap + 1) & ~size_t(1)) * 64 * a.filters * (i == 2 ? 4 : esz);
+    CREATE_TRY(cudaMalloc(&h->act[i], bytes));
+    // rows of boards past the batch are read (never used) by tiles that hold two boards: keep them finite
+    CREATE_TRY(cudaMemset(h->act[i], 0, bytes));
+  }
   CREATE_TRY(cudaMalloc(&h->featp, cap * a.policy_filters * 64 * 4));
   CREATE_TRY(cudaMalloc(&h->featv, cap * a.value_filters * 64 * 4));
   CREATE_TRY(cudaMalloc(&h->vhid, cap * a.value_fc * 4));
