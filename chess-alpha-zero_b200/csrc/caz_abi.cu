@@ -95,6 +95,7 @@ struct caz_handle {
   float* sb_hpart = nullptr;    // partial head-conv sums of the small-batch kernel
   float* sb_hstats = nullptr;   // its softmax / value statistics
   float *head_w = nullptr, *head_b = nullptr;
+  float *pfc_wb = nullptr, *vfc1_wb = nullptr;   // blocked copies for the small-batch kernel's bulk staging (conv_sb.cuh)
   float *pfc_w = nullptr, *pfc_b = nullptr, *vfc1_w = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr,
         *vfc2_b = nullptr;
   void* in_act = nullptr;  // [cap][64][in_cpad]
@@ -344,6 +345,24 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
     CU_TRY(h, cudaMalloc(&h->vfc2_b, 4));
   }
   int rc;
+  {
+    // blocked copies: policy Dense kernel as [128-label unit][k][128], value Dense kernel as [16-unit group][k][16], zero-padded
+    const int units = (a.n_labels + caz::sb::LABEL_UNIT - 1) / caz::sb::LABEL_UNIT;
+    const int groups = (a.value_fc + caz::sb::HID_GROUP - 1) / caz::sb::HID_GROUP;
+    std::vector<float> pb((size_t)units * kp * caz::sb::LABEL_UNIT, 0.0f), vb((size_t)groups * kv * caz::sb::HID_GROUP, 0.0f);
+    for (int k = 0; k < kp; ++k)
+      for (int n = 0; n < a.n_labels; ++n)
+        pb[((size_t)(n / caz::sb::LABEL_UNIT) * kp + k) * caz::sb::LABEL_UNIT + n % caz::sb::LABEL_UNIT] = pol[5].data[(size_t)k * a.n_labels + n];
+    for (int k = 0; k < kv; ++k)
+      for (int u = 0; u < a.value_fc; ++u)
+        vb[((size_t)(u / caz::sb::HID_GROUP) * kv + k) * caz::sb::HID_GROUP + u % caz::sb::HID_GROUP] = val[5].data[(size_t)k * a.value_fc + u];
+    if (!h->pfc_wb) {
+      CU_TRY(h, cudaMalloc(&h->pfc_wb, pb.size() * 4));
+      CU_TRY(h, cudaMalloc(&h->vfc1_wb, vb.size() * 4));
+    }
+    if ((rc = upload(h, h->pfc_wb, pb.data(), pb.size() * 4))) return rc;
+    if ((rc = upload(h, h->vfc1_wb, vb.data(), vb.size() * 4))) return rc;
+  }
   if ((rc = upload(h, h->head_w, hw.data(), hw.size() * 4))) return rc;
   if ((rc = upload(h, h->head_b, hb.data(), hb.size() * 4))) return rc;
   if ((rc = upload(h, h->pfc_w, pol[5].data, (size_t)pol[5].numel * 4))) return rc;
@@ -618,6 +637,8 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   args.hpart = h->sb_hpart;
   args.hstats = h->sb_hstats;
   args.pfc_w = h->pfc_w;
+  args.pfc_wb = h->pfc_wb;
+  args.vfc1_wb = h->vfc1_wb;
   args.pfc_b = h->pfc_b;
   args.vfc1_w = h->vfc1_w;
   args.vfc1_b = h->vfc1_b;
@@ -920,7 +941,7 @@ void caz_destroy(caz_handle* h) {
   if (h->sb_hpart) cudaFree(h->sb_hpart);
   if (h->sb_hstats) cudaFree(h->sb_hstats);
   if (h->sb_trace) cudaFree(h->sb_trace);
-  void* ptrs[] = {h->head_w, h->head_b, h->pfc_w, h->pfc_b, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, h->in_act,
+  void* ptrs[] = {h->pfc_wb, h->vfc1_wb, h->head_w, h->head_b, h->pfc_w, h->pfc_b, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, h->in_act,
                   h->act[0], h->act[1], h->act[2], h->featp, h->featv, h->vhid, h->a3p, h->a3v, h->w3p, h->w3v, h->bias3p, h->d_planes, h->d_policy, h->d_value,
                   h->d_mask, h->d_records, h->puct_buf, h->d_planes2, h->d_policy2, h->d_value2, h->d_mask2,
                   h->d_records2};

@@ -74,8 +74,10 @@ struct Args {
   const float* head_b;        // [pf+vf]
   float* hpart;               // [batch][16 channel groups][8 head filters][64 squares] partial head-conv sums
   const float* pfc_w;         // [pf*64][n_labels]
+  const float* pfc_wb;        // the same weights in 128-label blocks, [units][pf*64][128] zero-padded: ONE bulk copy per unit
   const float* pfc_b;
   const float* vfc1_w;        // [vf*64][value_fc]
+  const float* vfc1_wb;       // in 16-unit blocks, [groups][vf*64][16] zero-padded: one bulk copy per hidden group
   const float* vfc1_b;
   const float* vfc2_w;        // [value_fc]
   const float* vfc2_b;
@@ -203,25 +205,30 @@ __host__ __device__ inline bool heads_fit(int pf, int vf, int n_labels, int valu
   return pf * 64 * LABEL_CHUNK * 4 <= HEAD_SMEM_BYTES && (pf + vf) * 64 <= 512;
 }
 
+// staged value weights: [group][vf*64][16], groups 16 floats further apart than their size (bank spread)
+__host__ __device__ inline int value_group_pitch(int vf) { return vf * 64 * HID_GROUP + 16; }
 __host__ __device__ inline bool value_staged(int pf, int vf, int hsp) {
-  return (pf * 64 * LABEL_CHUNK + vf * 64 * hsp) * 4 <= HEAD_SMEM_BYTES;
+  return (pf * 64 * LABEL_CHUNK + hsp / HID_GROUP * value_group_pitch(vf)) * 4 <= HEAD_SMEM_BYTES;
 }
 
-// Stage head weights for this CTA: policy Dense rows [kp][lab_first, +cnt) -> s_wp[k][LABEL_CHUNK]; with_value: this
-// slice's columns of the value Dense kernel -> s_wv[k][hsp].  One warp; completion on `bar` (one phase per call).
+// Stage head weights for this CTA: the policy Dense kernel of 128-label units [unit0, unit0 + n_units) (n_units <= 2)
+// -> s_wp[unit][k][128]; with_value: hidden groups [grp0, grp0 + n_groups) of the value Dense kernel ->
+// s_wv[group][k][16].  One bulk copy per unit / group from the blocked copies of the weights (a bulk copy per weight
+// ROW, 384 of them, took the issuing warp 10 us: the copy engine accepts one every ~50 cycles).  One warp; completion
+// on `bar` (one phase per call).
 __device__ __forceinline__ void stage_head_weights(const Args& args, float* s_wp, float* s_wv, uint64_t* bar, int lane,
-                                                   int lab_first, int cnt, bool with_value, int h0, int hcnt, int hsp) {
+                                                   int unit0, int n_units, bool with_value, int grp0, int n_groups) {
   const int kp = args.pf * 64, kv = args.vf * 64;
-  if (lane == 0) {
-    ptx::mbar_expect_tx(bar, static_cast<uint32_t>((cnt > 0 ? kp * cnt : 0) + (with_value && hcnt > 0 ? kv * hcnt : 0)) * 4u);
-  }
+  const uint32_t unit_bytes = static_cast<uint32_t>(kp) * LABEL_UNIT * 4u, grp_bytes = static_cast<uint32_t>(kv) * HID_GROUP * 4u;
+  if (!with_value) n_groups = 0;
+  if (lane == 0) ptx::mbar_expect_tx(bar, static_cast<uint32_t>(n_units) * unit_bytes + static_cast<uint32_t>(n_groups) * grp_bytes);
   __syncwarp();
-  if (cnt > 0)
-    for (int k = lane; k < kp; k += 32)
-      bulk_g2s(s_wp + k * LABEL_CHUNK, args.pfc_w + static_cast<size_t>(k) * args.n_labels + lab_first, cnt * 4, bar);
-  if (with_value && hcnt > 0)
-    for (int k = lane; k < kv; k += 32)
-      bulk_g2s(s_wv + k * hsp, args.vfc1_w + static_cast<size_t>(k) * args.value_fc + h0, hcnt * 4, bar);
+  if (lane < n_units)
+    bulk_g2s(s_wp + static_cast<size_t>(lane) * kp * LABEL_UNIT, args.pfc_wb + static_cast<size_t>(unit0 + lane) * kp * LABEL_UNIT,
+             unit_bytes, bar);
+  else if (lane >= 8 && lane - 8 < n_groups)
+    bulk_g2s(s_wv + static_cast<size_t>(lane - 8) * value_group_pitch(args.vf),
+             args.vfc1_wb + static_cast<size_t>(grp0 + lane - 8) * kv * HID_GROUP, grp_bytes, bar);
 }
 
 // The MMAs of `TPS` consecutive taps of one 64-channel chunk (one weight-ring slot), issued by ONE thread.
@@ -286,6 +293,8 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   __shared__ __align__(16) float s_hw[HEAD_FILTERS_MAX * 128];  // this slice's columns of the 1x1 head convolutions
   __shared__ __align__(16) float s_feat[2 * 512];               // head-conv outputs of this tile's boards (Flatten order)
   __shared__ float s_red[64];
+  __shared__ float s_vb[256], s_vw[256];                        // this slice's hidden units: bias, output weight
+  __shared__ float s_stat[2 * HSTAT_FLOATS];                    // the tile's boards' head statistics (H3)
   __shared__ uint32_t s_rec[2 * 17];                            // this tile's board records (68 bytes each)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -310,8 +319,12 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   const int lab_cnt = max(0, min(hg.upl * LABEL_UNIT, args.n_labels - lab0));
   const int hid0 = slice * hg.hsp;                                      // this CTA's hidden units: [hid0, hid0 + hid_cnt)
   const int hid_cnt = max(0, min(hg.hsp, args.value_fc - hid0));
-  float* s_wp = reinterpret_cast<float*>(smem);                         // heads: [pf*64][LABEL_CHUNK], over the tower's tiles
-  float* s_wv = s_wp + args.pf * 64 * LABEL_CHUNK;                      //        [vf*64][hsp]
+  float* s_wp = reinterpret_cast<float*>(smem);                         // heads: [2 units][pf*64][128], over the tower's tiles
+  float* s_wv = s_wp + args.pf * 64 * LABEL_CHUNK;                      //        [gps groups][vf*64][16] (+16 between groups)
+  const int unit_first = slice * hg.upl;                                // this CTA's 128-label units: [unit_first, +upl)
+  auto units_in_chunk = [&](int c) {                                    // units of label chunk c that exist (0..2)
+    return max(0, min(min(2, hg.upl - 2 * c), hg.units_total - (unit_first + 2 * c)));
+  };
   long long* ktrace = (args.trace && blockIdx.x == trace_cta && threadIdx.x == 32) ? args.trace + args.n_layers * 8 : nullptr;
   if (args.trace && threadIdx.x == 0) {   // where does this CTA run
     unsigned smid;
@@ -427,8 +440,8 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     // The last layer's MMAs are done with the tiles and the ring: stage this CTA's head weights over them while the
     // epilogue warps are still busy (the Dense weights do not depend on the activations).
     ptx::mbar_wait(tower_done, 0, args.err_flag, ERR_HEADW);
-    stage_head_weights(args, s_wp, s_wv, hw_full, lane, lab0, min(lab_cnt, LABEL_CHUNK), value_staged(args.pf, args.vf, hg.hsp),
-                       hid0, hid_cnt, hg.hsp);
+    stage_head_weights(args, s_wp, s_wv, hw_full, lane, unit_first, units_in_chunk(0), value_staged(args.pf, args.vf, hg.hsp),
+                       slice * hg.gps, max(0, min(hg.gps, hg.groups_total - slice * hg.gps)));
   } else if (warp == 3) {
     // ============ activation producer: one halo tile per 64-channel chunk, as soon as the CTAs that own those
     // channels of this board tile have published the previous layer (no grid-wide barrier: a tile's CTAs only ever
@@ -693,8 +706,10 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       if (threadIdx.x == 128) publish(args, tile, slice, args.base + 1u + static_cast<unsigned>(l));
     }
   }
+  if (args.trace && blockIdx.x == trace_cta && lane == 0) args.trace[200 + warp] = clock64();
   ptx::tcgen05_fence_before();
   __syncthreads();
+  if (args.trace && blockIdx.x == trace_cta && lane == 0) args.trace[216 + warp] = clock64();
   if constexpr (PAIR) ptx::cluster_sync_all();  // nobody frees TMEM while the peer may still signal or read it
   if (warp == 2) {
     ptx::tcgen05_fence_after();
@@ -710,30 +725,61 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   const int hf_total = args.pf + args.vf;
   const int kp = args.pf * 64, kv = args.vf * 64;
   if (ktrace) ktrace[2] = clock64();
+  // requested now, used after H1: this thread's label biases and legal-move mask bytes, this slice's hidden-unit constants
+  const int n_lchunks = (hg.upl * LABEL_UNIT + LABEL_CHUNK - 1) / LABEL_CHUNK;
+  float pbias[LCHUNKS_MAX];
+  bool pmask[LCHUNKS_MAX][2];
+#pragma unroll
+  for (int c = 0; c < LCHUNKS_MAX; ++c) {
+    const int n = lab0 + c * LABEL_CHUNK + threadIdx.x;
+    const bool valid = c < n_lchunks && c * LABEL_CHUNK + threadIdx.x < lab_cnt;
+    pbias[c] = valid ? args.pfc_b[n] : 0.0f;
+#pragma unroll
+    for (int bl = 0; bl < 2; ++bl)
+      pmask[c][bl] = !(valid && args.mask && bl < args.nb && n0 + bl < args.batch) ||
+                     args.mask[static_cast<size_t>(n0 + bl) * args.n_labels + n] != 0;
+  }
+  {
+    const bool on = threadIdx.x < hid_cnt;
+    s_vb[threadIdx.x] = on ? args.vfc1_b[hid0 + threadIdx.x] : 0.0f;
+    s_vw[threadIdx.x] = on ? args.vfc2_w[hid0 + threadIdx.x] : 0.0f;
+  }
   const unsigned* tile_flags = tile_flag_line(args, s_near_copy, tile);   // written by warp 3 long before the __syncthreads above
   if (threadIdx.x == 0) wait_tile(args, tile_flags, args.base + L);   // the tile's CTAs have stored their partials
   __syncthreads();
   if (ktrace) ktrace[3] = clock64();
-  for (int i = threadIdx.x; i < args.nb * hf_total * 64; i += THREADS) {
-    const int sq = i & 63, f6 = (i >> 6) % hf_total, bl = i / (64 * hf_total);
-    float v = 0.0f;
-    if (n0 + bl < args.batch) {
-      const float* hp = args.hpart + ((static_cast<size_t>(n0 + bl) * 16) * HEAD_FILTERS_MAX + f6) * 64 + sq;
-      float part[16];
+  {
+    // up to four (board, head filter, square) items per thread; all of their partials are requested before any is summed
+    constexpr int ITEMS = (2 * HEAD_FILTERS_MAX * 64 + THREADS - 1) / THREADS;
+    const int n_items = args.nb * hf_total * 64;
+    float part[ITEMS][16], hb[ITEMS];
 #pragma unroll
-      for (int g = 0; g < 16; ++g) part[g] = g * 16 < args.filters ? hp[static_cast<size_t>(g) * HEAD_FILTERS_MAX * 64] : 0.0f;
+    for (int it = 0; it < ITEMS; ++it) {
+      const int i = threadIdx.x + it * THREADS;
+      const int sq = i & 63, f6 = (i >> 6) % hf_total, bl = i / (64 * hf_total);
+      const bool on = i < n_items && n0 + bl < args.batch;
+      const float* hp = args.hpart + ((static_cast<size_t>(on ? n0 + bl : 0) * 16) * HEAD_FILTERS_MAX + f6) * 64 + sq;
 #pragma unroll
-      for (int g = 0; g < 16; ++g) v += part[g];
-      v = fmaxf(v + args.head_b[f6], 0.0f);
+      for (int g = 0; g < 16; ++g) part[it][g] = (on && g * 16 < args.filters) ? hp[static_cast<size_t>(g) * HEAD_FILTERS_MAX * 64] : 0.0f;
+      hb[it] = on ? args.head_b[f6] : 0.0f;
     }
-    // Keras channels-first Flatten: index c*64 + square (model_chess.py:80,89); policy filters first, then value
-    s_feat[bl * 512 + (f6 < args.pf ? f6 * 64 + sq : kp + (f6 - args.pf) * 64 + sq)] = v;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int i = threadIdx.x + it * THREADS;
+      if (i >= n_items) break;
+      const int sq = i & 63, f6 = (i >> 6) % hf_total, bl = i / (64 * hf_total);
+      float v = 0.0f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) v += part[it][g];
+      v = n0 + bl < args.batch ? fmaxf(v + hb[it], 0.0f) : 0.0f;
+      // Keras channels-first Flatten: index c*64 + square (model_chess.py:80,89); policy filters first, then value
+      s_feat[bl * 512 + (f6 < args.pf ? f6 * 64 + sq : kp + (f6 - args.pf) * 64 + sq)] = v;
+    }
   }
   __syncthreads();
   if (ktrace) ktrace[4] = clock64();
 
   // ---- H2 ----
-  const int n_lchunks = (hg.upl * LABEL_UNIT + LABEL_CHUNK - 1) / LABEL_CHUNK;
   float lg[LCHUNKS_MAX][2];   // [label chunk][board of the tile]: this thread's logits (n_lchunks is checked on the host)
   const int unit_in_chunk = threadIdx.x >> 7;   // threads 0-127 / 128-255 = the chunk's first / second 128-label unit
 #pragma unroll
@@ -742,8 +788,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     if (c > 0) {
       __syncthreads();   // everyone is done with the previous chunk's weights
       if (warp == 0)
-        stage_head_weights(args, s_wp, s_wv, hw_full, lane, lab0 + c * LABEL_CHUNK, min(lab_cnt - c * LABEL_CHUNK, LABEL_CHUNK),
-                           false, 0, 0, hg.hsp);
+        stage_head_weights(args, s_wp, s_wv, hw_full, lane, unit_first + 2 * c, units_in_chunk(c), false, 0, 0);
     }
     ptx::mbar_wait(hw_full, c & 1, args.err_flag, ERR_HEADW);
     if (ktrace && c == 0) ktrace[5] = clock64();
@@ -751,21 +796,20 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     const bool valid = c * LABEL_CHUNK + threadIdx.x < lab_cnt;
     float a0 = 0.0f, a1 = 0.0f;
     if (valid) {
-      const float* wcol = s_wp + threadIdx.x;
+      const float bn = pbias[c];
+      const float* wcol = s_wp + (threadIdx.x >> 7) * kp * LABEL_UNIT + (threadIdx.x & 127);
 #pragma unroll 8
       for (int k = 0; k < kp; ++k) {
-        const float wv = wcol[k * LABEL_CHUNK];
+        const float wv = wcol[k * LABEL_UNIT];
         a0 = fmaf(s_feat[k], wv, a0);
         a1 = fmaf(s_feat[512 + k], wv, a1);
       }
-      const float bn = args.pfc_b[n];
       a0 += bn; a1 += bn;
     }
 #pragma unroll
     for (int bl = 0; bl < 2; ++bl) {
       const int b = n0 + bl;
-      const bool on = valid && bl < args.nb && b < args.batch &&
-                      (!args.mask || args.mask[static_cast<size_t>(b) * args.n_labels + n] != 0);
+      const bool on = valid && bl < args.nb && b < args.batch && pmask[c][bl];
       const float x = on ? (bl ? a1 : a0) : -INFINITY;
       lg[c][bl] = x;
       // statistics of this 128-label unit: max, then the sum of exp(x - max), reduced in a fixed order
@@ -806,7 +850,8 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       const bool staged = value_staged(args.pf, args.vf, hg.hsp);
       if (u < hid_cnt)
         for (int k = kq; k < kv; k += 8) {
-          const float wv = staged ? s_wv[k * hg.hsp + u] : __ldg(args.vfc1_w + static_cast<size_t>(k) * args.value_fc + hid0 + u);
+          const float wv = staged ? s_wv[(u >> 4) * value_group_pitch(args.vf) + k * HID_GROUP + (u & 15)]
+                                  : __ldg(args.vfc1_w + static_cast<size_t>(k) * args.value_fc + hid0 + u);
           a0 = fmaf(s_feat[kp + k], wv, a0);
           a1 = fmaf(s_feat[512 + kp + k], wv, a1);
         }
@@ -825,7 +870,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
             float hsum = 0.0f;
 #pragma unroll
             for (int kq = 0; kq < 8; ++kq) hsum += s_part[bl * per + kq * hg.hsp + u];
-            pv = fmaf(fmaxf(hsum + args.vfc1_b[hu], 0.0f), args.vfc2_w[hu], pv);
+            pv = fmaf(fmaxf(hsum + s_vb[u], 0.0f), s_vw[u], pv);
           }
         }
         args.hstats[static_cast<size_t>(b) * HSTAT_FLOATS + 2 * LABEL_UNITS_MAX + grp] = pv;
@@ -842,16 +887,22 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   if (ktrace) ktrace[7] = clock64();
 
   // ---- H3: softmax over all of the board's labels (model_chess.py:83) from the units' statistics; tanh value ----
+  // the tile's statistics come in with one L2 read per thread (ld.cg: other CTAs wrote them)
+  if (threadIdx.x < 2 * HSTAT_FLOATS) {
+    const int bl = threadIdx.x / HSTAT_FLOATS, j = threadIdx.x - bl * HSTAT_FLOATS;
+    s_stat[threadIdx.x] = (bl < args.nb && n0 + bl < args.batch) ? ptx::ld_cg_f32(args.hstats + static_cast<size_t>(n0 + bl) * HSTAT_FLOATS + j) : 0.0f;
+  }
+  __syncthreads();
 #pragma unroll
   for (int bl = 0; bl < 2; ++bl) {
     const int b = n0 + bl;
     if (bl >= args.nb || b >= args.batch) continue;
-    const float* st = args.hstats + static_cast<size_t>(b) * HSTAT_FLOATS;
+    const float* st = s_stat + bl * HSTAT_FLOATS;
     float mx = -INFINITY;
-    for (int u = 0; u < hg.units_total; ++u) mx = fmaxf(mx, ptx::ld_cg_f32(st + 2 * u));
+    for (int u = 0; u < hg.units_total; ++u) mx = fmaxf(mx, st[2 * u]);
     float z = 0.0f;
     for (int u = 0; u < hg.units_total; ++u) {
-      const float mu = ptx::ld_cg_f32(st + 2 * u), su = ptx::ld_cg_f32(st + 2 * u + 1);
+      const float mu = st[2 * u], su = st[2 * u + 1];
       if (mu != -INFINITY) z += su * expf(mu - mx);
     }
     const float inv = z > 0.0f ? 1.0f / z : 0.0f;
@@ -866,7 +917,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     }
     if (slice == 0 && threadIdx.x == 0) {
       float v = args.vfc2_b[0];
-      for (int g = 0; g < hg.groups_total; ++g) v += ptx::ld_cg_f32(st + 2 * LABEL_UNITS_MAX + g);
+      for (int g = 0; g < hg.groups_total; ++g) v += st[2 * LABEL_UNITS_MAX + g];
       args.value[b] = tanhf(v);
     }
   }

@@ -18,6 +18,10 @@ _lib.check(ev._handle, lib.caz_debug_sb_trace(ev._handle, 1, None, 0))
 ev.eval_device(d_x.data_ptr(), b, d_p.data_ptr(), d_v.data_ptr())
 st = np.zeros(17 * 8, np.int64)
 _lib.check(ev._handle, lib.caz_debug_sb_trace(ev._handle, 0, st.ctypes.data_as(ctypes.c_void_p), st.size))
+full = np.zeros(240, np.int64)
+_lib.check(ev._handle, lib.caz_debug_sb_trace(ev._handle, 0, full.ctypes.data_as(ctypes.c_void_p), full.size))
+print("warps reach the post-tower barrier at (us):", " ".join(f"{(v - st[0]) / 1965.0:7.2f}" for v in full[200:208]),
+      "| leave it at", f"{(full[216] - st[0]) / 1965.0:7.2f}")
 st = st.reshape(17, 8).astype(np.float64)
 t0 = st[0, 0]
 us = (st - t0) / 1965.0
