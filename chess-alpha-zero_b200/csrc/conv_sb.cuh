@@ -378,25 +378,40 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     const int hw = 8 + args.stem_k - 1, pad = (args.stem_k - 1) / 2;
     const int rows = hw * args.nb * hw;
     uint4* tile16 = reinterpret_cast<uint4*>(smem_a);
-    for (int i = t; i < rows * 8; i += nthr) tile16[i] = make_uint4(0u, 0u, 0u, 0u);
-    // board records are fetched once (17 words per board; they may live in the caller's pinned host memory) and decoded
-    // from shared memory
-    if (args.records && t < args.nb * 17) {
-      const int p = t / 17, wd = t - p * 17;
-      s_rec[p * 17 + wd] = n0 + p < args.batch ? reinterpret_cast<const uint32_t*>(args.records + static_cast<size_t>(n0 + p) * 68)[wd] : 0u;
-    }
-    asm volatile("bar.sync 2, 224;" ::: "memory");
-    const int per_board = args.in_planes * 64;
-    for (int i = t; i < args.nb * per_board; i += nthr) {
-      const int p = i / per_board, rem = i - p * per_board;
-      const int c = rem >> 6, sq = rem & 63;   // consecutive threads -> consecutive squares of one plane (coalesced)
-      const int b = n0 + p;
-      if (b >= args.batch) continue;
-      const float v = args.planes ? args.planes[(static_cast<size_t>(b) * args.in_planes + c) * 64 + sq]
-                                  : record_plane_value(reinterpret_cast<const uint8_t*>(s_rec + p * 17), c, sq);
-      const int row = ((sq >> 3) + pad) * args.nb * hw + p * hw + (sq & 7) + pad;
-      const int off = row * 128 + (((c >> 3) ^ (row & 7)) << 4) + ((c & 7) << 1);
-      *reinterpret_cast<uint16_t*>(smem_a + off) = ptx::pack_h16(v, args.fp16 != 0);
+    const int per_board = args.in_planes * 64, total = args.nb * per_board;
+    constexpr int PF = 8;   // values per thread requested at once (the loads used to be waited for one by one)
+    for (int base = 0; base < total || base == 0; base += nthr * PF) {
+      float v[PF];
+      if (args.planes) {
+        // fp32 NCHW planes: this tile's boards are contiguous, element i of the tile is planes[n0 * per_board + i]
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+          const int i = base + j * nthr + t;
+          v[j] = (i < total && n0 + i / per_board < args.batch) ? args.planes[static_cast<size_t>(n0) * per_board + i] : 0.0f;
+        }
+      }
+      if (base == 0) {
+        for (int i = t; i < rows * 8; i += nthr) tile16[i] = make_uint4(0u, 0u, 0u, 0u);
+        // board records are fetched once (17 words per board; they may live in the caller's pinned host memory) and
+        // decoded from shared memory
+        if (args.records && t < args.nb * 17) {
+          const int p = t / 17, wd = t - p * 17;
+          s_rec[p * 17 + wd] = n0 + p < args.batch ? reinterpret_cast<const uint32_t*>(args.records + static_cast<size_t>(n0 + p) * 68)[wd] : 0u;
+        }
+        asm volatile("bar.sync 2, 224;" ::: "memory");
+      }
+#pragma unroll
+      for (int j = 0; j < PF; ++j) {
+        const int i = base + j * nthr + t;
+        if (i >= total) break;
+        const int p = i / per_board, rem = i - p * per_board;
+        const int c = rem >> 6, sq = rem & 63;   // consecutive threads -> consecutive squares of one plane (coalesced)
+        if (n0 + p >= args.batch) continue;
+        const float val = args.planes ? v[j] : record_plane_value(reinterpret_cast<const uint8_t*>(s_rec + p * 17), c, sq);
+        const int row = ((sq >> 3) + pad) * args.nb * hw + p * hw + (sq & 7) + pad;
+        const int off = row * 128 + (((c >> 3) ^ (row & 7)) << 4) + ((c & 7) << 1);
+        *reinterpret_cast<uint16_t*>(smem_a + off) = ptx::pack_h16(val, args.fp16 != 0);
+      }
     }
     ptx::fence_proxy_async();   // generic-proxy writes -> the tensor core's async-proxy reads
     asm volatile("bar.sync 2, 224;" ::: "memory");
@@ -481,6 +496,9 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
         continue;
       }
       if (lane == 0) {
+        // (Requesting each plane as soon as the slices that produce ITS channels have published was tried: the planes
+        // become ready in any order but are consumed in order, and every request needs its own acquire fence --
+        // 5.9 us per layer instead of 4.85.)
         wait_tile(args, tile_flags, target);   // the tile's CTAs have published the previous layer
         ptx::fence_proxy_async_all();  // other CTAs' generic-proxy stores -> our async-proxy (TMA) reads
         if (args.trace && blockIdx.x == trace_cta) args.trace[l * 8 + 0] = clock64();
@@ -722,13 +740,18 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   // H2: this CTA's labels of the policy Dense layer and its hidden units of the value head, from staged weights;
   //     per-128-label softmax statistics and per-16-unit value partials are published for the tile.
   // H3: after the tile's second rendezvous every CTA normalises its own labels; slice 0 writes the value.
+  // EXPERIMENT (dbg bit 3): the heads run twice; the second pass shows what they cost with warm instruction caches
+#pragma unroll 1
+  for (int hpass = 0; hpass < ((args.dbg & 8) ? 2 : 1); ++hpass) {
+  long long* kt = hpass == 0 ? ktrace : (ktrace ? args.trace + 222 : nullptr);
   const int hf_total = args.pf + args.vf;
   const int kp = args.pf * 64, kv = args.vf * 64;
-  if (ktrace) ktrace[2] = clock64();
+  if (kt) kt[2] = clock64();
   // requested now, used after H1: this thread's label biases and legal-move mask bytes, this slice's hidden-unit constants
   const int n_lchunks = (hg.upl * LABEL_UNIT + LABEL_CHUNK - 1) / LABEL_CHUNK;
   float pbias[LCHUNKS_MAX];
   bool pmask[LCHUNKS_MAX][2];
+  const float vbias2 = args.vfc2_b[0];
 #pragma unroll
   for (int c = 0; c < LCHUNKS_MAX; ++c) {
     const int n = lab0 + c * LABEL_CHUNK + threadIdx.x;
@@ -747,37 +770,32 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   const unsigned* tile_flags = tile_flag_line(args, s_near_copy, tile);   // written by warp 3 long before the __syncthreads above
   if (threadIdx.x == 0) wait_tile(args, tile_flags, args.base + L);   // the tile's CTAs have stored their partials
   __syncthreads();
-  if (ktrace) ktrace[3] = clock64();
+  if (kt) kt[3] = clock64();
   {
-    // up to four (board, head filter, square) items per thread; all of their partials are requested before any is summed
-    constexpr int ITEMS = (2 * HEAD_FILTERS_MAX * 64 + THREADS - 1) / THREADS;
-    const int n_items = args.nb * hf_total * 64;
-    float part[ITEMS][16], hb[ITEMS];
+    // one thread per (board, head filter, four squares): sixteen 16-byte loads, all requested before any is summed
+    const int n_quads = args.nb * hf_total * 16;   // <= 2 * 8 * 16 = THREADS
+    const int t = threadIdx.x;
+    const int q = t & 15, f6 = (t >> 4) % hf_total, bl = t / (16 * hf_total);
+    const bool on = t < n_quads && n0 + bl < args.batch;
+    const float4* hp = reinterpret_cast<const float4*>(
+        args.hpart + ((static_cast<size_t>(on ? n0 + bl : 0) * 16) * HEAD_FILTERS_MAX + f6) * 64 + q * 4);
+    float4 part[16];
 #pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-      const int i = threadIdx.x + it * THREADS;
-      const int sq = i & 63, f6 = (i >> 6) % hf_total, bl = i / (64 * hf_total);
-      const bool on = i < n_items && n0 + bl < args.batch;
-      const float* hp = args.hpart + ((static_cast<size_t>(on ? n0 + bl : 0) * 16) * HEAD_FILTERS_MAX + f6) * 64 + sq;
+    for (int g = 0; g < 16; ++g)
+      part[g] = (on && g * 16 < args.filters) ? hp[static_cast<size_t>(g) * HEAD_FILTERS_MAX * 16] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float hb = on ? args.head_b[f6] : 0.0f;
+    if (t < n_quads) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int g = 0; g < 16; ++g) part[it][g] = (on && g * 16 < args.filters) ? hp[static_cast<size_t>(g) * HEAD_FILTERS_MAX * 64] : 0.0f;
-      hb[it] = on ? args.head_b[f6] : 0.0f;
-    }
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-      const int i = threadIdx.x + it * THREADS;
-      if (i >= n_items) break;
-      const int sq = i & 63, f6 = (i >> 6) % hf_total, bl = i / (64 * hf_total);
-      float v = 0.0f;
-#pragma unroll
-      for (int g = 0; g < 16; ++g) v += part[it][g];
-      v = n0 + bl < args.batch ? fmaxf(v + hb[it], 0.0f) : 0.0f;
+      for (int g = 0; g < 16; ++g) { v.x += part[g].x; v.y += part[g].y; v.z += part[g].z; v.w += part[g].w; }
+      v.x = on ? fmaxf(v.x + hb, 0.0f) : 0.0f; v.y = on ? fmaxf(v.y + hb, 0.0f) : 0.0f;
+      v.z = on ? fmaxf(v.z + hb, 0.0f) : 0.0f; v.w = on ? fmaxf(v.w + hb, 0.0f) : 0.0f;
       // Keras channels-first Flatten: index c*64 + square (model_chess.py:80,89); policy filters first, then value
-      s_feat[bl * 512 + (f6 < args.pf ? f6 * 64 + sq : kp + (f6 - args.pf) * 64 + sq)] = v;
+      *reinterpret_cast<float4*>(&s_feat[bl * 512 + (f6 < args.pf ? f6 * 64 : kp + (f6 - args.pf) * 64) + q * 4]) = v;
     }
   }
   __syncthreads();
-  if (ktrace) ktrace[4] = clock64();
+  if (kt) kt[4] = clock64();
 
   // ---- H2 ----
   float lg[LCHUNKS_MAX][2];   // [label chunk][board of the tile]: this thread's logits (n_lchunks is checked on the host)
@@ -791,23 +809,38 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
         stage_head_weights(args, s_wp, s_wv, hw_full, lane, unit_first + 2 * c, units_in_chunk(c), false, 0, 0);
     }
     ptx::mbar_wait(hw_full, c & 1, args.err_flag, ERR_HEADW);
-    if (ktrace && c == 0) ktrace[5] = clock64();
+    if (kt && c == 0) kt[5] = clock64();
     const int n = lab0 + c * LABEL_CHUNK + threadIdx.x;
     const bool valid = c * LABEL_CHUNK + threadIdx.x < lab_cnt;
     float a0 = 0.0f, a1 = 0.0f;
     if (valid) {
       const float bn = pbias[c];
       const float* wcol = s_wp + (threadIdx.x >> 7) * kp * LABEL_UNIT + (threadIdx.x & 127);
-#pragma unroll 8
-      for (int k = 0; k < kp; ++k) {
-        const float wv = wcol[k * LABEL_UNIT];
-        a0 = fmaf(s_feat[k], wv, a0);
-        a1 = fmaf(s_feat[512 + k], wv, a1);
+      // (the features are the same for every thread: one 16-byte broadcast load per four k)
+      const float4* f4 = reinterpret_cast<const float4*>(s_feat);
+#pragma unroll 4
+      for (int k = 0; k < kp; k += 4) {
+        const float4 fa = f4[k >> 2];
+        a0 = fmaf(fa.x, wcol[k * LABEL_UNIT], a0);
+        a0 = fmaf(fa.y, wcol[(k + 1) * LABEL_UNIT], a0);
+        a0 = fmaf(fa.z, wcol[(k + 2) * LABEL_UNIT], a0);
+        a0 = fmaf(fa.w, wcol[(k + 3) * LABEL_UNIT], a0);
+      }
+      if (args.nb == 2) {
+#pragma unroll 4
+        for (int k = 0; k < kp; k += 4) {
+          const float4 fa = f4[128 + (k >> 2)];
+          a1 = fmaf(fa.x, wcol[k * LABEL_UNIT], a1);
+          a1 = fmaf(fa.y, wcol[(k + 1) * LABEL_UNIT], a1);
+          a1 = fmaf(fa.z, wcol[(k + 2) * LABEL_UNIT], a1);
+          a1 = fmaf(fa.w, wcol[(k + 3) * LABEL_UNIT], a1);
+        }
       }
       a0 += bn; a1 += bn;
     }
 #pragma unroll
     for (int bl = 0; bl < 2; ++bl) {
+      if (bl >= args.nb) break;
       const int b = n0 + bl;
       const bool on = valid && bl < args.nb && b < args.batch && pmask[c][bl];
       const float x = on ? (bl ? a1 : a0) : -INFINITY;
@@ -837,7 +870,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       }
     }
   }
-  if (ktrace) ktrace[6] = clock64();
+  if (kt) kt[6] = clock64();
   // value head hidden layer (model_chess.py:91): unit u = hid0 + (t & (hsp-1))... every thread takes one (unit, k-eighth):
   // eight partial dot products per unit over k = kq, kq+8, ..., added in order
   {
@@ -853,28 +886,29 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
           const float wv = staged ? s_wv[(u >> 4) * value_group_pitch(args.vf) + k * HID_GROUP + (u & 15)]
                                   : __ldg(args.vfc1_w + static_cast<size_t>(k) * args.value_fc + hid0 + u);
           a0 = fmaf(s_feat[kp + k], wv, a0);
-          a1 = fmaf(s_feat[512 + kp + k], wv, a1);
+          if (args.nb == 2) a1 = fmaf(s_feat[512 + kp + k], wv, a1);
         }
       s_part[i] = a0;
       s_part[per + i] = a1;
     }
     __syncthreads();
-    // one thread per (board, 16-unit group): hidden = relu(sum of the 8 partials + bias), times the output weights
-    for (int i = threadIdx.x; i < 2 * hg.gps; i += THREADS) {
-      const int bl = i / hg.gps, gl = i % hg.gps, b = n0 + bl, grp = slice * hg.gps + gl;
-      if (bl < args.nb && b < args.batch && grp < hg.groups_total) {
-        float pv = 0.0f;
-        for (int uu = 0; uu < HID_GROUP; ++uu) {
-          const int u = gl * HID_GROUP + uu, hu = hid0 + u;
-          if (hu < args.value_fc) {
-            float hsum = 0.0f;
+    // one thread per (board, hidden unit): hidden = relu(sum of the 8 partials + bias) times its output weight; the 16
+    // products of a group are added by a fixed shuffle tree (whole warps take part: a group is half a warp)
+    const int n_hid = args.nb * hg.hsp;
+    for (int i = threadIdx.x; i < ((n_hid + 31) & ~31); i += THREADS) {
+      const int bl = i / hg.hsp, u = i - bl * hg.hsp, b = n0 + bl;
+      float pv = 0.0f;
+      if (i < n_hid && u < hid_cnt) {
+        float hsum = 0.0f;
 #pragma unroll
-            for (int kq = 0; kq < 8; ++kq) hsum += s_part[bl * per + kq * hg.hsp + u];
-            pv = fmaf(fmaxf(hsum + s_vb[u], 0.0f), s_vw[u], pv);
-          }
-        }
-        args.hstats[static_cast<size_t>(b) * HSTAT_FLOATS + 2 * LABEL_UNITS_MAX + grp] = pv;
+        for (int kq = 0; kq < 8; ++kq) hsum += s_part[bl * per + kq * hg.hsp + u];
+        pv = fmaxf(hsum + s_vb[u], 0.0f) * s_vw[u];
       }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
+      const int grp = slice * hg.gps + (u >> 4);
+      if (i < n_hid && (u & 15) == 0 && b < args.batch && grp < hg.groups_total)
+        args.hstats[static_cast<size_t>(b) * HSTAT_FLOATS + 2 * LABEL_UNITS_MAX + grp] = pv;
     }
   }
   __threadfence();
@@ -884,7 +918,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     wait_tile(args, tile_flags, args.base + 1u + L);
   }
   __syncthreads();
-  if (ktrace) ktrace[7] = clock64();
+  if (kt) kt[7] = clock64();
 
   // ---- H3: softmax over all of the board's labels (model_chess.py:83) from the units' statistics; tanh value ----
   // the tile's statistics come in with one L2 read per thread (ld.cg: other CTAs wrote them)
@@ -893,19 +927,25 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     s_stat[threadIdx.x] = (bl < args.nb && n0 + bl < args.batch) ? ptx::ld_cg_f32(args.hstats + static_cast<size_t>(n0 + bl) * HSTAT_FLOATS + j) : 0.0f;
   }
   __syncthreads();
+  // one warp per board: the maximum over the units and the normaliser (one expf per lane, fixed shuffle trees)
+  if (warp < args.nb) {
+    const float* st = s_stat + warp * HSTAT_FLOATS;
+    const float mu = lane < hg.units_total ? st[2 * lane] : -INFINITY, su = lane < hg.units_total ? st[2 * lane + 1] : 0.0f;
+    float mx = mu;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float z = mu != -INFINITY ? su * expf(mu - mx) : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    if (lane == 0) { s_red[2 * warp] = mx; s_red[2 * warp + 1] = z > 0.0f ? 1.0f / z : 0.0f; }
+  }
+  __syncthreads();
 #pragma unroll
   for (int bl = 0; bl < 2; ++bl) {
     const int b = n0 + bl;
     if (bl >= args.nb || b >= args.batch) continue;
     const float* st = s_stat + bl * HSTAT_FLOATS;
-    float mx = -INFINITY;
-    for (int u = 0; u < hg.units_total; ++u) mx = fmaxf(mx, st[2 * u]);
-    float z = 0.0f;
-    for (int u = 0; u < hg.units_total; ++u) {
-      const float mu = st[2 * u], su = st[2 * u + 1];
-      if (mu != -INFINITY) z += su * expf(mu - mx);
-    }
-    const float inv = z > 0.0f ? 1.0f / z : 0.0f;
+    const float mx = s_red[2 * bl], inv = s_red[2 * bl + 1];
 #pragma unroll
     for (int c = 0; c < LCHUNKS_MAX; ++c) {
       if (c >= n_lchunks) break;
@@ -916,10 +956,12 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       }
     }
     if (slice == 0 && threadIdx.x == 0) {
-      float v = args.vfc2_b[0];
+      float v = vbias2;
       for (int g = 0; g < hg.groups_total; ++g) v += st[2 * LABEL_UNITS_MAX + g];
       args.value[b] = tanhf(v);
     }
+  }
+  if (kt) kt[11] = clock64();
   }
   if (ktrace) {
     long long gt;

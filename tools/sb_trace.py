@@ -22,6 +22,8 @@ full = np.zeros(240, np.int64)
 _lib.check(ev._handle, lib.caz_debug_sb_trace(ev._handle, 0, full.ctypes.data_as(ctypes.c_void_p), full.size))
 print("warps reach the post-tower barrier at (us):", " ".join(f"{(v - st[0]) / 1965.0:7.2f}" for v in full[200:208]),
       "| leave it at", f"{(full[216] - st[0]) / 1965.0:7.2f}")
+print("heads pass 1 (us): start, tile ready, feat, staged, policy+stats, 2nd rendezvous, end:", " ".join(f"{(v - st[0]) / 1965.0:7.2f}" for v in list(st[15*8+2:15*8+8]) + [st[16*8+3]]))
+print("heads pass 2 (us):", " ".join(f"{(v - st[0]) / 1965.0:7.2f}" for v in list(full[224:230]) + [full[233]]))
 st = st.reshape(17, 8).astype(np.float64)
 t0 = st[0, 0]
 us = (st - t0) / 1965.0
