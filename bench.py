@@ -280,7 +280,7 @@ def latency_probe(ev, planes16, calls=1000):
     for _ in range(min(calls, 300)):
         ev.eval_device(d_x.data_ptr(), 16, d_p.data_ptr(), d_v.data_ptr())
         st = ev.profile_read(reset=True)
-        lib_dev.append(sum(v["ms"] for v in st.values()) * 1e-3)
+        lib_dev.append(sum(v["ms"] for v in st.values() if v["launches"] > 0) * 1e-3)
     ev.profile(False)
     q = lambda a, f: float(np.quantile(np.asarray(a), f) * 1e6)
     return {"batch": 16, "calls": calls, "host_call_p50_us": q(host, 0.5), "host_call_p99_us": q(host, 0.99),

@@ -86,6 +86,7 @@ struct caz_handle {
   CUtensorMap sb_tm_xb[2], sb_tm_y[2];  // halo views for 1 and 2 boards per CTA tile
   CUtensorMap sb_tm_w_stem[3], sb_tm_w_tower[3];      // weight maps for N_s = 16, 32, 64
   int sb_force_nb = 0;
+  unsigned char* sb_sm_near = nullptr;   // [smid] -> which flag-line class (copy) is the near one, 0xFF unknown
   unsigned* sb_counter = nullptr;   // progress flags of the small-batch kernel: 32 candidate grains of 4 KB
   uint16_t sb_flag_line[2][caz::sb::MAX_TILES];   // [copy][tile] -> candidate line of that tile's flags (copy 0 / 1: the two latency classes)
   bool sb_two_dies = false;
@@ -472,6 +473,37 @@ __global__ void flag_line_probe_kernel(unsigned* cand, unsigned* out_cycles) {
   }
 }
 
+// Which of the two latency classes is the NEAR one for each SM?  One CTA per SM (the shared-memory request keeps them
+// apart on an idle device) times publish -> visible on a line of each class, best of 32 rounds, and records the winner
+// under its %smid.  The forward kernel used to decide this itself during layer 0 with two rounds per launch, and a CTA
+// that guessed wrong slowed its whole board tile by 0.4 us per layer (5-7 us per pass, in ~half of the launches).
+__global__ void sm_near_probe_kernel(unsigned* cand, const uint16_t* line0, const uint16_t* line1, int n_lines, unsigned char* near_of_sm,
+                                     unsigned* cycles_of_sm, unsigned* turn) {
+  if (threadIdx.x != 0) return;
+  // one SM at a time (CTAs are dispatched in block order, so waiting for the lower block ids cannot deadlock; the wait is
+  // bounded all the same): concurrent probes of the same lines made a few SMs look equidistant from both classes
+  for (unsigned spins = 0; caz::ptx::ld_acquire_gpu(turn) != blockIdx.x && spins < (1u << 22); ++spins) __nanosleep(200);
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  unsigned best[2] = {0xffffffffu, 0xffffffffu};
+  for (unsigned round = 1; round <= 32; ++round)
+    for (int c = 0; c < 2; ++c) {
+      unsigned* p = cand + static_cast<size_t>((c ? line1 : line0)[round % (n_lines < 8 ? n_lines : 8)]) * 32 + 30;
+      const unsigned val = 0x5a000000u + round + (blockIdx.x << 8);
+      const long long t0 = clock64();
+      caz::ptx::publish_flag_gpu(p, val);
+      unsigned spins = 0;
+      while (caz::ptx::ld_relaxed_gpu(p) != val && ++spins < (1u << 20)) {}
+      const unsigned d = static_cast<unsigned>(clock64() - t0);
+      best[c] = d < best[c] ? d : best[c];
+    }
+  near_of_sm[smid] = best[1] < best[0] ? 1 : 0;
+  cycles_of_sm[2 * smid] = best[0];
+  cycles_of_sm[2 * smid + 1] = best[1];
+  __threadfence();
+  atomicAdd(turn, 1u);
+}
+
 // Lays out the two copies of the per-tile flag lines (conv_sb.cuh, Args::flag_line) on lines of the two latency
 // classes.  Without a clear split (one die, or noise) both copies still get distinct lines: nothing depends on the
 // split being right except speed.
@@ -501,6 +533,40 @@ int calibrate_flag_copies(caz_handle* h) {
   if (getenv("CAZ_SB_VERBOSE"))
     fprintf(stderr, "caz: flag lines: two latency classes=%d (gap %u, split %u, min %u, median %u, max %u)\n", (int)h->sb_two_dies, gap,
             split, sorted.front(), sorted[FLAG_CANDIDATES / 2], sorted.back());
+  // per-SM table of the nearer class (only with a clear split; otherwise the forward kernel probes for itself)
+  if (h->sb_two_dies && !getenv("CAZ_SB_NO_SM_TABLE")) {
+    const int n_sm_max = 1024;
+    uint16_t* d_lines = nullptr;
+    unsigned* d_c = nullptr;
+    CU_TRY(h, cudaMalloc(&h->sb_sm_near, n_sm_max));
+    CU_TRY(h, cudaMemset(h->sb_sm_near, 0xFF, n_sm_max));
+    CU_TRY(h, cudaMalloc(&d_lines, 2 * caz::sb::MAX_TILES * sizeof(uint16_t)));
+    CU_TRY(h, cudaMalloc(&d_c, (2 * n_sm_max + 1) * sizeof(unsigned)));
+    CU_TRY(h, cudaMemset(d_c, 0, (2 * n_sm_max + 1) * sizeof(unsigned)));
+    CU_TRY(h, cudaMemcpy(d_lines, h->sb_flag_line, 2 * caz::sb::MAX_TILES * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    const int probe_smem = 160 * 1024;   // one CTA per SM
+    CU_TRY(h, cudaFuncSetAttribute(sm_near_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, probe_smem));
+    sm_near_probe_kernel<<<h->num_sms, 32, probe_smem, h->stream>>>(h->sb_counter, d_lines, d_lines + caz::sb::MAX_TILES, caz::sb::MAX_TILES,
+                                                                    h->sb_sm_near, d_c, d_c + 2 * n_sm_max);
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (getenv("CAZ_SB_VERBOSE")) {
+      std::vector<unsigned char> nr(n_sm_max);
+      std::vector<unsigned> cy(2 * n_sm_max);
+      CU_TRY(h, cudaMemcpy(nr.data(), h->sb_sm_near, n_sm_max, cudaMemcpyDeviceToHost));
+      CU_TRY(h, cudaMemcpy(cy.data(), d_c, cy.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+      int cnt[3] = {0, 0, 0};
+      unsigned min_margin = 0xffffffffu;
+      for (int i = 0; i < n_sm_max; ++i) {
+        cnt[nr[i] <= 1 ? nr[i] : 2]++;
+        if (nr[i] <= 1) { const unsigned m = cy[2 * i] > cy[2 * i + 1] ? cy[2 * i] - cy[2 * i + 1] : cy[2 * i + 1] - cy[2 * i]; if (m < min_margin) min_margin = m; }
+      }
+      fprintf(stderr, "caz: per-SM near class: %d SMs -> class 0, %d -> class 1, smallest margin %u cycles\n", cnt[0], cnt[1], min_margin);
+      if (getenv("CAZ_SB_VERBOSE")[0] == '2')
+        for (int i = 0; i < h->num_sms + 8; ++i) fprintf(stderr, "  sm %d: %u / %u -> %d\n", i, cy[2 * i], cy[2 * i + 1], (int)nr[i]);
+    }
+    cudaFree(d_lines);
+    cudaFree(d_c);
+  }
   return CAZ_OK;
 }
 
@@ -648,6 +714,7 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   args.policy = d_policy;
   args.value = d_value;
   args.flag_base = h->sb_counter;
+  args.sm_near = h->sb_sm_near;
   for (int c = 0; c < 2; ++c)
     for (int t = 0; t < caz::sb::MAX_TILES; ++t) args.flag_line[c][t] = h->sb_flag_line[c][t];
 
@@ -941,6 +1008,7 @@ void caz_destroy(caz_handle* h) {
   if (h->sb_hpart) cudaFree(h->sb_hpart);
   if (h->sb_hstats) cudaFree(h->sb_hstats);
   if (h->sb_trace) cudaFree(h->sb_trace);
+  if (h->sb_sm_near) cudaFree(h->sb_sm_near);
   void* ptrs[] = {h->pfc_wb, h->vfc1_wb, h->head_w, h->head_b, h->pfc_w, h->pfc_b, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, h->in_act,
                   h->act[0], h->act[1], h->act[2], h->featp, h->featv, h->vhid, h->a3p, h->a3v, h->w3p, h->w3v, h->bias3p, h->d_planes, h->d_policy, h->d_value,
                   h->d_mask, h->d_records, h->puct_buf, h->d_planes2, h->d_policy2, h->d_value2, h->d_mask2,

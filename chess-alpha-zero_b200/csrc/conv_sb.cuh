@@ -92,6 +92,7 @@ struct Args {
   // from each latency class (caz_abi.cu classifies candidate lines at creation): a CTA publishes to both and polls the
   // one that answers faster from its own SM (probed once per launch, off the critical path).
   unsigned* flag_base;
+  const unsigned char* sm_near;       // nullptr or [%smid] -> the copy that is near for that SM (0xFF: unknown), caz_abi.cu
   uint16_t flag_line[2][MAX_TILES];   // [copy][tile] -> line index (x 32 words)
   unsigned base;              // flag value that means "nothing of this launch done yet" (monotonic across launches)
   long long* trace;           // nullptr or [n_layers+1][8] clock64 stamps of CTA 0 (see caz_debug_sb_trace)
@@ -477,8 +478,14 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
           else ptx::mbar_arrive_cluster(stem_ready, 0);   // release.cluster: this CTA's tile is complete
           // while layer 0 computes: which of the tile's two flag lines answers faster from this SM?  Publish a value
           // to this slice's scratch word of each line and time until a poll sees it (two rounds, best of each).
-          unsigned best[2] = {0xffffffffu, 0xffffffffu};
-          for (unsigned round = 1; round <= 2; ++round)
+          // which of the tile's two flag lines is the near one for this SM: from the table made at creation, else
+          // (no table, unknown SM) measured here while layer 0 computes
+          unsigned smid;
+          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+          const unsigned known = args.sm_near ? args.sm_near[smid] : 0xFFu;
+          unsigned best[2] = {known == 1u ? 1u : 0u, known == 1u ? 0u : 1u};
+          if (known > 1u) best[0] = best[1] = 0xffffffffu;
+          for (unsigned round = 1; round <= 2 && known > 1u; ++round)
             for (int c = 0; c < 2; ++c) {
               unsigned* pw = tile_flag_line(args, c, tile) + 16 + slice;
               const unsigned val = args.base + round;
