@@ -74,6 +74,7 @@ struct caz_handle {
   std::vector<ConvLayer> convs;  // stem, then conv1/conv2 of each block
   bool snake = true;             // odd layers walk the batch backwards (CAZ_SNAKE=0 turns it off)
   bool l2_prefetch = false;       // CAZ_L2_PREFETCH=0 turns the one-tile-ahead L2 prefetches off
+  bool pdl = true;               // programmatic dependent launch between the per-layer convolutions; CAZ_NO_PDL=1 turns it off
   bool use_2cta = true;          // per-layer convolutions as CTA pairs (cta_group::2); CAZ_CONV_2CTA=0 turns it off
   // weight slabs the layers point into: the tower's layers are contiguous so that one tensor map covers them
   void* w_stem = nullptr;
@@ -415,6 +416,7 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
     args.m_rows = batch * 64;
     args.out_rm = nullptr;
     args.l2_prefetch = h->l2_prefetch ? 1 : 0;
+    args.pdl = 0;
     args.reverse = (h->snake && (li & 1)) ? 1 : 0;
     if (const char* e = getenv("CAZ_DBG_EPI")) {   // timing experiments only (results are wrong): drop epilogue traffic
       const int m = atoi(e);
@@ -428,7 +430,20 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
       const int pairs = (args.num_tiles + 1) / 2;
       const int max_pairs = h->num_sms / 2;
       const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
-      caz::tc2::conv_tc2_kernel<<<grid, caz::tc2::THREADS, caz::tc2::SMEM_BYTES, h->stream>>>(*tmap_in, L.tmap_w2, args);
+      // consecutive layers overlap (prologue and first weights of layer l+1 under the tail of layer l): see conv_tc2.cuh
+      args.pdl = h->pdl ? 1 : 0;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(caz::tc2::THREADS);
+      cfg.dynamicSmemBytes = caz::tc2::SMEM_BYTES;
+      cfg.stream = h->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = h->pdl ? 1 : 0;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, caz::tc2::conv_tc2_kernel, *tmap_in, L.tmap_w2, args);
+      if (e != cudaSuccess) return fail(h, CAZ_ERR_CUDA, fmt("launch of conv_tc2_kernel failed: %s", cudaGetErrorString(e)));
       return check_launch(h, "conv_tc2_kernel");
     }
     const int grid = args.num_tiles < h->num_sms ? args.num_tiles : h->num_sms;
@@ -1115,6 +1130,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
     CREATE_TRY(cudaFuncSetAttribute(caz::tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc::SMEM_BYTES));
     CREATE_TRY(cudaFuncSetAttribute(caz::tc2::conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc2::SMEM_BYTES));
     if (const char* e = getenv("CAZ_CONV_2CTA")) h->use_2cta = atoi(e) != 0;
+    if (getenv("CAZ_NO_PDL")) h->pdl = false;
     if (const char* e = getenv("CAZ_L2_PREFETCH")) h->l2_prefetch = atoi(e) != 0;
     if (const char* e = getenv("CAZ_SNAKE")) h->snake = atoi(e) != 0;
   } else {

@@ -87,6 +87,7 @@ struct ConvArgs {
   float* out_rm;            // nullptr or fp32 [m_rows][n_total] row-major; bias is then [n_tiles * n]
   int reverse;              // walk the tiles from the last to the first (CTA-pair kernel; see conv_tc2.cuh)
   int l2_prefetch;          // pull the next tile's activations / residual into L2 one tile ahead
+  int pdl;                  // launched with programmatic stream serialization (CTA-pair kernel, see conv_tc2.cuh)
   int* err_flag;
 };
 

@@ -14,6 +14,7 @@
 //     accumulator-full barriers of BOTH CTAs
 //   * both CTAs' epilogue warps drain their own 128 accumulator rows and arrive on the leader's accumulator-empty
 //     barrier (8 arrivals: 4 local, 4 remote)
+//   * consecutive layers overlap through programmatic dependent launch (args.pdl, see below)
 #pragma once
 #include <cuda_bf16.h>
 
@@ -106,6 +107,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   ptx::cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+
+  // Programmatic dependent launch: a layer is one launch, and at a few hundred boards most of a launch is prologue, launch
+  // latency and tail.  The NEXT layer's grid may therefore start as soon as every CTA of this one has got here: it sets up
+  // its barriers and TMEM and streams its first weights (constants) on idle SMs, and only then waits for this grid to
+  // complete (griddepcontrol.wait: completion and visibility of everything the previous grid wrote) before it touches an
+  // activation -- every global read of activations and every global write sits behind that wait.
+  if (args.pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp != 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
 
   if (warp == 0) {
     // ===================== weight producer: this CTA's half of the output channels =====================
