@@ -747,7 +747,9 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   // H2: this CTA's labels of the policy Dense layer and its hidden units of the value head, from staged weights;
   //     per-128-label softmax statistics and per-16-unit value partials are published for the tile.
   // H3: after the tile's second rendezvous every CTA normalises its own labels; slice 0 writes the value.
-  // EXPERIMENT (dbg bit 3): the heads run twice; the second pass shows what they cost with warm instruction caches
+  // Measurement switch (CAZ_SB_DBG bit 3, tools/sb_trace.py): the heads run twice in one launch.  The second pass costs
+  // what the first does, i.e. the heads are not bound by cold instruction or data caches.  (Its outputs are not valid:
+  // the value phase reuses the policy weights' shared memory.)
 #pragma unroll 1
   for (int hpass = 0; hpass < ((args.dbg & 8) ? 2 : 1); ++hpass) {
   long long* kt = hpass == 0 ? ktrace : (ktrace ? args.trace + 222 : nullptr);
@@ -769,11 +771,9 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       pmask[c][bl] = !(valid && args.mask && bl < args.nb && n0 + bl < args.batch) ||
                      args.mask[static_cast<size_t>(n0 + bl) * args.n_labels + n] != 0;
   }
-  {
-    const bool on = threadIdx.x < hid_cnt;
-    s_vb[threadIdx.x] = on ? args.vfc1_b[hid0 + threadIdx.x] : 0.0f;
-    s_vw[threadIdx.x] = on ? args.vfc2_w[hid0 + threadIdx.x] : 0.0f;
-  }
+  // (kept in registers until H1's loads are on their way: a shared-memory store would wait for its load right here)
+  const float vb_r = threadIdx.x < hid_cnt ? args.vfc1_b[hid0 + threadIdx.x] : 0.0f;
+  const float vw_r = threadIdx.x < hid_cnt ? args.vfc2_w[hid0 + threadIdx.x] : 0.0f;
   const unsigned* tile_flags = tile_flag_line(args, s_near_copy, tile);   // written by warp 3 long before the __syncthreads above
   if (threadIdx.x == 0) wait_tile(args, tile_flags, args.base + L);   // the tile's CTAs have stored their partials
   __syncthreads();
@@ -791,6 +791,8 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     for (int g = 0; g < 16; ++g)
       part[g] = (on && g * 16 < args.filters) ? hp[static_cast<size_t>(g) * HEAD_FILTERS_MAX * 16] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float hb = on ? args.head_b[f6] : 0.0f;
+    s_vb[threadIdx.x] = vb_r;
+    s_vw[threadIdx.x] = vw_r;
     if (t < n_quads) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
