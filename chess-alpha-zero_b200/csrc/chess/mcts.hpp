@@ -116,8 +116,9 @@ struct FastRng {
     for (;;) {
       const float x = normal(), t = 1.0f + c * x;
       if (t <= 0.0f) continue;
-      const float v = t * t * t, u = uniform_open();
-      if (std::log(u) < 0.5f * x * x + d - d * v + d * std::log(v)) { g = d * v; break; }
+      const float v = t * t * t, u = uniform_open(), x2 = x * x;
+      // the paper's squeeze accepts ~92 % of the candidates without the two logarithms
+      if (u < 1.0f - 0.0331f * x2 * x2 || std::log(u) < 0.5f * x2 + d - d * v + d * std::log(v)) { g = d * v; break; }
     }
     if (alpha < 1.0f) g *= std::exp(std::log(uniform_open()) / alpha);
     return g;
