@@ -476,8 +476,10 @@ struct Position {
   }
   // the reference's tree key, state_key(env) = fen() without the fullmove number (player_chess.py:391-398):
   // everything in the transposition key plus the halfmove clock
-  uint64_t state_key() const {
-    uint64_t k = transposition_key() ^ (0x9E3779B97F4A7C15ull * static_cast<uint64_t>(halfmove + 1));
+  uint64_t state_key() const { return state_key_of(transposition_key(), halfmove); }
+  // (the search keeps the transposition key of the current position in its move stack: no second pass over the board)
+  static uint64_t state_key_of(uint64_t transposition, int halfmove_clock) {
+    uint64_t k = transposition ^ (0x9E3779B97F4A7C15ull * static_cast<uint64_t>(halfmove_clock + 1));
     k ^= k >> 29;
     return k * 0xBF58476D1CE4E5B9ull;
   }
@@ -532,10 +534,15 @@ struct Position {
   // the 68-byte board record of caz_encode (include/caz_b200.h): the position as fen() writes it
   void record(uint8_t* rec) const {
     static const int code_of[6] = {6, 5, 4, 3, 2, 1};   // "KQRBNPkqrbnp": K=1 Q=2 R=3 B=4 N=5 P=6, black +6
-    for (int r = 7; r >= 0; --r)
-      for (int f = 0; f < 8; ++f) {
-        const int sq = r * 8 + f, p = piece_at(sq);
-        rec[(7 - r) * 8 + f] = p == NO_PIECE ? 0 : static_cast<uint8_t>(code_of[p] + ((by_color[BLACK] & sq_bb(sq)) ? 6 : 0));
+    std::memset(rec, 0, 64);   // byte (7 - rank) * 8 + file = square ^ 56; one store per piece on the board
+    for (int c = 0; c < 2; ++c)
+      for (int p = 0; p < 6; ++p) {
+        BB b = by_piece[p] & by_color[c];
+        const uint8_t code = static_cast<uint8_t>(code_of[p] + (c == BLACK ? 6 : 0));
+        while (b) {
+          rec[lsb(b) ^ 56] = code;
+          b &= b - 1;
+        }
       }
     rec[64] = static_cast<uint8_t>((turn == BLACK ? 1 : 0) | ((castling & CR_WK) ? 2 : 0) | ((castling & CR_WQ) ? 4 : 0) |
                                    ((castling & CR_BK) ? 8 : 0) | ((castling & CR_BQ) ? 16 : 0));
@@ -567,20 +574,32 @@ inline Move move_from_uci(const std::string& s) {
 // A game: the position plus what result(claim_draw=True) needs from the move stack.
 struct Game {
   Position pos;
-  struct Hist { uint64_t key; bool irreversible_in; };   // key of a position, was the move INTO it irreversible
+  // key of a position; was the move INTO it irreversible; how often the position has occurred since the last
+  // irreversible move (this occurrence included); how many entries since then were repeats (occ >= 2)
+  struct Hist { uint64_t key; bool irreversible_in; uint16_t occ; uint16_t repeats; };
   std::vector<Hist> hist;
   int num_halfmoves = 0;   // ChessEnv.num_halfmoves
 
   void reset(const Position& p) {
     pos = p;
     hist.clear();
-    hist.push_back({pos.transposition_key(), true});
+    hist.push_back({pos.transposition_key(), true, 1, 0});
     num_halfmoves = 0;
   }
   void push(Move m) {
     const bool irr = pos.is_irreversible(m);
     pos.push(m);
-    hist.push_back({pos.transposition_key(), irr});
+    const uint64_t key = pos.transposition_key();
+    uint16_t occ = 1, repeats = 0;
+    if (!irr) {
+      // positions since the last irreversible move, newest first (the entry that move led INTO is the oldest)
+      for (size_t i = hist.size(); i-- > 0;) {
+        occ += hist[i].key == key;
+        if (hist[i].irreversible_in) break;
+      }
+      repeats = static_cast<uint16_t>(hist.back().repeats + (occ >= 2 ? 1 : 0));
+    }
+    hist.push_back({key, irr, occ, repeats});
     ++num_halfmoves;
   }
   void pop_to(size_t hist_size, const Position& p, int halfmoves) {   // undo a simulation
@@ -588,26 +607,18 @@ struct Game {
     pos = p;
     num_halfmoves = halfmoves;
   }
+  uint64_t state_key() const { return Position::state_key_of(hist.back().key, pos.halfmove); }
 
-  // Board.can_claim_threefold_repetition(), with the legal moves of the current position supplied
-  bool can_claim_threefold(const Move* legal, int n_legal) const {
-    const uint64_t key = hist.back().key;
-    // positions since the last irreversible move
+  // Board.can_claim_threefold_repetition(); move_at(i) yields the i-th legal move of the current position
+  template <class MoveAt>
+  bool can_claim_threefold(MoveAt move_at, int n_legal) const {
+    if (hist.back().occ >= 3) return true;
+    if (hist.back().repeats == 0) return false;   // no position occurred twice: no move can reach a third occurrence
     size_t first = hist.size() - 1;
     while (first > 0 && !hist[first].irreversible_in) --first;
-    int same = 0;
-    bool any_twice = false;
-    for (size_t i = first; i < hist.size(); ++i) {
-      if (hist[i].key == key) ++same;
-      if (!any_twice)
-        for (size_t j = first; j < i; ++j)
-          if (hist[j].key == hist[i].key) { any_twice = true; break; }
-    }
-    if (same >= 3) return true;
-    if (!any_twice) return false;   // no position occurred twice: no move can reach a third occurrence
     for (int m = 0; m < n_legal; ++m) {
       Position c = pos;
-      c.push(legal[m]);
+      c.push(move_at(m));
       const uint64_t k = c.transposition_key();
       int cnt = 0;
       for (size_t i = first; i < hist.size(); ++i) cnt += hist[i].key == k;
@@ -617,13 +628,17 @@ struct Game {
   }
 
   // Board.result(claim_draw=True): 0 = "*", 1 = "1-0", 2 = "0-1", 3 = "1/2-1/2"
-  int result(const Move* legal, int n_legal) const {
+  template <class MoveAt>
+  int result_with(MoveAt move_at, int n_legal) const {
     if (n_legal == 0 && pos.in_check()) return pos.turn == WHITE ? 2 : 1;
     if (pos.halfmove >= 100 && n_legal > 0) return 3;
-    if (can_claim_threefold(legal, n_legal)) return 3;
+    if (can_claim_threefold(move_at, n_legal)) return 3;
     if (pos.insufficient_material()) return 3;
     if (n_legal == 0) return 3;
     return 0;
+  }
+  int result(const Move* legal, int n_legal) const {
+    return result_with([legal](int i) { return legal[i]; }, n_legal);
   }
   int result() const {
     Move m[256];

@@ -400,23 +400,16 @@ class Mcts {
       int path_len = 0;
       bool stop_batch = false;
       for (bool is_root = true;; is_root = false) {
-        const uint64_t key = gs.game.pos.state_key();
+        const uint64_t key = gs.game.state_key();
         const int32_t found = gs.index.find(key);
         int n_legal;
-        const Move* lm;
-        Move known[256];
-        if (found >= 0) {
-          const Node& nd = gs.nodes[found];
-          n_legal = nd.n_edges;
-          for (int i = 0; i < n_legal; ++i) known[i] = gs.edges[nd.first_edge + i].move;
-          lm = known;
-        } else {
-          n_legal = gs.game.pos.legal_moves(legal);
-          lm = legal;
-        }
+        const Move* lm = legal;
+        if (found >= 0) n_legal = gs.nodes[found].n_edges;   // a known node's moves are its edges', read only if a claim needs them
+        else n_legal = gs.game.pos.legal_moves(legal);
         if (!is_root) {
           // `if env.done` (player_chess.py:176-180): env.step ended the game with result(claim_draw=True)
-          const int res = gs.game.result(lm, n_legal);
+          const Edge* known = found >= 0 ? gs.edges.data() + gs.nodes[found].first_edge : nullptr;
+          const int res = gs.game.result_with([known, lm](int i) { return known ? known[i].move : lm[i]; }, n_legal);
           if (res) {
             ++st.terminal_hits;
             backup(gs, path_begin, path_len, res == 3 ? 0.0 : -1.0, st);
