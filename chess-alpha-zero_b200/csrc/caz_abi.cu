@@ -59,6 +59,7 @@ struct ConvLayer {
   float* bias = nullptr;  // [cout]
   CUtensorMap tmap_w;    // box 64 x cout       (one-CTA kernel)
   CUtensorMap tmap_w2;   // box 64 x cout / 2   (CTA-pair kernel: each CTA stages half of the output channels)
+  CUtensorMap tmap_w2h;  // box 64 x cout / 4   (the same with two N tiles of cout / 2 channels)
 };
 
 }  // namespace
@@ -74,6 +75,7 @@ struct caz_handle {
   std::vector<ConvLayer> convs;  // stem, then conv1/conv2 of each block
   bool snake = true;             // odd layers walk the batch backwards (CAZ_SNAKE=0 turns it off)
   bool l2_prefetch = false;       // CAZ_L2_PREFETCH=0 turns the one-tile-ahead L2 prefetches off
+  bool split_n = true;           // two 128-channel N tiles per board group when the grid would not fill the device; CAZ_NO_SPLIT_N=1
   bool pdl = true;               // programmatic dependent launch between the per-layer convolutions; CAZ_NO_PDL=1 turns it off
   bool use_2cta = true;          // per-layer convolutions as CTA pairs (cta_group::2); CAZ_CONV_2CTA=0 turns it off
   // weight slabs the layers point into: the tower's layers are contiguous so that one tensor map covers them
@@ -269,6 +271,8 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
         if (rc) return rc;
         cuuint32_t box2[2] = {(cuuint32_t)rbytes / 2, (cuuint32_t)F / 2};
         if ((rc = make_tmap(h, &L.tmap_w2, L.w, 2, dims, strides, box2, rbytes))) return rc;
+        cuuint32_t box2h[2] = {(cuuint32_t)rbytes / 2, (cuuint32_t)(F >= 4 ? F / 4 : 1)};
+        if ((rc = make_tmap(h, &L.tmap_w2h, L.w, 2, dims, strides, box2h, rbytes))) return rc;
       }
     }
     if (tcp) {
@@ -429,7 +433,16 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
       // CTA pairs: one cta_group::2 MMA covers two tiles (four boards)
       const int pairs = (args.num_tiles + 1) / 2;
       const int max_pairs = h->num_sms / 2;
-      const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+      // Few boards (up to ~148): one M = 256 tile per CTA pair leaves half of the device idle, and a lone tile cannot
+      // overlap its epilogue with anything.  Two N tiles of 128 channels per board group: twice the CTAs, half the tile.
+      // (Not the last layer: the fused head convolutions want all 256 channels of a row in one thread.)
+      const bool split_n = h->split_n && !fuse_heads && L.cout == 256 && 2 * pairs <= max_pairs;
+      if (split_n) {
+        args.n_tiles = 2;
+        args.n = L.cout / 2;
+      }
+      const int work = pairs * args.n_tiles;
+      const int grid = 2 * (work < max_pairs ? work : max_pairs);
       // consecutive layers overlap (prologue and first weights of layer l+1 under the tail of layer l): see conv_tc2.cuh
       args.pdl = h->pdl ? 1 : 0;
       cudaLaunchConfig_t cfg = {};
@@ -442,7 +455,7 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
       at[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at;
       cfg.numAttrs = h->pdl ? 1 : 0;
-      cudaError_t e = cudaLaunchKernelEx(&cfg, caz::tc2::conv_tc2_kernel, *tmap_in, L.tmap_w2, args);
+      cudaError_t e = cudaLaunchKernelEx(&cfg, caz::tc2::conv_tc2_kernel, *tmap_in, split_n ? L.tmap_w2h : L.tmap_w2, args);
       if (e != cudaSuccess) return fail(h, CAZ_ERR_CUDA, fmt("launch of conv_tc2_kernel failed: %s", cudaGetErrorString(e)));
       return check_launch(h, "conv_tc2_kernel");
     }
@@ -1131,6 +1144,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
     CREATE_TRY(cudaFuncSetAttribute(caz::tc2::conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc2::SMEM_BYTES));
     if (const char* e = getenv("CAZ_CONV_2CTA")) h->use_2cta = atoi(e) != 0;
     if (getenv("CAZ_NO_PDL")) h->pdl = false;
+    if (getenv("CAZ_NO_SPLIT_N")) h->split_n = false;
     if (const char* e = getenv("CAZ_L2_PREFETCH")) h->l2_prefetch = atoi(e) != 0;
     if (const char* e = getenv("CAZ_SNAKE")) h->snake = atoi(e) != 0;
   } else {

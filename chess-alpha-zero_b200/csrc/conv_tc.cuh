@@ -139,20 +139,23 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
     return (static_cast<long>(n0 + ((r >> 3) & 1)) << 6) + ((2 * quad + (r >> 4)) << 3) + (r & 7);
   };
   auto live = [&](int r) -> bool { return ((r >> 3) & 1) < boards_live; };
-  const int tile = n0 >> 1, chunks = args.n >> 5, m = quad * 32 + lane;
+  // (two N tiles per board group, nt = 0 / 1: this epilogue owns 32-column chunks [chunk0, chunk0 + n / 32) of the row's
+  // n_total / 32; the residual stream and the 16-bit operand keep their full-width layouts)
+  const int tile = n0 >> 1, chunks = (args.n_tiles > 1 ? args.n_total : args.n) >> 5, chunk0 = nt * (args.n >> 5);
+  const int m = quad * 32 + lane, opitch = args.n_tiles > 1 ? args.n_total : args.n;
   const float4* res4 = reinterpret_cast<const float4*>(args.residual);
   float4* out4 = reinterpret_cast<float4*>(args.out_f32);
   float4 res_pf[8];
   if (args.residual) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) res_pf[q] = res4[xf_index(tile, chunks, 0, q, m)];
+    for (int q = 0; q < 8; ++q) res_pf[q] = res4[xf_index(tile, chunks, chunk0, q, m)];
     // The residual stream comes from HBM (it is larger than L2 at big batches) and is consumed 4 KiB per warp and chunk
     // with only one chunk of lookahead in registers: pull the NEXT tile's slice into L2 now, a whole tile ahead.
     // A warp's slice of one chunk is 8 x 512 contiguous bytes = 32 lines: one prefetch per lane and chunk.
     if (next_n0 >= 0 && args.l2_prefetch) {
       const int ntile = next_n0 >> 1;
-      for (int ch = 0; ch < chunks; ++ch)
-        ptx::prefetch_l2(res4 + xf_index(ntile, chunks, ch, lane >> 2, quad * 32 + (lane & 3) * 8));
+      for (int ch = 0; ch < (args.n >> 5); ++ch)
+        ptx::prefetch_l2(res4 + xf_index(ntile, chunks, chunk0 + ch, lane >> 2, quad * 32 + (lane & 3) * 8));
     }
   }
   ptx::mbar_wait(full_bar, full_phase, args.err_flag, ERR_EPILOGUE);
@@ -161,7 +164,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
 #pragma unroll
   for (int hf = 0; hf < HEAD_MAX_F; ++hf) hacc[hf] = 0.0f;
   for (int c0 = 0; c0 < args.n; c0 += 32) {
-    const int chunk = c0 >> 5;
+    const int chunk = chunk0 + (c0 >> 5);
     uint32_t v[32];
     ptx::tmem_ld_32x32(taddr + c0, v);
     ptx::tmem_ld_wait();
@@ -257,7 +260,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
       for (int i = 0; i < 4; ++i) {
         const int r = i * 8 + br;
         const uint4 o = stage_b[r * 4 + (bc ^ ((r >> 1) & 3))];
-        if (live(r)) *reinterpret_cast<uint4*>(args.out_bf16 + grow(r) * args.n + c0 + bc * 8) = o;
+        if (live(r)) *reinterpret_cast<uint4*>(args.out_bf16 + grow(r) * opitch + nt * args.n + c0 + bc * 8) = o;
       }
       __syncwarp();
     }
