@@ -435,7 +435,9 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
       const int max_pairs = h->num_sms / 2;
       // Few boards (up to ~148): one M = 256 tile per CTA pair leaves half of the device idle, and a lone tile cannot
       // overlap its epilogue with anything.  Two N tiles of 128 channels per board group: twice the CTAs, half the tile.
-      // (Not the last layer: the fused head convolutions want all 256 channels of a row in one thread.)
+      // (Not the last layer: the fused head convolutions want all 256 channels of a row in one thread.  Not for bigger
+      // batches either: splitting to fill a partly empty last wave was measured at 600-1 200 boards and costs 10 % --
+      // a half tile reads the same activations for half the work.)
       const bool split_n = h->split_n && !fuse_heads && L.cout == 256 && 2 * pairs <= max_pairs;
       if (split_n) {
         args.n_tiles = 2;
