@@ -231,9 +231,10 @@ def test_masked_softmax(net, ev_bf16):
     assert np.abs(pm - want).max() <= 1e-5
 
 
-@pytest.mark.parametrize("batch", [1, 2, 3, 16, 17, 48, 255])
+@pytest.mark.parametrize("batch", [1, 2, 3, 16, 17, 48, 100, 148, 149, 255])
 def test_ragged_batches_are_consistent(net, ev_bf16, batch):
-    """Per-layer kernels (small-batch kernel off): a position's result does not depend on its batch."""
+    """Per-layer kernels (small-batch kernel off): a position's result does not depend on its batch -- nor on whether
+    its board group ran as one 256-channel tile or as two 128-channel N tiles (up to 148 boards)."""
     x = net[2]
     ev_bf16.set_small_batch_limit(0)
     try:
