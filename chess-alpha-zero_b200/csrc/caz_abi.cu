@@ -658,7 +658,8 @@ bool sb_geometry(const caz_handle* h, int batch, int* nb_out, int* slices_out, i
     for (int ns = 32; ns <= 128; ns *= 2) {   // 128-channel slices: 37-72 boards
       const int s = a.filters / ns;
       if (a.filters % ns != 0 || s < 1 || s > 16 || ((batch + 1) / 2) * s * 2 > h->num_sms) continue;
-      if (!caz::sb::heads_fit(a.policy_filters, a.value_filters, a.n_labels, a.value_fc, s)) continue;
+      // (with up to 4 slices the two CTAs of a pair split their slice's labels and hidden units: conv_sb.cuh, hshare)
+      if (!caz::sb::heads_fit(a.policy_filters, a.value_filters, a.n_labels, a.value_fc, s <= 4 ? 2 * s : s)) continue;
       *nb_out = 1;
       *slices_out = s;
       if (pair_out) *pair_out = 1;

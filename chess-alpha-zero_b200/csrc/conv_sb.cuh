@@ -315,14 +315,23 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   const int tap_bytes = ns_cta * 128;
   const uint32_t tmem_cols = static_cast<uint32_t>(NACC * ns_cta);  // 64 .. 512: powers of two
   const unsigned L = static_cast<unsigned>(args.n_layers);
-  const HeadGeom hg = head_geom(args.n_labels, args.value_fc, args.n_slices);
-  const int lab0 = slice * hg.upl * LABEL_UNIT;                         // this CTA's labels: [lab0, lab0 + lab_cnt)
+  // Heads geometry.  The two CTAs of a pair hold the same slice, i.e. they would stage the same Dense weights for one
+  // board each.  With few slices (37-72 boards: 2 slices = 1 024 labels and 128 hidden units per CTA, four rounds of
+  // weight staging) they split the slice's labels and hidden units instead, and each does its share for BOTH boards:
+  // half the staging, and the value Dense columns fit next to the policy chunk again.  The canonical pieces (128-label
+  // units, 16-unit groups) and their summation order do not change, so neither do the results.
+  const bool hshare = PAIR && args.n_slices <= 4;
+  const int h_slices = hshare ? 2 * args.n_slices : args.n_slices;
+  const int hslice = hshare ? 2 * slice + static_cast<int>(rank) : slice;
+  const int hn0 = hshare ? (tile & ~1) : n0, hnb = hshare ? 2 : args.nb;   // the boards this CTA's heads serve
+  const HeadGeom hg = head_geom(args.n_labels, args.value_fc, h_slices);
+  const int lab0 = hslice * hg.upl * LABEL_UNIT;                        // this CTA's labels: [lab0, lab0 + lab_cnt)
   const int lab_cnt = max(0, min(hg.upl * LABEL_UNIT, args.n_labels - lab0));
-  const int hid0 = slice * hg.hsp;                                      // this CTA's hidden units: [hid0, hid0 + hid_cnt)
+  const int hid0 = hslice * hg.hsp;                                     // this CTA's hidden units: [hid0, hid0 + hid_cnt)
   const int hid_cnt = max(0, min(hg.hsp, args.value_fc - hid0));
   float* s_wp = reinterpret_cast<float*>(smem);                         // heads: [2 units][pf*64][128], over the tower's tiles
   float* s_wv = s_wp + args.pf * 64 * LABEL_CHUNK;                      //        [gps groups][vf*64][16] (+16 between groups)
-  const int unit_first = slice * hg.upl;                                // this CTA's 128-label units: [unit_first, +upl)
+  const int unit_first = hslice * hg.upl;                               // this CTA's 128-label units: [unit_first, +upl)
   auto units_in_chunk = [&](int c) {                                    // units of label chunk c that exist (0..2)
     return max(0, min(min(2, hg.upl - 2 * c), hg.units_total - (unit_first + 2 * c)));
   };
@@ -457,7 +466,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     // epilogue warps are still busy (the Dense weights do not depend on the activations).
     ptx::mbar_wait(tower_done, 0, args.err_flag, ERR_HEADW);
     stage_head_weights(args, s_wp, s_wv, hw_full, lane, unit_first, units_in_chunk(0), value_staged(args.pf, args.vf, hg.hsp),
-                       slice * hg.gps, max(0, min(hg.gps, hg.groups_total - slice * hg.gps)));
+                       hslice * hg.gps, max(0, min(hg.gps, hg.groups_total - hslice * hg.gps)));
   } else if (warp == 3) {
     // ============ activation producer: one halo tile per 64-channel chunk, as soon as the CTAs that own those
     // channels of this board tile have published the previous layer (no grid-wide barrier: a tile's CTAs only ever
@@ -768,24 +777,28 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     pbias[c] = valid ? args.pfc_b[n] : 0.0f;
 #pragma unroll
     for (int bl = 0; bl < 2; ++bl)
-      pmask[c][bl] = !(valid && args.mask && bl < args.nb && n0 + bl < args.batch) ||
-                     args.mask[static_cast<size_t>(n0 + bl) * args.n_labels + n] != 0;
+      pmask[c][bl] = !(valid && args.mask && bl < hnb && hn0 + bl < args.batch) ||
+                     args.mask[static_cast<size_t>(hn0 + bl) * args.n_labels + n] != 0;
   }
   // (kept in registers until H1's loads are on their way: a shared-memory store would wait for its load right here)
   const float vb_r = threadIdx.x < hid_cnt ? args.vfc1_b[hid0 + threadIdx.x] : 0.0f;
   const float vw_r = threadIdx.x < hid_cnt ? args.vfc2_w[hid0 + threadIdx.x] : 0.0f;
   const unsigned* tile_flags = tile_flag_line(args, s_near_copy, tile);   // written by warp 3 long before the __syncthreads above
-  if (threadIdx.x == 0) wait_tile(args, tile_flags, args.base + L);   // the tile's CTAs have stored their partials
+  const unsigned* peer_flags = tile_flag_line(args, s_near_copy, tile ^ 1);   // (shared heads: the pair's other board)
+  if (threadIdx.x == 0) {
+    wait_tile(args, tile_flags, args.base + L);   // the tile's CTAs have stored their partials
+    if (hshare) wait_tile(args, peer_flags, args.base + L);
+  }
   __syncthreads();
   if (kt) kt[3] = clock64();
   {
     // one thread per (board, head filter, four squares): sixteen 16-byte loads, all requested before any is summed
-    const int n_quads = args.nb * hf_total * 16;   // <= 2 * 8 * 16 = THREADS
+    const int n_quads = hnb * hf_total * 16;   // <= 2 * 8 * 16 = THREADS
     const int t = threadIdx.x;
     const int q = t & 15, f6 = (t >> 4) % hf_total, bl = t / (16 * hf_total);
-    const bool on = t < n_quads && n0 + bl < args.batch;
+    const bool on = t < n_quads && hn0 + bl < args.batch;
     const float4* hp = reinterpret_cast<const float4*>(
-        args.hpart + ((static_cast<size_t>(on ? n0 + bl : 0) * 16) * HEAD_FILTERS_MAX + f6) * 64 + q * 4);
+        args.hpart + ((static_cast<size_t>(on ? hn0 + bl : 0) * 16) * HEAD_FILTERS_MAX + f6) * 64 + q * 4);
     float4 part[16];
 #pragma unroll
     for (int g = 0; g < 16; ++g)
@@ -835,7 +848,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
         a0 = fmaf(fa.z, wcol[(k + 2) * LABEL_UNIT], a0);
         a0 = fmaf(fa.w, wcol[(k + 3) * LABEL_UNIT], a0);
       }
-      if (args.nb == 2) {
+      if (hnb == 2) {
 #pragma unroll 4
         for (int k = 0; k < kp; k += 4) {
           const float4 fa = f4[128 + (k >> 2)];
@@ -849,9 +862,9 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     }
 #pragma unroll
     for (int bl = 0; bl < 2; ++bl) {
-      if (bl >= args.nb) break;
-      const int b = n0 + bl;
-      const bool on = valid && bl < args.nb && b < args.batch && pmask[c][bl];
+      if (bl >= hnb) break;
+      const int b = hn0 + bl;
+      const bool on = valid && bl < hnb && b < args.batch && pmask[c][bl];
       const float x = on ? (bl ? a1 : a0) : -INFINITY;
       lg[c][bl] = x;
       // statistics of this 128-label unit: max, then the sum of exp(x - max), reduced in a fixed order
@@ -868,8 +881,8 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       __syncthreads();
       if (lane == 0) s_red[8 + warp] = e;
       __syncthreads();
-      const int unit = slice * hg.upl + c * (LABEL_CHUNK / LABEL_UNIT) + unit_in_chunk;
-      if ((threadIdx.x & 127) == 0 && bl < args.nb && b < args.batch && unit < LABEL_UNITS_MAX &&
+      const int unit = hslice * hg.upl + c * (LABEL_CHUNK / LABEL_UNIT) + unit_in_chunk;
+      if ((threadIdx.x & 127) == 0 && bl < hnb && b < args.batch && unit < LABEL_UNITS_MAX &&
           c * (LABEL_CHUNK / LABEL_UNIT) + unit_in_chunk < hg.upl) {
         const float se = (s_red[8 + unit_in_chunk * 4] + s_red[8 + unit_in_chunk * 4 + 1]) +
                          (s_red[8 + unit_in_chunk * 4 + 2] + s_red[8 + unit_in_chunk * 4 + 3]);
@@ -895,7 +908,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
           const float wv = staged ? s_wv[(u >> 4) * value_group_pitch(args.vf) + k * HID_GROUP + (u & 15)]
                                   : __ldg(args.vfc1_w + static_cast<size_t>(k) * args.value_fc + hid0 + u);
           a0 = fmaf(s_feat[kp + k], wv, a0);
-          if (args.nb == 2) a1 = fmaf(s_feat[512 + kp + k], wv, a1);
+          if (hnb == 2) a1 = fmaf(s_feat[512 + kp + k], wv, a1);
         }
       s_part[i] = a0;
       s_part[per + i] = a1;
@@ -903,9 +916,9 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     __syncthreads();
     // one thread per (board, hidden unit): hidden = relu(sum of the 8 partials + bias) times its output weight; the 16
     // products of a group are added by a fixed shuffle tree (whole warps take part: a group is half a warp)
-    const int n_hid = args.nb * hg.hsp;
+    const int n_hid = hnb * hg.hsp;
     for (int i = threadIdx.x; i < ((n_hid + 31) & ~31); i += THREADS) {
-      const int bl = i / hg.hsp, u = i - bl * hg.hsp, b = n0 + bl;
+      const int bl = i / hg.hsp, u = i - bl * hg.hsp, b = hn0 + bl;
       float pv = 0.0f;
       if (i < n_hid && u < hid_cnt) {
         float hsum = 0.0f;
@@ -915,7 +928,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       }
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
-      const int grp = slice * hg.gps + (u >> 4);
+      const int grp = hslice * hg.gps + (u >> 4);
       if (i < n_hid && (u & 15) == 0 && b < args.batch && grp < hg.groups_total)
         args.hstats[static_cast<size_t>(b) * HSTAT_FLOATS + 2 * LABEL_UNITS_MAX + grp] = pv;
     }
@@ -925,6 +938,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   if (threadIdx.x == 0) {
     publish(args, tile, slice, args.base + 1u + L);
     wait_tile(args, tile_flags, args.base + 1u + L);
+    if (hshare) wait_tile(args, peer_flags, args.base + 1u + L);
   }
   __syncthreads();
   if (kt) kt[7] = clock64();
@@ -933,11 +947,11 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   // the tile's statistics come in with one L2 read per thread (ld.cg: other CTAs wrote them)
   if (threadIdx.x < 2 * HSTAT_FLOATS) {
     const int bl = threadIdx.x / HSTAT_FLOATS, j = threadIdx.x - bl * HSTAT_FLOATS;
-    s_stat[threadIdx.x] = (bl < args.nb && n0 + bl < args.batch) ? ptx::ld_cg_f32(args.hstats + static_cast<size_t>(n0 + bl) * HSTAT_FLOATS + j) : 0.0f;
+    s_stat[threadIdx.x] = (bl < hnb && hn0 + bl < args.batch) ? ptx::ld_cg_f32(args.hstats + static_cast<size_t>(hn0 + bl) * HSTAT_FLOATS + j) : 0.0f;
   }
   __syncthreads();
   // one warp per board: the maximum over the units and the normaliser (one expf per lane, fixed shuffle trees)
-  if (warp < args.nb) {
+  if (warp < hnb) {
     const float* st = s_stat + warp * HSTAT_FLOATS;
     const float mu = lane < hg.units_total ? st[2 * lane] : -INFINITY, su = lane < hg.units_total ? st[2 * lane + 1] : 0.0f;
     float mx = mu;
@@ -951,8 +965,8 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
   __syncthreads();
 #pragma unroll
   for (int bl = 0; bl < 2; ++bl) {
-    const int b = n0 + bl;
-    if (bl >= args.nb || b >= args.batch) continue;
+    const int b = hn0 + bl;
+    if (bl >= hnb || b >= args.batch) continue;
     const float* st = s_stat + bl * HSTAT_FLOATS;
     const float mx = s_red[2 * bl], inv = s_red[2 * bl + 1];
 #pragma unroll
@@ -964,7 +978,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
         args.policy[static_cast<size_t>(b) * args.n_labels + n] = x == -INFINITY ? 0.0f : expf(x - mx) * inv;
       }
     }
-    if (slice == 0 && threadIdx.x == 0) {
+    if (hslice == 0 && threadIdx.x == 0) {
       float v = vbias2;
       for (int g = 0; g < hg.groups_total; ++g) v += st[2 * LABEL_UNITS_MAX + g];
       args.value[b] = tanhf(v);
