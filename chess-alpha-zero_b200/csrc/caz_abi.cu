@@ -1306,6 +1306,23 @@ int caz_submit(caz_handle* h, const float* planes, int32_t batch, float* policy,
   return CAZ_OK;
 }
 
+int caz_submit_records(caz_handle* h, const uint8_t* records, int32_t batch, float* policy, float* value,
+                       const uint8_t* legal_mask, uint32_t flags, int32_t* ticket) {
+  if (!h) return CAZ_ERR_INVALID;
+  if (!records || !policy || !value || !ticket || batch < 1 || batch > h->max_batch)
+    return fail(h, CAZ_ERR_INVALID, fmt("caz_submit_records: bad argument (batch %d, max_batch %d)", batch, h->max_batch));
+  const bool masked = (flags & CAZ_EVAL_MASKED_SOFTMAX) != 0;
+  if (masked && !legal_mask) return fail(h, CAZ_ERR_INVALID, "masked softmax needs a legal mask");
+  if (h->arch.input_planes != CAZ_PLANES) return fail(h, CAZ_ERR_INVALID, "board records need an 18-plane network");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  const int slot = h->next_slot;
+  if ((rc = enqueue_pipelined(h, slot, nullptr, records, batch, policy, value, legal_mask, masked))) return rc;
+  h->next_slot ^= 1;
+  *ticket = slot;
+  return CAZ_OK;
+}
+
 int caz_collect(caz_handle* h, int32_t ticket) {
   if (!h || ticket < 0 || ticket > 1) return fail(h, CAZ_ERR_INVALID, "caz_collect: bad ticket");
   int rc;

@@ -93,6 +93,21 @@ class Evaluator:
             _lib.check(self._handle, rc)
         return ticket.value
 
+    def submit_records(self, records, policy, value):
+        """submit() from board records (uint8 (B, 68)); policy (>= B, n_labels) and value (>= B,) are caller-owned,
+        ideally pinned.  A search driver with several groups of games submits under its own lock and collects outside
+        it: one group's read-back then overlaps another group's forward pass."""
+        r = _lib.as_array(records, np.uint8)
+        b = r.shape[0]
+        if r.ndim != 2 or r.shape[1] != _lib.RECORD_BYTES or policy.shape[0] < b or value.shape[0] < b:
+            raise ValueError("records must be uint8 (B, 68) and the outputs must hold B rows")
+        ticket = ctypes.c_int32(-1)
+        with self._lock:
+            rc = self._lib.caz_submit_records(self._handle, _lib.ptr(r), b, _lib.ptr(policy), _lib.ptr(value), None, 0,
+                                              ctypes.byref(ticket))
+            _lib.check(self._handle, rc)
+        return ticket.value
+
     def collect(self, ticket):
         _lib.check(self._handle, self._lib.caz_collect(self._handle, int(ticket)))
 

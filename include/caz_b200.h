@@ -127,6 +127,10 @@ int caz_eval_records(caz_handle* h, const uint8_t* records, int32_t batch, float
  * stay valid (and should be pinned, caz_host_alloc) until collected. */
 int caz_submit(caz_handle* h, const float* planes, int32_t batch, float* policy, float* value,
                const uint8_t* legal_mask, uint32_t flags, int32_t* ticket);
+/* caz_submit from board records (68 bytes per position, see caz_eval_records): what a batched search driver with two or
+ * more groups of games calls, so that one group's policy read-back runs under another group's forward pass. */
+int caz_submit_records(caz_handle* h, const uint8_t* records, int32_t batch, float* policy, float* value,
+                       const uint8_t* legal_mask, uint32_t flags, int32_t* ticket);
 int caz_collect(caz_handle* h, int32_t ticket);
 
 int caz_sync(caz_handle* h);

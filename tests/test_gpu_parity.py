@@ -374,6 +374,29 @@ def test_submit_collect_pipelined_api(net, ev_bf16):
         ev_bf16.submit(np.zeros((513, 18, 8, 8), np.float32), np.zeros((513, 1968), np.float32), np.zeros((513, 1), np.float32))
 
 
+def test_submit_records_pipelined_api(net, ev_bf16):
+    """caz_submit_records: two batches of board records in flight (what the self-play driver's two game groups do) give
+    exactly what the synchronous record call gives, which in turn is the plane call's result."""
+    from chess_alpha_zero_b200 import _lib, encoder
+    fens = net[3]
+    recs = encoder.fens_to_records(fens)
+    want = [ev_bf16.predict_records(recs[:200]), ev_bf16.predict_records(recs[56:256])]
+    base_p, base_v = ev_bf16.predict_on_batch(net[2])
+    assert np.array_equal(want[0][0], base_p[:200]) and np.array_equal(want[1][1], base_v[56:256])
+    pins = [(_lib.PinnedArray((200, 68), np.uint8), _lib.PinnedArray((200, 1968), np.float32),
+             _lib.PinnedArray((200,), np.float32)) for _ in range(2)]
+    pins[0][0].array[:] = recs[:200]
+    pins[1][0].array[:] = recs[56:256]
+    for rounds in range(3):
+        t = [ev_bf16.submit_records(pins[i][0].array, pins[i][1].array, pins[i][2].array) for i in range(2)]
+        assert sorted(t) == [0, 1]
+        for i in range(2):
+            ev_bf16.collect(t[i])
+            assert np.array_equal(pins[i][1].array, want[i][0]) and np.array_equal(pins[i][2].array, want[i][1].reshape(-1))
+        for i in range(2):
+            pins[i][1].array[:] = 0
+
+
 def test_shipped_json_variant_and_reload(net):
     cfg = oweights.keras_config(stem_k=3, value_filters=1)         # what data/model/model_best_config.json holds
     w = oweights.synth_weights(cfg, seed=4, recipe="randomized")

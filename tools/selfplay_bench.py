@@ -57,6 +57,10 @@ def run(ev, games=256, sims=800, search_threads=16, seconds=20.0, groups=0, host
     stop_at = time.perf_counter() + seconds
     ev_lock = threading.Lock()
     busy = [0.0]
+    # Two groups: caz_submit_records / caz_collect (two staging slots), so one group's policy read-back (16 MB per 2 048
+    # leaves) runs under the other group's forward pass.  More groups than slots: one synchronous call at a time.
+    pipelined = groups == 2 and not os.environ.get("CAZ_SELFPLAY_SYNC")
+    inflight, busy_from = [0], [0.0]
 
     def loop(i):
         g, (pp, pv), a = searches[i], pins[i], acc[i]
@@ -64,11 +68,24 @@ def run(ev, games=256, sims=800, search_threads=16, seconds=20.0, groups=0, host
             t0 = time.perf_counter()
             rec = g.collect()
             t1 = time.perf_counter()
-            with ev_lock:
-                t1b = time.perf_counter()
-                ev.predict_records_into(rec, pp.array, pv.array)
+            if pipelined:
+                with ev_lock:
+                    if inflight[0] == 0:
+                        busy_from[0] = time.perf_counter()
+                    inflight[0] += 1
+                    ticket = ev.submit_records(rec, pp.array, pv.array)
+                ev.collect(ticket)
                 t2 = time.perf_counter()
-                busy[0] += t2 - t1b
+                with ev_lock:
+                    inflight[0] -= 1
+                    if inflight[0] == 0:
+                        busy[0] += t2 - busy_from[0]
+            else:
+                with ev_lock:
+                    t1b = time.perf_counter()
+                    ev.predict_records_into(rec, pp.array, pv.array)
+                    t2 = time.perf_counter()
+                    busy[0] += t2 - t1b
             g.apply(pp.array[:len(rec)], pv.array[:len(rec)])
             t3 = time.perf_counter()
             a["collect"] += t1 - t0
@@ -100,7 +117,7 @@ def run(ev, games=256, sims=800, search_threads=16, seconds=20.0, groups=0, host
         "positions_per_s_through_evaluator": leaves / wall,
         "mean_batch": leaves / max(1, rounds),
         "evaluator_occupancy": busy[0] / wall,
-        "host_threads_per_group": host_threads, "groups": groups, "host_cores": cores,
+        "host_threads_per_group": host_threads, "groups": groups, "host_cores": cores, "pipelined_evaluator": pipelined,
         "per_round_ms": {k: 1e3 * sum(a[k] for a in acc) / max(1, rounds) for k in ("collect", "eval", "apply")},
         "moves_played": tot["moves_played"], "games_finished": tot["games_finished"],
         "terminal_hits": tot["terminal_hits"], "withdrawn": tot["withdrawn"],
