@@ -6,8 +6,7 @@ The search is the host-side batched driver (include/caz_mcts.h, chess-alpha-zero
 evaluated on the GPU through caz_eval_records (68-byte board records in, encoder + network on the device).
 `--groups G` splits the games into G parts whose rounds alternate, so one part's tree work overlaps the others'
 evaluation (G driver threads, one evaluator handle).  Default: 2 groups when the rank has 8 or more host cores, 4 groups
-of one worker thread each below that (8 GPUs on a 32-core box: 6.5 M sims/s at 96 % evaluator occupancy with 4 x 1,
-5.6 M at 70 % with 2 x 2).
+of one worker thread each below that (8 GPUs on a 32-core box: 6.75 M sims/s with 4 x 1, 5.6 M with 2 x 2).
 
 Prints one JSON line: sims/s (completed descents), positions/s through the evaluator, mean batch, evaluator occupancy
 (fraction of wall time inside caz_eval_records), moves and games completed, games/hour extrapolated from the moves.
@@ -57,9 +56,10 @@ def run(ev, games=256, sims=800, search_threads=16, seconds=20.0, groups=0, host
     stop_at = time.perf_counter() + seconds
     ev_lock = threading.Lock()
     busy = [0.0]
-    # Two groups: caz_submit_records / caz_collect (two staging slots), so one group's policy read-back (16 MB per 2 048
-    # leaves) runs under the other group's forward pass.  More groups than slots: one synchronous call at a time.
-    pipelined = groups == 2 and not os.environ.get("CAZ_SELFPLAY_SYNC")
+    # caz_submit_records / caz_collect: one group's policy read-back (16 MB per 2 048 leaves) runs under another group's
+    # forward pass (two staging slots; with four groups the third submission simply queues behind the first's slot).
+    # CAZ_SELFPLAY_SYNC=1: one synchronous caz_eval_records at a time.
+    pipelined = not os.environ.get("CAZ_SELFPLAY_SYNC")
     inflight, busy_from = [0], [0.0]
 
     def loop(i):
