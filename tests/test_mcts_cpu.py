@@ -84,6 +84,12 @@ def test_result_with_claimed_draws():
     # can_claim_threefold_repetition looks one move ahead)
     assert mcts.play(START, shuffle + shuffle[:3])[0] == "1/2-1/2"
     assert mcts.play(START, shuffle + shuffle)[0] == "1/2-1/2"
+    # an irreversible move starts the count again (the move stack keeps occurrences per reversible stretch)
+    after_pawns = shuffle + ["e2e4", "e7e5"]
+    assert mcts.play(START, after_pawns + shuffle)[0] == "*"
+    assert mcts.play(START, after_pawns + shuffle + shuffle[:2])[0] == "*"
+    assert mcts.play(START, after_pawns + shuffle + shuffle[:3])[0] == "1/2-1/2"
+    assert mcts.play(START, after_pawns + shuffle + "d2d4 g8f6 g1f3 f6g8 f3g1".split())[0] == "*"
     with pytest.raises(ValueError):
         mcts.play(START, ["e2e5"])
 
