@@ -14,6 +14,7 @@ CAZ_OK = 0
 PRECISION_BF16 = 0
 PRECISION_FP32 = 1
 PRECISION_FP16 = 2
+PRECISION_BF16_PURE = 3
 EVAL_MASKED_SOFTMAX = 1
 RECORD_BYTES = 68
 STAGES = 4

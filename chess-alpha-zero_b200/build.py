@@ -1,4 +1,6 @@
 """Builds the native library in-tree: csrc/caz_abi.cu -> _native/libcaz_b200.so (sm_100a only)."""
+import contextlib
+import fcntl
 import os
 import shutil
 import subprocess
@@ -12,6 +14,30 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE]
+
+
+@contextlib.contextmanager
+def _build_lock():
+    """One builder at a time (torchrun starts every rank at once); the output appears atomically (os.replace), so a
+    rank that dlopens while another one builds sees either the old library or the new one, never a partial file."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, ".build.lock"), "w") as f:
+        fcntl.flock(f, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(f, fcntl.LOCK_UN)
+
+
+def _compile(cmd, out_path, what):
+    tmp = f"{out_path}.tmp.{os.getpid()}"
+    res = subprocess.run(cmd + ["-o", tmp], capture_output=True, text=True)
+    if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        raise RuntimeError(f"{what} failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, out_path)
+    return res
 
 
 def _sources():
@@ -33,12 +59,11 @@ def build_native(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libcaz_b200.so (there is no CPU fallback)")
-    os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH, os.path.join(CSRC, "caz_abi.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    with _build_lock():
+        if not force and not is_stale():     # another rank built it while we waited for the lock
+            return LIB_PATH
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "caz_abi.cu")]
+        res = _compile(cmd, LIB_PATH, "nvcc")
     if verbose:
         print(res.stderr)
     return LIB_PATH
@@ -64,12 +89,12 @@ def build_mcts(force=False):
     gxx = shutil.which("g++")
     if not gxx:
         raise RuntimeError("g++ not found: cannot build libcaz_mcts.so")
-    os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", INCLUDE, "-I", CSRC, "-o", MCTS_LIB_PATH,
-           os.path.join(CSRC, "caz_mcts.cpp")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    with _build_lock():
+        if not force and not mcts_is_stale():
+            return MCTS_LIB_PATH
+        cmd = [gxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", INCLUDE, "-I", CSRC,
+               os.path.join(CSRC, "caz_mcts.cpp")]
+        _compile(cmd, MCTS_LIB_PATH, "g++")
     return MCTS_LIB_PATH
 
 

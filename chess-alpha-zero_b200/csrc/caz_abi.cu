@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -78,6 +79,11 @@ struct caz_handle {
   bool split_n = true;           // two 128-channel N tiles per board group when the grid would not fill the device; CAZ_NO_SPLIT_N=1
   bool pdl = true;               // programmatic dependent launch between the per-layer convolutions; CAZ_NO_PDL=1 turns it off
   bool use_2cta = true;          // per-layer convolutions as CTA pairs (cta_group::2); CAZ_CONV_2CTA=0 turns it off
+  // every environment switch is read ONCE, in caz_create (no getenv on the call path)
+  bool sb_no_pairs = false;      // CAZ_SB_NO_PAIRS
+  bool no_direct_output = false; // CAZ_NO_DIRECT_OUTPUT
+  int sb_dbg = 0;                // CAZ_SB_DBG
+  int dbg_epi = 0;               // CAZ_DBG_EPI (only with -DCAZ_TIMING_EXPERIMENTS)
   // weight slabs the layers point into: the tower's layers are contiguous so that one tensor map covers them
   void* w_stem = nullptr;
   void* sb_w_stem = nullptr;   // stem weights padded to 64 input channels (small-batch kernel)
@@ -125,7 +131,14 @@ struct caz_handle {
   uint8_t *d_mask2 = nullptr, *d_records2 = nullptr;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_in[2] = {}, ev_fwd[2] = {}, ev_out[2] = {};
-  int next_slot = 0;
+  // caz_submit / caz_collect: tickets count up; ticket t completes on ev_done[t % TICKET_RING], its staging slot is t & 1
+  // (a third submission simply queues behind the first one's slot on the streams).  caz_collect may run on another
+  // thread than caz_submit: it touches only its ring entry.
+  static constexpr int TICKET_RING = 16;
+  cudaEvent_t ev_done[TICKET_RING] = {};
+  std::atomic<int> ticket_state[TICKET_RING];   // 0 free, 1 in flight
+  int32_t next_ticket = 0;
+  std::mutex err_mutex;          // last_error is written under it (collect and submit may fail concurrently)
   int* err_flag_host = nullptr;  // mapped pinned: readable even after a device trap
   int* err_flag_dev = nullptr;
   // PUCT scratch
@@ -148,8 +161,10 @@ struct caz_handle {
 namespace {
 
 int fail(caz_handle* h, int code, const std::string& msg) {
-  if (h) h->err = msg;
-  else {
+  if (h) {
+    std::lock_guard<std::mutex> g(h->err_mutex);
+    h->err = msg;
+  } else {
     std::lock_guard<std::mutex> g(g_err_mutex);
     g_create_error = msg;
   }
@@ -172,8 +187,12 @@ int fail(caz_handle* h, int code, const std::string& msg) {
 
 int expected_tensor_count(const caz_arch& a) { return 5 + 10 * a.res_blocks + 7 + 9; }
 
-bool tensor_path(const caz_handle* h) { return h->precision == CAZ_PRECISION_BF16 || h->precision == CAZ_PRECISION_FP16; }
-bool is_fp16(const caz_handle* h) { return h->precision == CAZ_PRECISION_FP16; }
+bool tensor_path(const caz_handle* h) { return h->precision != CAZ_PRECISION_FP32; }
+// 16-bit formats of the two tensor-core operands (include/caz_b200.h): the bf16 build keeps every WEIGHT in bf16 and writes
+// the 16-bit operand copies of the ACTIVATIONS as fp16 -- tcgen05.mma kind::f16 takes the A and B formats independently
+bool act_fp16(const caz_handle* h) { return h->precision == CAZ_PRECISION_FP16 || h->precision == CAZ_PRECISION_BF16; }
+bool w_fp16(const caz_handle* h) { return h->precision == CAZ_PRECISION_FP16; }
+int operand_fmt(const caz_handle* h) { return (act_fp16(h) ? caz::ptx::FMT_A_FP16 : 0) | (w_fp16(h) ? caz::ptx::FMT_B_FP16 : 0); }
 
 // BatchNorm inference folded into the preceding bias-free convolution (Keras semantics,
 // model_chess.py:65-69): y = conv(x)*inv + (beta - mean*inv), inv = gamma / sqrt(var + eps).
@@ -198,7 +217,7 @@ int make_tmap(caz_handle* h, CUtensorMap* m, void* base, int rank, const cuuint6
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(h, CAZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, is_fp16(h) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, ones,
+  CUresult r = enc(m, act_fp16(h) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, ones,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -279,7 +298,7 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
       // W[oc][tap*cin_pad + ic] bf16, K-major rows: the B operand of the implicit GEMM
       // 16-bit words: bf16, or fp16 in the FP16 build (both have a +0.0 bit pattern of 0)
       std::vector<uint16_t> wp(ktot * F, 0);
-      const bool f16 = is_fp16(h);
+      const bool f16 = w_fp16(h);
       for (int tap = 0; tap < taps; ++tap)
         for (int ic = 0; ic < cin; ++ic) {
           const float* src = kt.data + ((size_t)tap * cin + ic) * F;
@@ -414,7 +433,7 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
     args.featv = h->featv;
     args.pf = h->arch.policy_filters;
     args.vf = h->arch.value_filters;
-    args.fp16 = is_fp16(h) ? 1 : 0;
+    args.fp16 = operand_fmt(h);
     args.n_tiles = 1;
     args.n_total = L.cout;
     args.m_rows = batch * 64;
@@ -422,12 +441,11 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
     args.l2_prefetch = h->l2_prefetch ? 1 : 0;
     args.pdl = 0;
     args.reverse = (h->snake && (li & 1)) ? 1 : 0;
-    if (const char* e = getenv("CAZ_DBG_EPI")) {   // timing experiments only (results are wrong): drop epilogue traffic
-      const int m = atoi(e);
-      if (m & 1) args.residual = nullptr;
-      if (m & 2) args.out_f32 = nullptr;
-      if (m & 4) args.out_bf16 = nullptr;
-    }
+#ifdef CAZ_TIMING_EXPERIMENTS   // never in the shipped library: results are wrong with these (drops epilogue traffic)
+    if (h->dbg_epi & 1) args.residual = nullptr;
+    if (h->dbg_epi & 2) args.out_f32 = nullptr;
+    if (h->dbg_epi & 4) args.out_bf16 = nullptr;
+#endif
     args.err_flag = h->err_flag_dev;
     if (h->use_2cta && args.num_tiles >= 2 && L.cout % 64 == 0) {
       // CTA pairs: one cta_group::2 MMA covers two tiles (four boards)
@@ -653,7 +671,7 @@ bool sb_geometry(const caz_handle* h, int batch, int* nb_out, int* slices_out, i
   // slice's weights: 484 KB of shared-memory traffic per layer instead of 630 KB at 16 boards, 630 KB
   // instead of 969 KB at 32; and all 128 epilogue threads have rows (an M = 64 single-CTA accumulator leaves half idle),
   // which is why the pair form also wins below 9 boards (measured: 111 us vs 115 us).
-  if (batch >= 1 && !h->sb_force_nb && !getenv("CAZ_SB_NO_PAIRS")) {
+  if (batch >= 1 && !h->sb_force_nb && !h->sb_no_pairs) {
     const caz_arch& a = h->arch;
     for (int ns = 32; ns <= 128; ns *= 2) {   // 128-channel slices: 37-72 boards
       const int s = a.filters / ns;
@@ -713,8 +731,8 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   args.blk_k = a.block_kernel;
   args.in_planes = a.input_planes;
   args.in_cpad = 64;
-  args.fp16 = is_fp16(h) ? 1 : 0;
-  { const char* e = getenv("CAZ_SB_DBG"); args.dbg = e ? atoi(e) : 0; }
+  args.fp16 = operand_fmt(h);
+  args.dbg = h->sb_dbg;
   const int sb_stem = caz::sb::taps_per_slot(a.stem_kernel, ns_cta) * ns_cta * 128;
   const int sb_blk = a.res_blocks > 0 ? caz::sb::taps_per_slot(a.block_kernel, ns_cta) * ns_cta * 128 : 0;
   args.slot_bytes = sb_stem > sb_blk ? sb_stem : sb_blk;
@@ -832,7 +850,7 @@ float widen16(uint16_t bits, bool f16) {
 
 // W [k][n] fp32 (Keras Dense kernel) -> [npad][3k] 16-bit rows = [wh | wl | wh]
 int upload_w3(caz_handle* h, uint16_t* dst, const float* w, int k, int n, int npad) {
-  const bool f16 = is_fp16(h);
+  const bool f16 = w_fp16(h);
   std::vector<uint16_t> w3((size_t)npad * 3 * k, 0);
   for (int col = 0; col < n; ++col)
     for (int kk = 0; kk < k; ++kk) {
@@ -883,7 +901,7 @@ int launch_dense_tc(caz_handle* h, const float* in, uint16_t* a3, const CUtensor
                     int n_tile, int n_tiles, int n_total, const float* bias, int relu, float* out, int m) {
   int rc;
   const size_t total = (size_t)(((m + 127) / 128) * 128) * k;
-  caz::split3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(in, a3, m, ((m + 127) / 128) * 128, k, is_fp16(h) ? 1 : 0);
+  caz::split3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(in, a3, m, ((m + 127) / 128) * 128, k, act_fp16(h) ? 1 : 0);
   if ((rc = check_launch(h, "split3_kernel"))) return rc;
   caz::tc::ConvArgs args{};
   args.batch = (m + 63) / 64;          // "boards" = groups of 64 rows
@@ -894,7 +912,7 @@ int launch_dense_tc(caz_handle* h, const float* in, uint16_t* a3, const CUtensor
   args.n = n_tile;
   args.relu = relu;
   args.bias = bias;
-  args.fp16 = is_fp16(h) ? 1 : 0;
+  args.fp16 = operand_fmt(h);
   args.n_tiles = n_tiles;
   args.n_total = n_total;
   args.m_rows = m;
@@ -926,14 +944,14 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
   // ---- stage 0: input pack (NCHW fp32 planes -> NHWC activations, channels zero-padded) ----
   if (d_planes) {
     const size_t smem = (size_t)a.input_planes * 65 * sizeof(float);
-    if (tcp && is_fp16(h)) caz::pack_planes_kernel<__half><<<batch, 256, smem, h->stream>>>(d_planes, static_cast<__half*>(h->in_act), batch, a.input_planes, h->in_cpad);
+    if (tcp && act_fp16(h)) caz::pack_planes_kernel<__half><<<batch, 256, smem, h->stream>>>(d_planes, static_cast<__half*>(h->in_act), batch, a.input_planes, h->in_cpad);
     else if (tcp) caz::pack_planes_kernel<__nv_bfloat16><<<batch, 256, smem, h->stream>>>(d_planes, static_cast<__nv_bfloat16*>(h->in_act), batch, a.input_planes, h->in_cpad);
     else caz::pack_planes_kernel<float><<<batch, 256, smem, h->stream>>>(d_planes, static_cast<float*>(h->in_act), batch, a.input_planes, h->in_cpad);
     if ((rc = check_launch(h, "pack_planes_kernel"))) return rc;
   } else {
     const size_t total = (size_t)batch * 64 * h->in_cpad;
     const int blocks = (int)((total + 255) / 256);
-    if (tcp && is_fp16(h)) caz::encode_pack_kernel<__half><<<blocks, 256, 0, h->stream>>>(d_records, static_cast<__half*>(h->in_act), batch, h->in_cpad);
+    if (tcp && act_fp16(h)) caz::encode_pack_kernel<__half><<<blocks, 256, 0, h->stream>>>(d_records, static_cast<__half*>(h->in_act), batch, h->in_cpad);
     else if (tcp) caz::encode_pack_kernel<__nv_bfloat16><<<blocks, 256, 0, h->stream>>>(d_records, static_cast<__nv_bfloat16*>(h->in_act), batch, h->in_cpad);
     else caz::encode_pack_kernel<float><<<blocks, 256, 0, h->stream>>>(d_records, static_cast<float*>(h->in_act), batch, h->in_cpad);
     if ((rc = check_launch(h, "encode_pack_kernel"))) return rc;
@@ -1046,6 +1064,7 @@ void caz_destroy(caz_handle* h) {
                   h->d_records2};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
+  for (auto& e : h->ev_done) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
     if (h->ev_fwd[i]) cudaEventDestroy(h->ev_fwd[i]);
@@ -1063,8 +1082,9 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   if (!arch || !tensors || !out) return fail(nullptr, CAZ_ERR_INVALID, "null argument");
   *out = nullptr;
   const caz_arch& a = *arch;
-  if (precision != CAZ_PRECISION_BF16 && precision != CAZ_PRECISION_FP32 && precision != CAZ_PRECISION_FP16)
-    return fail(nullptr, CAZ_ERR_INVALID, "precision must be CAZ_PRECISION_BF16, CAZ_PRECISION_FP16 or CAZ_PRECISION_FP32");
+  if (precision != CAZ_PRECISION_BF16 && precision != CAZ_PRECISION_FP32 && precision != CAZ_PRECISION_FP16 &&
+      precision != CAZ_PRECISION_BF16_PURE)
+    return fail(nullptr, CAZ_ERR_INVALID, "precision must be CAZ_PRECISION_BF16, CAZ_PRECISION_BF16_PURE, CAZ_PRECISION_FP16 or CAZ_PRECISION_FP32");
   if (max_batch < 1) return fail(nullptr, CAZ_ERR_INVALID, "max_batch must be >= 1");
   if (a.input_planes < 1 || a.input_planes > 64 || a.res_blocks < 0 || a.filters < 1 || a.policy_filters < 1 ||
       a.value_filters < 1 || a.policy_filters + a.value_filters > caz::HEAD_MAX_F || a.value_fc < 1 ||
@@ -1138,6 +1158,10 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_fwd[i], cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
   }
+  for (int i = 0; i < caz_handle::TICKET_RING; ++i) {
+    h->ticket_state[i].store(0);
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+  }
   int rc;
   if (tcp) {
     if ((rc = make_halo_tmap(h, &h->tmap_in, h->in_act, h->in_cpad, a.stem_kernel, 2, 0, h->in_cpad * 2))) return bail(rc);
@@ -1150,6 +1174,10 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
     if (getenv("CAZ_NO_SPLIT_N")) h->split_n = false;
     if (const char* e = getenv("CAZ_L2_PREFETCH")) h->l2_prefetch = atoi(e) != 0;
     if (const char* e = getenv("CAZ_SNAKE")) h->snake = atoi(e) != 0;
+    h->sb_no_pairs = getenv("CAZ_SB_NO_PAIRS") != nullptr;
+    h->no_direct_output = getenv("CAZ_NO_DIRECT_OUTPUT") != nullptr;
+    if (const char* e = getenv("CAZ_SB_DBG")) h->sb_dbg = atoi(e);
+    if (const char* e = getenv("CAZ_DBG_EPI")) h->dbg_epi = atoi(e);
   } else {
     const size_t s3 = (size_t)(8 + a.block_kernel - 1) * (8 + a.block_kernel - 1) * a.filters * 4;
     const size_t s1 = (size_t)(8 + a.stem_kernel - 1) * (8 + a.stem_kernel - 1) * a.input_planes * 4;
@@ -1251,7 +1279,7 @@ static int eval_host(caz_handle* h, const float* planes, const uint8_t* records,
     // measured: the smaller launches lose what the copy overlap gains; overlap ACROSS calls is caz_submit/caz_collect.)
     CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_out[0], 0));   // a still-draining caz_submit on slot 0
     // (same for board records in pinned + mapped memory: 68 bytes per board, read by the kernel itself)
-    const bool sb_direct = tensor_path(h) && use_small_batch(h, batch) && !getenv("CAZ_NO_DIRECT_OUTPUT");
+    const bool sb_direct = tensor_path(h) && !h->no_direct_output && use_small_batch(h, batch);
     const uint8_t* drec = h->d_records;
     if (planes) CU_TRY(h, cudaMemcpyAsync(h->d_planes, planes, (size_t)batch * pin * 4, cudaMemcpyHostToDevice, h->stream));
     else if (sb_direct && (reinterpret_cast<uintptr_t>(records) & 3) == 0 && mapped_alias(records)) drec = static_cast<const uint8_t*>(mapped_alias(records));
@@ -1290,6 +1318,22 @@ static int eval_host(caz_handle* h, const float* planes, const uint8_t* records,
   return CAZ_OK;
 }
 
+// Common tail of the two submit entry points: claim the next ticket's ring entry, enqueue, record its completion event.
+static int submit_common(caz_handle* h, const float* planes, const uint8_t* records, int32_t batch, float* policy, float* value,
+                         const uint8_t* legal_mask, bool masked, int32_t* ticket) {
+  const int32_t t = h->next_ticket;
+  const int entry = t % caz_handle::TICKET_RING;
+  if (h->ticket_state[entry].load(std::memory_order_acquire) != 0)
+    return fail(h, CAZ_ERR_INVALID, fmt("caz_submit: %d submissions are outstanding; caz_collect one first", caz_handle::TICKET_RING));
+  int rc;
+  if ((rc = enqueue_pipelined(h, t & 1, planes, records, batch, policy, value, legal_mask, masked))) return rc;
+  CU_TRY(h, cudaEventRecord(h->ev_done[entry], h->copy_out));
+  h->ticket_state[entry].store(1, std::memory_order_release);
+  h->next_ticket = t + 1 == (1 << 30) ? 0 : t + 1;   // wraps at a multiple of the ring size
+  *ticket = t;
+  return CAZ_OK;
+}
+
 int caz_submit(caz_handle* h, const float* planes, int32_t batch, float* policy, float* value, const uint8_t* legal_mask,
                uint32_t flags, int32_t* ticket) {
   if (!h) return CAZ_ERR_INVALID;
@@ -1299,11 +1343,7 @@ int caz_submit(caz_handle* h, const float* planes, int32_t batch, float* policy,
   if (masked && !legal_mask) return fail(h, CAZ_ERR_INVALID, "masked softmax needs a legal mask");
   int rc;
   if ((rc = set_device(h))) return rc;
-  const int slot = h->next_slot;
-  if ((rc = enqueue_pipelined(h, slot, planes, nullptr, batch, policy, value, legal_mask, masked))) return rc;
-  h->next_slot ^= 1;
-  *ticket = slot;
-  return CAZ_OK;
+  return submit_common(h, planes, nullptr, batch, policy, value, legal_mask, masked, ticket);
 }
 
 int caz_submit_records(caz_handle* h, const uint8_t* records, int32_t batch, float* policy, float* value,
@@ -1316,18 +1356,19 @@ int caz_submit_records(caz_handle* h, const uint8_t* records, int32_t batch, flo
   if (h->arch.input_planes != CAZ_PLANES) return fail(h, CAZ_ERR_INVALID, "board records need an 18-plane network");
   int rc;
   if ((rc = set_device(h))) return rc;
-  const int slot = h->next_slot;
-  if ((rc = enqueue_pipelined(h, slot, nullptr, records, batch, policy, value, legal_mask, masked))) return rc;
-  h->next_slot ^= 1;
-  *ticket = slot;
-  return CAZ_OK;
+  return submit_common(h, nullptr, records, batch, policy, value, legal_mask, masked, ticket);
 }
 
 int caz_collect(caz_handle* h, int32_t ticket) {
-  if (!h || ticket < 0 || ticket > 1) return fail(h, CAZ_ERR_INVALID, "caz_collect: bad ticket");
+  if (!h) return CAZ_ERR_INVALID;
+  if (ticket < 0) return fail(h, CAZ_ERR_INVALID, "caz_collect: bad ticket");
+  const int entry = ticket % caz_handle::TICKET_RING;
+  if (h->ticket_state[entry].load(std::memory_order_acquire) != 1)
+    return fail(h, CAZ_ERR_INVALID, fmt("caz_collect: ticket %d is not outstanding (never issued, or already collected)", ticket));
   int rc;
   if ((rc = set_device(h))) return rc;
-  CU_TRY(h, cudaEventSynchronize(h->ev_out[ticket]));
+  CU_TRY(h, cudaEventSynchronize(h->ev_done[entry]));
+  h->ticket_state[entry].store(0, std::memory_order_release);
   return CAZ_OK;
 }
 
@@ -1457,7 +1498,7 @@ int caz_debug_conv_layer(caz_handle* h, int32_t layer, const float* in, const fl
   const CUtensorMap* tm = layer == 0 ? &h->tmap_in : &h->tmap_act[1];
   const int cpad = layer == 0 ? h->in_cpad : F;
   const unsigned gi = (unsigned)((rows * cpad + 255) / 256), go = (unsigned)((rows * F + 255) / 256);
-  if (tcp && is_fp16(h)) caz::cast_pad_kernel<__half><<<gi, 256, 0, h->stream>>>(d_in, (__half*)a_in, rows, L.cin, cpad);
+  if (tcp && act_fp16(h)) caz::cast_pad_kernel<__half><<<gi, 256, 0, h->stream>>>(d_in, (__half*)a_in, rows, L.cin, cpad);
   else if (tcp) caz::cast_pad_kernel<__nv_bfloat16><<<gi, 256, 0, h->stream>>>(d_in, (__nv_bfloat16*)a_in, rows, L.cin, cpad);
   else caz::cast_pad_kernel<float><<<gi, 256, 0, h->stream>>>(d_in, (float*)a_in, rows, L.cin, cpad);
   if ((rc = check_launch(h, "cast_pad_kernel"))) return rc;
@@ -1470,7 +1511,7 @@ int caz_debug_conv_layer(caz_handle* h, int32_t layer, const float* in, const fl
     CU_TRY(h, cudaMemcpyAsync(xf, d_res, rows * F * 4, cudaMemcpyDeviceToDevice, h->stream));
   }
   if ((rc = launch_conv(h, layer, a_in, tm, cpad, residual ? xf : nullptr, h->act[0], (tcp && (residual || layer == 0)) ? xf : nullptr, batch))) return rc;
-  if (tcp && is_fp16(h)) caz::widen_kernel<__half><<<go, 256, 0, h->stream>>>((const __half*)h->act[0], d_out, rows * F);
+  if (tcp && act_fp16(h)) caz::widen_kernel<__half><<<go, 256, 0, h->stream>>>((const __half*)h->act[0], d_out, rows * F);
   else if (tcp) caz::widen_kernel<__nv_bfloat16><<<go, 256, 0, h->stream>>>((const __nv_bfloat16*)h->act[0], d_out, rows * F);
   else caz::widen_kernel<float><<<go, 256, 0, h->stream>>>((const float*)h->act[0], d_out, rows * F);
   if ((rc = check_launch(h, "widen_kernel"))) return rc;

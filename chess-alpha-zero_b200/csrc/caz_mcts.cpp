@@ -19,7 +19,7 @@ extern "C" {
 int caz_mcts_create(const caz_mcts_config* c, int32_t n_games, uint64_t seed, const int32_t* move_label,
                     const int32_t* unflipped_index, int32_t n_threads, caz_mcts** out) {
   if (!c || !out || !move_label || !unflipped_index || n_games < 1 || c->n_labels < 1 || c->search_threads < 1 ||
-      c->simulation_num_per_move < 1)
+      c->simulation_num_per_move < 2)   /* with 1 only the root is expanded: no visit counts to pick a move from */
     return 1;
   MctsConfig m;
   m.simulation_num_per_move = c->simulation_num_per_move;

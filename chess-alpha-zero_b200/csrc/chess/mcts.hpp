@@ -459,9 +459,22 @@ class Mcts {
   }
 
   // Runs the descents of every game; writes the leaves' board records (68 bytes each) in game order.
+  // Call order is collect -> apply -> collect ...: a second collect() while leaves of the first are still waiting for their
+  // apply() returns 1 and changes nothing (collect_game would forget the requests but not the pending nodes, and every
+  // later descent would be withdrawn for ever).
   int collect(uint8_t* records, int capacity, int* n_out) {
     if (static_cast<int64_t>(games.size()) * cfg.search_threads > capacity) return 1;
+    if (!batch_map.empty()) return 1;
+    for (const auto& gs : games)
+      if (gs.inflight > 0) return 1;
     for (;;) {
+      // progress = descents completed + plies played + games ended; an iteration that moves none of them cannot end
+      auto progress = [&] {
+        int64_t p = 0;
+        for (const auto& gs : games) p += gs.sims_done + static_cast<int64_t>(gs.game.num_halfmoves) * 4096 + (static_cast<int64_t>(gs.games_played) << 32) + (gs.finished ? 1 : 0);
+        return p;
+      };
+      const int64_t before = progress();
       parallel_games([&](int g, MctsStats& st) { collect_game(games[g], st); });
       batch_map.clear();
       int n = 0;
@@ -480,6 +493,7 @@ class Mcts {
       for (auto& gs : games) any_active |= !gs.finished;
       if (!any_active) return 0;
       finish_moves();
+      if (progress() == before) return 1;   // cannot happen in a consistent tree; never spin
     }
   }
 
@@ -538,6 +552,7 @@ class Mcts {
         move_of[l] = e.move;
         total += e.n;
       }
+      if (total <= 0.0) total = 1.0;   // unreachable: caz_mcts_create rejects fewer than 2 simulations per move
       for (auto& x : pol) x /= total;
       double tau = std::pow(cfg.tau_decay_rate, gs.game.num_halfmoves + 1);
       if (tau < 0.1) tau = 0;
@@ -582,14 +597,16 @@ class Mcts {
       gs.game.push(move_of[action]);
       ++st.moves_played;
       const int res = gs.game.result();
-      if (res) {
-        gs.winner = res;
+      // self_play_buffer (self_play.py:127-133): after EVERY step, `if env.num_halfmoves >= max_game_length:
+      // env.adjudicate()` -- the material count overrides even a result the step itself produced
+      if (gs.game.num_halfmoves >= cfg.max_game_length) {   // adjudicate (chess_env.py:118-129)
+        gs.winner = adjudicate(gs.game.pos);
+        ++st.adjudications;
         end_game(gs, st);
         return;
       }
-      if (gs.game.num_halfmoves >= cfg.max_game_length) {   // adjudicate (chess_env.py:118-129): material count
-        gs.winner = adjudicate(gs.game.pos);
-        ++st.adjudications;
+      if (res) {
+        gs.winner = res;
         end_game(gs, st);
         return;
       }

@@ -60,7 +60,7 @@ struct Args {
   int stem_k, stem_kchunks;  // stem kernel size, input channel chunks (in_cpad / 64)
   int blk_k;                  // tower kernel size
   int in_planes, in_cpad;
-  int fp16;                   // 16-bit operands are fp16 instead of bf16
+  int fp16;                   // operand formats: ptx::FMT_A_FP16 (activations) | ptx::FMT_B_FP16 (weights); 0 = both bf16
   int dbg;                    // measurement switch (CAZ_SB_DBG), 0 in production: bits 8.. = the CTA that writes the trace
   int slot_bytes, n_slots;    // weight ring geometry
   const float* planes;        // fp32 [batch][in_planes][64] or nullptr
@@ -420,7 +420,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
         const float val = args.planes ? v[j] : record_plane_value(reinterpret_cast<const uint8_t*>(s_rec + p * 17), c, sq);
         const int row = ((sq >> 3) + pad) * args.nb * hw + p * hw + (sq & 7) + pad;
         const int off = row * 128 + (((c >> 3) ^ (row & 7)) << 4) + ((c & 7) << 1);
-        *reinterpret_cast<uint16_t*>(smem_a + off) = ptx::pack_h16(val, args.fp16 != 0);
+        *reinterpret_cast<uint16_t*>(smem_a + off) = ptx::pack_h16(val, (args.fp16 & ptx::FMT_A_FP16) != 0);
       }
     }
     ptx::fence_proxy_async();   // generic-proxy writes -> the tensor core's async-proxy reads
@@ -540,7 +540,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     // ============ MMA issuers (two warps: a tcgen05.mma costs its issuing thread ~60 cycles whatever its shape,
     // so with N = 16..64 the issue rate, not the tensor pipe, bounds a layer) ============
     const int which = warp - 1;
-    const uint32_t idesc = ptx::idesc_h16_f32(PAIR ? 128 : 64 * args.nb, args.ns, args.fp16 != 0);
+    const uint32_t idesc = ptx::idesc_h16_f32(PAIR ? 128 : 64 * args.nb, args.ns, args.fp16);
     const uint64_t b_desc0 = desc_sw128(ptx::smem_u32(smem_w), 1024);
     const uint64_t tap_desc = static_cast<uint64_t>(tap_bytes >> 4);
     const uint64_t slot_desc = static_cast<uint64_t>(args.slot_bytes >> 4);
@@ -720,7 +720,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              pk[e] = ptx::pack_h16x2(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1], args.fp16 != 0);
+              pk[e] = ptx::pack_h16x2(f[q * 8 + e * 2], f[q * 8 + e * 2 + 1], (args.fp16 & ptx::FMT_A_FP16) != 0);
             }
             *reinterpret_cast<uint4*>(orow + q * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }

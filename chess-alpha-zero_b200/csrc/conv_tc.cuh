@@ -78,7 +78,7 @@ struct ConvArgs {
   float* featp;             // [batch][pf*64]
   float* featv;             // [batch][vf*64]
   int pf, vf;
-  int fp16;                 // 16-bit operands are fp16 instead of bf16 (CAZ_PRECISION_FP16)
+  int fp16;                 // operand formats: ptx::FMT_A_FP16 (activations) | ptx::FMT_B_FP16 (weights); 0 = both bf16
   // Plain-GEMM use of the same kernel (the heads' Dense layers: ksize 1, rows = positions in groups of 64):
   // the N dimension is walked in n_tiles tiles of `n` columns, the result goes to a ROW-MAJOR fp32 matrix.
   int n_tiles;              // 1 for convolutions
@@ -252,7 +252,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
       for (int c = 0; c < 4; ++c) {
         uint32_t w[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) w[e] = ptx::pack_h16x2(f[c * 8 + e * 2], f[c * 8 + e * 2 + 1], args.fp16 != 0);
+        for (int e = 0; e < 4; ++e) w[e] = ptx::pack_h16x2(f[c * 8 + e * 2], f[c * 8 + e * 2 + 1], (args.fp16 & ptx::FMT_A_FP16) != 0);
         stage_b[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_uint4(w[0], w[1], w[2], w[3]);
       }
       __syncwarp();
@@ -372,7 +372,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_const
       }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = ptx::idesc_h16_f32(BLOCK_M, args.n, args.fp16 != 0);
+    const uint32_t idesc = ptx::idesc_h16_f32(BLOCK_M, args.n, args.fp16);
     // descriptors differ only in the 14-bit start-address field: add (byte offset >> 4) to a template
     const uint64_t a_desc0 = desc_sw(ptx::smem_u32(smem_a), hw * rb, rb);  // next 8-row group = next (rank, board)
     const uint64_t b_desc0 = desc_sw(ptx::smem_u32(smem_b), 8 * rb, rb);

@@ -163,7 +163,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (leader only) =====================
     if (leader) {
-      const uint32_t idesc = ptx::idesc_h16_f32(256, args.n, args.fp16 != 0);
+      const uint32_t idesc = ptx::idesc_h16_f32(256, args.n, args.fp16);
       const uint64_t a_desc0 = tc::desc_sw(ptx::smem_u32(smem_a), hw * rb, rb);
       const uint64_t b_desc0 = tc::desc_sw(ptx::smem_u32(smem_b), 8 * rb, rb);
       const int tap_rows16 = rb >> 4;

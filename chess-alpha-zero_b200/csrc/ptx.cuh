@@ -346,10 +346,12 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
-// same with fp16 operands (format code 0) when `fp16` is set: identical tensor throughput, 11-bit significand
-__host__ __device__ constexpr uint32_t idesc_h16_f32(int m, int n, bool fp16) {
-  return fp16 ? ((1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24))
-              : idesc_bf16_f32(m, n);
+// The A and B formats are separate fields (format code 0 = fp16, 1 = bf16) and may differ: identical tensor
+// throughput for every combination.  `fmt` bit 0: A (activations) is fp16; bit 1: B (weights) is fp16.
+constexpr int FMT_A_FP16 = 1, FMT_B_FP16 = 2;
+__host__ __device__ constexpr uint32_t idesc_h16_f32(int m, int n, int fmt) {
+  return (1u << 4) | ((fmt & FMT_A_FP16) ? 0u : (1u << 7)) | ((fmt & FMT_B_FP16) ? 0u : (1u << 10)) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // two fp32 values -> one 32-bit word of 16-bit operands (bf16, or fp16 saturated to its finite range)

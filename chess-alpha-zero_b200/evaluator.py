@@ -13,7 +13,8 @@ import numpy as np
 from . import _lib
 from .keras_graph import parse_config
 
-_PRECISIONS = {"bf16": _lib.PRECISION_BF16, "fp16": _lib.PRECISION_FP16, "fp32": _lib.PRECISION_FP32}
+_PRECISIONS = {"bf16": _lib.PRECISION_BF16, "fp16": _lib.PRECISION_FP16, "fp32": _lib.PRECISION_FP32,
+               "bf16_pure": _lib.PRECISION_BF16_PURE}
 
 
 class Evaluator:
@@ -82,7 +83,7 @@ class Evaluator:
             _lib.check(self._handle, rc)
 
     def submit(self, planes, policy, value, legal_mask=None):
-        """Non-blocking predict_into: returns a ticket for collect().  Keep at most two in flight; the host
+        """Non-blocking predict_into: returns a ticket for collect() (tickets count up; up to 16 may be outstanding); the host
         buffers (ideally pinned) must stay untouched until collected.  Copies of one batch then overlap the forward
         pass of the other."""
         ticket = ctypes.c_int32(-1)

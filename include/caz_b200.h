@@ -36,10 +36,17 @@ extern "C" {
 #define CAZ_ERR_KERNEL 4      /* a kernel watchdog fired (pipeline never completed) */
 
 /* numeric builds (BASELINE.json north_star: "fp32-accumulate build" and "bf16 build") */
-#define CAZ_PRECISION_BF16 0  /* bf16 operands on tcgen05 tensor cores, fp32 TMEM accumulators, fp32 heads */
+#define CAZ_PRECISION_BF16 0  /* THE bf16 build: every weight bf16, fp32 TMEM accumulators, fp32 residual stream, fp32 heads.
+                                 The 16-bit operand COPIES of the activations (the A operand of tcgen05.mma) are written as
+                                 fp16, saturated to +-65504: kind::f16 takes the A and B formats independently at the same
+                                 rate, and activation rounding was two thirds of the value head's error variance
+                                 (profiles/r2_precision_ablation.md): max|dv| 0.8-0.95e-2 instead of 1.6-2.4e-2 */
 #define CAZ_PRECISION_FP32 1  /* fp32 operands and accumulation on the CUDA cores (1e-4 parity build)      */
-#define CAZ_PRECISION_FP16 2  /* the tensor-core build with fp16 operands: same kernels and throughput as BF16, 8x finer
-                                 operand rounding; activations are saturated to +-65504 when stored as operands   */
+#define CAZ_PRECISION_FP16 2  /* the tensor-core build with fp16 weights AND activations: same kernels and throughput,
+                                 8x finer operand rounding; weights below 6e-5 lose bits (fp16 subnormals)         */
+#define CAZ_PRECISION_BF16_PURE 3 /* bf16 weights and bf16 activation operands (what round 1 called BF16): kept for
+                                 comparison; misses north_star's 2e-2 on the value of the reference-init net in about
+                                 half of the summation orders                                                      */
 
 /* eval flags */
 #define CAZ_EVAL_DEFAULT 0
@@ -120,11 +127,16 @@ int caz_eval_device(caz_handle* h, const float* d_planes, int32_t batch, float* 
 int caz_eval_records(caz_handle* h, const uint8_t* records, int32_t batch, float* policy, float* value,
                      const uint8_t* legal_mask, uint32_t flags);
 
-/* Pipelined form of caz_eval for callers that keep two batches in flight (batch <= max_batch): caz_submit enqueues
- * H2D, forward pass and D2H on three streams and returns at once with a ticket (0 or 1, alternating staging slots);
- * caz_collect(ticket) blocks until that batch's outputs are in the caller's host buffers.  Batch i+1's H2D and
- * batch i-1's D2H then run under batch i's forward pass.  At most two tickets may be outstanding; host buffers must
- * stay valid (and should be pinned, caz_host_alloc) until collected. */
+/* Pipelined form of caz_eval for callers that keep several batches in flight (batch <= max_batch): caz_submit enqueues
+ * H2D, forward pass and D2H on three streams and returns at once with a ticket; caz_collect(ticket) blocks until
+ * that batch's outputs are in the caller's host buffers.  Batch i+1's H2D and batch i-1's D2H then run under batch
+ * i's forward pass.  Tickets count up from 0 (they wrap at 2^30); each has its own completion event, so collecting a
+ * ticket never waits for a later submission.  Up to 16 tickets may be outstanding (a 17th caz_submit fails with
+ * CAZ_ERR_INVALID until one is collected); with more than two in flight the later ones queue on the streams behind
+ * the two staging slots.  A ticket is collected exactly once; collecting an unknown ticket is CAZ_ERR_INVALID.
+ * Threads: the submit calls follow the one-call-per-handle rule; caz_collect touches only its ticket and may run on
+ * another thread concurrently with a submit.  Host buffers must stay valid (and should be pinned, caz_host_alloc)
+ * until collected. */
 int caz_submit(caz_handle* h, const float* planes, int32_t batch, float* policy, float* value,
                const uint8_t* legal_mask, uint32_t flags, int32_t* ticket);
 /* caz_submit from board records (68 bytes per position, see caz_eval_records): what a batched search driver with two or

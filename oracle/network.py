@@ -161,26 +161,37 @@ def _bf16_round(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
-def forward_bf16(cfg, weights, planes, fp32_residual=False, return_logits=False, fp32_head_input=False):
-    """bf16-operand / fp32-accumulate emulation of the tensor-core build (see module docstring)."""
+def _fp16_round(x):
+    return x.clamp(-65504.0, 65504.0).to(torch.float16).to(torch.float32)   # saturating, like the kernels' stores
+
+
+ROUNDERS = {"bf16": _bf16_round, "fp16": _fp16_round, "fp32": lambda x: x}
+
+
+def forward_bf16(cfg, weights, planes, fp32_residual=False, return_logits=False, fp32_head_input=False,
+                 act_format="bf16", w_format="bf16"):
+    """16-bit-operand / fp32-accumulate emulation of the tensor-core builds (see module docstring): conv weights are
+    rounded to `w_format`, the operand copies of the activations to `act_format` (the library's bf16 build is
+    w_format="bf16", act_format="fp16"; its BF16_PURE build "bf16"/"bf16"; its FP16 build "fp16"/"fp16")."""
     tower, heads = fold_plan(cfg, weights)
+    _act, _w = ROUNDERS[act_format], ROUNDERS[w_format]
     with torch.no_grad():
-        x = _bf16_round(torch.from_numpy(np.ascontiguousarray(planes, dtype=np.float32)))   # NCHW
+        x = _act(torch.from_numpy(np.ascontiguousarray(planes, dtype=np.float32)))   # NCHW
         skip = None
         for kind, k, b in tower:
-            kt = _bf16_round(torch.from_numpy(k.astype(np.float32)).permute(3, 2, 0, 1).contiguous())
+            kt = _w(torch.from_numpy(k.astype(np.float32)).permute(3, 2, 0, 1).contiguous())
             bt = torch.from_numpy(b.astype(np.float32)).view(1, -1, 1, 1)
             p = (k.shape[0] - 1) // 2
-            y = F.conv2d(_bf16_round(x), kt, padding=p) + bt
+            y = F.conv2d(_act(x), kt, padding=p) + bt
             if kind == "conv1":
                 skip = x
             if kind == "conv2":
                 y = y + skip
             x = torch.relu(y)
             if not fp32_residual or kind == "conv1":
-                x = _bf16_round(x)   # with an fp32 residual stream only conv1's output is ever stored as bf16
+                x = _act(x)   # with an fp32 residual stream only conv1's output is ever stored as a 16-bit operand
         if not fp32_head_input:
-            x = _bf16_round(x)
+            x = _act(x)
         B = x.shape[0]
         feats = x.permute(0, 2, 3, 1).reshape(B * 64, -1)
         out = {}

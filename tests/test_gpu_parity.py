@@ -21,13 +21,13 @@ from oracle import weights as oweights
 pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-4      # north_star: fp32-accumulate build
-BF16_TOL = 2e-2      # north_star: bf16 build, policy probabilities and value
-# The value head of the reference's random-init net saturates (|v| up to 0.99) and amplifies the tower's bf16 rounding
-# noise: max|dv| over 256 positions measures 1.9e-2 .. 2.4e-2 depending only on the fp32 summation ORDER inside the
-# MMAs (tap-major vs chunk-major K loop).  The gate below therefore allows 2.5e-2 on the value of that one net;
-# probabilities, the stress net and the argmax bar stay at north_star's figures.
-BF16_VALUE_TOL_REFERENCE_INIT = 2.5e-2
+BF16_TOL = 2e-2      # north_star: bf16 build, policy probabilities AND value, every network below
 ARGMAX_AGREE = 0.99  # north_star: bit-exact argmax move agreement
+# The bf16 build = bf16 weights x fp16 activation operands (include/caz_b200.h, profiles/r2_precision_ablation.md).
+# With bf16 activation operands too (precision="bf16_pure", round 1's build) the value head of the reference's
+# random-init net lands at max|dv| 1.6e-2 .. 2.4e-2 depending only on the fp32 summation order: recorded below, not gated
+# at north_star's figure.
+BF16_PURE_VALUE_TOL = 3e-2
 
 
 def _planes(n, seed=5):
@@ -117,8 +117,8 @@ def _ref_layer(cfg, w, layer, x_nhwc, res, bf16):
     _, k, b = tower[layer]
     kt = torch.from_numpy(k.astype(np.float32)).permute(3, 2, 0, 1).contiguous()
     xt = torch.from_numpy(x_nhwc.reshape(-1, 8, 8, x_nhwc.shape[-1])).permute(0, 3, 1, 2).contiguous()
-    if bf16:
-        kt, xt = kt.bfloat16().float(), xt.bfloat16().float()
+    if bf16:   # the bf16 build's operands: bf16 weights, fp16 activations
+        kt, xt = kt.bfloat16().float(), xt.half().float()
     y = F.conv2d(xt.double(), kt.double(), padding=(k.shape[0] - 1) // 2) + torch.from_numpy(b).view(1, -1, 1, 1)
     y = y.permute(0, 2, 3, 1).reshape(x_nhwc.shape[0], 64, -1)
     if res is not None:
@@ -180,18 +180,31 @@ def test_bf16_build_matches_oracle_reference_init(net_default):
     ev = caz.Evaluator(cfg, w, precision="bf16", max_batch=256)
     p, v = ev.predict_on_batch(x)
     dp, dv, agree = _bf16_report("bf16 vs fp32 oracle [keras_default]", p, v, wp, wv, len(x))
-    assert dp <= BF16_TOL and dv <= BF16_VALUE_TOL_REFERENCE_INIT and agree >= ARGMAX_AGREE
+    assert dp <= BF16_TOL and dv <= BF16_TOL and agree >= ARGMAX_AGREE
     assert np.allclose(p.sum(axis=1), 1, atol=1e-5)
     # informational: the CPU emulation of the same rounding points.  It cannot be a tight gate at network level --
     # a 1e-7 relative perturbation of one layer's accumulators flips bf16 roundings downstream and moves the final
     # activations by as much as the bf16 noise itself (measured); the tight checks are the per-layer tests above.
-    ep, evv = onet.forward_bf16(cfg, w, x, fp32_residual=True, fp32_head_input=True)
+    ep, evv = onet.forward_bf16(cfg, w, x, fp32_residual=True, fp32_head_input=True, act_format="fp16", w_format="bf16")
     print(f"   vs bf16 emulation: max|dp|={np.abs(p - ep).max():.3e} max|dv|={np.abs(v - evv).max():.3e}")
-    assert np.abs(p - ep).max() <= BF16_TOL and np.abs(v - evv).max() <= BF16_VALUE_TOL_REFERENCE_INIT
+    assert np.abs(p - ep).max() <= BF16_TOL and np.abs(v - evv).max() <= BF16_TOL
     ev.close()
     ev = caz.Evaluator(cfg, w, precision="fp32", max_batch=256)
     p, v = ev.predict_on_batch(x)
     assert np.abs(p - wp).max() <= FP32_TOL and np.abs(v - wv).max() <= FP32_TOL
+    ev.close()
+
+
+def test_bf16_pure_build_for_the_record(net_default):
+    """bf16 weights AND bf16 activation operands: probabilities and argmax inside north_star's bar, the value of this
+    net is not (measured 1.6e-2 .. 2.4e-2) -- which is why the bf16 build writes its activation operands as fp16."""
+    cfg, w, x, fens, (wp, wv) = net_default
+    ev = caz.Evaluator(cfg, w, precision="bf16_pure", max_batch=256)
+    p, v = ev.predict_on_batch(x)
+    dp, dv, agree = _bf16_report("bf16_pure vs fp32 oracle [keras_default]", p, v, wp, wv, len(x))
+    assert dp <= BF16_TOL and dv <= BF16_PURE_VALUE_TOL and agree >= ARGMAX_AGREE
+    ps, vs = ev.predict_on_batch(x[:16])                               # small-batch kernel, same operands
+    assert np.abs(ps - wp[:16]).max() <= BF16_TOL and np.abs(vs - wv[:16]).max() <= BF16_PURE_VALUE_TOL
     ev.close()
 
 
@@ -208,13 +221,14 @@ def test_fp16_build_matches_oracle_reference_init(net_default, net):
 
 
 def test_bf16_build_matches_oracle(net, ev_bf16):
-    """Stress recipe (random BN statistics, biases, head scales; many near-uniform policy rows, so the argmax bar
-    is lower than north_star's): probabilities and value inside north_star's 2e-2."""
+    """Stress recipe (random BN statistics, biases, head scales): probabilities and value inside north_star's 2e-2.  Many
+    of its policy rows are near-uniform (top-2 gap below the fp32 oracle's own summation noise), so the argmax bar is
+    98 % here; on the reference-init net above it is north_star's 99 %."""
     cfg, w, x, fens, (wp, wv) = net
     assert wp.max() > 0.01 and wp.std(axis=1).min() > 0              # the policy head is alive
     p, v = ev_bf16.predict_on_batch(x)
     dp, dv, agree = _bf16_report("bf16 vs fp32 oracle [randomized]", p, v, wp, wv, len(x))
-    assert dp <= BF16_TOL and dv <= BF16_TOL and agree >= 0.93
+    assert dp <= BF16_TOL and dv <= BF16_TOL and agree >= 0.98
     assert np.allclose(p.sum(axis=1), 1, atol=1e-5)
     p2, v2 = ev_bf16.predict_records(caz.encoder.fens_to_records(fens))
     assert np.array_equal(p2, p) and np.array_equal(v2, v)
@@ -252,19 +266,19 @@ def test_small_batch_persistent_kernel(net_default):
     ev = caz.Evaluator(cfg, w, precision="bf16", max_batch=256)
     ref_p, ref_v = ev.predict_on_batch(x[:64])
     dp, dv, agree = _bf16_report("small-batch kernel vs fp32 oracle [keras_default, 64]", ref_p, ref_v, wp[:64], wv[:64], 64)
-    assert dp <= BF16_TOL and dv <= BF16_VALUE_TOL_REFERENCE_INIT and agree >= ARGMAX_AGREE
+    assert dp <= BF16_TOL and dv <= BF16_TOL and agree >= ARGMAX_AGREE
     for batch in (1, 2, 3, 15, 16, 17, 32, 33, 36, 37, 48):
         p, v = ev.predict_on_batch(x[:batch])
         assert np.array_equal(p, ref_p[:batch]) and np.array_equal(v, ref_v[:batch]), batch
     for batch in (65, 72):   # the largest grids of the persistent kernel: 36 CTA pairs x 2 slices
         p, v = ev.predict_on_batch(x[:batch])
         assert np.array_equal(p[:64], ref_p) and np.array_equal(v[:64], ref_v), batch
-        assert np.abs(p - wp[:batch]).max() <= BF16_TOL and np.abs(v - wv[:batch]).max() <= BF16_VALUE_TOL_REFERENCE_INIT
+        assert np.abs(p - wp[:batch]).max() <= BF16_TOL and np.abs(v - wv[:batch]).max() <= BF16_TOL
     # against the per-layer kernels: same arithmetic up to fp32 summation order, so bf16-noise level agreement
     ev.set_small_batch_limit(0)
     big_p, big_v = ev.predict_on_batch(x[:64])
     print(f"   small vs per-layer path: max|dp|={np.abs(big_p - ref_p).max():.3e} max|dv|={np.abs(big_v - ref_v).max():.3e}")
-    assert np.abs(big_p - ref_p).max() <= BF16_TOL and np.abs(big_v - ref_v).max() <= BF16_VALUE_TOL_REFERENCE_INIT
+    assert np.abs(big_p - ref_p).max() <= BF16_TOL and np.abs(big_v - ref_v).max() <= BF16_TOL
     ev.close()
     # the architecture the reference ships as JSON (3x3 stem) and a 19-block tower through the same kernel
     for variant, n in ((dict(stem_k=3, value_filters=1), 16), (dict(blocks=19), 8)):
@@ -273,13 +287,11 @@ def test_small_batch_persistent_kernel(net_default):
         want_p, want_v = onet.forward_graph(cfg2, w2, x[:n])
         ev2 = caz.Evaluator(cfg2, w2, precision="bf16", max_batch=32)
         p, v = ev2.predict_on_batch(x[:n])
-        # north_star's 2e-2 is stated for the 7x256 net; 19 blocks accumulate ~1.6x the bf16 rounding noise
-        tol = BF16_TOL if "blocks" not in variant else 3e-2
-        assert np.abs(p - want_p).max() <= tol and np.abs(v - want_v).max() <= tol, variant
+        assert np.abs(p - want_p).max() <= BF16_TOL and np.abs(v - want_v).max() <= BF16_TOL, variant
         ev2.close()
 
 
-@pytest.mark.parametrize("precision,tol_p,tol_v", [("bf16", BF16_TOL, BF16_VALUE_TOL_REFERENCE_INIT), ("fp16", 4e-3, 4e-3)])
+@pytest.mark.parametrize("precision,tol_p,tol_v", [("bf16", BF16_TOL, BF16_TOL), ("fp16", 4e-3, 4e-3)])
 def test_small_batch_kernel_records_masks_and_precisions(net_default, precision, tol_p, tol_v):
     """The persistent kernel's other entrances: board records (its in-kernel encoder builds the stem tile), the
     legal-move mask in its per-tile softmax, fp16 operands."""
@@ -362,9 +374,14 @@ def test_submit_collect_pipelined_api(net, ev_bf16):
              _lib.PinnedArray((200, 1), np.float32)) for _ in range(2)]
     pins[0][0].array[:] = x[:200]
     pins[1][0].array[:] = x[56:256]
+    base = ev_bf16.submit(pins[0][0].array, pins[0][1].array, pins[0][2].array)     # tickets count up per handle
+    ev_bf16.collect(base)
+    with pytest.raises(caz.CazError):
+        ev_bf16.collect(base)                                                          # a ticket is collected once
+    base += 1
     for rounds in range(3):
         t = [ev_bf16.submit(pins[i][0].array, pins[i][1].array, pins[i][2].array) for i in range(2)]
-        assert sorted(t) == [0, 1]
+        assert t[1] == t[0] + 1 and t[0] == 2 * rounds + base
         for i in range(2):
             ev_bf16.collect(t[i])
             assert np.array_equal(pins[i][1].array, want[i][0]) and np.array_equal(pins[i][2].array, want[i][1])
@@ -372,6 +389,18 @@ def test_submit_collect_pipelined_api(net, ev_bf16):
             pins[i][1].array[:] = 0
     with pytest.raises(caz.CazError):
         ev_bf16.submit(np.zeros((513, 18, 8, 8), np.float32), np.zeros((513, 1968), np.float32), np.zeros((513, 1), np.float32))
+    # four submissions in flight (what the self-play driver does with four game groups): each ticket completes on its own
+    # event, in any collection order; the 17th outstanding submission is refused
+    more = [(_lib.PinnedArray((200, 1968), np.float32), _lib.PinnedArray((200, 1), np.float32)) for _ in range(4)]
+    t = [ev_bf16.submit(pins[i & 1][0].array, more[i][0].array, more[i][1].array) for i in range(4)]
+    for i in (2, 0, 3, 1):
+        ev_bf16.collect(t[i])
+        assert np.array_equal(more[i][0].array, want[i & 1][0]) and np.array_equal(more[i][1].array, want[i & 1][1])
+    t = [ev_bf16.submit(pins[0][0].array, more[0][0].array, more[0][1].array) for i in range(16)]
+    with pytest.raises(caz.CazError):
+        ev_bf16.submit(pins[0][0].array, more[0][0].array, more[0][1].array)
+    for tk in t:
+        ev_bf16.collect(tk)
 
 
 def test_submit_records_pipelined_api(net, ev_bf16):
@@ -387,9 +416,11 @@ def test_submit_records_pipelined_api(net, ev_bf16):
              _lib.PinnedArray((200,), np.float32)) for _ in range(2)]
     pins[0][0].array[:] = recs[:200]
     pins[1][0].array[:] = recs[56:256]
+    base = ev_bf16.submit_records(pins[0][0].array, pins[0][1].array, pins[0][2].array) + 1
+    ev_bf16.collect(base - 1)
     for rounds in range(3):
         t = [ev_bf16.submit_records(pins[i][0].array, pins[i][1].array, pins[i][2].array) for i in range(2)]
-        assert sorted(t) == [0, 1]
+        assert t[1] == t[0] + 1 and t[0] == 2 * rounds + base
         for i in range(2):
             ev_bf16.collect(t[i])
             assert np.array_equal(pins[i][1].array, want[i][0]) and np.array_equal(pins[i][2].array, want[i][1].reshape(-1))
@@ -425,7 +456,128 @@ def test_keras_default_init_19_blocks(net):
     ev.close()
 
 
+def test_per_layer_path_19_blocks_256_boards(net):
+    """Config 5's network (19 x 256) through the PER-LAYER kernels (CTA-pair implicit GEMM, PDL chain, heads as
+    tensor-core GEMMs): 256 distinct boards against the oracle, and the small-batch kernel's answer for the first 64."""
+    cfg = oweights.keras_config(blocks=19)
+    w = oweights.synth_weights(cfg, seed=6, recipe="keras_default")
+    x = net[2]
+    wp, wv = onet.forward_graph(cfg, w, x)
+    ev = caz.Evaluator(cfg, w, precision="bf16", max_batch=256)
+    l0 = ev.kernel_launches
+    p, v = ev.predict_on_batch(x)
+    assert ev.kernel_launches - l0 >= 1 + 39, "256 boards must take the per-layer path (one launch per convolution)"
+    dp, dv, agree = _bf16_report("per-layer path, 19x256, 256 boards", p, v, wp, wv, len(x))
+    assert dp <= BF16_TOL and dv <= BF16_TOL and agree >= ARGMAX_AGREE
+    assert np.allclose(p.sum(axis=1), 1, atol=1e-5)
+    ps, vs = ev.predict_on_batch(x[:64])                               # persistent kernel: same operands, other order
+    assert np.abs(ps - p[:64]).max() <= BF16_TOL and np.abs(vs - v[:64]).max() <= BF16_TOL
+    ev.set_small_batch_limit(0)
+    p2, v2 = ev.predict_on_batch(x[:150])                              # per-layer again, ragged: bit-identical rows
+    assert np.array_equal(p2, p[:150]) and np.array_equal(v2, v[:150])
+    ev.close()
+
+
+def test_4096_distinct_positions_against_oracle(net_default):
+    """BASELINE's full batch with 4096 DIFFERENT positions: a random 512-row subset is checked against the oracle, every
+    row is a probability vector, and the result does not depend on where in the batch a position sits."""
+    cfg, w = net_default[0], net_default[1]
+    fens = oenc.synthetic_fens(4096, seed=2024)
+    assert len(set(fens)) >= 4090
+    x = np.stack([oenc.canon_input_planes(f) for f in fens])
+    ev = caz.Evaluator(cfg, w, precision="bf16", max_batch=4096)
+    p, v = ev.predict_on_batch(x)
+    assert p.shape == (4096, 1968) and np.allclose(p.sum(axis=1), 1.0, atol=1e-5) and (np.abs(v) < 1).all()
+    rows = np.sort(np.random.default_rng(5).choice(4096, size=512, replace=False))
+    wp, wv = onet.forward_graph(cfg, w, x[rows])
+    dp, dv, agree = _bf16_report("4096 distinct positions, 512-row subset", p[rows], v[rows], wp, wv, 512)
+    assert dp <= BF16_TOL and dv <= BF16_TOL and agree >= ARGMAX_AGREE
+    pr, vr = ev.predict_records(caz.encoder.fens_to_records(fens))    # device-side encoder at full size
+    assert np.array_equal(pr, p) and np.array_equal(vr, v)
+    p2, v2 = ev.predict_on_batch(x[rows])                              # the same boards in a 512 batch
+    assert np.array_equal(p2, p[rows]) and np.array_equal(v2, v[rows])
+    ev.close()
+
+
 # ---- a7/a8: the pipe protocol, ours and the reference's own server class ------------------------
+def _reference_api_class():
+    """The reference's UNMODIFIED ChessModelAPI: from the checkout in the build container, or from the copy
+    __graft_entry__.build() stages under baseline/_ref/ (git-ignored; it travels to the GPU box with the snapshot)."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for src in ("/root/reference/src", os.path.join(root, "baseline", "_ref")):
+        if os.path.exists(os.path.join(src, "chess_zero", "agent", "api_chess.py")):
+            if src not in sys.path:
+                sys.path.insert(0, src)
+            return importlib.import_module("chess_zero.agent.api_chess").ChessModelAPI, src
+    return None, None
+
+
+def test_reference_chessmodelapi_runs_on_the_cuda_evaluator(net):
+    """Drop-in proof on hardware: the reference's own prediction_worker thread (api_chess.py:51-69) calls
+    self.agent_model.model.predict_on_batch on OUR ChessModel; 16 client threads speak its pipe protocol."""
+    RefAPI, src = _reference_api_class()
+    if RefAPI is None:
+        pytest.skip("no copy of the reference's api_chess.py (run __graft_entry__.build() where /root/reference exists)")
+    assert "chess-alpha-zero_b200" not in (RefAPI.__module__ or "") and RefAPI is not caz.ChessModelAPI
+    cfg, w, x, fens, (wp, wv) = net
+    model = caz.ChessModel(caz.Config("mini"), precision="bf16", max_batch=64)
+    model._install(cfg, w)
+    api = RefAPI(model)                                                # reference code from here on
+    pipes = [api.create_pipe() for _ in range(16)]
+    api.start()
+    results = {}
+
+    def client(i, pipe):
+        out = []
+        for j in range(i, 128, 16):
+            pipe.send(x[j])
+            p, v = pipe.recv()
+            out.append((j, p, v))
+        results[i] = out
+
+    ts = [threading.Thread(target=client, args=(i, p)) for i, p in enumerate(pipes)]
+    [t.start() for t in ts]
+    [t.join(timeout=60) for t in ts]
+    assert len(results) == 16 and sum(len(o) for o in results.values()) == 128
+    for out in results.values():
+        for j, p, v in out:
+            assert isinstance(v, float) and p.shape == (1968,) and p.dtype == np.float32
+            assert np.abs(p - wp[j]).max() <= BF16_TOL and abs(v - float(wv[j, 0])) <= BF16_TOL
+    print(f"   reference ChessModelAPI from {src}: 128 requests answered by the CUDA evaluator")
+    model.model.close()
+
+
+@pytest.mark.parametrize("transport", ["shm"])
+def test_shm_transport_on_the_real_evaluator(net, transport):
+    """create_pipe() clients over the shared-memory transport (shm_pipes.py), real evaluator behind the server."""
+    cfg, w, x, fens, (wp, wv) = net
+    model = caz.ChessModel(caz.Config("mini"), precision="bf16", max_batch=64, transport=transport)
+    model._install(cfg, w)
+    pipes = model.get_pipes(24)
+    results = {}
+
+    def client(i, pipe):
+        out = []
+        for j in range(i, 240, 24):
+            pipe.send(x[j])
+            p, v = pipe.recv()
+            out.append((j, np.array(p, copy=True), v))
+        results[i] = out
+
+    ts = [threading.Thread(target=client, args=(i, p)) for i, p in enumerate(pipes)]
+    [t.start() for t in ts]
+    [t.join(timeout=60) for t in ts]
+    assert len(results) == 24 and model.api.positions == 240
+    for out in results.values():
+        for j, p, v in out:
+            assert isinstance(v, float) and p.shape == (1968,) and p.dtype == np.float32
+            assert np.abs(p - wp[j]).max() <= BF16_TOL and abs(v - float(wv[j, 0])) <= BF16_TOL
+    model.api.stop()
+    model.model.close()
+
+
 def test_chessmodel_pipes_end_to_end(net, tmp_path):
     cfg, w, x, fens, (wp, wv) = net
     cpath, wpath = str(tmp_path / "model_best_config.json"), str(tmp_path / "model_best_weight.npz")

@@ -34,7 +34,7 @@ def test_selfplay_rounds_through_the_evaluator():
                 want_planes = np.stack([oenc.canon_input_planes(f) for f in fens])
                 assert planes.tobytes() == want_planes.tobytes()
             wp, wv = onet.forward_graph(cfg, w, planes)
-            assert np.abs(policy - wp).max() <= 2e-2 and np.abs(value - wv).max() <= 2.5e-2
+            assert np.abs(policy - wp).max() <= 2e-2 and np.abs(value - wv).max() <= 2e-2
             checked += 1
         s.apply(policy, value)
     st = s.stats()

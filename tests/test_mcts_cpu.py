@@ -258,3 +258,46 @@ def test_root_noise_is_dirichlet():
     from scipy import stats
     assert abs((x[:, 0] > 0.2).mean() - stats.beta.sf(0.2, alpha, (n - 1) * alpha)) < 2e-3
     assert not np.array_equal(mcts.dirichlet_draws(8, alpha, n, 4), x[:4])
+
+
+def test_double_collect_is_refused_and_the_search_goes_on():
+    """collect() twice without an apply() (a driver retrying after a failed evaluator call) must not spin: status 1,
+    nothing changes, and the original batch can still be applied."""
+    cfg = mcts.MctsConfig.normal(simulation_num_per_move=8, search_threads=4)
+    s = caz.SelfPlaySearch(2, cfg, seed=3, n_threads=4)
+    rec = s.collect().copy()
+    assert len(rec) == 2
+    before = s.stats()
+    with pytest.raises(RuntimeError):
+        s.collect()
+    assert s.stats() == before
+    s.apply(*_fake_net(rec))
+    _run(s, 30)
+    assert s.stats()["moves_played"] > 0
+    s.close()
+
+
+def test_one_simulation_per_move_is_rejected():
+    """With a single simulation only the root is expanded: there are no visit counts to choose a move from (the
+    reference would raise in np.random.choice)."""
+    with pytest.raises((RuntimeError, ValueError)):
+        caz.SelfPlaySearch(1, mcts.MctsConfig.normal(simulation_num_per_move=1), seed=1, n_threads=1)
+
+
+def test_adjudication_overrides_a_result_at_the_length_limit():
+    """self_play_buffer adjudicates by material whenever num_halfmoves >= max_game_length, even when the step itself
+    ended the game (self_play.py:127-133): a mate delivered on the last allowed ply is scored by material count."""
+    cfg = mcts.MctsConfig.normal(simulation_num_per_move=300, noise_eps=0.0, tau_decay_rate=0.01, continuous=0,
+                                 resign_enabled=0, max_game_length=1)
+    s = caz.SelfPlaySearch(1, cfg, seed=2, n_threads=1)
+    s.set_position(0, "6k1/5ppp/8/8/8/8/8/R5K1 w - - 0 1")      # Ra8 mates, but black has 3 pawns for the rook: 5 vs 3
+    uniform = lambda k: (np.full((k, labels.N_LABELS), 1.0 / labels.N_LABELS, np.float32), np.zeros(k, np.float32))  # noqa: E731
+    for _ in range(200):
+        rec = s.collect()
+        if len(rec) == 0:
+            break
+        s.apply(*uniform(len(rec)))
+    st = s.stats()
+    assert st["games_finished"] == 1 and st["adjudications"] == 1 and s.fen(0).startswith("R5k1/")
+    assert s.result(0) == "1-0"                                   # tanh(3 * (5 + 3 - 3 - 3) / (5 + 3 + 3 + 3)) > 0.01
+    s.close()
