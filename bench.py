@@ -9,12 +9,19 @@ architecture; there are no trained weights or datasets offline).  One process pe
 RANK/LOCAL_RANK/WORLD_SIZE); games/positions are independent, so ranks share nothing on the data path
 (weak scaling, no collective); torch.distributed is used only for the barrier and the max-over-ranks time.
 
+The K-step loop is repeated back to back (no synchronisation in between) until the timed region lasts --min-seconds
+(default 1 s): `steps` is K as asked, `repetitions` says how often it ran, `value` is over the whole region, so the
+number is a sustained one and is divided by the sustained peak.
+
 JSON keys beyond the base contract:
   value     device-resident throughput: inputs already in HBM, CUDA events on the evaluator's stream
   e2e       the same metric through the public API (Evaluator.predict_into == predict_on_batch semantics) with
             pinned HOST buffers: H2D of the planes and D2H of policy+value inside the timed region
-  roofline  the dominant kernel (3x3 implicit-GEMM conv): algorithmic FLOPs per launch / its mean launch time,
-            measured live with CUDA events around the tower stage of every timed step
+  roofline  the dominant kernel (tower_kernel: stem + all 3x3 implicit-GEMM convolutions + head 1x1 convolutions in one
+            launch; with CAZ_NO_TOWER=1 the per-layer conv kernel): algorithmic FLOPs per launch / its mean launch time,
+            measured live with CUDA events around the tower stage of every timed step; frac_burst / frac_sustained
+  small_batch  roofline block of the batch-16 persistent kernel: algorithmic bytes, L2->SM bytes, latency
+  selfplay  BASELINE configs[2] (N=1) / configs[3] (N>1, games sharded by rank, summed over ranks)
   cpu_baseline  the oracle (torch-CPU restatement of the Keras graph) on this box's host cores, bounded sample
 """
 import argparse
@@ -47,22 +54,18 @@ def conv3x3_flops_per_launch(batch, filters=256):
     return 2 * 64 * batch * filters * 9 * filters
 
 
-def ncu_traffic_bytes(batch):
-    """dram__bytes_read.sum + dram__bytes_write.sum per tower-conv launch from the committed ncu launch list
-    (profiles/r1_v11_launches.csv, batch 4096; mean over the conv1-type and conv2-type launches), else None."""
-    path = os.path.join(ROOT, "profiles", "r1_v11_launches.csv")
-    if not os.path.exists(path):
-        path = os.path.join(ROOT, "profiles", "r1_v6_launches.csv")
-    if batch != 4096 or not os.path.exists(path):
-        return None
-    import csv
-    per = {}
-    for row in csv.DictReader(l for l in open(path) if l.startswith('"')):
-        if "conv_tc" in row["Kernel Name"] and row["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[row["Metric Unit"]]
-            per[row["ID"]] = per.get(row["ID"], 0.0) + float(row["Metric Value"].replace(",", "")) * scale
-    vals = [v for v in per.values() if v > 150e6]     # tower launches (the stem and dense launches move less)
-    return sum(vals) / len(vals) if vals else None
+def ncu_facts():
+    """Numbers that only Nsight Compute can give (DRAM bytes per launch of the dominant kernel, L2->SM bytes per pass of
+    the small-batch kernel), copied by hand from the newest capture under profiles/ into profiles/roofline_traffic.json
+    together with the name of that capture."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
+def tower_flops_per_launch(batch, blocks=7, filters=256, stem_k=5, planes=18, pf=2, vf=4):
+    """Algorithmic FLOPs of ONE tower_kernel launch: stem + 2*blocks 3x3 convolutions + the heads' 1x1 convolutions."""
+    macs = planes * stem_k * stem_k * filters * 64 + 2 * blocks * filters * 9 * filters * 64 + filters * (pf + vf) * 64
+    return 2 * macs * batch
 
 
 def measured_peaks():
@@ -187,6 +190,16 @@ def max_over_ranks(x, world):
     return float(t.item())
 
 
+def sum_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
 def barrier(world):
     if world > 1:
         import torch.distributed as dist
@@ -223,7 +236,14 @@ def run_reference(args, world, rank):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg, weights = network(args.blocks)
-    sample_n = 256
+    # the full batch per step if the whole run then ends within ~2.5 minutes on this box, else the largest multiple of 256
+    probe = synthetic_batch_oracle(256, seed=11)
+    onet.forward_graph(cfg, weights, probe[:64])
+    t0 = time.perf_counter()
+    onet.forward_graph(cfg, weights, probe)
+    rate = 256 / (time.perf_counter() - t0)
+    budget = 150.0 * rate / max(1, args.steps + args.warmup)
+    sample_n = int(min(args.batch, max(256, budget // 256 * 256)))
     planes = synthetic_batch_oracle(sample_n, seed=11)
     for _ in range(args.warmup):
         onet.forward_graph(cfg, weights, planes)
@@ -238,8 +258,12 @@ def run_reference(args, world, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"7x256 policy/value net, 5x5 stem, batch {args.batch} (sampled {sample_n}/step)",
-                   "res_blocks": args.blocks, "sample_positions_per_step": sample_n},
+        "config": {"workload": f"{args.blocks}x256 policy/value net, 5x5 stem, batch {args.batch} per GPU "
+                               f"(BASELINE.json configs[{1 if args.blocks == 7 else 4}])",
+                   "res_blocks": args.blocks, "batch_per_gpu": args.batch, "positions_per_step": sample_n,
+                   "note": "CPU arm: one process on rank 0, all host threads" +
+                           ("" if sample_n == args.batch else f"; {sample_n} of the {args.batch} positions per step "
+                            "(bounded sample: positions/s does not depend on the batch at this size)")},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -298,11 +322,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="positions per GPU per step")
     ap.add_argument("--blocks", type=int, default=7, help="residual blocks (19 = config 5)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16_pure", "fp16", "fp32"])
+    ap.add_argument("--min-seconds", type=float, default=1.0,
+                    help="repeat the K-step loop back to back until the timed region is at least this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--selfplay-seconds", type=float, default=8.0,
-                    help="BASELINE configs[2]: seconds of 256-game / 800-sim self-play through this evaluator (0 = skip; N=1 only)")
+                    help="BASELINE configs[2] / [3]: seconds of 256-game / 800-sim self-play per GPU through this evaluator "
+                         "(0 = skip; N>1: every rank plays its own games, sims/s summed over ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -336,6 +363,15 @@ def main():
     for i in range(args.warmup):
         step(i)
     ev.sync()
+    # how often the K-step loop must repeat for the timed region to last --min-seconds (the same count on every rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(3):
+        step(i)
+    e1.record(stream)
+    e1.synchronize()
+    est_step_s = max_over_ranks(e0.elapsed_time(e1) * 1e-3 / 3, world)
+    reps = max(1, int(np.ceil(args.min_seconds / max(est_step_s * args.steps, 1e-9))))
     ev.profile(True)
     ev.profile_read(reset=True)
     sampler = ClockSampler(local)
@@ -345,13 +381,14 @@ def main():
     barrier(world)
     torch.cuda.synchronize()
     launches0 = ev.kernel_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
     t_wall0 = time.perf_counter()
-    e0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    e1.record(stream)
-    e1.synchronize()
+    marks[0].record(stream)
+    for r in range(reps):
+        for i in range(args.steps):
+            step(r * args.steps + i)
+        marks[r + 1].record(stream)
+    marks[-1].synchronize()
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()
     barrier(world)
@@ -359,8 +396,10 @@ def main():
     stages = ev.profile_read(reset=True)
     ev.profile(False)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    dev_s = max_over_ranks(e0.elapsed_time(e1) * 1e-3, world)
-    value = world * B * args.steps / dev_s
+    timed_steps = reps * args.steps
+    dev_s = max_over_ranks(marks[0].elapsed_time(marks[-1]) * 1e-3, world)
+    first_rep_s = max_over_ranks(marks[0].elapsed_time(marks[1]) * 1e-3, world)
+    value = world * B * timed_steps / dev_s
 
     # ---- e2e: host buffers in, host buffers out, through the public API -----------------------------
     # Two batches in flight (Evaluator.submit / collect = caz_submit / caz_collect): every step's planes are copied
@@ -390,7 +429,7 @@ def main():
     e2e_loop(4)
     barrier(world)
     t0 = time.perf_counter()
-    loss_like = e2e_loop(args.steps)
+    loss_like = e2e_loop(timed_steps)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
     barrier(world)
     # the plain synchronous call, for comparison (what ChessModelAPI's worker thread does per batch)
@@ -399,50 +438,106 @@ def main():
     for _ in range(max(args.steps // 4, 5)):
         ev.predict_into(px.array, pp.array, pv.array)
     sync_s = (time.perf_counter() - t0) / max(args.steps // 4, 5)
-    e2e = {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 18 * 64 * 4,
-           "d2h_bytes_per_step": B * (ev.n_labels + 1) * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
+    e2e = {"value": world * B * timed_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 18 * 64 * 4,
+           "d2h_bytes_per_step": B * (ev.n_labels + 1) * 4, "ms_per_step": 1e3 * e2e_s / timed_steps,
+           "steps_timed": timed_steps,
            "api": "Evaluator.submit/collect (caz_submit/caz_collect: predict_on_batch semantics, pinned host buffers, "
                   "two batches in flight)", "sync_call_positions_per_s": B / sync_s,
            "sync_call_api": "Evaluator.predict_into (caz_eval), one batch at a time", "checksum": loss_like}
 
+    selfplay = None
+    if args.selfplay_seconds > 0 and args.batch >= 2048:
+        # configs[2] (one GPU) / configs[3] (N GPUs: every rank plays its own 256 games on its own evaluator, no collective):
+        # the host-side batched search (include/caz_mcts.h) feeding caz_submit_records, game groups alternating
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import selfplay_bench
+        barrier(world)
+        mine = selfplay_bench.run(ev, games=256, sims=800, search_threads=16, seconds=args.selfplay_seconds, groups=0 if world > 1 else 2,
+                                  rank=rank, world=world, seed=1 + rank,
+                                  label=f"{args.blocks}x256 net ({args.precision}), random-init weights")
+        if world == 1:
+            selfplay = mine
+        else:
+            slowest = max_over_ranks(mine["seconds"], world)
+            selfplay = {"workload": mine["workload"] + f", per GPU x {world} GPUs (games sharded by rank, no collective)",
+                        "n_gpus": world, "seconds": slowest,
+                        "sims_per_s": sum_over_ranks(mine["sims_per_s"] * mine["seconds"], world) / slowest,
+                        "positions_per_s_through_evaluator":
+                            sum_over_ranks(mine["positions_per_s_through_evaluator"] * mine["seconds"], world) / slowest,
+                        "evaluator_occupancy_min": -max_over_ranks(-mine["evaluator_occupancy"], world),
+                        "evaluator_occupancy_mean": sum_over_ranks(mine["evaluator_occupancy"], world) / world,
+                        "moves_played": int(sum_over_ranks(mine["moves_played"], world)),
+                        "games_per_hour_at_80_moves": sum_over_ranks(mine["games_per_hour_at_80_moves"], world),
+                        "groups": mine["groups"], "host_threads_per_group": mine["host_threads_per_group"],
+                        "host_cores": mine["host_cores"], "rank0": mine}
     if rank != 0:
         return
     peaks = measured_peaks()
     tower = stages["tower"]
-    n_conv = max(tower["launches"], 1)
-    conv_ms = tower["ms"] / n_conv
-    achieved = conv3x3_flops_per_launch(B) / (conv_ms * 1e-3) / 1e12
-    peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (3x3x256->256 implicit GEMM)", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(B),
-                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step); "
-                               f"burst peak {peaks['bf16_tflops']}",
-                "flops_per_launch": conv3x3_flops_per_launch(B), "mean_launch_ms": conv_ms, "launches_timed": n_conv,
+    n_launch = max(tower["launches"], 1)
+    fused = tower["launches"] <= timed_steps          # one tower_kernel launch per step (stem inside it)
+    launch_ms = tower["ms"] / n_launch
+    flops_launch = tower_flops_per_launch(B, args.blocks) if fused else conv3x3_flops_per_launch(B)
+    achieved = flops_launch / (launch_ms * 1e-3) / 1e12
+    burst, sustained = peaks["bf16_tflops"], peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+    long_region = dev_s >= 1.0                        # a seconds-long region runs under the power cap: sustained peak
+    peak = sustained if long_region else burst
+    facts = ncu_facts()
+    traffic = facts.get("tower_kernel" if fused else "conv_tc2_kernel", {})
+    roofline = {"bound": "tensor",
+                "kernel": "tower_kernel (stem + all 3x3x256->256 implicit-GEMM convolutions + head 1x1 convolutions, one launch)"
+                          if fused else "conv_tc2_kernel (one 3x3x256->256 implicit-GEMM convolution per launch)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "frac_burst": achieved / burst, "frac_sustained": achieved / sustained,
+                "peak_source": f"{peaks['source']}: {'bf16_tflops_sustained' if long_region else 'bf16_tflops (burst)'} because the "
+                               f"timed region lasted {dev_s:.2f} s; burst {burst}, sustained {sustained}",
+                "traffic": traffic.get("dram_bytes_per_launch") if traffic.get("batch") == B and traffic.get("blocks", 7) == args.blocks else None,
+                "traffic_source": traffic.get("source"),
+                "flops_per_launch": flops_launch, "mean_launch_ms": launch_ms, "launches_timed": n_launch,
                 "whole_net_tflops": flops_per_position(args.blocks) * value / world / 1e12,
                 "whole_net_frac_of_peak": flops_per_position(args.blocks) * value / world / 1e12 / peak,
-                "stage_ms_per_step": {k: v["ms"] / args.steps for k, v in stages.items()}}
+                "whole_net_frac_burst": flops_per_position(args.blocks) * value / world / 1e12 / burst,
+                "stage_ms_per_step": {k: v["ms"] / timed_steps for k, v in stages.items()}}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
+        "ms_per_step": 1e3 * dev_s / timed_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "repetitions": reps, "timed_steps": timed_steps, "timed_region_s": dev_s,
+        "first_repetition": {"steps": args.steps, "ms_per_step": 1e3 * first_rep_s / args.steps,
+                             "value": world * B * args.steps / first_rep_s},
+        "dtype": {"bf16": "bf16", "bf16_pure": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": {"workload": f"{args.blocks}x256 policy/value net, 5x5 stem, batch {B} per GPU "
                                f"(BASELINE.json configs[{1 if args.blocks == 7 else 4}])",
                    "res_blocks": args.blocks, "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"replicas x{world}, positions sharded, no collective",
                    "weights": "random-init (Keras default initialisers), seeded",
+                   "operands": {"bf16": "weights bf16, activation operand copies fp16 (saturating), fp32 accumulation in TMEM, "
+                                        "fp32 residual stream and heads", "bf16_pure": "weights and activation operands bf16",
+                                "fp16": "weights and activation operands fp16", "fp32": "fp32 CUDA cores"}[args.precision],
+                   "timed_region": f"{reps} back-to-back repetitions of the {args.steps}-step loop = {timed_steps} steps, "
+                                   f"{dev_s:.2f} s (--min-seconds {args.min_seconds})",
                    "l2": f"inputs rotate over {NBUF} device batches; a step streams ~{1.9e-3 * B:.1f} GB of "
                          "activations through HBM (>> 126 MB L2); the 17.4 MB weight set is meant to stay L2-resident"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "flops_per_position": flops_per_position(args.blocks), "host_cores": os.cpu_count(),
     }
     if not args.no_latency and world == 1:
-        out["latency_b16"] = latency_probe(ev, host_batches[0][:16].copy())
-    if args.selfplay_seconds > 0 and world == 1 and args.batch >= 2048:
-        # configs[2]: the host-side batched search (include/caz_mcts.h) feeding caz_eval_records, two half-groups alternating
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
-        import selfplay_bench
-        out["selfplay"] = selfplay_bench.run(ev, games=256, sims=800, search_threads=16, seconds=args.selfplay_seconds, groups=2,
-                                             label=f"{args.blocks}x256 net ({args.precision}), random-init weights")
+        lat = latency_probe(ev, host_batches[0][:16].copy())
+        out["latency_b16"] = lat
+        # roofline block of the batch-16 persistent kernel: what it must read per pass (the folded weights, L2-resident,
+        # plus 12.5 KB per position in and out) against the time the device takes; L2->SM bytes from the newest ncu capture
+        alg = ev.weight_bytes + 16 * (18 * 64 * 4 + (ev.n_labels + 1) * 4)
+        sb = facts.get("forward_sb_kernel", {})
+        out["small_batch"] = {"batch": 16, "kernel": "forward_sb_kernel<pair> (whole forward pass, one cooperative launch)",
+                              "bound": "latency chain over L2 (15 layers x [MMA phase at the shared-memory roofline + fence/flag/poll/TMA])",
+                              "algorithmic_bytes": alg, "device_p50_us": lat["device_p50_us"],
+                              "achieved_gbs": alg / (lat["device_p50_us"] * 1e-6) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
+                              "frac_of_hbm_peak": alg / (lat["device_p50_us"] * 1e-6) / 1e9 / peaks["hbm_gbs"],
+                              "l2_to_sm_bytes_per_pass": sb.get("l2_to_sm_bytes_per_pass"),
+                              "l2_to_sm_gbs": (sb["l2_to_sm_bytes_per_pass"] / (lat["device_p50_us"] * 1e-6) / 1e9)
+                              if sb.get("l2_to_sm_bytes_per_pass") else None,
+                              "dram_bytes_per_pass": sb.get("dram_bytes_per_pass"), "ncu_source": sb.get("source")}
+    if selfplay is not None:
+        out["selfplay"] = selfplay
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(cfg, weights, host_batches[0])
     print(json.dumps(out))

@@ -21,6 +21,7 @@
 #include "conv_sb.cuh"
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
+#include "conv_tower.cuh"
 #include "kernels_simt.cuh"
 
 namespace {
@@ -89,6 +90,11 @@ struct caz_handle {
   void* sb_w_stem = nullptr;   // stem weights padded to 64 input channels (small-batch kernel)
   void* w_tower = nullptr;   // [2*res_blocks][filters][9*filters] (tensor-core build)
   float* bias_all = nullptr; // [1 + 2*res_blocks][filters]
+  // whole tower in one persistent launch (conv_tower.cuh): every batch the small-batch kernel does not take
+  bool tw_ok = false;        // architecture fits it
+  bool tw_enabled = true;    // CAZ_NO_TOWER=1 keeps the per-layer launch chain (conv_tc2.cuh)
+  int tw_interleave = 0;     // CAZ_TOWER_INTERLEAVE=1|2 forces the groups per super-group (0 = by batch size)
+  CUtensorMap tw_tm_w_tower; // all tower layers' weights as one matrix, box 64 x filters / 2
   // small-batch persistent tower kernel (conv_sb.cuh)
   bool sb_ok = false;        // architecture fits it
   int sb_limit = -1;         // batches <= this use it; -1 = automatic
@@ -146,6 +152,7 @@ struct caz_handle {
   size_t puct_cap = 0;
   int64_t launches = 0;
   int64_t weight_bytes = 0;
+  int64_t inexact_weights = 0;   // bf16 build: bf16-valued weights the fp16 encoding could not hold exactly (see weight_bits)
   // profiling
   // one event set per forward pass while profiling; drained (without blocking the forward passes) on read
   struct EvSet { cudaEvent_t ev[CAZ_STAGES + 1]; int64_t launches[CAZ_STAGES]; };
@@ -188,11 +195,33 @@ int fail(caz_handle* h, int code, const std::string& msg) {
 int expected_tensor_count(const caz_arch& a) { return 5 + 10 * a.res_blocks + 7 + 9; }
 
 bool tensor_path(const caz_handle* h) { return h->precision != CAZ_PRECISION_FP32; }
-// 16-bit formats of the two tensor-core operands (include/caz_b200.h): the bf16 build keeps every WEIGHT in bf16 and writes
-// the 16-bit operand copies of the ACTIVATIONS as fp16 -- tcgen05.mma kind::f16 takes the A and B formats independently
+// 16-bit formats of the two tensor-core operands (include/caz_b200.h).  tcgen05.mma kind::f16 has separate A and B format
+// fields, but a launch with A = fp16 and B = bf16 dies with "an illegal instruction was encountered" on sm_100a (measured
+// in round 2): both operands must have the same format.  The bf16 build therefore hands its bf16-VALUED weights to the
+// tensor core in the fp16 encoding -- every bf16 value with 2^-17 <= |w| < 65504 is exactly representable in fp16 (8
+// significant bits, fp16 keeps 11 down to 2^-14 and 8 down to 2^-17) -- next to fp16 activation operands.
 bool act_fp16(const caz_handle* h) { return h->precision == CAZ_PRECISION_FP16 || h->precision == CAZ_PRECISION_BF16; }
-bool w_fp16(const caz_handle* h) { return h->precision == CAZ_PRECISION_FP16; }
+bool w_fp16(const caz_handle* h) { return act_fp16(h); }   // the encoding the tensor core reads
+bool w_bf16_grid(const caz_handle* h) { return h->precision == CAZ_PRECISION_BF16 || h->precision == CAZ_PRECISION_BF16_PURE; }
 int operand_fmt(const caz_handle* h) { return (act_fp16(h) ? caz::ptx::FMT_A_FP16 : 0) | (w_fp16(h) ? caz::ptx::FMT_B_FP16 : 0); }
+
+// One folded convolution weight -> the 16-bit word the tensor core reads.  *inexact counts bf16 values that the fp16
+// encoding cannot hold exactly (|w| < 2^-17 and not 0, or >= 65504; saturated / rounded to nearest then).
+uint16_t weight_bits(const caz_handle* h, float v, int64_t* inexact) {
+  uint16_t bits;
+  if (w_bf16_grid(h)) {
+    const __nv_bfloat16 bv = __float2bfloat16_rn(v);
+    if (!w_fp16(h)) { memcpy(&bits, &bv, 2); return bits; }
+    const float g = __bfloat162float(bv);
+    const __half hv = __float2half_rn(fminf(fmaxf(g, -65504.0f), 65504.0f));
+    if (__half2float(hv) != g && inexact) ++*inexact;
+    memcpy(&bits, &hv, 2);
+    return bits;
+  }
+  const __half hv = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+  memcpy(&bits, &hv, 2);
+  return bits;
+}
 
 // BatchNorm inference folded into the preceding bias-free convolution (Keras semantics,
 // model_chess.py:65-69): y = conv(x)*inv + (beta - mean*inv), inv = gamma / sqrt(var + eps).
@@ -250,6 +279,7 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
   std::vector<float> inv, shift;
   const int n_convs = 1 + 2 * a.res_blocks;
   const bool first_install = h->convs.empty();
+  h->inexact_weights = 0;
   if (first_install) {
     h->convs.resize(n_convs);
     const int scin_pad = h->in_cpad;
@@ -298,17 +328,11 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
       // W[oc][tap*cin_pad + ic] bf16, K-major rows: the B operand of the implicit GEMM
       // 16-bit words: bf16, or fp16 in the FP16 build (both have a +0.0 bit pattern of 0)
       std::vector<uint16_t> wp(ktot * F, 0);
-      const bool f16 = w_fp16(h);
       for (int tap = 0; tap < taps; ++tap)
         for (int ic = 0; ic < cin; ++ic) {
           const float* src = kt.data + ((size_t)tap * cin + ic) * F;
-          for (int oc = 0; oc < F; ++oc) {
-            const float v = src[oc] * inv[oc];
-            uint16_t bits;
-            if (f16) { const __half hv = __float2half_rn(v); memcpy(&bits, &hv, 2); }
-            else { const __nv_bfloat16 bv = __float2bfloat16_rn(v); memcpy(&bits, &bv, 2); }
-            wp[(size_t)oc * ktot + (size_t)tap * cin_pad + ic] = bits;
-          }
+          for (int oc = 0; oc < F; ++oc)
+            wp[(size_t)oc * ktot + (size_t)tap * cin_pad + ic] = weight_bits(h, src[oc] * inv[oc], &h->inexact_weights);
         }
       int rc = upload(h, L.w, wp.data(), wp.size() * 2);
       if (rc) return rc;
@@ -806,6 +830,68 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   return CAZ_OK;
 }
 
+// ---- whole tower in one launch (conv_tower.cuh) ---------------------------------------------------------
+int setup_tower(caz_handle* h) {
+  const caz_arch& a = h->arch;
+  h->tw_ok = false;
+  if (!tensor_path(h) || !h->use_2cta || a.block_kernel != 3 || a.filters % 64 != 0 || a.filters > 256) return CAZ_OK;
+  const int hw = 8 + a.stem_kernel - 1;
+  if (hw * 2 * hw * h->in_cpad * 2 > caz::tw::A_SLOT_BYTES) return CAZ_OK;   // the stem's halo tile must fit a ring slot
+  if (a.res_blocks > 0) {
+    const cuuint64_t kt = (cuuint64_t)9 * a.filters;
+    cuuint64_t dims[2] = {kt, (cuuint64_t)a.filters * 2 * a.res_blocks};
+    cuuint64_t str[1] = {kt * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)a.filters / 2};
+    int rc;
+    if ((rc = make_tmap(h, &h->tw_tm_w_tower, h->w_tower, 2, dims, str, box))) return rc;
+  } else {
+    h->tw_tm_w_tower = h->convs[0].tmap_w2;
+  }
+  CU_TRY(h, cudaFuncSetAttribute(caz::tw::tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tw::SMEM_BYTES));
+  h->tw_ok = true;
+  return CAZ_OK;
+}
+
+bool use_tower(const caz_handle* h, int batch) { return h->tw_ok && h->tw_enabled && batch >= 1; }
+
+int launch_tower(caz_handle* h, int batch) {
+  const caz_arch& a = h->arch;
+  caz::tw::TowerArgs args{};
+  args.batch = batch;
+  args.n_layers = 1 + 2 * a.res_blocks;
+  args.stem_k = a.stem_kernel;
+  args.stem_row_bytes = h->in_cpad * 2;
+  args.n = a.filters;
+  args.fmt = operand_fmt(h);
+  args.pdl = 0;
+  args.bias_all = h->bias_all;
+  args.xf = static_cast<float*>(h->act[2]);
+  args.act0 = static_cast<__nv_bfloat16*>(h->act[0]);
+  args.act1 = static_cast<__nv_bfloat16*>(h->act[1]);
+  args.head_w = h->head_w;
+  args.head_b = h->head_b;
+  args.featp = h->featp;
+  args.featv = h->featv;
+  args.pf = a.policy_filters;
+  args.vf = a.value_filters;
+  args.err_flag = h->err_flag_dev;
+  const int groups = ((batch + 1) / 2 + 1) / 2, max_pairs = h->num_sms / 2;
+  // Enough boards for every pair to hold two groups: interleave them (the epilogue of one runs under the other's MMAs).
+  // Fewer: one group per pair on as many pairs as there are groups -- an exposed epilogue costs less than an idle SM.
+  args.interleave = h->tw_interleave ? h->tw_interleave : (groups > max_pairs ? 2 : 1);
+  const int supers = (groups + args.interleave - 1) / args.interleave;
+  const int pairs = supers < max_pairs ? supers : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(caz::tw::THREADS);
+  cfg.dynamicSmemBytes = caz::tw::SMEM_BYTES;
+  cfg.stream = h->stream;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, caz::tw::tower_kernel, h->tmap_in, h->tmap_act[0], h->tmap_act[1], h->convs[0].tmap_w2,
+                                     h->tw_tm_w_tower, args);
+  if (e != cudaSuccess) return fail(h, CAZ_ERR_CUDA, fmt("launch of tower_kernel failed: %s", cudaGetErrorString(e)));
+  return check_launch(h, "tower_kernel");
+}
+
 // Picks the event set for this forward pass (no synchronisation).
 int prof_begin(caz_handle* h) {
   h->ev = nullptr;
@@ -959,7 +1045,12 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
   if (prof) { CU_TRY(h, cudaEventRecord(h->ev[1], h->stream)); h->pending_launches[0] = h->launches - l0; l0 = h->launches; }
   float* xf = static_cast<float*>(h->act[2]);  // tensor-core build: fp32 residual stream
   int cur_fp32 = 0;
-  {
+  if (tcp && use_tower(h, batch)) {
+    // stem + tower + the heads' 1x1 convolutions: one persistent launch, booked under the tower stage
+    if (prof) { CU_TRY(h, cudaEventRecord(h->ev[2], h->stream)); h->pending_launches[1] = 0; }
+    if ((rc = launch_tower(h, batch))) return rc;
+    if (prof) { CU_TRY(h, cudaEventRecord(h->ev[3], h->stream)); h->pending_launches[2] = h->launches - l0; l0 = h->launches; }
+  } else {
   // ---- stage 1: stem ----
   // tensor-core build: the LAST convolution's epilogue also computes the heads' 1x1 convs (no activation store)
   const bool stem_is_last = tcp && a.res_blocks == 0;
@@ -1133,7 +1224,9 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   h->in_cpad = tcp ? (a.input_planes <= 32 ? 32 : 64) : a.input_planes;
   CREATE_TRY(cudaMalloc(&h->in_act, cap * 64 * h->in_cpad * esz));
   for (int i = 0; i < 3; ++i) {
-    const size_t bytes = ((cap + 1) & ~size_t(1)) * 64 * a.filters * (i == 2 ? 4 : esz);
+    // a CTA pair covers four boards (two tiles): the fp32 stream of a pair's second tile is stored even when its boards do
+    // not exist, so the buffers hold whole groups of four
+    const size_t bytes = ((cap + 3) & ~size_t(3)) * 64 * a.filters * (i == 2 ? 4 : esz);
     CREATE_TRY(cudaMalloc(&h->act[i], bytes));
     // rows of boards past the batch are read (never used) by tiles that hold two boards: keep them finite
     CREATE_TRY(cudaMemset(h->act[i], 0, bytes));
@@ -1171,6 +1264,8 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
     CREATE_TRY(cudaFuncSetAttribute(caz::tc2::conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc2::SMEM_BYTES));
     if (const char* e = getenv("CAZ_CONV_2CTA")) h->use_2cta = atoi(e) != 0;
     if (getenv("CAZ_NO_PDL")) h->pdl = false;
+    if (getenv("CAZ_NO_TOWER")) h->tw_enabled = false;
+    if (const char* e = getenv("CAZ_TOWER_INTERLEAVE")) h->tw_interleave = atoi(e) == 2 ? 2 : (atoi(e) == 1 ? 1 : 0);
     if (getenv("CAZ_NO_SPLIT_N")) h->split_n = false;
     if (const char* e = getenv("CAZ_L2_PREFETCH")) h->l2_prefetch = atoi(e) != 0;
     if (const char* e = getenv("CAZ_SNAKE")) h->snake = atoi(e) != 0;
@@ -1190,6 +1285,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
   }
 #undef CREATE_TRY
   if ((rc = install_weights(h, tensors, n_tensors))) return bail(rc);
+  if ((rc = setup_tower(h))) return bail(rc);
   if ((rc = setup_small_batch(h))) return bail(rc);
   *out = h;
   return CAZ_OK;
@@ -1539,11 +1635,20 @@ int caz_set_small_batch_limit(caz_handle* h, int32_t limit) {
   return CAZ_OK;
 }
 
+int caz_set_fused_tower(caz_handle* h, int32_t mode) {
+  if (!h) return CAZ_ERR_INVALID;
+  if (mode < -1 || mode > 2) return fail(h, CAZ_ERR_INVALID, "caz_set_fused_tower: mode must be -1, 0, 1 or 2");
+  h->tw_enabled = mode != 0;
+  h->tw_interleave = mode > 0 ? mode : 0;
+  return CAZ_OK;
+}
+
 int32_t caz_max_batch(const caz_handle* h) { return h ? h->max_batch : 0; }
 int32_t caz_precision(const caz_handle* h) { return h ? h->precision : -1; }
 void* caz_stream(const caz_handle* h) { return h ? static_cast<void*>(h->stream) : nullptr; }
 int64_t caz_kernel_launches(const caz_handle* h) { return h ? h->launches : 0; }
 int64_t caz_weight_bytes(const caz_handle* h) { return h ? h->weight_bytes : 0; }
+int64_t caz_inexact_weights(const caz_handle* h) { return h ? h->inexact_weights : 0; }
 
 int caz_profile(caz_handle* h, int32_t enable) {
   if (!h) return CAZ_ERR_INVALID;

@@ -153,6 +153,10 @@ class Evaluator:
         """Batches <= limit use the persistent small-batch tower kernel; -1 = automatic, 0 = never."""
         _lib.check(self._handle, self._lib.caz_set_small_batch_limit(self._handle, int(limit)))
 
+    def set_fused_tower(self, mode):
+        """-1: one persistent launch for stem + tower (default); 0: one launch per layer; 1 / 2: force the interleave."""
+        _lib.check(self._handle, self._lib.caz_set_fused_tower(self._handle, int(mode)))
+
     def sync(self):
         _lib.check(self._handle, self._lib.caz_sync(self._handle))
 
@@ -220,6 +224,11 @@ class Evaluator:
     @property
     def weight_bytes(self):
         return int(self._lib.caz_weight_bytes(self._handle))
+
+    @property
+    def inexact_weights(self):
+        """bf16 build: folded bf16 weights that the fp16 encoding read by the tensor core does not hold exactly."""
+        return int(self._lib.caz_inexact_weights(self._handle))
 
     def profile(self, enable=True):
         _lib.check(self._handle, self._lib.caz_profile(self._handle, 1 if enable else 0))

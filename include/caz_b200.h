@@ -36,11 +36,14 @@ extern "C" {
 #define CAZ_ERR_KERNEL 4      /* a kernel watchdog fired (pipeline never completed) */
 
 /* numeric builds (BASELINE.json north_star: "fp32-accumulate build" and "bf16 build") */
-#define CAZ_PRECISION_BF16 0  /* THE bf16 build: every weight bf16, fp32 TMEM accumulators, fp32 residual stream, fp32 heads.
-                                 The 16-bit operand COPIES of the activations (the A operand of tcgen05.mma) are written as
-                                 fp16, saturated to +-65504: kind::f16 takes the A and B formats independently at the same
-                                 rate, and activation rounding was two thirds of the value head's error variance
-                                 (profiles/r2_precision_ablation.md): max|dv| 0.8-0.95e-2 instead of 1.6-2.4e-2 */
+#define CAZ_PRECISION_BF16 0  /* THE bf16 build: every convolution weight is a bf16 VALUE (BN-folded in fp32, rounded to
+                                 bf16); fp32 TMEM accumulators, fp32 residual stream, fp32 heads.  The 16-bit operand COPIES
+                                 of the activations are fp16, saturated to +-65504: activation rounding was two thirds of
+                                 the value head's error variance with bf16 operands (profiles/r2_precision_ablation.md:
+                                 max|dv| 0.8-0.95e-2 instead of 1.6-2.4e-2).  tcgen05.mma kind::f16 refuses A = fp16 with
+                                 B = bf16 (illegal instruction on sm_100a, measured), so the bf16-valued weights are handed
+                                 over in the fp16 ENCODING, which holds every bf16 value with 2^-17 <= |w| < 65504 exactly;
+                                 caz_inexact_weights() counts the ones outside (rounded to nearest / saturated). */
 #define CAZ_PRECISION_FP32 1  /* fp32 operands and accumulation on the CUDA cores (1e-4 parity build)      */
 #define CAZ_PRECISION_FP16 2  /* the tensor-core build with fp16 weights AND activations: same kernels and throughput,
                                  8x finer operand rounding; weights below 6e-5 lose bits (fp16 subnormals)         */
@@ -181,12 +184,20 @@ int32_t caz_precision(const caz_handle* h);
 void* caz_stream(const caz_handle* h);            /* cudaStream_t the handle launches on */
 int64_t caz_kernel_launches(const caz_handle* h); /* kernels this handle has launched so far */
 int64_t caz_weight_bytes(const caz_handle* h);    /* folded device weight set, bytes */
+int64_t caz_inexact_weights(const caz_handle* h); /* bf16 build: folded bf16 weights not exactly representable in the fp16
+                                                     encoding the tensor core reads (0 for every network in the tests) */
 
 /* Batches of at most `limit` positions run the persistent small-batch tower kernel (one cooperative launch for
  * stem + all residual convs, weights streamed from L2); larger ones run one implicit-GEMM launch per layer.
  * limit < 0 restores the automatic choice, 0 disables the small-batch kernel.  Results are identical either way
  * up to fp32 summation order inside the MMA. */
 int caz_set_small_batch_limit(caz_handle* h, int32_t limit);
+
+/* Batches beyond the small-batch kernel run stem + tower + head convolutions as ONE persistent launch in which every
+ * CTA pair carries its own boards through all layers (mode 1 or 2 = boards groups per pair interleaved: forced; -1 =
+ * chosen by batch size, the default).  mode 0 selects the older chain of one implicit-GEMM launch per layer.  Results
+ * are bit-identical in every mode. */
+int caz_set_fused_tower(caz_handle* h, int32_t mode);
 
 /* Test hook: switch on per-layer clock64 stamps of CTA 0 of the small-batch kernel and/or read them back
  * (stamps: host int64 [n], 8 per layer: barrier passed, first A tile landed, last A tile landed, MMAs issued,

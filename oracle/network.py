@@ -216,6 +216,14 @@ def legal_masked_argmax(policy, masks):
     return p.argmax(axis=1)
 
 
+def decisive_rows(policy, masks, margin):
+    """Rows whose best legal move leads the second best by more than `margin`: where an argmax can be expected to survive
+    an error of margin / 2 per probability."""
+    p = np.where(masks != 0, policy, -1.0)
+    top2 = np.sort(p, axis=1)[:, -2:]
+    return (top2[:, 1] - top2[:, 0]) > margin
+
+
 def synthetic_legal_masks(n, n_labels=1968, seed=0):
     rng = np.random.RandomState(seed)
     masks = np.zeros((n, n_labels), dtype=np.uint8)
