@@ -93,7 +93,7 @@ struct caz_handle {
   // whole tower in one persistent launch (conv_tower.cuh): every batch the small-batch kernel does not take
   bool tw_ok = false;        // architecture fits it
   bool tw_enabled = true;    // CAZ_NO_TOWER=1 keeps the per-layer launch chain (conv_tc2.cuh)
-  int tw_interleave = 0;     // CAZ_TOWER_INTERLEAVE=1|2 forces the groups per super-group (0 = by batch size)
+  int tw_mode = 0;           // caz_set_fused_tower / CAZ_TOWER_MODE: 0 = by batch size, 1 / 2 = forced groups per pair
   CUtensorMap tw_tm_w_tower; // all tower layers' weights as one matrix, box 64 x filters / 2
   // small-batch persistent tower kernel (conv_sb.cuh)
   bool sb_ok = false;        // architecture fits it
@@ -135,6 +135,10 @@ struct caz_handle {
   // second staging slot + copy streams: caz_eval pipelines H2D / forward / D2H over chunks of a large batch
   float *d_planes2 = nullptr, *d_policy2 = nullptr, *d_value2 = nullptr;
   uint8_t *d_mask2 = nullptr, *d_records2 = nullptr;
+  // caz_submit_records_priors: CSR legal-move labels in, one float64 prior per legal move out (two staging slots)
+  int32_t* d_off[2] = {nullptr, nullptr};      // [cap + 1]
+  int32_t* d_lab[2] = {nullptr, nullptr};      // [cap * CAZ_MAX_MOVES]
+  double* d_pri[2] = {nullptr, nullptr};       // [cap * CAZ_MAX_MOVES]
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_in[2] = {}, ev_fwd[2] = {}, ev_out[2] = {};
   // caz_submit / caz_collect: tickets count up; ticket t completes on ev_done[t % TICKET_RING], its staging slot is t & 1
@@ -878,7 +882,9 @@ int launch_tower(caz_handle* h, int batch) {
   const int groups = ((batch + 1) / 2 + 1) / 2, max_pairs = h->num_sms / 2;
   // Enough boards for every pair to hold two groups: interleave them (the epilogue of one runs under the other's MMAs).
   // Fewer: one group per pair on as many pairs as there are groups -- an exposed epilogue costs less than an idle SM.
-  args.interleave = h->tw_interleave ? h->tw_interleave : (groups > max_pairs ? 2 : 1);
+  // (Cutting every layer of a lone group into two N tiles, first half drained and consumed while the second is computed,
+  // was built and measured in round 2: bit-identical, and not a microsecond faster -- 283.6 vs 286.1 us at 100 boards.)
+  args.interleave = h->tw_mode ? h->tw_mode : (groups > max_pairs ? 2 : 1);
   const int supers = (groups + args.interleave - 1) / args.interleave;
   const int pairs = supers < max_pairs ? supers : max_pairs;
   cudaLaunchConfig_t cfg = {};
@@ -1154,6 +1160,11 @@ void caz_destroy(caz_handle* h) {
                   h->d_mask, h->d_records, h->puct_buf, h->d_planes2, h->d_policy2, h->d_value2, h->d_mask2,
                   h->d_records2};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (h->d_off[i]) cudaFree(h->d_off[i]);
+    if (h->d_lab[i]) cudaFree(h->d_lab[i]);
+    if (h->d_pri[i]) cudaFree(h->d_pri[i]);
+  }
   if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
   for (auto& e : h->ev_done) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
@@ -1265,7 +1276,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
     if (const char* e = getenv("CAZ_CONV_2CTA")) h->use_2cta = atoi(e) != 0;
     if (getenv("CAZ_NO_PDL")) h->pdl = false;
     if (getenv("CAZ_NO_TOWER")) h->tw_enabled = false;
-    if (const char* e = getenv("CAZ_TOWER_INTERLEAVE")) h->tw_interleave = atoi(e) == 2 ? 2 : (atoi(e) == 1 ? 1 : 0);
+    if (const char* e = getenv("CAZ_TOWER_MODE")) h->tw_mode = atoi(e) >= 1 && atoi(e) <= 2 ? atoi(e) : 0;
     if (getenv("CAZ_NO_SPLIT_N")) h->split_n = false;
     if (const char* e = getenv("CAZ_L2_PREFETCH")) h->l2_prefetch = atoi(e) != 0;
     if (const char* e = getenv("CAZ_SNAKE")) h->snake = atoi(e) != 0;
@@ -1322,8 +1333,15 @@ int caz_eval_device(caz_handle* h, const float* d_planes, int32_t batch, float* 
 // One chunk (<= max_batch positions) through the three-stream pipeline: H2D on copy_in, forward on the compute
 // stream, D2H on copy_out, chained by events; `slot` picks one of the two staging buffer sets.  Nothing here blocks
 // the host.  Waiting on an event that was never recorded is a no-op, so first uses need no special case.
+struct PriorsRequest {   // caz_submit_records_priors: gather instead of the full-policy read-back
+  const int32_t* offsets;  // host [nb + 1]
+  const int32_t* labels;   // host [offsets[nb]]
+  double* priors;          // host [offsets[nb]] out
+};
+
 static int enqueue_pipelined(caz_handle* h, int slot, const float* planes, const uint8_t* records, int32_t nb,
-                             float* policy, float* value, const uint8_t* legal_mask, bool masked) {
+                             float* policy, float* value, const uint8_t* legal_mask, bool masked,
+                             const PriorsRequest* pr = nullptr) {
   const caz_arch& a = h->arch;
   const size_t pin = (size_t)a.input_planes * 64;
   float* dpl = slot ? h->d_planes2 : h->d_planes;
@@ -1337,14 +1355,35 @@ static int enqueue_pipelined(caz_handle* h, int slot, const float* planes, const
   if (planes) CU_TRY(h, cudaMemcpyAsync(dpl, planes, (size_t)nb * pin * 4, cudaMemcpyHostToDevice, h->copy_in));
   else CU_TRY(h, cudaMemcpyAsync(dre, records, (size_t)nb * CAZ_RECORD_BYTES, cudaMemcpyHostToDevice, h->copy_in));
   if (masked) CU_TRY(h, cudaMemcpyAsync(dma, legal_mask, (size_t)nb * a.n_labels, cudaMemcpyHostToDevice, h->copy_in));
+  const int32_t n_edges = pr ? pr->offsets[nb] : 0;
+  if (pr) {
+    if (!h->d_off[slot]) {   // first use: the staging for CSR labels and priors (11 MB per slot at 4096 boards)
+      const size_t cap = (size_t)h->max_batch;
+      CU_TRY(h, cudaMalloc(&h->d_off[slot], (cap + 1) * sizeof(int32_t)));
+      CU_TRY(h, cudaMalloc(&h->d_lab[slot], cap * CAZ_MAX_MOVES * sizeof(int32_t)));
+      CU_TRY(h, cudaMalloc(&h->d_pri[slot], cap * CAZ_MAX_MOVES * sizeof(double)));
+    }
+    CU_TRY(h, cudaMemcpyAsync(h->d_off[slot], pr->offsets, (size_t)(nb + 1) * 4, cudaMemcpyHostToDevice, h->copy_in));
+    if (n_edges > 0) CU_TRY(h, cudaMemcpyAsync(h->d_lab[slot], pr->labels, (size_t)n_edges * 4, cudaMemcpyHostToDevice, h->copy_in));
+  }
   CU_TRY(h, cudaEventRecord(h->ev_in[slot], h->copy_in));
   CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
   // ... and its outputs once the last D2H that drained them has finished
   CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_out[slot], 0));
   if ((rc = forward(h, planes ? dpl : nullptr, planes ? nullptr : dre, nb, dpo, dva, masked ? dma : nullptr))) return rc;
+  if (pr && n_edges > 0) {
+    // the prior push of select_action_q_and_u (player_chess.py:267-275) on the policy rows that never leave the device
+    const int wpb = 8;
+    caz::push_priors_kernel<<<(nb + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>(dpo, a.n_labels, h->d_off[slot], nb, h->d_lab[slot], h->d_pri[slot]);
+    if ((rc = check_launch(h, "push_priors_kernel"))) return rc;
+  }
   CU_TRY(h, cudaEventRecord(h->ev_fwd[slot], h->stream));
   CU_TRY(h, cudaStreamWaitEvent(h->copy_out, h->ev_fwd[slot], 0));
-  CU_TRY(h, cudaMemcpyAsync(policy, dpo, (size_t)nb * a.n_labels * 4, cudaMemcpyDeviceToHost, h->copy_out));
+  if (pr) {
+    if (n_edges > 0) CU_TRY(h, cudaMemcpyAsync(pr->priors, h->d_pri[slot], (size_t)n_edges * 8, cudaMemcpyDeviceToHost, h->copy_out));
+  } else {
+    CU_TRY(h, cudaMemcpyAsync(policy, dpo, (size_t)nb * a.n_labels * 4, cudaMemcpyDeviceToHost, h->copy_out));
+  }
   CU_TRY(h, cudaMemcpyAsync(value, dva, (size_t)nb * 4, cudaMemcpyDeviceToHost, h->copy_out));
   CU_TRY(h, cudaEventRecord(h->ev_out[slot], h->copy_out));
   return CAZ_OK;
@@ -1416,13 +1455,13 @@ static int eval_host(caz_handle* h, const float* planes, const uint8_t* records,
 
 // Common tail of the two submit entry points: claim the next ticket's ring entry, enqueue, record its completion event.
 static int submit_common(caz_handle* h, const float* planes, const uint8_t* records, int32_t batch, float* policy, float* value,
-                         const uint8_t* legal_mask, bool masked, int32_t* ticket) {
+                         const uint8_t* legal_mask, bool masked, int32_t* ticket, const PriorsRequest* pr = nullptr) {
   const int32_t t = h->next_ticket;
   const int entry = t % caz_handle::TICKET_RING;
   if (h->ticket_state[entry].load(std::memory_order_acquire) != 0)
     return fail(h, CAZ_ERR_INVALID, fmt("caz_submit: %d submissions are outstanding; caz_collect one first", caz_handle::TICKET_RING));
   int rc;
-  if ((rc = enqueue_pipelined(h, t & 1, planes, records, batch, policy, value, legal_mask, masked))) return rc;
+  if ((rc = enqueue_pipelined(h, t & 1, planes, records, batch, policy, value, legal_mask, masked, pr))) return rc;
   CU_TRY(h, cudaEventRecord(h->ev_done[entry], h->copy_out));
   h->ticket_state[entry].store(1, std::memory_order_release);
   h->next_ticket = t + 1 == (1 << 30) ? 0 : t + 1;   // wraps at a multiple of the ring size
@@ -1453,6 +1492,20 @@ int caz_submit_records(caz_handle* h, const uint8_t* records, int32_t batch, flo
   int rc;
   if ((rc = set_device(h))) return rc;
   return submit_common(h, nullptr, records, batch, policy, value, legal_mask, masked, ticket);
+}
+
+int caz_submit_records_priors(caz_handle* h, const uint8_t* records, int32_t batch, const int32_t* offsets, const int32_t* labels,
+                              double* priors, float* value, int32_t* ticket) {
+  if (!h) return CAZ_ERR_INVALID;
+  if (!records || !offsets || !labels || !priors || !value || !ticket || batch < 1 || batch > h->max_batch)
+    return fail(h, CAZ_ERR_INVALID, fmt("caz_submit_records_priors: bad argument (batch %d, max_batch %d)", batch, h->max_batch));
+  if (h->arch.input_planes != CAZ_PLANES) return fail(h, CAZ_ERR_INVALID, "board records need an 18-plane network");
+  if (offsets[0] != 0 || offsets[batch] < 0 || (int64_t)offsets[batch] > (int64_t)h->max_batch * CAZ_MAX_MOVES)
+    return fail(h, CAZ_ERR_INVALID, "caz_submit_records_priors: offsets must start at 0 and hold at most max_batch * CAZ_MAX_MOVES edges");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  const PriorsRequest pr{offsets, labels, priors};
+  return submit_common(h, nullptr, records, batch, nullptr, value, nullptr, false, ticket, &pr);
 }
 
 int caz_collect(caz_handle* h, int32_t ticket) {
@@ -1639,7 +1692,7 @@ int caz_set_fused_tower(caz_handle* h, int32_t mode) {
   if (!h) return CAZ_ERR_INVALID;
   if (mode < -1 || mode > 2) return fail(h, CAZ_ERR_INVALID, "caz_set_fused_tower: mode must be -1, 0, 1 or 2");
   h->tw_enabled = mode != 0;
-  h->tw_interleave = mode > 0 ? mode : 0;
+  h->tw_mode = mode > 0 ? mode : 0;
   return CAZ_OK;
 }
 

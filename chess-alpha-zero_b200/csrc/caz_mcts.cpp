@@ -72,6 +72,29 @@ int caz_mcts_collect(caz_mcts* m, uint8_t* records, int32_t capacity, int32_t* n
   return rc;
 }
 
+int caz_mcts_collect_csr(caz_mcts* m, uint8_t* records, int32_t capacity, int32_t* n_leaves, int32_t* offsets, int32_t* labels,
+                         int32_t edge_capacity) {
+  if (!m || !records || !n_leaves || !offsets || !labels) return 1;
+  int n = 0;
+  int rc;
+  try {
+    rc = m->impl->collect(records, capacity, &n, offsets, labels, edge_capacity);
+  } catch (...) {
+    rc = 2;
+  }
+  *n_leaves = n;
+  return rc;
+}
+
+int caz_mcts_apply_priors(caz_mcts* m, const double* priors, const float* value, int32_t n) {
+  if (!m || (n > 0 && (!priors || !value))) return 1;
+  try {
+    return m->impl->apply_priors(priors, value, n);
+  } catch (...) {
+    return 2;
+  }
+}
+
 int caz_mcts_apply(caz_mcts* m, const float* policy, const float* value, int32_t n) {
   if (!m || (n > 0 && (!policy || !value))) return 1;
   try {

@@ -54,6 +54,8 @@ struct MctsStats {
   int64_t white_wins, black_wins, draws, resignations, adjudications, tree_nodes_last;
 };
 
+constexpr int MAX_MOVES = 256;   // bound on the legal moves of a position (218 is the known maximum)
+
 struct Edge {
   Move move;
   int32_t label;   // index into the policy vector the network returned for this node (flip already applied)
@@ -285,6 +287,7 @@ class Mcts {
   int n_threads = 1;
   MctsStats stats{};
   std::vector<std::pair<int32_t, int32_t>> batch_map;   // leaf i of the last collect -> (game, request)
+  std::vector<int32_t> batch_edge_offsets;               // CSR offsets of the leaves' edges, same order
 
   Mcts(const MctsConfig& c, int n_games, uint64_t seed, const int32_t* labels, const int32_t* unflip, int threads)
       : cfg(c), games(n_games), move_label(labels, labels + 64 * 64 * 5), unflipped_index(unflip, unflip + c.n_labels),
@@ -462,8 +465,12 @@ class Mcts {
   // Call order is collect -> apply -> collect ...: a second collect() while leaves of the first are still waiting for their
   // apply() returns 1 and changes nothing (collect_game would forget the requests but not the pending nodes, and every
   // later descent would be withdrawn for ever).
-  int collect(uint8_t* records, int capacity, int* n_out) {
+  // With `offsets` / `labels` (CSR: offsets[n + 1], labels[offsets[n]]) the leaves' legal-move labels are written too, in
+  // edge order: what caz_submit_records_priors needs to send back one prior per legal move instead of the whole policy.
+  int collect(uint8_t* records, int capacity, int* n_out, int32_t* offsets = nullptr, int32_t* labels = nullptr,
+              int edge_capacity = 0) {
     if (static_cast<int64_t>(games.size()) * cfg.search_threads > capacity) return 1;
+    if (offsets && (!labels || static_cast<int64_t>(games.size()) * cfg.search_threads * MAX_MOVES > edge_capacity)) return 1;
     if (!batch_map.empty()) return 1;
     for (const auto& gs : games)
       if (gs.inflight > 0) return 1;
@@ -487,7 +494,23 @@ class Mcts {
         }
       }
       *n_out = n;
-      if (n > 0) return 0;
+      if (n > 0) {
+        batch_edge_offsets.assign(1, 0);
+        for (const auto& bm : batch_map) {
+          const GameSearch& gs = games[bm.first];
+          batch_edge_offsets.push_back(batch_edge_offsets.back() + gs.nodes[gs.requests[bm.second].node].n_edges);
+        }
+        if (offsets) {
+          std::memcpy(offsets, batch_edge_offsets.data(), batch_edge_offsets.size() * sizeof(int32_t));
+          int k = 0;
+          for (const auto& bm : batch_map) {
+            const GameSearch& gs = games[bm.first];
+            const Node& nd = gs.nodes[gs.requests[bm.second].node];
+            for (int e = 0; e < nd.n_edges; ++e) labels[k++] = gs.edges[nd.first_edge + e].label;
+          }
+        }
+        return 0;
+      }
       // nothing to evaluate (every descent ended in a terminal position): finish what can be finished and go on
       bool any_active = false;
       for (auto& gs : games) any_active |= !gs.finished;
@@ -500,6 +523,32 @@ class Mcts {
   // policy: [n][n_labels] network output for the leaves of the last collect (canonical, side to move = white);
   // value: [n].  Expands, backs up, plays the moves of the games whose search is complete.
   int apply(const float* policy, const float* value, int n) {
+    return apply_impl(n, value, [&](int i, GameSearch& gs, Node& nd) {
+      const float* pol = policy + static_cast<size_t>(i) * cfg.n_labels;
+      // push p to edges (player_chess.py:267-275): p = P[label] / (1e-8 + sum of the legal moves' P, in move order)
+      double tot = 1e-8;
+      for (int e = 0; e < nd.n_edges; ++e) {
+        Edge& ed = gs.edges[nd.first_edge + e];
+        const float pe = ed.label >= 0 ? pol[ed.label] : 0.0f;
+        ed.p = static_cast<double>(pe);
+        tot += static_cast<double>(pe);
+      }
+      for (int e = 0; e < nd.n_edges; ++e) gs.edges[nd.first_edge + e].p /= tot;
+    });
+  }
+
+  // The same with the prior push already done on the device (caz_submit_records_priors / push_priors_kernel: the same
+  // float32 -> float64 arithmetic in the same order, bit-identical): priors[offsets[i] + e] belongs to edge e of leaf i.
+  int apply_priors(const double* priors, const float* value, int n) {
+    if (static_cast<int>(batch_edge_offsets.size()) != n + 1) return 1;
+    return apply_impl(n, value, [&](int i, GameSearch& gs, Node& nd) {
+      const double* pr = priors + batch_edge_offsets[i];
+      for (int e = 0; e < nd.n_edges; ++e) gs.edges[nd.first_edge + e].p = pr[e];
+    });
+  }
+
+  template <class PushPriors>
+  int apply_impl(int n, const float* value, PushPriors&& push) {
     if (n != static_cast<int>(batch_map.size())) return 1;
     std::vector<int> first(games.size() + 1, 0);
     for (auto& bm : batch_map) ++first[bm.first + 1];
@@ -508,18 +557,9 @@ class Mcts {
       GameSearch& gs = games[g];
       for (size_t r = 0; r < gs.requests.size(); ++r) {
         const int i = first[g] + static_cast<int>(r);
-        const float* pol = policy + static_cast<size_t>(i) * cfg.n_labels;
         const Request& rq = gs.requests[r];
         Node& nd = gs.nodes[rq.node];
-        // push p to edges (player_chess.py:267-275): p = P[label] / (1e-8 + sum of the legal moves' P, in move order)
-        double tot = 1e-8;
-        for (int e = 0; e < nd.n_edges; ++e) {
-          Edge& ed = gs.edges[nd.first_edge + e];
-          const float pe = ed.label >= 0 ? pol[ed.label] : 0.0f;
-          ed.p = static_cast<double>(pe);
-          tot += static_cast<double>(pe);
-        }
-        for (int e = 0; e < nd.n_edges; ++e) gs.edges[nd.first_edge + e].p /= tot;
+        push(i, gs, nd);
         nd.pending = false;
         --gs.inflight;
         ++st.leaves_evaluated;

@@ -127,7 +127,10 @@ __device__ __forceinline__ size_t xf_index(int tile, int chunks, int chunk, int 
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* smem_epi, const float* s_bias,
                                               const float* s_head, int quad, int lane, int n0, uint32_t taddr,
                                               uint64_t* full_bar, uint32_t full_phase, uint64_t* empty_bar,
-                                              uint32_t release_rank, int nt = 0, int next_n0 = -1) {
+                                              uint32_t release_rank, int nt = 0, int next_n0 = -1, int n0_store = -1) {
+  // n0_store: first board of the tile in the ACTIVATION buffers when they are addressed by something else than the board
+  // number (the one-launch tower keeps them in a compact per-CTA scratch, conv_tower.cuh); -1 = n0
+  if (n0_store < 0) n0_store = n0;
   uint4* stage_b = reinterpret_cast<uint4*>(smem_epi + quad * EPI_WARP_BYTES);
   float4* stage_f = reinterpret_cast<float4*>(stage_b);
   const int fr = lane >> 3, fq = lane & 7;   // fp32 transposed mapping: row i*4+fr, float4 column fq
@@ -136,12 +139,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
   const int boards_live = left >= 2 ? 2 : (left > 0 ? left : 0);
   // global (NHWC) row of local row r, and whether its board exists
   auto grow = [&](int r) -> long {
-    return (static_cast<long>(n0 + ((r >> 3) & 1)) << 6) + ((2 * quad + (r >> 4)) << 3) + (r & 7);
+    return (static_cast<long>(n0_store + ((r >> 3) & 1)) << 6) + ((2 * quad + (r >> 4)) << 3) + (r & 7);
   };
   auto live = [&](int r) -> bool { return ((r >> 3) & 1) < boards_live; };
   // (two N tiles per board group, nt = 0 / 1: this epilogue owns 32-column chunks [chunk0, chunk0 + n / 32) of the row's
   // n_total / 32; the residual stream and the 16-bit operand keep their full-width layouts)
-  const int tile = n0 >> 1, chunks = (args.n_tiles > 1 ? args.n_total : args.n) >> 5, chunk0 = nt * (args.n >> 5);
+  const int tile = n0_store >> 1, chunks = (args.n_tiles > 1 ? args.n_total : args.n) >> 5, chunk0 = nt * (args.n >> 5);
   const int m = quad * 32 + lane, opitch = args.n_tiles > 1 ? args.n_total : args.n;
   const float4* res4 = reinterpret_cast<const float4*>(args.residual);
   float4* out4 = reinterpret_cast<float4*>(args.out_f32);

@@ -147,6 +147,11 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
     if (warp != 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // weights are constants; everything else waits
   }
 
+  // Intermediate activations (act0, act1, the fp32 stream) are SCRATCH: written and read back by the same CTA, dead after the
+  // last layer.  They are addressed by (pair, group slot, rank) instead of the board number, so that every round of
+  // super-groups rewrites the same <= 148 x 2 tiles (76 MB with the fp32 stream: L2-sized) instead of walking through
+  // batch-sized buffers whose dead lines the L2 would have to write back to HBM.
+  auto scratch_tile = [&](int g) -> int { return 2 * (G * pair0 + g) + static_cast<int>(rank); };
   // number of groups of super-group s that exist (1 or 2)
   auto groups_in = [&](int s) -> int { return G * s + G <= num_groups ? G : num_groups - G * s; };
 
@@ -187,7 +192,8 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
         // stem reads the packed input planes; conv1 (odd l) reads act0, conv2 (even l >= 2) reads act1
         const CUtensorMap* tm = l == 0 ? &tmap_in : ((l & 1) ? &tmap_x : &tmap_y);
         for (int g = 0; g < ng; ++g) {
-          const int tile = 2 * (G * s + g) + static_cast<int>(rank);
+          // (activations of layers > 0 live in this CTA's scratch tile, see `scratch_tile`)
+          const int tile = l == 0 ? 2 * (G * s + g) + static_cast<int>(rank) : scratch_tile(g);
           if (l > 0) {
             // this CTA's epilogue of (group g, layer l - 1) has stored and fenced the tile we are about to read
             ptx::mbar_wait(&act_ready[g], ready_phase[g], args.err_flag, ERRT_ACT_READY);
@@ -298,7 +304,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
           asm volatile("bar.sync 1, 128;" ::: "memory");
           tc::epilogue_tile(ca, smem_epi, sb, s_head, quad, lane, tile * 2,
                             tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS, &tmem_full[acc], acc_phase,
-                            &tmem_empty[acc], 0u /* the leader owns the accumulator-empty barrier */, 0, -1);
+                            &tmem_empty[acc], 0u /* the leader owns the accumulator-empty barrier */, 0, -1, scratch_tile(g) * 2);
           if (!last) {
             // what this warp stored must be visible to the TMA reads of the group's next layer (same CTA, async proxy)
             __threadfence();

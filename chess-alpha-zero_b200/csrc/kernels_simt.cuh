@@ -434,9 +434,16 @@ __global__ void push_priors_kernel(const float* __restrict__ policy, int n_label
   const float* row = policy + static_cast<size_t>(node) * n_labels;
   // the sum must be sequential to match the reference bit for bit; every lane computes it
   // redundantly from L1-resident values (<= 218 edges) instead of shuffling a serial chain.
+  // (a move without a label -- index < 0 -- counts as probability 0, as in the host-side search)
   double tot = 1e-8;
-  for (int e = beg; e < end; ++e) tot = __dadd_rn(tot, static_cast<double>(row[label_index[e]]));
-  for (int e = beg + lane; e < end; e += 32) priors[e] = __ddiv_rn(static_cast<double>(row[label_index[e]]), tot);
+  for (int e = beg; e < end; ++e) {
+    const int idx = label_index[e];
+    tot = __dadd_rn(tot, idx >= 0 ? static_cast<double>(row[idx]) : 0.0);
+  }
+  for (int e = beg + lane; e < end; e += 32) {
+    const int idx = label_index[e];
+    priors[e] = __ddiv_rn(idx >= 0 ? static_cast<double>(row[idx]) : 0.0, tot);
+  }
 }
 
 // select (:277-299): b = q + c_puct * p_ * sqrt(sum_n + 1) / (1 + n); first strict maximum from -999

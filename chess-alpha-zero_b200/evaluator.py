@@ -109,6 +109,24 @@ class Evaluator:
             _lib.check(self._handle, rc)
         return ticket.value
 
+    def submit_records_priors(self, records, offsets, labels, priors, value):
+        """submit_records() that returns one float64 prior per legal move (CSR `offsets` int32 (B + 1,), `labels` int32
+        (>= offsets[B],) as SelfPlaySearch.collect_csr hands them out) instead of the policy rows: the prior push of
+        select_action_q_and_u runs on the device, 8 bytes per legal move come back instead of 7 872 per position."""
+        r = _lib.as_array(records, np.uint8)
+        b = r.shape[0]
+        if r.ndim != 2 or r.shape[1] != _lib.RECORD_BYTES or offsets.dtype != np.int32 or labels.dtype != np.int32 \
+                or priors.dtype != np.float64 or offsets.shape[0] < b + 1 or value.shape[0] < b:
+            raise ValueError("records uint8 (B, 68); offsets / labels int32; priors float64; value float32 (>= B,)")
+        if priors.shape[0] < int(offsets[b]) or labels.shape[0] < int(offsets[b]):
+            raise ValueError("labels / priors are shorter than offsets[B]")
+        ticket = ctypes.c_int32(-1)
+        with self._lock:
+            rc = self._lib.caz_submit_records_priors(self._handle, _lib.ptr(r), b, _lib.ptr(offsets), _lib.ptr(labels),
+                                                     _lib.ptr(priors), _lib.ptr(value), ctypes.byref(ticket))
+            _lib.check(self._handle, rc)
+        return ticket.value
+
     def collect(self, ticket):
         _lib.check(self._handle, self._lib.caz_collect(self._handle, int(ticket)))
 
@@ -154,7 +172,8 @@ class Evaluator:
         _lib.check(self._handle, self._lib.caz_set_small_batch_limit(self._handle, int(limit)))
 
     def set_fused_tower(self, mode):
-        """-1: one persistent launch for stem + tower (default); 0: one launch per layer; 1 / 2: force the interleave."""
+        """-1: one persistent launch for stem + tower, form by batch size (default); 0: one launch per layer; 1 / 2: forced
+        forms of the one-launch tower (include/caz_b200.h)."""
         _lib.check(self._handle, self._lib.caz_set_fused_tower(self._handle, int(mode)))
 
     def sync(self):

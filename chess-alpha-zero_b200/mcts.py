@@ -16,7 +16,8 @@ from . import labels as _labels
 RECORD_BYTES = 68
 
 SYMBOLS = (
-    "caz_mcts_create", "caz_mcts_destroy", "caz_mcts_collect", "caz_mcts_apply", "caz_mcts_get_stats",
+    "caz_mcts_create", "caz_mcts_destroy", "caz_mcts_collect", "caz_mcts_apply", "caz_mcts_collect_csr",
+    "caz_mcts_apply_priors", "caz_mcts_get_stats",
     "caz_mcts_set_position", "caz_mcts_game_fen", "caz_mcts_game_result", "caz_mcts_root_edges",
     "caz_mcts_drain_play_data", "caz_mcts_debug_dirichlet", "caz_chess_perft",
     "caz_chess_legal_moves", "caz_chess_play", "caz_chess_record",
@@ -72,6 +73,9 @@ def load():
     lib.caz_mcts_destroy.restype = None
     lib.caz_mcts_collect.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, P(ctypes.c_int32)]
     lib.caz_mcts_apply.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
+    lib.caz_mcts_collect_csr.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, P(ctypes.c_int32), ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_int32]
+    lib.caz_mcts_apply_priors.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
     lib.caz_mcts_get_stats.argtypes = [ctypes.c_void_p, P(MctsStats)]
     lib.caz_mcts_set_position.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_char_p]
     lib.caz_mcts_game_fen.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32]
@@ -186,6 +190,36 @@ class SelfPlaySearch:
             raise RuntimeError(f"caz_mcts_collect failed ({rc})")
         self._n_last = n.value
         return self._records[:n.value]
+
+    MAX_MOVES = 256   # bound on a position's legal moves (csrc/chess/mcts.hpp)
+
+    def collect_csr(self, offsets=None, labels=None):
+        """collect() plus the leaves' legal moves as policy labels: returns (records [n][68], offsets int32 [n + 1], labels
+        int32 [offsets[n]]) -- the input of Evaluator.submit_records_priors.  `offsets` (capacity + 1) and `labels`
+        (capacity * 256) may be caller-owned (pinned) int32 arrays."""
+        if offsets is None:
+            offsets = np.zeros(self.capacity + 1, np.int32)
+        if labels is None:
+            labels = np.zeros(self.capacity * self.MAX_MOVES, np.int32)
+        n = ctypes.c_int32()
+        rc = load().caz_mcts_collect_csr(self._h, self._records.ctypes.data_as(ctypes.c_void_p), self.capacity, ctypes.byref(n),
+                                         offsets.ctypes.data_as(ctypes.c_void_p), labels.ctypes.data_as(ctypes.c_void_p),
+                                         labels.shape[0])
+        if rc:
+            raise RuntimeError(f"caz_mcts_collect_csr failed ({rc})")
+        self._n_last = n.value
+        return self._records[:n.value], offsets[:n.value + 1], labels[:int(offsets[n.value])] if n.value else labels[:0]
+
+    def apply_priors(self, priors, value):
+        """apply() from per-edge priors pushed on the device (float64, the order of the last collect_csr)."""
+        priors = np.ascontiguousarray(priors, dtype=np.float64)
+        value = np.ascontiguousarray(value, dtype=np.float32).reshape(-1)
+        if value.shape[0] < self._n_last:
+            raise ValueError("value does not match the last collect_csr()")
+        rc = load().caz_mcts_apply_priors(self._h, priors.ctypes.data_as(ctypes.c_void_p), value.ctypes.data_as(ctypes.c_void_p),
+                                          self._n_last)
+        if rc:
+            raise RuntimeError(f"caz_mcts_apply_priors failed ({rc})")
 
     def apply(self, policy, value):
         policy = np.ascontiguousarray(policy, dtype=np.float32)

@@ -146,6 +146,15 @@ int caz_submit(caz_handle* h, const float* planes, int32_t batch, float* policy,
  * more groups of games calls, so that one group's policy read-back runs under another group's forward pass. */
 int caz_submit_records(caz_handle* h, const uint8_t* records, int32_t batch, float* policy, float* value,
                        const uint8_t* legal_mask, uint32_t flags, int32_t* ticket);
+/* caz_submit_records for a search driver that knows the legal moves of its leaves: instead of the whole policy row
+ * (7 872 bytes per position) the device pushes the priors of select_action_q_and_u (player_chess.py:267-275) itself and
+ * returns one float64 per legal move, priors[offsets[i] + e] = P_i[labels[offsets[i] + e]] / (1e-8 + sum over the
+ * position's labels, left to right) -- bit-identical to caz_push_priors on the full row (labels < 0 count as 0).
+ *   offsets: host int32 [batch + 1] (CSR, offsets[0] = 0), labels: host int32 [offsets[batch]],
+ *   priors: host float64 [offsets[batch]] out, value: host float32 [batch] out; collected with caz_collect. */
+#define CAZ_MAX_MOVES 256 /* bound on the legal moves of one position (218 is the known maximum) */
+int caz_submit_records_priors(caz_handle* h, const uint8_t* records, int32_t batch, const int32_t* offsets,
+                              const int32_t* labels, double* priors, float* value, int32_t* ticket);
 int caz_collect(caz_handle* h, int32_t ticket);
 
 int caz_sync(caz_handle* h);
@@ -194,9 +203,9 @@ int64_t caz_inexact_weights(const caz_handle* h); /* bf16 build: folded bf16 wei
 int caz_set_small_batch_limit(caz_handle* h, int32_t limit);
 
 /* Batches beyond the small-batch kernel run stem + tower + head convolutions as ONE persistent launch in which every
- * CTA pair carries its own boards through all layers (mode 1 or 2 = boards groups per pair interleaved: forced; -1 =
- * chosen by batch size, the default).  mode 0 selects the older chain of one implicit-GEMM launch per layer.  Results
- * are bit-identical in every mode. */
+ * CTA pair carries its own boards through all layers.  mode -1 (default): the form is chosen by batch size; forced
+ * forms: 1 = one four-board group per pair, 2 = two groups interleaved layer by layer.  mode 0 selects the older chain
+ * of one implicit-GEMM launch per layer.  Results are bit-identical in every mode. */
 int caz_set_fused_tower(caz_handle* h, int32_t mode);
 
 /* Test hook: switch on per-layer clock64 stamps of CTA 0 of the small-batch kernel and/or read them back

@@ -62,6 +62,15 @@ int caz_mcts_collect(caz_mcts* m, uint8_t* records, int32_t capacity, int32_t* n
 /* policy: float32 [n][n_labels] and value: float32 [n] for the leaves of the last collect, in the same order. */
 int caz_mcts_apply(caz_mcts* m, const float* policy, const float* value, int32_t n);
 
+/* caz_mcts_collect that also lists every leaf's legal moves as policy labels (CSR: offsets int32 [n + 1], labels int32
+ * [offsets[n]], edge order = python-chess move order, -1 for a move without a label; edge_capacity >= capacity * 256):
+ * the input of caz_submit_records_priors, which then returns one prior per legal move instead of 1968 probabilities. */
+int caz_mcts_collect_csr(caz_mcts* m, uint8_t* records, int32_t capacity, int32_t* n_leaves, int32_t* offsets,
+                         int32_t* labels, int32_t edge_capacity);
+/* caz_mcts_apply from priors already pushed on the device (select_action_q_and_u's p = P[a] / (1e-8 + sum), float64
+ * [offsets[n]] in the order of the last caz_mcts_collect_csr): bit-identical trees to caz_mcts_apply. */
+int caz_mcts_apply_priors(caz_mcts* m, const double* priors, const float* value, int32_t n);
+
 int caz_mcts_get_stats(const caz_mcts* m, caz_mcts_stats* out);
 /* ChessEnv.update(fen): restart game `game` from a position */
 int caz_mcts_set_position(caz_mcts* m, int32_t game, const char* fen);

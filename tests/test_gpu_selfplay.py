@@ -42,3 +42,39 @@ def test_selfplay_rounds_through_the_evaluator():
     assert st["descents"] == st["leaves_evaluated"] + st["terminal_hits"]
     s.close()
     ev.close()
+
+
+def test_device_pushed_priors_are_bit_identical_and_build_the_same_trees():
+    """caz_submit_records_priors (legal-move labels in, one float64 prior per legal move out) against the full-policy path:
+    the priors equal caz_push_priors of the policy rows bit for bit, and two searches fed either way stay identical."""
+    from chess_alpha_zero_b200 import _lib
+    cfg = oweights.keras_config()
+    w = oweights.synth_weights(cfg, seed=0, recipe="randomized")
+    ev = caz.Evaluator(cfg, w, precision="bf16", max_batch=6 * 16)
+    mc = mcts.MctsConfig.normal(simulation_num_per_move=48, search_threads=16, continuous=0, max_game_length=4)
+    a = caz.SelfPlaySearch(6, mc, seed=9, n_threads=2)
+    b = caz.SelfPlaySearch(6, mc, seed=9, n_threads=2)
+    cap = b.capacity
+    off, lab = _lib.PinnedArray((cap + 1,), np.int32), _lib.PinnedArray((cap * 256,), np.int32)
+    pri, val = _lib.PinnedArray((cap * 256,), np.float64), _lib.PinnedArray((cap,), np.float32)
+    rounds = 0
+    for rnd in range(300):
+        rec_a = a.collect()
+        rec_b, o, l = b.collect_csr(off.array, lab.array)
+        assert np.array_equal(rec_a, rec_b)
+        if len(rec_a) == 0:
+            break
+        policy, value = ev.predict_records(rec_a)
+        ev.collect(ev.submit_records_priors(rec_b, off.array, lab.array, pri.array, val.array))
+        n_edges = int(o[-1])
+        want = ev.push_priors(policy, o, np.ascontiguousarray(np.maximum(l, 0)))
+        assert (l >= 0).all() and np.array_equal(pri.array[:n_edges], want)
+        assert np.array_equal(val.array[:len(rec_b)], value.reshape(-1))
+        a.apply(policy, value)
+        b.apply_priors(pri.array, val.array)
+        rounds += 1
+    assert rounds > 10 and a.stats() == b.stats() and a.stats()["games_finished"] == 6
+    assert [a.fen(g) for g in range(6)] == [b.fen(g) for g in range(6)]
+    a.close()
+    b.close()
+    ev.close()

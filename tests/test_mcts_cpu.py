@@ -301,3 +301,37 @@ def test_adjudication_overrides_a_result_at_the_length_limit():
     assert st["games_finished"] == 1 and st["adjudications"] == 1 and s.fen(0).startswith("R5k1/")
     assert s.result(0) == "1-0"                                   # tanh(3 * (5 + 3 - 3 - 3) / (5 + 3 + 3 + 3)) > 0.01
     s.close()
+
+
+def test_apply_priors_builds_the_same_trees_as_apply():
+    """The CSR path (collect_csr -> per-edge priors pushed elsewhere -> apply_priors) against apply(): the prior push is
+    restated here the way push_priors_kernel does it (float32 -> float64, sequential sum from 1e-8, labels < 0 as 0)."""
+    cfg = mcts.MctsConfig.normal(simulation_num_per_move=30, search_threads=8)
+    a = caz.SelfPlaySearch(4, cfg, seed=21, n_threads=2)
+    b = caz.SelfPlaySearch(4, cfg, seed=21, n_threads=2)
+    for _ in range(40):
+        rec_a = a.collect()
+        rec_b, off, lab = b.collect_csr()
+        assert np.array_equal(rec_a, rec_b) and off[0] == 0 and len(off) == len(rec_b) + 1 and len(lab) == off[-1]
+        if len(rec_a) == 0:
+            break
+        pol, val = _fake_net(rec_a)
+        priors = np.zeros(len(lab), np.float64)
+        for i in range(len(rec_b)):
+            idx = lab[off[i]:off[i + 1]]
+            raw = np.where(idx >= 0, pol[i][np.maximum(idx, 0)], 0.0).astype(np.float64)
+            tot = 1e-8
+            for x in raw:
+                tot += x
+            priors[off[i]:off[i + 1]] = raw / tot
+        a.apply(pol, val)
+        b.apply_priors(priors, val)
+    assert a.stats() == b.stats() and a.stats()["moves_played"] > 0
+    assert [a.fen(g) for g in range(4)] == [b.fen(g) for g in range(4)]
+    for g in range(4):
+        ea, eb = a.root_edges(g), b.root_edges(g)
+        assert (ea is None) == (eb is None)
+        if ea is not None:
+            assert all(np.array_equal(x, y) for x, y in zip(ea, eb))
+    a.close()
+    b.close()

@@ -43,13 +43,24 @@ def run(ev, games=256, sims=800, search_threads=16, seconds=20.0, groups=0, host
     mcfg = mcts.MctsConfig.normal(simulation_num_per_move=sims, search_threads=search_threads)
     searches = [caz.SelfPlaySearch(per_group, mcfg, seed=seed * 1000 + rank * 10 + g, n_threads=host_threads)
                 for g in range(groups)]
-    pins = [(_lib.PinnedArray((cap, 1968), np.float32), _lib.PinnedArray((cap,), np.float32)) for _ in searches]
+    # CAZ_SELFPLAY_FULL_POLICY=1: read the whole policy rows back (7 872 B per leaf) and push the priors on the host, as in
+    # round 1; default: caz_submit_records_priors -- the device pushes them, 8 B per legal move come back
+    full_policy = bool(os.environ.get("CAZ_SELFPLAY_FULL_POLICY")) or bool(os.environ.get("CAZ_SELFPLAY_SYNC"))
+    pins = [(_lib.PinnedArray((cap, 1968) if full_policy else (1, 1968), np.float32), _lib.PinnedArray((cap,), np.float32))
+            for _ in searches]
+    csr = [None if full_policy else (_lib.PinnedArray((cap + 1,), np.int32), _lib.PinnedArray((cap * 256,), np.int32),
+                                     _lib.PinnedArray((cap * 256,), np.float64)) for _ in searches]
 
     # warm-up round (first touch, clocks)
-    for g, (pp, pv) in zip(searches, pins):
-        rec = g.collect()
-        ev.predict_records_into(rec, pp.array, pv.array)
-        g.apply(pp.array[:len(rec)], pv.array[:len(rec)])
+    for g, (pp, pv), c in zip(searches, pins, csr):
+        if full_policy:
+            rec = g.collect()
+            ev.predict_records_into(rec, pp.array, pv.array)
+            g.apply(pp.array[:len(rec)], pv.array[:len(rec)])
+        else:
+            rec, off, lab = g.collect_csr(c[0].array, c[1].array)
+            ev.collect(ev.submit_records_priors(rec, c[0].array, c[1].array, c[2].array, pv.array))
+            g.apply_priors(c[2].array, pv.array)
     base = [g.stats() for g in searches]
 
     acc = [dict(collect=0.0, eval=0.0, apply=0.0, leaves=0, rounds=0) for _ in searches]
@@ -63,17 +74,18 @@ def run(ev, games=256, sims=800, search_threads=16, seconds=20.0, groups=0, host
     inflight, busy_from = [0], [0.0]
 
     def loop(i):
-        g, (pp, pv), a = searches[i], pins[i], acc[i]
+        g, (pp, pv), a, c = searches[i], pins[i], acc[i], csr[i]
         while time.perf_counter() < stop_at:
             t0 = time.perf_counter()
-            rec = g.collect()
+            rec = g.collect() if full_policy else g.collect_csr(c[0].array, c[1].array)[0]
             t1 = time.perf_counter()
             if pipelined:
                 with ev_lock:
                     if inflight[0] == 0:
                         busy_from[0] = time.perf_counter()
                     inflight[0] += 1
-                    ticket = ev.submit_records(rec, pp.array, pv.array)
+                    ticket = ev.submit_records(rec, pp.array, pv.array) if full_policy else \
+                        ev.submit_records_priors(rec, c[0].array, c[1].array, c[2].array, pv.array)
                 ev.collect(ticket)
                 t2 = time.perf_counter()
                 with ev_lock:
@@ -86,7 +98,10 @@ def run(ev, games=256, sims=800, search_threads=16, seconds=20.0, groups=0, host
                     ev.predict_records_into(rec, pp.array, pv.array)
                     t2 = time.perf_counter()
                     busy[0] += t2 - t1b
-            g.apply(pp.array[:len(rec)], pv.array[:len(rec)])
+            if full_policy:
+                g.apply(pp.array[:len(rec)], pv.array[:len(rec)])
+            else:
+                g.apply_priors(c[2].array, pv.array)
             t3 = time.perf_counter()
             a["collect"] += t1 - t0
             a["eval"] += t2 - t1
@@ -118,6 +133,8 @@ def run(ev, games=256, sims=800, search_threads=16, seconds=20.0, groups=0, host
         "mean_batch": leaves / max(1, rounds),
         "evaluator_occupancy": busy[0] / wall,
         "host_threads_per_group": host_threads, "groups": groups, "host_cores": cores, "pipelined_evaluator": pipelined,
+        "read_back": "full policy rows, priors pushed on the host" if full_policy else
+                     "priors of the legal moves, pushed on the device (caz_submit_records_priors)",
         "per_round_ms": {k: 1e3 * sum(a[k] for a in acc) / max(1, rounds) for k in ("collect", "eval", "apply")},
         "moves_played": tot["moves_played"], "games_finished": tot["games_finished"],
         "terminal_hits": tot["terminal_hits"], "withdrawn": tot["withdrawn"],
