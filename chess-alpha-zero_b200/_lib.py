@@ -24,7 +24,7 @@ SYMBOLS = (
     "caz_create", "caz_reload", "caz_destroy", "caz_eval", "caz_eval_device", "caz_eval_records", "caz_sync",
     "caz_encode", "caz_push_priors", "caz_puct_select", "caz_last_error", "caz_abi_version", "caz_max_batch",
     "caz_precision", "caz_stream", "caz_kernel_launches", "caz_weight_bytes", "caz_inexact_weights", "caz_profile", "caz_profile_read",
-    "caz_host_alloc", "caz_host_free", "caz_debug_conv_layer", "caz_set_small_batch_limit", "caz_set_fused_tower", "caz_debug_sb_trace", "caz_submit", "caz_submit_records", "caz_submit_records_priors", "caz_collect",
+    "caz_host_alloc", "caz_host_free", "caz_debug_conv_layer", "caz_set_small_batch_limit", "caz_set_fused_tower", "caz_debug_tower_trace", "caz_debug_sb_trace", "caz_submit", "caz_submit_records", "caz_submit_records_priors", "caz_collect",
 )
 
 
@@ -101,6 +101,7 @@ def load():
     lib.caz_set_small_batch_limit.argtypes = [vp, i32]
     lib.caz_set_fused_tower.argtypes = [vp, i32]
     lib.caz_debug_sb_trace.argtypes = [vp, i32, vp, i32]
+    lib.caz_debug_tower_trace.argtypes = [vp, i32, vp, i32]
     lib.caz_debug_conv_layer.argtypes = [vp, i32, vp, vp, i32, vp]
     lib.caz_host_alloc.argtypes = [i64]
     lib.caz_host_alloc.restype = vp

@@ -95,6 +95,8 @@ struct caz_handle {
   bool tw_enabled = true;    // CAZ_NO_TOWER=1 keeps the per-layer launch chain (conv_tc2.cuh)
   int tw_mode = 0;           // caz_set_fused_tower / CAZ_TOWER_MODE: 0 = by batch size, 1 / 2 = forced groups per pair
   CUtensorMap tw_tm_w_tower; // all tower layers' weights as one matrix, box 64 x filters / 2
+  long long* tw_trace = nullptr;   // [64][8] clock stamps (caz_debug_tower_trace)
+  bool tw_trace_on = false;
   // small-batch persistent tower kernel (conv_sb.cuh)
   bool sb_ok = false;        // architecture fits it
   int sb_limit = -1;         // batches <= this use it; -1 = automatic
@@ -428,6 +430,22 @@ int install_weights(caz_handle* h, const caz_tensor* t, int n_tensors) {
   h->weight_bytes = wbytes;
   if (tcp && (rc = setup_dense_tc(h, pol[5].data, pol[6].data, val[5].data))) return rc;
   return CAZ_OK;
+}
+
+// Launch with (or without) the programmatic-stream-serialization attribute: see pdl_sync() in kernels_simt.cuh.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 int check_launch(caz_handle* h, const char* what) {
@@ -852,6 +870,10 @@ int setup_tower(caz_handle* h) {
     h->tw_tm_w_tower = h->convs[0].tmap_w2;
   }
   CU_TRY(h, cudaFuncSetAttribute(caz::tw::tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tw::SMEM_BYTES));
+  if (!h->tw_trace) {
+    CU_TRY(h, cudaMalloc(&h->tw_trace, 64 * 8 * sizeof(long long)));
+    CU_TRY(h, cudaMemset(h->tw_trace, 0, 64 * 8 * sizeof(long long)));
+  }
   h->tw_ok = true;
   return CAZ_OK;
 }
@@ -867,7 +889,7 @@ int launch_tower(caz_handle* h, int batch) {
   args.stem_row_bytes = h->in_cpad * 2;
   args.n = a.filters;
   args.fmt = operand_fmt(h);
-  args.pdl = 0;
+  args.pdl = h->pdl ? 1 : 0;   // chained to the pack kernel before it and the head kernels after it
   args.bias_all = h->bias_all;
   args.xf = static_cast<float*>(h->act[2]);
   args.act0 = static_cast<__nv_bfloat16*>(h->act[0]);
@@ -879,6 +901,7 @@ int launch_tower(caz_handle* h, int batch) {
   args.pf = a.policy_filters;
   args.vf = a.value_filters;
   args.err_flag = h->err_flag_dev;
+  args.trace = (h->tw_trace_on && args.n_layers <= 64) ? h->tw_trace : nullptr;
   const int groups = ((batch + 1) / 2 + 1) / 2, max_pairs = h->num_sms / 2;
   // Enough boards for every pair to hold two groups: interleave them (the epilogue of one runs under the other's MMAs).
   // Fewer: one group per pair on as many pairs as there are groups -- an exposed epilogue costs less than an idle SM.
@@ -892,6 +915,11 @@ int launch_tower(caz_handle* h, int batch) {
   cfg.blockDim = dim3(caz::tw::THREADS);
   cfg.dynamicSmemBytes = caz::tw::SMEM_BYTES;
   cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = h->pdl ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, caz::tw::tower_kernel, h->tmap_in, h->tmap_act[0], h->tmap_act[1], h->convs[0].tmap_w2,
                                      h->tw_tm_w_tower, args);
   if (e != cudaSuccess) return fail(h, CAZ_ERR_CUDA, fmt("launch of tower_kernel failed: %s", cudaGetErrorString(e)));
@@ -993,7 +1021,8 @@ int launch_dense_tc(caz_handle* h, const float* in, uint16_t* a3, const CUtensor
                     int n_tile, int n_tiles, int n_total, const float* bias, int relu, float* out, int m) {
   int rc;
   const size_t total = (size_t)(((m + 127) / 128) * 128) * k;
-  caz::split3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(in, a3, m, ((m + 127) / 128) * 128, k, act_fp16(h) ? 1 : 0);
+  launch_chained(caz::split3_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, h->stream, h->pdl, in, a3, m,
+                 ((m + 127) / 128) * 128, k, act_fp16(h) ? 1 : 0);
   if ((rc = check_launch(h, "split3_kernel"))) return rc;
   caz::tc::ConvArgs args{};
   args.batch = (m + 63) / 64;          // "boards" = groups of 64 rows
@@ -1010,9 +1039,10 @@ int launch_dense_tc(caz_handle* h, const float* in, uint16_t* a3, const CUtensor
   args.m_rows = m;
   args.out_rm = out;
   args.err_flag = h->err_flag_dev;
+  args.pdl = h->pdl ? 1 : 0;
   const int work = ((args.num_tiles + 1) / 2) * n_tiles, max_pairs = h->num_sms / 2;
   const int grid = 2 * (work < max_pairs ? work : max_pairs);
-  caz::tc2::conv_tc2_kernel<<<grid, caz::tc2::THREADS, caz::tc2::SMEM_BYTES, h->stream>>>(*tm_a, *tm_w, args);
+  launch_chained(caz::tc2::conv_tc2_kernel, dim3(grid), dim3(caz::tc2::THREADS), caz::tc2::SMEM_BYTES, h->stream, h->pdl, *tm_a, *tm_w, args);
   return check_launch(h, "conv_tc2_kernel (dense)");
 }
 
@@ -1103,7 +1133,8 @@ int forward(caz_handle* h, const float* d_planes, const uint8_t* d_records, int 
       caz::dense_tiled_kernel<<<gv, 256, 0, h->stream>>>(h->featv, h->vfc1_w, h->vfc1_b, h->vhid, batch, vf * 64, a.value_fc, 1);
       if ((rc = check_launch(h, "dense_tiled_kernel (value)"))) return rc;
     }
-    caz::policy_softmax_kernel<<<batch, 256, 0, h->stream>>>(d_policy, d_mask, a.n_labels, h->vhid, h->vfc2_w, h->vfc2_b, d_value, a.value_fc);
+    launch_chained(caz::policy_softmax_kernel, dim3(batch), dim3(256), 0, h->stream, h->pdl && h->dense_tc, d_policy, d_mask, a.n_labels,
+                   h->vhid, h->vfc2_w, h->vfc2_b, d_value, a.value_fc);
     if ((rc = check_launch(h, "policy_softmax_kernel"))) return rc;
   }
   if (prof) { CU_TRY(h, cudaEventRecord(h->ev[4], h->stream)); h->pending_launches[3] = h->launches - l0; }
@@ -1154,6 +1185,7 @@ void caz_destroy(caz_handle* h) {
   if (h->sb_hpart) cudaFree(h->sb_hpart);
   if (h->sb_hstats) cudaFree(h->sb_hstats);
   if (h->sb_trace) cudaFree(h->sb_trace);
+  if (h->tw_trace) cudaFree(h->tw_trace);
   if (h->sb_sm_near) cudaFree(h->sb_sm_near);
   void* ptrs[] = {h->pfc_wb, h->vfc1_wb, h->head_w, h->head_b, h->pfc_w, h->pfc_b, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, h->in_act,
                   h->act[0], h->act[1], h->act[2], h->featp, h->featv, h->vhid, h->a3p, h->a3v, h->w3p, h->w3v, h->bias3p, h->d_planes, h->d_policy, h->d_value,
@@ -1678,6 +1710,18 @@ int caz_debug_sb_trace(caz_handle* h, int32_t enable, int64_t* stamps, int32_t n
   if (stamps && n > 0) {
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     CU_TRY(h, cudaMemcpy(stamps, h->sb_trace, (size_t)(n > 1024 + 16 * 256 * 2 ? 1024 + 16 * 256 * 2 : n) * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  return CAZ_OK;
+}
+
+int caz_debug_tower_trace(caz_handle* h, int32_t enable, int64_t* stamps, int32_t n) {
+  if (!h || !h->tw_ok) return fail(h, CAZ_ERR_INVALID, "one-launch tower kernel not available");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  h->tw_trace_on = enable != 0;
+  if (stamps && n > 0) {
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaMemcpy(stamps, h->tw_trace, (size_t)(n > 512 ? 512 : n) * sizeof(long long), cudaMemcpyDeviceToHost));
   }
   return CAZ_OK;
 }

@@ -127,7 +127,10 @@ __device__ __forceinline__ size_t xf_index(int tile, int chunks, int chunk, int 
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* smem_epi, const float* s_bias,
                                               const float* s_head, int quad, int lane, int n0, uint32_t taddr,
                                               uint64_t* full_bar, uint32_t full_phase, uint64_t* empty_bar,
-                                              uint32_t release_rank, int nt = 0, int next_n0 = -1, int n0_store = -1) {
+                                              uint32_t release_rank, int nt = 0, int next_n0 = -1, int n0_store = -1,
+                                              uint64_t* chunk_ready = nullptr) {
+  // chunk_ready: nullptr, or mbarriers [n / 64] of THIS CTA on which the warp arrives as soon as it has stored and fenced
+  // 64 more output channels (the one-launch tower starts the next layer on them while the rest is still being drained)
   // n0_store: first board of the tile in the ACTIVATION buffers when they are addressed by something else than the board
   // number (the one-launch tower keeps them in a compact per-CTA scratch, conv_tower.cuh); -1 = n0
   if (n0_store < 0) n0_store = n0;
@@ -266,6 +269,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
         if (live(r)) *reinterpret_cast<uint4*>(args.out_bf16 + grow(r) * opitch + nt * args.n + c0 + bc * 8) = o;
       }
       __syncwarp();
+    }
+    if (chunk_ready && ((c0 + 32) & 63) == 0) {
+      // channels [c0 - 32, c0 + 32) of this warp's rows are stored: visible to the TMA reads of the same CTA (async proxy)
+      __threadfence();
+      ptx::fence_proxy_async_all();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&chunk_ready[c0 >> 6]);
     }
   }
   if (args.head_w && live(lane)) {

@@ -17,8 +17,9 @@
 // pair owns tile 2 * (2s + g) + r; a tile = two boards).  Layers are walked with the two groups interleaved -- (A,0) (B,0) (A,1)
 // (B,1) ... -- so that while the epilogue warps drain layer l of group A, the tensor cores run layer l of group B, and
 // the two TMEM accumulator stages map one to each group.  The only new synchronisation is CTA-local: the epilogue warps
-// fence their global stores towards the async proxy and arrive on `act_ready[group]`; the activation producer waits for
-// it before it requests the group's next halo tiles with TMA.
+// fence their global stores towards the async proxy and arrive on `act_ready[group][chunk]` after every 64 output channels;
+// the activation producer waits for a chunk's barrier before it requests that 64-channel halo tile of the group's next
+// layer with TMA -- so a lone group's next layer starts on the first channels while the rest is still being drained.
 //
 // Everything else (halo tile + shifted UMMA descriptors, cta_group::2 MMAs, weight halves per CTA, multicast commits,
 // the fused epilogue) is conv_tc2.cuh / conv_tc.cuh.
@@ -64,6 +65,9 @@ struct TowerArgs {
   float* featv;
   int pf, vf;
   int* err_flag;
+  long long* trace;      // nullptr, or [n_layers][8] clock64 stamps of pair 0's leader CTA for its first super-group, group 0
+                         // (caz_debug_tower_trace): 0 first 64 input channels ready, 1 tile requested, 2 first chunk landed, 3 MMAs issued,
+                         // 4 accumulator complete, 5 epilogue done
 };
 
 // tmap_in: stem input halo view; tmap_x / tmap_y: halo views of act0 / act1; tmap_w_stem: [n][k*k*cin_pad], box (row/2) x n/2;
@@ -86,8 +90,8 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
   uint64_t* b_empty = b_full + B_STAGES;            // [B_STAGES]     per CTA, multicast arrive
   uint64_t* tmem_full = b_empty + B_STAGES;         // [ACC_STAGES]   per CTA, multicast arrive
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;    // [ACC_STAGES]   leader's copy live, 8 arrivals
-  uint64_t* act_ready = tmem_empty + ACC_STAGES;    // [2]            per CTA and group: the group's layer output is in memory
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(act_ready + 2);
+  uint64_t* act_ready = tmem_empty + ACC_STAGES;    // [2][4]         per CTA, group and 64-channel chunk: that part of the group's layer output is in memory
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(act_ready + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -97,6 +101,10 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
   const int num_tiles = (args.batch + 1) >> 1;          // two boards each
   const int num_groups = (num_tiles + 1) >> 1;          // four boards: one tile per CTA of the pair
   const int G = args.interleave;                        // groups per super-group
+  // A lone group has nothing to hide its epilogue under: it signals every 64 output channels (a fence each: twice the
+  // epilogue time, but the next layer starts ~7 000 cycles earlier).  Two interleaved groups signal once per tile: their
+  // epilogue must stay shorter than the other group's MMA phase.
+  const bool fine = G == 1;
   const int num_super = (num_groups + G - 1) / G;
   const int L = args.n_layers;
   const int n_half = args.n >> 1;
@@ -126,8 +134,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
       ptx::mbar_init(&tmem_full[i], 1);
       ptx::mbar_init(&tmem_empty[i], 8);
     }
-    ptx::mbar_init(&act_ready[0], 4);   // one arrive per epilogue warp
-    ptx::mbar_init(&act_ready[1], 4);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&act_ready[i], 4);   // one arrive per epilogue warp
     ptx::mbar_fence_init();
     ptx::fence_proxy_async();
   }
@@ -183,7 +190,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
     // ===================== activation producer: this CTA's two boards of every (group, layer) tile =====================
     int slot = 0;
     uint32_t phase = 0;
-    uint32_t ready_phase[2] = {0, 0};
+    uint32_t ready_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int s = pair0; s < num_super; s += n_pairs_grid) {
       const int ng = groups_in(s);
       for (int l = 0; l < L; ++l) {
@@ -194,19 +201,24 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
         for (int g = 0; g < ng; ++g) {
           // (activations of layers > 0 live in this CTA's scratch tile, see `scratch_tile`)
           const int tile = l == 0 ? 2 * (G * s + g) + static_cast<int>(rank) : scratch_tile(g);
-          if (l > 0) {
-            // this CTA's epilogue of (group g, layer l - 1) has stored and fenced the tile we are about to read
-            ptx::mbar_wait(&act_ready[g], ready_phase[g], args.err_flag, ERRT_ACT_READY);
-            ready_phase[g] ^= 1;
-            ptx::fence_proxy_async_all();
-          }
+          const bool tr = args.trace && blockIdx.x == 0 && s == pair0 && g == 0 && lane == 0;
           for (int kc = 0; kc < kch; ++kc) {
+            if (l > 0 && (fine || kc == 0)) {
+              // this CTA's epilogue of (group g, layer l - 1) has stored and fenced what we are about to read: the whole
+              // tile, or (lone group) these 64 channels -- the layer starts while the rest of its input is still being drained
+              const int r = g * 4 + (fine ? kc : 0);
+              ptx::mbar_wait(&act_ready[r], ready_phase[r], args.err_flag, ERRT_ACT_READY);
+              ready_phase[r] ^= 1;
+              ptx::fence_proxy_async_all();
+            }
+            if (tr && kc == 0) args.trace[l * 8 + 0] = clock64();
             ptx::mbar_wait(&a_empty[slot], phase ^ 1, args.err_flag, ERRT_PRODUCER_A);
             if (ptx::elect_one()) {
               if (leader) ptx::mbar_expect_tx(&a_full[slot], 2 * plane_bytes);
               ptx::tma_load_4d_2cta(smem_a + slot * A_SLOT_BYTES, tm, ptx::mapa_u32(&a_full[slot], 0), kc * kblk, -pad, tile * 2, -pad);
             }
             __syncwarp();
+            if (tr && kc == 0) args.trace[l * 8 + 1] = clock64();
             if (++slot == A_SLOTS) { slot = 0; phase ^= 1; }
           }
         }
@@ -229,8 +241,10 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
             ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, args.err_flag, ERRT_MMA_ACC);
             ptx::tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+            const bool tr = args.trace && blockIdx.x == 0 && s == pair0 && g == 0 && lane == 0;
             for (int kc = 0; kc < kch; ++kc) {
               ptx::mbar_wait(&a_full[slot], a_phase, args.err_flag, ERRT_MMA_A);
+              if (tr && kc == 0) args.trace[l * 8 + 2] = clock64();
               const uint64_t a_plane = a_desc0 + static_cast<uint64_t>((slot * A_SLOT_BYTES) >> 4);
               for (int dy = 0; dy < k; ++dy)
                 for (int dx = 0; dx < k; ++dx) {
@@ -257,6 +271,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
                 }
               if (++slot == A_SLOTS) { slot = 0; a_phase ^= 1; }
             }
+            if (tr) args.trace[l * 8 + 3] = clock64();
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
           }
         }
@@ -302,15 +317,22 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
           sb[et] = args.bias_all[l * args.n + (et < args.n ? et : 0)];
           if (et + 128 < args.n) sb[et + 128] = args.bias_all[l * args.n + et + 128];
           asm volatile("bar.sync 1, 128;" ::: "memory");
+          const bool tr = args.trace && blockIdx.x == 0 && s == pair0 && g == 0 && threadIdx.x == 128;
+          if (tr) {   // when the accumulator is complete (the epilogue proper waits for the same barrier again: no cost)
+            ptx::mbar_wait(&tmem_full[acc], acc_phase, args.err_flag, tc::ERR_EPILOGUE);
+            args.trace[l * 8 + 4] = clock64();
+          }
           tc::epilogue_tile(ca, smem_epi, sb, s_head, quad, lane, tile * 2,
                             tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS, &tmem_full[acc], acc_phase,
-                            &tmem_empty[acc], 0u /* the leader owns the accumulator-empty barrier */, 0, -1, scratch_tile(g) * 2);
-          if (!last) {
+                            &tmem_empty[acc], 0u /* the leader owns the accumulator-empty barrier */, 0, -1, scratch_tile(g) * 2,
+                            (last || !fine) ? nullptr : &act_ready[g * 4]);
+          if (tr) args.trace[l * 8 + 5] = clock64();
+          if (!last && !fine) {
             // what this warp stored must be visible to the TMA reads of the group's next layer (same CTA, async proxy)
             __threadfence();
             ptx::fence_proxy_async_all();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&act_ready[g]);
+            if (lane == 0) ptx::mbar_arrive(&act_ready[g * 4]);
           }
           if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }

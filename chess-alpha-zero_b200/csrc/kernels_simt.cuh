@@ -9,6 +9,14 @@
 
 namespace caz {
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
+// its predecessor in the stream is still running; this lets ITS successor do the same and then waits until the
+// predecessor has completed and its writes are visible -- before the first global access of the caller.  Without the
+// launch attribute both instructions do nothing.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
+}
+
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);
 template <>
@@ -71,6 +79,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ in, T* __restrict__ ou
 // fp32 [m][k] -> 16-bit [mpad][3k] = [hi | hi | lo] with hi = round16(x), lo = round16(x - hi): the A operand of the
 // "3-term split" tensor-core GEMM  x.w ~= hi.wh + hi.wl + lo.wh  (error ~2^-17 relative with bf16, fp32 accumulate)
 __global__ void split3_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int m, int mpad, int k, int fp16) {
+  pdl_sync();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<size_t>(mpad) * k) return;
   const int row = static_cast<int>(i / k), col = static_cast<int>(i - static_cast<size_t>(row) * k);
@@ -355,6 +364,7 @@ __global__ void __launch_bounds__(256)
 policy_softmax_kernel(float* __restrict__ policy, const uint8_t* __restrict__ mask, int n_labels,
                       const float* __restrict__ vhid, const float* __restrict__ w2, const float* __restrict__ b2,
                       float* __restrict__ value, int hid) {
+  pdl_sync();
   __shared__ float s_red[8];
   __shared__ float s_bc;
   float* row = policy + static_cast<size_t>(blockIdx.x) * n_labels;

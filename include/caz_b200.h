@@ -207,6 +207,10 @@ int caz_set_small_batch_limit(caz_handle* h, int32_t limit);
  * forms: 1 = one four-board group per pair, 2 = two groups interleaved layer by layer.  mode 0 selects the older chain
  * of one implicit-GEMM launch per layer.  Results are bit-identical in every mode. */
 int caz_set_fused_tower(caz_handle* h, int32_t mode);
+/* Test hook: per-layer clock64 stamps of the one-launch tower kernel (pair 0's leader CTA, its first super-group, group
+ * 0; stamps: host int64 [n <= 512], 8 per layer: activations ready, tile requested, first chunk landed, MMAs issued,
+ * accumulator complete, epilogue done, unused, unused). */
+int caz_debug_tower_trace(caz_handle* h, int32_t enable, int64_t* stamps, int32_t n);
 
 /* Test hook: switch on per-layer clock64 stamps of CTA 0 of the small-batch kernel and/or read them back
  * (stamps: host int64 [n], 8 per layer: barrier passed, first A tile landed, last A tile landed, MMAs issued,
