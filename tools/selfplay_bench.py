@@ -161,8 +161,11 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     args = ap.parse_args()
 
-    rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from chess_alpha_zero_b200 import sharding
+    _, world, rank = sharding.rank_world()
+    # configs[3]: --games is this GPU's share; the job's games are numbered globally, game_id mod world == rank
+    mine = sharding.games_for_rank(args.games * world, rank, world)
+    assert len(mine) == args.games and mine[0] == rank
     import torch
     torch.cuda.set_device(rank)
     import chess_alpha_zero_b200 as caz
