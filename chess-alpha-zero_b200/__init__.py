@@ -13,6 +13,7 @@ from .config import Config
 from .evaluator import Evaluator
 from .mcts import SelfPlaySearch
 from .model import ChessModel
+from .trainer import TrainConfig, Trainer
 
 __all__ = ["ChessModel", "ChessModelAPI", "Evaluator", "Config", "CazError", "library_path", "encoder",
-           "keras_graph", "labels", "mcts", "SelfPlaySearch"]
+           "keras_graph", "labels", "mcts", "SelfPlaySearch", "Trainer", "TrainConfig"]

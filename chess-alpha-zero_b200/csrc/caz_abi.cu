@@ -1776,3 +1776,5 @@ void caz_host_free(void* p) {
 }
 
 }  // extern "C"
+
+#include "caz_train.inc.cu"

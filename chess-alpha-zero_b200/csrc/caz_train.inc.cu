@@ -1,0 +1,477 @@
+// Training step of the reference's `opt` worker on the GPU (included at the end of caz_abi.cu: one
+// translation unit, so the tensor-core launch helpers above are in scope).
+//
+// Replaces  model.compile(Adam(), ['categorical_crossentropy', 'mean_squared_error'], loss_weights=[1.25, 1.0]) and one
+// batch of model.fit(state_ary, [policy_ary, value_ary], batch_size=384)  (reference src/chess_zero/worker/optimize.py:79-103)
+// on the graph of agent/model_chess.py:57-111: BatchNormalization in training mode, l2(1e-4) on every Conv2D and Dense
+// kernel (configs/normal.py:46-68).  Parameters, Adam moments and gradients are fp32 vectors in the tensor order of
+// caz_create (= Keras layer order); the gradient vector may live in caller-provided device memory so that a
+// torch.distributed all-reduce (NCCL) can run on it between caz_train_forward_backward and caz_train_apply.
+#include "train.cuh"
+
+namespace {
+
+struct TrainConv {
+  int k = 0, cin = 0, cout = 0;
+  size_t w = 0, gamma = 0, beta = 0, mmean = 0, mvar = 0;   // offsets into the flat parameter vector
+  float *z = nullptr, *a = nullptr;                         // [rows][cout]: convolution output, activation after BN (+skip) + ReLU
+  float *mean = nullptr, *invstd = nullptr;                 // batch statistics of this step
+};
+
+}  // namespace
+
+struct caz_trainer {
+  caz_arch arch{};
+  caz_train_config cfg{};
+  int device = 0, precision = CAZ_PRECISION_FP32, max_batch = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  size_t n_params = 0;
+  std::vector<size_t> tensor_off, tensor_len;   // per tensor of the caz_create order
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  bool grads_external = false;
+  uint8_t* seg = nullptr;
+  int64_t step = 0;
+  std::vector<TrainConv> convs;     // stem, conv1 / conv2 of every block
+  TrainConv pconv, vconv;           // heads' 1x1 convolutions (+ BN)
+  size_t pfc_w = 0, pfc_b = 0, vfc1_w = 0, vfc1_b = 0, vfc2_w = 0, vfc2_b = 0;
+  // batch-sized buffers
+  float *x0 = nullptr, *planes = nullptr, *policy_t = nullptr, *value_t = nullptr;
+  float *featp = nullptr, *logits = nullptr, *dlogits = nullptr, *probs = nullptr, *featv = nullptr, *hid = nullptr, *vpre = nullptr,
+        *vout = nullptr, *dvpre = nullptr, *dhid = nullptr, *dfeatp = nullptr, *dfeatv = nullptr;
+  float *d_a = nullptr, *d_b = nullptr, *d_skip = nullptr, *dz = nullptr, *dzp = nullptr, *dzv = nullptr, *dap = nullptr, *dav = nullptr;
+  float *w_flip = nullptr, *zero_bias = nullptr;
+  double *partial = nullptr, *loss_acc = nullptr;
+  float last_losses[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int tfail(caz_trainer* t, int code, const std::string& msg) {
+  if (t) t->err = msg;
+  else {
+    std::lock_guard<std::mutex> g(g_err_mutex);
+    g_create_error = msg;
+  }
+  return code;
+}
+
+#define TR_TRY(t, expr)                                                                                      \
+  do {                                                                                                       \
+    cudaError_t e__ = (expr);                                                                                \
+    if (e__ != cudaSuccess)                                                                                  \
+      return tfail((t), CAZ_ERR_CUDA, fmt("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+  } while (0)
+
+int tr_launch_ok(caz_trainer* t, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return tfail(t, CAZ_ERR_CUDA, fmt("launch of %s failed: %s", what, cudaGetErrorString(e)));
+  return CAZ_OK;
+}
+
+template <typename T>
+int tr_alloc(caz_trainer* t, T** p, size_t count) {
+  TR_TRY(t, cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  TR_TRY(t, cudaMemsetAsync(*p, 0, count * sizeof(T), t->stream));
+  return CAZ_OK;
+}
+
+unsigned blocks_for(size_t n, int per = 256) { return static_cast<unsigned>((n + per - 1) / per); }
+
+// "same" convolution on fp32 NHWC rows, raw output (no bias, no activation): out = conv(in, w) (+ add)
+int tr_conv_fp32(caz_trainer* t, const float* in, const float* w, const float* add, float* out, int batch, int k, int cin, int cout) {
+  const size_t smem = static_cast<size_t>(8 + k - 1) * (8 + k - 1) * cin * sizeof(float);
+  switch (k) {
+    case 1: caz::conv_fp32_kernel<1><<<batch, 256, smem, t->stream>>>(in, w, t->zero_bias, add, out, cin, cin, cout, 0); break;
+    case 3: caz::conv_fp32_kernel<3><<<batch, 256, smem, t->stream>>>(in, w, t->zero_bias, add, out, cin, cin, cout, 0); break;
+    case 5: caz::conv_fp32_kernel<5><<<batch, 256, smem, t->stream>>>(in, w, t->zero_bias, add, out, cin, cin, cout, 0); break;
+    case 7: caz::conv_fp32_kernel<7><<<batch, 256, smem, t->stream>>>(in, w, t->zero_bias, add, out, cin, cin, cout, 0); break;
+    default: return tfail(t, CAZ_ERR_INVALID, "unsupported kernel size");
+  }
+  return tr_launch_ok(t, "conv_fp32_kernel");
+}
+
+// C[m][n] = A . B (+ bias) with arbitrary strides (see gemm_kernel); ksplit > 1: C is cleared and the partial sums are added atomically
+int tr_gemm(caz_trainer* t, const float* a, long a_si, long a_sk, const float* b, long b_sk, long b_sj, const float* bias, float* c,
+            int m, int n, int k, int relu = 0, int ksplit = 1) {
+  if (ksplit > 1) TR_TRY(t, cudaMemsetAsync(c, 0, static_cast<size_t>(m) * n * sizeof(float), t->stream));
+  const dim3 grid((n + 31) / 32, (m + 31) / 32, ksplit);
+  caz::train::gemm_kernel<<<grid, 256, 0, t->stream>>>(a, a_si, a_sk, b, b_sk, b_sj, ksplit > 1 ? nullptr : bias, c, m, n, k, 0, ksplit > 1 ? 0 : relu);
+  return tr_launch_ok(t, "gemm_kernel");
+}
+
+// batch statistics of z (and the moving averages), then a = relu(BN(z) (+ skip))
+int tr_bn_forward(caz_trainer* t, TrainConv& L, const float* skip, int rows) {
+  const dim3 grid((L.cout + 31) / 32, caz::train::STAT_SPLITS);
+  caz::train::channel_sums_kernel<<<grid, 256, 0, t->stream>>>(0, L.z, nullptr, nullptr, nullptr, nullptr, rows, L.cout, t->partial);
+  int rc;
+  if ((rc = tr_launch_ok(t, "channel_sums_kernel"))) return rc;
+  caz::train::bn_finish_stats_kernel<<<(L.cout + 127) / 128, 128, 0, t->stream>>>(t->partial, rows, L.cout, t->arch.bn_epsilon, t->cfg.bn_momentum, L.mean,
+                                                                                L.invstd, t->params + L.mmean, t->params + L.mvar);
+  if ((rc = tr_launch_ok(t, "bn_finish_stats_kernel"))) return rc;
+  const size_t total = static_cast<size_t>(rows) * L.cout;
+  caz::train::bn_apply_kernel<__half><<<blocks_for(total), 256, 0, t->stream>>>(L.z, skip, t->params + L.gamma, t->params + L.beta, L.mean, L.invstd, total,
+                                                                                L.cout, L.a, nullptr);
+  return tr_launch_ok(t, "bn_apply_kernel");
+}
+
+// da (gradient wrt the layer's activation) -> dz (wrt its convolution output), dgamma / dbeta; dskip = gradient passed to the Add's other input
+int tr_bn_backward(caz_trainer* t, TrainConv& L, const float* da, float* dz, float* dskip, int dskip_accumulate, int rows) {
+  const dim3 grid((L.cout + 31) / 32, caz::train::STAT_SPLITS);
+  caz::train::channel_sums_kernel<<<grid, 256, 0, t->stream>>>(1, L.z, L.a, da, L.mean, L.invstd, rows, L.cout, t->partial);
+  int rc;
+  if ((rc = tr_launch_ok(t, "channel_sums_kernel (backward)"))) return rc;
+  caz::train::bn_param_grads_kernel<<<(L.cout + 127) / 128, 128, 0, t->stream>>>(t->partial, L.cout, t->grads + L.gamma, t->grads + L.beta);
+  if ((rc = tr_launch_ok(t, "bn_param_grads_kernel"))) return rc;
+  const size_t total = static_cast<size_t>(rows) * L.cout;
+  caz::train::bn_backward_kernel<__half><<<blocks_for(total), 256, 0, t->stream>>>(L.z, L.a, da, t->params + L.gamma, L.mean, L.invstd, t->partial, rows,
+                                                                                   L.cout, dz, nullptr, dskip, dskip_accumulate);
+  return tr_launch_ok(t, "bn_backward_kernel");
+}
+
+// dW of a k x k convolution (fp32 build)
+int tr_wgrad_fp32(caz_trainer* t, const float* x, const float* dz, int batch, const TrainConv& L) {
+  const int taps = L.k * L.k;
+  int splits = 1;
+  while (splits < 16 && taps * splits * ((L.cin + 31) / 32) * ((L.cout + 31) / 32) < 4 * 148 && splits * 2 <= batch) splits *= 2;
+  float* dw = t->grads + L.w;
+  if (splits > 1) TR_TRY(t, cudaMemsetAsync(dw, 0, static_cast<size_t>(taps) * L.cin * L.cout * sizeof(float), t->stream));
+  const dim3 grid((L.cout + 31) / 32, (L.cin + 31) / 32, taps * splits);
+  caz::train::conv_wgrad_fp32_kernel<<<grid, 256, 0, t->stream>>>(x, dz, batch, L.cin, L.cout, L.k, splits, dw);
+  return tr_launch_ok(t, "conv_wgrad_fp32_kernel");
+}
+
+// din = conv(dz, rot180(w)^T) (+ add): the input gradient of a "same" convolution
+int tr_dgrad_fp32(caz_trainer* t, const float* dz, const TrainConv& L, const float* add, float* din, int batch) {
+  const size_t total = static_cast<size_t>(L.k) * L.k * L.cin * L.cout;
+  caz::train::flip_weights_kernel<<<blocks_for(total), 256, 0, t->stream>>>(t->params + L.w, t->w_flip, L.k * L.k, L.cin, L.cout);
+  int rc;
+  if ((rc = tr_launch_ok(t, "flip_weights_kernel"))) return rc;
+  return tr_conv_fp32(t, dz, t->w_flip, add, din, batch, L.k, L.cout, L.cin);
+}
+
+int tr_forward_backward(caz_trainer* t, int batch) {
+  const caz_arch& a = t->arch;
+  const int rows = batch * 64, F = a.filters, pf = a.policy_filters, vf = a.value_filters, nl = a.n_labels, vfc = a.value_fc;
+  const int kp = pf * 64, kv = vf * 64;
+  int rc;
+  float* P = t->params;
+  float* G = t->grads;
+  // ---- forward ----
+  {
+    const size_t smem = static_cast<size_t>(a.input_planes) * 65 * sizeof(float);
+    caz::pack_planes_kernel<float><<<batch, 256, smem, t->stream>>>(t->planes, t->x0, batch, a.input_planes, a.input_planes);
+    if ((rc = tr_launch_ok(t, "pack_planes_kernel"))) return rc;
+  }
+  const int n_convs = static_cast<int>(t->convs.size());
+  for (int l = 0; l < n_convs; ++l) {
+    TrainConv& L = t->convs[l];
+    const float* in = l == 0 ? t->x0 : t->convs[l - 1].a;
+    if ((rc = tr_conv_fp32(t, in, P + L.w, nullptr, L.z, batch, L.k, L.cin, L.cout))) return rc;
+    const bool conv2 = l > 0 && (l & 1) == 0;
+    if ((rc = tr_bn_forward(t, L, conv2 ? t->convs[l - 2].a : nullptr, rows))) return rc;
+  }
+  const float* top = t->convs[n_convs - 1].a;
+  // heads' 1x1 convolutions as GEMMs over the rows
+  if ((rc = tr_gemm(t, top, F, 1, P + t->pconv.w, pf, 1, nullptr, t->pconv.z, rows, pf, F))) return rc;
+  if ((rc = tr_bn_forward(t, t->pconv, nullptr, rows))) return rc;
+  if ((rc = tr_gemm(t, top, F, 1, P + t->vconv.w, vf, 1, nullptr, t->vconv.z, rows, vf, F))) return rc;
+  if ((rc = tr_bn_forward(t, t->vconv, nullptr, rows))) return rc;
+  caz::train::flatten_kernel<<<blocks_for(static_cast<size_t>(rows) * pf), 256, 0, t->stream>>>(t->pconv.a, t->featp, batch, pf, 0);
+  caz::train::flatten_kernel<<<blocks_for(static_cast<size_t>(rows) * vf), 256, 0, t->stream>>>(t->vconv.a, t->featv, batch, vf, 0);
+  if ((rc = tr_launch_ok(t, "flatten_kernel"))) return rc;
+  if ((rc = tr_gemm(t, t->featp, kp, 1, P + t->pfc_w, nl, 1, P + t->pfc_b, t->logits, batch, nl, kp))) return rc;
+  if ((rc = tr_gemm(t, t->featv, kv, 1, P + t->vfc1_w, vfc, 1, P + t->vfc1_b, t->hid, batch, vfc, kv, 1))) return rc;
+  if ((rc = tr_gemm(t, t->hid, vfc, 1, P + t->vfc2_w, 1, 1, P + t->vfc2_b, t->vpre, batch, 1, vfc))) return rc;
+  // ---- losses and their gradients ----
+  TR_TRY(t, cudaMemsetAsync(t->loss_acc, 0, 4 * sizeof(double), t->stream));
+  caz::train::loss_kernel<<<batch, 256, 0, t->stream>>>(t->logits, t->policy_t, t->vpre, t->value_t, nl, t->cfg.policy_loss_weight, t->cfg.value_loss_weight,
+                                                        batch, t->dlogits, t->dvpre, t->probs, t->vout, t->loss_acc);
+  if ((rc = tr_launch_ok(t, "loss_kernel"))) return rc;
+  caz::train::l2_sum_kernel<<<148, 256, 0, t->stream>>>(P, t->seg, t->n_params, t->loss_acc + 2);
+  if ((rc = tr_launch_ok(t, "l2_sum_kernel"))) return rc;
+  // ---- backward: heads ----
+  // policy Dense: dW = featp^T . dlogits, db = column sums, dfeatp = dlogits . W^T
+  if ((rc = tr_gemm(t, t->featp, 1, kp, t->dlogits, nl, 1, nullptr, G + t->pfc_w, kp, nl, batch))) return rc;
+  caz::train::column_sum_kernel<<<(nl + 127) / 128, 128, 0, t->stream>>>(t->dlogits, batch, nl, G + t->pfc_b);
+  if ((rc = tr_gemm(t, t->dlogits, nl, 1, P + t->pfc_w, 1, nl, nullptr, t->dfeatp, batch, kp, nl))) return rc;
+  // value head: Dense(1, tanh) <- Dense(vfc, relu)
+  if ((rc = tr_gemm(t, t->hid, 1, vfc, t->dvpre, 1, 1, nullptr, G + t->vfc2_w, vfc, 1, batch))) return rc;
+  caz::train::column_sum_kernel<<<1, 32, 0, t->stream>>>(t->dvpre, batch, 1, G + t->vfc2_b);
+  if ((rc = tr_gemm(t, t->dvpre, 1, 1, P + t->vfc2_w, 1, 1, nullptr, t->dhid, batch, vfc, 1))) return rc;
+  caz::train::relu_backward_kernel<<<blocks_for(static_cast<size_t>(batch) * vfc), 256, 0, t->stream>>>(t->hid, t->dhid, static_cast<size_t>(batch) * vfc);
+  if ((rc = tr_gemm(t, t->featv, 1, kv, t->dhid, vfc, 1, nullptr, G + t->vfc1_w, kv, vfc, batch))) return rc;
+  caz::train::column_sum_kernel<<<(vfc + 127) / 128, 128, 0, t->stream>>>(t->dhid, batch, vfc, G + t->vfc1_b);
+  if ((rc = tr_gemm(t, t->dhid, vfc, 1, P + t->vfc1_w, 1, vfc, nullptr, t->dfeatv, batch, kv, vfc))) return rc;
+  if ((rc = tr_launch_ok(t, "head backward"))) return rc;
+  // un-flatten, BN + ReLU backward of the head convolutions, their weight gradients and the gradient wrt the tower's output
+  caz::train::flatten_kernel<<<blocks_for(static_cast<size_t>(rows) * pf), 256, 0, t->stream>>>(t->dap, t->dfeatp, batch, pf, 1);
+  caz::train::flatten_kernel<<<blocks_for(static_cast<size_t>(rows) * vf), 256, 0, t->stream>>>(t->dav, t->dfeatv, batch, vf, 1);
+  if ((rc = tr_bn_backward(t, t->pconv, t->dap, t->dzp, nullptr, 0, rows))) return rc;
+  if ((rc = tr_bn_backward(t, t->vconv, t->dav, t->dzv, nullptr, 0, rows))) return rc;
+  const int hsplit = 32;   // the reduction runs over all rows
+  if ((rc = tr_gemm(t, top, 1, F, t->dzp, pf, 1, nullptr, G + t->pconv.w, F, pf, rows, 0, hsplit))) return rc;
+  if ((rc = tr_gemm(t, top, 1, F, t->dzv, vf, 1, nullptr, G + t->vconv.w, F, vf, rows, 0, hsplit))) return rc;
+  float* dcur = t->d_a;   // gradient wrt the activation of the layer being processed
+  float* dalt = t->d_b;
+  if ((rc = tr_gemm(t, t->dzp, pf, 1, P + t->pconv.w, 1, pf, nullptr, dcur, rows, F, pf))) return rc;
+  {
+    const dim3 grid((F + 31) / 32, (rows + 31) / 32, 1);   // += the value head's share
+    caz::train::gemm_kernel<<<grid, 256, 0, t->stream>>>(t->dzv, vf, 1, P + t->vconv.w, 1, vf, nullptr, dcur, rows, F, vf, 1, 0);
+    if ((rc = tr_launch_ok(t, "gemm_kernel (accumulate)"))) return rc;
+  }
+  // ---- backward: tower ----
+  for (int l = n_convs - 1; l >= 0; --l) {
+    TrainConv& L = t->convs[l];
+    const bool conv2 = l > 0 && (l & 1) == 0, conv1 = (l & 1) == 1;
+    // conv2: the Add hands dy to the block's input as well (kept in d_skip until conv1's input gradient is formed)
+    if ((rc = tr_bn_backward(t, L, dcur, t->dz, conv2 ? t->d_skip : nullptr, 0, rows))) return rc;
+    const float* in = l == 0 ? t->x0 : t->convs[l - 1].a;
+    if ((rc = tr_wgrad_fp32(t, in, t->dz, batch, L))) return rc;
+    if (l == 0) break;
+    if ((rc = tr_dgrad_fp32(t, t->dz, L, conv1 ? t->d_skip : nullptr, dalt, batch))) return rc;
+    std::swap(dcur, dalt);
+  }
+  return CAZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void caz_train_destroy(caz_trainer* t) {
+  if (!t) return;
+  cudaSetDevice(t->device);
+  if (t->stream) cudaStreamSynchronize(t->stream);
+  std::vector<void*> ptrs = {t->params, t->adam_m, t->adam_v, t->seg, t->x0, t->planes, t->policy_t, t->value_t, t->featp, t->logits, t->dlogits,
+                             t->probs, t->featv, t->hid, t->vpre, t->vout, t->dvpre, t->dhid, t->dfeatp, t->dfeatv, t->d_a, t->d_b, t->d_skip, t->dz,
+                             t->dzp, t->dzv, t->dap, t->dav, t->w_flip, t->zero_bias, t->partial, t->loss_acc};
+  if (!t->grads_external) ptrs.push_back(t->grads);
+  auto free_conv = [&](TrainConv& L) { ptrs.push_back(L.z); ptrs.push_back(L.a); ptrs.push_back(L.mean); ptrs.push_back(L.invstd); };
+  for (auto& L : t->convs) free_conv(L);
+  free_conv(t->pconv);
+  free_conv(t->vconv);
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (t->stream) cudaStreamDestroy(t->stream);
+  delete t;
+}
+
+const char* caz_train_last_error(const caz_trainer* t) {
+  if (t) return t->err.c_str();
+  return caz_last_error(nullptr);
+}
+
+int64_t caz_train_param_count(const caz_arch* arch) {
+  if (!arch) return 0;
+  const caz_arch& a = *arch;
+  int64_t n = (int64_t)a.stem_kernel * a.stem_kernel * a.input_planes * a.filters + 4 * a.filters;
+  n += (int64_t)2 * a.res_blocks * ((int64_t)a.block_kernel * a.block_kernel * a.filters * a.filters + 4 * a.filters);
+  n += (int64_t)a.filters * a.policy_filters + 4 * a.policy_filters + (int64_t)a.policy_filters * 64 * a.n_labels + a.n_labels;
+  n += (int64_t)a.filters * a.value_filters + 4 * a.value_filters + (int64_t)a.value_filters * 64 * a.value_fc + a.value_fc + a.value_fc + 1;
+  return n;
+}
+
+int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensors, int32_t device, int32_t precision,
+                     int32_t max_batch, const caz_train_config* cfg, float* d_grads, caz_trainer** out) {
+  if (!arch || !tensors || !out || !cfg) return tfail(nullptr, CAZ_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const caz_arch& a = *arch;
+  if (precision != CAZ_PRECISION_FP32) return tfail(nullptr, CAZ_ERR_INVALID, "caz_train_create: only CAZ_PRECISION_FP32 is implemented");
+  if (max_batch < 1 || n_tensors != expected_tensor_count(a)) return tfail(nullptr, CAZ_ERR_INVALID, "caz_train_create: bad batch size or tensor count");
+  if (a.policy_filters + a.value_filters > caz::HEAD_MAX_F || (a.stem_kernel & 1) == 0 || (a.block_kernel & 1) == 0 || a.stem_kernel > 7 || a.block_kernel > 7)
+    return tfail(nullptr, CAZ_ERR_INVALID, "architecture outside the supported envelope");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    return tfail(nullptr, CAZ_ERR_NO_DEVICE, fmt("no CUDA device %d; this library has no CPU path", device));
+  caz_trainer* t = new caz_trainer();
+  t->arch = a;
+  t->cfg = *cfg;
+  t->device = device;
+  t->precision = precision;
+  t->max_batch = max_batch;
+  auto bail = [&](int rc) {
+    tfail(nullptr, rc, t->err);
+    caz_train_destroy(t);
+    return rc;
+  };
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    t->err = "cudaSetDevice / cudaStreamCreate failed";
+    return bail(CAZ_ERR_CUDA);
+  }
+  // ---- flat parameter layout in the tensor order of caz_create ----
+  std::vector<uint8_t> seg;
+  std::vector<float> host;
+  int ti = 0;
+  auto take = [&](int64_t expect, uint8_t kind) -> size_t {   // returns the offset, SIZE_MAX on a size mismatch
+    if (tensors[ti].numel != expect) return SIZE_MAX;
+    const size_t off = host.size();
+    host.insert(host.end(), tensors[ti].data, tensors[ti].data + expect);
+    seg.insert(seg.end(), static_cast<size_t>(expect), kind);
+    t->tensor_off.push_back(off);
+    t->tensor_len.push_back(static_cast<size_t>(expect));
+    ++ti;
+    return off;
+  };
+  bool ok = true;
+  auto take_conv = [&](TrainConv& L, int k, int cin, int cout) {
+    L.k = k; L.cin = cin; L.cout = cout;
+    ok &= (L.w = take((int64_t)k * k * cin * cout, 2)) != SIZE_MAX;
+    ok &= (L.gamma = take(cout, 1)) != SIZE_MAX;
+    ok &= (L.beta = take(cout, 1)) != SIZE_MAX;
+    ok &= (L.mmean = take(cout, 0)) != SIZE_MAX;
+    ok &= (L.mvar = take(cout, 0)) != SIZE_MAX;
+  };
+  t->convs.resize(1 + 2 * a.res_blocks);
+  take_conv(t->convs[0], a.stem_kernel, a.input_planes, a.filters);
+  for (int i = 1; ok && i < (int)t->convs.size(); ++i) take_conv(t->convs[i], a.block_kernel, a.filters, a.filters);
+  if (ok) {
+    take_conv(t->pconv, 1, a.filters, a.policy_filters);
+    ok &= (t->pfc_w = take((int64_t)a.policy_filters * 64 * a.n_labels, 2)) != SIZE_MAX;
+    ok &= (t->pfc_b = take(a.n_labels, 1)) != SIZE_MAX;
+  }
+  if (ok) {
+    take_conv(t->vconv, 1, a.filters, a.value_filters);
+    ok &= (t->vfc1_w = take((int64_t)a.value_filters * 64 * a.value_fc, 2)) != SIZE_MAX;
+    ok &= (t->vfc1_b = take(a.value_fc, 1)) != SIZE_MAX;
+    ok &= (t->vfc2_w = take(a.value_fc, 2)) != SIZE_MAX;
+    ok &= (t->vfc2_b = take(1, 1)) != SIZE_MAX;
+  }
+  if (!ok) { t->err = fmt("tensor %d has an unexpected size", ti); return bail(CAZ_ERR_INVALID); }
+  t->n_params = host.size();
+  int rc;
+#define TC(expr) do { if ((rc = (expr))) return bail(rc); } while (0)
+  TC(tr_alloc(t, &t->params, t->n_params));
+  TC(tr_alloc(t, &t->adam_m, t->n_params));
+  TC(tr_alloc(t, &t->adam_v, t->n_params));
+  TC(tr_alloc(t, &t->seg, t->n_params));
+  if (d_grads) { t->grads = d_grads; t->grads_external = true; }
+  else TC(tr_alloc(t, &t->grads, t->n_params));
+  if (cudaMemcpyAsync(t->params, host.data(), host.size() * 4, cudaMemcpyHostToDevice, t->stream) != cudaSuccess ||
+      cudaMemcpyAsync(t->seg, seg.data(), seg.size(), cudaMemcpyHostToDevice, t->stream) != cudaSuccess ||
+      cudaMemsetAsync(t->grads, 0, t->n_params * 4, t->stream) != cudaSuccess || cudaStreamSynchronize(t->stream) != cudaSuccess) {
+    t->err = "uploading the parameters failed";
+    return bail(CAZ_ERR_CUDA);
+  }
+  // ---- batch-sized buffers ----
+  const size_t B = (size_t)max_batch, R = B * 64, F = (size_t)a.filters;
+  auto alloc_conv = [&](TrainConv& L) -> int {
+    int r;
+    if ((r = tr_alloc(t, &L.z, R * L.cout))) return r;
+    if ((r = tr_alloc(t, &L.a, R * L.cout))) return r;
+    if ((r = tr_alloc(t, &L.mean, (size_t)L.cout))) return r;
+    return tr_alloc(t, &L.invstd, (size_t)L.cout);
+  };
+  for (auto& L : t->convs) TC(alloc_conv(L));
+  TC(alloc_conv(t->pconv));
+  TC(alloc_conv(t->vconv));
+  const size_t kp = (size_t)a.policy_filters * 64, kv = (size_t)a.value_filters * 64;
+  TC(tr_alloc(t, &t->planes, B * a.input_planes * 64));
+  TC(tr_alloc(t, &t->x0, R * a.input_planes));
+  TC(tr_alloc(t, &t->policy_t, B * a.n_labels));
+  TC(tr_alloc(t, &t->value_t, B));
+  TC(tr_alloc(t, &t->featp, B * kp));
+  TC(tr_alloc(t, &t->dfeatp, B * kp));
+  TC(tr_alloc(t, &t->logits, B * a.n_labels));
+  TC(tr_alloc(t, &t->dlogits, B * a.n_labels));
+  TC(tr_alloc(t, &t->probs, B * a.n_labels));
+  TC(tr_alloc(t, &t->featv, B * kv));
+  TC(tr_alloc(t, &t->dfeatv, B * kv));
+  TC(tr_alloc(t, &t->hid, B * a.value_fc));
+  TC(tr_alloc(t, &t->dhid, B * a.value_fc));
+  TC(tr_alloc(t, &t->vpre, B));
+  TC(tr_alloc(t, &t->vout, B));
+  TC(tr_alloc(t, &t->dvpre, B));
+  TC(tr_alloc(t, &t->d_a, R * F));
+  TC(tr_alloc(t, &t->d_b, R * F));
+  TC(tr_alloc(t, &t->d_skip, R * F));
+  TC(tr_alloc(t, &t->dz, R * F));
+  TC(tr_alloc(t, &t->dzp, R * a.policy_filters));
+  TC(tr_alloc(t, &t->dzv, R * a.value_filters));
+  TC(tr_alloc(t, &t->dap, R * a.policy_filters));
+  TC(tr_alloc(t, &t->dav, R * a.value_filters));
+  const size_t wmax = std::max((size_t)a.block_kernel * a.block_kernel * F * F, (size_t)a.stem_kernel * a.stem_kernel * a.input_planes * F);
+  TC(tr_alloc(t, &t->w_flip, wmax));
+  TC(tr_alloc(t, &t->zero_bias, std::max(F, (size_t)a.input_planes) + 64));
+  TC(tr_alloc(t, &t->partial, (size_t)2 * caz::train::STAT_SPLITS * std::max(F, (size_t)64)));
+  TC(tr_alloc(t, &t->loss_acc, (size_t)4));
+#undef TC
+  // the fp32 convolution keeps a zero-padded board of all input channels in shared memory
+  const size_t s3 = (size_t)(8 + a.block_kernel - 1) * (8 + a.block_kernel - 1) * a.filters * 4;
+  const size_t s1 = (size_t)(8 + a.stem_kernel - 1) * (8 + a.stem_kernel - 1) * std::max(a.input_planes, a.filters) * 4;
+  const int need = (int)std::max(s3, s1);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || need > (int)prop.sharedMemPerBlockOptin) {
+    t->err = "board tile does not fit shared memory";
+    return bail(CAZ_ERR_INVALID);
+  }
+  cudaFuncSetAttribute(caz::conv_fp32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+  cudaFuncSetAttribute(caz::conv_fp32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+  cudaFuncSetAttribute(caz::conv_fp32_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+  cudaFuncSetAttribute(caz::conv_fp32_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+  if (cudaStreamSynchronize(t->stream) != cudaSuccess) { t->err = "initialisation failed"; return bail(CAZ_ERR_CUDA); }
+  *out = t;
+  return CAZ_OK;
+}
+
+int caz_train_forward_backward(caz_trainer* t, const float* planes, const float* policy_target, const float* value_target, int32_t batch,
+                               float* losses) {
+  if (!t) return CAZ_ERR_INVALID;
+  if (!planes || !policy_target || !value_target || batch < 1 || batch > t->max_batch)
+    return tfail(t, CAZ_ERR_INVALID, fmt("caz_train_forward_backward: bad argument (batch %d, max_batch %d)", batch, t->max_batch));
+  TR_TRY(t, cudaSetDevice(t->device));
+  const caz_arch& a = t->arch;
+  TR_TRY(t, cudaMemcpyAsync(t->planes, planes, (size_t)batch * a.input_planes * 64 * 4, cudaMemcpyHostToDevice, t->stream));
+  TR_TRY(t, cudaMemcpyAsync(t->policy_t, policy_target, (size_t)batch * a.n_labels * 4, cudaMemcpyHostToDevice, t->stream));
+  TR_TRY(t, cudaMemcpyAsync(t->value_t, value_target, (size_t)batch * 4, cudaMemcpyHostToDevice, t->stream));
+  int rc;
+  if ((rc = tr_forward_backward(t, batch))) return rc;
+  double acc[4];
+  TR_TRY(t, cudaMemcpyAsync(acc, t->loss_acc, sizeof acc, cudaMemcpyDeviceToHost, t->stream));
+  TR_TRY(t, cudaStreamSynchronize(t->stream));
+  const float ce = (float)(acc[0] / batch), mse = (float)(acc[1] / batch), reg = (float)(t->cfg.l2 * acc[2]);
+  t->last_losses[0] = t->cfg.policy_loss_weight * ce + t->cfg.value_loss_weight * mse + reg;
+  t->last_losses[1] = ce;
+  t->last_losses[2] = mse;
+  t->last_losses[3] = reg;
+  if (losses) memcpy(losses, t->last_losses, sizeof t->last_losses);
+  return CAZ_OK;
+}
+
+int caz_train_apply(caz_trainer* t, float grad_scale) {
+  if (!t) return CAZ_ERR_INVALID;
+  TR_TRY(t, cudaSetDevice(t->device));
+  ++t->step;
+  const double b1 = t->cfg.beta_1, b2 = t->cfg.beta_2;
+  const float lr_t = (float)(t->cfg.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)t->step)) / (1.0 - std::pow(b1, (double)t->step)));
+  caz::train::adam_kernel<<<blocks_for(t->n_params), 256, 0, t->stream>>>(t->params, t->grads, t->adam_m, t->adam_v, t->seg, t->n_params, lr_t,
+                                                                       t->cfg.beta_1, t->cfg.beta_2, t->cfg.epsilon, t->cfg.l2, grad_scale);
+  int rc;
+  if ((rc = tr_launch_ok(t, "adam_kernel"))) return rc;
+  TR_TRY(t, cudaStreamSynchronize(t->stream));
+  return CAZ_OK;
+}
+
+int caz_train_read(caz_trainer* t, int32_t what, float* host, int64_t count) {
+  if (!t || !host) return CAZ_ERR_INVALID;
+  if (count != (int64_t)t->n_params) return tfail(t, CAZ_ERR_INVALID, fmt("caz_train_read: expected %lld values", (long long)t->n_params));
+  const float* src = what == 0 ? t->params : (what == 1 ? t->grads : (what == 2 ? t->adam_m : t->adam_v));
+  TR_TRY(t, cudaSetDevice(t->device));
+  TR_TRY(t, cudaStreamSynchronize(t->stream));
+  TR_TRY(t, cudaMemcpy(host, src, (size_t)count * 4, cudaMemcpyDeviceToHost));
+  return CAZ_OK;
+}
+
+int caz_train_read_outputs(caz_trainer* t, int32_t batch, float* policy, float* value) {
+  if (!t || batch < 1 || batch > t->max_batch) return CAZ_ERR_INVALID;
+  TR_TRY(t, cudaSetDevice(t->device));
+  TR_TRY(t, cudaStreamSynchronize(t->stream));
+  if (policy) TR_TRY(t, cudaMemcpy(policy, t->probs, (size_t)batch * t->arch.n_labels * 4, cudaMemcpyDeviceToHost));
+  if (value) TR_TRY(t, cudaMemcpy(value, t->vout, (size_t)batch * 4, cudaMemcpyDeviceToHost));
+  return CAZ_OK;
+}
+
+float* caz_train_grad_device_ptr(caz_trainer* t) { return t ? t->grads : nullptr; }
+int64_t caz_train_num_params(const caz_trainer* t) { return t ? (int64_t)t->n_params : 0; }
+int64_t caz_train_steps(const caz_trainer* t) { return t ? t->step : 0; }
+
+}  // extern "C"

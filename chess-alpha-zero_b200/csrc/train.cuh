@@ -1,0 +1,342 @@
+// CUDA-core kernels of the training step: what Keras runs for
+//   model.compile(Adam(), ['categorical_crossentropy', 'mean_squared_error'], loss_weights=[1.25, 1.0]); model.fit(...)
+// (reference src/chess_zero/worker/optimize.py:79-103) on the graph of agent/model_chess.py:57-111 -- BatchNormalization in
+// TRAINING mode (batch statistics, moving averages with momentum 0.99), l2(1e-4) on every Conv2D / Dense kernel.
+//
+// Everything here is fp32 on row-major NHWC tensors [rows = batch * 64][channels]; the convolutions themselves are
+// conv_fp32_kernel (fp32 build) or the tcgen05 implicit GEMM (16-bit builds), called from caz_train.inc.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels_simt.cuh"
+
+namespace caz {
+namespace train {
+
+constexpr int STAT_SPLITS = 64;   // row splits of the per-channel reductions (partials are summed in a fixed order)
+
+// ---- per-channel sums over the rows: partial[split][c] = sum over the split's rows of f(row, c) -------------------------
+// mode 0: (sum z, sum z^2)                                -> BatchNormalization batch statistics
+// mode 1: dy = da * (a > 0);  (sum dy, sum dy * xhat)     -> BatchNormalization backward, xhat = (z - mean) * invstd
+// out: partial[2][STAT_SPLITS][c] (double)
+__global__ void __launch_bounds__(256)
+channel_sums_kernel(int mode, const float* __restrict__ z, const float* __restrict__ a, const float* __restrict__ da,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, int rows, int c,
+                    double* __restrict__ partial) {
+  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int sub = threadIdx.x >> 5;   // 8 row lanes
+  const int split = blockIdx.y;
+  const int per = (rows + STAT_SPLITS - 1) / STAT_SPLITS;
+  const int r0 = split * per, r1 = min(rows, r0 + per);
+  double s0 = 0.0, s1 = 0.0;
+  if (ch < c) {
+    const float mu = mode ? mean[ch] : 0.0f, is = mode ? invstd[ch] : 0.0f;
+    for (int r = r0 + sub; r < r1; r += 8) {
+      const size_t i = static_cast<size_t>(r) * c + ch;
+      if (mode == 0) {
+        const float v = z[i];
+        s0 += v;
+        s1 += static_cast<double>(v) * v;
+      } else {
+        const float dy = a[i] > 0.0f ? da[i] : 0.0f;
+        s0 += dy;
+        s1 += static_cast<double>(dy) * ((z[i] - mu) * is);
+      }
+    }
+  }
+  __shared__ double sh[2][8][32];
+  sh[0][sub][threadIdx.x & 31] = s0;
+  sh[1][sub][threadIdx.x & 31] = s1;
+  __syncthreads();
+  if (sub == 0 && ch < c) {
+    for (int k = 1; k < 8; ++k) { s0 += sh[0][k][threadIdx.x]; s1 += sh[1][k][threadIdx.x]; }
+    partial[(0 * STAT_SPLITS + split) * c + ch] = s0;
+    partial[(1 * STAT_SPLITS + split) * c + ch] = s1;
+  }
+}
+
+// Batch statistics from the partial sums (Keras BatchNormalization in training mode: biased variance, epsilon inside the
+// square root) and the moving-average update  moving = moving * momentum + batch * (1 - momentum)  (keras 2.0.8
+// normalization.py: K.moving_average_update with the biased batch variance).
+__global__ void bn_finish_stats_kernel(const double* __restrict__ partial, int rows, int c, float eps, float momentum,
+                                       float* __restrict__ mean, float* __restrict__ invstd,
+                                       float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int k = 0; k < STAT_SPLITS; ++k) { s0 += partial[(0 * STAT_SPLITS + k) * c + ch]; s1 += partial[(1 * STAT_SPLITS + k) * c + ch]; }
+  const double mu = s0 / rows;
+  double var = s1 / rows - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[ch] = static_cast<float>(mu);
+  invstd[ch] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  if (moving_mean) {
+    moving_mean[ch] = moving_mean[ch] * momentum + static_cast<float>(mu) * (1.0f - momentum);
+    moving_var[ch] = moving_var[ch] * momentum + static_cast<float>(var) * (1.0f - momentum);
+  }
+}
+
+// a = relu(gamma * (z - mean) * invstd + beta (+ skip));  optional 16-bit NHWC copy for the tensor-core convolutions
+template <typename H>
+__global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ skip, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const float* __restrict__ mean,
+                                const float* __restrict__ invstd, size_t total, int c, float* __restrict__ a,
+                                H* __restrict__ a16) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = static_cast<int>(i % c);
+  float v = gamma[ch] * ((z[i] - mean[ch]) * invstd[ch]) + beta[ch];
+  if (skip) v += skip[i];
+  v = fmaxf(v, 0.0f);
+  a[i] = v;
+  if (a16) a16[i] = from_f32<H>(v);
+}
+
+// BatchNormalization backward (training mode) through the ReLU in front of it:
+//   dy = da * (a > 0);  dz = gamma * invstd * (dy - sum_dy / M - xhat * sum_dyx / M);  dgamma = sum_dyx;  dbeta = sum_dy
+// dskip (conv2 of a residual block): the Add passes dy on to the block's input.  `dskip_accumulate`: add instead of store.
+template <typename H>
+__global__ void bn_backward_kernel(const float* __restrict__ z, const float* __restrict__ a, const float* __restrict__ da,
+                                   const float* __restrict__ gamma, const float* __restrict__ mean,
+                                   const float* __restrict__ invstd, const double* __restrict__ partial, int rows, int c,
+                                   float* __restrict__ dz, H* __restrict__ dz16, float* __restrict__ dskip,
+                                   int dskip_accumulate) {
+  const size_t total = static_cast<size_t>(rows) * c;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = static_cast<int>(i % c);
+  // (every thread re-sums its channel's 64 partials from L1/L2: 128 loads against one row element -- the kernel is tiny)
+  double s0 = 0.0, s1 = 0.0;
+  for (int k = 0; k < STAT_SPLITS; ++k) { s0 += partial[(0 * STAT_SPLITS + k) * c + ch]; s1 += partial[(1 * STAT_SPLITS + k) * c + ch]; }
+  const float dy = a[i] > 0.0f ? da[i] : 0.0f;
+  const float xhat = (z[i] - mean[ch]) * invstd[ch];
+  const float v = gamma[ch] * invstd[ch] * (dy - static_cast<float>(s0 / rows) - xhat * static_cast<float>(s1 / rows));
+  dz[i] = v;
+  if (dz16) dz16[i] = from_f32<H>(v);
+  if (dskip) dskip[i] = dskip_accumulate ? dskip[i] + dy : dy;
+}
+
+// dgamma / dbeta from the partial sums of channel_sums_kernel mode 1
+__global__ void bn_param_grads_kernel(const double* __restrict__ partial, int c, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int k = 0; k < STAT_SPLITS; ++k) { s0 += partial[(0 * STAT_SPLITS + k) * c + ch]; s1 += partial[(1 * STAT_SPLITS + k) * c + ch]; }
+  dbeta[ch] = static_cast<float>(s0);
+  dgamma[ch] = static_cast<float>(s1);
+}
+
+// ---- a small general GEMM on the CUDA cores (heads' 1x1 convolutions and Dense layers, forward and backward) ----------
+//   C[i][j] (+)= sum_k A(i, k) * B(k, j) (+ bias[j]),  A(i, k) = a[i * a_si + k * a_sk],  B(k, j) = b[k * b_sk + j * b_sj]
+// 32 x 32 output tile per block, K in slabs of 32; gridDim.z splits K (the partial sums are added with atomicAdd into a
+// zeroed or accumulated C: pass accumulate = 1 and clear C first when gridDim.z > 1).
+__global__ void __launch_bounds__(256)
+gemm_kernel(const float* __restrict__ a, long a_si, long a_sk, const float* __restrict__ b, long b_sk, long b_sj,
+            const float* __restrict__ bias, float* __restrict__ c, int m, int n, int k, int accumulate, int relu) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // ty 0..7: rows ty, ty+8, ty+16, ty+24
+  const int kz = gridDim.z, kper = ((k + kz - 1) / kz + 31) / 32 * 32;
+  const int k0 = blockIdx.z * kper, k1 = min(k, k0 + kper);
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int kk = k0; kk < k1; kk += 32) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = i0 + ty + r * 8, ka = kk + tx;
+      sa[ty + r * 8][tx] = (i < m && ka < k1) ? a[i * a_si + ka * a_sk] : 0.0f;
+      const int kb = kk + ty + r * 8, j = j0 + tx;
+      sb[ty + r * 8][tx] = (kb < k1 && j < n) ? b[kb * b_sk + j * b_sj] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) {
+      const float bv = sb[q][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(sa[ty + r * 8][q], bv, acc[r]);
+    }
+    __syncthreads();
+  }
+  const int j = j0 + tx;
+  if (j >= n) return;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty + r * 8;
+    if (i >= m) continue;
+    float v = acc[r];
+    float* dst = c + static_cast<size_t>(i) * n + j;
+    if (kz > 1) { atomicAdd(dst, v); continue; }
+    if (bias) v += bias[j];
+    if (accumulate) v += *dst;
+    if (relu) v = fmaxf(v, 0.0f);
+    *dst = v;
+  }
+}
+
+// column sums of a row-major matrix (Dense bias gradients): out[j] = sum_i x[i][j]
+__global__ void column_sum_kernel(const float* __restrict__ x, int m, int n, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double s = 0.0;
+  for (int i = 0; i < m; ++i) s += x[static_cast<size_t>(i) * n + j];
+  out[j] = static_cast<float>(s);
+}
+
+// Flatten of a channels_first tensor (model_chess.py:81,90): head activations [b*64 + s][f] <-> features [b][f*64 + s]
+__global__ void flatten_kernel(float* __restrict__ rows_f, float* __restrict__ feat, int batch, int f, int to_rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * 64 * f) return;
+  const int b = i / (64 * f), rem = i - b * 64 * f, ch = rem / 64, s = rem - ch * 64;
+  const size_t r = (static_cast<size_t>(b) * 64 + s) * f + ch, q = static_cast<size_t>(b) * f * 64 + ch * 64 + s;
+  if (to_rows) rows_f[r] = feat[q];
+  else feat[q] = rows_f[r];
+}
+
+// ---- losses (optimize.py:100-103; keras losses on the TensorFlow backend) -------------------------------------------
+// policy: softmax over the logits; categorical_crossentropy = -sum_j t_j log(clip(p_j / sum p, 1e-7, 1 - 1e-7));
+//         d loss / d logits = p * sum_j t_j - t   (exact wherever the clip is inactive), scaled by weight / batch
+// value : v = tanh(pre);  mean_squared_error = (v - t)^2;  d / d pre = 2 (v - t) (1 - v^2), scaled by weight / batch
+// One block per position.  loss_acc[0] += CE, loss_acc[1] += MSE (sums over the batch, double).
+__global__ void __launch_bounds__(256)
+loss_kernel(const float* __restrict__ logits, const float* __restrict__ policy_t, const float* __restrict__ vpre,
+            const float* __restrict__ value_t, int n_labels, float w_policy, float w_value, int batch,
+            float* __restrict__ dlogits, float* __restrict__ dvpre, float* __restrict__ probs, float* __restrict__ vout,
+            double* __restrict__ loss_acc) {
+  __shared__ float s_red[8];
+  __shared__ float s_bc;
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* row = logits + static_cast<size_t>(b) * n_labels;
+  const float* trow = policy_t + static_cast<size_t>(b) * n_labels;
+  auto block_reduce = [&](float v, bool is_max) -> float {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float u = __shfl_xor_sync(0xffffffffu, v, o);
+      v = is_max ? fmaxf(v, u) : v + u;
+    }
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float r = s_red[0];
+      for (int k = 1; k < 8; ++k) r = is_max ? fmaxf(r, s_red[k]) : r + s_red[k];
+      s_bc = r;
+    }
+    __syncthreads();
+    return s_bc;
+  };
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < n_labels; j += 256) mx = fmaxf(mx, row[j]);
+  mx = block_reduce(mx, true);
+  float se = 0.0f, st = 0.0f;
+  for (int j = threadIdx.x; j < n_labels; j += 256) { se += expf(row[j] - mx); st += trow[j]; }
+  se = block_reduce(se, false);
+  st = block_reduce(st, false);
+  float ce = 0.0f;
+  for (int j = threadIdx.x; j < n_labels; j += 256) {
+    const float p = expf(row[j] - mx) / se, t = trow[j];
+    if (probs) probs[static_cast<size_t>(b) * n_labels + j] = p;
+    dlogits[static_cast<size_t>(b) * n_labels + j] = (p * st - t) * (w_policy / batch);
+    if (t != 0.0f) ce -= t * logf(fminf(fmaxf(p, 1e-7f), 1.0f - 1e-7f));
+  }
+  ce = block_reduce(ce, false);
+  if (threadIdx.x == 0) {
+    const float v = tanhf(vpre[b]), t = value_t[b];
+    if (vout) vout[b] = v;
+    dvpre[b] = 2.0f * (v - t) * (1.0f - v * v) * (w_value / batch);
+    atomicAdd(&loss_acc[0], static_cast<double>(ce));
+    atomicAdd(&loss_acc[1], static_cast<double>((v - t) * (v - t)));
+  }
+}
+
+// dh *= (h > 0)   (ReLU backward of the value head's hidden layer)
+__global__ void relu_backward_kernel(const float* __restrict__ h, float* __restrict__ dh, size_t total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < total && h[i] <= 0.0f) dh[i] = 0.0f;
+}
+
+// ---- weight gradient of a k x k "same" convolution on the CUDA cores (fp32 build) ---------------------------------------
+//   dw[tap][ic][oc] = sum over boards b and squares s of  x[b][s + tap][ic] * dz[b][s][oc]      (zero outside the board)
+// grid (oc tiles of 32, ic tiles of 32, taps * splits); a block walks its share of the boards, 64 squares at a time.
+// dw must be zero on entry when splits > 1 (atomicAdd).
+__global__ void __launch_bounds__(256)
+conv_wgrad_fp32_kernel(const float* __restrict__ x, const float* __restrict__ dz, int batch, int cin, int cout, int ksize,
+                       int splits, float* __restrict__ dw) {
+  __shared__ float sx[64][33], sd[64][33];
+  const int oc0 = blockIdx.x * 32, ic0 = blockIdx.y * 32;
+  const int tap = blockIdx.z / splits, split = blockIdx.z - tap * splits;
+  const int pad = (ksize - 1) / 2, dy = tap / ksize - pad, dx = tap % ksize - pad;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // thread: oc = oc0 + tx, ic = ic0 + ty + 8 r
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int b = split; b < batch; b += splits) {
+    // 64 squares x 32 channels of the shifted input and of dz
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int s = ty + q * 8;
+      const int r = (s >> 3) + dy, f = (s & 7) + dx;
+      const bool in = r >= 0 && r < 8 && f >= 0 && f < 8 && ic0 + tx < cin;
+      sx[s][tx] = in ? x[(static_cast<size_t>(b) * 64 + r * 8 + f) * cin + ic0 + tx] : 0.0f;
+      sd[s][tx] = oc0 + tx < cout ? dz[(static_cast<size_t>(b) * 64 + s) * cout + oc0 + tx] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int s = 0; s < 64; ++s) {
+      const float dv = sd[s][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(sx[s][ty + r * 8], dv, acc[r]);
+    }
+    __syncthreads();
+  }
+  if (oc0 + tx >= cout) return;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int ic = ic0 + ty + r * 8;
+    if (ic >= cin) continue;
+    float* dst = dw + (static_cast<size_t>(tap) * cin + ic) * cout + oc0 + tx;
+    if (splits > 1) atomicAdd(dst, acc[r]);
+    else *dst = acc[r];
+  }
+}
+
+// w'[tap'][oc][ic] = w[tap][ic][oc] with tap' the 180-degree rotation of tap: the weights of the INPUT-gradient convolution
+// (dx = conv(dz, w')), in the same [tap][in][out] layout conv_fp32_kernel reads
+__global__ void flip_weights_kernel(const float* __restrict__ w, float* __restrict__ wt, int taps, int cin, int cout) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(taps) * cin * cout;
+  if (i >= total) return;
+  const int oc = static_cast<int>(i % cout);
+  const int ic = static_cast<int>((i / cout) % cin);
+  const int tap = static_cast<int>(i / (static_cast<size_t>(cout) * cin));
+  wt[(static_cast<size_t>(taps - 1 - tap) * cout + oc) * cin + ic] = w[i];
+}
+
+// ---- Adam (keras 2.0.8 optimizers.Adam: lr 1e-3, beta_1 0.9, beta_2 0.999, epsilon 1e-8, decay 0) ----------------------
+//   g += 2 * l2 * p on regularised kernels (d/dp of l2 * sum p^2);  lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);
+//   m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= lr_t * m / (sqrt(v) + eps)
+// seg: per parameter 0 = not trainable (moving statistics), 1 = trainable, 2 = trainable + l2
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            const uint8_t* __restrict__ seg, size_t n, float lr_t, float b1, float b2, float eps, float l2,
+                            float grad_scale) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n || seg[i] == 0) return;
+  float gi = g[i] * grad_scale;
+  if (seg[i] == 2) gi += 2.0f * l2 * p[i];
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+// sum of squares of the l2-regularised parameters (reported as the regularisation part of the loss)
+__global__ void l2_sum_kernel(const float* __restrict__ p, const uint8_t* __restrict__ seg, size_t n, double* __restrict__ out) {
+  double s = 0.0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    if (seg[i] == 2) s += static_cast<double>(p[i]) * p[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+}  // namespace train
+}  // namespace caz

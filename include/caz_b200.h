@@ -237,6 +237,54 @@ int caz_debug_conv_layer(caz_handle* h, int32_t layer, const float* in, const fl
 void* caz_host_alloc(int64_t bytes);
 void caz_host_free(void* p);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Training step: what the reference's `opt` worker runs per batch,
+ *     model.compile(Adam(), ['categorical_crossentropy', 'mean_squared_error'], loss_weights=[1.25, 1.0])
+ *     model.fit(state_ary, [policy_ary, value_ary], batch_size=384, ...)        (worker/optimize.py:79-103)
+ * on the graph of agent/model_chess.py:57-111: BatchNormalization in training mode (batch statistics, moving averages),
+ * l2(1e-4) on every Conv2D / Dense kernel.  A trainer is separate from an evaluator handle; its weights go back
+ * through caz_train_read(what = 0) in the tensor order of caz_create (-> ChessModel.save, caz_reload).
+ * Multi-GPU: one trainer per GPU on its shard of the batch; the flat gradient vector (caz_train_grad_device_ptr, or
+ * caller-provided device memory) is summed over ranks between caz_train_forward_backward and caz_train_apply -- the
+ * Python side does that with torch.distributed.all_reduce (NCCL) -- and caz_train_apply takes 1 / world as grad_scale.
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct caz_trainer caz_trainer;
+
+typedef struct caz_train_config {
+  float learning_rate;      /* 1e-3  keras.optimizers.Adam defaults (keras 2.0.8)        */
+  float beta_1;             /* 0.9                                                        */
+  float beta_2;             /* 0.999                                                      */
+  float epsilon;            /* 1e-8                                                       */
+  float l2;                 /* 1e-4  ModelConfig.l2_reg (configs/normal.py:64)            */
+  float policy_loss_weight; /* 1.25  TrainerConfig.loss_weights (configs/normal.py:57)    */
+  float value_loss_weight;  /* 1.0                                                        */
+  float bn_momentum;        /* 0.99  BatchNormalization default                           */
+} caz_train_config;
+
+/* tensors: the initial weights, same order and layout as caz_create.  precision: CAZ_PRECISION_FP32 (all arithmetic fp32
+ * on the CUDA cores).  d_grads: NULL, or device memory for caz_train_param_count(arch) floats that receives the gradients. */
+int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensors, int32_t device, int32_t precision,
+                     int32_t max_batch, const caz_train_config* cfg, float* d_grads, caz_trainer** out);
+void caz_train_destroy(caz_trainer* t);
+const char* caz_train_last_error(const caz_trainer* t);
+int64_t caz_train_param_count(const caz_arch* arch); /* floats in the flat parameter / gradient vector (moving statistics included) */
+int64_t caz_train_num_params(const caz_trainer* t);
+int64_t caz_train_steps(const caz_trainer* t);       /* caz_train_apply calls so far (Adam's t) */
+/* Forward pass in training mode, losses, backward pass: fills the gradient vector (sum over this batch of the loss
+ * gradients, already divided by `batch`; the l2 term is added in caz_train_apply) and updates the BatchNormalization moving
+ * statistics.  planes: host float32 [batch][18][8][8]; policy_target: host float32 [batch][n_labels]; value_target: host
+ * float32 [batch].  losses (may be NULL): host float32 [4] = total, mean categorical cross-entropy, mean squared error,
+ * l2 term. */
+int caz_train_forward_backward(caz_trainer* t, const float* planes, const float* policy_target, const float* value_target,
+                               int32_t batch, float* losses);
+/* One Adam update from grad_scale * gradient vector (+ 2 * l2 * w on kernels). */
+int caz_train_apply(caz_trainer* t, float grad_scale);
+/* what: 0 parameters, 1 gradients, 2 / 3 Adam first / second moments; host float32 [caz_train_num_params] */
+int caz_train_read(caz_trainer* t, int32_t what, float* host, int64_t count);
+/* softmax policy and tanh value of the last forward pass (training-mode BatchNormalization): host [batch][n_labels], [batch] */
+int caz_train_read_outputs(caz_trainer* t, int32_t batch, float* policy, float* value);
+float* caz_train_grad_device_ptr(caz_trainer* t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,93 @@
+"""The GPU training step (include/caz_b200.h: caz_train_*) against the CPU oracle (oracle/training.py:
+torch autograd in float64, Keras semantics): losses, every gradient tensor, Adam updates and BatchNormalization moving
+averages over several steps.  Needs a B200 (-m gpu)."""
+import numpy as np
+import pytest
+
+import chess_alpha_zero_b200 as caz
+from oracle import encoder as oenc
+from oracle import training as otrain
+from oracle import weights as oweights
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, seed):
+    fens = oenc.synthetic_fens(n, seed=seed)
+    x = np.stack([oenc.canon_input_planes(f) for f in fens])
+    rng = np.random.RandomState(seed)
+    pt = np.zeros((n, 1968), np.float32)
+    for i in range(n):                                               # visit-count-like targets on 5..40 moves
+        k = rng.randint(5, 41)
+        idx = rng.permutation(1968)[:k]
+        pt[i, idx] = rng.dirichlet([0.5] * k)
+    vt = rng.choice([-1.0, 0.0, 1.0], size=n).astype(np.float32) * rng.uniform(0.2, 1.0, size=n).astype(np.float32)
+    return x, pt, vt
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+@pytest.mark.parametrize("variant", [dict(filters=64, blocks=2), dict(filters=32, blocks=1, stem_k=3, value_filters=1)])
+def test_gradients_and_losses_match_the_oracle(variant):
+    cfg = oweights.keras_config(**variant)
+    w = oweights.synth_weights(cfg, seed=2, recipe="randomized")
+    x, pt, vt = _data(24, seed=5)
+    ora = otrain.OracleTrainer(cfg, w)
+    want, _, want_g, (wp, wv), _ = ora.gradients(x, pt, vt)
+    tr = caz.Trainer(cfg, w, precision="fp32", max_batch=32)
+    got = tr.forward_backward(x, pt, vt)
+    assert abs(got["loss"] - want["total"]) <= 1e-4 * want["total"]
+    assert abs(got["policy_out_loss"] - want["ce"]) <= 1e-4 * want["ce"] and abs(got["value_out_loss"] - want["mse"]) <= 1e-4
+    assert abs(got["l2"] - want["l2"]) <= 1e-5 * want["l2"]
+    p, v = tr.outputs(24)
+    assert np.abs(p - wp).max() <= 1e-5 and np.abs(v - wv).max() <= 1e-5
+    g = tr.gradients()
+    worst = {}
+    for name, ref in want_g.items():
+        worst[name] = _rel(g[name], ref.numpy())
+    bad = {k: v for k, v in worst.items() if v > 1e-3}
+    print("   worst relative gradient error:", max(worst.items(), key=lambda kv: kv[1]))
+    assert not bad, bad
+    tr.close()
+
+
+def test_adam_steps_and_moving_statistics_follow_the_oracle():
+    cfg = oweights.keras_config(filters=64, blocks=2)
+    w = oweights.synth_weights(cfg, seed=4, recipe="randomized")
+    ora = otrain.OracleTrainer(cfg, w)
+    tr = caz.Trainer(cfg, w, precision="fp32", max_batch=32)
+    first = None
+    for step in range(4):
+        x, pt, vt = _data(16 + 4 * step, seed=20 + step)            # ragged batch sizes
+        want = ora.train_on_batch(x, pt, vt)
+        got = tr.train_on_batch(x, pt, vt)
+        first = first or got["loss"]
+        assert abs(got["loss"] - want["total"]) <= 2e-3 * want["total"], (step, got, want)
+    assert tr.steps == 4
+    ww, gw = ora.weights(), tr.weights()
+    # Adam's first steps are ~lr * sign(g): after 4 steps weights moved by up to 4e-3; agreement to a small fraction of that
+    for name in gw:
+        assert np.abs(gw[name] - ww[name]).max() <= 2e-4 + 1e-3 * np.abs(ww[name] - w[name]).max(), name
+    mv = "res1_batchnorm1/moving_variance:0"
+    assert np.abs(gw[mv] - w[mv]).max() > 1e-4                        # the moving statistics did move
+    # the trained weights load into an evaluator: Trainer.weights() -> Evaluator (ChessModel.save / caz_reload path)
+    ev = caz.Evaluator(cfg, gw, precision="fp32", max_batch=16)
+    p, v = ev.predict_on_batch(_data(8, seed=99)[0])
+    assert p.shape == (8, 1968) and np.allclose(p.sum(1), 1, atol=1e-5)
+    ev.close()
+    tr.close()
+
+
+def test_fit_signature_and_loss_goes_down():
+    """model.fit(state_ary, [policy_ary, value_ary], batch_size, epochs, shuffle, validation_split) (optimize.py:88-93)."""
+    cfg = oweights.keras_config(filters=32, blocks=1)
+    w = oweights.synth_weights(cfg, seed=1, recipe="keras_default")
+    x, pt, vt = _data(96, seed=7)
+    x[:, 16] = 0                                                      # (the raw clock plane makes tiny nets unstable)
+    tr = caz.Trainer(cfg, w, precision="fp32", max_batch=32)
+    hist = tr.fit(x, [pt, vt], batch_size=32, epochs=6, shuffle=True, validation_split=0.02, seed=0)
+    assert len(hist["loss"]) == 6 and hist["loss"][-1] < hist["loss"][0]
+    assert tr.steps == 6 * 3                                          # 94 training samples -> 3 batches per epoch
+    tr.close()
