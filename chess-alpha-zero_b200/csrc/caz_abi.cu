@@ -461,7 +461,7 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
                 void* out, float* out_f32, int batch, bool fuse_heads = false) {
   const ConvLayer& L = h->convs[li];
   if (tensor_path(h)) {
-    caz::tc::ConvArgs args;
+    caz::tc::ConvArgs args{};
     args.batch = batch;
     args.num_tiles = (batch + 1) / 2;
     args.ksize = L.k;

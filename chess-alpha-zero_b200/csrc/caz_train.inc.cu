@@ -16,6 +16,11 @@ struct TrainConv {
   size_t w = 0, gamma = 0, beta = 0, mmean = 0, mvar = 0;   // offsets into the flat parameter vector
   float *z = nullptr, *a = nullptr;                         // [rows][cout]: convolution output, activation after BN (+skip) + ReLU
   float *mean = nullptr, *invstd = nullptr;                 // batch statistics of this step
+  // 16-bit builds: fp16 NHWC copy of the activation (A operand of the next layer's forward convolution) and K-major
+  // 16-bit copies of the kernel for the forward (fp16) and the input-gradient (bf16, rotated + transposed) convolutions
+  uint16_t *a16 = nullptr, *wf = nullptr, *wb = nullptr;
+  int cin_pad = 0;
+  CUtensorMap tm_a16, tm_wf, tm_wb;
 };
 
 }  // namespace
@@ -43,6 +48,15 @@ struct caz_trainer {
   float *w_flip = nullptr, *zero_bias = nullptr;
   double *partial = nullptr, *loss_acc = nullptr;
   float last_losses[4] = {0, 0, 0, 0};
+  // 16-bit builds (tensor-core convolutions): forward fp16 x fp16, input and weight gradients bf16 x bf16, fp32 accumulation
+  bool tc = false;
+  int num_sms = 0, nb = 0;                 // nb: max_batch rounded up to 64 (board-minor extent of the weight-gradient operands)
+  uint16_t* x0_16 = nullptr;               // [rows][32] fp16: the stem's input, planes zero-padded to one 64-byte swizzle row
+  uint16_t* dz16 = nullptr;                // [rows][filters] bf16: A operand of the input-gradient convolution
+  // [channels][padded cell][nb] bf16: K-major operands of the weight-gradient GEMM (3x3 layers; the stem's own pitch)
+  __nv_bfloat16 *dzT = nullptr, *aT = nullptr, *dzT_stem = nullptr, *x0T = nullptr;
+  float* wg_partial = nullptr;             // [tap][K split][n_out][n_in] partial products
+  CUtensorMap tm_x0, tm_dz, tm_dzT, tm_dzT_stem, tm_aT, tm_x0T;
 };
 
 namespace {
@@ -103,7 +117,7 @@ int tr_gemm(caz_trainer* t, const float* a, long a_si, long a_sk, const float* b
 // batch statistics of z (and the moving averages), then a = relu(BN(z) (+ skip))
 int tr_bn_forward(caz_trainer* t, TrainConv& L, const float* skip, int rows) {
   const dim3 grid((L.cout + 31) / 32, caz::train::STAT_SPLITS);
-  caz::train::channel_sums_kernel<<<grid, 256, 0, t->stream>>>(0, L.z, nullptr, nullptr, nullptr, nullptr, rows, L.cout, t->partial);
+  caz::train::channel_sums_kernel<<<grid, 256, 0, t->stream>>>(0, L.z, nullptr, nullptr, nullptr, nullptr, nullptr, rows, L.cout, t->partial);
   int rc;
   if ((rc = tr_launch_ok(t, "channel_sums_kernel"))) return rc;
   caz::train::bn_finish_stats_kernel<<<(L.cout + 127) / 128, 128, 0, t->stream>>>(t->partial, rows, L.cout, t->arch.bn_epsilon, t->cfg.bn_momentum, L.mean,
@@ -111,21 +125,23 @@ int tr_bn_forward(caz_trainer* t, TrainConv& L, const float* skip, int rows) {
   if ((rc = tr_launch_ok(t, "bn_finish_stats_kernel"))) return rc;
   const size_t total = static_cast<size_t>(rows) * L.cout;
   caz::train::bn_apply_kernel<__half><<<blocks_for(total), 256, 0, t->stream>>>(L.z, skip, t->params + L.gamma, t->params + L.beta, L.mean, L.invstd, total,
-                                                                                L.cout, L.a, nullptr);
+                                                                                L.cout, L.a, reinterpret_cast<__half*>(L.a16));
   return tr_launch_ok(t, "bn_apply_kernel");
 }
 
 // da (gradient wrt the layer's activation) -> dz (wrt its convolution output), dgamma / dbeta; dskip = gradient passed to the Add's other input
-int tr_bn_backward(caz_trainer* t, TrainConv& L, const float* da, float* dz, float* dskip, int dskip_accumulate, int rows) {
+int tr_bn_backward(caz_trainer* t, TrainConv& L, const float* da, float* dz, float* dskip, int dskip_accumulate, int rows,
+                   const float* da2 = nullptr, uint16_t* dz16 = nullptr) {
   const dim3 grid((L.cout + 31) / 32, caz::train::STAT_SPLITS);
-  caz::train::channel_sums_kernel<<<grid, 256, 0, t->stream>>>(1, L.z, L.a, da, L.mean, L.invstd, rows, L.cout, t->partial);
+  caz::train::channel_sums_kernel<<<grid, 256, 0, t->stream>>>(1, L.z, L.a, da, da2, L.mean, L.invstd, rows, L.cout, t->partial);
   int rc;
   if ((rc = tr_launch_ok(t, "channel_sums_kernel (backward)"))) return rc;
   caz::train::bn_param_grads_kernel<<<(L.cout + 127) / 128, 128, 0, t->stream>>>(t->partial, L.cout, t->grads + L.gamma, t->grads + L.beta);
   if ((rc = tr_launch_ok(t, "bn_param_grads_kernel"))) return rc;
   const size_t total = static_cast<size_t>(rows) * L.cout;
-  caz::train::bn_backward_kernel<__half><<<blocks_for(total), 256, 0, t->stream>>>(L.z, L.a, da, t->params + L.gamma, L.mean, L.invstd, t->partial, rows,
-                                                                                   L.cout, dz, nullptr, dskip, dskip_accumulate);
+  caz::train::bn_backward_kernel<__nv_bfloat16><<<blocks_for(total), 256, 0, t->stream>>>(L.z, L.a, da, da2, t->params + L.gamma, L.mean, L.invstd,
+                                                                                          t->grads + L.beta, t->grads + L.gamma, rows, L.cout, dz, reinterpret_cast<__nv_bfloat16*>(dz16), dskip,
+                                                                                          dskip_accumulate);
   return tr_launch_ok(t, "bn_backward_kernel");
 }
 
@@ -150,6 +166,118 @@ int tr_dgrad_fp32(caz_trainer* t, const float* dz, const TrainConv& L, const flo
   return tr_conv_fp32(t, dz, t->w_flip, add, din, batch, L.k, L.cout, L.cin);
 }
 
+// ---- tensor-core convolutions of the 16-bit builds (conv_tc2_kernel, see conv_tc2.cuh) ------------------------------------
+int tr_tmap(caz_trainer* t, CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+            int row_bytes = 128) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return tfail(t, CAZ_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tfail(t, CAZ_ERR_CUDA, fmt("cuTensorMapEncodeTiled failed with CUresult %d", (int)r));
+  return CAZ_OK;
+}
+
+// halo view of 16-bit NHWC rows [boards][8][8][c] (see make_halo_tmap)
+int tr_halo_tmap(caz_trainer* t, CUtensorMap* m, void* base, int c, int k, int boards, int row_bytes = 128) {
+  const cuuint32_t hw = 8 + k - 1;
+  cuuint64_t dims[4] = {(cuuint64_t)c, 8, (cuuint64_t)boards, 8};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 128, (cuuint64_t)c * 16};
+  cuuint32_t box[4] = {(cuuint32_t)row_bytes / 2, hw, 2, hw};
+  return tr_tmap(t, m, base, 4, dims, strides, box, row_bytes);
+}
+
+// K-major matrix [rows][kdim] 16-bit, boxes of (row_bytes / 2) x box_rows
+int tr_kmajor_tmap(caz_trainer* t, CUtensorMap* m, void* base, size_t kdim, int rows, int box_rows, int row_bytes = 128) {
+  cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kdim * 2};
+  cuuint32_t box[2] = {(cuuint32_t)row_bytes / 2, (cuuint32_t)box_rows};
+  return tr_tmap(t, m, base, 2, dims, strides, box, row_bytes);
+}
+
+int tr_launch_tc(caz_trainer* t, const CUtensorMap& tm_a, const CUtensorMap& tm_b, caz::tc::ConvArgs& args, int work, const char* what) {
+  args.err_flag = nullptr;
+  const int max_pairs = t->num_sms / 2;
+  const int grid = 2 * (work < max_pairs ? work : max_pairs);
+  caz::tc2::conv_tc2_kernel<<<grid, caz::tc2::THREADS, caz::tc2::SMEM_BYTES, t->stream>>>(tm_a, tm_b, args);
+  return tr_launch_ok(t, what);
+}
+
+// out[rows][n] = conv(in16, w16): "same" convolution as an implicit GEMM on the tensor cores, raw fp32 row-major output
+int tr_conv_tc(caz_trainer* t, const CUtensorMap& tm_in, const CUtensorMap& tm_w, int ksize, int row_bytes, int kchunks, int n, int fmt,
+               float* out, int batch) {
+  caz::tc::ConvArgs args{};
+  args.batch = batch;
+  args.num_tiles = (batch + 1) / 2;
+  args.ksize = ksize;
+  args.row_bytes = row_bytes;
+  args.kchunks = kchunks;
+  args.n = n;
+  args.bias = t->zero_bias;
+  args.fp16 = fmt;
+  args.n_tiles = 1;
+  args.n_total = n;
+  args.m_rows = batch * 64;
+  args.out_rm = out;
+  return tr_launch_tc(t, tm_in, tm_w, args, (args.num_tiles + 1) / 2, "conv_tc2_kernel (training)");
+}
+
+// dW[tap][ic][oc] of a k x k convolution: x rows [batch * 64][cin] (fp32), dz rows [batch * 64][cout] (fp32) -> t->grads + L.w
+int tr_wgrad_tc(caz_trainer* t, const float* x, const float* dz, int batch, const TrainConv& L, const CUtensorMap& tm_dzT, const CUtensorMap& tm_xT) {
+  const int pad = (L.k - 1) / 2, pitch = 8 + 2 * pad, cells = pitch * pitch, taps = L.k * L.k;
+  const int n_in_pad = L.cin < 32 ? 32 : L.cin;
+  // K-major bf16 operands over the zero-padded board index (transpose_pad_kernel); the halo cells were zeroed at allocation
+  // and are never written (the stem's layout, pitch 8 + 2 pad, has its own buffers)
+  {
+    const dim3 g1(t->nb / 32, (L.cout + 31) / 32, 64), g2(t->nb / 32, (n_in_pad + 31) / 32, 64);
+    const bool stem = &L == &t->convs[0];
+    caz::train::transpose_pad_kernel<<<g1, 256, 0, t->stream>>>(dz, batch, L.cout, L.cout, t->nb, pad, stem ? t->dzT_stem : t->dzT);
+    caz::train::transpose_pad_kernel<<<g2, 256, 0, t->stream>>>(x, batch, L.cin, n_in_pad, t->nb, pad, stem ? t->x0T : t->aT);
+    int rc;
+    if ((rc = tr_launch_ok(t, "transpose_pad_kernel"))) return rc;
+  }
+  const int chunks = cells * t->nb / 64;
+  int splits = (t->num_sms / 2) / taps;
+  if (splits < 1) splits = 1;
+  if (splits > 16) splits = 16;
+  const int cps = (chunks + splits - 1) / splits;
+  caz::tc::ConvArgs args{};
+  args.batch = 4;            // M = 256 rows = four "boards" of 64 output channels (missing ones read as zeros)
+  args.num_tiles = 2;
+  args.ksize = 1;
+  args.row_bytes = 128;
+  args.kchunks = cps;
+  args.n = n_in_pad;
+  args.bias = t->zero_bias;
+  args.fp16 = 0;             // bf16 x bf16
+  args.n_tiles = 1;
+  args.n_total = n_in_pad;
+  args.m_rows = L.cout;
+  args.out_rm = t->wg_partial;
+  args.wg_splits = splits;
+  args.wg_k = L.k;
+  args.wg_pitch = pitch * t->nb;
+  args.wg_dx = t->nb;
+  int rc;
+  if ((rc = tr_launch_tc(t, tm_dzT, tm_xT, args, taps * splits, "conv_tc2_kernel (weight gradient)"))) return rc;
+  const dim3 gr((L.cin + 31) / 32, (L.cout + 31) / 32, taps);
+  caz::train::wgrad_reduce_kernel<<<gr, 256, 0, t->stream>>>(t->wg_partial, taps, splits, L.cout, L.cin, n_in_pad, t->grads + L.w);
+  return tr_launch_ok(t, "wgrad_reduce_kernel");
+}
+
+// the 16-bit copies of the convolution kernels follow the fp32 master weights (after creation and after every update)
+int tr_refresh_weights16(caz_trainer* t) {
+  if (!t->tc) return CAZ_OK;
+  for (size_t l = 0; l < t->convs.size(); ++l) {
+    TrainConv& L = t->convs[l];
+    const size_t total = static_cast<size_t>(L.k) * L.k * L.cin * L.cout;
+    caz::train::pack_conv_weights_kernel<<<blocks_for(total), 256, 0, t->stream>>>(t->params + L.w, L.k * L.k, L.cin, L.cin_pad, L.cout, L.wf, 1,
+                                                                                l == 0 ? nullptr : L.wb, 0);
+  }
+  return tr_launch_ok(t, "pack_conv_weights_kernel");
+}
+
 int tr_forward_backward(caz_trainer* t, int batch) {
   const caz_arch& a = t->arch;
   const int rows = batch * 64, F = a.filters, pf = a.policy_filters, vf = a.value_filters, nl = a.n_labels, vfc = a.value_fc;
@@ -164,10 +292,20 @@ int tr_forward_backward(caz_trainer* t, int batch) {
     if ((rc = tr_launch_ok(t, "pack_planes_kernel"))) return rc;
   }
   const int n_convs = static_cast<int>(t->convs.size());
+  if (t->tc) {
+    const size_t smem = static_cast<size_t>(a.input_planes) * 65 * sizeof(float);
+    caz::pack_planes_kernel<__half><<<batch, 256, smem, t->stream>>>(t->planes, reinterpret_cast<__half*>(t->x0_16), batch, a.input_planes, 32);
+    if ((rc = tr_launch_ok(t, "pack_planes_kernel (fp16)"))) return rc;
+  }
   for (int l = 0; l < n_convs; ++l) {
     TrainConv& L = t->convs[l];
     const float* in = l == 0 ? t->x0 : t->convs[l - 1].a;
-    if ((rc = tr_conv_fp32(t, in, P + L.w, nullptr, L.z, batch, L.k, L.cin, L.cout))) return rc;
+    if (t->tc) {
+      const int fmt = caz::ptx::FMT_A_FP16 | caz::ptx::FMT_B_FP16;
+      if (l == 0) rc = tr_conv_tc(t, t->tm_x0, L.tm_wf, L.k, 64, 1, L.cout, fmt, L.z, batch);
+      else rc = tr_conv_tc(t, t->convs[l - 1].tm_a16, L.tm_wf, L.k, 128, L.cin / 64, L.cout, fmt, L.z, batch);
+      if (rc) return rc;
+    } else if ((rc = tr_conv_fp32(t, in, P + L.w, nullptr, L.z, batch, L.k, L.cin, L.cout))) return rc;
     const bool conv2 = l > 0 && (l & 1) == 0;
     if ((rc = tr_bn_forward(t, L, conv2 ? t->convs[l - 2].a : nullptr, rows))) return rc;
   }
@@ -188,7 +326,7 @@ int tr_forward_backward(caz_trainer* t, int batch) {
   caz::train::loss_kernel<<<batch, 256, 0, t->stream>>>(t->logits, t->policy_t, t->vpre, t->value_t, nl, t->cfg.policy_loss_weight, t->cfg.value_loss_weight,
                                                         batch, t->dlogits, t->dvpre, t->probs, t->vout, t->loss_acc);
   if ((rc = tr_launch_ok(t, "loss_kernel"))) return rc;
-  caz::train::l2_sum_kernel<<<148, 256, 0, t->stream>>>(P, t->seg, t->n_params, t->loss_acc + 2);
+  caz::train::l2_sum_kernel<<<148 * 8, 256, 0, t->stream>>>(P, t->seg, t->n_params, t->loss_acc + 2);
   if ((rc = tr_launch_ok(t, "l2_sum_kernel"))) return rc;
   // ---- backward: heads ----
   // policy Dense: dW = featp^T . dlogits, db = column sums, dfeatp = dlogits . W^T
@@ -224,12 +362,18 @@ int tr_forward_backward(caz_trainer* t, int batch) {
   for (int l = n_convs - 1; l >= 0; --l) {
     TrainConv& L = t->convs[l];
     const bool conv2 = l > 0 && (l & 1) == 0, conv1 = (l & 1) == 1;
-    // conv2: the Add hands dy to the block's input as well (kept in d_skip until conv1's input gradient is formed)
-    if ((rc = tr_bn_backward(t, L, dcur, t->dz, conv2 ? t->d_skip : nullptr, 0, rows))) return rc;
+    // conv2: the Add hands dy to the block's input as well (kept in d_skip until the gradient wrt that input is complete).
+    // fp32 build: conv1's input-gradient convolution adds d_skip itself; 16-bit builds: the layer below reads it as da2.
+    const float* da2 = (t->tc && (l & 1) == 0 && l < n_convs - 1) ? t->d_skip : nullptr;
+    if ((rc = tr_bn_backward(t, L, dcur, t->dz, conv2 ? t->d_skip : nullptr, 0, rows, da2, t->tc ? t->dz16 : nullptr))) return rc;
     const float* in = l == 0 ? t->x0 : t->convs[l - 1].a;
-    if ((rc = tr_wgrad_fp32(t, in, t->dz, batch, L))) return rc;
+    if (t->tc) rc = tr_wgrad_tc(t, in, t->dz, batch, L, l == 0 ? t->tm_dzT_stem : t->tm_dzT, l == 0 ? t->tm_x0T : t->tm_aT);
+    else rc = tr_wgrad_fp32(t, in, t->dz, batch, L);
+    if (rc) return rc;
     if (l == 0) break;
-    if ((rc = tr_dgrad_fp32(t, t->dz, L, conv1 ? t->d_skip : nullptr, dalt, batch))) return rc;
+    if (t->tc) rc = tr_conv_tc(t, t->tm_dz, L.tm_wb, L.k, 128, L.cout / 64, L.cin, 0, dalt, batch);
+    else rc = tr_dgrad_fp32(t, t->dz, L, conv1 ? t->d_skip : nullptr, dalt, batch);
+    if (rc) return rc;
     std::swap(dcur, dalt);
   }
   return CAZ_OK;
@@ -247,7 +391,10 @@ void caz_train_destroy(caz_trainer* t) {
                              t->probs, t->featv, t->hid, t->vpre, t->vout, t->dvpre, t->dhid, t->dfeatp, t->dfeatv, t->d_a, t->d_b, t->d_skip, t->dz,
                              t->dzp, t->dzv, t->dap, t->dav, t->w_flip, t->zero_bias, t->partial, t->loss_acc};
   if (!t->grads_external) ptrs.push_back(t->grads);
-  auto free_conv = [&](TrainConv& L) { ptrs.push_back(L.z); ptrs.push_back(L.a); ptrs.push_back(L.mean); ptrs.push_back(L.invstd); };
+  for (void* p : {(void*)t->x0_16, (void*)t->dz16, (void*)t->dzT, (void*)t->aT, (void*)t->dzT_stem, (void*)t->x0T, (void*)t->wg_partial}) ptrs.push_back(p);
+  auto free_conv = [&](TrainConv& L) {
+    for (void* p : {(void*)L.z, (void*)L.a, (void*)L.mean, (void*)L.invstd, (void*)L.a16, (void*)L.wf, (void*)L.wb}) ptrs.push_back(p);
+  };
   for (auto& L : t->convs) free_conv(L);
   free_conv(t->pconv);
   free_conv(t->vconv);
@@ -276,7 +423,10 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
   if (!arch || !tensors || !out || !cfg) return tfail(nullptr, CAZ_ERR_INVALID, "null argument");
   *out = nullptr;
   const caz_arch& a = *arch;
-  if (precision != CAZ_PRECISION_FP32) return tfail(nullptr, CAZ_ERR_INVALID, "caz_train_create: only CAZ_PRECISION_FP32 is implemented");
+  if (precision != CAZ_PRECISION_FP32 && precision != CAZ_PRECISION_BF16)
+    return tfail(nullptr, CAZ_ERR_INVALID, "caz_train_create: precision must be CAZ_PRECISION_FP32 or CAZ_PRECISION_BF16");
+  if (precision == CAZ_PRECISION_BF16 && (a.filters % 64 != 0 || a.filters > 256 || a.input_planes > 32 || a.block_kernel != 3 || a.stem_kernel > 5))
+    return tfail(nullptr, CAZ_ERR_INVALID, "the tensor-core training build needs filters in {64, 128, 192, 256}, <= 32 input planes, 3x3 blocks and a stem of at most 5x5");
   if (max_batch < 1 || n_tensors != expected_tensor_count(a)) return tfail(nullptr, CAZ_ERR_INVALID, "caz_train_create: bad batch size or tensor count");
   if (a.policy_filters + a.value_filters > caz::HEAD_MAX_F || (a.stem_kernel & 1) == 0 || (a.block_kernel & 1) == 0 || a.stem_kernel > 7 || a.block_kernel > 7)
     return tfail(nullptr, CAZ_ERR_INVALID, "architecture outside the supported envelope");
@@ -408,6 +558,50 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
   cudaFuncSetAttribute(caz::conv_fp32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
   cudaFuncSetAttribute(caz::conv_fp32_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
   cudaFuncSetAttribute(caz::conv_fp32_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+  t->num_sms = prop.multiProcessorCount;
+  if (precision == CAZ_PRECISION_BF16) {
+    if (prop.major != 10) { t->err = "the tensor-core training build needs an sm_100 GPU"; return bail(CAZ_ERR_NO_DEVICE); }
+    t->tc = true;
+    t->nb = (max_batch + 63) / 64 * 64;
+    const int boards = (max_batch + 3) & ~3;
+    const size_t Rp = (size_t)boards * 64;
+#define TC2(expr) do { if ((rc = (expr))) return bail(rc); } while (0)
+    for (size_t l = 0; l < t->convs.size(); ++l) {
+      TrainConv& L = t->convs[l];
+      const int taps = L.k * L.k;
+      L.cin_pad = l == 0 ? 32 : L.cin;
+      TC2(tr_alloc(t, &L.a16, Rp * L.cout));
+      TC2(tr_alloc(t, &L.wf, (size_t)L.cout * taps * L.cin_pad));
+      TC2(tr_halo_tmap(t, &L.tm_a16, L.a16, L.cout, a.block_kernel, boards));
+      TC2(tr_kmajor_tmap(t, &L.tm_wf, L.wf, (size_t)taps * L.cin_pad, L.cout, L.cout / 2, l == 0 ? 64 : 128));
+      if (l > 0) {
+        TC2(tr_alloc(t, &L.wb, (size_t)L.cin * taps * L.cout));
+        TC2(tr_kmajor_tmap(t, &L.tm_wb, L.wb, (size_t)taps * L.cout, L.cin, L.cin / 2));
+      }
+    }
+    TC2(tr_alloc(t, &t->x0_16, Rp * 32));
+    TC2(tr_halo_tmap(t, &t->tm_x0, t->x0_16, 32, a.stem_kernel, boards, 64));
+    TC2(tr_alloc(t, &t->dz16, Rp * F));
+    TC2(tr_halo_tmap(t, &t->tm_dz, t->dz16, (int)F, a.block_kernel, boards));
+    const int pitch3 = 8 + a.block_kernel - 1, pitch_s = 8 + a.stem_kernel - 1;
+    const size_t k3 = (size_t)pitch3 * pitch3 * t->nb, ks = (size_t)pitch_s * pitch_s * t->nb;
+    TC2(tr_alloc(t, &t->dzT, F * k3));
+    TC2(tr_alloc(t, &t->aT, F * k3));
+    TC2(tr_alloc(t, &t->dzT_stem, F * ks));
+    TC2(tr_alloc(t, &t->x0T, (size_t)32 * ks));
+    TC2(tr_halo_tmap(t, &t->tm_dzT, t->dzT, (int)k3, 1, (int)F / 64));
+    TC2(tr_halo_tmap(t, &t->tm_dzT_stem, t->dzT_stem, (int)ks, 1, (int)F / 64));
+    TC2(tr_kmajor_tmap(t, &t->tm_aT, t->aT, k3, (int)F, (int)F / 2));
+    TC2(tr_kmajor_tmap(t, &t->tm_x0T, t->x0T, ks, 32, 16));
+    const size_t taps_max = (size_t)std::max(a.block_kernel * a.block_kernel, a.stem_kernel * a.stem_kernel);
+    TC2(tr_alloc(t, &t->wg_partial, (taps_max * 16 + 16) * F * std::max(F, (size_t)32)));
+#undef TC2
+    if (cudaFuncSetAttribute(caz::tc2::conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tc2::SMEM_BYTES) != cudaSuccess) {
+      t->err = "cudaFuncSetAttribute(conv_tc2_kernel) failed";
+      return bail(CAZ_ERR_CUDA);
+    }
+    if ((rc = tr_refresh_weights16(t))) return bail(rc);
+  }
   if (cudaStreamSynchronize(t->stream) != cudaSuccess) { t->err = "initialisation failed"; return bail(CAZ_ERR_CUDA); }
   *out = t;
   return CAZ_OK;
@@ -447,6 +641,7 @@ int caz_train_apply(caz_trainer* t, float grad_scale) {
                                                                        t->cfg.beta_1, t->cfg.beta_2, t->cfg.epsilon, t->cfg.l2, grad_scale);
   int rc;
   if ((rc = tr_launch_ok(t, "adam_kernel"))) return rc;
+  if ((rc = tr_refresh_weights16(t))) return rc;
   TR_TRY(t, cudaStreamSynchronize(t->stream));
   return CAZ_OK;
 }

@@ -88,6 +88,11 @@ struct ConvArgs {
   int reverse;              // walk the tiles from the last to the first (CTA-pair kernel; see conv_tc2.cuh)
   int l2_prefetch;          // pull the next tile's activations / residual into L2 one tile ahead
   int pdl;                  // launched with programmatic stream serialization (CTA-pair kernel, see conv_tc2.cuh)
+  // Weight-gradient use of the CTA-pair kernel (training, caz_train.inc.cu): out[tap][split] = A[:, K range] . B[:, K range + shift(tap)]^T
+  // with A = dz^T [n_out = 256 rows][K] and B = x^T [n_in rows][K], both over the zero-padded board index K = board * pitch^2 +
+  // (rank + pad) * pitch + file + pad, so that a filter tap is a plain shift of B's K coordinate.  wg_splits > 0 switches it on:
+  // work item t = (tap t / wg_splits, split t % wg_splits) covers K chunks [split * kchunks, (split + 1) * kchunks).
+  int wg_splits, wg_k, wg_pitch, wg_dx;   // K shift of tap (dy, dx): (dy - pad) * wg_pitch + (dx - pad) * wg_dx
   int* err_flag;
 };
 

@@ -64,7 +64,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   const bool leader = rank == 0;
   const int pair0 = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1;
   const int num_pairs = (args.num_tiles + 1) >> 1;
-  const int num_work = num_pairs * args.n_tiles;   // (board-pair pair, N tile) work items
+  const bool wg = args.wg_splits > 0;               // weight-gradient GEMM (see ConvArgs): work items are (tap, K split)
+  const int num_work = wg ? args.wg_k * args.wg_k * args.wg_splits : num_pairs * args.n_tiles;   // else (board-pair pair, N tile)
+  // K-coordinate shift of the B operand for the tap of work item t, and its first K chunk
+  auto wg_shift = [&](int t) -> int { const int tap = t / args.wg_splits; return (tap / args.wg_k - (args.wg_k - 1) / 2) * args.wg_pitch + (tap % args.wg_k - (args.wg_k - 1) / 2) * args.wg_dx; };
+  auto wg_kc0 = [&](int t) -> int { return (t % args.wg_splits) * args.kchunks; };
   // Consecutive layers walk the batch in opposite directions ("snake"): a layer starts with the tiles its predecessor
   // wrote LAST, which are still in the 126 MB L2 -- the activations of a big batch are larger than L2.
   auto pair_of = [&](int t) -> int { const int pr = t / args.n_tiles; return args.reverse ? num_pairs - 1 - pr : pr; };
@@ -123,14 +127,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
     int stage = 0;
     uint32_t phase = 0;
     for (int t = pair0; t < num_work; t += n_pairs_grid) {
-      const int nt = t % args.n_tiles;
+      const int nt = wg ? 0 : t % args.n_tiles;
       for (int kc = 0; kc < args.kchunks; ++kc)
         for (int tap = 0; tap < k * k; ++tap) {
           ptx::mbar_wait(&b_empty[stage], phase ^ 1, args.err_flag, ERR2_PRODUCER_B);
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_expect_tx(&b_full[stage], 2 * b_bytes);   // both CTAs' halves
+            const int col = wg ? (wg_kc0(t) + kc) * kblk + wg_shift(t) : (tap * args.kchunks + kc) * kblk;
             ptx::tma_load_2d_2cta(smem_b + stage * B_STAGE_BYTES, &tmap_w, ptx::mapa_u32(&b_full[stage], 0),
-                                  (tap * args.kchunks + kc) * kblk, nt * args.n + static_cast<int>(rank) * n_half);
+                                  col, nt * args.n + static_cast<int>(rank) * n_half);
           }
           __syncwarp();
           if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
@@ -141,10 +146,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
     int slot = 0;
     uint32_t phase = 0;
     for (int t = pair0; t < num_work; t += n_pairs_grid) {
-      const int tile = 2 * pair_of(t) + static_cast<int>(rank);
+      const int tile = wg ? static_cast<int>(rank) : 2 * pair_of(t) + static_cast<int>(rank);
+      const int kc_first = wg ? wg_kc0(t) : 0;
       // the activations of a big batch come from HBM and the ring holds only two chunk tiles: ask L2 for the NEXT
       // work item's tiles now, a whole tile ahead of need
-      if (args.l2_prefetch && t + n_pairs_grid < num_work && ptx::elect_one()) {
+      if (!wg && args.l2_prefetch && t + n_pairs_grid < num_work && ptx::elect_one()) {
         const int ntile = 2 * pair_of(t + n_pairs_grid) + static_cast<int>(rank);
         for (int kc = 0; kc < args.kchunks; ++kc) ptx::tma_prefetch_4d(&tmap_halo, kc * kblk, -pad, ntile * 2, -pad);
       }
@@ -153,7 +159,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
         ptx::mbar_wait(&a_empty[slot], phase ^ 1, args.err_flag, ERR2_PRODUCER_A);
         if (ptx::elect_one()) {
           if (leader) ptx::mbar_expect_tx(&a_full[slot], 2 * plane_bytes);
-          ptx::tma_load_4d_2cta(smem_a + slot * plane_bytes, &tmap_halo, ptx::mapa_u32(&a_full[slot], 0), kc * kblk,
+          ptx::tma_load_4d_2cta(smem_a + slot * plane_bytes, &tmap_halo, ptx::mapa_u32(&a_full[slot], 0), (kc_first + kc) * kblk,
                                 -pad, tile * 2, -pad);
         }
         __syncwarp();
@@ -210,6 +216,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair0; t < num_work; t += n_pairs_grid) {
+      if (wg) {
+        // one [m_rows][n_total] partial product per (tap, K split), this CTA's 128 of the 256 rows
+        ConvArgs wa = args;
+        wa.out_rm = args.out_rm + static_cast<size_t>(t) * args.m_rows * args.n_total;
+        tc::epilogue_tile(wa, smem_epi, s_bias, s_head, quad, lane, static_cast<int>(rank) * 2,
+                          tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS, &tmem_full[acc], acc_phase,
+                          &tmem_empty[acc], 0u, 0, -1);
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       const int tile = 2 * pair_of(t) + static_cast<int>(rank);
       const int tn = t + n_pairs_grid;
       const int next_tile = tn < num_work ? 2 * pair_of(tn) + static_cast<int>(rank) : -1;

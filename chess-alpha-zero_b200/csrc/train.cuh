@@ -22,7 +22,7 @@ constexpr int STAT_SPLITS = 64;   // row splits of the per-channel reductions (p
 // out: partial[2][STAT_SPLITS][c] (double)
 __global__ void __launch_bounds__(256)
 channel_sums_kernel(int mode, const float* __restrict__ z, const float* __restrict__ a, const float* __restrict__ da,
-                    const float* __restrict__ mean, const float* __restrict__ invstd, int rows, int c,
+                    const float* __restrict__ da2, const float* __restrict__ mean, const float* __restrict__ invstd, int rows, int c,
                     double* __restrict__ partial) {
   const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
   const int sub = threadIdx.x >> 5;   // 8 row lanes
@@ -39,7 +39,7 @@ channel_sums_kernel(int mode, const float* __restrict__ z, const float* __restri
         s0 += v;
         s1 += static_cast<double>(v) * v;
       } else {
-        const float dy = a[i] > 0.0f ? da[i] : 0.0f;
+        const float dy = a[i] > 0.0f ? da[i] + (da2 ? da2[i] : 0.0f) : 0.0f;   // da2: the gradient that arrived over the skip connection
         s0 += dy;
         s1 += static_cast<double>(dy) * ((z[i] - mu) * is);
       }
@@ -98,20 +98,20 @@ __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __rest
 // dskip (conv2 of a residual block): the Add passes dy on to the block's input.  `dskip_accumulate`: add instead of store.
 template <typename H>
 __global__ void bn_backward_kernel(const float* __restrict__ z, const float* __restrict__ a, const float* __restrict__ da,
-                                   const float* __restrict__ gamma, const float* __restrict__ mean,
-                                   const float* __restrict__ invstd, const double* __restrict__ partial, int rows, int c,
-                                   float* __restrict__ dz, H* __restrict__ dz16, float* __restrict__ dskip,
-                                   int dskip_accumulate) {
+                                   const float* da2, const float* __restrict__ gamma, const float* __restrict__ mean,
+                                   const float* __restrict__ invstd, const float* __restrict__ sum_dy,
+                                   const float* __restrict__ sum_dyx, int rows, int c,
+                                   float* __restrict__ dz, H* __restrict__ dz16, float* dskip, int dskip_accumulate) {
+  // sum_dy / sum_dyx: the channel sums, = dbeta / dgamma as bn_param_grads_kernel left them in the gradient vector
+  // (da2 and dskip may be the same buffer: each thread reads its element of da2 before it writes that element of dskip)
   const size_t total = static_cast<size_t>(rows) * c;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int ch = static_cast<int>(i % c);
-  // (every thread re-sums its channel's 64 partials from L1/L2: 128 loads against one row element -- the kernel is tiny)
-  double s0 = 0.0, s1 = 0.0;
-  for (int k = 0; k < STAT_SPLITS; ++k) { s0 += partial[(0 * STAT_SPLITS + k) * c + ch]; s1 += partial[(1 * STAT_SPLITS + k) * c + ch]; }
-  const float dy = a[i] > 0.0f ? da[i] : 0.0f;
+  const float s0 = sum_dy[ch], s1 = sum_dyx[ch];
+  const float dy = a[i] > 0.0f ? da[i] + (da2 ? da2[i] : 0.0f) : 0.0f;
   const float xhat = (z[i] - mean[ch]) * invstd[ch];
-  const float v = gamma[ch] * invstd[ch] * (dy - static_cast<float>(s0 / rows) - xhat * static_cast<float>(s1 / rows));
+  const float v = gamma[ch] * invstd[ch] * (dy - s0 / rows - xhat * (s1 / rows));
   dz[i] = v;
   if (dz16) dz16[i] = from_f32<H>(v);
   if (dskip) dskip[i] = dskip_accumulate ? dskip[i] + dy : dy;
@@ -308,6 +308,76 @@ __global__ void flip_weights_kernel(const float* __restrict__ w, float* __restri
   const int ic = static_cast<int>((i / cout) % cin);
   const int tap = static_cast<int>(i / (static_cast<size_t>(cout) * cin));
   wt[(static_cast<size_t>(taps - 1 - tap) * cout + oc) * cin + ic] = w[i];
+}
+
+// ---- operand preparation for the tensor-core convolutions of the 16-bit training builds ------------------------------
+// fp32 convolution kernel [tap][ic][oc] (Keras HWIO) ->
+//   wf [oc][tap * cin_pad + ic]               K-major rows for the FORWARD implicit GEMM (16-bit, format f_fp16)
+//   wb [ic][tap' * cout + oc], tap' = 180-degree rotation of tap:  K-major rows for the INPUT-GRADIENT convolution
+//                                                                  dx = conv(dz, rot180(w)^T) (16-bit, format b_fp16)
+__global__ void pack_conv_weights_kernel(const float* __restrict__ w, int taps, int cin, int cin_pad, int cout, uint16_t* __restrict__ wf,
+                                         int f_fp16, uint16_t* __restrict__ wb, int b_fp16) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(taps) * cin * cout;
+  if (i >= total) return;
+  const int oc = static_cast<int>(i % cout);
+  const int ic = static_cast<int>((i / cout) % cin);
+  const int tap = static_cast<int>(i / (static_cast<size_t>(cout) * cin));
+  const float v = w[i];
+  auto bits = [](float x, int fp16) -> uint16_t {
+    if (fp16) { const __half h = __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f)); return *reinterpret_cast<const uint16_t*>(&h); }
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    return *reinterpret_cast<const uint16_t*>(&h);
+  };
+  wf[static_cast<size_t>(oc) * taps * cin_pad + static_cast<size_t>(tap) * cin_pad + ic] = bits(v, f_fp16);
+  if (wb) wb[static_cast<size_t>(ic) * taps * cout + static_cast<size_t>(taps - 1 - tap) * cout + oc] = bits(v, b_fp16);
+}
+
+// rows [board * 64 + square][c] fp32  ->  K-major operand of the weight-gradient GEMM, bf16:
+//   out[ch][cell][board],  cell = (rank + pad) * pitch + file + pad over the zero-padded board (pitch = 8 + 2 pad),
+//   board < nb (nb = boards rounded up to 64; boards >= batch and channels >= c are written as zeros, halo cells stay zero
+//   from the allocation).  With this order a filter tap is a shift of the K index by a multiple of nb elements: 16-byte
+//   aligned, as the TMA box origin of the shifted operand has to be.
+// grid (nb / 32, c_pad / 32, 64 squares), 256 threads
+__global__ void __launch_bounds__(256)
+transpose_pad_kernel(const float* __restrict__ x, int batch, int c, int c_pad, int nb, int pad, __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b0 = blockIdx.x * 32, c0 = blockIdx.y * 32, sq = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int pitch = 8 + 2 * pad, cells = pitch * pitch, cell = ((sq >> 3) + pad) * pitch + (sq & 7) + pad;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int b = b0 + ty + r * 8, ch = c0 + tx;
+    tile[ty + r * 8][tx] = (b < batch && ch < c) ? x[(static_cast<size_t>(b) * 64 + sq) * c + ch] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int ch = c0 + ty + r * 8, b = b0 + tx;
+    if (ch < c_pad && b < nb) out[(static_cast<size_t>(ch) * cells + cell) * nb + b] = __float2bfloat16_rn(tile[tx][ty + r * 8]);
+  }
+}
+
+// partial [tap][split][n_out][n_in_pad] (fp32, one tensor-core GEMM tile each) -> dw [tap][ic][oc] (Keras layout), summed over the splits
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int taps, int splits, int n_out, int n_in, int n_in_pad, float* __restrict__ dw) {
+  __shared__ float tile[32][33];
+  const int ic0 = blockIdx.x * 32, oc0 = blockIdx.y * 32, tap = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int oc = oc0 + ty + r * 8, ic = ic0 + tx;
+    float s = 0.0f;
+    if (oc < n_out && ic < n_in)
+      for (int k = 0; k < splits; ++k) s += partial[((static_cast<size_t>(tap) * splits + k) * n_out + oc) * n_in_pad + ic];
+    tile[ty + r * 8][tx] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int ic = ic0 + ty + r * 8, oc = oc0 + tx;
+    if (ic < n_in && oc < n_out) dw[(static_cast<size_t>(tap) * n_in + ic) * n_out + oc] = tile[tx][ty + r * 8];
+  }
 }
 
 // ---- Adam (keras 2.0.8 optimizers.Adam: lr 1e-3, beta_1 0.9, beta_2 0.999, epsilon 1e-8, decay 0) ----------------------

@@ -83,7 +83,7 @@ class Trainer:
             self._grad_tensor = torch.zeros(self.n_params, dtype=torch.float32, device=torch.device("cuda", self.device))
             grad_ptr = ctypes.c_void_p(self._grad_tensor.data_ptr())
         self._h = ctypes.c_void_p()
-        codes = {"fp32": _lib.PRECISION_FP32}
+        codes = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}
         if precision not in codes:
             raise ValueError(f"precision must be one of {sorted(codes)}")
         rc = lib.caz_train_create(ctypes.byref(self.arch), arr, len(keep), self.device, codes[precision], self.max_batch,

@@ -262,7 +262,9 @@ typedef struct caz_train_config {
 } caz_train_config;
 
 /* tensors: the initial weights, same order and layout as caz_create.  precision: CAZ_PRECISION_FP32 (all arithmetic fp32
- * on the CUDA cores).  d_grads: NULL, or device memory for caz_train_param_count(arch) floats that receives the gradients. */
+ * on the CUDA cores: the parity build) or CAZ_PRECISION_BF16 (mixed precision: fp32 master weights, moments, BatchNormalization
+ * and heads; the stem's and the tower's convolutions on the tensor cores with fp32 accumulation -- forward fp16 x fp16,
+ * input gradients and weight gradients bf16 x bf16).  d_grads: NULL, or device memory for caz_train_param_count(arch) floats that receives the gradients. */
 int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensors, int32_t device, int32_t precision,
                      int32_t max_batch, const caz_train_config* cfg, float* d_grads, caz_trainer** out);
 void caz_train_destroy(caz_trainer* t);
