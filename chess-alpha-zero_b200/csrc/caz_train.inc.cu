@@ -120,8 +120,8 @@ int tr_bn_forward(caz_trainer* t, TrainConv& L, const float* skip, int rows) {
   caz::train::channel_sums_kernel<<<grid, 256, 0, t->stream>>>(0, L.z, nullptr, nullptr, nullptr, nullptr, nullptr, rows, L.cout, t->partial);
   int rc;
   if ((rc = tr_launch_ok(t, "channel_sums_kernel"))) return rc;
-  caz::train::bn_finish_stats_kernel<<<(L.cout + 127) / 128, 128, 0, t->stream>>>(t->partial, rows, L.cout, t->arch.bn_epsilon, t->cfg.bn_momentum, L.mean,
-                                                                                L.invstd, t->params + L.mmean, t->params + L.mvar);
+  caz::train::bn_finish_stats_kernel<<<(L.cout + 127) / 128, 128, 0, t->stream>>>(t->partial, rows, L.cout, t->arch.bn_epsilon, L.mean, L.invstd,
+                                                                                t->grads + L.mmean, t->grads + L.mvar);
   if ((rc = tr_launch_ok(t, "bn_finish_stats_kernel"))) return rc;
   const size_t total = static_cast<size_t>(rows) * L.cout;
   caz::train::bn_apply_kernel<__half><<<blocks_for(total), 256, 0, t->stream>>>(L.z, skip, t->params + L.gamma, t->params + L.beta, L.mean, L.invstd, total,
@@ -468,8 +468,8 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
     ok &= (L.w = take((int64_t)k * k * cin * cout, 2)) != SIZE_MAX;
     ok &= (L.gamma = take(cout, 1)) != SIZE_MAX;
     ok &= (L.beta = take(cout, 1)) != SIZE_MAX;
-    ok &= (L.mmean = take(cout, 0)) != SIZE_MAX;
-    ok &= (L.mvar = take(cout, 0)) != SIZE_MAX;
+    ok &= (L.mmean = take(cout, 3)) != SIZE_MAX;
+    ok &= (L.mvar = take(cout, 3)) != SIZE_MAX;
   };
   t->convs.resize(1 + 2 * a.res_blocks);
   take_conv(t->convs[0], a.stem_kernel, a.input_planes, a.filters);
@@ -638,7 +638,7 @@ int caz_train_apply(caz_trainer* t, float grad_scale) {
   const double b1 = t->cfg.beta_1, b2 = t->cfg.beta_2;
   const float lr_t = (float)(t->cfg.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)t->step)) / (1.0 - std::pow(b1, (double)t->step)));
   caz::train::adam_kernel<<<blocks_for(t->n_params), 256, 0, t->stream>>>(t->params, t->grads, t->adam_m, t->adam_v, t->seg, t->n_params, lr_t,
-                                                                       t->cfg.beta_1, t->cfg.beta_2, t->cfg.epsilon, t->cfg.l2, grad_scale);
+                                                                       t->cfg.beta_1, t->cfg.beta_2, t->cfg.epsilon, t->cfg.l2, grad_scale, t->cfg.bn_momentum);
   int rc;
   if ((rc = tr_launch_ok(t, "adam_kernel"))) return rc;
   if ((rc = tr_refresh_weights16(t))) return rc;

@@ -57,11 +57,13 @@ channel_sums_kernel(int mode, const float* __restrict__ z, const float* __restri
 }
 
 // Batch statistics from the partial sums (Keras BatchNormalization in training mode: biased variance, epsilon inside the
-// square root) and the moving-average update  moving = moving * momentum + batch * (1 - momentum)  (keras 2.0.8
-// normalization.py: K.moving_average_update with the biased batch variance).
-__global__ void bn_finish_stats_kernel(const double* __restrict__ partial, int rows, int c, float eps, float momentum,
+// square root).  The batch mean / variance are also left in the GRADIENT vector's slots of the moving statistics: the
+// moving-average update  moving = moving * momentum + batch * (1 - momentum)  (keras 2.0.8 normalization.py:
+// K.moving_average_update with the biased batch variance) happens in adam_kernel, after the data-parallel all-reduce has
+// averaged the ranks' batch statistics, so that every rank keeps identical moving statistics.
+__global__ void bn_finish_stats_kernel(const double* __restrict__ partial, int rows, int c, float eps,
                                        float* __restrict__ mean, float* __restrict__ invstd,
-                                       float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+                                       float* __restrict__ batch_mean_out, float* __restrict__ batch_var_out) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   double s0 = 0.0, s1 = 0.0;
@@ -71,10 +73,8 @@ __global__ void bn_finish_stats_kernel(const double* __restrict__ partial, int r
   if (var < 0.0) var = 0.0;
   mean[ch] = static_cast<float>(mu);
   invstd[ch] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  if (moving_mean) {
-    moving_mean[ch] = moving_mean[ch] * momentum + static_cast<float>(mu) * (1.0f - momentum);
-    moving_var[ch] = moving_var[ch] * momentum + static_cast<float>(var) * (1.0f - momentum);
-  }
+  batch_mean_out[ch] = static_cast<float>(mu);
+  batch_var_out[ch] = static_cast<float>(var);
 }
 
 // a = relu(gamma * (z - mean) * invstd + beta (+ skip));  optional 16-bit NHWC copy for the tensor-core convolutions
@@ -383,12 +383,17 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int taps, int splits, int
 // ---- Adam (keras 2.0.8 optimizers.Adam: lr 1e-3, beta_1 0.9, beta_2 0.999, epsilon 1e-8, decay 0) ----------------------
 //   g += 2 * l2 * p on regularised kernels (d/dp of l2 * sum p^2);  lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);
 //   m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= lr_t * m / (sqrt(v) + eps)
-// seg: per parameter 0 = not trainable (moving statistics), 1 = trainable, 2 = trainable + l2
+// seg: per parameter 0 = frozen, 1 = trainable, 2 = trainable + l2, 3 = BatchNormalization moving statistic (its "gradient"
+// slot holds this step's batch statistic, summed over the ranks: moving = moving * momentum + mean batch statistic * (1 - momentum))
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             const uint8_t* __restrict__ seg, size_t n, float lr_t, float b1, float b2, float eps, float l2,
-                            float grad_scale) {
+                            float grad_scale, float bn_momentum) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n || seg[i] == 0) return;
+  if (seg[i] == 3) {
+    p[i] = p[i] * bn_momentum + g[i] * grad_scale * (1.0f - bn_momentum);
+    return;
+  }
   float gi = g[i] * grad_scale;
   if (seg[i] == 2) gi += 2.0f * l2 * p[i];
   const float mi = b1 * m[i] + (1.0f - b1) * gi;

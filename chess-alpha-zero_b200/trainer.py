@@ -127,7 +127,8 @@ class Trainer:
         return self._read(0)
 
     def gradients(self):
-        """Gradients of the data loss left by the last forward_backward (the l2 term is added inside apply)."""
+        """Gradients of the data loss left by the last forward_backward (the l2 term is added inside apply); the entries of
+        the moving statistics hold the batch mean / variance of that pass."""
         return self._read(1)
 
     @property

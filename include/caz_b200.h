@@ -273,8 +273,9 @@ int64_t caz_train_param_count(const caz_arch* arch); /* floats in the flat param
 int64_t caz_train_num_params(const caz_trainer* t);
 int64_t caz_train_steps(const caz_trainer* t);       /* caz_train_apply calls so far (Adam's t) */
 /* Forward pass in training mode, losses, backward pass: fills the gradient vector (sum over this batch of the loss
- * gradients, already divided by `batch`; the l2 term is added in caz_train_apply) and updates the BatchNormalization moving
- * statistics.  planes: host float32 [batch][18][8][8]; policy_target: host float32 [batch][n_labels]; value_target: host
+ * gradients, already divided by `batch`; the l2 term is added in caz_train_apply; the slots of the BatchNormalization moving
+ * statistics receive this batch's mean / variance, which caz_train_apply folds into the moving averages -- after an
+ * all-reduce they are the mean over the ranks, so every rank keeps identical statistics).  planes: host float32 [batch][18][8][8]; policy_target: host float32 [batch][n_labels]; value_target: host
  * float32 [batch].  losses (may be NULL): host float32 [4] = total, mean categorical cross-entropy, mean squared error,
  * l2 term. */
 int caz_train_forward_backward(caz_trainer* t, const float* planes, const float* policy_target, const float* value_target,
