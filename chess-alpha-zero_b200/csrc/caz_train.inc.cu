@@ -21,6 +21,7 @@ struct TrainConv {
   uint16_t *a16 = nullptr, *wf = nullptr, *wb = nullptr;
   int cin_pad = 0;
   CUtensorMap tm_a16, tm_wf, tm_wb;
+  CUtensorMap tm_wf_h, tm_wb_h;   // the same weight matrices in boxes of cout / 4 (cin / 4) rows: two N tiles per board group
 };
 
 }  // namespace
@@ -48,6 +49,9 @@ struct caz_trainer {
   float *w_flip = nullptr, *zero_bias = nullptr;
   double *partial = nullptr, *loss_acc = nullptr;
   float last_losses[4] = {0, 0, 0, 0};
+  // the ~230 launches of a step are captured once per batch size and replayed as one CUDA graph (CAZ_TRAIN_NO_GRAPH=1: off)
+  bool use_graph = true;
+  std::vector<std::pair<int, cudaGraphExec_t>> graphs;
   // 16-bit builds (tensor-core convolutions): forward fp16 x fp16, input and weight gradients bf16 x bf16, fp32 accumulation
   bool tc = false;
   int num_sms = 0, nb = 0;                 // nb: max_batch rounded up to 64 (board-minor extent of the weight-gradient operands)
@@ -116,32 +120,35 @@ int tr_gemm(caz_trainer* t, const float* a, long a_si, long a_sk, const float* b
 
 // batch statistics of z (and the moving averages), then a = relu(BN(z) (+ skip))
 int tr_bn_forward(caz_trainer* t, TrainConv& L, const float* skip, int rows) {
-  const dim3 grid((L.cout + 31) / 32, caz::train::STAT_SPLITS);
+  const dim3 grid((L.cout + 127) / 128, caz::train::STAT_SPLITS);
   caz::train::channel_sums_kernel<<<grid, 256, 0, t->stream>>>(0, L.z, nullptr, nullptr, nullptr, nullptr, nullptr, rows, L.cout, t->partial);
   int rc;
   if ((rc = tr_launch_ok(t, "channel_sums_kernel"))) return rc;
-  caz::train::bn_finish_stats_kernel<<<(L.cout + 127) / 128, 128, 0, t->stream>>>(t->partial, rows, L.cout, t->arch.bn_epsilon, L.mean, L.invstd,
+  caz::train::bn_finish_stats_kernel<<<(L.cout + 7) / 8, 256, 0, t->stream>>>(t->partial, rows, L.cout, t->arch.bn_epsilon, L.mean, L.invstd,
                                                                                 t->grads + L.mmean, t->grads + L.mvar);
   if ((rc = tr_launch_ok(t, "bn_finish_stats_kernel"))) return rc;
   const size_t total = static_cast<size_t>(rows) * L.cout;
-  caz::train::bn_apply_kernel<__half><<<blocks_for(total), 256, 0, t->stream>>>(L.z, skip, t->params + L.gamma, t->params + L.beta, L.mean, L.invstd, total,
-                                                                                L.cout, L.a, reinterpret_cast<__half*>(L.a16));
+  const int vec4 = (L.cout & 3) == 0 && (L.gamma & 3) == 0 && (L.beta & 3) == 0;   // float4 slices of the parameter vectors
+  caz::train::bn_apply_kernel<__half><<<blocks_for(vec4 ? total / 4 : total), 256, 0, t->stream>>>(L.z, skip, t->params + L.gamma, t->params + L.beta, L.mean,
+                                                                                                   L.invstd, total, L.cout, L.a,
+                                                                                                   reinterpret_cast<__half*>(L.a16), vec4);
   return tr_launch_ok(t, "bn_apply_kernel");
 }
 
 // da (gradient wrt the layer's activation) -> dz (wrt its convolution output), dgamma / dbeta; dskip = gradient passed to the Add's other input
 int tr_bn_backward(caz_trainer* t, TrainConv& L, const float* da, float* dz, float* dskip, int dskip_accumulate, int rows,
                    const float* da2 = nullptr, uint16_t* dz16 = nullptr) {
-  const dim3 grid((L.cout + 31) / 32, caz::train::STAT_SPLITS);
+  const dim3 grid((L.cout + 127) / 128, caz::train::STAT_SPLITS);
   caz::train::channel_sums_kernel<<<grid, 256, 0, t->stream>>>(1, L.z, L.a, da, da2, L.mean, L.invstd, rows, L.cout, t->partial);
   int rc;
   if ((rc = tr_launch_ok(t, "channel_sums_kernel (backward)"))) return rc;
-  caz::train::bn_param_grads_kernel<<<(L.cout + 127) / 128, 128, 0, t->stream>>>(t->partial, L.cout, t->grads + L.gamma, t->grads + L.beta);
+  caz::train::bn_param_grads_kernel<<<(L.cout + 7) / 8, 256, 0, t->stream>>>(t->partial, L.cout, t->grads + L.gamma, t->grads + L.beta);
   if ((rc = tr_launch_ok(t, "bn_param_grads_kernel"))) return rc;
   const size_t total = static_cast<size_t>(rows) * L.cout;
-  caz::train::bn_backward_kernel<__nv_bfloat16><<<blocks_for(total), 256, 0, t->stream>>>(L.z, L.a, da, da2, t->params + L.gamma, L.mean, L.invstd,
+  const int vec4 = (L.cout & 3) == 0 && (L.gamma & 3) == 0 && (L.beta & 3) == 0;
+  caz::train::bn_backward_kernel<__nv_bfloat16><<<blocks_for(vec4 ? total / 4 : total), 256, 0, t->stream>>>(L.z, L.a, da, da2, t->params + L.gamma, L.mean, L.invstd,
                                                                                           t->grads + L.beta, t->grads + L.gamma, rows, L.cout, dz, reinterpret_cast<__nv_bfloat16*>(dz16), dskip,
-                                                                                          dskip_accumulate);
+                                                                                          dskip_accumulate, vec4);
   return tr_launch_ok(t, "bn_backward_kernel");
 }
 
@@ -205,8 +212,8 @@ int tr_launch_tc(caz_trainer* t, const CUtensorMap& tm_a, const CUtensorMap& tm_
 }
 
 // out[rows][n] = conv(in16, w16): "same" convolution as an implicit GEMM on the tensor cores, raw fp32 row-major output
-int tr_conv_tc(caz_trainer* t, const CUtensorMap& tm_in, const CUtensorMap& tm_w, int ksize, int row_bytes, int kchunks, int n, int fmt,
-               float* out, int batch) {
+int tr_conv_tc(caz_trainer* t, const CUtensorMap& tm_in, const CUtensorMap& tm_w, const CUtensorMap& tm_w_half, int ksize, int row_bytes,
+               int kchunks, int n, int fmt, float* out, int batch) {
   caz::tc::ConvArgs args{};
   args.batch = batch;
   args.num_tiles = (batch + 1) / 2;
@@ -220,7 +227,16 @@ int tr_conv_tc(caz_trainer* t, const CUtensorMap& tm_in, const CUtensorMap& tm_w
   args.n_total = n;
   args.m_rows = batch * 64;
   args.out_rm = out;
-  return tr_launch_tc(t, tm_in, tm_w, args, (args.num_tiles + 1) / 2, "conv_tc2_kernel (training)");
+  // Two N tiles of n / 2 channels per board group when that fills the last wave better: batch 384 = 96 groups on 74 CTA pairs
+  // is two waves of whole tiles but 2.6 waves of half tiles (= 1.3 tile times)
+  const int pairs = (args.num_tiles + 1) / 2, maxp = t->num_sms / 2;
+  const int waves_whole = (pairs + maxp - 1) / maxp, half_waves = (2 * pairs + maxp - 1) / maxp;
+  if (n % 64 == 0 && half_waves < 2 * waves_whole) {
+    args.n_tiles = 2;
+    args.n = n / 2;
+    return tr_launch_tc(t, tm_in, tm_w_half, args, 2 * pairs, "conv_tc2_kernel (training, two N tiles)");
+  }
+  return tr_launch_tc(t, tm_in, tm_w, args, pairs, "conv_tc2_kernel (training)");
 }
 
 // dW[tap][ic][oc] of a k x k convolution: x rows [batch * 64][cin] (fp32), dz rows [batch * 64][cout] (fp32) -> t->grads + L.w
@@ -269,13 +285,15 @@ int tr_wgrad_tc(caz_trainer* t, const float* x, const float* dz, int batch, cons
 // the 16-bit copies of the convolution kernels follow the fp32 master weights (after creation and after every update)
 int tr_refresh_weights16(caz_trainer* t) {
   if (!t->tc) return CAZ_OK;
+  if (t->convs.size() > caz::train::PACK_MAX_LAYERS) return tfail(t, CAZ_ERR_INVALID, "too many convolution layers for the weight packing table");
+  caz::train::PackTable tab{};
   for (size_t l = 0; l < t->convs.size(); ++l) {
     TrainConv& L = t->convs[l];
-    const size_t total = static_cast<size_t>(L.k) * L.k * L.cin * L.cout;
-    caz::train::pack_conv_weights_kernel<<<blocks_for(total), 256, 0, t->stream>>>(t->params + L.w, L.k * L.k, L.cin, L.cin_pad, L.cout, L.wf, 1,
-                                                                                l == 0 ? nullptr : L.wb, 0);
+    tab.layer[l] = caz::train::PackLayer{t->params + L.w, L.wf, l == 0 ? nullptr : L.wb, L.k * L.k, L.cin, L.cin_pad, L.cout};
   }
-  return tr_launch_ok(t, "pack_conv_weights_kernel");
+  const dim3 grid(64, static_cast<unsigned>(t->convs.size()));
+  caz::train::pack_all_conv_weights_kernel<<<grid, 256, 0, t->stream>>>(tab, 1, 0);
+  return tr_launch_ok(t, "pack_all_conv_weights_kernel");
 }
 
 int tr_forward_backward(caz_trainer* t, int batch) {
@@ -302,8 +320,8 @@ int tr_forward_backward(caz_trainer* t, int batch) {
     const float* in = l == 0 ? t->x0 : t->convs[l - 1].a;
     if (t->tc) {
       const int fmt = caz::ptx::FMT_A_FP16 | caz::ptx::FMT_B_FP16;
-      if (l == 0) rc = tr_conv_tc(t, t->tm_x0, L.tm_wf, L.k, 64, 1, L.cout, fmt, L.z, batch);
-      else rc = tr_conv_tc(t, t->convs[l - 1].tm_a16, L.tm_wf, L.k, 128, L.cin / 64, L.cout, fmt, L.z, batch);
+      if (l == 0) rc = tr_conv_tc(t, t->tm_x0, L.tm_wf, L.tm_wf_h, L.k, 64, 1, L.cout, fmt, L.z, batch);
+      else rc = tr_conv_tc(t, t->convs[l - 1].tm_a16, L.tm_wf, L.tm_wf_h, L.k, 128, L.cin / 64, L.cout, fmt, L.z, batch);
       if (rc) return rc;
     } else if ((rc = tr_conv_fp32(t, in, P + L.w, nullptr, L.z, batch, L.k, L.cin, L.cout))) return rc;
     const bool conv2 = l > 0 && (l & 1) == 0;
@@ -311,9 +329,10 @@ int tr_forward_backward(caz_trainer* t, int batch) {
   }
   const float* top = t->convs[n_convs - 1].a;
   // heads' 1x1 convolutions as GEMMs over the rows
-  if ((rc = tr_gemm(t, top, F, 1, P + t->pconv.w, pf, 1, nullptr, t->pconv.z, rows, pf, F))) return rc;
+  caz::train::head_conv_forward_kernel<<<blocks_for(static_cast<size_t>(rows) * 32), 256, 0, t->stream>>>(top, P + t->pconv.w, P + t->vconv.w, t->pconv.z,
+                                                                                                      t->vconv.z, rows, F, pf, vf);
+  if ((rc = tr_launch_ok(t, "head_conv_forward_kernel"))) return rc;
   if ((rc = tr_bn_forward(t, t->pconv, nullptr, rows))) return rc;
-  if ((rc = tr_gemm(t, top, F, 1, P + t->vconv.w, vf, 1, nullptr, t->vconv.z, rows, vf, F))) return rc;
   if ((rc = tr_bn_forward(t, t->vconv, nullptr, rows))) return rc;
   caz::train::flatten_kernel<<<blocks_for(static_cast<size_t>(rows) * pf), 256, 0, t->stream>>>(t->pconv.a, t->featp, batch, pf, 0);
   caz::train::flatten_kernel<<<blocks_for(static_cast<size_t>(rows) * vf), 256, 0, t->stream>>>(t->vconv.a, t->featv, batch, vf, 0);
@@ -332,7 +351,7 @@ int tr_forward_backward(caz_trainer* t, int batch) {
   // policy Dense: dW = featp^T . dlogits, db = column sums, dfeatp = dlogits . W^T
   if ((rc = tr_gemm(t, t->featp, 1, kp, t->dlogits, nl, 1, nullptr, G + t->pfc_w, kp, nl, batch))) return rc;
   caz::train::column_sum_kernel<<<(nl + 127) / 128, 128, 0, t->stream>>>(t->dlogits, batch, nl, G + t->pfc_b);
-  if ((rc = tr_gemm(t, t->dlogits, nl, 1, P + t->pfc_w, 1, nl, nullptr, t->dfeatp, batch, kp, nl))) return rc;
+  if ((rc = tr_gemm(t, t->dlogits, nl, 1, P + t->pfc_w, 1, nl, nullptr, t->dfeatp, batch, kp, nl, 0, 8))) return rc;
   // value head: Dense(1, tanh) <- Dense(vfc, relu)
   if ((rc = tr_gemm(t, t->hid, 1, vfc, t->dvpre, 1, 1, nullptr, G + t->vfc2_w, vfc, 1, batch))) return rc;
   caz::train::column_sum_kernel<<<1, 32, 0, t->stream>>>(t->dvpre, batch, 1, G + t->vfc2_b);
@@ -347,17 +366,18 @@ int tr_forward_backward(caz_trainer* t, int batch) {
   caz::train::flatten_kernel<<<blocks_for(static_cast<size_t>(rows) * vf), 256, 0, t->stream>>>(t->dav, t->dfeatv, batch, vf, 1);
   if ((rc = tr_bn_backward(t, t->pconv, t->dap, t->dzp, nullptr, 0, rows))) return rc;
   if ((rc = tr_bn_backward(t, t->vconv, t->dav, t->dzv, nullptr, 0, rows))) return rc;
-  const int hsplit = 32;   // the reduction runs over all rows
-  if ((rc = tr_gemm(t, top, 1, F, t->dzp, pf, 1, nullptr, G + t->pconv.w, F, pf, rows, 0, hsplit))) return rc;
-  if ((rc = tr_gemm(t, top, 1, F, t->dzv, vf, 1, nullptr, G + t->vconv.w, F, vf, rows, 0, hsplit))) return rc;
+  TR_TRY(t, cudaMemsetAsync(G + t->pconv.w, 0, static_cast<size_t>(F) * pf * sizeof(float), t->stream));
+  TR_TRY(t, cudaMemsetAsync(G + t->vconv.w, 0, static_cast<size_t>(F) * vf * sizeof(float), t->stream));
+  {
+    const dim3 grid((F + 255) / 256, 128);
+    caz::train::head_conv_backward_weight_kernel<<<grid, 256, 0, t->stream>>>(top, t->dzp, t->dzv, G + t->pconv.w, G + t->vconv.w, rows, F, pf, vf);
+    if ((rc = tr_launch_ok(t, "head_conv_backward_weight_kernel"))) return rc;
+  }
   float* dcur = t->d_a;   // gradient wrt the activation of the layer being processed
   float* dalt = t->d_b;
-  if ((rc = tr_gemm(t, t->dzp, pf, 1, P + t->pconv.w, 1, pf, nullptr, dcur, rows, F, pf))) return rc;
-  {
-    const dim3 grid((F + 31) / 32, (rows + 31) / 32, 1);   // += the value head's share
-    caz::train::gemm_kernel<<<grid, 256, 0, t->stream>>>(t->dzv, vf, 1, P + t->vconv.w, 1, vf, nullptr, dcur, rows, F, vf, 1, 0);
-    if ((rc = tr_launch_ok(t, "gemm_kernel (accumulate)"))) return rc;
-  }
+  caz::train::head_conv_backward_data_kernel<<<blocks_for(static_cast<size_t>(rows) * F), 256, 0, t->stream>>>(t->dzp, t->dzv, P + t->pconv.w, P + t->vconv.w,
+                                                                                                           dcur, rows, F, pf, vf);
+  if ((rc = tr_launch_ok(t, "head_conv_backward_data_kernel"))) return rc;
   // ---- backward: tower ----
   for (int l = n_convs - 1; l >= 0; --l) {
     TrainConv& L = t->convs[l];
@@ -371,7 +391,7 @@ int tr_forward_backward(caz_trainer* t, int batch) {
     else rc = tr_wgrad_fp32(t, in, t->dz, batch, L);
     if (rc) return rc;
     if (l == 0) break;
-    if (t->tc) rc = tr_conv_tc(t, t->tm_dz, L.tm_wb, L.k, 128, L.cout / 64, L.cin, 0, dalt, batch);
+    if (t->tc) rc = tr_conv_tc(t, t->tm_dz, L.tm_wb, L.tm_wb_h, L.k, 128, L.cout / 64, L.cin, 0, dalt, batch);
     else rc = tr_dgrad_fp32(t, t->dz, L, conv1 ? t->d_skip : nullptr, dalt, batch);
     if (rc) return rc;
     std::swap(dcur, dalt);
@@ -399,6 +419,7 @@ void caz_train_destroy(caz_trainer* t) {
   free_conv(t->pconv);
   free_conv(t->vconv);
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& g : t->graphs) cudaGraphExecDestroy(g.second);
   if (t->stream) cudaStreamDestroy(t->stream);
   delete t;
 }
@@ -559,6 +580,7 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
   cudaFuncSetAttribute(caz::conv_fp32_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
   cudaFuncSetAttribute(caz::conv_fp32_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
   t->num_sms = prop.multiProcessorCount;
+  if (getenv("CAZ_TRAIN_NO_GRAPH")) t->use_graph = false;
   if (precision == CAZ_PRECISION_BF16) {
     if (prop.major != 10) { t->err = "the tensor-core training build needs an sm_100 GPU"; return bail(CAZ_ERR_NO_DEVICE); }
     t->tc = true;
@@ -574,9 +596,11 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
       TC2(tr_alloc(t, &L.wf, (size_t)L.cout * taps * L.cin_pad));
       TC2(tr_halo_tmap(t, &L.tm_a16, L.a16, L.cout, a.block_kernel, boards));
       TC2(tr_kmajor_tmap(t, &L.tm_wf, L.wf, (size_t)taps * L.cin_pad, L.cout, L.cout / 2, l == 0 ? 64 : 128));
+      TC2(tr_kmajor_tmap(t, &L.tm_wf_h, L.wf, (size_t)taps * L.cin_pad, L.cout, L.cout / 4, l == 0 ? 64 : 128));
       if (l > 0) {
         TC2(tr_alloc(t, &L.wb, (size_t)L.cin * taps * L.cout));
         TC2(tr_kmajor_tmap(t, &L.tm_wb, L.wb, (size_t)taps * L.cout, L.cin, L.cin / 2));
+        TC2(tr_kmajor_tmap(t, &L.tm_wb_h, L.wb, (size_t)taps * L.cout, L.cin, L.cin / 4));
       }
     }
     TC2(tr_alloc(t, &t->x0_16, Rp * 32));
@@ -618,7 +642,27 @@ int caz_train_forward_backward(caz_trainer* t, const float* planes, const float*
   TR_TRY(t, cudaMemcpyAsync(t->policy_t, policy_target, (size_t)batch * a.n_labels * 4, cudaMemcpyHostToDevice, t->stream));
   TR_TRY(t, cudaMemcpyAsync(t->value_t, value_target, (size_t)batch * 4, cudaMemcpyHostToDevice, t->stream));
   int rc;
-  if ((rc = tr_forward_backward(t, batch))) return rc;
+  cudaGraphExec_t exec = nullptr;
+  for (auto& g : t->graphs)
+    if (g.first == batch) exec = g.second;
+  if (t->use_graph && !exec) {
+    // first step at this batch size: record the launch sequence (pointers and sizes are fixed per batch size)
+    cudaGraph_t graph = nullptr;
+    TR_TRY(t, cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
+    rc = tr_forward_backward(t, batch);
+    const cudaError_t ce = cudaStreamEndCapture(t->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      exec = nullptr;
+      t->use_graph = false;   // fall back to plain launches
+    } else {
+      t->graphs.emplace_back(batch, exec);
+    }
+    if (graph) cudaGraphDestroy(graph);
+  }
+  if (exec) TR_TRY(t, cudaGraphLaunch(exec, t->stream));
+  else if ((rc = tr_forward_backward(t, batch))) return rc;
   double acc[4];
   TR_TRY(t, cudaMemcpyAsync(acc, t->loss_acc, sizeof acc, cudaMemcpyDeviceToHost, t->stream));
   TR_TRY(t, cudaStreamSynchronize(t->stream));

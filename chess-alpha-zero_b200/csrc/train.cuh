@@ -14,7 +14,9 @@
 namespace caz {
 namespace train {
 
-constexpr int STAT_SPLITS = 64;   // row splits of the per-channel reductions (partials are summed in a fixed order)
+constexpr int STAT_SPLITS = 128;
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }   // row splits of the per-channel reductions (partials are summed in a fixed order)
 
 // ---- per-channel sums over the rows: partial[split][c] = sum over the split's rows of f(row, c) -------------------------
 // mode 0: (sum z, sum z^2)                                -> BatchNormalization batch statistics
@@ -24,13 +26,56 @@ __global__ void __launch_bounds__(256)
 channel_sums_kernel(int mode, const float* __restrict__ z, const float* __restrict__ a, const float* __restrict__ da,
                     const float* __restrict__ da2, const float* __restrict__ mean, const float* __restrict__ invstd, int rows, int c,
                     double* __restrict__ partial) {
-  const int ch = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int sub = threadIdx.x >> 5;   // 8 row lanes
+  // a block covers 128 channels (32 lanes x float4) x 8 row lanes; c is a multiple of 4 on this path (c < 4: scalar path below)
   const int split = blockIdx.y;
   const int per = (rows + STAT_SPLITS - 1) / STAT_SPLITS;
   const int r0 = split * per, r1 = min(rows, r0 + per);
-  double s0 = 0.0, s1 = 0.0;
-  if (ch < c) {
+  const int sub = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ double sh[2][8][128];
+  if ((c & 3) == 0) {
+    const int ch = blockIdx.x * 128 + lane * 4;
+    double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+    if (ch < c) {
+      float4 mu = make_float4(0, 0, 0, 0), is = mu;
+      if (mode) { mu = *reinterpret_cast<const float4*>(mean + ch); is = *reinterpret_cast<const float4*>(invstd + ch); }
+      for (int r = r0 + sub; r < r1; r += 8) {
+        const size_t i = static_cast<size_t>(r) * c + ch;
+        const float4 zv = *reinterpret_cast<const float4*>(z + i);
+        if (mode == 0) {
+          s0[0] += zv.x; s0[1] += zv.y; s0[2] += zv.z; s0[3] += zv.w;
+          s1[0] += static_cast<double>(zv.x) * zv.x; s1[1] += static_cast<double>(zv.y) * zv.y;
+          s1[2] += static_cast<double>(zv.z) * zv.z; s1[3] += static_cast<double>(zv.w) * zv.w;
+        } else {
+          const float4 av = *reinterpret_cast<const float4*>(a + i);
+          float4 dv = *reinterpret_cast<const float4*>(da + i);
+          if (da2) {   // the gradient that arrived over the skip connection
+            const float4 d2 = *reinterpret_cast<const float4*>(da2 + i);
+            dv.x += d2.x; dv.y += d2.y; dv.z += d2.z; dv.w += d2.w;
+          }
+          const float dy[4] = {av.x > 0.0f ? dv.x : 0.0f, av.y > 0.0f ? dv.y : 0.0f, av.z > 0.0f ? dv.z : 0.0f, av.w > 0.0f ? dv.w : 0.0f};
+          const float xh[4] = {(zv.x - mu.x) * is.x, (zv.y - mu.y) * is.y, (zv.z - mu.z) * is.z, (zv.w - mu.w) * is.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { s0[q] += dy[q]; s1[q] += static_cast<double>(dy[q]) * xh[q]; }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { sh[0][sub][lane * 4 + q] = s0[q]; sh[1][sub][lane * 4 + q] = s1[q]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int cc = blockIdx.x * 128 + threadIdx.x;
+      if (cc < c) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int k = 0; k < 8; ++k) { t0 += sh[0][k][threadIdx.x]; t1 += sh[1][k][threadIdx.x]; }
+        partial[(0 * STAT_SPLITS + split) * c + cc] = t0;
+        partial[(1 * STAT_SPLITS + split) * c + cc] = t1;
+      }
+    }
+    return;
+  }
+  // scalar path (the heads' 1x1 convolutions have 1, 2 or 4 channels... and anything not a multiple of 4)
+  for (int ch = blockIdx.x * 128 + lane; ch < min(c, blockIdx.x * 128 + 128); ch += 32) {
+    double s0 = 0.0, s1 = 0.0;
     const float mu = mode ? mean[ch] : 0.0f, is = mode ? invstd[ch] : 0.0f;
     for (int r = r0 + sub; r < r1; r += 8) {
       const size_t i = static_cast<size_t>(r) * c + ch;
@@ -39,21 +84,33 @@ channel_sums_kernel(int mode, const float* __restrict__ z, const float* __restri
         s0 += v;
         s1 += static_cast<double>(v) * v;
       } else {
-        const float dy = a[i] > 0.0f ? da[i] + (da2 ? da2[i] : 0.0f) : 0.0f;   // da2: the gradient that arrived over the skip connection
+        const float dy = a[i] > 0.0f ? da[i] + (da2 ? da2[i] : 0.0f) : 0.0f;
         s0 += dy;
         s1 += static_cast<double>(dy) * ((z[i] - mu) * is);
       }
     }
+    sh[0][sub][ch & 127] = s0;
+    sh[1][sub][ch & 127] = s1;
   }
-  __shared__ double sh[2][8][32];
-  sh[0][sub][threadIdx.x & 31] = s0;
-  sh[1][sub][threadIdx.x & 31] = s1;
   __syncthreads();
-  if (sub == 0 && ch < c) {
-    for (int k = 1; k < 8; ++k) { s0 += sh[0][k][threadIdx.x]; s1 += sh[1][k][threadIdx.x]; }
-    partial[(0 * STAT_SPLITS + split) * c + ch] = s0;
-    partial[(1 * STAT_SPLITS + split) * c + ch] = s1;
+  if (threadIdx.x < 128) {
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (cc < c) {
+      double t0 = 0.0, t1 = 0.0;
+      for (int k = 0; k < 8; ++k) { t0 += sh[0][k][threadIdx.x]; t1 += sh[1][k][threadIdx.x]; }
+      partial[(0 * STAT_SPLITS + split) * c + cc] = t0;
+      partial[(1 * STAT_SPLITS + split) * c + cc] = t1;
+    }
   }
+}
+
+// sum over the STAT_SPLITS partials of channel `ch` by one warp (lane-strided, then a shuffle tree): s0 / s1 valid in every lane
+__device__ __forceinline__ void warp_sum_partials(const double* __restrict__ partial, int c, int ch, int lane, double& s0, double& s1) {
+  s0 = 0.0;
+  s1 = 0.0;
+  for (int k = lane; k < STAT_SPLITS; k += 32) { s0 += partial[(0 * STAT_SPLITS + k) * c + ch]; s1 += partial[(1 * STAT_SPLITS + k) * c + ch]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
 }
 
 // Batch statistics from the partial sums (Keras BatchNormalization in training mode: biased variance, epsilon inside the
@@ -64,10 +121,11 @@ channel_sums_kernel(int mode, const float* __restrict__ z, const float* __restri
 __global__ void bn_finish_stats_kernel(const double* __restrict__ partial, int rows, int c, float eps,
                                        float* __restrict__ mean, float* __restrict__ invstd,
                                        float* __restrict__ batch_mean_out, float* __restrict__ batch_var_out) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;   // one warp per channel
   if (ch >= c) return;
-  double s0 = 0.0, s1 = 0.0;
-  for (int k = 0; k < STAT_SPLITS; ++k) { s0 += partial[(0 * STAT_SPLITS + k) * c + ch]; s1 += partial[(1 * STAT_SPLITS + k) * c + ch]; }
+  double s0, s1;
+  warp_sum_partials(partial, c, ch, lane, s0, s1);
+  if (lane != 0) return;
   const double mu = s0 / rows;
   double var = s1 / rows - mu * mu;
   if (var < 0.0) var = 0.0;
@@ -82,7 +140,28 @@ template <typename H>
 __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ skip, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, size_t total, int c, float* __restrict__ a,
-                                H* __restrict__ a16) {
+                                H* __restrict__ a16, int vec4) {
+  if (vec4) {   // four channels per thread (the host checked c % 4 == 0 and the 16-byte alignment of the parameter slices)
+    const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i >= total) return;
+    const int ch = static_cast<int>(i % c);
+    const float4 zv = *reinterpret_cast<const float4*>(z + i), g = *reinterpret_cast<const float4*>(gamma + ch),
+                 b = *reinterpret_cast<const float4*>(beta + ch), mu = *reinterpret_cast<const float4*>(mean + ch),
+                 is = *reinterpret_cast<const float4*>(invstd + ch);
+    float4 v = make_float4(g.x * ((zv.x - mu.x) * is.x) + b.x, g.y * ((zv.y - mu.y) * is.y) + b.y, g.z * ((zv.z - mu.z) * is.z) + b.z,
+                           g.w * ((zv.w - mu.w) * is.w) + b.w);
+    if (skip) {
+      const float4 sk = *reinterpret_cast<const float4*>(skip + i);
+      v.x += sk.x; v.y += sk.y; v.z += sk.z; v.w += sk.w;
+    }
+    v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
+    *reinterpret_cast<float4*>(a + i) = v;
+    if (a16) {
+      H h[4] = {from_f32<H>(v.x), from_f32<H>(v.y), from_f32<H>(v.z), from_f32<H>(v.w)};
+      *reinterpret_cast<uint2*>(a16 + i) = *reinterpret_cast<const uint2*>(h);
+    }
+    return;
+  }
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int ch = static_cast<int>(i % c);
@@ -101,10 +180,40 @@ __global__ void bn_backward_kernel(const float* __restrict__ z, const float* __r
                                    const float* da2, const float* __restrict__ gamma, const float* __restrict__ mean,
                                    const float* __restrict__ invstd, const float* __restrict__ sum_dy,
                                    const float* __restrict__ sum_dyx, int rows, int c,
-                                   float* __restrict__ dz, H* __restrict__ dz16, float* dskip, int dskip_accumulate) {
+                                   float* __restrict__ dz, H* __restrict__ dz16, float* dskip, int dskip_accumulate, int vec4) {
   // sum_dy / sum_dyx: the channel sums, = dbeta / dgamma as bn_param_grads_kernel left them in the gradient vector
   // (da2 and dskip may be the same buffer: each thread reads its element of da2 before it writes that element of dskip)
   const size_t total = static_cast<size_t>(rows) * c;
+  if (vec4) {   // four channels per thread
+    const size_t i4 = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= total) return;
+    const int ch4 = static_cast<int>(i4 % c);
+    const float4 zv = *reinterpret_cast<const float4*>(z + i4), av = *reinterpret_cast<const float4*>(a + i4);
+    float4 dv = *reinterpret_cast<const float4*>(da + i4);
+    if (da2) {
+      const float4 d2 = *reinterpret_cast<const float4*>(da2 + i4);
+      dv.x += d2.x; dv.y += d2.y; dv.z += d2.z; dv.w += d2.w;
+    }
+    const float4 g = *reinterpret_cast<const float4*>(gamma + ch4), mu = *reinterpret_cast<const float4*>(mean + ch4),
+                 is = *reinterpret_cast<const float4*>(invstd + ch4), s0 = *reinterpret_cast<const float4*>(sum_dy + ch4),
+                 s1 = *reinterpret_cast<const float4*>(sum_dyx + ch4);
+    const float4 dy = make_float4(av.x > 0.0f ? dv.x : 0.0f, av.y > 0.0f ? dv.y : 0.0f, av.z > 0.0f ? dv.z : 0.0f, av.w > 0.0f ? dv.w : 0.0f);
+    const float4 o = make_float4(g.x * is.x * (dy.x - s0.x / rows - (zv.x - mu.x) * is.x * (s1.x / rows)),
+                                 g.y * is.y * (dy.y - s0.y / rows - (zv.y - mu.y) * is.y * (s1.y / rows)),
+                                 g.z * is.z * (dy.z - s0.z / rows - (zv.z - mu.z) * is.z * (s1.z / rows)),
+                                 g.w * is.w * (dy.w - s0.w / rows - (zv.w - mu.w) * is.w * (s1.w / rows)));
+    *reinterpret_cast<float4*>(dz + i4) = o;
+    if (dz16) {
+      H h[4] = {from_f32<H>(o.x), from_f32<H>(o.y), from_f32<H>(o.z), from_f32<H>(o.w)};
+      *reinterpret_cast<uint2*>(dz16 + i4) = *reinterpret_cast<const uint2*>(h);
+    }
+    if (dskip) {
+      float4 sk = dy;
+      if (dskip_accumulate) { const float4 old = *reinterpret_cast<const float4*>(dskip + i4); sk.x += old.x; sk.y += old.y; sk.z += old.z; sk.w += old.w; }
+      *reinterpret_cast<float4*>(dskip + i4) = sk;
+    }
+    return;
+  }
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int ch = static_cast<int>(i % c);
@@ -120,10 +229,11 @@ __global__ void bn_backward_kernel(const float* __restrict__ z, const float* __r
 // dgamma / dbeta from the partial sums of channel_sums_kernel mode 1
 __global__ void bn_param_grads_kernel(const double* __restrict__ partial, int c, float* __restrict__ dgamma,
                                       float* __restrict__ dbeta) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;   // one warp per channel
   if (ch >= c) return;
-  double s0 = 0.0, s1 = 0.0;
-  for (int k = 0; k < STAT_SPLITS; ++k) { s0 += partial[(0 * STAT_SPLITS + k) * c + ch]; s1 += partial[(1 * STAT_SPLITS + k) * c + ch]; }
+  double s0, s1;
+  warp_sum_partials(partial, c, ch, lane, s0, s1);
+  if (lane != 0) return;
   dbeta[ch] = static_cast<float>(s0);
   dgamma[ch] = static_cast<float>(s1);
 }
@@ -171,6 +281,88 @@ gemm_kernel(const float* __restrict__ a, long a_si, long a_sk, const float* __re
     if (accumulate) v += *dst;
     if (relu) v = fmaxf(v, 0.0f);
     *dst = v;
+  }
+}
+
+// ---- the heads' 1x1 convolutions (model_chess.py:77-78,86-87) over all rows, both heads in one pass over the tower's output ----
+constexpr int HEADS_MAX_F = 8;   // policy + value filters
+
+// zp[row][pf], zv[row][vf] = top[row][:] . wp[:, :], wv[:, :]   (w: Keras (1, 1, C, f) = [c][f]); one warp per row
+__global__ void __launch_bounds__(256)
+head_conv_forward_kernel(const float* __restrict__ top, const float* __restrict__ wp, const float* __restrict__ wv, float* __restrict__ zp,
+                         float* __restrict__ zv, int rows, int c, int pf, int vf) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float acc[HEADS_MAX_F];
+#pragma unroll
+  for (int f = 0; f < HEADS_MAX_F; ++f) acc[f] = 0.0f;
+  for (int ch = lane; ch < c; ch += 32) {
+    const float x = top[static_cast<size_t>(row) * c + ch];
+#pragma unroll
+    for (int f = 0; f < HEADS_MAX_F; ++f) {
+      if (f < pf) acc[f] = fmaf(x, __ldg(wp + ch * pf + f), acc[f]);
+      else if (f < pf + vf) acc[f] = fmaf(x, __ldg(wv + ch * vf + f - pf), acc[f]);
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < HEADS_MAX_F; ++f) {
+    if (f >= pf + vf) break;
+    float v = acc[f];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) {
+      if (f < pf) zp[static_cast<size_t>(row) * pf + f] = v;
+      else zv[static_cast<size_t>(row) * vf + f - pf] = v;
+    }
+  }
+}
+
+// dtop[row][ch] = sum_f dzp[row][f] wp[ch][f] + sum_f dzv[row][f] wv[ch][f]: the gradient wrt the tower's output, written once
+__global__ void head_conv_backward_data_kernel(const float* __restrict__ dzp, const float* __restrict__ dzv, const float* __restrict__ wp,
+                                               const float* __restrict__ wv, float* __restrict__ dtop, int rows, int c, int pf, int vf) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(rows) * c) return;
+  const int ch = static_cast<int>(i % c);
+  const size_t row = i / c;
+  float v = 0.0f;
+  for (int f = 0; f < pf; ++f) v = fmaf(dzp[row * pf + f], __ldg(wp + ch * pf + f), v);
+  for (int f = 0; f < vf; ++f) v = fmaf(dzv[row * vf + f], __ldg(wv + ch * vf + f), v);
+  dtop[i] = v;
+}
+
+// dwp[ch][f] += sum over this block's rows of top[row][ch] dzp[row][f] (dwv alike); grid (c / 256, row splits); dwp / dwv zeroed by the caller
+__global__ void __launch_bounds__(256)
+head_conv_backward_weight_kernel(const float* __restrict__ top, const float* __restrict__ dzp, const float* __restrict__ dzv, float* __restrict__ dwp,
+                                 float* __restrict__ dwv, int rows, int c, int pf, int vf) {
+  const int ch = blockIdx.x * 256 + threadIdx.x;
+  const int per = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  __shared__ float sd[64][HEADS_MAX_F];
+  float acc[HEADS_MAX_F];
+#pragma unroll
+  for (int f = 0; f < HEADS_MAX_F; ++f) acc[f] = 0.0f;
+  const int ft = pf + vf;
+  for (int rb = r0; rb < r1; rb += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * ft; i += 256) {
+      const int r = rb + i / ft, f = i % ft;
+      sd[i / ft][f] = r < r1 ? (f < pf ? dzp[static_cast<size_t>(r) * pf + f] : dzv[static_cast<size_t>(r) * vf + f - pf]) : 0.0f;
+    }
+    __syncthreads();
+    if (ch < c) {
+      const int n = min(64, r1 - rb);
+      for (int r = 0; r < n; ++r) {
+        const float x = top[static_cast<size_t>(rb + r) * c + ch];
+#pragma unroll
+        for (int f = 0; f < HEADS_MAX_F; ++f)
+          if (f < ft) acc[f] = fmaf(x, sd[r][f], acc[f]);
+      }
+    }
+  }
+  if (ch >= c) return;
+#pragma unroll
+  for (int f = 0; f < HEADS_MAX_F; ++f) {
+    if (f < pf) atomicAdd(dwp + ch * pf + f, acc[f]);
+    else if (f < ft) atomicAdd(dwv + ch * vf + f - pf, acc[f]);
   }
 }
 
@@ -331,6 +523,28 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int taps, 
   };
   wf[static_cast<size_t>(oc) * taps * cin_pad + static_cast<size_t>(tap) * cin_pad + ic] = bits(v, f_fp16);
   if (wb) wb[static_cast<size_t>(ic) * taps * cout + static_cast<size_t>(taps - 1 - tap) * cout + oc] = bits(v, b_fp16);
+}
+
+// the same for every convolution of the network in ONE launch: blockIdx.y = layer
+struct PackLayer { const float* w; uint16_t* wf; uint16_t* wb; int taps, cin, cin_pad, cout; };
+constexpr int PACK_MAX_LAYERS = 48;
+struct PackTable { PackLayer layer[PACK_MAX_LAYERS]; };
+__global__ void pack_all_conv_weights_kernel(const PackTable tab, int f_fp16, int b_fp16) {
+  const PackLayer& L = tab.layer[blockIdx.y];
+  const size_t total = static_cast<size_t>(L.taps) * L.cin * L.cout;
+  auto bits = [](float x, int fp16) -> uint16_t {
+    if (fp16) { const __half h = __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f)); return *reinterpret_cast<const uint16_t*>(&h); }
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    return *reinterpret_cast<const uint16_t*>(&h);
+  };
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int oc = static_cast<int>(i % L.cout);
+    const int ic = static_cast<int>((i / L.cout) % L.cin);
+    const int tap = static_cast<int>(i / (static_cast<size_t>(L.cout) * L.cin));
+    const float v = L.w[i];
+    L.wf[static_cast<size_t>(oc) * L.taps * L.cin_pad + static_cast<size_t>(tap) * L.cin_pad + ic] = bits(v, f_fp16);
+    if (L.wb) L.wb[static_cast<size_t>(ic) * L.taps * L.cout + static_cast<size_t>(L.taps - 1 - tap) * L.cout + oc] = bits(v, b_fp16);
+  }
 }
 
 // rows [board * 64 + square][c] fp32  ->  K-major operand of the weight-gradient GEMM, bf16:
