@@ -95,6 +95,12 @@ struct caz_handle {
   bool tw_enabled = true;    // CAZ_NO_TOWER=1 keeps the per-layer launch chain (conv_tc2.cuh)
   int tw_mode = 0;           // caz_set_fused_tower / CAZ_TOWER_MODE: 0 = by batch size, 1 / 2 = forced groups per pair
   CUtensorMap tw_tm_w_tower; // all tower layers' weights as one matrix, box 64 x filters / 2
+  // the tower's intermediate activations: ONE slab [fp32 stream | 16-bit x | 16-bit y] for <= 8 boards per CTA pair, behind an
+  // L2 persistence window (CAZ_NO_L2_PERSIST=1: no window)
+  void* tw_scratch = nullptr;
+  size_t tw_scratch_bytes = 0;
+  int tw_scratch_boards = 0;
+  CUtensorMap tw_tm_x, tw_tm_y;
   long long* tw_trace = nullptr;   // [64][8] clock stamps (caz_debug_tower_trace)
   bool tw_trace_on = false;
   // small-batch persistent tower kernel (conv_sb.cuh)
@@ -870,6 +876,39 @@ int setup_tower(caz_handle* h) {
     h->tw_tm_w_tower = h->convs[0].tmap_w2;
   }
   CU_TRY(h, cudaFuncSetAttribute(caz::tw::tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::tw::SMEM_BYTES));
+  if (!h->tw_scratch) {
+    // Scratch of the one-launch tower: every CTA pair rewrites the same <= 8 boards (two groups) layer after layer.  Left to
+    // itself the L2 writes those dirty lines back to HBM almost as fast as they are produced (3.1 GB per launch at 4 096
+    // boards, although every line is rewritten two layers later); marked PERSISTING they stay: 0.8 GB, and the power the HBM
+    // traffic cost goes to the SM clock (+3.8 % positions/s, measured back to back on one box).
+    const int boards = std::min((h->max_batch + 3) & ~3, 8 * (h->num_sms / 2));
+    const size_t esz = 2, f32 = (size_t)boards * 64 * a.filters * 4, h16 = (size_t)boards * 64 * a.filters * esz;
+    h->tw_scratch_boards = boards;
+    h->tw_scratch_bytes = f32 + 2 * h16;
+    CU_TRY(h, cudaMalloc(&h->tw_scratch, h->tw_scratch_bytes));
+    CU_TRY(h, cudaMemset(h->tw_scratch, 0, h->tw_scratch_bytes));
+    char* base = static_cast<char*>(h->tw_scratch);
+    int rc;
+    if ((rc = make_halo_tmap(h, &h->tw_tm_x, base + f32, a.filters, a.block_kernel, 2, boards))) return rc;
+    if ((rc = make_halo_tmap(h, &h->tw_tm_y, base + f32 + h16, a.filters, a.block_kernel, 2, boards))) return rc;
+    if (!getenv("CAZ_NO_L2_PERSIST")) {
+      cudaDeviceProp prop;
+      CU_TRY(h, cudaGetDeviceProperties(&prop, h->device));
+      size_t cur = 0;
+      cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+      const size_t lim = std::min(std::max(cur, h->tw_scratch_bytes), (size_t)prop.persistingL2CacheMaxSize);
+      cudaStreamAttrValue av = {};
+      av.accessPolicyWindow.base_ptr = h->tw_scratch;
+      av.accessPolicyWindow.num_bytes = std::min(h->tw_scratch_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+      av.accessPolicyWindow.hitRatio = lim >= h->tw_scratch_bytes ? 1.0f : (float)((double)lim / (double)h->tw_scratch_bytes);
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      // (a device without the feature, or a refused limit, only costs the speed-up)
+      if (lim > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess)
+        cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+      cudaGetLastError();
+    }
+  }
   if (!h->tw_trace) {
     CU_TRY(h, cudaMalloc(&h->tw_trace, 64 * 8 * sizeof(long long)));
     CU_TRY(h, cudaMemset(h->tw_trace, 0, 64 * 8 * sizeof(long long)));
@@ -891,9 +930,13 @@ int launch_tower(caz_handle* h, int batch) {
   args.fmt = operand_fmt(h);
   args.pdl = h->pdl ? 1 : 0;   // chained to the pack kernel before it and the head kernels after it
   args.bias_all = h->bias_all;
-  args.xf = static_cast<float*>(h->act[2]);
-  args.act0 = static_cast<__nv_bfloat16*>(h->act[0]);
-  args.act1 = static_cast<__nv_bfloat16*>(h->act[1]);
+  {
+    char* base = static_cast<char*>(h->tw_scratch);
+    const size_t f32 = (size_t)h->tw_scratch_boards * 64 * a.filters * 4, h16 = (size_t)h->tw_scratch_boards * 64 * a.filters * 2;
+    args.xf = reinterpret_cast<float*>(base);
+    args.act0 = reinterpret_cast<__nv_bfloat16*>(base + f32);
+    args.act1 = reinterpret_cast<__nv_bfloat16*>(base + f32 + h16);
+  }
   args.head_w = h->head_w;
   args.head_b = h->head_b;
   args.featp = h->featp;
@@ -920,7 +963,7 @@ int launch_tower(caz_handle* h, int batch) {
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = h->pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, caz::tw::tower_kernel, h->tmap_in, h->tmap_act[0], h->tmap_act[1], h->convs[0].tmap_w2,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, caz::tw::tower_kernel, h->tmap_in, h->tw_tm_x, h->tw_tm_y, h->convs[0].tmap_w2,
                                      h->tw_tm_w_tower, args);
   if (e != cudaSuccess) return fail(h, CAZ_ERR_CUDA, fmt("launch of tower_kernel failed: %s", cudaGetErrorString(e)));
   return check_launch(h, "tower_kernel");
@@ -1186,6 +1229,7 @@ void caz_destroy(caz_handle* h) {
   if (h->sb_hstats) cudaFree(h->sb_hstats);
   if (h->sb_trace) cudaFree(h->sb_trace);
   if (h->tw_trace) cudaFree(h->tw_trace);
+  if (h->tw_scratch) cudaFree(h->tw_scratch);
   if (h->sb_sm_near) cudaFree(h->sb_sm_near);
   void* ptrs[] = {h->pfc_wb, h->vfc1_wb, h->head_w, h->head_b, h->pfc_w, h->pfc_b, h->vfc1_w, h->vfc1_b, h->vfc2_w, h->vfc2_b, h->in_act,
                   h->act[0], h->act[1], h->act[2], h->featp, h->featv, h->vhid, h->a3p, h->a3v, h->w3p, h->w3v, h->bias3p, h->d_planes, h->d_policy, h->d_value,
