@@ -269,6 +269,39 @@ def run_reference(args, world, rank):
         "gpu_launches": 0}))
 
 
+def training_leg(args, cfg, weights, ev, local, rank, world, batch=384):
+    """SURVEY.md 8 f4 (not the headline metric): the `opt` worker's step -- training-mode BatchNormalization, cross-entropy x 1.25 +
+    MSE, l2, Adam (worker/optimize.py:79-103) -- at batch 384 per GPU on this net, tensor-core build.  With N > 1 every rank
+    trains on its own shard and the flat gradient vector is summed with torch.distributed.all_reduce (NCCL): the one collective
+    of this repository.  Returns positions/s over all ranks (host-visible wall time, max over ranks)."""
+    import torch
+    import chess_alpha_zero_b200 as caz
+    from chess_alpha_zero_b200 import encoder
+    planes = ev.encode(encoder.fens_to_records(encoder.synthetic_fens(batch, seed=300 + rank)))
+    rng = np.random.RandomState(rank)
+    pt = np.zeros((batch, ev.n_labels), np.float32)
+    for i in range(batch):
+        idx = rng.permutation(ev.n_labels)[:30]
+        pt[i, idx] = rng.dirichlet([0.5] * 30)
+    vt = rng.uniform(-1, 1, size=batch).astype(np.float32)
+    tr = caz.Trainer(cfg, weights, device=local, precision="bf16", max_batch=batch)
+    losses = [tr.train_on_batch(planes, pt, vt)["loss"] for _ in range(3)]
+    barrier(world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.train_steps):
+        losses.append(tr.train_on_batch(planes, pt, vt)["loss"])
+    dt = max_over_ranks(time.perf_counter() - t0, world)
+    digest = float(np.abs(np.concatenate([v.reshape(-1) for v in tr.weights().values()])).sum())
+    same = max_over_ranks(digest, world) == -max_over_ranks(-digest, world)
+    tr.close()
+    return {"metric": "training positions/s (forward + backward + Adam, batch 384 per GPU)", "value": world * batch * args.train_steps / dt,
+            "unit": UNIT, "ms_per_step": 1e3 * dt / args.train_steps, "steps": args.train_steps, "n_gpus": world, "precision": "bf16 (mixed)",
+            "approx_tflops": 3 * flops_per_position(args.blocks) * world * batch * args.train_steps / dt / 1e12,
+            "loss_first_last": [losses[0], losses[-1]], "ranks_hold_identical_weights": bool(same),
+            "collective": "torch.distributed.all_reduce (NCCL) of the flat fp32 gradient vector, every step" if world > 1 else None}
+
+
 def latency_probe(ev, planes16, calls=1000):
     """p50 of the host-visible call at batch 16 (pinned buffers), and of the device part (CUDA events)."""
     import torch
@@ -325,6 +358,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16_pure", "fp16", "fp32"])
     ap.add_argument("--min-seconds", type=float, default=1.0,
                     help="repeat the K-step loop back to back until the timed region is at least this long")
+    ap.add_argument("--train-steps", type=int, default=10,
+                    help="SURVEY 8 f4: timed steps of the training leg (forward + backward + Adam at batch 384 per GPU, gradients "
+                         "all-reduced with NCCL when N > 1; 0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--selfplay-seconds", type=float, default=8.0,
@@ -470,6 +506,9 @@ def main():
                         "games_per_hour_at_80_moves": sum_over_ranks(mine["games_per_hour_at_80_moves"], world),
                         "groups": mine["groups"], "host_threads_per_group": mine["host_threads_per_group"],
                         "host_cores": mine["host_cores"], "rank0": mine}
+    training = None
+    if args.train_steps > 0:
+        training = training_leg(args, cfg, weights, ev, local, rank, world)
     if rank != 0:
         return
     peaks = measured_peaks()
@@ -538,6 +577,8 @@ def main():
                               "dram_bytes_per_pass": sb.get("dram_bytes_per_pass"), "ncu_source": sb.get("source")}
     if selfplay is not None:
         out["selfplay"] = selfplay
+    if training is not None:
+        out["training"] = training
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(cfg, weights, host_batches[0])
     print(json.dumps(out))
