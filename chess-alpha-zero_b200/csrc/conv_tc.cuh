@@ -50,7 +50,8 @@ constexpr int EPI_WARP0 = 4;
 constexpr int ACC_STAGES = 2;
 constexpr int ACC_COLS = 256;                          // TMEM columns per accumulator stage (N <= 256)
 constexpr int A_RING_BYTES = 2 * (10 * 2 * 10 * 128);  // 51 200: two 3x3 chunk tiles (or one 5x5 / 7x7 one)
-constexpr int MAX_A_SLOTS = 3;   // 3x3 and larger chunk tiles: two fit the ring; the 16 KB tiles of the GEMM uses (ksize 1): three
+constexpr int MAX_A_SLOTS = 8;   // 3x3 and larger chunk tiles: two fit the ring; the 16 KB tiles of the GEMM uses (ksize 1): three, or up to
+                                 // eight in the weight-gradient GEMM, which re-balances the two rings (conv_tc2.cuh)
 constexpr int B_STAGE_BYTES = 256 * BLOCK_K * 2;       // 32 KiB (N = 256 rows)
 constexpr int EPI_WARP_BYTES = 4096;                   // per-warp 32x32 fp32 transpose buffer
 constexpr int HEAD_MAX_F = 8;                          // policy + value 1x1 filters fused into the last epilogue

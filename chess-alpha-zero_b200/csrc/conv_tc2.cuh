@@ -45,8 +45,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + A_RING_BYTES;
-  uint8_t* smem_epi = smem_b + B_STAGES * B_STAGE_BYTES;
+  uint8_t* smem_epi = smem + A_RING_BYTES + B_STAGES * B_STAGE_BYTES;
   float* s_bias = reinterpret_cast<float*>(smem_epi + 4 * tc::EPI_WARP_BYTES);
   float* s_head = s_bias + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + tc::EPI_BYTES);
@@ -62,9 +61,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   const int lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
+  const bool wg = args.wg_splits > 0;               // weight-gradient GEMM (see ConvArgs): work items are (tap, K split)
   const int pair0 = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1;
   const int num_pairs = (args.num_tiles + 1) >> 1;
-  const bool wg = args.wg_splits > 0;               // weight-gradient GEMM (see ConvArgs): work items are (tap, K split)
   const int num_work = wg ? args.wg_k * args.wg_k * args.wg_splits : num_pairs * args.n_tiles;   // else (board-pair pair, N tile)
   // K-coordinate shift of the B operand for the tap of work item t, and its first K chunk
   auto wg_shift = [&](int t) -> int { const int tap = t / args.wg_splits; return (tap / args.wg_k - (args.wg_k - 1) / 2) * args.wg_pitch + (tap % args.wg_k - (args.wg_k - 1) / 2) * args.wg_dx; };
@@ -75,9 +74,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   const int k = args.ksize, pad = (k - 1) / 2, hw = 8 + k - 1;
   const int rb = args.row_bytes, kblk = rb >> 1;
   const int plane_bytes = hw * 2 * hw * rb;
-  const int a_slots = A_RING_BYTES / plane_bytes < MAX_A_SLOTS ? A_RING_BYTES / plane_bytes : MAX_A_SLOTS;
   const int n_half = args.n >> 1;
   const uint32_t b_bytes = static_cast<uint32_t>(n_half) * rb;
+  // Ring geometry.  Convolutions: 8 weight stages of 16 KB, and as many chunk tiles as fit 51 KB.  The weight-gradient GEMM
+  // streams BOTH operands once (16 KB of A and n/2 rows of B per K chunk, four MMAs each): its weight stages shrink to what
+  // a chunk needs, six of them, and the rest of the operand area becomes activation slots (five at 256 columns, eight at 32)
+  // -- with three slots the GEMM waited for A most of the time (63 -> 46 us per 3x3 layer with three, measured).
+  const int bstage_bytes = wg ? static_cast<int>((b_bytes + 1023u) & ~1023u) : B_STAGE_BYTES;
+  const int n_bstages = wg ? 6 : B_STAGES;
+  const int a_room = wg ? A_RING_BYTES + B_STAGES * B_STAGE_BYTES - n_bstages * bstage_bytes : A_RING_BYTES;
+  const int a_slots = a_room / plane_bytes < MAX_A_SLOTS ? a_room / plane_bytes : MAX_A_SLOTS;
+  uint8_t* smem_b = smem + (wg ? a_slots * plane_bytes : A_RING_BYTES);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_halo);
@@ -134,11 +141,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_expect_tx(&b_full[stage], 2 * b_bytes);   // both CTAs' halves
             const int col = wg ? (wg_kc0(t) + kc) * kblk + wg_shift(t) : (tap * args.kchunks + kc) * kblk;
-            ptx::tma_load_2d_2cta(smem_b + stage * B_STAGE_BYTES, &tmap_w, ptx::mapa_u32(&b_full[stage], 0),
+            ptx::tma_load_2d_2cta(smem_b + stage * bstage_bytes, &tmap_w, ptx::mapa_u32(&b_full[stage], 0),
                                   col, nt * args.n + static_cast<int>(rank) * n_half);
           }
           __syncwarp();
-          if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == n_bstages) { stage = 0; phase ^= 1; }
         }
     }
   } else if (warp == 3) {
@@ -188,7 +195,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
               ptx::tcgen05_fence_after();
               if (ptx::elect_one()) {
                 const uint64_t adesc = a_plane + static_cast<uint64_t>((dy * 2 * hw + dx) * tap_rows16);
-                const uint64_t bdesc = b_desc0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
+                const uint64_t bdesc = b_desc0 + static_cast<uint64_t>((stage * bstage_bytes) >> 4);
                 const uint32_t first = (kc | dy | dx) == 0 ? 0u : 1u;
                 ptx::mma_bf16_ss_2cta(tmem_d, adesc, bdesc, idesc, first);
                 ptx::mma_bf16_ss_2cta(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
@@ -203,7 +210,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
                 }
               }
               __syncwarp();
-              if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+              if (++stage == n_bstages) { stage = 0; phase ^= 1; }
             }
           if (++slot == a_slots) { slot = 0; a_phase ^= 1; }
         }
