@@ -288,6 +288,35 @@ def test_fused_tower_matches_per_layer_chain(net, ev_bf16, batch):
         ev_bf16.set_small_batch_limit(-1)
 
 
+def test_fused_tower_soak(net, ev_bf16):
+    """Random batch sizes above the small-batch kernel's range, queued back to back for a few seconds with small batches in
+    between (the scratch slab and the act_ready barriers are reused launch after launch): every checked result is
+    bit-identical to the per-layer chain's."""
+    import time
+    import torch
+    x = np.ascontiguousarray(np.concatenate([net[2], net[2][::-1]]))
+    sizes = [73, 100, 148, 149, 256, 296, 297, 300, 512]
+    ev_bf16.set_fused_tower(0)
+    want = {b: ev_bf16.predict_on_batch(x[:b]) for b in sizes}
+    ev_bf16.set_fused_tower(-1)
+    d_x = torch.from_numpy(x).cuda()
+    d_p = torch.empty((512, 1968), device="cuda")
+    d_v = torch.empty((512,), device="cuda")
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(1)
+    t0, launches = time.time(), 0
+    while time.time() - t0 < 3.0:
+        for _ in range(20):
+            b = int(rng.choice(sizes)) if rng.random() < 0.8 else int(rng.integers(1, 73))
+            ev_bf16.eval_device(d_x.data_ptr(), b, d_p.data_ptr(), d_v.data_ptr())
+        b = int(rng.choice(sizes))
+        ev_bf16.eval_device(d_x.data_ptr(), b, d_p.data_ptr(), d_v.data_ptr())
+        ev_bf16.sync()
+        launches += 21
+        assert np.array_equal(d_p[:b].cpu().numpy(), want[b][0]) and np.array_equal(d_v[:b].cpu().numpy(), want[b][1].reshape(-1)), (b, launches)
+    assert launches > 2000
+
+
 def test_small_batch_persistent_kernel(net_default):
     """Batches <= 64 run the persistent whole-tower kernel (halo tile + shifted UMMA descriptors, weights streamed
     from L2, grid barriers).  Same north_star gate as the per-layer path, and batch-size independent bit for bit."""
