@@ -32,6 +32,9 @@ class Evaluator:
         rc = self._lib.caz_create(ctypes.byref(self.arch), tensors, len(keep), self.device,
                                   _PRECISIONS[precision], int(max_batch), ctypes.byref(self._handle))
         _lib.check(None, rc)
+        self.weights = weights                 # {Keras name: array}: what fit() starts from and ChessModel.save writes
+        self._trainer = None
+        self._loss_weights = None
         self.max_batch = int(max_batch)
         self.n_labels = int(self.arch.n_labels)
         self.input_planes = int(self.arch.input_planes)
@@ -54,6 +57,37 @@ class Evaluator:
         tensors, keep = self._pack(weights)
         with self._lock:
             _lib.check(self._handle, self._lib.caz_reload(self._handle, tensors, len(keep)))
+        self.weights = weights
+
+    # -- training: the two Keras calls OptimizeWorker makes on model.model (worker/optimize.py:88-103) ------------
+    def compile(self, optimizer=None, loss=None, loss_weights=None, **_):
+        """model.compile(optimizer=Adam(), loss=['categorical_crossentropy', 'mean_squared_error'], loss_weights=[1.25, 1.0])
+        (optimize.py:97-103).  The optimizer is Adam with the Keras 2.0.8 defaults whatever is passed (the reference passes
+        Adam()); the two losses are the ones the reference names; only loss_weights is a free parameter."""
+        if loss is not None and list(loss) != ["categorical_crossentropy", "mean_squared_error"]:
+            raise ValueError("only loss=['categorical_crossentropy', 'mean_squared_error'] is implemented")
+        self._loss_weights = [float(v) for v in loss_weights] if loss_weights is not None else [1.0, 1.0]
+        self._trainer = None
+
+    def fit(self, x, y, batch_size=32, epochs=1, shuffle=True, validation_split=0.0, callbacks=None, precision="bf16", seed=None, **_):
+        """model.fit(state_ary, [policy_ary, value_ary], batch_size=..., epochs=..., shuffle=True, validation_split=0.02,
+        callbacks=[...]) (optimize.py:88-93) on the GPU (trainer.py); afterwards this evaluator predicts with the trained weights
+        (inference-mode BatchNormalization with the updated moving statistics).  Returns an object with a Keras-like
+        ``.history`` dict.  Callbacks are ignored."""
+        from .trainer import TrainConfig, Trainer
+        if self._loss_weights is None:
+            raise RuntimeError("compile() first, as Keras demands")
+        if self._trainer is None or self._trainer.max_batch < batch_size or self._trainer.precision != precision:
+            if self._trainer is not None:
+                self._trainer.close()
+            cfg = TrainConfig.normal(policy_loss_weight=self._loss_weights[0], value_loss_weight=self._loss_weights[1])
+            self._trainer = Trainer(self.keras_config, self.weights, device=self.device, precision=precision, max_batch=batch_size, config=cfg)
+        hist = self._trainer.fit(x, y, batch_size=batch_size, epochs=epochs, shuffle=shuffle, validation_split=validation_split, seed=seed)
+        self.reload(self._trainer.weights())
+
+        class History:
+            history = hist
+        return History()
 
     # -- the operator ----------------------------------------------------------------------------
     def predict_on_batch(self, data, legal_mask=None):
@@ -258,7 +292,13 @@ class Evaluator:
         _lib.check(self._handle, self._lib.caz_profile_read(self._handle, ms, n, 1 if reset else 0))
         return {name: {"ms": float(ms[i]), "launches": int(n[i])} for i, name in enumerate(_lib.STAGE_NAMES)}
 
+    def _close_trainer(self):
+        if getattr(self, "_trainer", None) is not None:
+            self._trainer.close()
+            self._trainer = None
+
     def close(self):
+        self._close_trainer()
         if getattr(self, "_handle", None) and self._handle.value:
             self._lib.caz_destroy(self._handle)
             self._handle = ctypes.c_void_p()

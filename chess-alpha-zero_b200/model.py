@@ -85,5 +85,7 @@ class ChessModel:
             raise RuntimeError("nothing to save: call build() or load() first")
         with open(config_path, "wt") as f:
             json.dump(self.keras_config, f)
+        if self.model is not None:
+            self.weights = self.model.weights      # model.model.fit(...) may have trained them (worker/optimize.py:88-93)
         keras_graph.save_weight_file(weight_path, self.weights, self.keras_config)
         self.digest = self.fetch_digest(weight_path)

@@ -143,3 +143,31 @@ def test_tensor_core_build_trains():
     assert np.allclose(p.sum(1), 1, atol=1e-4) and np.isfinite(v).all()
     ev.close()
     tr.close()
+
+
+def test_optimize_worker_calls_on_chessmodel(tmp_path):
+    """The three things OptimizeWorker does with the model (worker/optimize.py:88-115): model.model.compile(...),
+    model.model.fit(state_ary, [policy_ary, value_ary], batch_size, epochs, shuffle, validation_split, callbacks), model.save(...)
+    -- on caz.ChessModel, whose .model is the CUDA evaluator; the saved weights load into a fresh model that predicts the same."""
+    import json
+    from chess_alpha_zero_b200 import keras_graph
+    cfg = oweights.keras_config(filters=64, blocks=2)
+    w = oweights.synth_weights(cfg, seed=1, recipe="keras_default")
+    x, pt, vt = _data(96, seed=7)
+    x[:, 16] = 0
+    model = caz.ChessModel(caz.Config("mini"), precision="bf16", max_batch=64)
+    model._install(cfg, w)
+    before = model.model.predict_on_batch(x[:8])
+    model.model.compile(optimizer=None, loss=["categorical_crossentropy", "mean_squared_error"], loss_weights=[1.25, 1.0])
+    hist = model.model.fit(x, [pt, vt], batch_size=32, epochs=3, shuffle=True, validation_split=0.02, callbacks=[object()])
+    assert len(hist.history["loss"]) == 3 and hist.history["loss"][-1] < hist.history["loss"][0]
+    after = model.model.predict_on_batch(x[:8])
+    assert np.abs(after[0] - before[0]).max() > 1e-6                  # the evaluator now runs the trained weights
+    cpath, wpath = str(tmp_path / "model_config.json"), str(tmp_path / "model_weight.h5")
+    model.save(cpath, wpath)
+    fresh = caz.ChessModel(caz.Config("mini"), precision="bf16", max_batch=64)
+    assert fresh.load(cpath, wpath)
+    again = fresh.model.predict_on_batch(x[:8])
+    assert np.array_equal(again[0], after[0]) and np.array_equal(again[1], after[1])
+    model.model.close()
+    fresh.model.close()
