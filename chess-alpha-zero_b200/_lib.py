@@ -22,7 +22,7 @@ STAGE_NAMES = ("pack", "stem", "tower", "heads")
 
 SYMBOLS = (
     "caz_create", "caz_reload", "caz_destroy", "caz_eval", "caz_eval_device", "caz_eval_records", "caz_sync",
-    "caz_encode", "caz_push_priors", "caz_puct_select", "caz_last_error", "caz_abi_version", "caz_max_batch",
+    "caz_encode", "caz_push_priors", "caz_puct_select", "caz_puct_select_device", "caz_last_error", "caz_abi_version", "caz_max_batch",
     "caz_precision", "caz_stream", "caz_kernel_launches", "caz_weight_bytes", "caz_inexact_weights", "caz_profile", "caz_profile_read",
     "caz_host_alloc", "caz_host_free", "caz_debug_conv_layer", "caz_set_small_batch_limit", "caz_set_fused_tower", "caz_debug_tower_trace", "caz_debug_sb_trace", "caz_submit", "caz_submit_records", "caz_submit_records_priors", "caz_collect",
     "caz_train_create", "caz_train_destroy", "caz_train_last_error", "caz_train_param_count", "caz_train_num_params", "caz_train_steps",
@@ -78,6 +78,7 @@ def load():
     lib.caz_eval_device.argtypes = [vp, vp, i32, vp, vp, vp, u32]
     lib.caz_eval_records.argtypes = [vp, vp, i32, vp, vp, vp, u32]
     lib.caz_sync.argtypes = [vp]
+    lib.caz_puct_select_device.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, f64, f64, vp]
     lib.caz_submit.argtypes = [vp, vp, i32, vp, vp, vp, u32, ctypes.POINTER(i32)]
     lib.caz_submit_records.argtypes = [vp, vp, i32, vp, vp, vp, u32, ctypes.POINTER(i32)]
     lib.caz_submit_records_priors.argtypes = [vp, vp, i32, vp, vp, vp, vp, ctypes.POINTER(i32)]

@@ -1698,6 +1698,22 @@ int caz_puct_select(caz_handle* h, const int32_t* offsets, int32_t n_nodes, cons
   return CAZ_OK;
 }
 
+int caz_puct_select_device(caz_handle* h, const int32_t* d_offsets, int32_t n_nodes, const int32_t* d_n, const double* d_q,
+                            const double* d_p, const int32_t* d_sum_n, const double* d_noise, const uint8_t* d_is_root, double c_puct,
+                            double noise_eps, int32_t* d_best_edge) {
+  if (!h) return CAZ_ERR_INVALID;
+  if (n_nodes == 0) return CAZ_OK;
+  if (!d_offsets || !d_n || !d_q || !d_p || !d_sum_n || !d_best_edge || n_nodes < 0)
+    return fail(h, CAZ_ERR_INVALID, "caz_puct_select_device: bad argument");
+  int rc;
+  if ((rc = set_device(h))) return rc;
+  const bool with_noise = d_noise && d_is_root;
+  const int wpb = 8;
+  caz::puct_select_kernel<<<(n_nodes + wpb - 1) / wpb, wpb * 32, 0, h->stream>>>(d_offsets, n_nodes, d_n, d_q, d_p, d_sum_n, with_noise ? d_noise : nullptr,
+                                                                               with_noise ? d_is_root : nullptr, c_puct, noise_eps, d_best_edge);
+  return check_launch(h, "puct_select_kernel");
+}
+
 int caz_debug_conv_layer(caz_handle* h, int32_t layer, const float* in, const float* residual, int32_t batch,
                          float* out) {
   if (!h) return CAZ_ERR_INVALID;

@@ -184,6 +184,11 @@ int caz_push_priors(caz_handle* h, const float* policy, int32_t n_labels, const 
 int caz_puct_select(caz_handle* h, const int32_t* offsets, int32_t n_nodes, const int32_t* n, const double* q,
                     const double* p, const int32_t* sum_n, const double* noise, const uint8_t* is_root,
                     double c_puct, double noise_eps, int32_t* best_edge);
+/* The same on DEVICE-resident node arrays (a driver that keeps its trees on the GPU): enqueues the kernel on the handle's
+ * stream and returns; no copies, no synchronisation (caz_sync or a stream event before reading d_best_edge). */
+int caz_puct_select_device(caz_handle* h, const int32_t* d_offsets, int32_t n_nodes, const int32_t* d_n, const double* d_q,
+                            const double* d_p, const int32_t* d_sum_n, const double* d_noise, const uint8_t* d_is_root,
+                            double c_puct, double noise_eps, int32_t* d_best_edge);
 
 /* --- introspection / measurement ------------------------------------------------------------ */
 const char* caz_last_error(const caz_handle* h); /* h == NULL: last error of a failed caz_create */
