@@ -109,6 +109,16 @@ def test_push_priors_and_select_bit_exact(ev_fp32, golden_dir):
     for i in range(0, 4096, 7):
         s = slice(off[i], off[i + 1])
         assert best[i] == opuct.select(n[s], q[s], p[s], sum_n[i], 1.5), i
+    # the same kernel on device-resident node arrays (caz_puct_select_device: no copies, asynchronous on the handle's stream)
+    from chess_alpha_zero_b200 import _lib
+    d = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (off, n, q, p, sum_n)]
+    d_best = torch.full((4096,), -7, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    rc = _lib.load().caz_puct_select_device(ev_fp32._handle, d[0].data_ptr(), 4096, d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
+                                            d[4].data_ptr(), None, None, 1.5, 0.0, d_best.data_ptr())
+    assert rc == 0
+    ev_fp32.sync()
+    assert np.array_equal(d_best.cpu().numpy(), best)
 
 
 # ---- a2/a3: one layer at a time -----------------------------------------------------------------
