@@ -26,7 +26,8 @@ SYMBOLS = (
     "caz_precision", "caz_stream", "caz_kernel_launches", "caz_weight_bytes", "caz_inexact_weights", "caz_profile", "caz_profile_read",
     "caz_host_alloc", "caz_host_free", "caz_debug_conv_layer", "caz_set_small_batch_limit", "caz_set_fused_tower", "caz_debug_tower_trace", "caz_debug_sb_trace", "caz_submit", "caz_submit_records", "caz_submit_records_priors", "caz_collect",
     "caz_train_create", "caz_train_destroy", "caz_train_last_error", "caz_train_param_count", "caz_train_num_params", "caz_train_steps",
-    "caz_train_forward_backward", "caz_train_apply", "caz_train_read", "caz_train_read_outputs", "caz_train_grad_device_ptr",
+    "caz_train_forward_backward", "caz_train_forward_backward_begin", "caz_train_forward_backward_end", "caz_train_wait_gradients",
+    "caz_train_gradient_split", "caz_train_apply", "caz_train_read", "caz_train_read_outputs", "caz_train_grad_device_ptr",
 )
 
 

@@ -44,7 +44,8 @@ struct caz_trainer {
   // batch-sized buffers
   float *x0 = nullptr, *planes = nullptr, *policy_t = nullptr, *value_t = nullptr;
   float *featp = nullptr, *logits = nullptr, *dlogits = nullptr, *probs = nullptr, *featv = nullptr, *hid = nullptr, *vpre = nullptr,
-        *vout = nullptr, *dvpre = nullptr, *dhid = nullptr, *dfeatp = nullptr, *dfeatv = nullptr;
+        *vout = nullptr, *dvpre = nullptr, *dhid = nullptr, *dfeatp = nullptr, *dfeatv = nullptr, *gemm_partial = nullptr;
+  size_t gemm_partial_floats = 0;
   float *d_a = nullptr, *d_b = nullptr, *d_skip = nullptr, *dz = nullptr, *dzp = nullptr, *dzv = nullptr, *dap = nullptr, *dav = nullptr;
   float *w_flip = nullptr, *zero_bias = nullptr;
   double *partial = nullptr, *loss_acc = nullptr;
@@ -52,6 +53,12 @@ struct caz_trainer {
   // the ~230 launches of a step are captured once per batch size and replayed as one CUDA graph (CAZ_TRAIN_NO_GRAPH=1: off)
   bool use_graph = true;
   std::vector<std::pair<int, cudaGraphExec_t>> graphs;
+  // data-parallel overlap: ev_mid fires when the gradients of the upper half of the network (vector elements >= grad_split)
+  // are complete, ev_end when all are -- the caller's all-reduce stream waits on them (caz_train_wait_gradients)
+  cudaEvent_t ev_mid = nullptr, ev_end = nullptr;
+  size_t grad_split = 0;
+  bool capturing = false;
+  int pending_batch = 0;
   // 16-bit builds (tensor-core convolutions): forward fp16 x fp16, input and weight gradients bf16 x bf16, fp32 accumulation
   bool tc = false;
   int num_sms = 0, nb = 0;                 // nb: max_batch rounded up to 64 (board-minor extent of the weight-gradient operands)
@@ -94,6 +101,7 @@ int tr_alloc(caz_trainer* t, T** p, size_t count) {
   return CAZ_OK;
 }
 
+constexpr int HEAD_WGRAD_SPLITS = 128;   // row slices of the heads' 1x1 weight gradients
 unsigned blocks_for(size_t n, int per = 256) { return static_cast<unsigned>((n + per - 1) / per); }
 
 // "same" convolution on fp32 NHWC rows, raw output (no bias, no activation): out = conv(in, w) (+ add)
@@ -109,13 +117,19 @@ int tr_conv_fp32(caz_trainer* t, const float* in, const float* w, const float* a
   return tr_launch_ok(t, "conv_fp32_kernel");
 }
 
-// C[m][n] = A . B (+ bias) with arbitrary strides (see gemm_kernel); ksplit > 1: C is cleared and the partial sums are added atomically
+// C[m][n] = A . B (+ bias) with arbitrary strides (see gemm_kernel); ksplit > 1 (no bias, no relu): K in ksplit slices whose
+// partial products go through t->gemm_partial and are summed in a fixed order
 int tr_gemm(caz_trainer* t, const float* a, long a_si, long a_sk, const float* b, long b_sk, long b_sj, const float* bias, float* c,
             int m, int n, int k, int relu = 0, int ksplit = 1) {
-  if (ksplit > 1) TR_TRY(t, cudaMemsetAsync(c, 0, static_cast<size_t>(m) * n * sizeof(float), t->stream));
+  const size_t count = static_cast<size_t>(m) * n;
+  if (ksplit > 1 && count * ksplit > t->gemm_partial_floats) return tfail(t, CAZ_ERR_INVALID, "tr_gemm: split-K scratch too small");
   const dim3 grid((n + 31) / 32, (m + 31) / 32, ksplit);
-  caz::train::gemm_kernel<<<grid, 256, 0, t->stream>>>(a, a_si, a_sk, b, b_sk, b_sj, ksplit > 1 ? nullptr : bias, c, m, n, k, 0, ksplit > 1 ? 0 : relu);
-  return tr_launch_ok(t, "gemm_kernel");
+  caz::train::gemm_kernel<<<grid, 256, 0, t->stream>>>(a, a_si, a_sk, b, b_sk, b_sj, ksplit > 1 ? nullptr : bias,
+                                                       ksplit > 1 ? t->gemm_partial : c, m, n, k, 0, ksplit > 1 ? 0 : relu);
+  int rc;
+  if ((rc = tr_launch_ok(t, "gemm_kernel")) || ksplit <= 1) return rc;
+  caz::train::sum_partials_kernel<<<blocks_for(count), 256, 0, t->stream>>>(t->gemm_partial, ksplit, count, c);
+  return tr_launch_ok(t, "sum_partials_kernel");
 }
 
 // batch statistics of z (and the moving averages), then a = relu(BN(z) (+ skip))
@@ -366,12 +380,13 @@ int tr_forward_backward(caz_trainer* t, int batch) {
   caz::train::flatten_kernel<<<blocks_for(static_cast<size_t>(rows) * vf), 256, 0, t->stream>>>(t->dav, t->dfeatv, batch, vf, 1);
   if ((rc = tr_bn_backward(t, t->pconv, t->dap, t->dzp, nullptr, 0, rows))) return rc;
   if ((rc = tr_bn_backward(t, t->vconv, t->dav, t->dzv, nullptr, 0, rows))) return rc;
-  TR_TRY(t, cudaMemsetAsync(G + t->pconv.w, 0, static_cast<size_t>(F) * pf * sizeof(float), t->stream));
-  TR_TRY(t, cudaMemsetAsync(G + t->vconv.w, 0, static_cast<size_t>(F) * vf * sizeof(float), t->stream));
   {
-    const dim3 grid((F + 255) / 256, 128);
-    caz::train::head_conv_backward_weight_kernel<<<grid, 256, 0, t->stream>>>(top, t->dzp, t->dzv, G + t->pconv.w, G + t->vconv.w, rows, F, pf, vf);
+    const dim3 grid((F + 255) / 256, HEAD_WGRAD_SPLITS);
+    caz::train::head_conv_backward_weight_kernel<<<grid, 256, 0, t->stream>>>(top, t->dzp, t->dzv, t->gemm_partial, rows, F, pf, vf);
     if ((rc = tr_launch_ok(t, "head_conv_backward_weight_kernel"))) return rc;
+    caz::train::head_conv_weight_reduce_kernel<<<blocks_for(static_cast<size_t>(F) * (pf + vf)), 256, 0, t->stream>>>(
+        t->gemm_partial, HEAD_WGRAD_SPLITS, F, pf, vf, G + t->pconv.w, G + t->vconv.w);
+    if ((rc = tr_launch_ok(t, "head_conv_weight_reduce_kernel"))) return rc;
   }
   float* dcur = t->d_a;   // gradient wrt the activation of the layer being processed
   float* dalt = t->d_b;
@@ -395,7 +410,11 @@ int tr_forward_backward(caz_trainer* t, int batch) {
     else rc = tr_dgrad_fp32(t, t->dz, L, conv1 ? t->d_skip : nullptr, dalt, batch);
     if (rc) return rc;
     std::swap(dcur, dalt);
+    if (l == n_convs / 2 && t->ev_mid)   // everything from this layer upwards (and the heads) has its gradients
+      TR_TRY(t, cudaEventRecordWithFlags(t->ev_mid, t->stream, t->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   }
+  if (n_convs < 3 && t->ev_mid)   // no upper half to speak of: "mid" = end
+    TR_TRY(t, cudaEventRecordWithFlags(t->ev_mid, t->stream, t->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   return CAZ_OK;
 }
 
@@ -409,7 +428,7 @@ void caz_train_destroy(caz_trainer* t) {
   if (t->stream) cudaStreamSynchronize(t->stream);
   std::vector<void*> ptrs = {t->params, t->adam_m, t->adam_v, t->seg, t->x0, t->planes, t->policy_t, t->value_t, t->featp, t->logits, t->dlogits,
                              t->probs, t->featv, t->hid, t->vpre, t->vout, t->dvpre, t->dhid, t->dfeatp, t->dfeatv, t->d_a, t->d_b, t->d_skip, t->dz,
-                             t->dzp, t->dzv, t->dap, t->dav, t->w_flip, t->zero_bias, t->partial, t->loss_acc};
+                             t->dzp, t->dzv, t->dap, t->dav, t->w_flip, t->zero_bias, t->partial, t->loss_acc, t->gemm_partial};
   if (!t->grads_external) ptrs.push_back(t->grads);
   for (void* p : {(void*)t->x0_16, (void*)t->dz16, (void*)t->dzT, (void*)t->aT, (void*)t->dzT_stem, (void*)t->x0T, (void*)t->wg_partial}) ptrs.push_back(p);
   auto free_conv = [&](TrainConv& L) {
@@ -420,6 +439,8 @@ void caz_train_destroy(caz_trainer* t) {
   free_conv(t->vconv);
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& g : t->graphs) cudaGraphExecDestroy(g.second);
+  if (t->ev_mid) cudaEventDestroy(t->ev_mid);
+  if (t->ev_end) cudaEventDestroy(t->ev_end);
   if (t->stream) cudaStreamDestroy(t->stream);
   delete t;
 }
@@ -542,6 +563,8 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
   TC(tr_alloc(t, &t->value_t, B));
   TC(tr_alloc(t, &t->featp, B * kp));
   TC(tr_alloc(t, &t->dfeatp, B * kp));
+  t->gemm_partial_floats = std::max(8 * B * kp, (size_t)HEAD_WGRAD_SPLITS * F * (a.policy_filters + a.value_filters));
+  TC(tr_alloc(t, &t->gemm_partial, t->gemm_partial_floats));
   TC(tr_alloc(t, &t->logits, B * a.n_labels));
   TC(tr_alloc(t, &t->dlogits, B * a.n_labels));
   TC(tr_alloc(t, &t->probs, B * a.n_labels));
@@ -581,6 +604,12 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
   cudaFuncSetAttribute(caz::conv_fp32_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
   t->num_sms = prop.multiProcessorCount;
   if (getenv("CAZ_TRAIN_NO_GRAPH")) t->use_graph = false;
+  if (cudaEventCreateWithFlags(&t->ev_mid, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&t->ev_end, cudaEventDisableTiming) != cudaSuccess) {
+    t->err = "cudaEventCreate failed";
+    return bail(CAZ_ERR_CUDA);
+  }
+  t->grad_split = t->convs[t->convs.size() / 2].w;   // gradients of convs[n / 2 ...] and the heads: complete at ev_mid
+  if (t->convs.size() < 3) t->grad_split = 0;
   if (precision == CAZ_PRECISION_BF16) {
     if (prop.major != 10) { t->err = "the tensor-core training build needs an sm_100 GPU"; return bail(CAZ_ERR_NO_DEVICE); }
     t->tc = true;
@@ -631,8 +660,8 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
   return CAZ_OK;
 }
 
-int caz_train_forward_backward(caz_trainer* t, const float* planes, const float* policy_target, const float* value_target, int32_t batch,
-                               float* losses) {
+int caz_train_forward_backward_begin(caz_trainer* t, const float* planes, const float* policy_target, const float* value_target,
+                                     int32_t batch) {
   if (!t) return CAZ_ERR_INVALID;
   if (!planes || !policy_target || !value_target || batch < 1 || batch > t->max_batch)
     return tfail(t, CAZ_ERR_INVALID, fmt("caz_train_forward_backward: bad argument (batch %d, max_batch %d)", batch, t->max_batch));
@@ -649,7 +678,9 @@ int caz_train_forward_backward(caz_trainer* t, const float* planes, const float*
     // first step at this batch size: record the launch sequence (pointers and sizes are fixed per batch size)
     cudaGraph_t graph = nullptr;
     TR_TRY(t, cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
+    t->capturing = true;
     rc = tr_forward_backward(t, batch);
+    t->capturing = false;
     const cudaError_t ce = cudaStreamEndCapture(t->stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
@@ -663,6 +694,26 @@ int caz_train_forward_backward(caz_trainer* t, const float* planes, const float*
   }
   if (exec) TR_TRY(t, cudaGraphLaunch(exec, t->stream));
   else if ((rc = tr_forward_backward(t, batch))) return rc;
+  TR_TRY(t, cudaEventRecord(t->ev_end, t->stream));
+  t->pending_batch = batch;
+  return CAZ_OK;
+}
+
+int caz_train_wait_gradients(caz_trainer* t, int32_t part, void* stream) {
+  if (!t || part < 0 || part > 1) return CAZ_ERR_INVALID;
+  TR_TRY(t, cudaSetDevice(t->device));
+  TR_TRY(t, cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), part == 0 ? t->ev_mid : t->ev_end, 0));
+  return CAZ_OK;
+}
+
+int64_t caz_train_gradient_split(const caz_trainer* t) { return t ? (int64_t)t->grad_split : 0; }
+
+int caz_train_forward_backward_end(caz_trainer* t, float* losses) {
+  if (!t) return CAZ_ERR_INVALID;
+  if (t->pending_batch < 1) return tfail(t, CAZ_ERR_INVALID, "caz_train_forward_backward_end without a begin");
+  const int batch = t->pending_batch;
+  t->pending_batch = 0;
+  TR_TRY(t, cudaSetDevice(t->device));
   double acc[4];
   TR_TRY(t, cudaMemcpyAsync(acc, t->loss_acc, sizeof acc, cudaMemcpyDeviceToHost, t->stream));
   TR_TRY(t, cudaStreamSynchronize(t->stream));
@@ -673,6 +724,13 @@ int caz_train_forward_backward(caz_trainer* t, const float* planes, const float*
   t->last_losses[3] = reg;
   if (losses) memcpy(losses, t->last_losses, sizeof t->last_losses);
   return CAZ_OK;
+}
+
+int caz_train_forward_backward(caz_trainer* t, const float* planes, const float* policy_target, const float* value_target, int32_t batch,
+                               float* losses) {
+  int rc;
+  if ((rc = caz_train_forward_backward_begin(t, planes, policy_target, value_target, batch))) return rc;
+  return caz_train_forward_backward_end(t, losses);
 }
 
 int caz_train_apply(caz_trainer* t, float grad_scale) {

@@ -240,8 +240,9 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ partial, int c,
 
 // ---- a small general GEMM on the CUDA cores (heads' 1x1 convolutions and Dense layers, forward and backward) ----------
 //   C[i][j] (+)= sum_k A(i, k) * B(k, j) (+ bias[j]),  A(i, k) = a[i * a_si + k * a_sk],  B(k, j) = b[k * b_sk + j * b_sj]
-// 32 x 32 output tile per block, K in slabs of 32; gridDim.z splits K (the partial sums are added with atomicAdd into a
-// zeroed or accumulated C: pass accumulate = 1 and clear C first when gridDim.z > 1).
+// 32 x 32 output tile per block, K in slabs of 32; gridDim.z splits K: slice z writes its partial sums to c + z * m * n and
+// sum_partials_kernel adds the slices in a fixed order (no atomicAdd on the data-gradient path: run-to-run rounding noise there
+// is amplified by every 16-bit rounding of the tensor-core build's backward pass).
 __global__ void __launch_bounds__(256)
 gemm_kernel(const float* __restrict__ a, long a_si, long a_sk, const float* __restrict__ b, long b_sk, long b_sj,
             const float* __restrict__ bias, float* __restrict__ c, int m, int n, int k, int accumulate, int relu) {
@@ -276,12 +277,20 @@ gemm_kernel(const float* __restrict__ a, long a_si, long a_sk, const float* __re
     if (i >= m) continue;
     float v = acc[r];
     float* dst = c + static_cast<size_t>(i) * n + j;
-    if (kz > 1) { atomicAdd(dst, v); continue; }
+    if (kz > 1) { dst[static_cast<size_t>(blockIdx.z) * m * n] = v; continue; }
     if (bias) v += bias[j];
     if (accumulate) v += *dst;
     if (relu) v = fmaxf(v, 0.0f);
     *dst = v;
   }
+}
+
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int splits, size_t count, float* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s = partial[i];
+  for (int k = 1; k < splits; ++k) s += partial[k * count + i];
+  out[i] = s;
 }
 
 // ---- the heads' 1x1 convolutions (model_chess.py:77-78,86-87) over all rows, both heads in one pass over the tower's output ----
@@ -330,10 +339,11 @@ __global__ void head_conv_backward_data_kernel(const float* __restrict__ dzp, co
   dtop[i] = v;
 }
 
-// dwp[ch][f] += sum over this block's rows of top[row][ch] dzp[row][f] (dwv alike); grid (c / 256, row splits); dwp / dwv zeroed by the caller
+// partial[split][ch][f] = sum over this block's rows of top[row][ch] dz[row][f] (f: policy filters, then value filters);
+// grid (c / 256, row splits); head_conv_weight_reduce_kernel adds the splits in a fixed order
 __global__ void __launch_bounds__(256)
-head_conv_backward_weight_kernel(const float* __restrict__ top, const float* __restrict__ dzp, const float* __restrict__ dzv, float* __restrict__ dwp,
-                                 float* __restrict__ dwv, int rows, int c, int pf, int vf) {
+head_conv_backward_weight_kernel(const float* __restrict__ top, const float* __restrict__ dzp, const float* __restrict__ dzv,
+                                 float* __restrict__ partial, int rows, int c, int pf, int vf) {
   const int ch = blockIdx.x * 256 + threadIdx.x;
   const int per = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   __shared__ float sd[64][HEADS_MAX_F];
@@ -359,11 +369,21 @@ head_conv_backward_weight_kernel(const float* __restrict__ top, const float* __r
     }
   }
   if (ch >= c) return;
+  float* dst = partial + (static_cast<size_t>(blockIdx.y) * c + ch) * ft;
 #pragma unroll
-  for (int f = 0; f < HEADS_MAX_F; ++f) {
-    if (f < pf) atomicAdd(dwp + ch * pf + f, acc[f]);
-    else if (f < ft) atomicAdd(dwv + ch * vf + f - pf, acc[f]);
-  }
+  for (int f = 0; f < HEADS_MAX_F; ++f)
+    if (f < ft) dst[f] = acc[f];
+}
+
+__global__ void head_conv_weight_reduce_kernel(const float* __restrict__ partial, int splits, int c, int pf, int vf, float* __restrict__ dwp,
+                                               float* __restrict__ dwv) {
+  const int ft = pf + vf, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c * ft) return;
+  float s = 0.0f;
+  for (int k = 0; k < splits; ++k) s += partial[static_cast<size_t>(k) * c * ft + i];
+  const int ch = i / ft, f = i - ch * ft;
+  if (f < pf) dwp[ch * pf + f] = s;
+  else dwv[ch * vf + f - pf] = s;
 }
 
 // column sums of a row-major matrix (Dense bias gradients): out[j] = sum_i x[i][j]

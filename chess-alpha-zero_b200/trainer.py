@@ -51,6 +51,11 @@ class Trainer:
         lib.caz_train_steps.argtypes = [vp]
         lib.caz_train_steps.restype = i64
         lib.caz_train_forward_backward.argtypes = [vp, vp, vp, vp, i32, vp]
+        lib.caz_train_forward_backward_begin.argtypes = [vp, vp, vp, vp, i32]
+        lib.caz_train_forward_backward_end.argtypes = [vp, vp]
+        lib.caz_train_wait_gradients.argtypes = [vp, i32, vp]
+        lib.caz_train_gradient_split.argtypes = [vp]
+        lib.caz_train_gradient_split.restype = i64
         lib.caz_train_apply.argtypes = [vp, ctypes.c_float]
         lib.caz_train_read.argtypes = [vp, i32, vp, i64]
         lib.caz_train_read_outputs.argtypes = [vp, i32, vp, vp]
@@ -162,10 +167,32 @@ class Trainer:
         self._check(self._lib.caz_train_apply(self._h, scale))
 
     def train_on_batch(self, planes, policy_target, value_target):
-        """One optimizer step on this rank's shard of the batch (model.train_on_batch semantics)."""
-        out = self.forward_backward(planes, policy_target, value_target)
-        self.apply()
-        return out
+        """One optimizer step on this rank's shard of the batch (model.train_on_batch semantics).  Data parallel: the
+        all-reduce of the upper half of the gradient vector (the layers the backward pass finishes first) runs under the
+        backward pass of the lower half."""
+        if self._dist is None:
+            out = self.forward_backward(planes, policy_target, value_target)
+            self.apply()
+            return out
+        import torch
+        x = _lib.as_array(planes, np.float32)
+        pt = _lib.as_array(policy_target, np.float32, (x.shape[0], self.arch.n_labels))
+        vt = _lib.as_array(value_target, np.float32).reshape(-1)
+        self._check(self._lib.caz_train_forward_backward_begin(self._h, _lib.ptr(x), _lib.ptr(pt), _lib.ptr(vt), x.shape[0]))
+        split = int(self._lib.caz_train_gradient_split(self._h))
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        self._check(self._lib.caz_train_wait_gradients(self._h, 0, stream))
+        works = [self._dist.all_reduce(self._grad_tensor[split:], op=self._dist.ReduceOp.SUM, async_op=True)]
+        self._check(self._lib.caz_train_wait_gradients(self._h, 1, stream))
+        if split > 0:
+            works.append(self._dist.all_reduce(self._grad_tensor[:split], op=self._dist.ReduceOp.SUM, async_op=True))
+        losses = np.zeros(4, np.float32)
+        self._check(self._lib.caz_train_forward_backward_end(self._h, _lib.ptr(losses)))
+        for wk in works:
+            wk.wait()
+        torch.cuda.synchronize(self.device)
+        self._check(self._lib.caz_train_apply(self._h, 1.0 / self._dist.get_world_size()))
+        return {"loss": float(losses[0]), "policy_out_loss": float(losses[1]), "value_out_loss": float(losses[2]), "l2": float(losses[3])}
 
     def fit(self, x, y, batch_size=384, epochs=1, shuffle=True, validation_split=0.0, seed=None):
         """model.fit(state_ary, [policy_ary, value_ary], batch_size, epochs, shuffle, validation_split) of

@@ -285,6 +285,16 @@ int64_t caz_train_steps(const caz_trainer* t);       /* caz_train_apply calls so
  * l2 term. */
 int caz_train_forward_backward(caz_trainer* t, const float* planes, const float* policy_target, const float* value_target,
                                int32_t batch, float* losses);
+/* The same in two halves, for overlapping the data-parallel all-reduce with the backward pass: _begin enqueues everything
+ * on the trainer's stream and returns; caz_train_wait_gradients(t, part, stream) makes `stream` (a cudaStream_t of the
+ * caller, e.g. the one the NCCL all-reduce is issued from) wait until part 0 = the gradient elements
+ * [caz_train_gradient_split(t), n) -- the upper half of the tower and the heads, which the backward pass finishes first --
+ * or part 1 = all of them are complete; _end waits for the stream and returns the losses. */
+int caz_train_forward_backward_begin(caz_trainer* t, const float* planes, const float* policy_target, const float* value_target,
+                                     int32_t batch);
+int caz_train_wait_gradients(caz_trainer* t, int32_t part, void* stream);
+int64_t caz_train_gradient_split(const caz_trainer* t);
+int caz_train_forward_backward_end(caz_trainer* t, float* losses);
 /* One Adam update from grad_scale * gradient vector (+ 2 * l2 * w on kernels). */
 int caz_train_apply(caz_trainer* t, float grad_scale);
 /* what: 0 parameters, 1 gradients, 2 / 3 Adam first / second moments; host float32 [caz_train_num_params] */

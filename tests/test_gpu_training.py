@@ -171,3 +171,86 @@ def test_optimize_worker_calls_on_chessmodel(tmp_path):
     assert np.array_equal(again[0], after[0]) and np.array_equal(again[1], after[1])
     model.model.close()
     fresh.model.close()
+
+
+def test_gradient_halves_are_complete_when_their_events_fire():
+    """caz_train_forward_backward_begin / caz_train_wait_gradients / _end, the hooks the data-parallel all-reduce hangs on:
+    a side stream that waits for part 0 must see the final gradients of the upper half of the network (elements
+    >= caz_train_gradient_split) although the backward pass of the lower half is still running, and after part 1 all of
+    them.  Every step gets different positions, so values left by the step before cannot pass; steps 2.. replay the CUDA
+    graph, where the mid-backward event is an event-record node."""
+    import ctypes
+    import torch
+    cfg = oweights.keras_config(filters=64, blocks=3)
+    w = oweights.synth_weights(cfg, seed=4, recipe="keras_default")
+    B = 48
+    x, pt, vt = _data(4 * B, seed=9)
+    for precision in ("fp32", "bf16"):
+        tr = caz.Trainer(cfg, w, precision=precision, max_batch=B, distributed=True)   # gradient vector in a torch tensor
+        lib, h = tr._lib, tr._h
+        split = int(lib.caz_train_gradient_split(h))
+        assert 0 < split < tr.n_params
+        side = torch.cuda.Stream()
+        sp = ctypes.c_void_p(side.cuda_stream)
+        for step in range(4):
+            sl = slice(step * B, (step + 1) * B)
+            xs, ps, vs = np.ascontiguousarray(x[sl]), np.ascontiguousarray(pt[sl]), np.ascontiguousarray(vt[sl])
+            tr._check(lib.caz_train_forward_backward_begin(h, xs.ctypes.data, ps.ctypes.data, vs.ctypes.data, B))
+            with torch.cuda.stream(side):
+                tr._check(lib.caz_train_wait_gradients(h, 0, sp))
+                upper = tr._grad_tensor[split:].clone()
+                tr._check(lib.caz_train_wait_gradients(h, 1, sp))
+                lower = tr._grad_tensor[:split].clone()
+            losses = np.zeros(4, np.float32)
+            tr._check(lib.caz_train_forward_backward_end(h, losses.ctypes.data))
+            side.synchronize()
+            final = tr._grad_tensor.clone()
+            assert float(final.abs().max()) > 0 and np.isfinite(losses).all()
+            assert torch.equal(upper, final[split:]), (precision, step)
+            assert torch.equal(lower, final[:split]), (precision, step)
+        tr.close()
+
+
+def test_overlapped_all_reduce_step_runs_like_the_plain_step():
+    """Trainer.train_on_batch under torch.distributed: begin, the all-reduce of the upper half of the gradient vector issued
+    behind caz_train_wait_gradients(part 0), then the lower half, then Adam.  With a one-rank NCCL group the all-reduce is
+    the identity, so this is the plumbing only (tools/train_bench.py --verify compares the two orders on 2..8 GPUs).  The
+    tensor-core build has no atomicAdd anywhere in the step and is reproducible bit for bit: four overlapped steps must
+    leave exactly the weights and losses of four plain steps.  The fp32 build's weight-gradient kernel adds its board
+    slices atomically: there the agreement is to float rounding."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    cfg = oweights.keras_config(filters=64, blocks=3)
+    w = oweights.synth_weights(cfg, seed=4, recipe="keras_default")
+    x, pt, vt = _data(32, seed=9)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                            device_id=torch.device("cuda", 0))
+    try:
+        for precision in ("fp32", "bf16"):
+            ta = caz.Trainer(cfg, w, precision=precision, max_batch=32, distributed=True)
+            tb = caz.Trainer(cfg, w, precision=precision, max_batch=32, distributed=False)
+            tc = caz.Trainer(cfg, w, precision=precision, max_batch=32, distributed=False)   # control: plain against plain
+            for _ in range(4):
+                la = ta.train_on_batch(x, pt, vt)
+                lb = tb.train_on_batch(x, pt, vt)
+                tc.train_on_batch(x, pt, vt)
+                if precision == "bf16":
+                    assert la == lb, (la, lb)
+                assert all(abs(la[k] - lb[k]) <= 1e-5 * abs(lb[k]) for k in la), (la, lb)
+            wa, wb = ta.weights(), tb.weights()
+            fa = np.concatenate([v.reshape(-1) for v in wa.values()])
+            fb = np.concatenate([v.reshape(-1) for v in wb.values()])
+            d = np.abs(fa - fb)
+            dc = np.abs(np.concatenate([v.reshape(-1) for v in tc.weights().values()]) - fb)
+            tc.close()
+            print(f"   {precision}: weights after 4 steps differ by max {d.max():.2e}, mean {d.mean():.2e}, {np.mean(d > 1e-5):.2e} of them > 1e-5"
+                  f" (two plain runs: max {dc.max():.2e}, mean {dc.mean():.2e})")
+            assert d.max() <= (0.0 if precision == "bf16" else 2e-5) and d.mean() <= 1e-8
+            ta.close()
+            tb.close()
+    finally:
+        dist.destroy_process_group()

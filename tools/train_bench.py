@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--filters", type=int, default=256)
     ap.add_argument("--verify", action="store_true",
                     help="before timing: the all-reduced gradient of the first step against one GPU running every rank's shard in turn")
+    ap.add_argument("--no-overlap", action="store_true", help="all-reduce the whole gradient vector after the backward pass has ended")
     args = ap.parse_args()
     world, rank, local = bench.dist_setup(int(os.environ.get("WORLD_SIZE", "1")))
     import torch
@@ -80,6 +81,19 @@ def main():
             verify = {"max_abs_diff": float(np.abs(got - want).max()), "max_abs_gradient": float(np.abs(want).max()),
                       "relative": float(np.abs(got - want).max() / np.abs(want).max())}
         ev2.close()
+        # the overlapped step (all-reduce of the upper half under the backward pass of the lower half) against the plain one
+        ta = caz.Trainer(cfg, w, device=local, precision=args.precision, max_batch=B)
+        tb = caz.Trainer(cfg, w, device=local, precision=args.precision, max_batch=B)
+        for _ in range(3):
+            ta.train_on_batch(planes, pt, vt)
+            tb.forward_backward(planes, pt, vt)
+            tb.apply()
+        fa = np.concatenate([v.reshape(-1) for v in ta.weights().values()])
+        fb_ = np.concatenate([v.reshape(-1) for v in tb.weights().values()])
+        ta.close()
+        tb.close()
+        if rank == 0:
+            verify["overlapped_vs_plain_weights_after_3_steps_max_abs_diff"] = float(np.abs(fa - fb_).max())
     tr = caz.Trainer(cfg, w, device=local, precision=args.precision, max_batch=B)
     losses = [tr.train_on_batch(planes, pt, vt)["loss"] for _ in range(3)]
     bench.barrier(world)
@@ -88,9 +102,12 @@ def main():
     fb = 0.0
     for _ in range(args.steps):
         t1 = time.perf_counter()
-        out = tr.forward_backward(planes, pt, vt)
-        fb += time.perf_counter() - t1
-        tr.apply()
+        if world > 1 and not args.no_overlap:
+            out = tr.train_on_batch(planes, pt, vt)
+        else:
+            out = tr.forward_backward(planes, pt, vt)
+            fb += time.perf_counter() - t1
+            tr.apply()
         losses.append(out["loss"])
     dt = bench.max_over_ranks(time.perf_counter() - t0, world)
     # all ranks must hold the same weights after the all-reduced updates
@@ -105,7 +122,8 @@ def main():
                           "net": f"{args.blocks}x{args.filters}", "approx_tflops": flops / 1e12,
                           "loss_first_last": [losses[0], losses[-1]], "ranks_hold_identical_weights": bool(same),
                           "allreduced_gradient_vs_one_gpu_running_all_shards": verify,
-                          "collective": "torch.distributed.all_reduce (NCCL) of the flat fp32 gradient vector" if world > 1 else None}))
+                          "collective": ("torch.distributed.all_reduce (NCCL) of the flat fp32 gradient vector" +
+                                         ("" if args.no_overlap else ", upper half under the backward pass of the lower half")) if world > 1 else None}))
     tr.close()
 
 
