@@ -58,6 +58,8 @@ struct caz_trainer {
   cudaEvent_t ev_mid = nullptr, ev_end = nullptr;
   size_t grad_split = 0;
   bool capturing = false;
+  bool profiling = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> prof;
   int pending_batch = 0;
   // 16-bit builds (tensor-core convolutions): forward fp16 x fp16, input and weight gradients bf16 x bf16, fp32 accumulation
   bool tc = false;
@@ -91,7 +93,31 @@ int tfail(caz_trainer* t, int code, const std::string& msg) {
 int tr_launch_ok(caz_trainer* t, const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return tfail(t, CAZ_ERR_CUDA, fmt("launch of %s failed: %s", what, cudaGetErrorString(e)));
+  if (t->profiling) {   // CAZ_TRAIN_PROFILE: an event behind every launch (group); caz_train_forward_backward_end prints the table
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) == cudaSuccess && cudaEventRecord(ev, t->stream) == cudaSuccess) t->prof.emplace_back(what, ev);
+  }
   return CAZ_OK;
+}
+
+// CAZ_TRAIN_PROFILE=1: device time between consecutive launch groups of the last step, summed per kernel name, to stderr
+void tr_profile_report(caz_trainer* t) {
+  std::vector<std::pair<std::string, std::pair<double, int>>> rows;
+  double total = 0.0;
+  for (size_t i = 1; i < t->prof.size(); ++i) {
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, t->prof[i - 1].second, t->prof[i].second);
+    total += ms;
+    bool found = false;
+    for (auto& r : rows)
+      if (r.first == t->prof[i].first) { r.second.first += ms; r.second.second += 1; found = true; }
+    if (!found) rows.push_back({t->prof[i].first, {ms, 1}});
+  }
+  std::sort(rows.begin(), rows.end(), [](const auto& a, const auto& b) { return a.second.first > b.second.first; });
+  fprintf(stderr, "caz_train profile (one step, plain launches, %.1f us):\n", total * 1e3);
+  for (auto& r : rows) fprintf(stderr, "  %9.1f us %4d x %7.1f us  %s\n", r.second.first * 1e3, r.second.second, r.second.first * 1e3 / r.second.second, r.first.c_str());
+  for (auto& pr : t->prof) cudaEventDestroy(pr.second);
+  t->prof.clear();
 }
 
 template <typename T>
@@ -134,8 +160,8 @@ int tr_gemm(caz_trainer* t, const float* a, long a_si, long a_sk, const float* b
 
 // batch statistics of z (and the moving averages), then a = relu(BN(z) (+ skip))
 int tr_bn_forward(caz_trainer* t, TrainConv& L, const float* skip, int rows) {
-  const dim3 grid((L.cout + 127) / 128, caz::train::STAT_SPLITS);
-  caz::train::channel_sums_kernel<<<grid, 256, 0, t->stream>>>(0, L.z, nullptr, nullptr, nullptr, nullptr, nullptr, rows, L.cout, t->partial);
+  const dim3 grid((L.cout + caz::train::STAT_CH - 1) / caz::train::STAT_CH, caz::train::STAT_SPLITS);
+  caz::train::channel_sums_kernel<<<grid, caz::train::STAT_THREADS, 0, t->stream>>>(0, L.z, nullptr, nullptr, nullptr, nullptr, nullptr, rows, L.cout, t->partial);
   int rc;
   if ((rc = tr_launch_ok(t, "channel_sums_kernel"))) return rc;
   caz::train::bn_finish_stats_kernel<<<(L.cout + 7) / 8, 256, 0, t->stream>>>(t->partial, rows, L.cout, t->arch.bn_epsilon, L.mean, L.invstd,
@@ -152,8 +178,8 @@ int tr_bn_forward(caz_trainer* t, TrainConv& L, const float* skip, int rows) {
 // da (gradient wrt the layer's activation) -> dz (wrt its convolution output), dgamma / dbeta; dskip = gradient passed to the Add's other input
 int tr_bn_backward(caz_trainer* t, TrainConv& L, const float* da, float* dz, float* dskip, int dskip_accumulate, int rows,
                    const float* da2 = nullptr, uint16_t* dz16 = nullptr) {
-  const dim3 grid((L.cout + 127) / 128, caz::train::STAT_SPLITS);
-  caz::train::channel_sums_kernel<<<grid, 256, 0, t->stream>>>(1, L.z, L.a, da, da2, L.mean, L.invstd, rows, L.cout, t->partial);
+  const dim3 grid((L.cout + caz::train::STAT_CH - 1) / caz::train::STAT_CH, caz::train::STAT_SPLITS);
+  caz::train::channel_sums_kernel<<<grid, caz::train::STAT_THREADS, 0, t->stream>>>(1, L.z, L.a, da, da2, L.mean, L.invstd, rows, L.cout, t->partial);
   int rc;
   if ((rc = tr_launch_ok(t, "channel_sums_kernel (backward)"))) return rc;
   caz::train::bn_param_grads_kernel<<<(L.cout + 7) / 8, 256, 0, t->stream>>>(t->partial, L.cout, t->grads + L.gamma, t->grads + L.beta);
@@ -260,7 +286,7 @@ int tr_wgrad_tc(caz_trainer* t, const float* x, const float* dz, int batch, cons
   // K-major bf16 operands over the zero-padded board index (transpose_pad_kernel); the halo cells were zeroed at allocation
   // and are never written (the stem's layout, pitch 8 + 2 pad, has its own buffers)
   {
-    const dim3 g1(t->nb / 32, (L.cout + 31) / 32, 64), g2(t->nb / 32, (n_in_pad + 31) / 32, 64);
+    const dim3 g1(t->nb / 64, (L.cout + 63) / 64, 64), g2(t->nb / 64, (n_in_pad + 63) / 64, 64);
     const bool stem = &L == &t->convs[0];
     caz::train::transpose_pad_kernel<<<g1, 256, 0, t->stream>>>(dz, batch, L.cout, L.cout, t->nb, pad, stem ? t->dzT_stem : t->dzT);
     caz::train::transpose_pad_kernel<<<g2, 256, 0, t->stream>>>(x, batch, L.cin, n_in_pad, t->nb, pad, stem ? t->x0T : t->aT);
@@ -359,20 +385,18 @@ int tr_forward_backward(caz_trainer* t, int batch) {
   caz::train::loss_kernel<<<batch, 256, 0, t->stream>>>(t->logits, t->policy_t, t->vpre, t->value_t, nl, t->cfg.policy_loss_weight, t->cfg.value_loss_weight,
                                                         batch, t->dlogits, t->dvpre, t->probs, t->vout, t->loss_acc);
   if ((rc = tr_launch_ok(t, "loss_kernel"))) return rc;
-  caz::train::l2_sum_kernel<<<148 * 8, 256, 0, t->stream>>>(P, t->seg, t->n_params, t->loss_acc + 2);
-  if ((rc = tr_launch_ok(t, "l2_sum_kernel"))) return rc;
   // ---- backward: heads ----
   // policy Dense: dW = featp^T . dlogits, db = column sums, dfeatp = dlogits . W^T
   if ((rc = tr_gemm(t, t->featp, 1, kp, t->dlogits, nl, 1, nullptr, G + t->pfc_w, kp, nl, batch))) return rc;
-  caz::train::column_sum_kernel<<<(nl + 127) / 128, 128, 0, t->stream>>>(t->dlogits, batch, nl, G + t->pfc_b);
+  caz::train::column_sum_kernel<<<(nl + 31) / 32, 256, 0, t->stream>>>(t->dlogits, batch, nl, G + t->pfc_b);
   if ((rc = tr_gemm(t, t->dlogits, nl, 1, P + t->pfc_w, 1, nl, nullptr, t->dfeatp, batch, kp, nl, 0, 8))) return rc;
   // value head: Dense(1, tanh) <- Dense(vfc, relu)
   if ((rc = tr_gemm(t, t->hid, 1, vfc, t->dvpre, 1, 1, nullptr, G + t->vfc2_w, vfc, 1, batch))) return rc;
-  caz::train::column_sum_kernel<<<1, 32, 0, t->stream>>>(t->dvpre, batch, 1, G + t->vfc2_b);
+  caz::train::column_sum_kernel<<<1, 256, 0, t->stream>>>(t->dvpre, batch, 1, G + t->vfc2_b);
   if ((rc = tr_gemm(t, t->dvpre, 1, 1, P + t->vfc2_w, 1, 1, nullptr, t->dhid, batch, vfc, 1))) return rc;
   caz::train::relu_backward_kernel<<<blocks_for(static_cast<size_t>(batch) * vfc), 256, 0, t->stream>>>(t->hid, t->dhid, static_cast<size_t>(batch) * vfc);
   if ((rc = tr_gemm(t, t->featv, 1, kv, t->dhid, vfc, 1, nullptr, G + t->vfc1_w, kv, vfc, batch))) return rc;
-  caz::train::column_sum_kernel<<<(vfc + 127) / 128, 128, 0, t->stream>>>(t->dhid, batch, vfc, G + t->vfc1_b);
+  caz::train::column_sum_kernel<<<(vfc + 31) / 32, 256, 0, t->stream>>>(t->dhid, batch, vfc, G + t->vfc1_b);
   if ((rc = tr_gemm(t, t->dhid, vfc, 1, P + t->vfc1_w, 1, vfc, nullptr, t->dfeatv, batch, kv, vfc))) return rc;
   if ((rc = tr_launch_ok(t, "head backward"))) return rc;
   // un-flatten, BN + ReLU backward of the head convolutions, their weight gradients and the gradient wrt the tower's output
@@ -587,7 +611,7 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
   TC(tr_alloc(t, &t->w_flip, wmax));
   TC(tr_alloc(t, &t->zero_bias, std::max(F, (size_t)a.input_planes) + 64));
   TC(tr_alloc(t, &t->partial, (size_t)2 * caz::train::STAT_SPLITS * std::max(F, (size_t)64)));
-  TC(tr_alloc(t, &t->loss_acc, (size_t)4));
+  TC(tr_alloc(t, &t->loss_acc, (size_t)8));   // [0] CE, [1] MSE of the step; [4] sum of squares of the l2-regularised parameters
 #undef TC
   // the fp32 convolution keeps a zero-padded board of all input channels in shared memory
   const size_t s3 = (size_t)(8 + a.block_kernel - 1) * (8 + a.block_kernel - 1) * a.filters * 4;
@@ -604,6 +628,7 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
   cudaFuncSetAttribute(caz::conv_fp32_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
   t->num_sms = prop.multiProcessorCount;
   if (getenv("CAZ_TRAIN_NO_GRAPH")) t->use_graph = false;
+  if (getenv("CAZ_TRAIN_PROFILE")) { t->use_graph = false; t->profiling = true; }
   if (cudaEventCreateWithFlags(&t->ev_mid, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&t->ev_end, cudaEventDisableTiming) != cudaSuccess) {
     t->err = "cudaEventCreate failed";
     return bail(CAZ_ERR_CUDA);
@@ -655,6 +680,8 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
     }
     if ((rc = tr_refresh_weights16(t))) return bail(rc);
   }
+  // the l2 term of the first step's loss; afterwards adam_kernel leaves the sum of squares of the weights it has just written
+  caz::train::l2_sum_kernel<<<t->num_sms * 8, 256, 0, t->stream>>>(t->params, t->seg, t->n_params, t->loss_acc + 4);
   if (cudaStreamSynchronize(t->stream) != cudaSuccess) { t->err = "initialisation failed"; return bail(CAZ_ERR_CUDA); }
   *out = t;
   return CAZ_OK;
@@ -671,6 +698,11 @@ int caz_train_forward_backward_begin(caz_trainer* t, const float* planes, const 
   TR_TRY(t, cudaMemcpyAsync(t->policy_t, policy_target, (size_t)batch * a.n_labels * 4, cudaMemcpyHostToDevice, t->stream));
   TR_TRY(t, cudaMemcpyAsync(t->value_t, value_target, (size_t)batch * 4, cudaMemcpyHostToDevice, t->stream));
   int rc;
+  if (t->profiling) {
+    for (auto& pr : t->prof) cudaEventDestroy(pr.second);
+    t->prof.clear();
+    tr_launch_ok(t, "start");
+  }
   cudaGraphExec_t exec = nullptr;
   for (auto& g : t->graphs)
     if (g.first == batch) exec = g.second;
@@ -714,10 +746,11 @@ int caz_train_forward_backward_end(caz_trainer* t, float* losses) {
   const int batch = t->pending_batch;
   t->pending_batch = 0;
   TR_TRY(t, cudaSetDevice(t->device));
-  double acc[4];
+  double acc[5];
   TR_TRY(t, cudaMemcpyAsync(acc, t->loss_acc, sizeof acc, cudaMemcpyDeviceToHost, t->stream));
   TR_TRY(t, cudaStreamSynchronize(t->stream));
-  const float ce = (float)(acc[0] / batch), mse = (float)(acc[1] / batch), reg = (float)(t->cfg.l2 * acc[2]);
+  if (t->profiling && t->step == 3) tr_profile_report(t);
+  const float ce = (float)(acc[0] / batch), mse = (float)(acc[1] / batch), reg = (float)(t->cfg.l2 * acc[4]);
   t->last_losses[0] = t->cfg.policy_loss_weight * ce + t->cfg.value_loss_weight * mse + reg;
   t->last_losses[1] = ce;
   t->last_losses[2] = mse;
@@ -739,8 +772,10 @@ int caz_train_apply(caz_trainer* t, float grad_scale) {
   ++t->step;
   const double b1 = t->cfg.beta_1, b2 = t->cfg.beta_2;
   const float lr_t = (float)(t->cfg.learning_rate * std::sqrt(1.0 - std::pow(b2, (double)t->step)) / (1.0 - std::pow(b1, (double)t->step)));
-  caz::train::adam_kernel<<<blocks_for(t->n_params), 256, 0, t->stream>>>(t->params, t->grads, t->adam_m, t->adam_v, t->seg, t->n_params, lr_t,
-                                                                       t->cfg.beta_1, t->cfg.beta_2, t->cfg.epsilon, t->cfg.l2, grad_scale, t->cfg.bn_momentum);
+  TR_TRY(t, cudaMemsetAsync(t->loss_acc + 4, 0, sizeof(double), t->stream));
+  caz::train::adam_kernel<<<t->num_sms * 8, 256, 0, t->stream>>>(t->params, t->grads, t->adam_m, t->adam_v, t->seg, t->n_params, lr_t, t->cfg.beta_1,
+                                                              t->cfg.beta_2, t->cfg.epsilon, t->cfg.l2, grad_scale, t->cfg.bn_momentum,
+                                                              t->loss_acc + 4);
   int rc;
   if ((rc = tr_launch_ok(t, "adam_kernel"))) return rc;
   if ((rc = tr_refresh_weights16(t))) return rc;

@@ -14,31 +14,35 @@
 namespace caz {
 namespace train {
 
-constexpr int STAT_SPLITS = 128;
+constexpr int STAT_SPLITS = 64;    // row splits of the per-channel reductions (partials are summed in a fixed order)
+constexpr int STAT_THREADS = 512;
+constexpr int STAT_CH = 64;        // channels per block: 16 lanes x float4
+constexpr int STAT_ROW_LANES = STAT_THREADS / 16;
 
-__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }   // row splits of the per-channel reductions (partials are summed in a fixed order)
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ---- per-channel sums over the rows: partial[split][c] = sum over the split's rows of f(row, c) -------------------------
 // mode 0: (sum z, sum z^2)                                -> BatchNormalization batch statistics
 // mode 1: dy = da * (a > 0);  (sum dy, sum dy * xhat)     -> BatchNormalization backward, xhat = (z - mean) * invstd
-// out: partial[2][STAT_SPLITS][c] (double)
-__global__ void __launch_bounds__(256)
+// out: partial[2][STAT_SPLITS][c] (double); grid ((c + 63) / 64, STAT_SPLITS), STAT_THREADS threads
+__global__ void __launch_bounds__(STAT_THREADS)
 channel_sums_kernel(int mode, const float* __restrict__ z, const float* __restrict__ a, const float* __restrict__ da,
                     const float* __restrict__ da2, const float* __restrict__ mean, const float* __restrict__ invstd, int rows, int c,
                     double* __restrict__ partial) {
-  // a block covers 128 channels (32 lanes x float4) x 8 row lanes; c is a multiple of 4 on this path (c < 4: scalar path below)
+  // a block covers 64 channels (16 lanes x float4) x 32 row lanes; c < 4 or not a multiple of 4: scalar path below
   const int split = blockIdx.y;
   const int per = (rows + STAT_SPLITS - 1) / STAT_SPLITS;
   const int r0 = split * per, r1 = min(rows, r0 + per);
-  const int sub = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ double sh[2][8][128];
+  const int sub = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  __shared__ double sh[2][STAT_ROW_LANES][STAT_CH];
+  double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
   if ((c & 3) == 0) {
-    const int ch = blockIdx.x * 128 + lane * 4;
-    double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+    const int ch = blockIdx.x * STAT_CH + lane * 4;
     if (ch < c) {
       float4 mu = make_float4(0, 0, 0, 0), is = mu;
       if (mode) { mu = *reinterpret_cast<const float4*>(mean + ch); is = *reinterpret_cast<const float4*>(invstd + ch); }
-      for (int r = r0 + sub; r < r1; r += 8) {
+#pragma unroll 4
+      for (int r = r0 + sub; r < r1; r += STAT_ROW_LANES) {
         const size_t i = static_cast<size_t>(r) * c + ch;
         const float4 zv = *reinterpret_cast<const float4*>(z + i);
         if (mode == 0) {
@@ -61,45 +65,37 @@ channel_sums_kernel(int mode, const float* __restrict__ z, const float* __restri
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) { sh[0][sub][lane * 4 + q] = s0[q]; sh[1][sub][lane * 4 + q] = s1[q]; }
-    __syncthreads();
-    if (threadIdx.x < 128) {
-      const int cc = blockIdx.x * 128 + threadIdx.x;
-      if (cc < c) {
-        double t0 = 0.0, t1 = 0.0;
-        for (int k = 0; k < 8; ++k) { t0 += sh[0][k][threadIdx.x]; t1 += sh[1][k][threadIdx.x]; }
-        partial[(0 * STAT_SPLITS + split) * c + cc] = t0;
-        partial[(1 * STAT_SPLITS + split) * c + cc] = t1;
+  } else {
+    // scalar path (the heads' 1x1 convolutions have 1, 2 or 4 channels... and anything not a multiple of 4): channel lane + 16 q
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ch = blockIdx.x * STAT_CH + lane + 16 * q;
+      if (ch < c) {
+        const float mu = mode ? mean[ch] : 0.0f, is = mode ? invstd[ch] : 0.0f;
+        for (int r = r0 + sub; r < r1; r += STAT_ROW_LANES) {
+          const size_t i = static_cast<size_t>(r) * c + ch;
+          if (mode == 0) {
+            const float v = z[i];
+            s0[q] += v;
+            s1[q] += static_cast<double>(v) * v;
+          } else {
+            const float dy = a[i] > 0.0f ? da[i] + (da2 ? da2[i] : 0.0f) : 0.0f;
+            s0[q] += dy;
+            s1[q] += static_cast<double>(dy) * ((z[i] - mu) * is);
+          }
+        }
       }
+      sh[0][sub][lane + 16 * q] = s0[q];
+      sh[1][sub][lane + 16 * q] = s1[q];
     }
-    return;
-  }
-  // scalar path (the heads' 1x1 convolutions have 1, 2 or 4 channels... and anything not a multiple of 4)
-  for (int ch = blockIdx.x * 128 + lane; ch < min(c, blockIdx.x * 128 + 128); ch += 32) {
-    double s0 = 0.0, s1 = 0.0;
-    const float mu = mode ? mean[ch] : 0.0f, is = mode ? invstd[ch] : 0.0f;
-    for (int r = r0 + sub; r < r1; r += 8) {
-      const size_t i = static_cast<size_t>(r) * c + ch;
-      if (mode == 0) {
-        const float v = z[i];
-        s0 += v;
-        s1 += static_cast<double>(v) * v;
-      } else {
-        const float dy = a[i] > 0.0f ? da[i] + (da2 ? da2[i] : 0.0f) : 0.0f;
-        s0 += dy;
-        s1 += static_cast<double>(dy) * ((z[i] - mu) * is);
-      }
-    }
-    sh[0][sub][ch & 127] = s0;
-    sh[1][sub][ch & 127] = s1;
   }
   __syncthreads();
-  if (threadIdx.x < 128) {
-    const int cc = blockIdx.x * 128 + threadIdx.x;
+  if (threadIdx.x < 2 * STAT_CH) {
+    const int which = threadIdx.x / STAT_CH, cl = threadIdx.x % STAT_CH, cc = blockIdx.x * STAT_CH + cl;
     if (cc < c) {
-      double t0 = 0.0, t1 = 0.0;
-      for (int k = 0; k < 8; ++k) { t0 += sh[0][k][threadIdx.x]; t1 += sh[1][k][threadIdx.x]; }
-      partial[(0 * STAT_SPLITS + split) * c + cc] = t0;
-      partial[(1 * STAT_SPLITS + split) * c + cc] = t1;
+      double t = 0.0;
+      for (int k = 0; k < STAT_ROW_LANES; ++k) t += sh[which][k][cl];
+      partial[(which * STAT_SPLITS + split) * c + cc] = t;
     }
   }
 }
@@ -387,12 +383,20 @@ __global__ void head_conv_weight_reduce_kernel(const float* __restrict__ partial
 }
 
 // column sums of a row-major matrix (Dense bias gradients): out[j] = sum_i x[i][j]
-__global__ void column_sum_kernel(const float* __restrict__ x, int m, int n, float* __restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+// block = 32 columns x 8 row lanes (256 threads); the row lanes' sums are added in a fixed order
+__global__ void __launch_bounds__(256) column_sum_kernel(const float* __restrict__ x, int m, int n, float* __restrict__ out) {
+  __shared__ double sh[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, j = blockIdx.x * 32 + tx;
   double s = 0.0;
-  for (int i = 0; i < m; ++i) s += x[static_cast<size_t>(i) * n + j];
-  out[j] = static_cast<float>(s);
+  if (j < n)
+    for (int i = ty; i < m; i += 8) s += x[static_cast<size_t>(i) * n + j];
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && j < n) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += sh[k][tx];
+    out[j] = static_cast<float>(t);
+  }
 }
 
 // Flatten of a channels_first tensor (model_chess.py:81,90): head activations [b*64 + s][f] <-> features [b][f*64 + s]
@@ -549,21 +553,37 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int taps, 
 struct PackLayer { const float* w; uint16_t* wf; uint16_t* wb; int taps, cin, cin_pad, cout; };
 constexpr int PACK_MAX_LAYERS = 48;
 struct PackTable { PackLayer layer[PACK_MAX_LAYERS]; };
-__global__ void pack_all_conv_weights_kernel(const PackTable tab, int f_fp16, int b_fp16) {
+// a block walks (tap, 32 ic x 32 oc) tiles: reads and the wb stores run along oc, the wf stores along ic (through shared memory)
+__global__ void __launch_bounds__(256) pack_all_conv_weights_kernel(const PackTable tab, int f_fp16, int b_fp16) {
   const PackLayer& L = tab.layer[blockIdx.y];
-  const size_t total = static_cast<size_t>(L.taps) * L.cin * L.cout;
+  __shared__ float tile[32][33];
   auto bits = [](float x, int fp16) -> uint16_t {
     if (fp16) { const __half h = __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f)); return *reinterpret_cast<const uint16_t*>(&h); }
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
     return *reinterpret_cast<const uint16_t*>(&h);
   };
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int oc = static_cast<int>(i % L.cout);
-    const int ic = static_cast<int>((i / L.cout) % L.cin);
-    const int tap = static_cast<int>(i / (static_cast<size_t>(L.cout) * L.cin));
-    const float v = L.w[i];
-    L.wf[static_cast<size_t>(oc) * L.taps * L.cin_pad + static_cast<size_t>(tap) * L.cin_pad + ic] = bits(v, f_fp16);
-    if (L.wb) L.wb[static_cast<size_t>(ic) * L.taps * L.cout + static_cast<size_t>(L.taps - 1 - tap) * L.cout + oc] = bits(v, b_fp16);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ict = (L.cin + 31) / 32, oct = (L.cout + 31) / 32, tiles = L.taps * ict * oct;
+  for (int tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+    const int tap = tl / (ict * oct), ic0 = (tl / oct) % ict * 32, oc0 = tl % oct * 32;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ic = ic0 + ty + r * 8, oc = oc0 + tx;
+      float v = 0.0f;
+      if (ic < L.cin && oc < L.cout) {
+        v = L.w[(static_cast<size_t>(tap) * L.cin + ic) * L.cout + oc];
+        if (L.wb) L.wb[static_cast<size_t>(ic) * L.taps * L.cout + static_cast<size_t>(L.taps - 1 - tap) * L.cout + oc] = bits(v, b_fp16);
+      }
+      tile[ty + r * 8][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int oc = oc0 + ty + r * 8, ic = ic0 + tx;
+      if (ic < L.cin && oc < L.cout)
+        L.wf[static_cast<size_t>(oc) * L.taps * L.cin_pad + static_cast<size_t>(tap) * L.cin_pad + ic] = bits(tile[tx][ty + r * 8], f_fp16);
+    }
   }
 }
 
@@ -572,23 +592,30 @@ __global__ void pack_all_conv_weights_kernel(const PackTable tab, int f_fp16, in
 //   board < nb (nb = boards rounded up to 64; boards >= batch and channels >= c are written as zeros, halo cells stay zero
 //   from the allocation).  With this order a filter tap is a shift of the K index by a multiple of nb elements: 16-byte
 //   aligned, as the TMA box origin of the shifted operand has to be.
-// grid (nb / 32, c_pad / 32, 64 squares), 256 threads
+// grid (nb / 64, (c_pad + 63) / 64, 64 squares), 256 threads: a block turns 64 boards x 64 channels of one square
+// (reads: 64 channels = 256 B per board; stores: 64 boards = 128 B per channel, two boards per thread)
 __global__ void __launch_bounds__(256)
 transpose_pad_kernel(const float* __restrict__ x, int batch, int c, int c_pad, int nb, int pad, __nv_bfloat16* __restrict__ out) {
-  __shared__ float tile[32][33];
-  const int b0 = blockIdx.x * 32, c0 = blockIdx.y * 32, sq = blockIdx.z;
+  __shared__ float tile[64][65];
+  const int b0 = blockIdx.x * 64, c0 = blockIdx.y * 64, sq = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int pitch = 8 + 2 * pad, cells = pitch * pitch, cell = ((sq >> 3) + pad) * pitch + (sq & 7) + pad;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int b = b0 + ty + r * 8, ch = c0 + tx;
-    tile[ty + r * 8][tx] = (b < batch && ch < c) ? x[(static_cast<size_t>(b) * 64 + sq) * c + ch] : 0.0f;
+  for (int r = 0; r < 8; ++r) {
+    const int b = b0 + ty + r * 8;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int ch = c0 + tx + q * 32;
+      tile[ty + r * 8][tx + q * 32] = (b < batch && ch < c) ? x[(static_cast<size_t>(b) * 64 + sq) * c + ch] : 0.0f;
+    }
   }
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int ch = c0 + ty + r * 8, b = b0 + tx;
-    if (ch < c_pad && b < nb) out[(static_cast<size_t>(ch) * cells + cell) * nb + b] = __float2bfloat16_rn(tile[tx][ty + r * 8]);
+  for (int r = 0; r < 8; ++r) {
+    const int chl = ty + r * 8, ch = c0 + chl, b = b0 + 2 * tx;   // nb is a multiple of 64: b + 1 < nb whenever b < nb
+    if (ch < c_pad && b < nb)
+      *reinterpret_cast<__nv_bfloat162*>(out + (static_cast<size_t>(ch) * cells + cell) * nb + b) =
+          __floats2bfloat162_rn(tile[2 * tx][chl], tile[2 * tx + 1][chl]);
   }
 }
 
@@ -619,22 +646,41 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int taps, int splits, int
 //   m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= lr_t * m / (sqrt(v) + eps)
 // seg: per parameter 0 = frozen, 1 = trainable, 2 = trainable + l2, 3 = BatchNormalization moving statistic (its "gradient"
 // slot holds this step's batch statistic, summed over the ranks: moving = moving * momentum + mean batch statistic * (1 - momentum))
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            const uint8_t* __restrict__ seg, size_t n, float lr_t, float b1, float b2, float eps, float l2,
-                            float grad_scale, float bn_momentum) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n || seg[i] == 0) return;
-  if (seg[i] == 3) {
-    p[i] = p[i] * bn_momentum + g[i] * grad_scale * (1.0f - bn_momentum);
-    return;
+// l2_out (zeroed by the caller): sum of squares of the UPDATED l2-regularised parameters, the regularisation part of the next
+// step's loss (saves a pass over the parameters per step)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            const uint8_t* __restrict__ seg, size_t n, float lr_t, float b1, float b2, float eps, float l2,
+            float grad_scale, float bn_momentum, double* __restrict__ l2_out) {
+  double sq = 0.0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint8_t sg = seg[i];
+    if (sg == 0) continue;
+    if (sg == 3) {
+      p[i] = p[i] * bn_momentum + g[i] * grad_scale * (1.0f - bn_momentum);
+      continue;
+    }
+    float gi = g[i] * grad_scale;
+    const float pi = p[i];
+    if (sg == 2) gi += 2.0f * l2 * pi;
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float pn = pi - lr_t * mi / (sqrtf(vi) + eps);
+    p[i] = pn;
+    if (sg == 2) sq += static_cast<double>(pn) * pn;
   }
-  float gi = g[i] * grad_scale;
-  if (seg[i] == 2) gi += 2.0f * l2 * p[i];
-  const float mi = b1 * m[i] + (1.0f - b1) * gi;
-  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
-  m[i] = mi;
-  v[i] = vi;
-  p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  __shared__ double sh[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0 && l2_out) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += sh[k];
+    atomicAdd(l2_out, t);
+  }
 }
 
 // sum of squares of the l2-regularised parameters (reported as the regularisation part of the loss)
