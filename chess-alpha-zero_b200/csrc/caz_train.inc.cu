@@ -19,8 +19,11 @@ struct TrainConv {
   // 16-bit builds: fp16 NHWC copy of the activation (A operand of the next layer's forward convolution) and K-major
   // 16-bit copies of the kernel for the forward (fp16) and the input-gradient (bf16, rotated + transposed) convolutions
   uint16_t *a16 = nullptr, *wf = nullptr, *wb = nullptr;
+  // ... and the activation once more as the K-major bf16 operand [cout][cell][board] of the NEXT layer's weight-gradient GEMM
+  // (written by bn_apply_tile_kernel in the forward pass; halo cells stay zero from the allocation)
+  uint16_t* aT = nullptr;
   int cin_pad = 0;
-  CUtensorMap tm_a16, tm_wf, tm_wb;
+  CUtensorMap tm_a16, tm_wf, tm_wb, tm_aT;
   CUtensorMap tm_wf_h, tm_wb_h;   // the same weight matrices in boxes of cout / 4 (cin / 4) rows: two N tiles per board group
 };
 
@@ -59,6 +62,7 @@ struct caz_trainer {
   size_t grad_split = 0;
   bool capturing = false;
   bool profiling = false;
+  bool no_tile = false;   // CAZ_TRAIN_NO_TILE: BatchNormalization passes and transposes as separate kernels (the fallback for odd shapes)
   std::vector<std::pair<const char*, cudaEvent_t>> prof;
   int pending_batch = 0;
   // 16-bit builds (tensor-core convolutions): forward fp16 x fp16, input and weight gradients bf16 x bf16, fp32 accumulation
@@ -158,6 +162,12 @@ int tr_gemm(caz_trainer* t, const float* a, long a_si, long a_sk, const float* b
   return tr_launch_ok(t, "sum_partials_kernel");
 }
 
+// 16-bit builds, tower layers: the BatchNormalization passes run as tile kernels that also write the K-major operands of the
+// weight-gradient GEMMs (train.cuh); needs 64-channel tiles and float2 slices of the parameter vectors
+bool tr_tile_path(const caz_trainer* t, const TrainConv& L) {
+  return t->tc && L.a16 && (L.cout & 63) == 0 && (L.gamma & 3) == 0 && (L.beta & 3) == 0 && !t->no_tile;
+}
+
 // batch statistics of z (and the moving averages), then a = relu(BN(z) (+ skip))
 int tr_bn_forward(caz_trainer* t, TrainConv& L, const float* skip, int rows) {
   const dim3 grid((L.cout + caz::train::STAT_CH - 1) / caz::train::STAT_CH, caz::train::STAT_SPLITS);
@@ -169,6 +179,14 @@ int tr_bn_forward(caz_trainer* t, TrainConv& L, const float* skip, int rows) {
   if ((rc = tr_launch_ok(t, "bn_finish_stats_kernel"))) return rc;
   const size_t total = static_cast<size_t>(rows) * L.cout;
   const int vec4 = (L.cout & 3) == 0 && (L.gamma & 3) == 0 && (L.beta & 3) == 0;   // float4 slices of the parameter vectors
+  if (tr_tile_path(t, L)) {
+    const int pad = (t->arch.block_kernel - 1) / 2;
+    const dim3 tg(t->nb / 64, L.cout / 64, 64);
+    caz::train::bn_apply_tile_kernel<<<tg, 256, 0, t->stream>>>(L.z, skip, t->params + L.gamma, t->params + L.beta, L.mean, L.invstd, rows / 64, L.cout,
+                                                               t->nb, pad, L.a, reinterpret_cast<__half*>(L.a16),
+                                                               reinterpret_cast<__nv_bfloat16*>(L.aT));
+    return tr_launch_ok(t, "bn_apply_tile_kernel");
+  }
   caz::train::bn_apply_kernel<__half><<<blocks_for(vec4 ? total / 4 : total), 256, 0, t->stream>>>(L.z, skip, t->params + L.gamma, t->params + L.beta, L.mean,
                                                                                                    L.invstd, total, L.cout, L.a,
                                                                                                    reinterpret_cast<__half*>(L.a16), vec4);
@@ -177,7 +195,7 @@ int tr_bn_forward(caz_trainer* t, TrainConv& L, const float* skip, int rows) {
 
 // da (gradient wrt the layer's activation) -> dz (wrt its convolution output), dgamma / dbeta; dskip = gradient passed to the Add's other input
 int tr_bn_backward(caz_trainer* t, TrainConv& L, const float* da, float* dz, float* dskip, int dskip_accumulate, int rows,
-                   const float* da2 = nullptr, uint16_t* dz16 = nullptr) {
+                   const float* da2 = nullptr, uint16_t* dz16 = nullptr, __nv_bfloat16* dzT = nullptr) {
   const dim3 grid((L.cout + caz::train::STAT_CH - 1) / caz::train::STAT_CH, caz::train::STAT_SPLITS);
   caz::train::channel_sums_kernel<<<grid, caz::train::STAT_THREADS, 0, t->stream>>>(1, L.z, L.a, da, da2, L.mean, L.invstd, rows, L.cout, t->partial);
   int rc;
@@ -186,6 +204,13 @@ int tr_bn_backward(caz_trainer* t, TrainConv& L, const float* da, float* dz, flo
   if ((rc = tr_launch_ok(t, "bn_param_grads_kernel"))) return rc;
   const size_t total = static_cast<size_t>(rows) * L.cout;
   const int vec4 = (L.cout & 3) == 0 && (L.gamma & 3) == 0 && (L.beta & 3) == 0;
+  if (dzT && !dskip_accumulate) {   // tile path (the caller checked tr_tile_path): no fp32 dz, the transposed operand instead
+    const dim3 tg(t->nb / 64, L.cout / 64, 64);
+    caz::train::bn_backward_tile_kernel<<<tg, 256, 0, t->stream>>>(L.z, L.a, da, da2, t->params + L.gamma, L.mean, L.invstd, t->grads + L.beta,
+                                                                  t->grads + L.gamma, rows / 64, L.cout, t->nb, (L.k - 1) / 2,
+                                                                  reinterpret_cast<__nv_bfloat16*>(dz16), dzT, dskip);
+    return tr_launch_ok(t, "bn_backward_tile_kernel");
+  }
   caz::train::bn_backward_kernel<__nv_bfloat16><<<blocks_for(vec4 ? total / 4 : total), 256, 0, t->stream>>>(L.z, L.a, da, da2, t->params + L.gamma, L.mean, L.invstd,
                                                                                           t->grads + L.beta, t->grads + L.gamma, rows, L.cout, dz, reinterpret_cast<__nv_bfloat16*>(dz16), dskip,
                                                                                           dskip_accumulate, vec4);
@@ -280,6 +305,7 @@ int tr_conv_tc(caz_trainer* t, const CUtensorMap& tm_in, const CUtensorMap& tm_w
 }
 
 // dW[tap][ic][oc] of a k x k convolution: x rows [batch * 64][cin] (fp32), dz rows [batch * 64][cout] (fp32) -> t->grads + L.w
+// x / dz == nullptr: that operand has already been written in K-major form (tile kernels)
 int tr_wgrad_tc(caz_trainer* t, const float* x, const float* dz, int batch, const TrainConv& L, const CUtensorMap& tm_dzT, const CUtensorMap& tm_xT) {
   const int pad = (L.k - 1) / 2, pitch = 8 + 2 * pad, cells = pitch * pitch, taps = L.k * L.k;
   const int n_in_pad = L.cin < 32 ? 32 : L.cin;
@@ -288,10 +314,10 @@ int tr_wgrad_tc(caz_trainer* t, const float* x, const float* dz, int batch, cons
   {
     const dim3 g1(t->nb / 64, (L.cout + 63) / 64, 64), g2(t->nb / 64, (n_in_pad + 63) / 64, 64);
     const bool stem = &L == &t->convs[0];
-    caz::train::transpose_pad_kernel<<<g1, 256, 0, t->stream>>>(dz, batch, L.cout, L.cout, t->nb, pad, stem ? t->dzT_stem : t->dzT);
-    caz::train::transpose_pad_kernel<<<g2, 256, 0, t->stream>>>(x, batch, L.cin, n_in_pad, t->nb, pad, stem ? t->x0T : t->aT);
+    if (dz) caz::train::transpose_pad_kernel<<<g1, 256, 0, t->stream>>>(dz, batch, L.cout, L.cout, t->nb, pad, stem ? t->dzT_stem : t->dzT);
+    if (x) caz::train::transpose_pad_kernel<<<g2, 256, 0, t->stream>>>(x, batch, L.cin, n_in_pad, t->nb, pad, stem ? t->x0T : t->aT);
     int rc;
-    if ((rc = tr_launch_ok(t, "transpose_pad_kernel"))) return rc;
+    if ((dz || x) && (rc = tr_launch_ok(t, "transpose_pad_kernel"))) return rc;
   }
   const int chunks = cells * t->nb / 64;
   int splits = (t->num_sms / 2) / taps;
@@ -424,9 +450,13 @@ int tr_forward_backward(caz_trainer* t, int batch) {
     // conv2: the Add hands dy to the block's input as well (kept in d_skip until the gradient wrt that input is complete).
     // fp32 build: conv1's input-gradient convolution adds d_skip itself; 16-bit builds: the layer below reads it as da2.
     const float* da2 = (t->tc && (l & 1) == 0 && l < n_convs - 1) ? t->d_skip : nullptr;
-    if ((rc = tr_bn_backward(t, L, dcur, t->dz, conv2 ? t->d_skip : nullptr, 0, rows, da2, t->tc ? t->dz16 : nullptr))) return rc;
+    const bool tile = tr_tile_path(t, L);   // dz leaves the BatchNormalization pass as dz16 + dzT; the layer below left its aT
+    const bool in_tile = l > 0 && tr_tile_path(t, t->convs[l - 1]) && t->convs[l - 1].aT;
+    if ((rc = tr_bn_backward(t, L, dcur, t->dz, conv2 ? t->d_skip : nullptr, 0, rows, da2, t->tc ? t->dz16 : nullptr,
+                             tile ? (l == 0 ? t->dzT_stem : t->dzT) : nullptr))) return rc;
     const float* in = l == 0 ? t->x0 : t->convs[l - 1].a;
-    if (t->tc) rc = tr_wgrad_tc(t, in, t->dz, batch, L, l == 0 ? t->tm_dzT_stem : t->tm_dzT, l == 0 ? t->tm_x0T : t->tm_aT);
+    if (t->tc) rc = tr_wgrad_tc(t, in_tile ? nullptr : in, tile ? nullptr : t->dz, batch, L, l == 0 ? t->tm_dzT_stem : t->tm_dzT,
+                                l == 0 ? t->tm_x0T : (in_tile ? t->convs[l - 1].tm_aT : t->tm_aT));
     else rc = tr_wgrad_fp32(t, in, t->dz, batch, L);
     if (rc) return rc;
     if (l == 0) break;
@@ -456,7 +486,7 @@ void caz_train_destroy(caz_trainer* t) {
   if (!t->grads_external) ptrs.push_back(t->grads);
   for (void* p : {(void*)t->x0_16, (void*)t->dz16, (void*)t->dzT, (void*)t->aT, (void*)t->dzT_stem, (void*)t->x0T, (void*)t->wg_partial}) ptrs.push_back(p);
   auto free_conv = [&](TrainConv& L) {
-    for (void* p : {(void*)L.z, (void*)L.a, (void*)L.mean, (void*)L.invstd, (void*)L.a16, (void*)L.wf, (void*)L.wb}) ptrs.push_back(p);
+    for (void* p : {(void*)L.z, (void*)L.a, (void*)L.mean, (void*)L.invstd, (void*)L.a16, (void*)L.wf, (void*)L.wb, (void*)L.aT}) ptrs.push_back(p);
   };
   for (auto& L : t->convs) free_conv(L);
   free_conv(t->pconv);
@@ -665,6 +695,13 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
     const size_t k3 = (size_t)pitch3 * pitch3 * t->nb, ks = (size_t)pitch_s * pitch_s * t->nb;
     TC2(tr_alloc(t, &t->dzT, F * k3));
     TC2(tr_alloc(t, &t->aT, F * k3));
+    if (getenv("CAZ_TRAIN_NO_TILE")) t->no_tile = true;
+    for (size_t l = 0; l + 1 < t->convs.size() && !t->no_tile; ++l) {   // inputs of the tower's weight-gradient GEMMs
+      TrainConv& L = t->convs[l];
+      if ((L.cout & 63) != 0 || (size_t)L.cout != F) continue;
+      TC2(tr_alloc(t, &L.aT, F * k3));
+      TC2(tr_kmajor_tmap(t, &L.tm_aT, L.aT, k3, (int)F, (int)F / 2));
+    }
     TC2(tr_alloc(t, &t->dzT_stem, F * ks));
     TC2(tr_alloc(t, &t->x0T, (size_t)32 * ks));
     TC2(tr_halo_tmap(t, &t->tm_dzT, t->dzT, (int)k3, 1, (int)F / 64));

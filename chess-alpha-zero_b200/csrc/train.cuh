@@ -222,6 +222,95 @@ __global__ void bn_backward_kernel(const float* __restrict__ z, const float* __r
   if (dskip) dskip[i] = dskip_accumulate ? dskip[i] + dy : dy;
 }
 
+// ---- tensor-core build: the two BatchNormalization passes over a TILE of 64 boards x 64 channels of one square ----------
+// Same arithmetic as bn_apply_kernel / bn_backward_kernel, but a block owns 64 boards of one square, so that besides the
+// row-major outputs it can write, through shared memory, the K-major bf16 operand of the weight-gradient GEMM
+//   outT[ch][cell][board],  cell = (rank + pad) * pitch + file + pad over the zero-padded board (see transpose_pad_kernel)
+// in 128-byte runs -- the separate transposes (a read of the fp32 tensor and a launch each) are gone, and the backward
+// pass no longer writes the fp32 dz at all.  c % 64 == 0; grid (nb / 64, c / 64, 64 squares), 256 threads; boards >= batch
+// are written as zeros to outT.
+__device__ __forceinline__ void tile_store_transposed(const float (*tile)[65], __nv_bfloat16* __restrict__ outT, int c0, int b0, int nb,
+                                                      int pad, int sq, int tx, int ty) {
+  const int pitch = 8 + 2 * pad, cells = pitch * pitch, cell = ((sq >> 3) + pad) * pitch + (sq & 7) + pad;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int chl = ty + r * 8, b = b0 + 2 * tx;
+    if (b < nb)
+      *reinterpret_cast<__nv_bfloat162*>(outT + (static_cast<size_t>(c0 + chl) * cells + cell) * nb + b) =
+          __floats2bfloat162_rn(tile[2 * tx][chl], tile[2 * tx + 1][chl]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_tile_kernel(const float* __restrict__ z, const float* __restrict__ skip, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd, int batch, int c,
+                     int nb, int pad, float* __restrict__ a, __half* __restrict__ a16, __nv_bfloat16* __restrict__ aT) {
+  __shared__ float tile[64][65];
+  const int b0 = blockIdx.x * 64, c0 = blockIdx.y * 64, sq = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, ch = c0 + 2 * tx;
+  const float2 g = *reinterpret_cast<const float2*>(gamma + ch), be = *reinterpret_cast<const float2*>(beta + ch),
+               mu = *reinterpret_cast<const float2*>(mean + ch), is = *reinterpret_cast<const float2*>(invstd + ch);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int bl = ty + r * 8, b = b0 + bl;
+    float2 v = make_float2(0.0f, 0.0f);
+    if (b < batch) {
+      const size_t i = (static_cast<size_t>(b) * 64 + sq) * c + ch;
+      const float2 zv = *reinterpret_cast<const float2*>(z + i);
+      v = make_float2(g.x * ((zv.x - mu.x) * is.x) + be.x, g.y * ((zv.y - mu.y) * is.y) + be.y);
+      if (skip) {
+        const float2 sk = *reinterpret_cast<const float2*>(skip + i);
+        v.x += sk.x; v.y += sk.y;
+      }
+      v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f);
+      *reinterpret_cast<float2*>(a + i) = v;
+      *reinterpret_cast<__half2*>(a16 + i) = __floats2half2_rn(v.x, v.y);
+    }
+    tile[bl][2 * tx] = v.x;
+    tile[bl][2 * tx + 1] = v.y;
+  }
+  if (!aT) return;
+  __syncthreads();
+  tile_store_transposed(tile, aT, c0, b0, nb, pad, sq, tx, ty);
+}
+
+__global__ void __launch_bounds__(256)
+bn_backward_tile_kernel(const float* __restrict__ z, const float* __restrict__ a, const float* __restrict__ da, const float* da2,
+                        const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ sum_dy, const float* __restrict__ sum_dyx, int batch, int c, int nb, int pad,
+                        __nv_bfloat16* __restrict__ dz16, __nv_bfloat16* __restrict__ dzT, float* dskip) {
+  // (da2 and dskip may be the same buffer: each thread reads its elements of da2 before it writes them to dskip)
+  __shared__ float tile[64][65];
+  const int b0 = blockIdx.x * 64, c0 = blockIdx.y * 64, sq = blockIdx.z, rows = batch * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, ch = c0 + 2 * tx;
+  const float2 g = *reinterpret_cast<const float2*>(gamma + ch), mu = *reinterpret_cast<const float2*>(mean + ch),
+               is = *reinterpret_cast<const float2*>(invstd + ch), s0 = *reinterpret_cast<const float2*>(sum_dy + ch),
+               s1 = *reinterpret_cast<const float2*>(sum_dyx + ch);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int bl = ty + r * 8, b = b0 + bl;
+    float2 o = make_float2(0.0f, 0.0f);
+    if (b < batch) {
+      const size_t i = (static_cast<size_t>(b) * 64 + sq) * c + ch;
+      const float2 zv = *reinterpret_cast<const float2*>(z + i), av = *reinterpret_cast<const float2*>(a + i);
+      float2 dv = *reinterpret_cast<const float2*>(da + i);
+      if (da2) {
+        const float2 d2 = *reinterpret_cast<const float2*>(da2 + i);
+        dv.x += d2.x; dv.y += d2.y;
+      }
+      const float2 dy = make_float2(av.x > 0.0f ? dv.x : 0.0f, av.y > 0.0f ? dv.y : 0.0f);
+      o = make_float2(g.x * is.x * (dy.x - s0.x / rows - (zv.x - mu.x) * is.x * (s1.x / rows)),
+                      g.y * is.y * (dy.y - s0.y / rows - (zv.y - mu.y) * is.y * (s1.y / rows)));
+      *reinterpret_cast<__nv_bfloat162*>(dz16 + i) = __floats2bfloat162_rn(o.x, o.y);
+      if (dskip) *reinterpret_cast<float2*>(dskip + i) = dy;
+    }
+    tile[bl][2 * tx] = o.x;
+    tile[bl][2 * tx + 1] = o.y;
+  }
+  __syncthreads();
+  tile_store_transposed(tile, dzT, c0, b0, nb, pad, sq, tx, ty);
+}
+
 // dgamma / dbeta from the partial sums of channel_sums_kernel mode 1
 __global__ void bn_param_grads_kernel(const double* __restrict__ partial, int c, float* __restrict__ dgamma,
                                       float* __restrict__ dbeta) {
