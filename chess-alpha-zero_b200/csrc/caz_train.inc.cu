@@ -319,7 +319,9 @@ int tr_wgrad_tc(caz_trainer* t, const float* x, const float* dz, int batch, cons
     int rc;
     if ((dz || x) && (rc = tr_launch_ok(t, "transpose_pad_kernel"))) return rc;
   }
-  const int chunks = cells * t->nb / 64;
+  // K over the real cells only (ConvArgs::wg_cpc): dz^T is zero on the halo cells
+  const bool compact = !getenv("CAZ_TRAIN_WG_PADDED");
+  const int chunks = (compact ? 64 : cells) * t->nb / 64;
   int splits = (t->num_sms / 2) / taps;
   if (splits < 1) splits = 1;
   if (splits > 16) splits = 16;
@@ -341,6 +343,7 @@ int tr_wgrad_tc(caz_trainer* t, const float* x, const float* dz, int batch, cons
   args.wg_k = L.k;
   args.wg_pitch = pitch * t->nb;
   args.wg_dx = t->nb;
+  args.wg_cpc = compact ? t->nb / 64 : 0;
   int rc;
   if ((rc = tr_launch_tc(t, tm_dzT, tm_xT, args, taps * splits, "conv_tc2_kernel (weight gradient)"))) return rc;
   const dim3 gr((L.cin + 31) / 32, (L.cout + 31) / 32, taps);

@@ -94,6 +94,10 @@ struct ConvArgs {
   // (rank + pad) * pitch + file + pad, so that a filter tap is a plain shift of B's K coordinate.  wg_splits > 0 switches it on:
   // work item t = (tap t / wg_splits, split t % wg_splits) covers K chunks [split * kchunks, (split + 1) * kchunks).
   int wg_splits, wg_k, wg_pitch, wg_dx;   // K shift of tap (dy, dx): (dy - pad) * wg_pitch + (dx - pad) * wg_dx
+  // wg_cpc > 0: K runs over the 64 REAL cells only (wg_cpc chunks of 64 boards per cell): chunk j of the work list is chunk
+  // (cell(j / wg_cpc) * wg_cpc + j % wg_cpc) of the padded index -- A (dz^T) is zero on the halo cells, so those chunks (36 of
+  // 100 for a 3x3 kernel, 80 of 144 for 5x5) need neither loading nor multiplying
+  int wg_cpc;
   int* err_flag;
 };
 

@@ -73,6 +73,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   auto pair_of = [&](int t) -> int { const int pr = t / args.n_tiles; return args.reverse ? num_pairs - 1 - pr : pr; };
   const int k = args.ksize, pad = (k - 1) / 2, hw = 8 + k - 1;
   const int rb = args.row_bytes, kblk = rb >> 1;
+  auto wg_col = [&](int t, int kc) -> int {   // K coordinate (elements) of chunk kc of work item t, see ConvArgs::wg_cpc
+    int j = wg_kc0(t) + kc;
+    if (args.wg_cpc > 0) {
+      const int cc = j / args.wg_cpc, sub = j - cc * args.wg_cpc, pitch = args.wg_pitch / args.wg_dx, wpad = (args.wg_k - 1) / 2;
+      j = (((cc >> 3) + wpad) * pitch + (cc & 7) + wpad) * args.wg_cpc + sub;
+    }
+    return j * kblk;
+  };
   const int plane_bytes = hw * 2 * hw * rb;
   const int n_half = args.n >> 1;
   const uint32_t b_bytes = static_cast<uint32_t>(n_half) * rb;
@@ -140,7 +148,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
           ptx::mbar_wait(&b_empty[stage], phase ^ 1, args.err_flag, ERR2_PRODUCER_B);
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_expect_tx(&b_full[stage], 2 * b_bytes);   // both CTAs' halves
-            const int col = wg ? (wg_kc0(t) + kc) * kblk + wg_shift(t) : (tap * args.kchunks + kc) * kblk;
+            const int col = wg ? wg_col(t, kc) + wg_shift(t) : (tap * args.kchunks + kc) * kblk;
             ptx::tma_load_2d_2cta(smem_b + stage * bstage_bytes, &tmap_w, ptx::mapa_u32(&b_full[stage], 0),
                                   col, nt * args.n + static_cast<int>(rank) * n_half);
           }
@@ -166,8 +174,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
         ptx::mbar_wait(&a_empty[slot], phase ^ 1, args.err_flag, ERR2_PRODUCER_A);
         if (ptx::elect_one()) {
           if (leader) ptx::mbar_expect_tx(&a_full[slot], 2 * plane_bytes);
-          ptx::tma_load_4d_2cta(smem_a + slot * plane_bytes, &tmap_halo, ptx::mapa_u32(&a_full[slot], 0), (kc_first + kc) * kblk,
-                                -pad, tile * 2, -pad);
+          ptx::tma_load_4d_2cta(smem_a + slot * plane_bytes, &tmap_halo, ptx::mapa_u32(&a_full[slot], 0),
+                                wg ? wg_col(t, kc) : (kc_first + kc) * kblk, -pad, tile * 2, -pad);
         }
         __syncwarp();
         if (++slot == a_slots) { slot = 0; phase ^= 1; }

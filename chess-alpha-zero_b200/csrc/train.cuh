@@ -331,21 +331,35 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ partial, int c,
 __global__ void __launch_bounds__(256)
 gemm_kernel(const float* __restrict__ a, long a_si, long a_sk, const float* __restrict__ b, long b_sk, long b_sj,
             const float* __restrict__ bias, float* __restrict__ c, int m, int n, int k, int accumulate, int relu) {
-  __shared__ float sa[32][33], sb[32][33];
+  __shared__ float sa[32][33], sb[32][33];   // sa[i][k], sb[k][j]
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // ty 0..7: rows ty, ty+8, ty+16, ty+24
   const int kz = gridDim.z, kper = ((k + kz - 1) / kz + 31) / 32 * 32;
   const int k0 = blockIdx.z * kper, k1 = min(k, k0 + kper);
+  // the lanes of a warp run along whichever index of the operand is contiguous in memory (A may be a transposed view, B too)
+  const bool a_lanes_k = a_sk == 1 || a_si != 1, b_lanes_j = b_sj == 1 || b_sk != 1;
+  float ra[4], rb[4];
+  auto fetch = [&](int kk) {   // this thread's elements of the slab starting at kk, into registers
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int q = ty + r * 8;
+      const int ia = i0 + (a_lanes_k ? q : tx), ka = kk + (a_lanes_k ? tx : q);
+      ra[r] = (ia < m && ka < k1) ? a[ia * a_si + ka * a_sk] : 0.0f;
+      const int kb = kk + (b_lanes_j ? q : tx), jb = j0 + (b_lanes_j ? tx : q);
+      rb[r] = (kb < k1 && jb < n) ? b[kb * b_sk + jb * b_sj] : 0.0f;
+    }
+  };
   float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (k0 < k1) fetch(k0);
   for (int kk = k0; kk < k1; kk += 32) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int i = i0 + ty + r * 8, ka = kk + tx;
-      sa[ty + r * 8][tx] = (i < m && ka < k1) ? a[i * a_si + ka * a_sk] : 0.0f;
-      const int kb = kk + ty + r * 8, j = j0 + tx;
-      sb[ty + r * 8][tx] = (kb < k1 && j < n) ? b[kb * b_sk + j * b_sj] : 0.0f;
+      const int q = ty + r * 8;
+      if (a_lanes_k) sa[q][tx] = ra[r]; else sa[tx][q] = ra[r];
+      if (b_lanes_j) sb[q][tx] = rb[r]; else sb[tx][q] = rb[r];
     }
     __syncthreads();
+    if (kk + 32 < k1) fetch(kk + 32);   // the next slab's loads fly under this slab's arithmetic
 #pragma unroll 8
     for (int q = 0; q < 32; ++q) {
       const float bv = sb[q][tx];
