@@ -197,16 +197,18 @@ int tr_bn_forward(caz_trainer* t, TrainConv& L, const float* skip, int rows) {
 int tr_bn_backward(caz_trainer* t, TrainConv& L, const float* da, float* dz, float* dskip, int dskip_accumulate, int rows,
                    const float* da2 = nullptr, uint16_t* dz16 = nullptr, __nv_bfloat16* dzT = nullptr) {
   const dim3 grid((L.cout + caz::train::STAT_CH - 1) / caz::train::STAT_CH, caz::train::STAT_SPLITS);
-  caz::train::channel_sums_kernel<<<grid, caz::train::STAT_THREADS, 0, t->stream>>>(1, L.z, L.a, da, da2, L.mean, L.invstd, rows, L.cout, t->partial);
+  const bool tile_path = dzT && !dskip_accumulate;   // (the caller checked tr_tile_path)
+  caz::train::channel_sums_kernel<<<grid, caz::train::STAT_THREADS, 0, t->stream>>>(1, L.z, L.a, da, da2, L.mean, L.invstd, rows, L.cout, t->partial,
+                                                                                    tile_path ? reinterpret_cast<const __half*>(L.a16) : nullptr);
   int rc;
   if ((rc = tr_launch_ok(t, "channel_sums_kernel (backward)"))) return rc;
   caz::train::bn_param_grads_kernel<<<(L.cout + 7) / 8, 256, 0, t->stream>>>(t->partial, L.cout, t->grads + L.gamma, t->grads + L.beta);
   if ((rc = tr_launch_ok(t, "bn_param_grads_kernel"))) return rc;
   const size_t total = static_cast<size_t>(rows) * L.cout;
   const int vec4 = (L.cout & 3) == 0 && (L.gamma & 3) == 0 && (L.beta & 3) == 0;
-  if (dzT && !dskip_accumulate) {   // tile path (the caller checked tr_tile_path): no fp32 dz, the transposed operand instead
+  if (tile_path) {   // no fp32 dz, the transposed operand instead
     const dim3 tg(t->nb / 64, L.cout / 64, 64);
-    caz::train::bn_backward_tile_kernel<<<tg, 256, 0, t->stream>>>(L.z, L.a, da, da2, t->params + L.gamma, L.mean, L.invstd, t->grads + L.beta,
+    caz::train::bn_backward_tile_kernel<<<tg, 256, 0, t->stream>>>(L.z, reinterpret_cast<const __half*>(L.a16), da, da2, t->params + L.gamma, L.mean, L.invstd, t->grads + L.beta,
                                                                   t->grads + L.gamma, rows / 64, L.cout, t->nb, (L.k - 1) / 2,
                                                                   reinterpret_cast<__nv_bfloat16*>(dz16), dzT, dskip);
     return tr_launch_ok(t, "bn_backward_tile_kernel");

@@ -28,7 +28,8 @@ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_c
 __global__ void __launch_bounds__(STAT_THREADS)
 channel_sums_kernel(int mode, const float* __restrict__ z, const float* __restrict__ a, const float* __restrict__ da,
                     const float* __restrict__ da2, const float* __restrict__ mean, const float* __restrict__ invstd, int rows, int c,
-                    double* __restrict__ partial) {
+                    double* __restrict__ partial, const __half* __restrict__ a16 = nullptr) {
+  // a16 (tensor-core build, c % 4 == 0): the ReLU mask is read from the fp16 copy of the activation (half the bytes of `a`)
   // a block covers 64 channels (16 lanes x float4) x 32 row lanes; c < 4 or not a multiple of 4: scalar path below
   const int split = blockIdx.y;
   const int per = (rows + STAT_SPLITS - 1) / STAT_SPLITS;
@@ -50,7 +51,14 @@ channel_sums_kernel(int mode, const float* __restrict__ z, const float* __restri
           s1[0] += static_cast<double>(zv.x) * zv.x; s1[1] += static_cast<double>(zv.y) * zv.y;
           s1[2] += static_cast<double>(zv.z) * zv.z; s1[3] += static_cast<double>(zv.w) * zv.w;
         } else {
-          const float4 av = *reinterpret_cast<const float4*>(a + i);
+          float4 av;
+          if (a16) {
+            const uint2 raw = *reinterpret_cast<const uint2*>(a16 + i);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            av = make_float4(lo.x, lo.y, hi.x, hi.y);
+          } else {
+            av = *reinterpret_cast<const float4*>(a + i);
+          }
           float4 dv = *reinterpret_cast<const float4*>(da + i);
           if (da2) {   // the gradient that arrived over the skip connection
             const float4 d2 = *reinterpret_cast<const float4*>(da2 + i);
@@ -223,7 +231,8 @@ __global__ void bn_backward_kernel(const float* __restrict__ z, const float* __r
 }
 
 // ---- tensor-core build: the two BatchNormalization passes over a TILE of 64 boards x 64 channels of one square ----------
-// Same arithmetic as bn_apply_kernel / bn_backward_kernel, but a block owns 64 boards of one square, so that besides the
+// Same arithmetic as bn_apply_kernel / bn_backward_kernel (the ReLU mask is taken from the fp16 copy of the activation: it
+// differs from the fp32 one only where 0 < a < 2^-25), but a block owns 64 boards of one square, so that besides the
 // row-major outputs it can write, through shared memory, the K-major bf16 operand of the weight-gradient GEMM
 //   outT[ch][cell][board],  cell = (rank + pad) * pitch + file + pad over the zero-padded board (see transpose_pad_kernel)
 // in 128-byte runs -- the separate transposes (a read of the fp32 tensor and a launch each) are gone, and the backward
@@ -275,7 +284,7 @@ bn_apply_tile_kernel(const float* __restrict__ z, const float* __restrict__ skip
 }
 
 __global__ void __launch_bounds__(256)
-bn_backward_tile_kernel(const float* __restrict__ z, const float* __restrict__ a, const float* __restrict__ da, const float* da2,
+bn_backward_tile_kernel(const float* __restrict__ z, const __half* __restrict__ a16, const float* __restrict__ da, const float* da2,
                         const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ sum_dy, const float* __restrict__ sum_dyx, int batch, int c, int nb, int pad,
                         __nv_bfloat16* __restrict__ dz16, __nv_bfloat16* __restrict__ dzT, float* dskip) {
@@ -292,7 +301,7 @@ bn_backward_tile_kernel(const float* __restrict__ z, const float* __restrict__ a
     float2 o = make_float2(0.0f, 0.0f);
     if (b < batch) {
       const size_t i = (static_cast<size_t>(b) * 64 + sq) * c + ch;
-      const float2 zv = *reinterpret_cast<const float2*>(z + i), av = *reinterpret_cast<const float2*>(a + i);
+      const float2 zv = *reinterpret_cast<const float2*>(z + i), av = __half22float2(*reinterpret_cast<const __half2*>(a16 + i));
       float2 dv = *reinterpret_cast<const float2*>(da + i);
       if (da2) {
         const float2 d2 = *reinterpret_cast<const float2*>(da2 + i);
