@@ -299,7 +299,8 @@ def training_leg(args, cfg, weights, ev, local, rank, world, batch=384):
             "unit": UNIT, "ms_per_step": 1e3 * dt / args.train_steps, "steps": args.train_steps, "n_gpus": world, "precision": "bf16 (mixed)",
             "approx_tflops": 3 * flops_per_position(args.blocks) * world * batch * args.train_steps / dt / 1e12,
             "loss_first_last": [losses[0], losses[-1]], "ranks_hold_identical_weights": bool(same),
-            "collective": "torch.distributed.all_reduce (NCCL) of the flat fp32 gradient vector, every step" if world > 1 else None}
+            "collective": ("torch.distributed.all_reduce (NCCL) of the flat fp32 gradient vector, every step; the upper half of the "
+                           "network's gradients is reduced under the backward pass of the lower half") if world > 1 else None}
 
 
 def latency_probe(ev, planes16, calls=1000):

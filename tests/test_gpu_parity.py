@@ -574,6 +574,9 @@ def test_4096_distinct_positions_against_oracle(net_default):
 
 
 # ---- a7/a8: the pipe protocol, ours and the reference's own server class ------------------------
+_REFERENCE_API_KEEPALIVE = []
+
+
 def _reference_api_class():
     """The reference's UNMODIFIED ChessModelAPI: from the checkout in the build container, or from the copy
     __graft_entry__.build() stages under baseline/_ref/ (git-ignored; it travels to the GPU box with the snapshot)."""
@@ -621,6 +624,9 @@ def test_reference_chessmodelapi_runs_on_the_cuda_evaluator(net):
             assert np.abs(p - wp[j]).max() <= BF16_TOL and abs(v - float(wv[j, 0])) <= BF16_TOL
     print(f"   reference ChessModelAPI from {src}: 128 requests answered by the CUDA evaluator")
     model.model.close()
+    # the reference's worker thread has no way to stop: keep its pipes open so that it sleeps in connection.wait() for the
+    # rest of the session instead of dying with EOFError inside some later test
+    _REFERENCE_API_KEEPALIVE.append((api, pipes))
 
 
 @pytest.mark.parametrize("transport", ["shm"])
