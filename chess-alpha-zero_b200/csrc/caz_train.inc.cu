@@ -62,6 +62,7 @@ struct caz_trainer {
   size_t grad_split = 0;
   bool capturing = false;
   bool profiling = false;
+  bool mask_fp32 = false;   // CAZ_TRAIN_MASK_FP32: the backward passes read the ReLU mask from the fp32 activations
   bool no_tile = false;   // CAZ_TRAIN_NO_TILE: BatchNormalization passes and transposes as separate kernels (the fallback for odd shapes)
   std::vector<std::pair<const char*, cudaEvent_t>> prof;
   int pending_batch = 0;
@@ -199,7 +200,7 @@ int tr_bn_backward(caz_trainer* t, TrainConv& L, const float* da, float* dz, flo
   const dim3 grid((L.cout + caz::train::STAT_CH - 1) / caz::train::STAT_CH, caz::train::STAT_SPLITS);
   const bool tile_path = dzT && !dskip_accumulate;   // (the caller checked tr_tile_path)
   caz::train::channel_sums_kernel<<<grid, caz::train::STAT_THREADS, 0, t->stream>>>(1, L.z, L.a, da, da2, L.mean, L.invstd, rows, L.cout, t->partial,
-                                                                                    tile_path ? reinterpret_cast<const __half*>(L.a16) : nullptr);
+                                                                                    tile_path && !t->mask_fp32 ? reinterpret_cast<const __half*>(L.a16) : nullptr);
   int rc;
   if ((rc = tr_launch_ok(t, "channel_sums_kernel (backward)"))) return rc;
   caz::train::bn_param_grads_kernel<<<(L.cout + 7) / 8, 256, 0, t->stream>>>(t->partial, L.cout, t->grads + L.gamma, t->grads + L.beta);
@@ -208,7 +209,7 @@ int tr_bn_backward(caz_trainer* t, TrainConv& L, const float* da, float* dz, flo
   const int vec4 = (L.cout & 3) == 0 && (L.gamma & 3) == 0 && (L.beta & 3) == 0;
   if (tile_path) {   // no fp32 dz, the transposed operand instead
     const dim3 tg(t->nb / 64, L.cout / 64, 64);
-    caz::train::bn_backward_tile_kernel<<<tg, 256, 0, t->stream>>>(L.z, reinterpret_cast<const __half*>(L.a16), da, da2, t->params + L.gamma, L.mean, L.invstd, t->grads + L.beta,
+    caz::train::bn_backward_tile_kernel<<<tg, 256, 0, t->stream>>>(L.z, L.a, t->mask_fp32 ? nullptr : reinterpret_cast<const __half*>(L.a16), da, da2, t->params + L.gamma, L.mean, L.invstd, t->grads + L.beta,
                                                                   t->grads + L.gamma, rows / 64, L.cout, t->nb, (L.k - 1) / 2,
                                                                   reinterpret_cast<__nv_bfloat16*>(dz16), dzT, dskip);
     return tr_launch_ok(t, "bn_backward_tile_kernel");
@@ -701,6 +702,7 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
     TC2(tr_alloc(t, &t->dzT, F * k3));
     TC2(tr_alloc(t, &t->aT, F * k3));
     if (getenv("CAZ_TRAIN_NO_TILE")) t->no_tile = true;
+    if (getenv("CAZ_TRAIN_MASK_FP32")) t->mask_fp32 = true;
     for (size_t l = 0; l + 1 < t->convs.size() && !t->no_tile; ++l) {   // inputs of the tower's weight-gradient GEMMs
       TrainConv& L = t->convs[l];
       if ((L.cout & 63) != 0 || (size_t)L.cout != F) continue;

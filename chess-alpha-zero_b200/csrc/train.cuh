@@ -231,8 +231,9 @@ __global__ void bn_backward_kernel(const float* __restrict__ z, const float* __r
 }
 
 // ---- tensor-core build: the two BatchNormalization passes over a TILE of 64 boards x 64 channels of one square ----------
-// Same arithmetic as bn_apply_kernel / bn_backward_kernel (the ReLU mask is taken from the fp16 copy of the activation: it
-// differs from the fp32 one only where 0 < a < 2^-25), but a block owns 64 boards of one square, so that besides the
+// Same arithmetic as bn_apply_kernel / bn_backward_kernel (bit-identical results when the ReLU mask is read from the fp32
+// activation, CAZ_TRAIN_MASK_FP32; by default it comes from the fp16 copy -- half the bytes -- which differs where
+// 0 < a < 2^-25: about one element per few layers, far fewer than the forward pass's 16-bit operands flip), but a block owns 64 boards of one square, so that besides the
 // row-major outputs it can write, through shared memory, the K-major bf16 operand of the weight-gradient GEMM
 //   outT[ch][cell][board],  cell = (rank + pad) * pitch + file + pad over the zero-padded board (see transpose_pad_kernel)
 // in 128-byte runs -- the separate transposes (a read of the fp32 tensor and a launch each) are gone, and the backward
@@ -284,7 +285,7 @@ bn_apply_tile_kernel(const float* __restrict__ z, const float* __restrict__ skip
 }
 
 __global__ void __launch_bounds__(256)
-bn_backward_tile_kernel(const float* __restrict__ z, const __half* __restrict__ a16, const float* __restrict__ da, const float* da2,
+bn_backward_tile_kernel(const float* __restrict__ z, const float* __restrict__ a, const __half* __restrict__ a16, const float* __restrict__ da, const float* da2,
                         const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ sum_dy, const float* __restrict__ sum_dyx, int batch, int c, int nb, int pad,
                         __nv_bfloat16* __restrict__ dz16, __nv_bfloat16* __restrict__ dzT, float* dskip) {
@@ -301,7 +302,8 @@ bn_backward_tile_kernel(const float* __restrict__ z, const __half* __restrict__ 
     float2 o = make_float2(0.0f, 0.0f);
     if (b < batch) {
       const size_t i = (static_cast<size_t>(b) * 64 + sq) * c + ch;
-      const float2 zv = *reinterpret_cast<const float2*>(z + i), av = __half22float2(*reinterpret_cast<const __half2*>(a16 + i));
+      const float2 zv = *reinterpret_cast<const float2*>(z + i),
+                   av = a16 ? __half22float2(*reinterpret_cast<const __half2*>(a16 + i)) : *reinterpret_cast<const float2*>(a + i);
       float2 dv = *reinterpret_cast<const float2*>(da + i);
       if (da2) {
         const float2 d2 = *reinterpret_cast<const float2*>(da2 + i);

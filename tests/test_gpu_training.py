@@ -254,3 +254,45 @@ def test_overlapped_all_reduce_step_runs_like_the_plain_step():
             tb.close()
     finally:
         dist.destroy_process_group()
+
+
+def test_tile_kernels_and_halo_free_weight_gradient_change_nothing(monkeypatch):
+    """The tensor-core build's BatchNormalization tile kernels (which also write the K-major operands of the weight-gradient
+    GEMMs) against the separate elementwise + transpose kernels they replaced (CAZ_TRAIN_NO_TILE=1): with the ReLU mask read
+    from the fp32 activations (CAZ_TRAIN_MASK_FP32=1) every gradient tensor and the losses are the same bit for bit.  By
+    default the mask comes from the fp16 activations (half the bytes): it differs where 0 < a < 2^-25 -- one element of one
+    layer in this case -- which moves that channel's sums: bounded here at 5e-3 of each tensor's largest entry (the forward
+    pass's 16-bit operands flip far more masks than that).  And the weight-gradient GEMM over the real cells only against
+    the one over the whole zero-padded index (CAZ_TRAIN_WG_PADDED=1): same products, other split boundaries -> equal to
+    fp32 summation rounding."""
+    cfg = oweights.keras_config(filters=64, blocks=2)
+    w = oweights.synth_weights(cfg, seed=2, recipe="randomized")
+    x, pt, vt = _data(70, seed=5)
+
+    def run():
+        tr = caz.Trainer(cfg, w, precision="bf16", max_batch=73)
+        losses = tr.forward_backward(x, pt, vt)
+        g = tr.gradients()
+        tr.close()
+        return losses, g
+
+    l_new, g_new = run()
+    monkeypatch.setenv("CAZ_TRAIN_MASK_FP32", "1")
+    l_m32, g_m32 = run()
+    monkeypatch.setenv("CAZ_TRAIN_NO_TILE", "1")
+    l_old, g_old = run()
+    monkeypatch.delenv("CAZ_TRAIN_NO_TILE")
+    monkeypatch.delenv("CAZ_TRAIN_MASK_FP32")
+    assert l_new == l_old == l_m32, (l_new, l_old, l_m32)
+    for k in g_old:
+        assert np.array_equal(g_m32[k], g_old[k]), k
+    differing = {k: _rel(g_new[k], g_old[k]) for k in g_new if not np.array_equal(g_new[k], g_old[k])}
+    print(f"   fp16 mask vs fp32 mask: {len(g_new) - len(differing)} of {len(g_new)} tensors bit-identical; worst of the others "
+          f"{max(differing.values(), default=0.0):.2e}")
+    assert all(v <= 5e-3 for v in differing.values()), differing
+    monkeypatch.setenv("CAZ_TRAIN_WG_PADDED", "1")
+    l_pad, g_pad = run()
+    assert l_pad == l_new
+    worst = max(_rel(g_new[k], g_pad[k]) for k in g_new)
+    print(f"   real-cell K vs padded K: worst relative difference {worst:.2e}")
+    assert worst <= 2e-5
