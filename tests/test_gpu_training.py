@@ -296,3 +296,27 @@ def test_tile_kernels_and_halo_free_weight_gradient_change_nothing(monkeypatch):
     worst = max(_rel(g_new[k], g_pad[k]) for k in g_new)
     print(f"   real-cell K vs padded K: worst relative difference {worst:.2e}")
     assert worst <= 2e-5
+
+
+def test_trainer_rejects_bad_calls():
+    """Error behaviour of the training ABI: loud, and the trainer stays usable afterwards."""
+    cfg = oweights.keras_config(filters=64, blocks=1)
+    w = oweights.synth_weights(cfg, seed=1, recipe="keras_default")
+    x, pt, vt = _data(8, seed=3)
+    tr = caz.Trainer(cfg, w, precision="bf16", max_batch=6)
+    with pytest.raises(caz.CazError, match="batch 8, max_batch 6"):
+        tr.forward_backward(x, pt, vt)
+    with pytest.raises(ValueError):
+        tr.forward_backward(x[:4], pt[:4, :100], vt[:4])               # policy targets of the wrong width
+    with pytest.raises(ValueError):
+        tr.forward_backward(x[:4], pt[:4], vt[:3])                     # one value target missing
+    losses = np.zeros(4, np.float32)
+    rc = tr._lib.caz_train_forward_backward_end(tr._h, losses.ctypes.data)
+    assert rc != 0 and b"without a begin" in tr._lib.caz_train_last_error(tr._h)
+    assert tr._lib.caz_train_wait_gradients(tr._h, 2, None) != 0       # there are two parts, 0 and 1
+    out = tr.train_on_batch(x[:6], pt[:6], vt[:6])                     # still works
+    assert np.isfinite(out["loss"]) and tr.steps == 1
+    with pytest.raises(ValueError, match="precision"):
+        caz.Trainer(cfg, w, precision="fp8")
+    tr.close()
+    tr.close()                                                         # idempotent
