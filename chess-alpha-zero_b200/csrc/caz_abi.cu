@@ -527,7 +527,7 @@ int launch_conv(caz_handle* h, int li, const void* in, const CUtensorMap* tmap_i
       at[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at;
       cfg.numAttrs = h->pdl ? 1 : 0;
-      cudaError_t e = cudaLaunchKernelEx(&cfg, caz::tc2::conv_tc2_kernel, *tmap_in, split_n ? L.tmap_w2h : L.tmap_w2, args);
+      cudaError_t e = cudaLaunchKernelEx(&cfg, caz::tc2::conv_tc2_kernel, *tmap_in, split_n ? L.tmap_w2h : L.tmap_w2, L.tmap_w2, args);
       if (e != cudaSuccess) return fail(h, CAZ_ERR_CUDA, fmt("launch of conv_tc2_kernel failed: %s", cudaGetErrorString(e)));
       return check_launch(h, "conv_tc2_kernel");
     }
@@ -1085,7 +1085,7 @@ int launch_dense_tc(caz_handle* h, const float* in, uint16_t* a3, const CUtensor
   args.pdl = h->pdl ? 1 : 0;
   const int work = ((args.num_tiles + 1) / 2) * n_tiles, max_pairs = h->num_sms / 2;
   const int grid = 2 * (work < max_pairs ? work : max_pairs);
-  launch_chained(caz::tc2::conv_tc2_kernel, dim3(grid), dim3(caz::tc2::THREADS), caz::tc2::SMEM_BYTES, h->stream, h->pdl, *tm_a, *tm_w, args);
+  launch_chained(caz::tc2::conv_tc2_kernel, dim3(grid), dim3(caz::tc2::THREADS), caz::tc2::SMEM_BYTES, h->stream, h->pdl, *tm_a, *tm_w, *tm_w, args);
   return check_launch(h, "conv_tc2_kernel (dense)");
 }
 

@@ -271,11 +271,12 @@ int tr_kmajor_tmap(caz_trainer* t, CUtensorMap* m, void* base, size_t kdim, int 
   return tr_tmap(t, m, base, 2, dims, strides, box, row_bytes);
 }
 
-int tr_launch_tc(caz_trainer* t, const CUtensorMap& tm_a, const CUtensorMap& tm_b, caz::tc::ConvArgs& args, int work, const char* what) {
+int tr_launch_tc(caz_trainer* t, const CUtensorMap& tm_a, const CUtensorMap& tm_b, caz::tc::ConvArgs& args, int work, const char* what,
+                 const CUtensorMap* tm_b_whole = nullptr) {
   args.err_flag = nullptr;
   const int max_pairs = t->num_sms / 2;
   const int grid = 2 * (work < max_pairs ? work : max_pairs);
-  caz::tc2::conv_tc2_kernel<<<grid, caz::tc2::THREADS, caz::tc2::SMEM_BYTES, t->stream>>>(tm_a, tm_b, args);
+  caz::tc2::conv_tc2_kernel<<<grid, caz::tc2::THREADS, caz::tc2::SMEM_BYTES, t->stream>>>(tm_a, tm_b, tm_b_whole ? *tm_b_whole : tm_b, args);
   return tr_launch_ok(t, what);
 }
 
@@ -297,12 +298,19 @@ int tr_conv_tc(caz_trainer* t, const CUtensorMap& tm_in, const CUtensorMap& tm_w
   args.out_rm = out;
   // Two N tiles of n / 2 channels per board group when that fills the last wave better: batch 384 = 96 groups on 74 CTA pairs
   // is two waves of whole tiles but 2.6 waves of half tiles (= 1.3 tile times)
+  // ... or MIXED: whole tiles for as many full rounds as the groups fill, half tiles for the rest (ConvArgs::mixed_whole).
+  // Measured tile times on 74 pairs: whole 12.5 us, half 8.65 us (an N = 128 MMA sweep is not half an N = 256 one).
   const int pairs = (args.num_tiles + 1) / 2, maxp = t->num_sms / 2;
-  const int waves_whole = (pairs + maxp - 1) / maxp, half_waves = (2 * pairs + maxp - 1) / maxp;
-  if (n % 64 == 0 && half_waves < 2 * waves_whole) {
+  const double t_whole = 12.5, t_half = 8.65;
+  const int full = pairs / maxp * maxp;   // groups that make full rounds of whole tiles
+  const double c_whole = (pairs + maxp - 1) / maxp * t_whole, c_half = (2 * pairs + maxp - 1) / maxp * t_half,
+               c_mixed = full / maxp * t_whole + (2 * (pairs - full) + maxp - 1) / maxp * t_half;
+  if (n % 64 == 0 && !getenv("CAZ_TRAIN_WHOLE_TILES") && (c_half < c_whole || c_mixed < c_whole)) {
     args.n_tiles = 2;
     args.n = n / 2;
-    return tr_launch_tc(t, tm_in, tm_w_half, args, 2 * pairs, "conv_tc2_kernel (training, two N tiles)");
+    args.mixed_whole = (c_mixed < c_half && !getenv("CAZ_TRAIN_NO_MIXED")) ? full : 0;
+    return tr_launch_tc(t, tm_in, tm_w_half, args, args.mixed_whole + 2 * (pairs - args.mixed_whole),
+                        args.mixed_whole ? "conv_tc2_kernel (training, whole + half N tiles)" : "conv_tc2_kernel (training, two N tiles)", &tm_w);
   }
   return tr_launch_tc(t, tm_in, tm_w, args, pairs, "conv_tc2_kernel (training)");
 }

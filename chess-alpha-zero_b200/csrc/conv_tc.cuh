@@ -98,6 +98,7 @@ struct ConvArgs {
   // (cell(j / wg_cpc) * wg_cpc + j % wg_cpc) of the padded index -- A (dz^T) is zero on the halo cells, so those chunks (36 of
   // 100 for a 3x3 kernel, 80 of 144 for 5x5) need neither loading nor multiplying
   int wg_cpc;
+  int mixed_whole;          // CTA-pair kernel, n_tiles == 2: this many leading work items take both N tiles at once (conv_tc2.cuh)
   int* err_flag;
 };
 

@@ -38,10 +38,11 @@ constexpr int SMEM_BYTES = A_RING_BYTES + B_STAGES * B_STAGE_BYTES + tc::EPI_BYT
 
 enum : int { ERR2_PRODUCER_B = 301, ERR2_PRODUCER_A = 302, ERR2_MMA_B = 303, ERR2_MMA_A = 304, ERR2_MMA_ACC = 305 };
 
-// tmap_w: weight rows [oc][K] with box 64 x (n/2)
+// tmap_w: weight rows [oc][K] with box 64 x (n/2); tmap_w_whole: the same matrix with box 64 x n, used by the full-width work
+// items of a mixed launch (ConvArgs::mixed_whole; any valid map otherwise)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_constant__ CUtensorMap tmap_w,
-                const ConvArgs args) {
+                const __grid_constant__ CUtensorMap tmap_w_whole, const ConvArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -64,13 +65,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   const bool wg = args.wg_splits > 0;               // weight-gradient GEMM (see ConvArgs): work items are (tap, K split)
   const int pair0 = blockIdx.x >> 1, n_pairs_grid = gridDim.x >> 1;
   const int num_pairs = (args.num_tiles + 1) >> 1;
-  const int num_work = wg ? args.wg_k * args.wg_k * args.wg_splits : num_pairs * args.n_tiles;   // else (board-pair pair, N tile)
+  // Two N tiles per board group (n_tiles == 2, args.n = half the width) may be MIXED: the first mixed_whole work items take a
+  // whole group (both N tiles in one 2 n wide tile -- one MMA sweep at full efficiency), the groups after them are split.  96
+  // groups on 74 CTA pairs: 74 whole tiles, then 44 half tiles = one whole + one half tile time instead of three half tiles.
+  const int mixed_whole = (!wg && args.n_tiles == 2) ? args.mixed_whole : 0;
+  const int num_work = wg ? args.wg_k * args.wg_k * args.wg_splits   // (tap, K split), else (board-pair pair, N tile)
+                          : (args.n_tiles == 2 ? mixed_whole + 2 * (num_pairs - mixed_whole) : num_pairs * args.n_tiles);
+  auto item_whole = [&](int t) -> bool { return t < mixed_whole; };
+  auto item_nt = [&](int t) -> int { return args.n_tiles == 2 ? (t < mixed_whole ? 0 : (t - mixed_whole) & 1) : t % args.n_tiles; };
   // K-coordinate shift of the B operand for the tap of work item t, and its first K chunk
   auto wg_shift = [&](int t) -> int { const int tap = t / args.wg_splits; return (tap / args.wg_k - (args.wg_k - 1) / 2) * args.wg_pitch + (tap % args.wg_k - (args.wg_k - 1) / 2) * args.wg_dx; };
   auto wg_kc0 = [&](int t) -> int { return (t % args.wg_splits) * args.kchunks; };
   // Consecutive layers walk the batch in opposite directions ("snake"): a layer starts with the tiles its predecessor
   // wrote LAST, which are still in the 126 MB L2 -- the activations of a big batch are larger than L2.
-  auto pair_of = [&](int t) -> int { const int pr = t / args.n_tiles; return args.reverse ? num_pairs - 1 - pr : pr; };
+  auto pair_of = [&](int t) -> int {
+    const int pr = args.n_tiles == 2 ? (t < mixed_whole ? t : mixed_whole + ((t - mixed_whole) >> 1)) : t / args.n_tiles;
+    return args.reverse ? num_pairs - 1 - pr : pr;
+  };
   const int k = args.ksize, pad = (k - 1) / 2, hw = 8 + k - 1;
   const int rb = args.row_bytes, kblk = rb >> 1;
   auto wg_col = [&](int t, int kc) -> int {   // K coordinate (elements) of chunk kc of work item t, see ConvArgs::wg_cpc
@@ -142,15 +153,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
     int stage = 0;
     uint32_t phase = 0;
     for (int t = pair0; t < num_work; t += n_pairs_grid) {
-      const int nt = wg ? 0 : t % args.n_tiles;
+      const int nt = wg ? 0 : item_nt(t);
+      const bool whole = !wg && item_whole(t);
+      const int rows = whole ? args.n : n_half;   // this CTA's half of the item's output channels
       for (int kc = 0; kc < args.kchunks; ++kc)
         for (int tap = 0; tap < k * k; ++tap) {
           ptx::mbar_wait(&b_empty[stage], phase ^ 1, args.err_flag, ERR2_PRODUCER_B);
           if (ptx::elect_one()) {
-            if (leader) ptx::mbar_expect_tx(&b_full[stage], 2 * b_bytes);   // both CTAs' halves
+            if (leader) ptx::mbar_expect_tx(&b_full[stage], 2u * static_cast<uint32_t>(rows) * rb);   // both CTAs' halves
             const int col = wg ? wg_col(t, kc) + wg_shift(t) : (tap * args.kchunks + kc) * kblk;
-            ptx::tma_load_2d_2cta(smem_b + stage * bstage_bytes, &tmap_w, ptx::mapa_u32(&b_full[stage], 0),
-                                  col, nt * args.n + static_cast<int>(rank) * n_half);
+            ptx::tma_load_2d_2cta(smem_b + stage * bstage_bytes, whole ? &tmap_w_whole : &tmap_w, ptx::mapa_u32(&b_full[stage], 0),
+                                  col, nt * args.n + static_cast<int>(rank) * rows);
           }
           __syncwarp();
           if (++stage == n_bstages) { stage = 0; phase ^= 1; }
@@ -184,7 +197,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (leader only) =====================
     if (leader) {
-      const uint32_t idesc = ptx::idesc_h16_f32(256, args.n, args.fp16);
+      const uint32_t idesc_item = ptx::idesc_h16_f32(256, args.n, args.fp16);
+      const uint32_t idesc_whole = mixed_whole > 0 ? ptx::idesc_h16_f32(256, 2 * args.n, args.fp16) : idesc_item;
       const uint64_t a_desc0 = tc::desc_sw(ptx::smem_u32(smem_a), hw * rb, rb);
       const uint64_t b_desc0 = tc::desc_sw(ptx::smem_u32(smem_b), 8 * rb, rb);
       const int tap_rows16 = rb >> 4;
@@ -194,6 +208,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1, args.err_flag, ERR2_MMA_ACC);
         ptx::tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * ACC_COLS;
+        const uint32_t idesc = (!wg && item_whole(t)) ? idesc_whole : idesc_item;
         for (int kc = 0; kc < args.kchunks; ++kc) {
           ptx::mbar_wait(&a_full[slot], a_phase, args.err_flag, ERR2_MMA_A);
           const uint64_t a_plane = a_desc0 + static_cast<uint64_t>((slot * plane_bytes) >> 4);
@@ -244,9 +259,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap_halo, const __grid_cons
       const int tile = 2 * pair_of(t) + static_cast<int>(rank);
       const int tn = t + n_pairs_grid;
       const int next_tile = tn < num_work ? 2 * pair_of(tn) + static_cast<int>(rank) : -1;
-      tc::epilogue_tile(args, smem_epi, s_bias, s_head, quad, lane, tile * 2,
+      ConvArgs ea = args;
+      if (item_whole(t)) ea.n = 2 * args.n;   // columns [0, 2 n) of the n_total wide rows, N tile 0
+      tc::epilogue_tile(ea, smem_epi, s_bias, s_head, quad, lane, tile * 2,
                         tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * ACC_COLS, &tmem_full[acc], acc_phase,
-                        &tmem_empty[acc], 0u /* the leader owns the accumulator-empty barrier */, t % args.n_tiles,
+                        &tmem_empty[acc], 0u /* the leader owns the accumulator-empty barrier */, item_nt(t),
                         next_tile >= 0 && next_tile < args.num_tiles ? next_tile * 2 : -1);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
