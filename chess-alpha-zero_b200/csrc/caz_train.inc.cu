@@ -62,6 +62,7 @@ struct caz_trainer {
   size_t grad_split = 0;
   bool capturing = false;
   bool profiling = false;
+  float* conv_stats = nullptr;   // tensor-core build: BatchNormalization partial sums written by the convolution epilogues
   bool mask_fp32 = false;   // CAZ_TRAIN_MASK_FP32: the backward passes read the ReLU mask from the fp32 activations
   bool no_tile = false;   // CAZ_TRAIN_NO_TILE: BatchNormalization passes and transposes as separate kernels (the fallback for odd shapes)
   std::vector<std::pair<const char*, cudaEvent_t>> prof;
@@ -171,13 +172,21 @@ bool tr_tile_path(const caz_trainer* t, const TrainConv& L) {
 
 // batch statistics of z (and the moving averages), then a = relu(BN(z) (+ skip))
 int tr_bn_forward(caz_trainer* t, TrainConv& L, const float* skip, int rows) {
-  const dim3 grid((L.cout + caz::train::STAT_CH - 1) / caz::train::STAT_CH, caz::train::STAT_SPLITS);
-  caz::train::channel_sums_kernel<<<grid, caz::train::STAT_THREADS, 0, t->stream>>>(0, L.z, nullptr, nullptr, nullptr, nullptr, nullptr, rows, L.cout, t->partial);
   int rc;
-  if ((rc = tr_launch_ok(t, "channel_sums_kernel"))) return rc;
-  caz::train::bn_finish_stats_kernel<<<(L.cout + 7) / 8, 256, 0, t->stream>>>(t->partial, rows, L.cout, t->arch.bn_epsilon, L.mean, L.invstd,
-                                                                                t->grads + L.mmean, t->grads + L.mvar);
-  if ((rc = tr_launch_ok(t, "bn_finish_stats_kernel"))) return rc;
+  if (t->conv_stats && L.a16) {
+    // tower layer of the tensor-core build: the convolution's epilogue has left the partial sums (ConvArgs::stats)
+    caz::train::bn_finish_stats_f32_kernel<<<(L.cout + 7) / 8, 256, 0, t->stream>>>(t->conv_stats, ((rows / 64 + 1) / 2) * 4, rows, L.cout,
+                                                                                      t->arch.bn_epsilon, L.mean, L.invstd, t->grads + L.mmean,
+                                                                                      t->grads + L.mvar);
+    if ((rc = tr_launch_ok(t, "bn_finish_stats_f32_kernel"))) return rc;
+  } else {
+    const dim3 grid((L.cout + caz::train::STAT_CH - 1) / caz::train::STAT_CH, caz::train::STAT_SPLITS);
+    caz::train::channel_sums_kernel<<<grid, caz::train::STAT_THREADS, 0, t->stream>>>(0, L.z, nullptr, nullptr, nullptr, nullptr, nullptr, rows, L.cout, t->partial);
+    if ((rc = tr_launch_ok(t, "channel_sums_kernel"))) return rc;
+    caz::train::bn_finish_stats_kernel<<<(L.cout + 7) / 8, 256, 0, t->stream>>>(t->partial, rows, L.cout, t->arch.bn_epsilon, L.mean, L.invstd,
+                                                                                  t->grads + L.mmean, t->grads + L.mvar);
+    if ((rc = tr_launch_ok(t, "bn_finish_stats_kernel"))) return rc;
+  }
   const size_t total = static_cast<size_t>(rows) * L.cout;
   const int vec4 = (L.cout & 3) == 0 && (L.gamma & 3) == 0 && (L.beta & 3) == 0;   // float4 slices of the parameter vectors
   if (tr_tile_path(t, L)) {
@@ -282,7 +291,7 @@ int tr_launch_tc(caz_trainer* t, const CUtensorMap& tm_a, const CUtensorMap& tm_
 
 // out[rows][n] = conv(in16, w16): "same" convolution as an implicit GEMM on the tensor cores, raw fp32 row-major output
 int tr_conv_tc(caz_trainer* t, const CUtensorMap& tm_in, const CUtensorMap& tm_w, const CUtensorMap& tm_w_half, int ksize, int row_bytes,
-               int kchunks, int n, int fmt, float* out, int batch) {
+               int kchunks, int n, int fmt, float* out, int batch, bool stats = false) {
   caz::tc::ConvArgs args{};
   args.batch = batch;
   args.num_tiles = (batch + 1) / 2;
@@ -296,6 +305,10 @@ int tr_conv_tc(caz_trainer* t, const CUtensorMap& tm_in, const CUtensorMap& tm_w
   args.n_total = n;
   args.m_rows = batch * 64;
   args.out_rm = out;
+  if (stats) {   // per-channel sum and sum of squares of the output, per epilogue warp (ConvArgs::stats)
+    args.stats = t->conv_stats;
+    args.stats_slots = args.num_tiles * 4;
+  }
   // Two N tiles of n / 2 channels per board group when that fills the last wave better: batch 384 = 96 groups on 74 CTA pairs
   // is two waves of whole tiles but 2.6 waves of half tiles (= 1.3 tile times)
   // ... or MIXED: whole tiles for as many full rounds as the groups fill, half tiles for the rest (ConvArgs::mixed_whole).
@@ -400,8 +413,8 @@ int tr_forward_backward(caz_trainer* t, int batch) {
     const float* in = l == 0 ? t->x0 : t->convs[l - 1].a;
     if (t->tc) {
       const int fmt = caz::ptx::FMT_A_FP16 | caz::ptx::FMT_B_FP16;
-      if (l == 0) rc = tr_conv_tc(t, t->tm_x0, L.tm_wf, L.tm_wf_h, L.k, 64, 1, L.cout, fmt, L.z, batch);
-      else rc = tr_conv_tc(t, t->convs[l - 1].tm_a16, L.tm_wf, L.tm_wf_h, L.k, 128, L.cin / 64, L.cout, fmt, L.z, batch);
+      if (l == 0) rc = tr_conv_tc(t, t->tm_x0, L.tm_wf, L.tm_wf_h, L.k, 64, 1, L.cout, fmt, L.z, batch, t->conv_stats != nullptr);
+      else rc = tr_conv_tc(t, t->convs[l - 1].tm_a16, L.tm_wf, L.tm_wf_h, L.k, 128, L.cin / 64, L.cout, fmt, L.z, batch, t->conv_stats != nullptr);
       if (rc) return rc;
     } else if ((rc = tr_conv_fp32(t, in, P + L.w, nullptr, L.z, batch, L.k, L.cin, L.cout))) return rc;
     const bool conv2 = l > 0 && (l & 1) == 0;
@@ -496,7 +509,7 @@ void caz_train_destroy(caz_trainer* t) {
   if (t->stream) cudaStreamSynchronize(t->stream);
   std::vector<void*> ptrs = {t->params, t->adam_m, t->adam_v, t->seg, t->x0, t->planes, t->policy_t, t->value_t, t->featp, t->logits, t->dlogits,
                              t->probs, t->featv, t->hid, t->vpre, t->vout, t->dvpre, t->dhid, t->dfeatp, t->dfeatv, t->d_a, t->d_b, t->d_skip, t->dz,
-                             t->dzp, t->dzv, t->dap, t->dav, t->w_flip, t->zero_bias, t->partial, t->loss_acc, t->gemm_partial};
+                             t->dzp, t->dzv, t->dap, t->dav, t->w_flip, t->zero_bias, t->partial, t->loss_acc, t->gemm_partial, t->conv_stats};
   if (!t->grads_external) ptrs.push_back(t->grads);
   for (void* p : {(void*)t->x0_16, (void*)t->dz16, (void*)t->dzT, (void*)t->aT, (void*)t->dzT_stem, (void*)t->x0T, (void*)t->wg_partial}) ptrs.push_back(p);
   auto free_conv = [&](TrainConv& L) {
@@ -709,6 +722,7 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
     const size_t k3 = (size_t)pitch3 * pitch3 * t->nb, ks = (size_t)pitch_s * pitch_s * t->nb;
     TC2(tr_alloc(t, &t->dzT, F * k3));
     TC2(tr_alloc(t, &t->aT, F * k3));
+    if (!getenv("CAZ_TRAIN_NO_CONV_STATS")) TC2(tr_alloc(t, &t->conv_stats, (size_t)2 * F * ((boards + 1) / 2) * 4));
     if (getenv("CAZ_TRAIN_NO_TILE")) t->no_tile = true;
     if (getenv("CAZ_TRAIN_MASK_FP32")) t->mask_fp32 = true;
     for (size_t l = 0; l + 1 < t->convs.size() && !t->no_tile; ++l) {   // inputs of the tower's weight-gradient GEMMs

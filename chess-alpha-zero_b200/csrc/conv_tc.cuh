@@ -99,6 +99,12 @@ struct ConvArgs {
   // 100 for a 3x3 kernel, 80 of 144 for 5x5) need neither loading nor multiplying
   int wg_cpc;
   int mixed_whole;          // CTA-pair kernel, n_tiles == 2: this many leading work items take both N tiles at once (conv_tc2.cuh)
+  // Training (BatchNormalization batch statistics out of the convolution's epilogue, with out_rm): nullptr, or
+  // [2][n_total][stats_slots] floats -- every epilogue warp leaves the sum and the sum of squares of its 32 rows of each of
+  // its output columns in slot (CTA tile * 4 + warp); rows beyond the batch are zero and add nothing (zero bias).  Each
+  // (column, slot) is written exactly once per launch; bn_finish_stats_f32_kernel adds the slots in a fixed order.
+  float* stats;
+  int stats_slots;
   int* err_flag;
 };
 
@@ -246,6 +252,19 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
       for (int q = 0; q < 8; ++q)
         stage_f[lane * 8 + (q ^ (lane & 7))] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
       __syncwarp();
+      if (args.stats && tile * 4 + quad < args.stats_slots) {   // column c0 + lane of this warp's 32 rows (a CTA tile past the batch has no slot)
+        const float* sf = reinterpret_cast<const float*>(stage_f);
+        float s = 0.0f, q2 = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const float x = sf[(r * 8 + ((lane >> 2) ^ (r & 7))) * 4 + (lane & 3)];
+          s += x;
+          q2 = fmaf(x, x, q2);
+        }
+        const size_t at = static_cast<size_t>(nt * args.n + c0 + lane) * args.stats_slots + tile * 4 + quad;
+        args.stats[at] = s;
+        args.stats[static_cast<size_t>(args.n_total) * args.stats_slots + at] = q2;
+      }
       const int col = nt * args.n + c0 + fq * 4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {

@@ -139,6 +139,29 @@ __global__ void bn_finish_stats_kernel(const double* __restrict__ partial, int r
   batch_var_out[ch] = static_cast<float>(var);
 }
 
+// The same from the partial sums the tensor-core convolution's epilogue left (ConvArgs::stats: [2][c][slots] floats, one slot
+// per epilogue warp and CTA tile): one warp per channel, double accumulation, fixed order.
+__global__ void bn_finish_stats_f32_kernel(const float* __restrict__ partial, int slots, int rows, int c, float eps,
+                                           float* __restrict__ mean, float* __restrict__ invstd,
+                                           float* __restrict__ batch_mean_out, float* __restrict__ batch_var_out) {
+  const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (ch >= c) return;
+  const float* p0 = partial + static_cast<size_t>(ch) * slots;
+  const float* p1 = partial + (static_cast<size_t>(c) + ch) * slots;
+  double s0 = 0.0, s1 = 0.0;
+  for (int k = lane; k < slots; k += 32) { s0 += p0[k]; s1 += p1[k]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  if (lane != 0) return;
+  const double mu = s0 / rows;
+  double var = s1 / rows - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[ch] = static_cast<float>(mu);
+  invstd[ch] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  batch_mean_out[ch] = static_cast<float>(mu);
+  batch_var_out[ch] = static_cast<float>(var);
+}
+
 // a = relu(gamma * (z - mean) * invstd + beta (+ skip));  optional 16-bit NHWC copy for the tensor-core convolutions
 template <typename H>
 __global__ void bn_apply_kernel(const float* __restrict__ z, const float* __restrict__ skip, const float* __restrict__ gamma,
