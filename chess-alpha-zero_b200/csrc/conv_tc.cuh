@@ -101,7 +101,7 @@ struct ConvArgs {
   int mixed_whole;          // CTA-pair kernel, n_tiles == 2: this many leading work items take both N tiles at once (conv_tc2.cuh)
   // Training (BatchNormalization batch statistics out of the convolution's epilogue, with out_rm): nullptr, or
   // [2][n_total][stats_slots] floats -- every epilogue warp leaves the sum and the sum of squares of its 32 rows of each of
-  // its output columns in slot (CTA tile * 4 + warp); rows beyond the batch are zero and add nothing (zero bias).  Each
+  // its output columns in slot (CTA tile * 4 + warp); rows of boards beyond the batch are left out.  Each
   // (column, slot) is written exactly once per launch; bn_finish_stats_f32_kernel adds the slots in a fixed order.
   float* stats;
   int stats_slots;
@@ -257,7 +257,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
         float s = 0.0f, q2 = 0.0f;
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
-          const float x = sf[(r * 8 + ((lane >> 2) ^ (r & 7))) * 4 + (lane & 3)];
+          // (a board past the batch reads whatever an earlier, larger batch left in the operand buffer: not part of the sums)
+          const float x = live(r) ? sf[(r * 8 + ((lane >> 2) ^ (r & 7))) * 4 + (lane & 3)] : 0.0f;
           s += x;
           q2 = fmaf(x, x, q2);
         }

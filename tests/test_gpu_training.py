@@ -334,3 +334,30 @@ def test_trainer_rejects_bad_calls():
         caz.Trainer(cfg, w, precision="fp8")
     tr.close()
     tr.close()                                                         # idempotent
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_a_short_odd_batch_after_a_long_one(precision):
+    """Model.fit's last batch of an epoch is short: a step at batch 5 on a trainer that has just run batch 12 must equal the
+    same step on a fresh trainer bit for bit (tensor-core build; the fp32 build to float rounding of its atomic weight-gradient
+    sums) -- nothing may be read from what the longer batch left in the buffers (operand rows of boards past the batch,
+    K-major operands, statistics slots)."""
+    cfg = oweights.keras_config(filters=64, blocks=2)
+    w = oweights.synth_weights(cfg, seed=3, recipe="keras_default")
+    x, pt, vt = _data(12, seed=11)
+    used = caz.Trainer(cfg, w, precision=precision, max_batch=12)
+    used.forward_backward(x, pt, vt)                                   # fills every buffer with 12 boards, no update
+    got_l = used.forward_backward(x[:5], pt[:5], vt[:5])
+    got = used.gradients()
+    used.close()
+    fresh = caz.Trainer(cfg, w, precision=precision, max_batch=12)
+    want_l = fresh.forward_backward(x[:5], pt[:5], vt[:5])
+    want = fresh.gradients()
+    fresh.close()
+    if precision == "bf16":
+        assert got_l == want_l
+        for k in want:
+            assert np.array_equal(got[k], want[k]), k
+    else:
+        assert all(abs(got_l[k] - want_l[k]) <= 1e-6 * abs(want_l[k]) + 1e-9 for k in want_l)
+        assert max(_rel(got[k], want[k]) for k in want) <= 1e-5
