@@ -107,7 +107,7 @@ struct caz_handle {
   bool sb_ok = false;        // architecture fits it
   int sb_limit = -1;         // batches <= this use it; -1 = automatic
   CUtensorMap sb_tm_xb[2], sb_tm_y[2];  // halo views for 1 and 2 boards per CTA tile
-  CUtensorMap sb_tm_w_stem[3], sb_tm_w_tower[3];      // weight maps for N_s = 16, 32, 64
+  CUtensorMap sb_tm_w_stem[4], sb_tm_w_tower[4];      // weight maps for N_s = 16, 32, 64, 128
   int sb_force_nb = 0;
   unsigned char* sb_sm_near = nullptr;   // [smid] -> which flag-line class (copy) is the near one, 0xFF unknown
   unsigned* sb_counter = nullptr;   // progress flags of the small-batch kernel: 32 candidate grains of 4 KB
@@ -683,7 +683,7 @@ int setup_small_batch(caz_handle* h) {
   }
   if (const char* e = getenv("CAZ_SB_BOARDS")) h->sb_force_nb = atoi(e);
   const int F = a.filters;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const cuuint32_t ns = 16u << i;
     if (ns > (cuuint32_t)F) { h->sb_tm_w_stem[i] = h->sb_tm_w_stem[0]; h->sb_tm_w_tower[i] = h->sb_tm_w_tower[0]; continue; }
     const cuuint64_t kst = (cuuint64_t)a.stem_kernel * a.stem_kernel * 64;
@@ -709,6 +709,7 @@ int setup_small_batch(caz_handle* h) {
   CU_TRY(h, cudaMemset(h->sb_trace, 0, (1024 + 16 * 256 * 2) * sizeof(long long)));
   CU_TRY(h, cudaFuncSetAttribute(caz::sb::forward_sb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::sb::SMEM_BYTES));
   CU_TRY(h, cudaFuncSetAttribute(caz::sb::forward_sb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::sb::SMEM_BYTES));
+  CU_TRY(h, cudaFuncSetAttribute(caz::sb::forward_sb_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, caz::sb::SMEM_BYTES));
   h->sb_ok = true;
   return CAZ_OK;
 }
@@ -740,9 +741,9 @@ bool sb_geometry(const caz_handle* h, int batch, int* nb_out, int* slices_out, i
     for (int nb = 1; nb <= 2; ++nb) {
       if (h->sb_force_nb && nb != h->sb_force_nb) continue;
       const int tiles = (batch + nb - 1) / nb;
-      for (int s = 16; s >= 4; s >>= 1) {
+      for (int s = 16; s >= 2; s >>= 1) {   // (two 128-channel slices of two-board tiles: 73-148 boards)
         const int ns = h->arch.filters / s;
-        if (ns < 16 || ns > 64 || h->arch.filters % s != 0 || tiles * s > h->num_sms) continue;
+        if (ns < 16 || ns > 128 || h->arch.filters % s != 0 || tiles * s > h->num_sms) continue;
         if (!caz::sb::heads_fit(h->arch.policy_filters, h->arch.value_filters, h->arch.n_labels, h->arch.value_fc, s)) continue;
         // first pass: one board per tile (M = 64: the tensor pipe is bound by operand reads from shared memory,
         // (M + N) * 32 B per MMA, tools/ub/ub_small.cu) as long as that leaves slices of at most 32 channels
@@ -755,8 +756,12 @@ bool sb_geometry(const caz_handle* h, int batch, int* nb_out, int* slices_out, i
   return false;
 }
 
+// Batches up to here take the persistent small-batch kernel unless told otherwise: 37 two-board tiles x 4 slices of 64 channels
+// = 148 CTAs.  (caz_set_small_batch_limit(h, 148) extends it to two 128-channel slices per tile: measured 281 us at 128 boards,
+// no better than the one-launch tower -- 15.3 us per layer, of which 5 us epilogue over 128 channels per thread -- so not automatic.)
+constexpr int SB_AUTO_LIMIT = 74;
 bool use_small_batch(const caz_handle* h, int batch) {
-  const int limit = h->sb_limit < 0 ? caz::sb::MAX_BATCH : h->sb_limit;
+  const int limit = h->sb_limit < 0 ? SB_AUTO_LIMIT : h->sb_limit;
   int nb, sl;
   return batch <= limit && batch <= caz::sb::MAX_BATCH && sb_geometry(h, batch, &nb, &sl);
 }
@@ -769,7 +774,7 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
   sb_geometry(h, batch, &nb, &slices, &pair);
   const int ns = a.filters / slices;
   const int ns_cta = pair ? ns / 2 : ns;   // weight rows one CTA stages
-  const int wi = ns_cta == 16 ? 0 : (ns_cta == 32 ? 1 : 2);
+  const int wi = ns_cta == 16 ? 0 : (ns_cta == 32 ? 1 : (ns_cta == 64 ? 2 : 3));
   caz::sb::Args args;
   args.batch = batch;
   args.nb = nb;
@@ -851,8 +856,10 @@ int launch_forward_small(caz_handle* h, const float* d_planes, const uint8_t* d_
     attrs[0] = attrs[1];
     cfg.numAttrs = 1;
   }
-  cudaError_t e = cudaLaunchKernelExC(&cfg, pair ? reinterpret_cast<const void*>(caz::sb::forward_sb_kernel<true>)
-                                                 : reinterpret_cast<const void*>(caz::sb::forward_sb_kernel<false>), params);
+  const void* kernel = pair ? reinterpret_cast<const void*>(caz::sb::forward_sb_kernel<true>)
+                            : (ns_cta > 64 ? reinterpret_cast<const void*>(caz::sb::forward_sb_kernel<false, 8>)
+                                           : reinterpret_cast<const void*>(caz::sb::forward_sb_kernel<false>));
+  cudaError_t e = cudaLaunchKernelExC(&cfg, kernel, params);
   if (e != cudaSuccess) return fail(h, CAZ_ERR_CUDA, fmt("cooperative launch of forward_sb_kernel failed: %s", cudaGetErrorString(e)));
   h->launches++;
   return CAZ_OK;

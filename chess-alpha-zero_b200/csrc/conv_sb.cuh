@@ -45,14 +45,14 @@ constexpr int NACC = 4;   // accumulator groups in TMEM: one per K sub-step of a
 constexpr int BAR_BYTES = 1024;
 constexpr int SMEM_BYTES = A_BYTES + W_RING_BYTES + BAR_BYTES + 1024 /*alignment*/;
 constexpr int HEAD_SMEM_BYTES = A_BYTES + W_RING_BYTES;        // what the head phases may use for staged weights
-constexpr int MAX_BATCH = 72;   // 36 CTA pairs x 2 slices of 128 channels = 144 CTAs
-constexpr int MAX_TILES = 72;   // board tiles per launch (one flag line each)
+constexpr int MAX_BATCH = 148;  // 74 two-board tiles x 2 slices of 128 channels = 148 CTAs (up to 72 boards: 36 CTA pairs x 2 slices x 2)
+constexpr int MAX_TILES = 74;   // board tiles per launch (one flag line each)
 
 struct Args {
   int batch;        // positions (<= MAX_BATCH)
   int n_layers;     // 1 + 2 * res_blocks
   int nb;           // boards per CTA tile: 2 (M = 128) or 1 (M = 64: half the A-operand bytes per MMA)
-  int ns;           // output channels per slice (16, 32 or 64)
+  int ns;           // output channels per slice (16, 32, 64 or 128)
   int pair;         // 1: the two CTAs of a cluster share a slice (cta_group::2, M = 128: one board each, half of the
                     //    slice's weights each); needs nb = 1 and ns >= 32
   int n_slices;     // filters / ns
@@ -273,7 +273,9 @@ __device__ __forceinline__ void issue_taps(uint64_t a_plane, uint64_t b_slot, in
   }
 }
 
-template <bool PAIR>
+// RES: 16-channel chunks of the slice a thread's epilogue carries (4: slices up to 64 channels per CTA; 8: the 128-channel
+// slices of 73-148 boards -- a separate instantiation, so that the latency-critical small forms keep their register budget)
+template <bool PAIR, int RES = 4>
 __global__ void __launch_bounds__(THREADS, 1)
 forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
                   const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_w_stem,
@@ -641,9 +643,9 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       s_hw[i] = (f6 < hf_all && j < args.ns) ? args.head_w[f6 * args.filters + col0 + j] : 0.0f;
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    float res[4][16];   // fp32 residual stream: this thread's row, this CTA's channels (up to 64)
+    float res[RES][16];   // fp32 residual stream: this thread's row, this CTA's channels (up to 16 RES)
 #pragma unroll
-    for (int ci = 0; ci < 4; ++ci)
+    for (int ci = 0; ci < RES; ++ci)
 #pragma unroll
       for (int j = 0; j < 16; ++j) res[ci][j] = 0.0f;
     for (int l = 0; l < args.n_layers; ++l) {
@@ -653,7 +655,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
       const bool two_issuers = (l == 0 ? args.stem_kchunks : args.filters / 64) > 1;
       const float* bias = args.bias_all + static_cast<size_t>(l) * args.filters + col0 + cb;
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
+      for (int ci = 0; ci < RES; ++ci) {
         const int c0 = ci * 16;
         if (c0 >= ns_cta) break;
         // bias is fetched BEFORE the wait; the fp32 residual stream of this row and these channels never leaves the

@@ -203,8 +203,9 @@ int64_t caz_inexact_weights(const caz_handle* h); /* bf16 build: folded bf16 wei
 
 /* Batches of at most `limit` positions run the persistent small-batch tower kernel (one cooperative launch for
  * stem + all residual convs, weights streamed from L2); larger ones run one implicit-GEMM launch per layer.
- * limit < 0 restores the automatic choice, 0 disables the small-batch kernel.  Results are identical either way
- * up to fp32 summation order inside the MMA. */
+ * limit < 0 restores the automatic choice (74 positions), 0 disables the small-batch kernel; the kernel itself goes up
+ * to 148 positions (limits above that are clamped).  Results are identical either way up to fp32 summation order inside
+ * the MMA. */
 int caz_set_small_batch_limit(caz_handle* h, int32_t limit);
 
 /* Batches beyond the small-batch kernel run stem + tower + head convolutions as ONE persistent launch in which every

@@ -338,10 +338,22 @@ def test_small_batch_persistent_kernel(net_default):
     for batch in (1, 2, 3, 15, 16, 17, 32, 33, 36, 37, 48):
         p, v = ev.predict_on_batch(x[:batch])
         assert np.array_equal(p, ref_p[:batch]) and np.array_equal(v, ref_v[:batch]), batch
-    for batch in (65, 72):   # the largest grids of the persistent kernel: 36 CTA pairs x 2 slices
+    for batch in (65, 72, 73, 74):   # the largest grids: 36 CTA pairs x 2 slices, then 37 two-board tiles x 4 slices = 148 CTAs
+        l0 = ev.kernel_launches
         p, v = ev.predict_on_batch(x[:batch])
+        assert ev.kernel_launches - l0 == 1, batch
         assert np.array_equal(p[:64], ref_p) and np.array_equal(v[:64], ref_v), batch
         assert np.abs(p - wp[:batch]).max() <= BF16_TOL and np.abs(v - wv[:batch]).max() <= BF16_TOL
+    # on request (caz_set_small_batch_limit) up to 148 boards: two-board tiles x two 128-channel slices, the instantiation
+    # whose epilogue threads carry 128 channels; same arithmetic, same bits
+    ev.set_small_batch_limit(148)
+    for batch in (75, 100, 147, 148):
+        l0 = ev.kernel_launches
+        p, v = ev.predict_on_batch(x[:batch])
+        assert ev.kernel_launches - l0 == 1, batch
+        assert np.array_equal(p[:64], ref_p) and np.array_equal(v[:64], ref_v), batch
+        assert np.abs(p - wp[:batch]).max() <= BF16_TOL and np.abs(v - wv[:batch]).max() <= BF16_TOL
+    ev.set_small_batch_limit(-1)
     # against the per-layer kernels: same arithmetic up to fp32 summation order, so bf16-noise level agreement
     ev.set_small_batch_limit(0)
     big_p, big_v = ev.predict_on_batch(x[:64])

@@ -9,9 +9,10 @@ import chess_alpha_zero_b200 as caz
 from chess_alpha_zero_b200 import _lib
 b = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 cfg, weights = bench.network(7)
-ev = caz.Evaluator(cfg, weights, precision="bf16", max_batch=64)
-planes = bench.synthetic_batch(64, seed=3, ev=ev)
-d_x = torch.from_numpy(planes).cuda(); d_p = torch.empty((64, 1968), device="cuda"); d_v = torch.empty((64,), device="cuda")
+ev = caz.Evaluator(cfg, weights, precision="bf16", max_batch=160)
+ev.set_small_batch_limit(int(os.environ.get("SB_LIMIT", "-1")))   # 148: the two-slice form of 73-148 boards
+planes = bench.synthetic_batch(160, seed=3, ev=ev)
+d_x = torch.from_numpy(planes).cuda(); d_p = torch.empty((160, 1968), device="cuda"); d_v = torch.empty((160,), device="cuda")
 for _ in range(5): ev.eval_device(d_x.data_ptr(), b, d_p.data_ptr(), d_v.data_ptr())
 lib = _lib.load()
 _lib.check(ev._handle, lib.caz_debug_sb_trace(ev._handle, 1, None, 0))
