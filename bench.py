@@ -317,6 +317,18 @@ def latency_probe(ev, planes16, calls=1000):
         t0 = time.perf_counter()
         ev.predict_into(pin_x.array, pin_p.array, pin_v.array)
         host.append(time.perf_counter() - t0)
+    # the same call from 68-byte board records, the form the batched search submits (the encoder runs inside the kernel, which
+    # reads the records straight from the pinned buffer)
+    from chess_alpha_zero_b200 import encoder
+    pin_r = _lib.PinnedArray((16, _lib.RECORD_BYTES), np.uint8)
+    pin_r.array[:] = encoder.fens_to_records(encoder.synthetic_fens(16, seed=3))
+    for _ in range(50):
+        ev.predict_records_into(pin_r.array, pin_p.array, pin_v.array)
+    host_rec = []
+    for _ in range(calls):
+        t0 = time.perf_counter()
+        ev.predict_records_into(pin_r.array, pin_p.array, pin_v.array)
+        host_rec.append(time.perf_counter() - t0)
     stream = torch.cuda.ExternalStream(ev.stream)
     d_x = torch.from_numpy(planes16).cuda()
     d_p = torch.empty((16, 1968), dtype=torch.float32, device="cuda")
@@ -342,9 +354,11 @@ def latency_probe(ev, planes16, calls=1000):
     ev.profile(False)
     q = lambda a, f: float(np.quantile(np.asarray(a), f) * 1e6)
     return {"batch": 16, "calls": calls, "host_call_p50_us": q(host, 0.5), "host_call_p99_us": q(host, 0.99),
+            "host_call_records_p50_us": q(host_rec, 0.5), "host_call_records_p99_us": q(host_rec, 0.99),
             "device_p50_us": q(lib_dev, 0.5), "device_p99_us": q(lib_dev, 0.99),
             "device_incl_python_launch_p50_us": q(dev, 0.5), "device_incl_python_launch_p99_us": q(dev, 0.99),
-            "note": "host call = predict_on_batch-equivalent with pinned buffers incl. H2D+D2H+sync; pipe round trips excluded; "
+            "note": "host call = predict_on_batch-equivalent with pinned buffers incl. H2D+D2H+sync; host_call_records = the same from "
+                    "68-byte board records (caz_eval_records, no input copy); pipe round trips excluded; "
                     "device = CUDA events recorded by the library around its launch (launch overhead included)"}
 
 
