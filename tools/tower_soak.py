@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Soak test of the one-launch tower (conv_tower.cuh): random batch sizes 73..700 back to back through the device-resident
+"""Soak test of the one-launch tower (conv_tower.cuh): random batch sizes 75..700 back to back through the device-resident
 entry point, mixed with small-batch launches, every result compared bit for bit with the per-layer chain's answer for that
 batch.  A missed act_ready arrival, a stale scratch tile or a ring bug shows up as a mismatch or as CAZ_ERR_KERNEL.
     python tools/tower_soak.py [seconds]"""
@@ -18,7 +18,7 @@ seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 30.0
 cfg, weights = bench.network(7)
 ev = caz.Evaluator(cfg, weights, precision="bf16", max_batch=704)
 x = bench.synthetic_batch(704, seed=3, ev=ev)
-sizes = [73, 74, 100, 148, 149, 255, 256, 295, 296, 297, 300, 511, 592, 593, 700]
+sizes = [75, 76, 100, 148, 149, 255, 256, 295, 296, 297, 300, 511, 592, 593, 700]   # (up to 74 boards the persistent small-batch kernel runs)
 ev.set_fused_tower(0)
 want = {b: ev.predict_on_batch(x[:b]) for b in sizes}
 ev.set_fused_tower(-1)
