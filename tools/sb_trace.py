@@ -35,3 +35,4 @@ cyc = st[16, 2] - st[15, 0]; ns = st[16, 1] - st[16, 0]
 print(f"CTA 0 lifetime: {cyc:.0f} cycles in {ns / 1e3:.2f} us (globaltimer) -> SM clock {cyc / ns * 1e3:.0f} MHz; the table assumes 1965 MHz")
 for l in (0, 1, 2, 3, 13, 14):
     print(f"{l:5d} " + " ".join(f"{us[l, i]:9.2f}" for i in range(7)) + f"   last A plane landed {us[l, 7]:6.2f}")
+
