@@ -84,6 +84,7 @@ struct caz_handle {
   bool sb_no_pairs = false;      // CAZ_SB_NO_PAIRS
   bool no_direct_output = false; // CAZ_NO_DIRECT_OUTPUT
   int sb_dbg = 0;                // CAZ_SB_DBG
+  bool tw_all_lanes_fence = false;   // CAZ_TOWER_ALL_LANES_FENCE
   int dbg_epi = 0;               // CAZ_DBG_EPI (only with -DCAZ_TIMING_EXPERIMENTS)
   // weight slabs the layers point into: the tower's layers are contiguous so that one tensor map covers them
   void* w_stem = nullptr;
@@ -958,6 +959,7 @@ int launch_tower(caz_handle* h, int batch) {
   // (Cutting every layer of a lone group into two N tiles, first half drained and consumed while the second is computed,
   // was built and measured in round 2: bit-identical, and not a microsecond faster -- 283.6 vs 286.1 us at 100 boards.)
   args.interleave = h->tw_mode ? h->tw_mode : (groups > max_pairs ? 2 : 1);
+  args.all_lanes_fence = h->tw_all_lanes_fence ? 1 : 0;
   const int supers = (groups + args.interleave - 1) / args.interleave;
   const int pairs = supers < max_pairs ? supers : max_pairs;
   cudaLaunchConfig_t cfg = {};
@@ -1366,6 +1368,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
     h->sb_no_pairs = getenv("CAZ_SB_NO_PAIRS") != nullptr;
     h->no_direct_output = getenv("CAZ_NO_DIRECT_OUTPUT") != nullptr;
     if (const char* e = getenv("CAZ_SB_DBG")) h->sb_dbg = atoi(e);
+    if (getenv("CAZ_TOWER_ALL_LANES_FENCE")) h->tw_all_lanes_fence = true;
     if (const char* e = getenv("CAZ_DBG_EPI")) h->dbg_epi = atoi(e);
   } else {
     const size_t s3 = (size_t)(8 + a.block_kernel - 1) * (8 + a.block_kernel - 1) * a.filters * 4;

@@ -105,6 +105,7 @@ struct ConvArgs {
   // (column, slot) is written exactly once per launch; bn_finish_stats_f32_kernel adds the slots in a fixed order.
   float* stats;
   int stats_slots;
+  int all_lanes_fence;      // one-launch tower, A/B switch (CAZ_TOWER_ALL_LANES_FENCE): every lane fences before a readiness arrive
   int* err_flag;
 };
 
@@ -303,10 +304,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint8_t* sme
     }
     if (chunk_ready && ((c0 + 32) & 63) == 0) {
       // channels [c0 - 32, c0 + 32) of this warp's rows are stored: visible to the TMA reads of the same CTA (async proxy)
-      __threadfence();
-      ptx::fence_proxy_async_all();
+      // (one gpu-scope fence by the arriving lane, cumulative over the warp's stores through __syncwarp -- the TMA reads them
+      // from L2; every lane fencing twice cost 0.85 us per fence point instead of 0.3, measured in conv_sb.cuh)
+      if (args.all_lanes_fence) { __threadfence(); ptx::fence_proxy_async_all(); }
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&chunk_ready[c0 >> 6]);
+      if (lane == 0) {
+        if (!args.all_lanes_fence) ptx::fence_acq_rel_gpu();
+        ptx::mbar_arrive(&chunk_ready[c0 >> 6]);
+      }
     }
   }
   if (args.head_w && live(lane)) {

@@ -53,6 +53,7 @@ struct TowerArgs {
   int n;                 // filters (= output channels of every layer), multiple of 64, <= 256
   int fmt;               // operand formats (ptx::FMT_*)
   int pdl;               // launched with programmatic stream serialization: wait for the previous grid before the first read
+  int all_lanes_fence;   // A/B switch (CAZ_TOWER_ALL_LANES_FENCE): the epilogue's readiness arrives behind two fences of every lane
   int interleave;        // groups per super-group: 2 (the groups alternate layer by layer: epilogue under the other group's
                          // MMAs) or 1 (few boards: every group gets its own CTA pair, the epilogue is exposed)
   const float* bias_all; // [n_layers][n] folded BatchNorm shifts
@@ -300,6 +301,7 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
     ca.out_rm = nullptr;
     ca.l2_prefetch = 0;
     ca.err_flag = args.err_flag;
+    ca.all_lanes_fence = args.all_lanes_fence;
     for (int s = pair0; s < num_super; s += n_pairs_grid) {
       const int ng = groups_in(s);
       for (int l = 0; l < L; ++l) {
@@ -329,10 +331,12 @@ tower_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant_
           if (tr) args.trace[l * 8 + 5] = clock64();
           if (!last && !fine) {
             // what this warp stored must be visible to the TMA reads of the group's next layer (same CTA, async proxy)
-            __threadfence();
-            ptx::fence_proxy_async_all();
+            if (args.all_lanes_fence) { __threadfence(); ptx::fence_proxy_async_all(); }
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&act_ready[g * 4]);
+            if (lane == 0) {
+              if (!args.all_lanes_fence) ptx::fence_acq_rel_gpu();   // cumulative over the warp's stores (see conv_tc.cuh)
+              ptx::mbar_arrive(&act_ready[g * 4]);
+            }
           }
           if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
