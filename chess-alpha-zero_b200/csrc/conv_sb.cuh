@@ -944,9 +944,10 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
         args.hstats[static_cast<size_t>(b) * HSTAT_FLOATS + 2 * LABEL_UNITS_MAX + grp] = pv;
     }
   }
-  __threadfence();
+  if (args.dbg & 4) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (!(args.dbg & 4)) ptx::fence_acq_rel_gpu();   // one cumulative fence behind the barrier (see the tower's release)
     publish(args, tile, slice, args.base + 1u + L);
     wait_tile(args, tile_flags, args.base + 1u + L);
     if (hshare) wait_tile(args, peer_flags, args.base + 1u + L);
