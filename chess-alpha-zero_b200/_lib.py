@@ -5,6 +5,7 @@ point raises -- there is no CPU fallback and nothing here imports ``oracle``.
 """
 import ctypes
 import os
+import weakref
 
 import numpy as np
 
@@ -121,8 +122,24 @@ def check(handle, rc):
         raise CazError(rc, msg.decode("utf-8", "replace") if msg else "unknown")
 
 
+_PTR_CACHE = {}
+
+
 def ptr(a):
-    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+    """c_void_p of an array's data.  ndarray.ctypes builds a helper object on every access (~1 us, four of them per call on
+    the latency path): the pointer of an array that does not own its memory -- a PinnedArray view, which cannot be resized in
+    place -- is remembered by object identity (checked through a weak reference)."""
+    if a is None:
+        return None
+    hit = _PTR_CACHE.get(id(a))
+    if hit is not None and hit[0]() is a:
+        return hit[1]
+    p = ctypes.c_void_p(a.ctypes.data)
+    if not a.flags.owndata:
+        if len(_PTR_CACHE) >= 64:
+            _PTR_CACHE.clear()
+        _PTR_CACHE[id(a)] = (weakref.ref(a), p)
+    return p
 
 
 def as_array(a, dtype, shape=None):

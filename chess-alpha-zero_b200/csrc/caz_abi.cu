@@ -85,6 +85,9 @@ struct caz_handle {
   bool no_direct_output = false; // CAZ_NO_DIRECT_OUTPUT
   int sb_dbg = 0;                // CAZ_SB_DBG
   bool tw_all_lanes_fence = false;   // CAZ_TOWER_ALL_LANES_FENCE
+  bool host_timing = false;          // CAZ_HOST_TIMING
+  double ht_sum[3] = {0, 0, 0};
+  long ht_calls = 0;
   int dbg_epi = 0;               // CAZ_DBG_EPI (only with -DCAZ_TIMING_EXPERIMENTS)
   // weight slabs the layers point into: the tower's layers are contiguous so that one tensor map covers them
   void* w_stem = nullptr;
@@ -1229,6 +1232,9 @@ void caz_destroy(caz_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->host_timing && h->ht_calls > 0)
+    fprintf(stderr, "caz host timing over %ld synchronous calls: before the launch %.2f us, launch %.2f us, copies back + synchronize %.2f us\n",
+            h->ht_calls, h->ht_sum[0] / h->ht_calls * 1e-3, h->ht_sum[1] / h->ht_calls * 1e-3, h->ht_sum[2] / h->ht_calls * 1e-3);
   if (h->w_stem) cudaFree(h->w_stem);
   if (h->sb_w_stem) cudaFree(h->sb_w_stem);
   if (h->w_tower) cudaFree(h->w_tower);
@@ -1369,6 +1375,7 @@ int caz_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_tensor
     h->no_direct_output = getenv("CAZ_NO_DIRECT_OUTPUT") != nullptr;
     if (const char* e = getenv("CAZ_SB_DBG")) h->sb_dbg = atoi(e);
     if (getenv("CAZ_TOWER_ALL_LANES_FENCE")) h->tw_all_lanes_fence = true;
+    if (getenv("CAZ_HOST_TIMING")) h->host_timing = true;
     if (const char* e = getenv("CAZ_DBG_EPI")) h->dbg_epi = atoi(e);
   } else {
     const size_t s3 = (size_t)(8 + a.block_kernel - 1) * (8 + a.block_kernel - 1) * a.filters * 4;
@@ -1496,6 +1503,10 @@ static int eval_host(caz_handle* h, const float* planes, const uint8_t* records,
   const caz_arch& a = h->arch;
   const size_t pin = (size_t)a.input_planes * 64;
   if (batch <= h->max_batch) {
+    // CAZ_HOST_TIMING=1: where a synchronous call's host time goes (averages printed by caz_destroy)
+    const bool ht = h->host_timing;
+    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e9 + ts.tv_nsec; };
+    const double t_in = ht ? now() : 0.0;
     // One pass on one stream, no cross-stream events: the latency path.  (Cutting a batch into pipelined chunks was
     // measured: the smaller launches lose what the copy overlap gains; overlap ACROSS calls is caz_submit/caz_collect.)
     CU_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_out[0], 0));   // a still-draining caz_submit on slot 0
@@ -1516,12 +1527,18 @@ static int eval_host(caz_handle* h, const float* planes, const uint8_t* records,
       void* av = mapped_alias(value);
       if (ap && av) { dpol = static_cast<float*>(ap); dval = static_cast<float*>(av); direct = true; }
     }
+    const double t_pre = ht ? now() : 0.0;
     if ((rc = forward(h, planes ? h->d_planes : nullptr, planes ? nullptr : drec, batch, dpol, dval, masked ? h->d_mask : nullptr))) return rc;
+    const double t_launched = ht ? now() : 0.0;
     if (!direct) {
       CU_TRY(h, cudaMemcpyAsync(policy, h->d_policy, (size_t)batch * a.n_labels * 4, cudaMemcpyDeviceToHost, h->stream));
       CU_TRY(h, cudaMemcpyAsync(value, h->d_value, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
     }
     CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (ht) {
+      const double t_out = now();
+      h->ht_sum[0] += t_pre - t_in; h->ht_sum[1] += t_launched - t_pre; h->ht_sum[2] += t_out - t_launched; ++h->ht_calls;
+    }
     return CAZ_OK;
   }
   // larger than the device buffers: max_batch-sized chunks, alternating staging slots, copies under compute
