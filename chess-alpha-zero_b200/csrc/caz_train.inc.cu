@@ -63,6 +63,7 @@ struct caz_trainer {
   bool capturing = false;
   bool profiling = false;
   float* conv_stats = nullptr;   // tensor-core build: BatchNormalization partial sums written by the convolution epilogues
+  bool whole_tiles = false, no_mixed = false, wg_padded = false;   // CAZ_TRAIN_WHOLE_TILES / _NO_MIXED / _WG_PADDED (A/B switches, read at creation)
   bool mask_fp32 = false;   // CAZ_TRAIN_MASK_FP32: the backward passes read the ReLU mask from the fp32 activations
   bool no_tile = false;   // CAZ_TRAIN_NO_TILE: BatchNormalization passes and transposes as separate kernels (the fallback for odd shapes)
   std::vector<std::pair<const char*, cudaEvent_t>> prof;
@@ -318,10 +319,10 @@ int tr_conv_tc(caz_trainer* t, const CUtensorMap& tm_in, const CUtensorMap& tm_w
   const int full = pairs / maxp * maxp;   // groups that make full rounds of whole tiles
   const double c_whole = (pairs + maxp - 1) / maxp * t_whole, c_half = (2 * pairs + maxp - 1) / maxp * t_half,
                c_mixed = full / maxp * t_whole + (2 * (pairs - full) + maxp - 1) / maxp * t_half;
-  if (n % 64 == 0 && !getenv("CAZ_TRAIN_WHOLE_TILES") && (c_half < c_whole || c_mixed < c_whole)) {
+  if (n % 64 == 0 && !t->whole_tiles && (c_half < c_whole || c_mixed < c_whole)) {
     args.n_tiles = 2;
     args.n = n / 2;
-    args.mixed_whole = (c_mixed < c_half && !getenv("CAZ_TRAIN_NO_MIXED")) ? full : 0;
+    args.mixed_whole = (c_mixed < c_half && !t->no_mixed) ? full : 0;
     return tr_launch_tc(t, tm_in, tm_w_half, args, args.mixed_whole + 2 * (pairs - args.mixed_whole),
                         args.mixed_whole ? "conv_tc2_kernel (training, whole + half N tiles)" : "conv_tc2_kernel (training, two N tiles)", &tm_w);
   }
@@ -344,7 +345,7 @@ int tr_wgrad_tc(caz_trainer* t, const float* x, const float* dz, int batch, cons
     if ((dz || x) && (rc = tr_launch_ok(t, "transpose_pad_kernel"))) return rc;
   }
   // K over the real cells only (ConvArgs::wg_cpc): dz^T is zero on the halo cells
-  const bool compact = !getenv("CAZ_TRAIN_WG_PADDED");
+  const bool compact = !t->wg_padded;
   const int chunks = (compact ? 64 : cells) * t->nb / 64;
   int splits = (t->num_sms / 2) / taps;
   if (splits < 1) splits = 1;
@@ -724,6 +725,9 @@ int caz_train_create(const caz_arch* arch, const caz_tensor* tensors, int32_t n_
     TC2(tr_alloc(t, &t->aT, F * k3));
     if (!getenv("CAZ_TRAIN_NO_CONV_STATS")) TC2(tr_alloc(t, &t->conv_stats, (size_t)2 * F * ((boards + 1) / 2) * 4));
     if (getenv("CAZ_TRAIN_NO_TILE")) t->no_tile = true;
+    if (getenv("CAZ_TRAIN_WHOLE_TILES")) t->whole_tiles = true;
+    if (getenv("CAZ_TRAIN_NO_MIXED")) t->no_mixed = true;
+    if (getenv("CAZ_TRAIN_WG_PADDED")) t->wg_padded = true;
     if (getenv("CAZ_TRAIN_MASK_FP32")) t->mask_fp32 = true;
     for (size_t l = 0; l + 1 < t->convs.size() && !t->no_tile; ++l) {   // inputs of the tower's weight-gradient GEMMs
       TrainConv& L = t->convs[l];
