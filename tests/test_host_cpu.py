@@ -215,3 +215,33 @@ def test_pipe_server_delivers_failures_instead_of_hanging(transport):
     pipe.send(np.zeros((18, 8, 8), np.float32))
     assert pipe.poll(5.0)
     assert isinstance(pipe.recv(), RuntimeError)
+
+
+def test_pointer_cache_only_for_arrays_that_cannot_move():
+    """_lib.ptr remembers the data pointer of arrays that do not own their memory (pinned views), never of ones that do
+    (an owning array may be resized in place), and a dead array's id cannot alias a new one."""
+    import ctypes
+    from chess_alpha_zero_b200 import _lib
+    buf = (ctypes.c_uint8 * 64)()
+    view = np.frombuffer(buf, dtype=np.uint8)
+    p1, p2 = _lib.ptr(view), _lib.ptr(view)
+    assert p1 is p2 and p1.value == ctypes.addressof(buf)
+    own = np.zeros(16, np.float32)
+    q1, q2 = _lib.ptr(own), _lib.ptr(own)
+    assert q1 is not q2 and q1.value == q2.value == own.ctypes.data
+    key = id(view)
+    del view
+    other = np.frombuffer((ctypes.c_uint8 * 64)(), dtype=np.uint8)
+    assert _lib.ptr(other).value == other.ctypes.data          # whatever id it got, the weak reference check holds
+    assert _lib.ptr(None) is None and key is not None
+
+
+def test_tools_compile():
+    """Every measurement tool at least parses (they run on the GPU box only)."""
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "tools", "*.py"))) + [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    assert len(files) > 15
+    import ast
+    for f in files:
+        ast.parse(open(f).read(), filename=f)
