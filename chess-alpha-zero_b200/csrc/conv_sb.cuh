@@ -124,6 +124,16 @@ __host__ __device__ inline int taps_per_slot(int k, int ns) {
   return 1;
 }
 
+// ... for a layer in a ring whose slots were sized by ANOTHER layer (the stem's 5x5 filter rows do not fit where the tower's
+// 3x3 rows do): as many single taps as the slot holds, instead of one tap in a mostly empty slot -- with four 24 KB slots
+// holding 8 KB each, the 25 taps of the stem were a chain of 25 weight round trips (7.2 us at 48 boards, 2.6 us per tower layer)
+__host__ __device__ inline int taps_in_slot(int k, int ns, int slot_bytes) {
+  const int t = taps_per_slot(k, ns);
+  if (t > 1) return t;
+  const int fit = slot_bytes / (ns * 128);
+  return fit < 1 ? 1 : (fit > k * k ? k * k : fit);
+}
+
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
@@ -439,24 +449,25 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     for (int l = 0; l < args.n_layers; ++l) {
       const int k = l == 0 ? args.stem_k : args.blk_k;
       const int kch = l == 0 ? args.stem_kchunks : args.filters / 64;
-      const int tps = taps_per_slot(k, ns_cta);
+      const int tps = taps_in_slot(k, ns_cta, args.slot_bytes);
       const CUtensorMap* tm = l == 0 ? &tm_w_stem : &tm_w_tower;
       const int row = (l == 0 ? 0 : (l - 1) * args.filters) + col0 + static_cast<int>(rank) * ns_cta;
       for (int kc = 0; kc < kch; ++kc)
         for (int tap0 = 0; tap0 < k * k; tap0 += tps) {
           ptx::mbar_wait(&w_empty[slot], phase ^ 1, args.err_flag, ERR_W);
+          const int nt = min(tps, k * k - tap0);   // (a filter whose taps do not divide into slots: the last slot is short)
           if (ptx::elect_one()) {
             if constexpr (!PAIR) {
-              ptx::mbar_expect_tx(&w_full[slot], tps * tap_bytes);
-              for (int t = 0; t < tps; ++t)
+              ptx::mbar_expect_tx(&w_full[slot], nt * tap_bytes);
+              for (int t = 0; t < nt; ++t)
                 ptx::tma_load_2d(smem_w + slot * args.slot_bytes + t * tap_bytes, tm, &w_full[slot],
                                  ((tap0 + t) * kch + kc) * 64, row);
             } else {
               // both CTAs' halves of the slot count on the LEADER's barrier; each CTA waits for its own slot to be free
               // (the leader's tcgen05.commit arrives on w_empty in both CTAs)
-              if (leader) ptx::mbar_expect_tx(&w_full[slot], 2 * tps * tap_bytes);
+              if (leader) ptx::mbar_expect_tx(&w_full[slot], 2 * nt * tap_bytes);
               const uint32_t bar0 = ptx::mapa_u32(&w_full[slot], 0);
-              for (int t = 0; t < tps; ++t)
+              for (int t = 0; t < nt; ++t)
                 ptx::tma_load_2d_2cta(smem_w + slot * args.slot_bytes + t * tap_bytes, tm, bar0,
                                       ((tap0 + t) * kch + kc) * 64, row);
             }
@@ -554,7 +565,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
     for (int l = 0; l < args.n_layers; ++l) {
       const int k = l == 0 ? args.stem_k : args.blk_k;
       const int kch = l == 0 ? args.stem_kchunks : args.filters / 64;
-      const int tps = taps_per_slot(k, ns_cta);
+      const int tps = taps_in_slot(k, ns_cta, args.slot_bytes);
       const int hw = 8 + k - 1;
       const uint64_t plane_desc = static_cast<uint64_t>((hw * args.nb * hw * 128) >> 4);
       const uint64_t rp8 = static_cast<uint64_t>(args.nb * hw * 8);  // halo rows between consecutive ranks, x 128 B / 16
@@ -584,7 +595,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
                 else if (shape == 1) issue_taps<3, 3, false>(a_plane, b_slot, dy0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
                 else if (shape == 2) issue_taps<5, 5, false>(a_plane, b_slot, dy0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
                 else
-                  for (int t = 0, dy = dy0, dx = dx0; t < tps; ++t) {
+                  for (int t = 0, dy = dy0, dx = dx0; t < min(tps, k * k - tap0); ++t) {
                     issue_taps<1, 1, false>(a_plane, b_slot + static_cast<uint64_t>(t) * tap_desc, dy, dx, rp8, tap_desc, tm0, tm1,
                                             idesc, fresh && t == 0);
                     if (++dx == k) { dx = 0; ++dy; }
@@ -595,7 +606,7 @@ forward_sb_kernel(const __grid_constant__ CUtensorMap tm_xb,
                 else if (shape == 1) issue_taps<3, 3, true>(a_plane, b_slot, dy0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
                 else if (shape == 2) issue_taps<5, 5, true>(a_plane, b_slot, dy0, 0, rp8, tap_desc, tm0, tm1, idesc, fresh);
                 else
-                  for (int t = 0, dy = dy0, dx = dx0; t < tps; ++t) {
+                  for (int t = 0, dy = dy0, dx = dx0; t < min(tps, k * k - tap0); ++t) {
                     issue_taps<1, 1, true>(a_plane, b_slot + static_cast<uint64_t>(t) * tap_desc, dy, dx, rp8, tap_desc, tm0, tm1,
                                            idesc, fresh && t == 0);
                     if (++dx == k) { dx = 0; ++dy; }
